@@ -1,0 +1,144 @@
+/* qlidar.h -- C ABI of the B200-native (sm_100a) quantized sparse-3D-conv backbone path.
+ *
+ * The reference (BiboyQG/Quantization-on-3D-Object-Detection) has NO C/FFI boundary of its own for this path:
+ * it is Python that calls two third-party packages, spconv 2.x (pybind `core_cc`, not vendored) and
+ * pytorch_quantization.  Each entry point below therefore cites the reference *call site* whose work it
+ * replaces (paths relative to the reference root).  The Python mirror of the reference's module API
+ * (quantization-on-3d-object-detection_b200/qlidar) binds exactly these symbols through ctypes; the stub a
+ * maintainer would add on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *  - no allocation, no synchronisation, no global state: the caller owns all buffers and the stream;
+ *  - row counts live on the device (`n_dev`, int32) so a whole backbone forward is sync-free and can be
+ *    captured in a CUDA graph; `n_cap` is the host-known capacity used to size grids and buffers; a NULL
+ *    `n_dev` means "exactly n_cap rows";
+ *  - coords are int32 [b, z, y, x] rows; the linear key ((b*D+z)*H+y)*W+x must fit in 32 bits;
+ *  - return value: QL_OK or a negative QL_ERR_* code; nothing throws.
+ */
+#ifndef QLIDAR_H_
+#define QLIDAR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ql_stream_t; /* cudaStream_t */
+
+enum {
+    QL_OK = 0,
+    QL_ERR_INVALID = -1,        /* bad argument (null pointer, unsupported channel count, ...) */
+    QL_ERR_CUDA = -2,           /* a CUDA runtime call or launch failed; see ql_last_cuda_error() */
+    QL_ERR_GRID_TOO_LARGE = -3, /* B*D*H*W does not fit the 32-bit key */
+    QL_ERR_WORKSPACE = -4,      /* workspace too small */
+    QL_ERR_UNSUPPORTED = -5
+};
+
+enum { QL_F16 = 0, QL_F32 = 1, QL_S8 = 2, QL_S32 = 3 };
+
+/* quantize_rows modes */
+enum {
+    QL_Q_CODES_PER_TENSOR = 0, /* int8 codes, one scale for the tensor   (QConvNd cw=False, quant/quant.py:28-32) */
+    QL_Q_FAKE_PER_CHANNEL = 1, /* fp16 fake-quant, amax per input channel (QConvNd cw=True,  quant/quant.py:21-26) */
+    QL_Q_FAKE_PER_TENSOR = 2,  /* fp16 fake-quant, one amax */
+    QL_Q_FAKE_PER_ROW = 3      /* fp16 fake-quant, amax per voxel row     (GQConv3d, quant/quant_conv3d.py:112-131) */
+};
+
+int ql_abi_version(void);
+const char* ql_error_string(int code);
+const char* ql_last_cuda_error(void);
+int ql_num_sms_on_device(void);
+
+/* ---- coordinate hash (replaces [EXT] spconv's hash table behind SubMConv3d/SparseConv3d.forward,
+ *      call sites pcdet/models/backbones_3d/spconv_backbone.py:12-17; SPCONV_USE_DIRECT_TABLE=False,
+ *      pcdet/utils/spconv_utils.py:4-5).  Table = uint64 slots {key:32 | value:32}, capacity a power of two. */
+int64_t ql_hash_capacity(int64_t max_entries);
+int ql_hash_build(const int32_t* coords, int64_t n_cap, const int32_t* n_dev,
+                  int32_t B, int32_t D, int32_t H, int32_t W,
+                  uint64_t* table, int64_t table_cap, ql_stream_t stream);
+
+/* ---- voxelization + mean VFE (replaces VoxelGeneratorWrapper.generate -> [EXT] Point2VoxelCPU3d,
+ *      pcdet/datasets/processor/data_processor.py:45-61,151-153; collate_batch's batch column,
+ *      pcdet/datasets/dataset.py:237-244; MeanVFE.forward, pcdet/models/backbones_3d/vfe/mean_vfe.py:25-29;
+ *      with max_pts_per_voxel == 0: DynamicMeanVFE.forward, .../vfe/dynamic_mean_vfe.py:53-72).
+ *      points: [n_points, point_stride] fp32; column 0 is the batch index when has_batch_col != 0, then x,y,z,
+ *      then the remaining features (n_feat counts x,y,z).  Voxels are numbered in first-touch order over the
+ *      point array (== spconv's CPU voxelizer); a voxel keeps its first `max_pts_per_voxel` points; voxels
+ *      numbered >= max_voxels are dropped.  Outputs: out_feats [max_voxels, n_feat] fp32 (mean), out_coords
+ *      [max_voxels, 4] int32, out_npts [max_voxels] int32, *n_voxels_dev, and the hash table coords -> row. */
+size_t ql_voxelize_workspace_bytes(int64_t max_points, int64_t max_voxels, int32_t n_feat, int32_t max_pts_per_voxel);
+int ql_voxelize_mean(const float* points, int64_t n_points, int32_t point_stride, int32_t has_batch_col, int32_t n_feat,
+                     const float* range_min_xyz_host, const float* voxel_size_xyz_host, const int32_t* grid_xyz_host,
+                     int32_t batch_size, int32_t max_pts_per_voxel, int64_t max_voxels,
+                     float* out_feats, int32_t* out_coords, int32_t* out_npts, int32_t* n_voxels_dev,
+                     uint64_t* table, int64_t table_cap, void* workspace, size_t workspace_bytes, ql_stream_t stream);
+/* MeanVFE on an already voxelized (V,T,F) tensor (mean_vfe.py:25-29); num_points is float32 when
+ * num_points_is_float (pcdet/models/__init__.py:36 casts everything to float) else int32. */
+int ql_mean_vfe(const float* voxels, const void* num_points, int32_t num_points_is_float, int64_t V, int32_t T, int32_t F,
+                float* out_feats, ql_stream_t stream);
+
+/* ---- rulebook / indice pairs (replaces [EXT] spconv indice-pair generation inside
+ *      SubMConv3d/SparseConv3d.forward; keys at spconv_backbone.py:194-231).
+ *      Layout produced: nbr[tile][k][128] int32, tile = row/128: the input row feeding output row
+ *      tile*128+r through kernel offset k = (kz*KH+ky)*KW+kx, or -1.  ksize/stride/pad are zyx triples. */
+int64_t ql_rulebook_num_tiles(int64_t n_out_cap);
+int ql_rulebook_subm(const int32_t* coords, int64_t n_cap, const int32_t* n_dev,
+                     int32_t B, int32_t D, int32_t H, int32_t W, const int32_t* ksize_host,
+                     const uint64_t* table, int64_t table_cap, int32_t* nbr_out, ql_stream_t stream);
+size_t ql_rulebook_strided_workspace_bytes(int64_t n_in_cap, int32_t kvol);
+int ql_rulebook_strided(const int32_t* in_coords, int64_t n_in_cap, const int32_t* n_in_dev,
+                        int32_t B, int32_t D, int32_t H, int32_t W,
+                        const int32_t* ksize_host, const int32_t* stride_host, const int32_t* pad_host,
+                        const uint64_t* in_table, int64_t in_table_cap,
+                        int32_t* out_coords, int64_t n_out_cap, int32_t* n_out_dev,
+                        uint64_t* out_table, int64_t out_table_cap, int32_t* nbr_out,
+                        void* workspace, size_t workspace_bytes, ql_stream_t stream);
+
+/* ---- implicit gather-GEMM-scatter sparse conv on tcgen05 tensor cores (replaces QConvNd.forward ->
+ *      [EXT] spconv conv forward, quant/quant.py:36-58, plus the BatchNorm1d/ReLU/residual that follow it in
+ *      post_act_block / SparseBasicBlock, spconv_backbone.py:8-27,51-67).
+ *      feats: [n_in, c_in] fp16 (kind::f16, fp32 accumulate) or int8 codes (kind::i8, int32 accumulate).
+ *      w_packed: per-output-channel int8 codes (as fp16 exact integers for the f16 kind) in the shared-memory
+ *      image built by ql_pack_weights_host.  Epilogue: y = acc * (scale[oc] * (act_scale_dev ? *act_scale_dev : 1))
+ *      + shift[oc] (+ residual) ; optional ReLU; written as out_dtype (QL_F16/QL_F32) -- or the raw
+ *      accumulators when out_dtype == QL_S32 (int32 for the i8 kind, fp32 bits for the f16 kind).
+ *      Optional second output out_q = clamp(rint(y * out_qscale[oc]), -127, 127) int8 (static re-quantization
+ *      for the next layer) and absmax[oc] (atomic max of |y|, fp32, caller zero-initialises). */
+size_t ql_packed_weight_bytes(int32_t c_in, int32_t c_out, int32_t kvol, int32_t elem_dtype);
+int ql_pack_weights_host(const void* w_host, int32_t elem_dtype, int32_t c_in, int32_t c_out, int32_t kvol,
+                         void* packed_host);
+int ql_spconv_mma(const void* feats, int32_t in_dtype, const int32_t* nbr, int64_t n_out_cap, const int32_t* n_out_dev,
+                  int32_t c_in, int32_t c_out, int32_t kvol, const void* w_packed,
+                  const float* scale, const float* shift, const float* act_scale_dev,
+                  const void* residual_f16, int32_t relu,
+                  void* out, int32_t out_dtype, int8_t* out_q, const float* out_qscale, float* absmax,
+                  ql_stream_t stream);
+
+/* ---- fp32 SIMT stem conv for the un-quantized conv_input (C_in = 4/5 raw point features; quant_centerpoint.py
+ *      backbone_no_list = ['backbone_3d.conv_input.0'], :24-26).  w: [kvol][c_in][c_out] fp32. */
+int ql_stem_conv(const float* feats, int32_t c_in, const int32_t* nbr, int64_t n_out_cap, const int32_t* n_out_dev,
+                 int32_t c_out, int32_t kvol, const float* w, const float* scale, const float* shift, int32_t relu,
+                 void* out, int32_t out_dtype, float* absmax, ql_stream_t stream);
+
+/* ---- activation quantizer ([EXT] pytorch_quantization TensorQuantizer as configured at quant/quant.py:14-32).
+ *      absmax_cols: absmax[c] = max(absmax[c], max_rows |x[:,c]|).  quantize_rows: see QL_Q_* modes; `smooth`
+ *      (nullable, [c]) divides x first (SmoothQuant, quant/smoothquant.py:72-79); act_scale_out[0] receives the
+ *      de-quantization scale amax/bound for QL_Q_CODES_PER_TENSOR. */
+int ql_absmax_cols(const void* x, int32_t dtype, int64_t n_cap, const int32_t* n_dev, int32_t c, float* absmax,
+                   ql_stream_t stream);
+int ql_quantize_rows(const void* x, int32_t in_dtype, int64_t n_cap, const int32_t* n_dev, int32_t c,
+                     const float* absmax, const float* smooth, int32_t bits, int32_t mode,
+                     void* out, float* act_scale_out, ql_stream_t stream);
+
+/* ---- BEV hand-off (replaces HeightCompression.forward -> [EXT] SparseConvTensor.dense(),
+ *      pcdet/models/backbones_2d/map_to_bev/height_compression.py:20-24): out[b, c*D+d, y, x], zero filled. */
+int ql_bev_densify(const void* feats, int32_t in_dtype, int32_t c, const uint64_t* table, int64_t table_cap,
+                   int32_t B, int32_t D, int32_t H, int32_t W, void* out, int32_t out_dtype, ql_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QLIDAR_H_ */

@@ -1,0 +1,748 @@
+"""CPU ORACLE (test infrastructure, NOT product code) for the Q-LiDAR quantized sparse-3D-conv path.
+
+This file is a CPU restatement (numpy for the integer/index work, torch-CPU for the matmuls) of the
+algorithms on the reference's hot path.  Only `tests/`, `__graft_entry__.smoke()` and the
+`cpu_baseline` / `--impl reference` legs of `bench.py` may import it; the product package
+(`quantization-on-3d-object-detection_b200/qlidar`) never does.
+
+PARITY UNPINNED: the reference (BiboyQG/Quantization-on-3D-Object-Detection == OpenPCDet v0.6.0 + quant/)
+ships no tests, golden vectors or fixtures for this path, and the arithmetic lives in two
+un-vendored, un-pinned third-party packages that are not installed in this image:
+  * spconv 2.x (traveller59/spconv; `pip install spconv-cu116`, unversioned: docker/cu116.Dockerfile:66;
+    observed 2.x with ConvAlgo.MaskImplicitGemm: tools/demo.ipynb:255)
+  * pytorch_quantization (NVIDIA TensorRT repo; imported at quant/quant.py:1-2, listed nowhere)
+Their *published* algorithms are restated here and anchored on the reference's own call sites (cited per
+function as `file:line` relative to /root/reference).  The oracle earns trust by independent cross-checks in
+tests/test_oracle_*.py: sparse conv vs dense torch.nn.functional.conv3d, int32 path vs float64, and
+property tests (permutation invariance, subm preserves the active set, strided out-set = dilate o subsample).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# ----------------------------------------------------------------------------------------------
+# Configs (constants only; tools/cfgs/dataset_configs/{kitti,waymo}_dataset.yaml,
+# tools/cfgs/nuscenes_models/cbgs_voxel0075_res3d_centerpoint.yaml -- SURVEY.md §8 table)
+# ----------------------------------------------------------------------------------------------
+CONFIGS = {
+    # name: (point_cloud_range xyzxyz, voxel_size xyz, num point features, max pts/voxel, max voxels @test)
+    "kitti": dict(pc_range=[0.0, -40.0, -3.0, 70.4, 40.0, 1.0], voxel_size=[0.05, 0.05, 0.1], nfeat=4,
+                  max_pts=5, max_voxels=40000),        # kitti_dataset.yaml:4,50,65-70
+    "waymo": dict(pc_range=[-75.2, -75.2, -2.0, 75.2, 75.2, 4.0], voxel_size=[0.1, 0.1, 0.15], nfeat=5,
+                  max_pts=5, max_voxels=150000),       # waymo_dataset.yaml:5,63,79-84
+    "nuscenes": dict(pc_range=[-54.0, -54.0, -5.0, 54.0, 54.0, 3.0], voxel_size=[0.075, 0.075, 0.2], nfeat=5,
+                     max_pts=10, max_voxels=160000),   # cbgs_voxel0075_res3d_centerpoint.yaml:6,55-60
+}
+
+
+def grid_size_xyz(pc_range, voxel_size) -> np.ndarray:
+    """pcdet/datasets/processor/data_processor.py:135-137: round((max-min)/voxel) as int64, xyz order."""
+    r = np.asarray(pc_range, dtype=np.float64)
+    g = (r[3:6] - r[0:3]) / np.asarray(voxel_size, dtype=np.float64)
+    return np.round(g).astype(np.int64)
+
+
+def sparse_shape_zyx(grid_xyz) -> List[int]:
+    """pcdet/models/backbones_3d/spconv_backbone.py:191: sparse_shape = grid_size[::-1] + [1, 0, 0]."""
+    g = [int(v) for v in grid_xyz]
+    return [g[2] + 1, g[1], g[0]]
+
+
+# ----------------------------------------------------------------------------------------------
+# a1 / a4 / a4'  Voxelization + mean VFE
+# ----------------------------------------------------------------------------------------------
+def point_to_cell(points_xyz: np.ndarray, pc_range, voxel_size, grid_xyz):
+    """fp32 floor((p - min) / vs) per axis, in-grid mask with exclusive upper bound.
+
+    Follows pcdet/models/backbones_3d/vfe/dynamic_mean_vfe.py:53-54 (torch fp32 floor + `< grid_size`)
+    and [EXT] spconv Point2VoxelCPU3d (same fp32 expression, out-of-range points skipped).
+    """
+    p = np.asarray(points_xyz, dtype=np.float32)
+    mn = np.asarray(pc_range[:3], dtype=np.float32)
+    vs = np.asarray(voxel_size, dtype=np.float32)
+    c = np.floor((p - mn) / vs)                       # fp32 arithmetic (numpy keeps float32)
+    g = np.asarray(grid_xyz, dtype=np.float32)
+    mask = np.all((c >= 0) & (c < g), axis=1)
+    return c.astype(np.int32), mask
+
+
+def voxelize_hard(points: np.ndarray, pc_range, voxel_size, max_pts: int, max_voxels: int):
+    """Hard voxelization of ONE frame, first-touch order, caps applied in point order.
+
+    Restates [EXT] spconv.utils.Point2VoxelCPU3d.point_to_voxel as called from
+    pcdet/datasets/processor/data_processor.py:45-61,151-153: points outside the grid are skipped; a new
+    voxel is opened for the first point that lands in an empty cell unless `max_voxels` voxels already
+    exist (then that point is dropped, later points may still join existing voxels); a voxel keeps its
+    first `max_pts` points.  Returns (voxels (V,T,F) zero padded, coords (V,3) zyx int32, num_points (V,) int32).
+    """
+    points = np.ascontiguousarray(points, dtype=np.float32)
+    grid = grid_size_xyz(pc_range, voxel_size)
+    cell, mask = point_to_cell(points[:, :3], pc_range, voxel_size, grid)
+    idx = np.nonzero(mask)[0]
+    cell = cell[idx].astype(np.int64)
+    key = (cell[:, 2] * grid[1] + cell[:, 1]) * grid[0] + cell[:, 0]      # z,y,x linearisation
+    uniq, first, inv = np.unique(key, return_index=True, return_inverse=True)
+    order = np.argsort(first, kind="stable")          # voxels in first-touch order
+    rank = np.empty_like(order)
+    rank[order] = np.arange(order.size)
+    vid = rank[inv]                                   # voxel id per (in-range) point
+    keep_v = vid < max_voxels
+    V = int(min(order.size, max_voxels))
+    # position of each point inside its voxel, in point order
+    srt = np.argsort(vid, kind="stable")
+    vs_sorted = vid[srt]
+    start = np.searchsorted(vs_sorted, np.arange(order.size))
+    pos = np.empty(idx.size, dtype=np.int64)
+    pos[srt] = np.arange(idx.size) - start[vs_sorted]
+    keep = keep_v & (pos < max_pts)
+    F_ = points.shape[1]
+    voxels = np.zeros((V, max_pts, F_), dtype=np.float32)
+    voxels[vid[keep], pos[keep]] = points[idx[keep]]
+    num = np.zeros(V, dtype=np.int32)
+    np.add.at(num, vid[keep], 1)
+    kz = uniq[order][:V]
+    coords = np.stack([kz // (grid[1] * grid[0]), (kz // grid[0]) % grid[1], kz % grid[0]], axis=1).astype(np.int32)
+    return voxels, coords, num
+
+
+def mean_vfe(voxels: np.ndarray, num_points: np.ndarray) -> np.ndarray:
+    """pcdet/models/backbones_3d/vfe/mean_vfe.py:25-29: sum over T / clamp_min(num_points, 1)."""
+    s = torch.from_numpy(voxels).sum(dim=1)
+    n = torch.clamp_min(torch.from_numpy(num_points).view(-1, 1).float(), 1.0)
+    return (s / n).numpy()
+
+
+def collate_voxels(per_frame):
+    """pcdet/datasets/dataset.py:232-244: concat voxels/num_points, prepend batch index to coords."""
+    feats, coords, nums = [], [], []
+    for b, (v, c, n) in enumerate(per_frame):
+        feats.append(v)
+        nums.append(n)
+        coords.append(np.concatenate([np.full((c.shape[0], 1), b, dtype=np.int32), c], axis=1))
+    return np.concatenate(feats), np.concatenate(coords), np.concatenate(nums)
+
+
+def voxelize_mean_batch(points_b: np.ndarray, pc_range, voxel_size, max_pts: int, max_voxels: int):
+    """Fused a1+a2+a4 on a collated `points (sum P, 1+F)` array (batch index in column 0, frames
+    contiguous): per-frame hard voxelization, mean VFE, `[b,z,y,x]` coords.  `max_voxels` is per frame.
+    This is the semantics of the GPU op `ql_voxelize_mean` (first-touch order over the whole array)."""
+    out = []
+    bidx = points_b[:, 0].astype(np.int64)
+    B = int(bidx.max()) + 1 if points_b.shape[0] else 0
+    for b in range(B):
+        out.append(voxelize_hard(points_b[bidx == b, 1:], pc_range, voxel_size, max_pts, max_voxels))
+    voxels, coords, nums = collate_voxels(out)
+    return mean_vfe(voxels, nums), coords, nums
+
+
+def voxelize_dynamic_mean(points_b: np.ndarray, pc_range, voxel_size):
+    """pcdet/models/backbones_3d/vfe/dynamic_mean_vfe.py:53-72: no caps, mean over all points of a voxel,
+    output sorted by key b*XYZ + x*YZ + y*Z + z, coords as [b,z,y,x]."""
+    grid = grid_size_xyz(pc_range, voxel_size)
+    cell, mask = point_to_cell(points_b[:, 1:4], pc_range, voxel_size, grid)
+    pts = points_b[mask]
+    cell = cell[mask].astype(np.int64)
+    sxyz, syz, sz = grid[0] * grid[1] * grid[2], grid[1] * grid[2], grid[2]
+    key = pts[:, 0].astype(np.int64) * sxyz + cell[:, 0] * syz + cell[:, 1] * sz + cell[:, 2]
+    uniq, inv, cnt = np.unique(key, return_inverse=True, return_counts=True)
+    sums = np.zeros((uniq.size, pts.shape[1] - 1), dtype=np.float64)
+    np.add.at(sums, inv, pts[:, 1:].astype(np.float64))
+    mean = (sums / cnt[:, None]).astype(np.float32)
+    coords = np.stack([uniq // sxyz, uniq % sz, (uniq % syz) // sz, (uniq % sxyz) // syz], axis=1).astype(np.int32)
+    return mean, coords, cnt.astype(np.int32)
+
+
+# ----------------------------------------------------------------------------------------------
+# a7  Rulebook (indice pairs)
+# ----------------------------------------------------------------------------------------------
+def _triple(v) -> Tuple[int, int, int]:
+    if isinstance(v, (int, np.integer)):
+        return (int(v),) * 3
+    v = tuple(int(x) for x in v)
+    assert len(v) == 3
+    return v
+
+
+def conv_out_shape(in_shape, ksize, stride, pad) -> List[int]:
+    """[EXT] spconv output-shape rule per dim: (in + 2*pad - k)//stride + 1 (dilation 1); consistent with
+    the shape comments at spconv_backbone.py:206,213,220,229."""
+    k, s, p = _triple(ksize), _triple(stride), _triple(pad)
+    return [(int(in_shape[d]) + 2 * p[d] - k[d]) // s[d] + 1 for d in range(3)]
+
+
+def _lin(coords: np.ndarray, shape) -> np.ndarray:
+    c = coords.astype(np.int64)
+    return ((c[:, 0] * shape[0] + c[:, 1]) * shape[1] + c[:, 2]) * shape[2] + c[:, 3]
+
+
+def _lookup(sorted_keys, sorted_idx, q):
+    pos = np.searchsorted(sorted_keys, q)
+    pos_c = np.minimum(pos, sorted_keys.size - 1)
+    hit = sorted_keys[pos_c] == q
+    return np.where(hit, sorted_idx[pos_c], -1)
+
+
+def kernel_offsets(ksize) -> np.ndarray:
+    """Offsets enumerated as k = (kz*KH + ky)*KW + kx, the order of the weight tensor
+    (C_out, kd, kh, kw, C_in) (spconv-2 layout, quant/quant.py:37-39, detector3d_template.py:346)."""
+    k = _triple(ksize)
+    kz, ky, kx = np.meshgrid(np.arange(k[0]), np.arange(k[1]), np.arange(k[2]), indexing="ij")
+    return np.stack([kz.ravel(), ky.ravel(), kx.ravel()], axis=1).astype(np.int64)
+
+
+def rulebook_subm(coords: np.ndarray, spatial_shape, ksize) -> np.ndarray:
+    """Submanifold rulebook ([EXT] spconv SubMConv: stride 1, pad = k//2, outputs == inputs, same order).
+    Returns nbr (K, N) int32: nbr[k, o] = input row at coord(o) + offset_k - k//2, or -1.
+    Cross-correlation orientation (== nn.Conv3d with W.permute(0,4,1,2,3)); pinned by the dense cross-check."""
+    N = coords.shape[0]
+    k = _triple(ksize)
+    offs = kernel_offsets(k)
+    nbr = np.full((offs.shape[0], N), -1, dtype=np.int32)
+    if N == 0:
+        return nbr
+    keys = _lin(coords, spatial_shape)
+    order = np.argsort(keys, kind="stable")
+    sk, si = keys[order], order.astype(np.int64)
+    c = coords.astype(np.int64)
+    shp = np.asarray(spatial_shape, dtype=np.int64)
+    for ki, (dz, dy, dx) in enumerate(offs):
+        q = c.copy()
+        q[:, 1] += dz - k[0] // 2
+        q[:, 2] += dy - k[1] // 2
+        q[:, 3] += dx - k[2] // 2
+        ok = np.all((q[:, 1:] >= 0) & (q[:, 1:] < shp), axis=1)
+        res = _lookup(sk, si, _lin(q, spatial_shape))
+        nbr[ki] = np.where(ok, res, -1)
+    return nbr
+
+
+def rulebook_strided(coords: np.ndarray, spatial_shape, ksize, stride, pad):
+    """Regular (strided) sparse conv rulebook ([EXT] spconv SparseConv3d): an output site is active iff its
+    window contains >= 1 active input.  Output ORDER is implementation-defined in spconv; this framework
+    fixes it to first-touch order over the enumeration (input row i, offset k) -> sequence i*K + k.
+    Returns (out_coords (M,4) int32, out_shape, nbr (K, M) int32) with nbr[k,o] = row of input at
+    o*stride - pad + offset_k."""
+    k, s, p = _triple(ksize), _triple(stride), _triple(pad)
+    out_shape = conv_out_shape(spatial_shape, k, s, p)
+    offs = kernel_offsets(k)
+    K = offs.shape[0]
+    N = coords.shape[0]
+    c = coords.astype(np.int64)
+    osh = np.asarray(out_shape, dtype=np.int64)
+    cand_keys, cand_seq = [], []
+    for ki, off in enumerate(offs):
+        num = c[:, 1:] + np.asarray(p) - off
+        o = num // np.asarray(s)
+        ok = np.all((num % np.asarray(s) == 0) & (o >= 0) & (o < osh), axis=1)
+        oc = np.concatenate([c[ok, :1], o[ok]], axis=1)
+        cand_keys.append(_lin(oc, out_shape))
+        cand_seq.append(np.nonzero(ok)[0].astype(np.int64) * K + ki)
+    cand_keys = np.concatenate(cand_keys) if N else np.zeros(0, np.int64)
+    cand_seq = np.concatenate(cand_seq) if N else np.zeros(0, np.int64)
+    srt = np.argsort(cand_seq, kind="stable")
+    cand_keys, cand_seq = cand_keys[srt], cand_seq[srt]
+    uniq, first = np.unique(cand_keys, return_index=True)
+    order = np.argsort(first, kind="stable")
+    okeys = uniq[order]
+    M = okeys.size
+    W_, H_, D_ = out_shape[2], out_shape[1], out_shape[0]
+    out_coords = np.stack([okeys // (D_ * H_ * W_), (okeys // (H_ * W_)) % D_, (okeys // W_) % H_, okeys % W_],
+                          axis=1).astype(np.int32)
+    nbr = np.full((K, M), -1, dtype=np.int32)
+    if N and M:
+        ikeys = _lin(coords, spatial_shape)
+        iorder = np.argsort(ikeys, kind="stable")
+        sk, si = ikeys[iorder], iorder.astype(np.int64)
+        ish = np.asarray(spatial_shape, dtype=np.int64)
+        oc64 = out_coords.astype(np.int64)
+        for ki, off in enumerate(offs):
+            q = oc64.copy()
+            q[:, 1:] = oc64[:, 1:] * np.asarray(s) - np.asarray(p) + off
+            ok = np.all((q[:, 1:] >= 0) & (q[:, 1:] < ish), axis=1)
+            res = _lookup(sk, si, _lin(np.where(ok[:, None], q, 0), spatial_shape))
+            nbr[ki] = np.where(ok, res, -1)
+    return out_coords, out_shape, nbr
+
+
+def pairs_in_coord_space(nbr: np.ndarray, in_coords: np.ndarray, out_coords: np.ndarray) -> np.ndarray:
+    """(k, in_coord, out_coord) rows sorted lexicographically -- the order-free form in which indice pairs
+    are compared (SURVEY.md §8d parity gates)."""
+    k, o = np.nonzero(nbr >= 0)
+    i = nbr[k, o]
+    rows = np.concatenate([k[:, None].astype(np.int64), in_coords[i].astype(np.int64), out_coords[o].astype(np.int64)], axis=1)
+    if rows.shape[0] == 0:
+        return rows
+    return rows[np.lexsort(rows.T[::-1])]
+
+
+# ----------------------------------------------------------------------------------------------
+# a9 / §8a-Q  TensorQuantizer ([EXT] pytorch_quantization) semantics
+# ----------------------------------------------------------------------------------------------
+def quant_bound(bits: int) -> float:
+    return float(2 ** (bits - 1) - 1)                 # narrow_range symmetric: 127 / 32767
+
+
+def dynamic_amax(t: torch.Tensor, axis=None) -> torch.Tensor:
+    """max|t| over every dim NOT in `axis`, keepdim ([EXT] TensorQuantizer dynamic amax; descriptors built at
+    quant/quant.py:14-32: weights axis=(0) on (oc, ic*K); activations axis=(1) if cw else None)."""
+    a = t.detach().abs()
+    if axis is None:
+        return a.max() if a.numel() else a.new_zeros(())
+    axes = (axis,) if isinstance(axis, int) else tuple(axis)
+    red = [d for d in range(t.dim()) if d not in axes]
+    return a.amax(dim=red, keepdim=True) if red else a
+
+
+def quant_scale(amax: torch.Tensor, bits: int) -> torch.Tensor:
+    """scale = bound / amax, with amax <= 2^-24 -> scale 0 ([EXT] fake_tensor_quant epsilon rule)."""
+    bound = quant_bound(bits)
+    amax = amax.to(torch.float32)
+    tiny = amax <= (1.0 / (1 << 24))
+    return torch.where(tiny, torch.zeros_like(amax), bound / torch.where(tiny, torch.ones_like(amax), amax))
+
+
+def quantize_codes(t: torch.Tensor, amax: torch.Tensor, bits: int) -> torch.Tensor:
+    """q = clamp(round_half_even(t * scale), -bound, +bound) as int32 (torch.round == rint)."""
+    bound = quant_bound(bits)
+    q = torch.round(t.to(torch.float32) * quant_scale(amax, bits)).clamp_(-bound, bound)
+    return q.to(torch.int32)
+
+
+def fake_quant(t: torch.Tensor, bits: int, axis=None, amax: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """t_fq = q / scale (scale==0 -> 0): quantize -> round -> clamp -> DEquantize, still fp32.  This is what
+    every reference wrapper feeds to the unmodified fp32 spconv layer (quant/quant.py:44,51)."""
+    if amax is None:
+        amax = dynamic_amax(t, axis)
+    sc = quant_scale(amax, bits)
+    q = quantize_codes(t, amax, bits).to(torch.float32)
+    return torch.where(sc == 0, torch.zeros_like(q), q / torch.where(sc == 0, torch.ones_like(sc), sc))
+
+
+def weight_matrix(weight: torch.Tensor) -> torch.Tensor:
+    """(oc, kd, kh, kw, ic) -> (oc, ic*K) exactly as quant/quant.py:37-43 (permute(0,4,1,2,3).view(oc,-1))."""
+    oc = weight.shape[0]
+    dim = weight.dim()
+    return weight.permute([0, dim - 1] + list(range(1, dim - 1))).contiguous().view(oc, -1)
+
+
+def weight_from_matrix(wm: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    """Inverse of weight_matrix (quant/quant.py:45-48)."""
+    oc, ic = like.shape[0], like.shape[-1]
+    kdim = tuple(like.shape[1:-1])
+    dim = like.dim()
+    return wm.view((oc, ic) + kdim).permute([0] + list(range(2, dim)) + [1]).contiguous()
+
+
+def quantize_weight_per_oc(weight: torch.Tensor, bits: int = 8):
+    """Per-output-channel weight codes + amax (QuantDescriptor(num_bits=w_bits, axis=(0)), quant/quant.py:14-18)."""
+    wm = weight_matrix(weight)
+    amax = dynamic_amax(wm, axis=0)                   # (oc,1)
+    q = quantize_codes(wm, amax, bits)
+    return weight_from_matrix(q, weight), amax.view(-1)
+
+
+# ----------------------------------------------------------------------------------------------
+# a8  Sparse convolution (spconv "Native" algorithm: per-offset gather -> GEMM -> scatter-add)
+# ----------------------------------------------------------------------------------------------
+def sparse_conv(features: torch.Tensor, nbr: np.ndarray, weight: torch.Tensor,
+                bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[o,:] = sum_k W[:,k,:] @ x[nbr[k,o],:] (+bias); weight (oc, kd,kh,kw, ic).  fp32 (or fp64)."""
+    oc, ic = weight.shape[0], weight.shape[-1]
+    K = nbr.shape[0]
+    M = nbr.shape[1]
+    w = weight.reshape(oc, K, ic)
+    out = torch.zeros((M, oc), dtype=features.dtype)
+    nbr_t = torch.from_numpy(nbr.astype(np.int64))
+    for k in range(K):
+        o = torch.nonzero(nbr_t[k] >= 0).squeeze(1)
+        if o.numel() == 0:
+            continue
+        g = features.index_select(0, nbr_t[k][o])
+        out.index_add_(0, o, g @ w[:, k, :].to(features.dtype).t())
+    if bias is not None:
+        out += bias.to(out.dtype)
+    return out
+
+
+def sparse_conv_int(qx: torch.Tensor, nbr: np.ndarray, qw: torch.Tensor) -> torch.Tensor:
+    """INT8 x INT8 -> INT32 accumulators, exact (int64 matmul on CPU, result fits int32)."""
+    oc, ic = qw.shape[0], qw.shape[-1]
+    K, M = nbr.shape
+    w = qw.reshape(oc, K, ic).to(torch.int64)
+    out = torch.zeros((M, oc), dtype=torch.int64)
+    nbr_t = torch.from_numpy(nbr.astype(np.int64))
+    x64 = qx.to(torch.int64)
+    for k in range(K):
+        o = torch.nonzero(nbr_t[k] >= 0).squeeze(1)
+        if o.numel() == 0:
+            continue
+        g = x64.index_select(0, nbr_t[k][o])
+        out.index_add_(0, o, g @ w[:, k, :].t())
+    assert out.abs().max() < 2 ** 31 if out.numel() else True
+    return out.to(torch.int32)
+
+
+def bn_fold(gamma, beta, mean, var, eps):
+    """Eval-mode BatchNorm1d as y = a*x + b (spconv_backbone.py:189 eps=1e-3; read eps from the module)."""
+    a = gamma / torch.sqrt(var + eps)
+    return a, beta - a * mean
+
+
+# ----------------------------------------------------------------------------------------------
+# Quantized conv modes
+# ----------------------------------------------------------------------------------------------
+def qconv_reference_math(features, nbr, weight, bias, w_bits, act_bits, cw, act_amax=None):
+    """QConvNd.forward exactly (quant/quant.py:36-58): fake-quant(w) per oc, fake-quant(x) per tensor
+    (cw=False) or per input channel (cw=True, axis=1), fp32 sparse conv, +bias."""
+    wq = weight_from_matrix(fake_quant(weight_matrix(weight), w_bits, axis=0), weight)
+    xq = fake_quant(features, act_bits, axis=1 if cw else None, amax=act_amax)
+    return sparse_conv(xq, nbr, wq, bias)
+
+
+def qconv_w8a8_pt(features, nbr, weight, bias, act_amax=None):
+    """W8A8 per-tensor: int8 codes, INT32 accumulate, dequant with (amax_x/127)*(amax_w[oc]/127).
+    Returns (acc int32, y fp32, amax_x, amax_w)."""
+    qw, amax_w = quantize_weight_per_oc(weight, 8)
+    amax_x = dynamic_amax(features) if act_amax is None else act_amax
+    qx = quantize_codes(features, amax_x, 8)
+    acc = sparse_conv_int(qx, nbr, qw)
+    y = acc.to(torch.float32) * ((amax_x.to(torch.float32) / 127.0) * (amax_w / 127.0)).view(1, -1)
+    if bias is not None:
+        y = y + bias
+    return acc, y, amax_x, amax_w
+
+
+def smoothquant_scale(act_amax_ic: torch.Tensor, weight: torch.Tensor, alpha: float) -> torch.Tensor:
+    """s[ic] = amax_x[ic]^alpha / amax_w[ic]^(1-alpha), zeros -> 1 (quant/smoothquant.py:69-76 formula,
+    per input channel: in a dense unfold every voxel appears at every kernel position)."""
+    w_ic = weight.abs().amax(dim=tuple(range(weight.dim() - 1)))           # max over oc,k
+    s = act_amax_ic.view(-1) ** alpha / w_ic ** (1.0 - alpha)
+    s = torch.where((s == 0) | ~torch.isfinite(s), torch.ones_like(s), s)
+    return s
+
+
+def qconv_w8a8_sq(features, nbr, weight, bias, alpha=0.5):
+    """SmoothQuant: x' = x/s, w' = w*s, then W8A8 per-tensor on (x', w')."""
+    s = smoothquant_scale(dynamic_amax(features, axis=1), weight, alpha)
+    return qconv_w8a8_pt(features / s.view(1, -1), nbr, weight * s.view(*([1] * (weight.dim() - 1)), -1), bias)
+
+
+# ----------------------------------------------------------------------------------------------
+# a12  dense() / HeightCompression
+# ----------------------------------------------------------------------------------------------
+def to_dense(features: torch.Tensor, coords: np.ndarray, spatial_shape, batch_size: int) -> torch.Tensor:
+    """[EXT] SparseConvTensor.dense(): scatter rows into zeros (B, D,H,W, C) -> (B, C, D,H,W)."""
+    D, H, W = [int(v) for v in spatial_shape]
+    C = features.shape[1]
+    out = torch.zeros((batch_size, D, H, W, C), dtype=features.dtype)
+    c = torch.from_numpy(coords.astype(np.int64))
+    out[c[:, 0], c[:, 1], c[:, 2], c[:, 3]] = features
+    return out.permute(0, 4, 1, 2, 3).contiguous()
+
+
+def height_compression(features, coords, spatial_shape, batch_size):
+    """pcdet/models/backbones_2d/map_to_bev/height_compression.py:20-24: dense().view(N, C*D, H, W)."""
+    d = to_dense(features, coords, spatial_shape, batch_size)
+    N, C, D, H, W = d.shape
+    return d.view(N, C * D, H, W)
+
+
+def bev_merge2d(features: torch.Tensor, coords: np.ndarray):
+    """VoxelResBackBone8xVoxelNeXt.bev_out (spconv_backbone_voxelnext.py:149-164): drop z, torch.unique(dim=0)
+    (lexicographically sorted [b,y,x]) and index_add_ duplicates."""
+    ind = torch.from_numpy(coords[:, [0, 2, 3]].astype(np.int64))
+    uniq, inv = torch.unique(ind, dim=0, return_inverse=True)
+    out = features.new_zeros((uniq.shape[0], features.shape[1]))
+    out.index_add_(0, inv, features)
+    return out, uniq.numpy().astype(np.int32)
+
+
+# ----------------------------------------------------------------------------------------------
+# Sparse tensor + network restatement (a5, a6, a13)
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class SpT:
+    features: torch.Tensor
+    coords: np.ndarray                      # (N,4) int32 [b,z,y,x]
+    spatial_shape: List[int]
+    batch_size: int
+    rulebooks: Dict[str, tuple] = field(default_factory=dict)
+
+    def replace(self, f):
+        return SpT(f, self.coords, self.spatial_shape, self.batch_size, self.rulebooks)
+
+
+@dataclass
+class ConvSpec:
+    name: str
+    cin: int
+    cout: int
+    ksize: Tuple[int, int, int]
+    stride: Tuple[int, int, int]
+    pad: Tuple[int, int, int]
+    subm: bool
+    key: str
+    bias: bool
+    bn_eps: float = 1e-3
+
+
+@dataclass
+class QuantCfg:
+    """mode: 'fp32' | 'ref' (reference fake-quant math, QConvNd) | 'w8a8_pt' | 'w8a8_sq' ;
+    w_bits/act_bits/cw as in quant/quant.py:8; no_list = dotted conv names left un-quantized
+    (quant/quant_centerpoint.py:24-26)."""
+    mode: str = "fp32"
+    w_bits: int = 8
+    act_bits: int = 8
+    cw: bool = False
+    alpha: float = 0.5
+    no_list: Tuple[str, ...] = ()
+
+
+def run_conv(x: SpT, spec: ConvSpec, params: Dict[str, torch.Tensor], q: QuantCfg, record=None) -> SpT:
+    """One (optionally quantized) sparse conv incl. rulebook caching per indice_key ([EXT] spconv indice_dict)."""
+    if spec.key in x.rulebooks:
+        out_coords, out_shape, nbr = x.rulebooks[spec.key]
+    else:
+        if spec.subm:
+            out_coords, out_shape, nbr = x.coords, x.spatial_shape, rulebook_subm(x.coords, x.spatial_shape, spec.ksize)
+        else:
+            out_coords, out_shape, nbr = rulebook_strided(x.coords, x.spatial_shape, spec.ksize, spec.stride, spec.pad)
+        x.rulebooks[spec.key] = (out_coords, out_shape, nbr)
+    w = params[spec.name + ".weight"]
+    b = params.get(spec.name + ".bias") if spec.bias else None
+    mode = "fp32" if spec.name in q.no_list else q.mode
+    if mode == "fp32":
+        y = sparse_conv(x.features, nbr, w, b)
+    elif mode == "ref":
+        y = qconv_reference_math(x.features, nbr, w, b, q.w_bits, q.act_bits, q.cw)
+    elif mode == "w8a8_pt":
+        acc, y, _, _ = qconv_w8a8_pt(x.features, nbr, w, b)
+        if record is not None:
+            record[spec.name + ".acc"] = acc
+    elif mode == "w8a8_sq":
+        acc, y, _, _ = qconv_w8a8_sq(x.features, nbr, w, b, q.alpha)
+    else:
+        raise ValueError(mode)
+    out = SpT(y, out_coords, list(out_shape), x.batch_size, x.rulebooks if spec.subm else {})
+    if record is not None:
+        record[spec.name] = y
+    return out
+
+
+def bn_relu(x: SpT, name: str, params, eps: float, relu=True, residual: Optional[torch.Tensor] = None) -> SpT:
+    a, b = bn_fold(params[name + ".weight"], params[name + ".bias"], params[name + ".running_mean"],
+                   params[name + ".running_var"], eps)
+    y = x.features * a + b
+    if residual is not None:
+        y = y + residual
+    if relu:
+        y = torch.relu(y)
+    return x.replace(y)
+
+
+def backbone_specs(arch: str, input_channels: int, channels=None, kernel_sizes=None, out_channel=None) -> List[dict]:
+    """Layer list of VoxelBackBone8x (spconv_backbone.py:78-118), VoxelResBackBone8x (:193-234) and
+    VoxelResBackBone8xVoxelNeXt (spconv_backbone_voxelnext.py:81-138) as a flat program of ops."""
+    prog: List[dict] = []
+
+    def conv(name, cin, cout, k, s, p, subm, key, bias):
+        return ConvSpec(name, cin, cout, _triple(k), _triple(s), _triple(p), subm, key, bias)
+
+    def post_act(prefix, cin, cout, k, s, p, subm, key):
+        prog.append(dict(op="conv_bn_relu", conv=conv(prefix + ".0", cin, cout, k, s, p, subm, key, False), bn=prefix + ".1"))
+
+    def basic(prefix, c, key, bias=True):
+        prog.append(dict(op="basic_block", conv1=conv(prefix + ".conv1", c, c, 3, 1, 1, True, key, bias), bn1=prefix + ".bn1",
+                         conv2=conv(prefix + ".conv2", c, c, 3, 1, 1, True, key, bias), bn2=prefix + ".bn2"))
+
+    if arch == "VoxelBackBone8x":
+        post_act("conv_input", input_channels, 16, 3, 1, 1, True, "subm1")
+        post_act("conv1.0", 16, 16, 3, 1, 1, True, "subm1")
+        prog.append(dict(op="tap", name="x_conv1"))
+        for si, (ci, co, pad) in enumerate([(16, 32, 1), (32, 64, 1), (64, 64, (0, 1, 1))], start=2):
+            post_act(f"conv{si}.0", ci, co, 3, 2, pad, False, f"spconv{si}")
+            post_act(f"conv{si}.1", co, co, 3, 1, 1, True, f"subm{si}")
+            post_act(f"conv{si}.2", co, co, 3, 1, 1, True, f"subm{si}")
+            prog.append(dict(op="tap", name=f"x_conv{si}"))
+        post_act("conv_out", 64, 128, (3, 1, 1), (2, 1, 1), 0, False, "spconv_down2")
+    elif arch == "VoxelResBackBone8x":
+        post_act("conv_input", input_channels, 16, 3, 1, 1, True, "subm1")
+        basic("conv1.0", 16, "res1")
+        basic("conv1.1", 16, "res1")
+        prog.append(dict(op="tap", name="x_conv1"))
+        for si, (ci, co, pad) in enumerate([(16, 32, 1), (32, 64, 1), (64, 128, (0, 1, 1))], start=2):
+            post_act(f"conv{si}.0", ci, co, 3, 2, pad, False, f"spconv{si}")
+            basic(f"conv{si}.1", co, f"res{si}")
+            basic(f"conv{si}.2", co, f"res{si}")
+            prog.append(dict(op="tap", name=f"x_conv{si}"))
+        post_act("conv_out", 128, 128, (3, 1, 1), (2, 1, 1), 0, False, "spconv_down2")
+    elif arch == "VoxelResBackBone8xVoxelNeXt":
+        ch = list(channels or [16, 32, 64, 128, 128])
+        ks = list(kernel_sizes or [3, 3, 3, 3])
+        oc = int(out_channel or 128)
+        post_act("conv_input", input_channels, ch[0], 3, 1, 1, True, "subm1")
+        basic("conv1.0", ch[0], "res1")
+        basic("conv1.1", ch[0], "res1")
+        prog.append(dict(op="tap", name="x_conv1"))
+        stage = [(ch[0], ch[1], ks[0]), (ch[1], ch[2], ks[1]), (ch[2], ch[3], ks[2]), (ch[3], ch[4], ks[3]), (ch[4], ch[4], ks[3])]
+        for si, (ci, co, k) in enumerate(stage, start=2):
+            post_act(f"conv{si}.0", ci, co, k, 2, k // 2, False, f"spconv{si}")
+            basic(f"conv{si}.1", co, f"res{si}")
+            basic(f"conv{si}.2", co, f"res{si}")
+            prog.append(dict(op="tap", name=f"x_conv{si}"))
+        prog.append(dict(op="voxelnext_bev"))
+        prog.append(dict(op="conv_bn_relu", conv=conv("conv_out.0", ch[3], oc, (1, 3, 3), 1, (0, 1, 1), False, "spconv_down2", False), bn="conv_out.1"))
+        prog.append(dict(op="conv_bn_relu", conv=conv("shared_conv.0", oc, oc, (1, 3, 3), 1, (0, 1, 1), True, "subm_shared", True),
+                         bn="shared_conv.1", bn_eps=1e-5))
+    else:
+        raise ValueError(arch)
+    return prog
+
+
+def all_conv_specs(prog) -> List[ConvSpec]:
+    out = []
+    for op in prog:
+        if op["op"] == "conv_bn_relu":
+            out.append(op["conv"])
+        elif op["op"] == "basic_block":
+            out += [op["conv1"], op["conv2"]]
+    return out
+
+
+def init_params(prog, seed: int = 4) -> Dict[str, torch.Tensor]:
+    """Random-init weights per SURVEY.md §8d: W ~ N(0, sqrt(2/(K*C_in))) in (oc,kd,kh,kw,ic); bias N(0,.01);
+    BN gamma~U(.5,1.5), beta~N(0,.1), mean~N(0,.1), var~U(.5,1.5).  torch.manual_seed(4) is the reference's
+    seed (quant/quant_centerpoint.py:174)."""
+    g = torch.Generator().manual_seed(seed)
+    P: Dict[str, torch.Tensor] = {}
+
+    def bn(name, c):
+        P[name + ".weight"] = torch.rand(c, generator=g) + 0.5
+        P[name + ".bias"] = torch.randn(c, generator=g) * 0.1
+        P[name + ".running_mean"] = torch.randn(c, generator=g) * 0.1
+        P[name + ".running_var"] = torch.rand(c, generator=g) + 0.5
+
+    for op in prog:
+        convs = []
+        if op["op"] == "conv_bn_relu":
+            convs = [(op["conv"], op["bn"])]
+        elif op["op"] == "basic_block":
+            convs = [(op["conv1"], op["bn1"]), (op["conv2"], op["bn2"])]
+        for spec, bnname in convs:
+            K = spec.ksize[0] * spec.ksize[1] * spec.ksize[2]
+            std = math.sqrt(2.0 / (K * spec.cin))
+            P[spec.name + ".weight"] = torch.randn((spec.cout,) + spec.ksize + (spec.cin,), generator=g) * std
+            if spec.bias:
+                P[spec.name + ".bias"] = torch.randn(spec.cout, generator=g) * 0.01
+            bn(bnname, spec.cout)
+    return P
+
+
+def backbone_forward(prog, params, features: torch.Tensor, coords: np.ndarray, sparse_shape, batch_size: int,
+                     q: QuantCfg = QuantCfg(), record: Optional[dict] = None):
+    """VoxelResBackBone8x.forward (spconv_backbone.py:243-295) / VoxelBackBone8x (:129-181) /
+    VoxelResBackBone8xVoxelNeXt.forward (spconv_backbone_voxelnext.py:166-225) on the CPU.
+    Returns (encoded SpT, dict of taps)."""
+    x = SpT(features, coords.astype(np.int32), list(sparse_shape), batch_size)
+    taps: Dict[str, SpT] = {}
+    for op in prog:
+        kind = op["op"]
+        if kind == "conv_bn_relu":
+            x = run_conv(x, op["conv"], params, q, record)
+            x = bn_relu(x, op["bn"], params, op.get("bn_eps", 1e-3))
+        elif kind == "basic_block":
+            # SparseBasicBlock.forward (spconv_backbone.py:51-67); identity is the un-quantized block input
+            identity = x.features
+            out = run_conv(x, op["conv1"], params, q, record)
+            out = bn_relu(out, op["bn1"], params, 1e-3)
+            out = run_conv(out, op["conv2"], params, q, record)
+            x = bn_relu(out, op["bn2"], params, 1e-3, relu=True, residual=identity)
+        elif kind == "tap":
+            taps[op["name"]] = x
+        elif kind == "voxelnext_bev":
+            # spconv_backbone_voxelnext.py:194-199: scale stage-5/6 indices onto the stage-4 grid, concat, merge in 2-D
+            x4, x5, x6 = taps["x_conv4"], taps["x_conv5"], taps["x_conv6"]
+            c5 = x5.coords.copy(); c5[:, 1:] *= 2
+            c6 = x6.coords.copy(); c6[:, 1:] *= 4
+            feats = torch.cat([x4.features, x5.features, x6.features])
+            cc = np.concatenate([x4.coords, c5, c6])
+            f2, c2 = bev_merge2d(feats, cc)
+            c2 = np.stack([c2[:, 0], np.zeros_like(c2[:, 0]), c2[:, 1], c2[:, 2]], axis=1).astype(np.int32)
+            x = SpT(f2, c2, [1] + list(x4.spatial_shape[1:]), batch_size)
+        else:
+            raise ValueError(kind)
+        if record is not None and kind in ("conv_bn_relu", "basic_block"):
+            nm = op["conv"].name if kind == "conv_bn_relu" else op["conv2"].name
+            record[nm + ".post"] = x.features
+    return x, taps
+
+
+# ----------------------------------------------------------------------------------------------
+# Synthetic frame generators ("G1 lidar-like", "G2 surface sheet")
+# ----------------------------------------------------------------------------------------------
+def synth_lidar_frame(cfg: str, seed: int, n_az: Optional[int] = None, n_beams: Optional[int] = None) -> np.ndarray:
+    """G1: sensor at origin above a ground plane, `n_beams` elevation rings x `n_az` azimuth steps; each ray hits
+    the ground or one of a set of random vertical cylinders; range noise N(0,0.02). Returns (P, F) float32."""
+    rng = np.random.default_rng(seed)
+    if cfg == "kitti":
+        elev = np.deg2rad(np.linspace(-24.8, 2.0, n_beams or 64)); n_az = n_az or 1400
+        sensor_h, n_cyl, ext, max_r, nf = 1.73, 60, 60.0, 80.0, 4
+    else:
+        elev = np.deg2rad(np.linspace(-17.6, 2.4, n_beams or 192)); n_az = n_az or 2650
+        sensor_h, n_cyl, ext, max_r, nf = 2.0, 120, 75.0, 75.0, 5
+    az = np.linspace(-np.pi, np.pi, n_az, endpoint=False)
+    cyl_c = rng.uniform(-ext, ext, size=(n_cyl, 2))
+    cyl_r = rng.uniform(0.5, 2.5, size=n_cyl)
+    cyl_h = rng.uniform(1.5, 3.5, size=n_cyl)
+    A, E = np.meshgrid(az, elev, indexing="ij")
+    dx, dy, dz = np.cos(E) * np.cos(A), np.cos(E) * np.sin(A), np.sin(E)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t_ground = np.where(dz < -1e-6, -sensor_h / dz, np.inf)
+    t_best = np.minimum(t_ground, max_r * 1.5)
+    dxy2 = dx * dx + dy * dy
+    for c, r, h in zip(cyl_c, cyl_r, cyl_h):
+        # ray-circle intersection in the xy plane
+        b = dx * c[0] + dy * c[1]
+        cc = c[0] * c[0] + c[1] * c[1] - r * r
+        disc = b * b - dxy2 * cc
+        with np.errstate(invalid="ignore"):
+            t = (b - np.sqrt(np.where(disc >= 0, disc, np.nan))) / dxy2
+        z = t * dz                                    # relative to the sensor
+        ok = (disc >= 0) & (t > 0.5) & (z >= -sensor_h) & (z <= -sensor_h + h)
+        t_best = np.where(ok & (t < t_best), t, t_best)
+    t_best = t_best + rng.normal(0.0, 0.02, size=t_best.shape)
+    valid = np.isfinite(t_best) & (t_best < max_r) & (t_best > 0.5)
+    x, y, z = (t_best * dx)[valid], (t_best * dy)[valid], (t_best * dz)[valid]
+    if cfg != "kitti":
+        z = z + sensor_h                              # vehicle frame: ground at z = 0 (KITTI stays in the sensor frame)
+    if cfg == "kitti":
+        keep = (x > 0) & (np.abs(np.arctan2(y, x)) < np.pi / 4)
+        x, y, z = x[keep], y[keep], z[keep]
+    feats = [x, y, z] + [rng.uniform(0, 1, size=x.shape) for _ in range(nf - 3)]
+    pts = np.stack(feats, axis=1).astype(np.float32)
+    if cfg != "kitti":                                # Waymo/nuScenes shuffle points at test time (waymo_dataset.yaml:72-76)
+        pts = pts[rng.permutation(pts.shape[0])]
+    return pts
+
+
+def synth_batch(cfg: str, batch: int, first_seed: int = 1000, **kw) -> np.ndarray:
+    """Collated `points (sum P, 1+F)` with the batch index in column 0 (dataset.py collate of 'points')."""
+    fr = [synth_lidar_frame(cfg, first_seed + i, **kw) for i in range(batch)]
+    return np.concatenate([np.concatenate([np.full((f.shape[0], 1), i, np.float32), f], axis=1) for i, f in enumerate(fr)])
+
+
+def synth_surface_sheet(S: int, seed: int = 2000, depth: int = 40) -> np.ndarray:
+    """G2: S x S (x,y) patch with z0(x,y) a clipped 2-D random walk in [0,depth): N = S^2 voxels. Returns (N,4) [b,z,y,x]."""
+    rng = np.random.default_rng(seed)
+    steps_y = rng.integers(-1, 2, size=(S, 1)).cumsum(axis=0)
+    steps_x = rng.integers(-1, 2, size=(S, S)).cumsum(axis=1)
+    z = np.clip(depth // 2 + steps_y + steps_x, 0, depth - 1)
+    yy, xx = np.meshgrid(np.arange(S), np.arange(S), indexing="ij")
+    return np.stack([np.zeros(S * S, np.int64), z.ravel(), yy.ravel(), xx.ravel()], axis=1).astype(np.int32)

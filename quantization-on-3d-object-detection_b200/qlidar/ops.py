@@ -1,0 +1,243 @@
+"""Tensor-level wrappers over the C ABI (include/qlidar.h).  PyTorch is used only for device memory and the
+current stream; every computation below is a hand-written sm_100a kernel in libqlidar_b200.so.  There is no
+CPU path: CPU tensors are rejected."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (QL_F16, QL_F32, QL_S8, QL_S32, QL_Q_CODES_PER_TENSOR, QL_Q_FAKE_PER_CHANNEL, QL_Q_FAKE_PER_TENSOR,
+                   QL_Q_FAKE_PER_ROW, TILE_M, QlidarError, check, lib)
+
+_DT = {torch.float16: QL_F16, torch.float32: QL_F32, torch.int8: QL_S8, torch.int32: QL_S32}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and (not t.is_cuda or not t.is_contiguous()):
+            raise QlidarError("qlidar ops need contiguous CUDA tensors (there is no CPU fallback)")
+
+
+def _i32x3(v):
+    if isinstance(v, int):
+        v = (v, v, v)
+    a = (C.c_int32 * 3)(*[int(x) for x in v])
+    return a
+
+
+def triple(v) -> Tuple[int, int, int]:
+    if isinstance(v, int):
+        return (v, v, v)
+    v = tuple(int(x) for x in v)
+    if len(v) != 3:
+        raise ValueError("expected an int or a 3-tuple")
+    return v
+
+
+def conv_out_shape(in_shape, ksize, stride, pad):
+    k, s, p = triple(ksize), triple(stride), triple(pad)
+    return [(int(in_shape[d]) + 2 * p[d] - k[d]) // s[d] + 1 for d in range(3)]
+
+
+def num_tiles(n_cap: int) -> int:
+    return (int(n_cap) + TILE_M - 1) // TILE_M
+
+
+def hash_capacity(n: int) -> int:
+    return int(lib().ql_hash_capacity(int(n)))
+
+
+def hash_build(coords: torch.Tensor, n_dev: Optional[torch.Tensor], grid: Sequence[int], table: Optional[torch.Tensor] = None):
+    """grid = (B, D, H, W).  Returns the uint64-slot table as an int64 tensor."""
+    _need_cuda(coords, n_dev, table)
+    n_cap = coords.shape[0]
+    if table is None:
+        table = torch.empty(hash_capacity(n_cap), dtype=torch.int64, device=coords.device)
+    B, D, H, W = [int(v) for v in grid]
+    check(lib().ql_hash_build(_ptr(coords), n_cap, _ptr(n_dev), B, D, H, W, _ptr(table), table.numel(), _stream()), "ql_hash_build")
+    return table
+
+
+def voxelize_mean(points: torch.Tensor, pc_range, voxel_size, grid_xyz, batch_size: int, max_pts: int, max_voxels: int,
+                  has_batch_col: bool = True, n_feat: Optional[int] = None, out=None, workspace=None):
+    """Fused hard voxelization + mean VFE (+ DynamicMeanVFE semantics when max_pts == 0).
+    Returns (feats [max_voxels,F] f32, coords [max_voxels,4] i32, npts [max_voxels] i32, n_dev [1] i32, table)."""
+    _need_cuda(points)
+    if points.dtype != torch.float32 or points.dim() != 2:
+        raise QlidarError("points must be a float32 (P, stride) tensor")
+    P, stride = points.shape
+    F = int(n_feat) if n_feat is not None else stride - (1 if has_batch_col else 0)
+    dev = points.device
+    if out is None:
+        feats = torch.empty((max_voxels, F), dtype=torch.float32, device=dev)
+        coords = torch.empty((max_voxels, 4), dtype=torch.int32, device=dev)
+        npts = torch.empty((max_voxels,), dtype=torch.int32, device=dev)
+        n_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
+        table = torch.empty(hash_capacity(max(P, 1)), dtype=torch.int64, device=dev)
+    else:
+        feats, coords, npts, n_dev, table = out
+    ws_bytes = int(lib().ql_voxelize_workspace_bytes(P, max_voxels, F, max_pts))
+    if workspace is None or workspace.numel() < ws_bytes:
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    rmin = (C.c_float * 3)(*[float(v) for v in pc_range[:3]])
+    vs = (C.c_float * 3)(*[float(v) for v in voxel_size])
+    g = (C.c_int32 * 3)(*[int(v) for v in grid_xyz])
+    check(lib().ql_voxelize_mean(_ptr(points), P, stride, 1 if has_batch_col else 0, F, rmin, vs, g, int(batch_size), int(max_pts),
+                                 int(max_voxels), _ptr(feats), _ptr(coords), _ptr(npts), _ptr(n_dev), _ptr(table), table.numel(),
+                                 _ptr(workspace), workspace.numel(), _stream()), "ql_voxelize_mean")
+    return feats, coords, npts, n_dev, table
+
+
+def mean_vfe(voxels: torch.Tensor, num_points: torch.Tensor) -> torch.Tensor:
+    _need_cuda(voxels, num_points)
+    V, T, F = voxels.shape
+    if voxels.dtype != torch.float32 or num_points.dtype not in (torch.float32, torch.int32):
+        raise QlidarError("mean_vfe expects float32 voxels and float32/int32 num_points")
+    out = torch.empty((V, F), dtype=torch.float32, device=voxels.device)
+    check(lib().ql_mean_vfe(_ptr(voxels), _ptr(num_points), 1 if num_points.dtype == torch.float32 else 0, V, T, F, _ptr(out), _stream()),
+          "ql_mean_vfe")
+    return out
+
+
+def rulebook_subm(coords: torch.Tensor, n_dev: Optional[torch.Tensor], grid, ksize, table: torch.Tensor,
+                  nbr: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nbr int32 [tiles, K, 128]."""
+    _need_cuda(coords, n_dev, table, nbr)
+    k = triple(ksize)
+    K = k[0] * k[1] * k[2]
+    n_cap = coords.shape[0]
+    if nbr is None:
+        nbr = torch.empty((num_tiles(n_cap), K, TILE_M), dtype=torch.int32, device=coords.device)
+    B, D, H, W = [int(v) for v in grid]
+    check(lib().ql_rulebook_subm(_ptr(coords), n_cap, _ptr(n_dev), B, D, H, W, _i32x3(k), _ptr(table), table.numel(), _ptr(nbr), _stream()),
+          "ql_rulebook_subm")
+    return nbr
+
+
+def rulebook_strided(coords: torch.Tensor, n_in_dev: Optional[torch.Tensor], grid, ksize, stride, pad, in_table: torch.Tensor,
+                     n_out_cap: int, out=None, workspace=None):
+    """Returns (out_coords [n_out_cap,4], n_out_dev [1], out_table, nbr [tiles,K,128], out_grid (B,D,H,W))."""
+    _need_cuda(coords, n_in_dev, in_table)
+    k, s, p = triple(ksize), triple(stride), triple(pad)
+    K = k[0] * k[1] * k[2]
+    n_in_cap = coords.shape[0]
+    dev = coords.device
+    B, D, H, W = [int(v) for v in grid]
+    od, oh, ow = conv_out_shape((D, H, W), k, s, p)
+    if out is None:
+        out_coords = torch.empty((n_out_cap, 4), dtype=torch.int32, device=dev)
+        n_out_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
+        out_table = torch.empty(hash_capacity(n_out_cap), dtype=torch.int64, device=dev)
+        nbr = torch.empty((num_tiles(n_out_cap), K, TILE_M), dtype=torch.int32, device=dev)
+    else:
+        out_coords, n_out_dev, out_table, nbr = out
+    ws_bytes = int(lib().ql_rulebook_strided_workspace_bytes(n_in_cap, K))
+    if workspace is None or workspace.numel() < ws_bytes:
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib().ql_rulebook_strided(_ptr(coords), n_in_cap, _ptr(n_in_dev), B, D, H, W, _i32x3(k), _i32x3(s), _i32x3(p), _ptr(in_table),
+                                    in_table.numel(), _ptr(out_coords), int(n_out_cap), _ptr(n_out_dev), _ptr(out_table),
+                                    out_table.numel(), _ptr(nbr), _ptr(workspace), workspace.numel(), _stream()), "ql_rulebook_strided")
+    return out_coords, n_out_dev, out_table, nbr, (B, od, oh, ow)
+
+
+def pack_weights(w: torch.Tensor) -> torch.Tensor:
+    """w: CPU tensor (c_out, K, c_in) int8 codes or float16 -> CPU uint8 tensor with the shared-memory image."""
+    if w.is_cuda:
+        w = w.cpu()
+    w = w.contiguous()
+    if w.dtype not in (torch.int8, torch.float16) or w.dim() != 3:
+        raise QlidarError("pack_weights expects (c_out, K, c_in) int8 or float16")
+    c_out, K, c_in = w.shape
+    dt = _DT[w.dtype]
+    nbytes = int(lib().ql_packed_weight_bytes(c_in, c_out, K, dt))
+    if nbytes == 0:
+        raise QlidarError("unsupported weight shape")
+    out = torch.empty(nbytes, dtype=torch.uint8)
+    check(lib().ql_pack_weights_host(C.c_void_p(w.data_ptr()), dt, c_in, c_out, K, C.c_void_p(out.data_ptr())), "ql_pack_weights_host")
+    return out
+
+
+def spconv_mma(feats: torch.Tensor, nbr: torch.Tensor, n_out_cap: int, n_out_dev: Optional[torch.Tensor], c_out: int,
+               w_packed: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, *, act_scale: Optional[torch.Tensor] = None,
+               residual: Optional[torch.Tensor] = None, relu: bool = False, out: Optional[torch.Tensor] = None,
+               out_dtype: torch.dtype = torch.float16, out_q: Optional[torch.Tensor] = None,
+               out_qscale: Optional[torch.Tensor] = None, absmax: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(feats, nbr, n_out_dev, w_packed, scale, shift, act_scale, residual, out, out_q, out_qscale, absmax)
+    if feats.dtype not in (torch.float16, torch.int8):
+        raise QlidarError("spconv_mma gathers float16 rows or int8 codes")
+    if residual is not None and residual.dtype != torch.float16:
+        raise QlidarError("residual must be float16")
+    c_in = feats.shape[1]
+    K = nbr.shape[1]
+    if out is None:
+        out = torch.empty((n_out_cap, c_out), dtype=out_dtype, device=feats.device)
+    raw = out.dtype == torch.int32
+    if not raw and out.dtype not in (torch.float16, torch.float32):
+        raise QlidarError("out must be float16/float32 (or int32 for the raw accumulators)")
+    check(lib().ql_spconv_mma(_ptr(feats), _DT[feats.dtype], _ptr(nbr), int(n_out_cap), _ptr(n_out_dev), c_in, int(c_out), K,
+                              _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(act_scale), _ptr(residual), 1 if relu else 0,
+                              _ptr(out), _DT[out.dtype], _ptr(out_q), _ptr(out_qscale), _ptr(absmax), _stream()), "ql_spconv_mma")
+    return out
+
+
+def stem_conv(feats: torch.Tensor, nbr: torch.Tensor, n_out_cap: int, n_out_dev: Optional[torch.Tensor], w_kio: torch.Tensor,
+              scale: torch.Tensor, shift: torch.Tensor, relu: bool = True, out: Optional[torch.Tensor] = None,
+              out_dtype: torch.dtype = torch.float16, absmax: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """w_kio: (K, c_in, c_out) fp32."""
+    _need_cuda(feats, nbr, n_out_dev, w_kio, scale, shift, out, absmax)
+    if feats.dtype != torch.float32 or w_kio.dtype != torch.float32:
+        raise QlidarError("stem_conv is the fp32 path")
+    K, c_in, c_out = w_kio.shape
+    if out is None:
+        out = torch.empty((n_out_cap, c_out), dtype=out_dtype, device=feats.device)
+    check(lib().ql_stem_conv(_ptr(feats), c_in, _ptr(nbr), int(n_out_cap), _ptr(n_out_dev), c_out, K, _ptr(w_kio), _ptr(scale), _ptr(shift),
+                             1 if relu else 0, _ptr(out), _DT[out.dtype], _ptr(absmax), _stream()), "ql_stem_conv")
+    return out
+
+
+def absmax_cols(x: torch.Tensor, n_dev: Optional[torch.Tensor] = None, absmax: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x, n_dev, absmax)
+    n, c = x.shape
+    if absmax is None:
+        absmax = torch.zeros((c,), dtype=torch.float32, device=x.device)
+    check(lib().ql_absmax_cols(_ptr(x), _DT[x.dtype], n, _ptr(n_dev), c, _ptr(absmax), _stream()), "ql_absmax_cols")
+    return absmax
+
+
+def quantize_rows(x: torch.Tensor, absmax: Optional[torch.Tensor], mode: int, bits: int = 8, n_dev: Optional[torch.Tensor] = None,
+                  smooth: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, act_scale: Optional[torch.Tensor] = None):
+    """Returns (out, act_scale): int8 codes + device scalar de-quantisation scale (CODES_PER_TENSOR) or fp16 fake-quant rows."""
+    _need_cuda(x, absmax, n_dev, smooth, out, act_scale)
+    n, c = x.shape
+    if out is None:
+        out = torch.empty((n, c), dtype=torch.int8 if mode == QL_Q_CODES_PER_TENSOR else torch.float16, device=x.device)
+    if act_scale is None and mode == QL_Q_CODES_PER_TENSOR:
+        act_scale = torch.zeros((1,), dtype=torch.float32, device=x.device)
+    check(lib().ql_quantize_rows(_ptr(x), _DT[x.dtype], n, _ptr(n_dev), c, _ptr(absmax), _ptr(smooth), int(bits), int(mode), _ptr(out),
+                                 _ptr(act_scale), _stream()), "ql_quantize_rows")
+    return out, act_scale
+
+
+def bev_densify(feats: torch.Tensor, table: torch.Tensor, grid, out: Optional[torch.Tensor] = None,
+                out_dtype: torch.dtype = torch.float16) -> torch.Tensor:
+    """grid = (B, D, H, W) -> out (B, C*D, H, W) with channel index c*D + d (== dense().view(N, C*D, H, W))."""
+    _need_cuda(feats, table, out)
+    B, D, H, W = [int(v) for v in grid]
+    c = feats.shape[1]
+    if out is None:
+        out = torch.empty((B, c * D, H, W), dtype=out_dtype, device=feats.device)
+    check(lib().ql_bev_densify(_ptr(feats), _DT[feats.dtype], c, _ptr(table), table.numel(), B, D, H, W, _ptr(out), _DT[out.dtype], _stream()),
+          "ql_bev_densify")
+    return out

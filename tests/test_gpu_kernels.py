@@ -1,0 +1,305 @@
+"""GPU parity tests: every kernel is called through the C ABI (qlidar.ops -> libqlidar_b200.so) and compared with the
+CPU oracle on the same seeded inputs.  Integer / index results are bit-exact; floating point tolerances are stated."""
+import numpy as np
+import pytest
+import torch
+
+import qlidar_oracle as O
+from helpers import nbr_to_tiles, tiles_to_nbr, random_coords
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from qlidar import ops as _ops
+    return _ops
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda().contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ rulebooks
+@pytest.mark.parametrize("ksize", [3, (3, 1, 1), (1, 3, 3), 5])
+def test_rulebook_subm_bit_exact(ops, ksize):
+    rng = np.random.default_rng(1)
+    B, D, H, W = 2, 9, 40, 36
+    coords = random_coords(rng, B, D, H, W, 0.08)
+    ref = O.rulebook_subm(coords, [D, H, W], ksize)
+    c = dev(coords)
+    table = ops.hash_build(c, None, (B, D, H, W))
+    nbr = ops.rulebook_subm(c, None, (B, D, H, W), ksize, table)
+    got = tiles_to_nbr(nbr.cpu().numpy(), coords.shape[0])
+    assert np.array_equal(got, ref)
+    # rows of the last tile beyond N are -1
+    tail = nbr.cpu().numpy().transpose(1, 0, 2).reshape(ref.shape[0], -1)[:, coords.shape[0]:]
+    assert (tail == -1).all()
+
+
+def test_rulebook_subm_device_count(ops):
+    """n_dev < n_cap: only the first n rows take part; later tiles are untouched."""
+    rng = np.random.default_rng(2)
+    B, D, H, W = 1, 5, 30, 30
+    coords = random_coords(rng, B, D, H, W, 0.2)
+    n = coords.shape[0] - 57
+    ref = O.rulebook_subm(coords[:n], [D, H, W], 3)
+    c = dev(coords)
+    n_dev = torch.tensor([n], dtype=torch.int32, device="cuda")
+    table = ops.hash_build(c, n_dev, (B, D, H, W))
+    nbr = ops.rulebook_subm(c, n_dev, (B, D, H, W), 3, table)
+    assert np.array_equal(tiles_to_nbr(nbr.cpu().numpy(), n), ref)
+
+
+@pytest.mark.parametrize("k,s,p", [(3, 2, 1), (3, 2, (0, 1, 1)), ((3, 1, 1), (2, 1, 1), 0), (5, 2, 2), ((1, 3, 3), 1, (0, 1, 1))])
+def test_rulebook_strided_bit_exact(ops, k, s, p):
+    rng = np.random.default_rng(3)
+    B, D, H, W = 2, 11, 33, 38
+    coords = random_coords(rng, B, D, H, W, 0.05)
+    oc_ref, osh, nbr_ref = O.rulebook_strided(coords, [D, H, W], k, s, p)
+    c = dev(coords)
+    table = ops.hash_build(c, None, (B, D, H, W))
+    cap = oc_ref.shape[0] + 300
+    out_coords, n_out, out_table, nbr, ogrid = ops.rulebook_strided(c, None, (B, D, H, W), k, s, p, table, cap)
+    n = int(n_out.item())
+    assert n == oc_ref.shape[0]
+    assert list(ogrid[1:]) == list(osh)
+    assert np.array_equal(out_coords[:n].cpu().numpy(), oc_ref)          # same first-touch order
+    assert np.array_equal(tiles_to_nbr(nbr.cpu().numpy(), n), nbr_ref)
+    # order-free form required by the parity gate: (k, in_coord, out_coord) sorted sets
+    a = O.pairs_in_coord_space(tiles_to_nbr(nbr.cpu().numpy(), n), coords, out_coords[:n].cpu().numpy())
+    b = O.pairs_in_coord_space(nbr_ref, coords, oc_ref)
+    assert np.array_equal(a, b)
+    # the output table maps out coords -> rows: a submanifold rulebook on the outputs must hit every centre
+    nbr2 = ops.rulebook_subm(out_coords, n_out, ogrid, (1, 1, 1), out_table)
+    assert np.array_equal(tiles_to_nbr(nbr2.cpu().numpy(), n)[0], np.arange(n))
+
+
+def test_rulebook_strided_overflow_is_safe(ops):
+    rng = np.random.default_rng(4)
+    B, D, H, W = 1, 8, 20, 20
+    coords = random_coords(rng, B, D, H, W, 0.1)
+    oc_ref, _, _ = O.rulebook_strided(coords, [D, H, W], 3, 2, 1)
+    c = dev(coords)
+    table = ops.hash_build(c, None, (B, D, H, W))
+    cap = oc_ref.shape[0] // 2
+    out_coords, n_out, out_table, nbr, ogrid = ops.rulebook_strided(c, None, (B, D, H, W), 3, 2, 1, table, cap)
+    assert int(n_out.item()) == cap
+    assert np.array_equal(out_coords.cpu().numpy(), oc_ref[:cap])
+    assert nbr.max().item() < coords.shape[0]
+
+
+# ------------------------------------------------------------------------------------------------ voxelization
+@pytest.mark.parametrize("cfg,batch", [("kitti", 1), ("waymo", 2)])
+def test_voxelize_hard_matches_cpu_voxelizer(ops, cfg, batch):
+    c = O.CONFIGS[cfg]
+    kw = dict(n_az=500) if cfg == "kitti" else dict(n_beams=32, n_az=700)
+    pts = O.synth_batch(cfg, batch, **kw)
+    grid = O.grid_size_xyz(c["pc_range"], c["voxel_size"])
+    f_ref, c_ref, n_ref = O.voxelize_mean_batch(pts, c["pc_range"], c["voxel_size"], c["max_pts"], 10 ** 7)
+    cap = c_ref.shape[0] + 100
+    feats, coords, npts, n_dev, table = ops.voxelize_mean(dev(pts), c["pc_range"], c["voxel_size"], grid, batch, c["max_pts"], cap)
+    n = int(n_dev.item())
+    assert n == c_ref.shape[0]
+    assert np.array_equal(coords[:n].cpu().numpy(), c_ref)               # identical first-touch order
+    assert np.array_equal(npts[:n].cpu().numpy(), n_ref)
+    # mean of <= 5 fp32 values: summation order may differ by 1 ulp
+    np.testing.assert_allclose(feats[:n].cpu().numpy(), f_ref, rtol=1e-6, atol=1e-6)
+    # the table hands coords -> row to the stage-1 rulebook
+    sparse_shape = O.sparse_shape_zyx(grid)
+    nbr = ops.rulebook_subm(coords, n_dev, (batch, *sparse_shape), (1, 1, 1), table)
+    assert np.array_equal(tiles_to_nbr(nbr.cpu().numpy(), n)[0], np.arange(n))
+
+
+def test_voxelize_voxel_cap(ops):
+    c = O.CONFIGS["kitti"]
+    pts = O.synth_batch("kitti", 1, n_az=400)
+    grid = O.grid_size_xyz(c["pc_range"], c["voxel_size"])
+    f_ref, c_ref, n_ref = O.voxelize_mean_batch(pts, c["pc_range"], c["voxel_size"], 3, 1000)
+    feats, coords, npts, n_dev, table = ops.voxelize_mean(dev(pts), c["pc_range"], c["voxel_size"], grid, 1, 3, 1000)
+    assert int(n_dev.item()) == 1000 == c_ref.shape[0]
+    assert np.array_equal(coords.cpu().numpy(), c_ref)
+    assert np.array_equal(npts.cpu().numpy(), n_ref)
+    np.testing.assert_allclose(feats.cpu().numpy(), f_ref, rtol=1e-6, atol=1e-6)
+
+
+def test_voxelize_dynamic_matches_dynamic_mean_vfe(ops):
+    c = O.CONFIGS["waymo"]
+    pts = O.synth_batch("waymo", 2, n_beams=24, n_az=600)
+    grid = O.grid_size_xyz(c["pc_range"], c["voxel_size"])
+    f_ref, c_ref, n_ref = O.voxelize_dynamic_mean(pts, c["pc_range"], c["voxel_size"])
+    feats, coords, npts, n_dev, _ = ops.voxelize_mean(dev(pts), c["pc_range"], c["voxel_size"], grid, 2, 0, c_ref.shape[0] + 10)
+    n = int(n_dev.item())
+    assert n == c_ref.shape[0]
+    got_c = coords[:n].cpu().numpy().astype(np.int64)
+    order = np.lexsort((got_c[:, 1], got_c[:, 2], got_c[:, 3], got_c[:, 0]))   # DynamicMeanVFE key: b, x, y, z
+    assert np.array_equal(got_c[order], c_ref)                          # coordinate SETS bit-exact
+    assert np.array_equal(npts[:n].cpu().numpy()[order], n_ref)
+    # unbounded number of fp32 atomic adds per voxel: tolerance 1e-5 relative to the coordinate magnitude (~75 m)
+    np.testing.assert_allclose(feats[:n].cpu().numpy()[order], f_ref, rtol=1e-5, atol=1e-4)
+
+
+def test_mean_vfe(ops):
+    rng = np.random.default_rng(5)
+    V, T, F = 1000, 5, 4
+    num = rng.integers(0, T + 1, size=V).astype(np.int32)
+    vox = rng.normal(size=(V, T, F)).astype(np.float32)
+    vox[np.arange(T)[None, :] >= num[:, None]] = 0
+    ref = O.mean_vfe(vox, num)
+    got = ops.mean_vfe(dev(vox), dev(num.astype(np.float32)))
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=1e-6, atol=1e-6)
+    got = ops.mean_vfe(dev(vox), dev(num))
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ sparse conv
+def _conv_case(rng, n_target, cin, cout, ksize=3, subm=True, stride=1, pad=1):
+    S = int(np.sqrt(n_target))
+    coords = O.synth_surface_sheet(S, seed=int(rng.integers(1 << 30)), depth=12)
+    shape = [12, S, S]
+    if subm:
+        nbr = O.rulebook_subm(coords, shape, ksize)
+    else:
+        _, _, nbr = O.rulebook_strided(coords, shape, ksize, stride, pad)
+    return coords, nbr
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 16), (32, 32), (64, 64), (128, 128), (16, 32), (64, 128), (128, 256), (256, 256)])
+def test_spconv_i8_accumulators_bit_exact(ops, cin, cout):
+    rng = np.random.default_rng(10 + cin + cout)
+    coords, nbr = _conv_case(rng, 3000, cin, cout)
+    N = coords.shape[0]
+    qx = torch.from_numpy(rng.integers(-127, 128, size=(N, cin)).astype(np.int8))
+    qw = torch.from_numpy(rng.integers(-127, 128, size=(cout, 3, 3, 3, cin)).astype(np.int8))
+    ref = O.sparse_conv_int(qx, nbr, qw)
+    wp = ops.pack_weights(qw.reshape(cout, 27, cin)).cuda()
+    one = torch.ones(cout, device="cuda")
+    zero = torch.zeros(cout, device="cuda")
+    out = torch.full((N, cout), -12345, dtype=torch.int32, device="cuda")
+    ops.spconv_mma(dev(qx), dev(nbr_to_tiles(nbr)), N, None, cout, wp, one, zero, out=out)
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), ref), f"mismatches: {(out.cpu() != ref).sum().item()} of {ref.numel()}"
+
+
+@pytest.mark.parametrize("cin,cout,ksize,subm,stride,pad", [
+    (16, 16, 3, True, 1, 1), (32, 64, 3, False, 2, 1), (64, 64, 3, True, 1, 1), (128, 128, (3, 1, 1), False, (2, 1, 1), 0),
+    (32, 64, 5, False, 2, 2), (128, 128, 3, True, 1, 1), (64, 64, (1, 3, 3), True, 1, (0, 1, 1))])
+def test_spconv_f16_matches_fp64_oracle(ops, cin, cout, ksize, subm, stride, pad):
+    rng = np.random.default_rng(20 + cin)
+    coords, nbr = _conv_case(rng, 2500, cin, cout, ksize, subm, stride, pad)
+    n_in, n_out = coords.shape[0], nbr.shape[1]
+    K = nbr.shape[0]
+    x = torch.from_numpy(rng.normal(size=(n_in, cin)).astype(np.float32)).half()
+    qw = torch.from_numpy(rng.integers(-127, 128, size=(cout, K, cin)).astype(np.int8))
+    k3 = O._triple(ksize)
+    ref = O.sparse_conv(x.double(), nbr, qw.double().reshape((cout,) + k3 + (cin,)))
+    wp = ops.pack_weights(qw.half()).cuda()
+    one = torch.ones(cout, device="cuda")
+    zero = torch.zeros(cout, device="cuda")
+    out = ops.spconv_mma(dev(x), dev(nbr_to_tiles(nbr)), n_out, None, cout, wp, one, zero, out_dtype=torch.float32)
+    # fp16 operands are exact, products exact in fp32, only the fp32 accumulation order differs: 1e-4 of max|ref|
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err <= 1e-4 * ref.abs().max().item(), err
+
+
+def test_spconv_epilogue_fusion(ops):
+    """dequant scale * BN scale/shift + residual + ReLU, fp16 out, int8 re-quantised out, per-channel absmax, device count."""
+    rng = np.random.default_rng(30)
+    cin = cout = 64
+    coords, nbr = _conv_case(rng, 4000, cin, cout)
+    N = coords.shape[0]
+    n_live = N - 100
+    x = torch.from_numpy(rng.normal(size=(N, cin)).astype(np.float32)).half()
+    qw = torch.from_numpy(rng.integers(-127, 128, size=(cout, 27, cin)).astype(np.int8))
+    scale = torch.from_numpy(rng.uniform(0.5, 1.5, cout).astype(np.float32)) * 1e-3
+    shift = torch.from_numpy(rng.normal(size=cout).astype(np.float32))
+    res = torch.from_numpy(rng.normal(size=(N, cout)).astype(np.float32)).half()
+    act_scale = torch.tensor([0.37], dtype=torch.float32)
+    qscale = torch.from_numpy(rng.uniform(20, 40, cout).astype(np.float32))
+    nbr_live = nbr.copy()
+    ref = O.sparse_conv(x.double(), nbr_live, qw.double().reshape(cout, 3, 3, 3, cin))
+    y = torch.relu(ref * (scale.double() * 0.37) + shift.double() + res.double())[:n_live]
+    n_dev = torch.tensor([n_live], dtype=torch.int32, device="cuda")
+    out = torch.zeros((N, cout), dtype=torch.float16, device="cuda")
+    out_q = torch.zeros((N, cout), dtype=torch.int8, device="cuda")
+    absmax = torch.zeros(cout, dtype=torch.float32, device="cuda")
+    ops.spconv_mma(dev(x), dev(nbr_to_tiles(nbr)), N, n_dev, cout, ops.pack_weights(qw.half()).cuda(), dev(scale), dev(shift),
+                   act_scale=dev(act_scale), residual=dev(res), relu=True, out=out, out_q=out_q, out_qscale=dev(qscale), absmax=absmax)
+    got = out.cpu().double()
+    tol = 2e-3 * y.abs().max().item()                                   # fp16 output rounding (2^-11 relative)
+    assert (got[:n_live] - y).abs().max().item() <= tol
+    assert (got[n_live:] == 0).all()                                    # rows past the device count are not written
+    np.testing.assert_allclose(absmax.cpu().numpy(), y.abs().amax(dim=0).numpy(), rtol=2e-3)
+    q_ref = torch.clamp(torch.round(y * qscale.double()), -127, 127)
+    dq = (out_q.cpu().double()[:n_live] - q_ref).abs()
+    assert dq.max().item() <= 1 and (dq > 0).double().mean().item() < 0.02   # only rounding-boundary flips
+
+
+def test_stem_conv(ops):
+    rng = np.random.default_rng(40)
+    coords, nbr = _conv_case(rng, 3000, 5, 16)
+    N = coords.shape[0]
+    x = torch.from_numpy(rng.normal(size=(N, 5)).astype(np.float32) * 10)
+    w = torch.from_numpy(rng.normal(size=(16, 3, 3, 3, 5)).astype(np.float32))
+    scale = torch.from_numpy(rng.uniform(0.5, 1.5, 16).astype(np.float32))
+    shift = torch.from_numpy(rng.normal(size=16).astype(np.float32))
+    ref = torch.relu(O.sparse_conv(x.double(), nbr, w.double()) * scale.double() + shift.double())
+    w_kio = w.reshape(16, 27, 5).permute(1, 2, 0).contiguous()
+    absmax = torch.zeros(16, device="cuda")
+    out = ops.stem_conv(dev(x), dev(nbr_to_tiles(nbr)), N, None, dev(w_kio), dev(scale), dev(shift), relu=True,
+                        out_dtype=torch.float32, absmax=absmax)
+    assert (out.cpu().double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+    np.testing.assert_allclose(absmax.cpu().numpy(), ref.abs().amax(dim=0).numpy(), rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ quantizer
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_quantize_rows_codes_bit_exact(ops, dtype):
+    rng = np.random.default_rng(50)
+    x = torch.from_numpy(rng.normal(size=(5000, 64)).astype(np.float32))
+    x[::97, 3] *= 20
+    x = x.to(dtype)
+    xf = x.float()
+    amax = O.dynamic_amax(xf)
+    q_ref = O.quantize_codes(xf, amax, 8)
+    absmax = ops.absmax_cols(dev(x))
+    np.testing.assert_array_equal(absmax.cpu().numpy(), xf.abs().amax(dim=0).numpy())
+    q, act_scale = ops.quantize_rows(dev(x), absmax, ops.QL_Q_CODES_PER_TENSOR)
+    assert torch.equal(q.cpu().int(), q_ref)
+    assert abs(act_scale.item() - amax.item() / 127.0) <= 1e-7 * amax.item()
+
+
+def test_quantize_rows_smooth_and_fake(ops):
+    rng = np.random.default_rng(51)
+    x = torch.from_numpy(rng.normal(size=(3000, 32)).astype(np.float32))
+    s = torch.from_numpy(rng.uniform(0.5, 2.0, 32).astype(np.float32))
+    absmax = ops.absmax_cols(dev(x))
+    q, act_scale = ops.quantize_rows(dev(x), absmax, ops.QL_Q_CODES_PER_TENSOR, smooth=dev(s))
+    xs = x / s
+    assert torch.equal(q.cpu().int(), O.quantize_codes(xs, O.dynamic_amax(xs), 8))
+    fq, _ = ops.quantize_rows(dev(x), absmax, ops.QL_Q_FAKE_PER_CHANNEL)
+    ref = O.fake_quant(x, 8, axis=1)
+    assert (fq.cpu().float() - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()   # fp16 storage of the fake-quant value
+    fr, _ = ops.quantize_rows(dev(x), None, ops.QL_Q_FAKE_PER_ROW)
+    ref = O.fake_quant(x, 8, axis=0)
+    assert (fr.cpu().float() - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------------ BEV
+@pytest.mark.parametrize("D,H,W,C", [(2, 47, 45, 128), (2, 188, 188, 128), (5, 20, 24, 64)])
+def test_bev_densify(ops, D, H, W, C):
+    rng = np.random.default_rng(60)
+    B = 2
+    coords = random_coords(rng, B, D, H, W, 0.15)
+    f = torch.from_numpy(rng.normal(size=(coords.shape[0], C)).astype(np.float32)).half()
+    ref = O.height_compression(f.float(), coords, [D, H, W], B)
+    c = dev(coords)
+    table = ops.hash_build(c, None, (B, D, H, W))
+    out = ops.bev_densify(dev(f), table, (B, D, H, W))
+    assert out.shape == (B, C * D, H, W)
+    assert torch.equal(out.cpu().float(), ref)
+    out32 = ops.bev_densify(dev(f.float()), table, (B, D, H, W), out_dtype=torch.float32)
+    assert torch.equal(out32.cpu(), ref)

@@ -1,0 +1,160 @@
+"""CPU: pin the oracle.  The reference ships no golden vectors for this path, so the oracle is
+pinned by independent restatements: dense torch conv3d, float64 integer arithmetic, and structural properties."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import qlidar_oracle as O
+from helpers import random_coords
+
+CASES = [(3, 1, 1, True), (3, 2, 1, False), (3, 2, (0, 1, 1), False), ((3, 1, 1), (2, 1, 1), 0, False), (5, 2, 2, False),
+         ((1, 3, 3), 1, (0, 1, 1), False), ((1, 3, 3), 1, (0, 1, 1), True)]
+
+
+@pytest.mark.parametrize("k,s,p,subm", CASES)
+def test_sparse_conv_equals_dense_conv3d(k, s, p, subm):
+    rng = np.random.default_rng(0)
+    torch.manual_seed(0)
+    B, D, H, W = 2, 7, 9, 8
+    coords = random_coords(rng, B, D, H, W, 0.15)
+    cin, cout = 5, 6
+    x = torch.randn(len(coords), cin, dtype=torch.float64)
+    dense = O.to_dense(x, coords, [D, H, W], B)
+    k3 = O._triple(k)
+    w = torch.randn((cout,) + k3 + (cin,), dtype=torch.float64)
+    ref = F.conv3d(dense, w.permute(0, 4, 1, 2, 3), stride=O._triple(s), padding=O._triple(p))
+    if subm:
+        nbr, oc, osh = O.rulebook_subm(coords, [D, H, W], k), coords, [D, H, W]
+    else:
+        oc, osh, nbr = O.rulebook_strided(coords, [D, H, W], k, s, p)
+        occ = torch.zeros((B, 1, D, H, W), dtype=torch.float64)
+        occ[coords[:, 0], 0, coords[:, 1], coords[:, 2], coords[:, 3]] = 1
+        act = F.conv3d(occ, torch.ones((1, 1) + k3, dtype=torch.float64), stride=O._triple(s), padding=O._triple(p)) > 0
+        assert int(act.sum()) == len(oc)                      # out-set = dilate o subsample
+        assert list(act.shape[2:]) == list(osh)
+        assert len(np.unique(O._lin(oc, osh))) == len(oc)
+    y = O.sparse_conv(x, nbr, w)
+    refs = ref.permute(0, 2, 3, 4, 1)[oc[:, 0], oc[:, 1], oc[:, 2], oc[:, 3]]
+    assert (y - refs).abs().max().item() < 1e-10
+
+
+def test_rulebook_permutation_invariance():
+    rng = np.random.default_rng(1)
+    coords = random_coords(rng, 1, 6, 12, 12, 0.2)
+    perm = rng.permutation(len(coords))
+    a = O.pairs_in_coord_space(O.rulebook_subm(coords, [6, 12, 12], 3), coords, coords)
+    b = O.pairs_in_coord_space(O.rulebook_subm(coords[perm], [6, 12, 12], 3), coords[perm], coords[perm])
+    assert np.array_equal(a, b)
+    oc1, _, n1 = O.rulebook_strided(coords, [6, 12, 12], 3, 2, 1)
+    oc2, _, n2 = O.rulebook_strided(coords[perm], [6, 12, 12], 3, 2, 1)
+    assert np.array_equal(O.pairs_in_coord_space(n1, coords, oc1), O.pairs_in_coord_space(n2, coords[perm], oc2))
+
+
+def test_strided_first_touch_order_matches_naive_loop():
+    rng = np.random.default_rng(2)
+    coords = random_coords(rng, 2, 5, 9, 9, 0.2)
+    oc, osh, _ = O.rulebook_strided(coords, [5, 9, 9], 3, 2, 1)
+    seen, order = {}, []
+    for c in coords:                                          # pure-Python restatement of the numbering rule
+        for kz in range(3):
+            for ky in range(3):
+                for kx in range(3):
+                    n = (c[1] + 1 - kz, c[2] + 1 - ky, c[3] + 1 - kx)
+                    if any(v % 2 for v in n) or any(v < 0 for v in n):
+                        continue
+                    o = (int(c[0]), n[0] // 2, n[1] // 2, n[2] // 2)
+                    if o[1] >= osh[0] or o[2] >= osh[1] or o[3] >= osh[2]:
+                        continue
+                    if o not in seen:
+                        seen[o] = len(order)
+                        order.append(o)
+    assert np.array_equal(oc, np.asarray(order, dtype=np.int32))
+
+
+def test_backbone_shapes_match_reference_comments():
+    # spconv_backbone.py:206,213,220,229 and SURVEY.md 8: KITTI [41,1600,1408]->[21,800,704]->[11,400,352]->[5,200,176]->[2,200,176]
+    s = [41, 1600, 1408]
+    s = O.conv_out_shape(s, 3, 2, 1); assert s == [21, 800, 704]
+    s = O.conv_out_shape(s, 3, 2, 1); assert s == [11, 400, 352]
+    s = O.conv_out_shape(s, 3, 2, (0, 1, 1)); assert s == [5, 200, 176]
+    s = O.conv_out_shape(s, (3, 1, 1), (2, 1, 1), 0); assert s == [2, 200, 176]
+    assert O.sparse_shape_zyx(O.grid_size_xyz(**{k: O.CONFIGS["waymo"][k] for k in ("pc_range", "voxel_size")})) == [41, 1504, 1504]
+
+
+def test_fake_quant_semantics():
+    # TensorQuantizer defaults: 8 bit, narrow range, symmetric, round half to even, amax<=2^-24 -> 0
+    t = torch.tensor([[0.5, -1.0, 1.0, 0.0039370079 * 0.5]])
+    fq = O.fake_quant(t, 8)
+    assert fq[0, 1].item() == -1.0 and fq[0, 2].item() == 1.0
+    q = O.quantize_codes(torch.tensor([0.5, 1.5, 2.5, -0.5, 127.0, -300.0]), torch.tensor(127.0), 8)
+    assert q.tolist() == [0, 2, 2, 0, 127, -127]              # half-to-even and clamp to +-127
+    assert O.fake_quant(torch.zeros(4, 3), 8).abs().sum().item() == 0
+    x = torch.randn(50, 6)
+    per_c = O.fake_quant(x, 8, axis=1)
+    for c in range(6):
+        assert torch.equal(per_c[:, c], O.fake_quant(x[:, c], 8))
+    assert O.quant_bound(16) == 32767.0
+
+
+def test_weight_matrix_roundtrip_and_per_oc_quant():
+    w = torch.randn(8, 3, 3, 3, 4)
+    assert torch.equal(O.weight_from_matrix(O.weight_matrix(w), w), w)
+    q, amax = O.quantize_weight_per_oc(w)
+    assert q.abs().amax(dim=(1, 2, 3, 4)).tolist() == [127] * 8
+    assert torch.allclose(amax, w.abs().amax(dim=(1, 2, 3, 4)))
+
+
+def test_w8a8_pt_int_path_is_the_reference_math():
+    """Per-tensor activation scale factors out of the sum: int32 accumulate * scales == QConvNd fake-quant conv."""
+    rng = np.random.default_rng(3)
+    coords = random_coords(rng, 1, 6, 14, 14, 0.25)
+    nbr = O.rulebook_subm(coords, [6, 14, 14], 3)
+    x = torch.randn(len(coords), 16)
+    w = torch.randn(16, 3, 3, 3, 16) * 0.1
+    b = torch.randn(16) * 0.01
+    acc, y, amax_x, amax_w = O.qconv_w8a8_pt(x, nbr, w, b)
+    ref = O.qconv_reference_math(x, nbr, w, b, 8, 8, cw=False)
+    assert (y - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+    # exactness of the integer path against float64
+    qw, _ = O.quantize_weight_per_oc(w)
+    qx = O.quantize_codes(x, amax_x, 8)
+    ref64 = O.sparse_conv(qx.double(), nbr, qw.double())
+    assert torch.equal(acc.double(), ref64)
+
+
+def test_voxelize_hard_caps_and_order():
+    pts = np.array([[0.01, 0.01, 0.01, 1], [5.0, 5.0, 0.5, 2], [0.02, 0.02, 0.02, 3], [0.03, 0.03, 0.03, 4],
+                    [100.0, 0, 0, 5], [9.9, 0.0, 0.0, 6]], dtype=np.float32)
+    v, c, n = O.voxelize_hard(pts, [0, 0, 0, 10, 10, 1], [1.0, 1.0, 1.0], max_pts=2, max_voxels=2)
+    assert c.tolist() == [[0, 0, 0], [0, 5, 5]] and n.tolist() == [2, 1]
+    assert v[0, :, 3].tolist() == [1.0, 3.0]                  # first two points in point order; 4th dropped by the cap
+    m = O.mean_vfe(v, n)
+    assert np.allclose(m[0], [0.015, 0.015, 0.015, 2.0])
+
+
+def test_dense_and_height_compression_layout():
+    rng = np.random.default_rng(4)
+    coords = random_coords(rng, 2, 2, 5, 6, 0.4)
+    f = torch.randn(len(coords), 3)
+    hc = O.height_compression(f, coords, [2, 5, 6], 2)
+    assert hc.shape == (2, 6, 5, 6)
+    i = 7
+    b, d, y, x = coords[i]
+    assert torch.equal(hc[b, torch.arange(3) * 2 + d, y, x], f[i])    # channel index = c*D + d
+
+
+def test_backbone_oracle_runs_small():
+    prog = O.backbone_specs("VoxelResBackBone8x", 4)
+    P = O.init_params(prog)
+    assert len(O.all_conv_specs(prog)) == 21
+    rng = np.random.default_rng(5)
+    coords = random_coords(rng, 1, 41, 64, 64, 0.01)
+    f = torch.randn(len(coords), 4)
+    out, taps = O.backbone_forward(prog, P, f, coords, [41, 64, 64], 1)
+    assert out.features.shape[1] == 128 and out.spatial_shape == [2, 8, 8]
+    assert taps["x_conv4"].spatial_shape == [5, 8, 8]
+    rec = {}
+    out_q, _ = O.backbone_forward(prog, P, f, coords, [41, 64, 64], 1, O.QuantCfg(mode="w8a8_pt", no_list=("conv_input.0",)), rec)
+    rel = (out_q.features - out.features).abs().max() / out.features.abs().max()
+    assert rel < 0.2 and "conv1.0.conv1.acc" in rec
