@@ -68,7 +68,8 @@ int ql_hash_build(const int32_t* coords, int64_t n_cap, const int32_t* n_dev,
  *      then the remaining features (n_feat counts x,y,z).  Voxels are numbered in first-touch order over the
  *      point array (== spconv's CPU voxelizer); a voxel keeps its first `max_pts_per_voxel` points; voxels
  *      numbered >= max_voxels are dropped.  Outputs: out_feats [max_voxels, n_feat] fp32 (mean), out_coords
- *      [max_voxels, 4] int32, out_npts [max_voxels] int32, *n_voxels_dev, and the hash table coords -> row. */
+ *      [max_voxels, 4] int32, out_npts [max_voxels] int32, n_voxels_dev int32[2] = {rows kept, voxels found before
+ *      the cap}, and the hash table coords -> row. */
 size_t ql_voxelize_workspace_bytes(int64_t max_points, int64_t max_voxels, int32_t n_feat, int32_t max_pts_per_voxel);
 int ql_voxelize_mean(const float* points, int64_t n_points, int32_t point_stride, int32_t has_batch_col, int32_t n_feat,
                      const float* range_min_xyz_host, const float* voxel_size_xyz_host, const int32_t* grid_xyz_host,
@@ -83,7 +84,9 @@ int ql_mean_vfe(const float* voxels, const void* num_points, int32_t num_points_
 /* ---- rulebook / indice pairs (replaces [EXT] spconv indice-pair generation inside
  *      SubMConv3d/SparseConv3d.forward; keys at spconv_backbone.py:194-231).
  *      Layout produced: nbr[tile][k][128] int32, tile = row/128: the input row feeding output row
- *      tile*128+r through kernel offset k = (kz*KH+ky)*KW+kx, or -1.  ksize/stride/pad are zyx triples. */
+ *      tile*128+r through kernel offset k = (kz*KH+ky)*KW+kx, or -1.  ksize/stride/pad are zyx triples.
+ *      Strided: n_out_dev is int32[2] = {rows kept (<= n_out_cap), active output sites found}; [1] > [0] means the
+ *      caller's capacity overflowed (the surplus sites are dropped and never referenced). */
 int64_t ql_rulebook_num_tiles(int64_t n_out_cap);
 int ql_rulebook_subm(const int32_t* coords, int64_t n_cap, const int32_t* n_dev,
                      int32_t B, int32_t D, int32_t H, int32_t W, const int32_t* ksize_host,

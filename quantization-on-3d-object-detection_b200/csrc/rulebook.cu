@@ -222,7 +222,7 @@ extern "C" int ql_rulebook_strided(const int32_t* in_coords, int64_t n_in_cap, c
     int* block_counts = (int*)workspace;
     if (cudaMemsetAsync(out_table, 0xFF, (size_t)out_table_cap * 8, st) != cudaSuccess) return QL_ERR_CUDA;
     if (n_in_cap == 0) {
-        if (cudaMemsetAsync(n_out_dev, 0, 4, st) != cudaSuccess) return QL_ERR_CUDA;
+        if (cudaMemsetAsync(n_out_dev, 0, 8, st) != cudaSuccess) return QL_ERR_CUDA;
         return QL_OK;
     }
     uint32_t omask = (uint32_t)(out_table_cap - 1);
@@ -230,7 +230,7 @@ extern "C" int ql_rulebook_strided(const int32_t* in_coords, int64_t n_in_cap, c
     k_rb_insert<<<nb, QL_SCAN_THREADS, 0, st>>>((const int4*)in_coords, n_in_cap, n_in_dev, cg, gout, (uint2*)out_table, omask);
     k_rb_number<0><<<nb, QL_SCAN_THREADS, 0, st>>>((const int4*)in_coords, n_in_cap, n_in_dev, cg, gout, (uint2*)out_table, omask,
                                                    block_counts, (int4*)out_coords, n_out_cap);
-    k_scan_blocks<<<1, QL_SCAN_THREADS, 0, st>>>(block_counts, (int)nb, block_counts + nb, n_out_dev, n_out_cap);
+    k_scan_blocks<<<1, QL_SCAN_THREADS, 0, st>>>(block_counts, (int)nb, n_out_dev + 1, n_out_dev, n_out_cap);
     k_rb_number<1><<<nb, QL_SCAN_THREADS, 0, st>>>((const int4*)in_coords, n_in_cap, n_in_dev, cg, gout, (uint2*)out_table, omask,
                                                    block_counts, (int4*)out_coords, n_out_cap);
     k_rb_strip_flag<<<(unsigned)((out_table_cap + 255) / 256), 256, 0, st>>>((uint2*)out_table, out_table_cap);

@@ -274,7 +274,6 @@ extern "C" int ql_voxelize_mean(const float* points, int64_t n_points, int32_t p
     uint32_t* tmin = (uint32_t*)(ws + w.tmin);
     float* sums = (float*)(ws + w.sums);
     int* cnt = (int*)(ws + w.cnt);
-    int* ntotal = (int*)(ws + w.ntotal);
 
     if (cudaMemsetAsync(table, 0xFF, (size_t)table_cap * 8, st) != cudaSuccess) return QL_ERR_CUDA;
     if (cudaMemsetAsync(pt_vid, 0xFF, (size_t)(n_points > 0 ? n_points : 1) * 4, st) != cudaSuccess) return QL_ERR_CUDA;
@@ -285,7 +284,7 @@ extern "C" int ql_voxelize_mean(const float* points, int64_t n_points, int32_t p
         if (cudaMemsetAsync(cnt, 0, (size_t)max_voxels * 4, st) != cudaSuccess) return QL_ERR_CUDA;
     }
     if (n_points == 0) {
-        if (cudaMemsetAsync(n_voxels_dev, 0, 4, st) != cudaSuccess) return QL_ERR_CUDA;
+        if (cudaMemsetAsync(n_voxels_dev, 0, 8, st) != cudaSuccess) return QL_ERR_CUDA;
         return QL_OK;
     }
     uint32_t cap_mask = (uint32_t)(table_cap - 1);
@@ -293,7 +292,7 @@ extern "C" int ql_voxelize_mean(const float* points, int64_t n_points, int32_t p
     unsigned nb = (unsigned)((n_points + kBlockPts - 1) / kBlockPts);
     k_vox_insert<<<gp, kThreads, 0, st>>>(P, (uint2*)table, cap_mask, pt_slot);
     k_vox_count<<<nb, kThreads, 0, st>>>(n_points, (const uint2*)table, pt_slot, blocks);
-    k_scan_blocks<<<1, kThreads, 0, st>>>(blocks, (int)nb, ntotal, n_voxels_dev, max_voxels);
+    k_scan_blocks<<<1, kThreads, 0, st>>>(blocks, (int)nb, n_voxels_dev + 1, n_voxels_dev, max_voxels);
     k_vox_assign<<<nb, kThreads, 0, st>>>(P, (const uint2*)table, pt_slot, blocks, pt_vid, vox_first, out_coords);
     k_vox_gather<<<gp, kThreads, 0, st>>>(P, (const uint2*)table, pt_slot, pt_vid, tmin, sums, cnt);
     k_vox_drop<<<gp, kThreads, 0, st>>>(P, (uint2*)table, pt_slot, pt_vid);

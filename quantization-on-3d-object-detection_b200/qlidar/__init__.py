@@ -1,0 +1,15 @@
+"""qlidar -- B200-native (sm_100a) quantized sparse-3D-conv backbone path behind the Q-LiDAR / OpenPCDet module API.
+
+Python here is the host-side mirror of the reference's plugin interface; all compute is in libqlidar_b200.so
+(include/qlidar.h).  Importing this package never falls back to a CPU implementation."""
+from . import ops
+from ._lib import QlidarError, lib
+from .sparse import (SparseConvTensor, SparseModule, SparseSequential, SparseConvolution, SubMConv3d, SparseConv3d,
+                     SubMConv2d, SparseConv2d, SparseInverseConv3d, replace_feature)
+from .tensor_quant import QuantDescriptor, TensorQuantizer, MaxCalibrator
+from .quant import QConvNd, QConv3d, QConv2d, GQConv3d, q_conv3d, collect_stats, compute_amax
+from .backbones import (Cfg, post_act_block, SparseBasicBlock, VoxelBackBone8x, VoxelResBackBone8x,
+                        VoxelResBackBone8xVoxelNeXt, MeanVFE, DynamicMeanVFE, VoxelGeneratorWrapper, HeightCompression)
+from .engine import BackboneEngine
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,325 @@
+"""Drop-in mirrors of the pcdet plugins on the hot path, with the same constructor signatures, attributes, module
+tree (=> identical state_dict keys and `named_children` paths for q_conv3d's no_list) and batch_dict contract:
+
+  MeanVFE                      pcdet/models/backbones_3d/vfe/mean_vfe.py:6-31
+  DynamicMeanVFE               pcdet/models/backbones_3d/vfe/dynamic_mean_vfe.py:38-76
+  VoxelBackBone8x              pcdet/models/backbones_3d/spconv_backbone.py:70-181
+  VoxelResBackBone8x           pcdet/models/backbones_3d/spconv_backbone.py:184-295
+  VoxelResBackBone8xVoxelNeXt  pcdet/models/backbones_3d/spconv_backbone_voxelnext.py:69-225
+  HeightCompression            pcdet/models/backbones_2d/map_to_bev/height_compression.py:4-26
+
+`forward(batch_dict)` runs the module tree op by op (each conv = one fused kernel).  The graph-captured, sync-free
+whole-backbone schedule lives in qlidar.engine.BackboneEngine (built from these modules)."""
+from __future__ import annotations
+
+from functools import partial
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from . import sparse as spconv
+from .sparse import SparseConvTensor, replace_feature
+
+
+class Cfg(dict):
+    """Minimal EasyDict stand-in (pcdet/config.py uses easydict): attribute access + .get()."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def _cfg(c):
+    return c if isinstance(c, Cfg) else Cfg(c or {})
+
+
+def post_act_block(in_channels, out_channels, kernel_size, indice_key=None, stride=1, padding=0, conv_type='subm', norm_fn=None):
+    """spconv_backbone.py:8-27."""
+    if conv_type == 'subm':
+        conv = spconv.SubMConv3d(in_channels, out_channels, kernel_size, bias=False, indice_key=indice_key)
+    elif conv_type == 'spconv':
+        conv = spconv.SparseConv3d(in_channels, out_channels, kernel_size, stride=stride, padding=padding, bias=False,
+                                   indice_key=indice_key)
+    elif conv_type == 'inverseconv':
+        conv = spconv.SparseInverseConv3d(in_channels, out_channels, kernel_size, indice_key=indice_key, bias=False)
+    else:
+        raise NotImplementedError
+    return spconv.SparseSequential(conv, norm_fn(out_channels), nn.ReLU())
+
+
+class SparseBasicBlock(spconv.SparseModule):
+    """spconv_backbone.py:30-67 (res-block convs carry a bias: `bias = norm_fn is not None`, :37-38)."""
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, bias=None, norm_fn=None, downsample=None, indice_key=None):
+        super().__init__()
+        assert norm_fn is not None
+        if bias is None:
+            bias = norm_fn is not None
+        self.conv1 = spconv.SubMConv3d(inplanes, planes, kernel_size=3, stride=stride, padding=1, bias=bias, indice_key=indice_key)
+        self.bn1 = norm_fn(planes)
+        self.relu = nn.ReLU()
+        self.conv2 = spconv.SubMConv3d(planes, planes, kernel_size=3, stride=stride, padding=1, bias=bias, indice_key=indice_key)
+        self.bn2 = norm_fn(planes)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        identity = x
+        out = self.conv1(x)
+        out = replace_feature(out, self.bn1(out.features))
+        out = replace_feature(out, self.relu(out.features))
+        out = self.conv2(out)
+        out = replace_feature(out, self.bn2(out.features))
+        if self.downsample is not None:
+            identity = self.downsample(x)
+        out = replace_feature(out, out.features + identity.features)
+        out = replace_feature(out, self.relu(out.features))
+        return out
+
+
+class _BackboneBase(nn.Module):
+    def _input_tensor(self, batch_dict):
+        voxel_features, voxel_coords = batch_dict['voxel_features'], batch_dict['voxel_coords']
+        # load_data_to_gpu casts coords to float32 (pcdet/models/__init__.py:36); `.int()` undoes it (spconv_backbone.py:258)
+        idx = voxel_coords if voxel_coords.dtype == torch.int32 else voxel_coords.int()
+        return SparseConvTensor(features=voxel_features, indices=idx.contiguous(), spatial_shape=self.sparse_shape,
+                                batch_size=batch_dict['batch_size'])
+
+    @staticmethod
+    def _publish(batch_dict, out, taps):
+        batch_dict.update({'encoded_spconv_tensor': out, 'encoded_spconv_tensor_stride': 8})
+        batch_dict.update({'multi_scale_3d_features': taps})
+        batch_dict.update({'multi_scale_3d_strides': {'x_conv1': 1, 'x_conv2': 2, 'x_conv3': 4, 'x_conv4': 8}})
+        return batch_dict
+
+
+class VoxelBackBone8x(_BackboneBase):
+    def __init__(self, model_cfg, input_channels, grid_size, **kwargs):
+        super().__init__()
+        self.model_cfg = _cfg(model_cfg)
+        norm_fn = partial(nn.BatchNorm1d, eps=1e-3, momentum=0.01)
+        self.sparse_shape = [int(v) for v in (np.asarray(grid_size)[::-1] + [1, 0, 0])]
+        self.conv_input = spconv.SparseSequential(
+            spconv.SubMConv3d(input_channels, 16, 3, padding=1, bias=False, indice_key='subm1'), norm_fn(16), nn.ReLU())
+        block = post_act_block
+        self.conv1 = spconv.SparseSequential(block(16, 16, 3, norm_fn=norm_fn, padding=1, indice_key='subm1'))
+        self.conv2 = spconv.SparseSequential(
+            block(16, 32, 3, norm_fn=norm_fn, stride=2, padding=1, indice_key='spconv2', conv_type='spconv'),
+            block(32, 32, 3, norm_fn=norm_fn, padding=1, indice_key='subm2'),
+            block(32, 32, 3, norm_fn=norm_fn, padding=1, indice_key='subm2'))
+        self.conv3 = spconv.SparseSequential(
+            block(32, 64, 3, norm_fn=norm_fn, stride=2, padding=1, indice_key='spconv3', conv_type='spconv'),
+            block(64, 64, 3, norm_fn=norm_fn, padding=1, indice_key='subm3'),
+            block(64, 64, 3, norm_fn=norm_fn, padding=1, indice_key='subm3'))
+        self.conv4 = spconv.SparseSequential(
+            block(64, 64, 3, norm_fn=norm_fn, stride=2, padding=(0, 1, 1), indice_key='spconv4', conv_type='spconv'),
+            block(64, 64, 3, norm_fn=norm_fn, padding=1, indice_key='subm4'),
+            block(64, 64, 3, norm_fn=norm_fn, padding=1, indice_key='subm4'))
+        last_pad = self.model_cfg.get('last_pad', 0)
+        self.conv_out = spconv.SparseSequential(
+            spconv.SparseConv3d(64, 128, (3, 1, 1), stride=(2, 1, 1), padding=last_pad, bias=False, indice_key='spconv_down2'),
+            norm_fn(128), nn.ReLU())
+        self.num_point_features = 128
+        self.backbone_channels = {'x_conv1': 16, 'x_conv2': 32, 'x_conv3': 64, 'x_conv4': 64}
+
+    def forward(self, batch_dict):
+        x = self.conv_input(self._input_tensor(batch_dict))
+        x_conv1 = self.conv1(x)
+        x_conv2 = self.conv2(x_conv1)
+        x_conv3 = self.conv3(x_conv2)
+        x_conv4 = self.conv4(x_conv3)
+        out = self.conv_out(x_conv4)
+        return self._publish(batch_dict, out, {'x_conv1': x_conv1, 'x_conv2': x_conv2, 'x_conv3': x_conv3, 'x_conv4': x_conv4})
+
+
+class VoxelResBackBone8x(_BackboneBase):
+    def __init__(self, model_cfg, input_channels, grid_size, **kwargs):
+        super().__init__()
+        self.model_cfg = _cfg(model_cfg)
+        use_bias = self.model_cfg.get('USE_BIAS', None)
+        norm_fn = partial(nn.BatchNorm1d, eps=1e-3, momentum=0.01)
+        self.sparse_shape = [int(v) for v in (np.asarray(grid_size)[::-1] + [1, 0, 0])]
+        self.conv_input = spconv.SparseSequential(
+            spconv.SubMConv3d(input_channels, 16, 3, padding=1, bias=False, indice_key='subm1'), norm_fn(16), nn.ReLU())
+        block = post_act_block
+        self.conv1 = spconv.SparseSequential(
+            SparseBasicBlock(16, 16, bias=use_bias, norm_fn=norm_fn, indice_key='res1'),
+            SparseBasicBlock(16, 16, bias=use_bias, norm_fn=norm_fn, indice_key='res1'))
+        self.conv2 = spconv.SparseSequential(
+            block(16, 32, 3, norm_fn=norm_fn, stride=2, padding=1, indice_key='spconv2', conv_type='spconv'),
+            SparseBasicBlock(32, 32, bias=use_bias, norm_fn=norm_fn, indice_key='res2'),
+            SparseBasicBlock(32, 32, bias=use_bias, norm_fn=norm_fn, indice_key='res2'))
+        self.conv3 = spconv.SparseSequential(
+            block(32, 64, 3, norm_fn=norm_fn, stride=2, padding=1, indice_key='spconv3', conv_type='spconv'),
+            SparseBasicBlock(64, 64, bias=use_bias, norm_fn=norm_fn, indice_key='res3'),
+            SparseBasicBlock(64, 64, bias=use_bias, norm_fn=norm_fn, indice_key='res3'))
+        self.conv4 = spconv.SparseSequential(
+            block(64, 128, 3, norm_fn=norm_fn, stride=2, padding=(0, 1, 1), indice_key='spconv4', conv_type='spconv'),
+            SparseBasicBlock(128, 128, bias=use_bias, norm_fn=norm_fn, indice_key='res4'),
+            SparseBasicBlock(128, 128, bias=use_bias, norm_fn=norm_fn, indice_key='res4'))
+        last_pad = self.model_cfg.get('last_pad', 0)
+        self.conv_out = spconv.SparseSequential(
+            spconv.SparseConv3d(128, 128, (3, 1, 1), stride=(2, 1, 1), padding=last_pad, bias=False, indice_key='spconv_down2'),
+            norm_fn(128), nn.ReLU())
+        self.num_point_features = 128
+        self.backbone_channels = {'x_conv1': 16, 'x_conv2': 32, 'x_conv3': 64, 'x_conv4': 128}
+
+    def forward(self, batch_dict):
+        x = self.conv_input(self._input_tensor(batch_dict))
+        x_conv1 = self.conv1(x)
+        x_conv2 = self.conv2(x_conv1)
+        x_conv3 = self.conv3(x_conv2)
+        x_conv4 = self.conv4(x_conv3)
+        out = self.conv_out(x_conv4)
+        return self._publish(batch_dict, out, {'x_conv1': x_conv1, 'x_conv2': x_conv2, 'x_conv3': x_conv3, 'x_conv4': x_conv4})
+
+
+class _VoxelNeXtBasicBlock(SparseBasicBlock):
+    """spconv_backbone_voxelnext.py:30-66 (no `bias` argument: always biased)."""
+
+    def __init__(self, inplanes, planes, stride=1, norm_fn=None, downsample=None, indice_key=None):
+        super().__init__(inplanes, planes, stride=stride, bias=None, norm_fn=norm_fn, downsample=downsample, indice_key=indice_key)
+
+
+class VoxelResBackBone8xVoxelNeXt(_BackboneBase):
+    def __init__(self, model_cfg, input_channels, grid_size, **kwargs):
+        super().__init__()
+        self.model_cfg = _cfg(model_cfg)
+        norm_fn = partial(nn.BatchNorm1d, eps=1e-3, momentum=0.01)
+        ks = self.model_cfg.get('SPCONV_KERNEL_SIZES', [3, 3, 3, 3])
+        ch = self.model_cfg.get('CHANNELS', [16, 32, 64, 128, 128])
+        out_channel = self.model_cfg.get('OUT_CHANNEL', 128)
+        self.sparse_shape = [int(v) for v in (np.asarray(grid_size)[::-1] + [1, 0, 0])]
+        self.conv_input = spconv.SparseSequential(
+            spconv.SubMConv3d(input_channels, ch[0], 3, padding=1, bias=False, indice_key='subm1'), norm_fn(ch[0]), nn.ReLU())
+        block, BB = post_act_block, _VoxelNeXtBasicBlock
+        self.conv1 = spconv.SparseSequential(BB(ch[0], ch[0], norm_fn=norm_fn, indice_key='res1'), BB(ch[0], ch[0], norm_fn=norm_fn, indice_key='res1'))
+        stages = [(ch[0], ch[1], ks[0]), (ch[1], ch[2], ks[1]), (ch[2], ch[3], ks[2]), (ch[3], ch[4], ks[3]), (ch[4], ch[4], ks[3])]
+        for i, (ci, co, k) in enumerate(stages, start=2):
+            setattr(self, f'conv{i}', spconv.SparseSequential(
+                block(ci, co, k, norm_fn=norm_fn, stride=2, padding=int(k // 2), indice_key=f'spconv{i}', conv_type='spconv'),
+                BB(co, co, norm_fn=norm_fn, indice_key=f'res{i}'), BB(co, co, norm_fn=norm_fn, indice_key=f'res{i}')))
+        self.conv_out = spconv.SparseSequential(
+            spconv.SparseConv2d(ch[3], out_channel, 3, stride=1, padding=1, bias=False, indice_key='spconv_down2'),
+            norm_fn(out_channel), nn.ReLU())
+        self.shared_conv = spconv.SparseSequential(
+            spconv.SubMConv2d(out_channel, out_channel, 3, stride=1, padding=1, bias=True), nn.BatchNorm1d(out_channel), nn.ReLU(True))
+        self.forward_ret_dict = {}
+        self.num_point_features = out_channel
+        self.backbone_channels = {'x_conv1': ch[0], 'x_conv2': ch[1], 'x_conv3': ch[2], 'x_conv4': ch[3]}
+
+    def bev_out(self, x_conv):
+        """spconv_backbone_voxelnext.py:149-164: drop z, merge duplicate (b,y,x) rows by summation.  The unique/
+        index_add_ pair is torch plumbing here; the fused CUDA merge is a SURVEY.md 8(a13) follow-up."""
+        features_cat = x_conv.features
+        indices_cat = x_conv.indices[:, [0, 2, 3]]
+        spatial_shape = x_conv.spatial_shape[1:]
+        indices_unique, _inv = torch.unique(indices_cat, dim=0, return_inverse=True)
+        features_unique = features_cat.new_zeros((indices_unique.shape[0], features_cat.shape[1]))
+        features_unique.index_add_(0, _inv, features_cat)
+        return SparseConvTensor(features=features_unique, indices=indices_unique.int().contiguous(), spatial_shape=spatial_shape,
+                                batch_size=x_conv.batch_size)
+
+    def forward(self, batch_dict):
+        x = self.conv_input(self._input_tensor(batch_dict))
+        x_conv1 = self.conv1(x)
+        x_conv2 = self.conv2(x_conv1)
+        x_conv3 = self.conv3(x_conv2)
+        x_conv4 = self.conv4(x_conv3)
+        x_conv5 = self.conv5(x_conv4)
+        x_conv6 = self.conv6(x_conv5)
+        x_conv5.indices[:, 1:] *= 2
+        x_conv6.indices[:, 1:] *= 4
+        x_conv4 = x_conv4.replace_feature(torch.cat([x_conv4.features, x_conv5.features, x_conv6.features]))
+        x_conv4.indices = torch.cat([x_conv4.indices, x_conv5.indices, x_conv6.indices])
+        out = self.bev_out(x_conv4)
+        out = self.conv_out(out)
+        out = self.shared_conv(out)
+        return self._publish(batch_dict, out, {'x_conv1': x_conv1, 'x_conv2': x_conv2, 'x_conv3': x_conv3, 'x_conv4': x_conv4})
+
+
+# ---------------------------------------------------------------------------------------------------------- VFE
+class MeanVFE(nn.Module):
+    def __init__(self, model_cfg=None, num_point_features=4, **kwargs):
+        super().__init__()
+        self.model_cfg = _cfg(model_cfg)
+        self.num_point_features = num_point_features
+
+    def get_output_feature_dim(self):
+        return self.num_point_features
+
+    def forward(self, batch_dict, **kwargs):
+        voxels, num = batch_dict['voxels'], batch_dict['voxel_num_points']
+        if num.dtype not in (torch.float32, torch.int32):
+            num = num.int()
+        batch_dict['voxel_features'] = ops.mean_vfe(voxels.contiguous(), num.contiguous())
+        return batch_dict
+
+
+class DynamicMeanVFE(nn.Module):
+    """No caps, mean over all points of a voxel.  Output order is first-touch (the reference's torch.unique order is
+    key-sorted; compare as sets)."""
+
+    def __init__(self, model_cfg=None, num_point_features=4, voxel_size=None, grid_size=None, point_cloud_range=None, **kwargs):
+        super().__init__()
+        self.model_cfg = _cfg(model_cfg)
+        self.num_point_features = num_point_features
+        self.voxel_size = [float(v) for v in voxel_size]
+        self.grid_size = [int(v) for v in grid_size]
+        self.point_cloud_range = [float(v) for v in point_cloud_range]
+
+    def get_output_feature_dim(self):
+        return self.num_point_features
+
+    @torch.no_grad()
+    def forward(self, batch_dict, **kwargs):
+        points = batch_dict['points'].contiguous()
+        cap = int(batch_dict.get('max_voxels', points.shape[0]))
+        feats, coords, npts, n_dev, table = ops.voxelize_mean(points, self.point_cloud_range, self.voxel_size, self.grid_size,
+                                                              batch_dict['batch_size'], 0, max(cap, 1))
+        n = int(n_dev[0].item())
+        batch_dict['voxel_features'] = feats[:n]
+        batch_dict['voxel_coords'] = coords[:n]
+        return batch_dict
+
+
+class VoxelGeneratorWrapper:
+    """GPU counterpart of pcdet/datasets/processor/data_processor.py:16-61 (same ctor keywords, `generate(points)`
+    returns (voxel mean features, zyx coordinates, num_points) for ONE frame; the (V,T,F) padded tensor is never
+    materialised because MeanVFE is fused)."""
+
+    def __init__(self, vsize_xyz, coors_range_xyz, num_point_features, max_num_points_per_voxel, max_num_voxels):
+        self.vsize, self.range = [float(v) for v in vsize_xyz], [float(v) for v in coors_range_xyz]
+        self.nfeat, self.max_pts, self.max_voxels = int(num_point_features), int(max_num_points_per_voxel), int(max_num_voxels)
+        r = np.asarray(self.range, dtype=np.float64)
+        self.grid = np.round((r[3:6] - r[0:3]) / np.asarray(self.vsize, dtype=np.float64)).astype(np.int64).tolist()
+
+    def generate(self, points: torch.Tensor):
+        feats, coords, npts, n_dev, _ = ops.voxelize_mean(points.contiguous(), self.range, self.vsize, self.grid, 1, self.max_pts,
+                                                          self.max_voxels, has_batch_col=False, n_feat=self.nfeat)
+        n = int(n_dev[0].item())
+        return feats[:n], coords[:n, 1:], npts[:n]
+
+
+# ---------------------------------------------------------------------------------------------------------- BEV
+class HeightCompression(nn.Module):
+    def __init__(self, model_cfg, **kwargs):
+        super().__init__()
+        self.model_cfg = _cfg(model_cfg)
+        self.num_bev_features = self.model_cfg.NUM_BEV_FEATURES
+
+    def forward(self, batch_dict):
+        t = batch_dict['encoded_spconv_tensor']
+        spatial_features = t.dense()
+        N, C, D, H, W = spatial_features.shape
+        batch_dict['spatial_features'] = spatial_features.view(N, C * D, H, W)
+        batch_dict['spatial_features_stride'] = batch_dict['encoded_spconv_tensor_stride']
+        return batch_dict

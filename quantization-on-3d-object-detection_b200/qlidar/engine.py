@@ -1,0 +1,405 @@
+"""Sync-free, CUDA-graph-captured schedule of the whole hot path:
+
+    points (P, 1+F) --voxelize+meanVFE--> stem --> [rulebook, fused conv]* --> BEV densify --> spatial_features
+
+built from an (optionally q_conv3d-quantised) VoxelResBackBone8x / VoxelBackBone8x module tree.  Row counts never
+leave the device (every kernel takes a capacity + a device-side count), buffers are allocated once, BatchNorm is
+folded into the conv epilogue, and the ~45 launches of one forward replay as one graph.
+
+Reference schedule being replaced: Detector.forward's module loop (pcdet/models/detectors/centerpoint.py:9-11)
+over MeanVFE (mean_vfe.py:25-29), VoxelResBackBone8x.forward (spconv_backbone.py:243-295; per conv QConvNd.forward,
+quant/quant.py:36-58, then BatchNorm1d/ReLU/add as separate ATen kernels) and HeightCompression
+(height_compression.py:20-24), with voxelisation done on the CPU by DataLoader workers (data_processor.py:151-153)."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import QlidarError
+from .quant import QConvNd
+from .sparse import SparseConvolution, SparseSequential, SparseConvTensor, _round_up
+from .backbones import SparseBasicBlock
+
+
+@dataclass
+class Layer:
+    name: str
+    kind: str                      # 'stem' | 'f16' | 'i8' | 'cw'
+    cin: int
+    cout: int
+    ksize: tuple
+    stride: tuple
+    pad: tuple
+    subm: bool
+    relu: bool
+    residual: bool                 # add the block input (SparseBasicBlock.forward, spconv_backbone.py:64)
+    block_input: bool              # this layer's input is a block input (keep it for the residual)
+    tap: Optional[str] = None      # publish the output as multi_scale_3d_features[tap]
+    w: Optional[torch.Tensor] = None
+    scale: Optional[torch.Tensor] = None
+    shift: Optional[torch.Tensor] = None
+    act_bits: int = 16
+    act_amax: Optional[torch.Tensor] = None      # calibrated amax (static mode) or None (dynamic)
+    stage_in: int = 0
+    stage_out: int = 0
+    rb_key: tuple = ()
+    out: Optional[torch.Tensor] = None
+    q_buf: Optional[torch.Tensor] = None
+    act_scale: Optional[torch.Tensor] = None
+    in_absmax: Optional[torch.Tensor] = None
+    out_absmax: Optional[torch.Tensor] = None
+
+
+@dataclass
+class Stage:
+    grid: tuple                    # (B, D, H, W)
+    cap: int
+    coords: Optional[torch.Tensor] = None
+    n_dev: Optional[torch.Tensor] = None
+    table: Optional[torch.Tensor] = None
+
+
+def _bn_fold(bn: nn.BatchNorm1d):
+    a = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)      # eps read from the module
+    return a, bn.bias.detach().float() - a * bn.running_mean.detach().float()
+
+
+def _unwrap(m):
+    if isinstance(m, QConvNd):
+        return m.module, m
+    if isinstance(m, SparseConvolution):
+        return m, None
+    raise QlidarError(f"unsupported module in a conv slot: {type(m).__name__}")
+
+
+class BackboneEngine:
+    def __init__(self, backbone: nn.Module, batch_size: int, max_voxels: int, *, max_points: Optional[int] = None,
+                 pc_range=None, voxel_size=None, max_pts_per_voxel: int = 5, n_point_features: Optional[int] = None,
+                 bev: bool = True, bev_dtype=torch.float16, use_graph: bool = True, stage_cap_ratio: float = 1.0, stage_caps=None,
+                 device="cuda"):
+        self.dev = torch.device(device)
+        self.B = int(batch_size)
+        self.max_voxels = int(max_voxels)                 # total over the batch
+        self.max_points = max_points
+        self.pc_range, self.voxel_size, self.max_pts = pc_range, voxel_size, int(max_pts_per_voxel)
+        self.bev, self.bev_dtype, self.use_graph = bev, bev_dtype, use_graph
+        self.sparse_shape = list(backbone.sparse_shape)
+        self.grid_xyz = [self.sparse_shape[2], self.sparse_shape[1], self.sparse_shape[0] - 1]
+        self.layers: List[Layer] = []
+        self.stages: List[Stage] = [Stage((self.B, *self.sparse_shape), self.max_voxels)]
+        self.rulebooks: Dict[tuple, torch.Tensor] = {}
+        self._cap_ratio = stage_cap_ratio
+        self._stage_caps = list(stage_caps) if stage_caps is not None else None
+        self._graph = None
+        self._timing = None
+        self.kernels_per_forward = 0
+        self._compile(backbone)
+        self.nfeat = n_point_features or self.layers[0].cin
+        self._allocate()
+
+    # ------------------------------------------------------------------ compile the module tree into a layer list
+    def _add_conv(self, name, convm, bn, relu, residual=False, block_input=False):
+        conv, qw = _unwrap(convm)
+        if conv.ndim != 3:
+            raise QlidarError("the engine schedules the 3-D backbones; VoxelNeXt's 2-D tail runs through the module path")
+        a, b = _bn_fold(bn)
+        K = int(np.prod(conv.kernel_size))
+        cin, cout = conv.in_channels, conv.out_channels
+        bias = conv.bias.detach().float() if conv.bias is not None else torch.zeros(cout)
+        L = Layer(name=name, kind="f16", cin=cin, cout=cout, ksize=tuple(conv.kernel_size), stride=tuple(conv.stride),
+                  pad=tuple(conv.padding), subm=conv.subm, relu=relu, residual=residual, block_input=block_input)
+        if qw is not None:
+            codes, amax_w, bound = qw.weight_codes()
+            w_scale = (amax_w / bound).cpu()
+            L.act_bits = qw.act_quant.num_bits
+            L.act_amax = None if qw.act_quant.amax is None else qw.act_quant.amax.detach().float().reshape(-1).cpu()
+        else:
+            codes, w_scale = None, torch.ones(cout)
+        if cin < 8:
+            # raw point features must stay fp32 (metres in fp16 lose centimetres): SIMT stem, weights fake-quantised if wrapped
+            if qw is not None and L.act_bits <= 8:
+                raise QlidarError("8-bit activation quantisation of conv_input is served by the module path (QConvNd), not the engine")
+            if cout not in (16, 32):
+                raise QlidarError("stem conv supports 16/32 output channels")
+            wf = conv.weight.detach().float().reshape(cout, K, cin) if codes is None else codes.cpu() * w_scale.view(-1, 1, 1)
+            L.kind = "stem"
+            L.w = wf.permute(1, 2, 0).contiguous().to(self.dev)                       # (K, cin, cout)
+            L.scale = a.cpu().to(self.dev)
+            L.shift = (bias.cpu() * a.cpu() + b.cpu()).to(self.dev)
+        else:
+            if cin % 16 or cout % 16:
+                raise QlidarError("engine layers need channel counts that are multiples of 16")
+            if qw is None or L.act_bits > 8:
+                L.kind = "f16"
+                wt = conv.weight.detach().float().reshape(cout, K, cin).cpu() if codes is None else codes.cpu()
+                L.w = ops.pack_weights(wt.to(torch.float16)).to(self.dev)
+            elif qw.cw or qw.per_row:
+                L.kind = "cw"
+                L.w = ops.pack_weights(codes.cpu().to(torch.float16)).to(self.dev)
+            else:
+                L.kind = "i8"
+                L.w = ops.pack_weights(codes.cpu().to(torch.int8)).to(self.dev)
+            L.scale = (w_scale * a.cpu()).to(self.dev)
+            L.shift = (bias.cpu() * a.cpu() + b.cpu()).to(self.dev)
+        # stage bookkeeping
+        L.stage_in = len(self.stages) - 1
+        if conv.subm:
+            L.stage_out = L.stage_in
+            L.rb_key = ("subm", L.stage_in, L.ksize)
+        else:
+            g = self.stages[-1].grid
+            od, oh, ow = ops.conv_out_shape(g[1:], L.ksize, L.stride, L.pad)
+            cap = max(128, int(self.stages[-1].cap * self._cap_ratio))
+            if self._stage_caps is not None:
+                cap = int(self._stage_caps[len(self.stages)])
+            self.stages.append(Stage((g[0], od, oh, ow), cap))
+            L.stage_out = len(self.stages) - 1
+            L.rb_key = ("strided", L.stage_in, L.ksize, L.stride, L.pad)
+        self.layers.append(L)
+        return L
+
+    def _compile(self, bb):
+        def seq_conv_bn_relu(prefix, seq):
+            mods = list(seq._modules.values())
+            if not (len(mods) == 3 and isinstance(mods[1], nn.BatchNorm1d) and isinstance(mods[2], nn.ReLU)):
+                raise QlidarError(f"{prefix}: expected conv, BatchNorm1d, ReLU")
+            return self._add_conv(prefix + ".0", mods[0], mods[1], True)
+
+        seq_conv_bn_relu("conv_input", bb.conv_input)
+        i = 1
+        while hasattr(bb, f"conv{i}"):
+            top = getattr(bb, f"conv{i}")
+            last = None
+            for cname, child in top._modules.items():
+                p = f"conv{i}.{cname}"
+                if isinstance(child, SparseBasicBlock):
+                    if child.downsample is not None:
+                        raise QlidarError("downsample branches are not used by the reference backbones")
+                    self._add_conv(p + ".conv1", child.conv1, child.bn1, True, block_input=True)
+                    last = self._add_conv(p + ".conv2", child.conv2, child.bn2, True, residual=True)
+                elif isinstance(child, SparseSequential):
+                    last = seq_conv_bn_relu(p, child)
+                else:
+                    raise QlidarError(f"{p}: unsupported child {type(child).__name__}")
+            if i <= 4:
+                last.tap = f"x_conv{i}"
+            i += 1
+        seq_conv_bn_relu("conv_out", bb.conv_out)
+        self.num_convs = len(self.layers)
+
+    # ------------------------------------------------------------------ static buffers
+    def _allocate(self):
+        dev = self.dev
+        z = lambda *s, dt=torch.float16: torch.zeros(s, dtype=dt, device=dev)
+        s0 = self.stages[0]
+        s0.coords = z(s0.cap, 4, dt=torch.int32)
+        s0.n_dev = z(2, dt=torch.int32)
+        self.vox_feats = z(s0.cap, self.nfeat, dt=torch.float32)
+        self.vox_npts = z(s0.cap, dt=torch.int32)
+        if self.max_points is not None:
+            self.points = torch.full((self.max_points, 1 + self.nfeat), 1e30, dtype=torch.float32, device=dev)
+            self.points[:, 0] = 0
+            s0.table = z(ops.hash_capacity(self.max_points), dt=torch.int64)
+            self.vox_ws = z(int(ops.lib().ql_voxelize_workspace_bytes(self.max_points, s0.cap, self.nfeat, self.max_pts)), dt=torch.uint8)
+        else:
+            s0.table = z(ops.hash_capacity(s0.cap), dt=torch.int64)
+        for st in self.stages[1:]:
+            st.coords = z(st.cap, 4, dt=torch.int32)
+            st.n_dev = z(2, dt=torch.int32)
+            st.table = z(ops.hash_capacity(st.cap), dt=torch.int64)
+        self.rb_ws = z(int(ops.lib().ql_rulebook_strided_workspace_bytes(self.max_voxels, 343)), dt=torch.uint8)
+        n_abs = sum(L.cout for L in self.layers) + 256
+        self.absmax_pool = z(n_abs, dt=torch.float32)
+        off = 0
+        prev_absmax = None
+        for L in self.layers:
+            so = self.stages[L.stage_out]
+            if L.rb_key not in self.rulebooks:
+                K = int(np.prod(L.ksize))
+                self.rulebooks[L.rb_key] = z(ops.num_tiles(so.cap), K, ops.TILE_M, dt=torch.int32)
+            L.out = z(so.cap, L.cout)
+            L.out_absmax = self.absmax_pool[off:off + L.cout]
+            off += L.cout
+            L.in_absmax = prev_absmax
+            prev_absmax = L.out_absmax
+            if L.kind == "i8":
+                L.q_buf = z(self.stages[L.stage_in].cap, L.cin, dt=torch.int8)
+                L.act_scale = z(1, dt=torch.float32)
+            elif L.kind == "cw":
+                L.q_buf = z(self.stages[L.stage_in].cap, L.cin)
+            if L.act_amax is not None:
+                L.act_amax = (L.act_amax.expand(L.cin) if L.act_amax.numel() == 1 else L.act_amax).contiguous().to(dev)
+        last = self.stages[-1]
+        if self.bev:
+            B, D, H, W = last.grid
+            self.spatial_features = z(B, self.layers[-1].cout * D, H, W, dt=self.bev_dtype)
+        self._need_absmax = [i for i, L in enumerate(self.layers[:-1])
+                             if self.layers[i + 1].kind in ("i8", "cw") and self.layers[i + 1].act_amax is None]
+
+    # ------------------------------------------------------------------ the schedule
+    def _op(self, label, n_kernels, fn, *a, **kw):
+        """Run one C-ABI op; when timing is on, bracket it with CUDA events on the launching (current) stream."""
+        self.kernels_per_forward += n_kernels
+        if self._timing is None:
+            return fn(*a, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*a, **kw)
+        e1.record()
+        self._timing.append((label, e0, e1))
+        return r
+
+    def _run_backbone(self):
+        built = set()
+        x = self.vox_feats
+        block_in = None
+        if self._need_absmax:
+            self.absmax_pool.zero_()
+        for i, L in enumerate(self.layers):
+            si, so = self.stages[L.stage_in], self.stages[L.stage_out]
+            nbr = self.rulebooks[L.rb_key]
+            if L.rb_key not in built:
+                if L.subm:
+                    self._op("rulebook_subm:" + L.name, 1, ops.rulebook_subm, si.coords, si.n_dev, si.grid, L.ksize, si.table, nbr=nbr)
+                else:
+                    self._op("rulebook_strided:" + L.name, 6, ops.rulebook_strided, si.coords, si.n_dev, si.grid, L.ksize, L.stride, L.pad,
+                             si.table, so.cap, out=(so.coords, so.n_dev, so.table, nbr), workspace=self.rb_ws)
+                built.add(L.rb_key)
+            absmax = L.out_absmax if i in self._need_absmax else None
+            if L.block_input:
+                block_in = x
+            res = block_in if L.residual else None
+            if L.kind == "stem":
+                self._op("stem:" + L.name, 1, ops.stem_conv, x, nbr, so.cap, so.n_dev, L.w, L.scale, L.shift, relu=L.relu, out=L.out, absmax=absmax)
+            elif L.kind == "f16":
+                self._op("conv:" + L.name, 1, ops.spconv_mma, x, nbr, so.cap, so.n_dev, L.cout, L.w, L.scale, L.shift, residual=res,
+                         relu=L.relu, out=L.out, absmax=absmax)
+            elif L.kind == "i8":
+                am = L.act_amax if L.act_amax is not None else L.in_absmax
+                self._op("quantize:" + L.name, 1, ops.quantize_rows, x, am, ops.QL_Q_CODES_PER_TENSOR, L.act_bits, si.n_dev, out=L.q_buf,
+                         act_scale=L.act_scale)
+                self._op("conv:" + L.name, 1, ops.spconv_mma, L.q_buf, nbr, so.cap, so.n_dev, L.cout, L.w, L.scale, L.shift, act_scale=L.act_scale, residual=res,
+                               relu=L.relu, out=L.out, absmax=absmax)
+            elif L.kind == "cw":
+                am = L.act_amax if L.act_amax is not None else L.in_absmax
+                self._op("quantize:" + L.name, 1, ops.quantize_rows, x, am, ops.QL_Q_FAKE_PER_CHANNEL, L.act_bits, si.n_dev, out=L.q_buf)
+                self._op("conv:" + L.name, 1, ops.spconv_mma, L.q_buf, nbr, so.cap, so.n_dev, L.cout, L.w, L.scale, L.shift, residual=res, relu=L.relu, out=L.out,
+                               absmax=absmax)
+            x = L.out
+        if self.bev:
+            last = self.stages[-1]
+            self._op("bev_densify", 1, ops.bev_densify, x, last.table, last.grid, out=self.spatial_features)
+
+    def _run_from_points(self):
+        s0 = self.stages[0]
+        self.kernels_per_forward = 0
+        self._op("voxelize_mean", 7, ops.voxelize_mean, self.points, self.pc_range, self.voxel_size, self.grid_xyz, self.B, self.max_pts, s0.cap,
+                 out=(self.vox_feats, s0.coords, self.vox_npts, s0.n_dev, s0.table), workspace=self.vox_ws)
+        self._run_backbone()
+
+    def _replay(self, fn):
+        if not self.use_graph:
+            fn()
+            return
+        if self._graph is None or self._graph[0] is not fn.__func__:
+            fn()                                                  # warm-up (first-use attribute setup) outside capture
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            self._graph = (fn.__func__, g)
+        self._graph[1].replay()
+
+    # ------------------------------------------------------------------ public entry points
+    def set_points(self, points: torch.Tensor):
+        """Copy a collated (P, 1+F) fp32 point array (host or device) into the static input buffer; rows past P are
+        parked outside the point-cloud range so the voxeliser skips them."""
+        if self.max_points is None:
+            raise QlidarError("engine was built without max_points")
+        P = points.shape[0]
+        if P > self.max_points:
+            raise QlidarError("more points than max_points")
+        self.points[:P].copy_(points, non_blocking=True)
+        if P < self.max_points:
+            self.points[P:, 1:4] = 1e30
+
+    def forward_points(self, points: Optional[torch.Tensor] = None):
+        if points is not None:
+            self.set_points(points)
+        self._replay(self._run_from_points)
+        return self.outputs()
+
+    def forward_voxels(self, voxel_features: torch.Tensor, voxel_coords: torch.Tensor):
+        """batch_dict-style entry: already voxelised input (voxel_features (V,F) fp32, voxel_coords (V,4) int32/float)."""
+        s0 = self.stages[0]
+        V = voxel_features.shape[0]
+        if V > s0.cap:
+            raise QlidarError("more voxels than the engine capacity")
+        self.vox_feats[:V].copy_(voxel_features)
+        s0.coords[:V].copy_(voxel_coords.int() if voxel_coords.dtype != torch.int32 else voxel_coords)
+        s0.n_dev.fill_(V)
+        ops.hash_build(s0.coords, s0.n_dev, s0.grid, table=s0.table)
+        self._replay(self._run_backbone)
+        return self.outputs()
+
+    def outputs(self):
+        out = {"stage_counts": [st.n_dev for st in self.stages], "encoded_features": self.layers[-1].out,
+               "encoded_coords": self.stages[-1].coords, "encoded_grid": self.stages[-1].grid}
+        if self.bev:
+            out["spatial_features"] = self.spatial_features
+        out["taps"] = {L.tap: (L.out, self.stages[L.stage_out]) for L in self.layers if L.tap}
+        return out
+
+    def counts(self) -> List[int]:
+        return [int(v) for v in torch.stack([st.n_dev for st in self.stages])[:, 0].cpu().tolist()]
+
+    def overflowed(self) -> bool:
+        """True when a stage found more active sites than its capacity (rows were dropped): raise the capacities."""
+        c = torch.stack([st.n_dev for st in self.stages]).cpu()
+        return bool((c[:, 1] > c[:, 0]).any().item())
+
+    def profile_ops(self, from_points: bool = True, iters: int = 5, flush=None):
+        """Eager (no graph) passes with every op bracketed by CUDA events on the launching stream.  A long spin kernel is
+        queued first so the CPU enqueues the whole pass while the GPU is busy and the events see back-to-back execution.
+        Returns {label: mean milliseconds}."""
+        acc: Dict[str, float] = {}
+        order: List[str] = []
+        for it in range(iters + 1):
+            if flush is not None:
+                flush()
+            self._timing = []
+            torch.cuda._sleep(int(3e7))
+            (self._run_from_points if from_points else self._run_backbone)()
+            torch.cuda.synchronize()
+            if it > 0:                                   # first pass is a warm-up
+                for label, e0, e1 in self._timing:
+                    if label not in acc:
+                        acc[label] = 0.0
+                        order.append(label)
+                    acc[label] += e0.elapsed_time(e1) / iters
+            self._timing = None
+        return {k: acc[k] for k in order}
+
+    # ------------------------------------------------------------------ accounting for the roofline report
+    def layer_accounting(self):
+        """Algorithmic bytes / flops per launch: call after a forward; reads counts and pair counts back."""
+        counts = self.counts()
+        acct = []
+        pairs = {k: int((v >= 0).sum().item()) for k, v in self.rulebooks.items()}
+        for L in self.layers:
+            n_in, n_out = counts[L.stage_in], counts[L.stage_out]
+            K = int(np.prod(L.ksize))
+            tiles = ops.num_tiles(n_out)
+            # rows past n_out in the last tile are -1 already; tiles past the live count hold stale data -> recount live ones
+            P = int((self.rulebooks[L.rb_key][:tiles] >= 0).sum().item())
+            b_act = 4 if L.kind == "stem" else (1 if L.kind == "i8" else 2)
+            b_w = 4 if L.kind == "stem" else (1 if L.kind == "i8" else 2)
+            by = n_in * L.cin * b_act + n_out * L.cout * 2 + K * L.cin * L.cout * b_w + 4 * P + (n_out * L.cout * 2 if L.residual else 0)
+            acct.append(dict(name=L.name, kind=L.kind, n_in=n_in, n_out=n_out, pairs=P, cin=L.cin, cout=L.cout, K=K,
+                             bytes_alg=by, flops_alg=2 * P * L.cin * L.cout, rulebook_bytes_read=tiles * K * 512))
+        return acct

@@ -73,7 +73,7 @@ def hash_build(coords: torch.Tensor, n_dev: Optional[torch.Tensor], grid: Sequen
 def voxelize_mean(points: torch.Tensor, pc_range, voxel_size, grid_xyz, batch_size: int, max_pts: int, max_voxels: int,
                   has_batch_col: bool = True, n_feat: Optional[int] = None, out=None, workspace=None):
     """Fused hard voxelization + mean VFE (+ DynamicMeanVFE semantics when max_pts == 0).
-    Returns (feats [max_voxels,F] f32, coords [max_voxels,4] i32, npts [max_voxels] i32, n_dev [1] i32, table)."""
+    Returns (feats [max_voxels,F] f32, coords [max_voxels,4] i32, npts [max_voxels] i32, n_dev [2] i32 = (kept, found), table)."""
     _need_cuda(points)
     if points.dtype != torch.float32 or points.dim() != 2:
         raise QlidarError("points must be a float32 (P, stride) tensor")
@@ -84,7 +84,7 @@ def voxelize_mean(points: torch.Tensor, pc_range, voxel_size, grid_xyz, batch_si
         feats = torch.empty((max_voxels, F), dtype=torch.float32, device=dev)
         coords = torch.empty((max_voxels, 4), dtype=torch.int32, device=dev)
         npts = torch.empty((max_voxels,), dtype=torch.int32, device=dev)
-        n_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
+        n_dev = torch.zeros((2,), dtype=torch.int32, device=dev)
         table = torch.empty(hash_capacity(max(P, 1)), dtype=torch.int64, device=dev)
     else:
         feats, coords, npts, n_dev, table = out
@@ -128,7 +128,7 @@ def rulebook_subm(coords: torch.Tensor, n_dev: Optional[torch.Tensor], grid, ksi
 
 def rulebook_strided(coords: torch.Tensor, n_in_dev: Optional[torch.Tensor], grid, ksize, stride, pad, in_table: torch.Tensor,
                      n_out_cap: int, out=None, workspace=None):
-    """Returns (out_coords [n_out_cap,4], n_out_dev [1], out_table, nbr [tiles,K,128], out_grid (B,D,H,W))."""
+    """Returns (out_coords [n_out_cap,4], n_out_dev [2] = (kept, found), out_table, nbr [tiles,K,128], out_grid (B,D,H,W))."""
     _need_cuda(coords, n_in_dev, in_table)
     k, s, p = triple(ksize), triple(stride), triple(pad)
     K = k[0] * k[1] * k[2]
@@ -138,7 +138,7 @@ def rulebook_strided(coords: torch.Tensor, n_in_dev: Optional[torch.Tensor], gri
     od, oh, ow = conv_out_shape((D, H, W), k, s, p)
     if out is None:
         out_coords = torch.empty((n_out_cap, 4), dtype=torch.int32, device=dev)
-        n_out_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
+        n_out_dev = torch.zeros((2,), dtype=torch.int32, device=dev)
         out_table = torch.empty(hash_capacity(n_out_cap), dtype=torch.int64, device=dev)
         nbr = torch.empty((num_tiles(n_out_cap), K, TILE_M), dtype=torch.int32, device=dev)
     else:

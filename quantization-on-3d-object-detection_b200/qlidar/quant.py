@@ -1,0 +1,179 @@
+"""Drop-in mirror of the reference's 3-D quantisation API -- QConvNd (quant/quant.py:6-58; variants QConv3d/QConv2d
+quant/quant_voxelnext.py:75-115,138-169; GQConv3d quant/quant_conv3d.py:70-138), q_conv3d, collect_stats, compute_amax
+(quant/quantize.py:13-43,175-207) -- executing REAL integer kernels instead of fake-quant around fp32 spconv.
+
+Mode selection per wrapper:
+  act_bits <= 8, cw=False : W8A8-pt  int8 codes x int8 codes -> INT32 (tcgen05 kind::i8), dequant in the epilogue
+  act_bits <= 8, cw=True  : W8A8-cw  per-input-channel fake-quant (does not factor out of the sum): fp16 fake-quant
+                                      rows x exact int8-code weights (tcgen05 kind::f16, fp32 accumulate)
+  act_bits  > 8           : W8A16    fp16 rows (int16 grid vs fp16 grid differ by <= 2^-11 relative) x int8-code weights
+  per_row=True            : GQConv3d per-voxel-row amax, same kernel as cw
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .sparse import (SparseConvolution, SparseConvTensor, SparseModule, SubMConv3d, SparseConv3d, SubMConv2d, SparseConv2d,
+                     _make_output, _round_up)
+from .tensor_quant import QuantDescriptor, TensorQuantizer, reduce_amax
+
+
+class QConvNd(SparseModule):
+    """Channel-wise Quant Module for SubMConvNd & SparseConvNd (same ctor and attributes as quant/quant.py:6-34)."""
+
+    def __init__(self, module: SparseConvolution, w_bits: int, act_bits: int, cw: bool, per_row: bool = False):
+        super().__init__()
+        self.module = module
+        self.w = self.module.weight.data.clone()
+        self.w_quant = TensorQuantizer(QuantDescriptor(num_bits=w_bits, axis=(0)))
+        self.act_quant = TensorQuantizer(QuantDescriptor(num_bits=act_bits, axis=(1)) if cw else QuantDescriptor(num_bits=act_bits))
+        self.cw = bool(cw)
+        self.per_row = bool(per_row)
+        self._cache = {}
+
+    # ---- weights: per-output-channel codes (QuantDescriptor(axis=(0)) on (oc, ic*K), quant/quant.py:14-18,42-44) ----
+    def weight_codes(self):
+        """(codes (oc, K, ic) float, amax_w (oc,)) -- codes are integers in [-bound, bound]."""
+        wt = self.module.weight.detach()
+        oc, ic = wt.shape[0], wt.shape[-1]
+        wm = wt.reshape(oc, -1, ic).float()
+        amax = self.w_quant.amax.view(-1).to(wm.device) if self.w_quant.amax is not None else wm.abs().amax(dim=(1, 2))
+        bound = float(2 ** (self.w_quant.num_bits - 1) - 1)
+        tiny = amax <= (1.0 / (1 << 24))
+        scale = torch.where(tiny, torch.zeros_like(amax), bound / torch.where(tiny, torch.ones_like(amax), amax))
+        codes = torch.round(wm * scale.view(-1, 1, 1)).clamp_(-bound, bound)
+        return codes, amax, bound
+
+    def _prepared(self, dev, kind: str):
+        wt = self.module.weight
+        key = (wt._version, wt.data_ptr(), str(dev), kind, self.w_quant.num_bits, None if self.w_quant.amax is None else self.w_quant.amax.sum().item())
+        hit = self._cache.get(kind)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        codes, amax, bound = self.weight_codes()
+        oc, K, ic = codes.shape
+        ic_p = _round_up(ic, 16 if kind == "i8" else 8)
+        oc_p = _round_up(oc, 16)
+        w = torch.zeros((oc_p, K, ic_p), dtype=torch.int8 if kind == "i8" else torch.float16)
+        w[:oc, :, :ic] = codes.to(w.dtype).cpu()
+        packed = ops.pack_weights(w).to(dev)
+        w_scale = torch.zeros(oc_p, dtype=torch.float32, device=dev)
+        w_scale[:oc] = (amax / bound).to(dev)                           # de-quantisation scale amax_w[oc] / bound
+        shift = torch.zeros(oc_p, dtype=torch.float32, device=dev)
+        if self.module.bias is not None:
+            shift[:oc] = self.module.bias.detach().float().to(dev)
+        val = (packed, ic_p, oc_p, w_scale, shift)
+        self._cache[kind] = (key, val)
+        return val
+
+    def _act_absmax(self, f: torch.Tensor, n_dev) -> torch.Tensor:
+        """Per-channel |x| max vector feeding the quantise kernel: calibrated `_amax` if present, else dynamic."""
+        c = f.shape[1]
+        a = self.act_quant.amax
+        if a is not None:
+            a = a.to(f.device).float().reshape(-1)
+            return (a.expand(c) if a.numel() == 1 else a).contiguous()
+        return ops.absmax_cols(f, n_dev)
+
+    def forward(self, x: SparseConvTensor) -> SparseConvTensor:
+        conv = self.module
+        aq = self.act_quant
+        if aq._if_calib:                                             # collect_stats: MaxCalibrator running max
+            am = ops.absmax_cols(x.features.contiguous(), x._n_dev)
+            aq._calibrator.collect(am.view(1, -1) if self.cw else am.max().view(()))  # noqa: the calibrator sees reduced maxima
+        if aq._disabled or not aq._if_quant:
+            return conv(x)                                           # quantisers off (calibration pass): plain conv
+        rb = conv.get_rulebook(x)
+        f = x.features
+        in_dtype = f.dtype
+        f = (f if f.dtype in (torch.float16, torch.float32) else f.float()).contiguous()
+        bits = aq.num_bits
+        out_dtype = torch.float32 if in_dtype == torch.float32 else torch.float16
+        n_dev = x._n_dev
+        if bits <= 8 and not self.cw and not self.per_row:
+            packed, ic_p, oc_p, w_scale, shift = self._prepared(f.device, "i8")
+            q, act_scale = ops.quantize_rows(f, self._act_absmax(f, n_dev), ops.QL_Q_CODES_PER_TENSOR, bits, n_dev)
+            if ic_p != conv.in_channels:
+                q = torch.nn.functional.pad(q, (0, ic_p - conv.in_channels)).contiguous()
+            y = ops.spconv_mma(q, rb.nbr, rb.n_out, rb.n_out_dev, oc_p, packed, w_scale, shift, act_scale=act_scale, out_dtype=out_dtype)
+        else:
+            packed, ic_p, oc_p, w_scale, shift = self._prepared(f.device, "f16")
+            if bits > 8:
+                fh = f if f.dtype == torch.float16 else f.half()
+            elif self.per_row:
+                fh, _ = ops.quantize_rows(f, None, ops.QL_Q_FAKE_PER_ROW, bits, n_dev)
+            else:
+                fh, _ = ops.quantize_rows(f, self._act_absmax(f, n_dev), ops.QL_Q_FAKE_PER_CHANNEL, bits, n_dev)
+            if ic_p != conv.in_channels:
+                fh = torch.nn.functional.pad(fh, (0, ic_p - conv.in_channels))
+            y = ops.spconv_mma(fh.contiguous(), rb.nbr, rb.n_out, rb.n_out_dev, oc_p, packed, w_scale, shift, out_dtype=out_dtype)
+        if oc_p != conv.out_channels:
+            y = y[:, :conv.out_channels].contiguous()
+        return _make_output(x, rb, y, conv.ndim)
+
+
+class QConv3d(QConvNd):
+    """quant/quant_voxelnext.py:75-115 (identical to QConvNd for 3-D convs)."""
+
+
+class QConv2d(QConvNd):
+    """quant/quant_voxelnext.py:138-169 for SubMConv2d/SparseConv2d.  The reference forgets to `replace_feature` the
+    quantised activations; this mirror implements the evident intent (per-tensor act quant)."""
+
+    def __init__(self, module, w_bits, act_bits):
+        super().__init__(module, w_bits, act_bits, cw=False)
+
+
+class GQConv3d(QConvNd):
+    """quant/quant_conv3d.py:70-138: per-voxel-row activation amax (axis=0 on <=64-row groups; grouping does not
+    change the values).  The reference writes the fake-quantised rows back in place (a bug); not mirrored."""
+
+    def __init__(self, module, w_bits=8, act_bits=8, n=64):
+        super().__init__(module, w_bits, act_bits, cw=False, per_row=True)
+        self.n = n
+
+
+def q_conv3d(model, module_dict, curr_path, w_bits, act_bits, cw, src, no_list) -> None:
+    """quant/quantize.py:13-43: recursive named_children walk; swap `src` instances whose dotted path is not in no_list."""
+    for name, module in model.named_children():
+        path = f"{curr_path}.{name}" if curr_path else name
+        q_conv3d(module, module_dict, path, w_bits, act_bits, cw, src, no_list)
+        if isinstance(module, src) and path not in no_list:
+            model._modules[name] = QConvNd(module=module, w_bits=w_bits, act_bits=act_bits, cw=cw)
+    return
+
+
+def collect_stats(model, data_loader, n_batches=200, to_device=None):
+    """quant/quantize.py:175-194 (including its `i > n_batches` break, i.e. n_batches + 2 batches)."""
+    model.eval()
+    for name, module in model.named_modules():
+        if name.endswith("_quantizer") or name.endswith("_quant"):
+            module.enable_calib()
+            module.disable_quant()
+    with torch.no_grad():
+        for i, batch_dict in enumerate(data_loader):
+            if to_device is not None:
+                to_device(batch_dict)
+            model(batch_dict)
+            if i > n_batches:
+                break
+    for name, module in model.named_modules():
+        if name.endswith("_quantizer") or name.endswith("_quant"):
+            module.disable_calib()
+            module.enable_quant()
+    return
+
+
+def compute_amax(model, device, **kwargs):
+    """quant/quantize.py:198-207."""
+    for _, module in model.named_modules():
+        if isinstance(module, TensorQuantizer):
+            if module._calibrator is not None:
+                module.load_calib_amax(strict=False)
+                if module.amax is not None:
+                    module._amax = module._amax.to(device)
+    return

@@ -219,7 +219,7 @@ class SparseConvolution(SparseModule):
                 per_in *= -(-k[d] // s[d])
             cap = max(1, min(n * per_in, grid[0] * od * oh * ow))
             out_c, n_out_dev, out_table, nbr, ogrid = ops.rulebook_strided(idx4, x._n_dev, grid, k, s, p, x.table(), cap)
-            n_out = int(n_out_dev.item())          # module API returns exact shapes (one sync per strided rulebook)
+            n_out = int(n_out_dev[0].item())          # module API returns exact shapes (one sync per strided rulebook)
             out_c = out_c[:n_out]
             nbr = nbr[:ops.num_tiles(max(n_out, 1))]
             out_idx = out_c if self.ndim == 3 else out_c[:, [0, 2, 3]].contiguous()

@@ -1,0 +1,239 @@
+"""GPU parity of the drop-in module API and of the graph-captured engine against the CPU oracle's restatement of
+VoxelResBackBone8x / VoxelBackBone8x / QConvNd (fp32 fake-quant "reference math").
+
+Tolerance (north star): de-quantised features max-abs error <= 1e-2 * max|ref| per tensor; coordinates bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import qlidar_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-2
+# Whole-network runs with 8-bit ACTIVATION quantisation are chaotic at the code level: an fp16-vs-fp32 difference of
+# 1e-4 in a layer input flips a few round-half-even decisions, each flip moves that activation by amax/127 (0.8 %),
+# and 20 stacked layers amplify it.  Layer-level parity (teacher forced, same inputs) is held to 2e-3 and the INT32
+# accumulators to bit-exactness elsewhere in this file; every one of the 21 layers is
+# additionally checked teacher-forced (test_every_backbone_layer_teacher_forced); end to end we bound max-abs by 1e-1 and
+# mean-abs by 5e-3 of max|ref|.
+TOL_A8_MAX, TOL_A8_MEAN = 1e-1, 5e-3
+
+
+def check_feats(got, ref, a8):
+    e = (got.double().cpu() - ref.double()).abs()
+    m = max(ref.abs().max().item(), 1e-12)
+    if a8:
+        assert e.max().item() / m <= TOL_A8_MAX and e.mean().item() / m <= TOL_A8_MEAN, (e.max().item() / m, e.mean().item() / m)
+    else:
+        assert e.max().item() / m <= TOL, e.max().item() / m
+
+
+def rel_err(got: torch.Tensor, ref: torch.Tensor) -> float:
+    return (got.double().cpu() - ref.double()).abs().max().item() / max(ref.abs().max().item(), 1e-12)
+
+
+def make_frame(cfg="kitti", batch=1, **kw):
+    c = O.CONFIGS[cfg]
+    kw = kw or (dict(n_az=300) if cfg == "kitti" else dict(n_beams=24, n_az=500))
+    pts = O.synth_batch(cfg, batch, **kw)
+    feats, coords, _ = O.voxelize_mean_batch(pts, c["pc_range"], c["voxel_size"], c["max_pts"], c["max_voxels"])
+    grid = O.grid_size_xyz(c["pc_range"], c["voxel_size"])
+    return pts, torch.from_numpy(feats), coords, grid, c
+
+
+def build(arch, nfeat, grid, seed=4, **cfg):
+    import qlidar
+    prog = O.backbone_specs(arch, nfeat, cfg.get("CHANNELS"), cfg.get("SPCONV_KERNEL_SIZES"), cfg.get("OUT_CHANNEL"))
+    P = O.init_params(prog, seed)
+    bb = getattr(qlidar, arch)(cfg, nfeat, np.asarray(grid))
+    missing, unexpected = bb.load_state_dict(P, strict=False)
+    assert not unexpected and all(k.endswith("num_batches_tracked") for k in missing), (missing, unexpected)
+    return prog, P, bb.cuda().eval()
+
+
+def batch_dict(feats, coords, batch):
+    # load_data_to_gpu casts every array, coords included, to float32 (pcdet/models/__init__.py:36)
+    return {"voxel_features": feats.cuda(), "voxel_coords": torch.from_numpy(coords).float().cuda(), "batch_size": batch}
+
+
+@pytest.mark.parametrize("arch", ["VoxelResBackBone8x", "VoxelBackBone8x"])
+def test_module_path_unquantized(arch):
+    _, feats, coords, grid, c = make_frame("kitti")
+    prog, P, bb = build(arch, 4, grid)
+    ref, taps = O.backbone_forward(prog, P, feats, coords, O.sparse_shape_zyx(grid), 1)
+    with torch.no_grad():
+        out = bb(batch_dict(feats, coords, 1))
+    enc = out["encoded_spconv_tensor"]
+    assert np.array_equal(enc.indices.cpu().numpy(), ref.coords)
+    assert enc.spatial_shape == ref.spatial_shape
+    assert rel_err(enc.features, ref.features) <= TOL
+    for k, t in taps.items():
+        got = out["multi_scale_3d_features"][k]
+        assert np.array_equal(got.indices.cpu().numpy(), t.coords)
+        assert rel_err(got.features, t.features) <= TOL
+    assert out["encoded_spconv_tensor_stride"] == 8
+
+
+@pytest.mark.parametrize("w_bits,act_bits,cw", [(8, 8, False), (8, 8, True), (8, 16, False), (8, 16, True), (4, 8, False)])
+def test_qconvnd_single_layer_matches_reference_math(w_bits, act_bits, cw):
+    """QConvNd(module, w_bits, act_bits, cw) on one SubMConv3d/SparseConv3d vs quant/quant.py:36-58 restated in fp32."""
+    import qlidar
+    rng = np.random.default_rng(7)
+    coords = O.synth_surface_sheet(50, seed=11, depth=12)
+    x = torch.from_numpy(rng.normal(size=(coords.shape[0], 32)).astype(np.float32))
+    x[:, 3] *= 8
+    for subm in (True, False):
+        conv = (qlidar.SubMConv3d(32, 64, 3, padding=1, bias=True, indice_key="k") if subm
+                else qlidar.SparseConv3d(32, 64, 3, stride=2, padding=1, bias=True, indice_key="k")).cuda()
+        q = qlidar.QConvNd(conv, w_bits, act_bits, cw)
+        w, b = conv.weight.detach().cpu(), conv.bias.detach().cpu()
+        if subm:
+            nbr, oc = O.rulebook_subm(coords, [12, 50, 50], 3), coords
+        else:
+            oc, _, nbr = O.rulebook_strided(coords, [12, 50, 50], 3, 2, 1)
+        ref = O.qconv_reference_math(x, nbr, w, b, w_bits, act_bits, cw)
+        st = qlidar.SparseConvTensor(x.cuda(), torch.from_numpy(coords).cuda(), [12, 50, 50], 1)
+        w_before = conv.weight.detach().clone()
+        with torch.no_grad():
+            y = q(st)
+        assert torch.equal(conv.weight.detach(), w_before)            # the wrapper must not alter module.weight
+        assert np.array_equal(y.indices.cpu().numpy(), oc)
+        assert rel_err(y.features, ref) <= 2e-3, (subm, rel_err(y.features, ref))
+
+
+def test_gqconv3d_per_row():
+    import qlidar
+    rng = np.random.default_rng(8)
+    coords = O.synth_surface_sheet(40, seed=12, depth=12)
+    x = torch.from_numpy(rng.normal(size=(coords.shape[0], 16)).astype(np.float32))
+    conv = qlidar.SubMConv3d(16, 16, 3, padding=1, bias=False, indice_key="k").cuda()
+    nbr = O.rulebook_subm(coords, [12, 40, 40], 3)
+    w = conv.weight.detach().cpu()
+    wq = O.weight_from_matrix(O.fake_quant(O.weight_matrix(w), 8, axis=0), w)
+    ref = O.sparse_conv(O.fake_quant(x, 8, axis=0), nbr, wq)          # quant_conv3d.py:112-131: amax per voxel row
+    with torch.no_grad():
+        y = qlidar.GQConv3d(conv)(qlidar.SparseConvTensor(x.cuda(), torch.from_numpy(coords).cuda(), [12, 40, 40], 1))
+    assert rel_err(y.features, ref) <= 2e-3
+
+
+@pytest.mark.parametrize("w_bits,act_bits,cw,mode", [(8, 8, False, "ref"), (8, 8, True, "ref"), (8, 16, True, "ref")])
+def test_q_conv3d_surgery_whole_backbone(w_bits, act_bits, cw, mode):
+    """quant_centerpoint.quant(): q_conv3d over the backbone, conv_input.0 in the no_list when sq (=cw) is on."""
+    import qlidar
+    _, feats, coords, grid, c = make_frame("kitti")
+    prog, P, bb = build("VoxelResBackBone8x", 4, grid)
+    no_list = ["conv_input.0"] if cw else []
+    qlidar.q_conv3d(bb, {}, "", w_bits, act_bits, cw, (qlidar.SubMConv3d, qlidar.SparseConv3d), no_list)
+    n_wrapped = sum(isinstance(m, qlidar.QConvNd) for m in bb.modules())
+    assert n_wrapped == (20 if cw else 21)
+    ref, _ = O.backbone_forward(prog, P, feats, coords, O.sparse_shape_zyx(grid), 1,
+                                O.QuantCfg(mode=mode, w_bits=w_bits, act_bits=act_bits, cw=cw, no_list=tuple(no_list)))
+    with torch.no_grad():
+        out = bb(batch_dict(feats, coords, 1))
+    enc = out["encoded_spconv_tensor"]
+    assert np.array_equal(enc.indices.cpu().numpy(), ref.coords)
+    check_feats(enc.features, ref.features, act_bits <= 8)
+
+
+def test_height_compression_module():
+    import qlidar
+    _, feats, coords, grid, c = make_frame("kitti")
+    prog, P, bb = build("VoxelResBackBone8x", 4, grid)
+    ref, _ = O.backbone_forward(prog, P, feats, coords, O.sparse_shape_zyx(grid), 1)
+    with torch.no_grad():
+        bd = bb(batch_dict(feats, coords, 1))
+        bd = qlidar.HeightCompression(qlidar.Cfg(NUM_BEV_FEATURES=256))(bd)
+    sf = bd["spatial_features"]
+    ref_bev = O.height_compression(ref.features, ref.coords, ref.spatial_shape, 1)
+    assert tuple(sf.shape) == tuple(ref_bev.shape) == (1, 256, 200, 176)
+    assert rel_err(sf, ref_bev) <= TOL
+    assert torch.equal(sf.cpu() != 0, ref_bev != 0) or ((sf.cpu() != 0) ^ (ref_bev != 0)).float().mean().item() < 1e-3
+
+
+@pytest.mark.parametrize("quant", [None, (8, 16, True), (8, 8, False), (8, 8, True)])
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_engine_from_points_matches_oracle(quant, use_graph):
+    """points -> voxelize+meanVFE -> backbone -> BEV in one graph replay vs the oracle end to end (Waymo-shaped, batch 2)."""
+    import qlidar
+    pts, feats, coords, grid, c = make_frame("waymo", batch=2)
+    prog, P, bb = build("VoxelResBackBone8x", 5, grid)
+    qc = O.QuantCfg()
+    if quant is not None:
+        w_bits, act_bits, cw = quant
+        no_list = ["conv_input.0"]
+        qlidar.q_conv3d(bb, {}, "", w_bits, act_bits, cw, (qlidar.SubMConv3d, qlidar.SparseConv3d), no_list)
+        qc = O.QuantCfg(mode="ref", w_bits=w_bits, act_bits=act_bits, cw=cw, no_list=tuple(no_list))
+    rec = {}
+    ref, taps = O.backbone_forward(prog, P, feats, coords, O.sparse_shape_zyx(grid), 2, qc, rec)
+    eng = qlidar.BackboneEngine(bb, 2, coords.shape[0] + 1000, max_points=pts.shape[0] + 500, pc_range=c["pc_range"],
+                                voxel_size=c["voxel_size"], max_pts_per_voxel=c["max_pts"], use_graph=use_graph, stage_cap_ratio=4.0)
+    for _ in range(2):                                                # second call replays the captured graph
+        out = eng.forward_points(torch.from_numpy(pts))
+    torch.cuda.synchronize()
+    counts = eng.counts()
+    assert not eng.overflowed()
+    assert counts[0] == coords.shape[0] and counts[-1] == ref.coords.shape[0]
+    n = counts[-1]
+    assert np.array_equal(out["encoded_coords"][:n].cpu().numpy(), ref.coords)
+    a8 = quant is not None and quant[1] <= 8
+    check_feats(out["encoded_features"][:n], ref.features, a8)
+    for name, (f, st) in out["taps"].items():
+        m = taps[name].coords.shape[0]
+        assert np.array_equal(st.coords[:m].cpu().numpy(), taps[name].coords)
+        check_feats(f[:m], taps[name].features, a8)
+    ref_bev = O.height_compression(ref.features, ref.coords, ref.spatial_shape, 2)
+    check_feats(out["spatial_features"], ref_bev, a8)
+
+
+def test_engine_int32_accumulators_match_oracle_on_first_quantized_layer():
+    """W8A8-pt: the i8 path's quantised codes and INT32 accumulators are bit-exact when fed identical fp16 features."""
+    import qlidar
+    from qlidar import ops
+    rng = np.random.default_rng(9)
+    coords = O.synth_surface_sheet(60, seed=13, depth=12)
+    x = torch.from_numpy(rng.normal(size=(coords.shape[0], 64)).astype(np.float32)).half()
+    w = torch.from_numpy(rng.normal(size=(64, 3, 3, 3, 64)).astype(np.float32)) * 0.05
+    nbr = O.rulebook_subm(coords, [12, 60, 60], 3)
+    acc_ref, y_ref, amax_x, amax_w = O.qconv_w8a8_pt(x.float(), nbr, w, None)
+    conv = qlidar.SubMConv3d(64, 64, 3, padding=1, bias=False, indice_key="k").cuda()
+    conv.weight.data.copy_(w)
+    q = qlidar.QConvNd(conv, 8, 8, False)
+    packed, ic_p, oc_p, w_scale, shift = q._prepared(torch.device("cuda"), "i8")
+    st = qlidar.SparseConvTensor(x.cuda(), torch.from_numpy(coords).cuda(), [12, 60, 60], 1)
+    rb = conv.get_rulebook(st)
+    codes, act_scale = ops.quantize_rows(x.cuda(), ops.absmax_cols(x.cuda()), ops.QL_Q_CODES_PER_TENSOR)
+    acc = torch.zeros((coords.shape[0], 64), dtype=torch.int32, device="cuda")
+    ops.spconv_mma(codes, rb.nbr, rb.n_out, None, 64, packed, w_scale, shift, out=acc)
+    assert torch.equal(acc.cpu(), acc_ref)
+    with torch.no_grad():
+        y = q(st)
+    assert rel_err(y.features, y_ref) <= 2e-3
+
+
+@pytest.mark.parametrize("w_bits,act_bits,cw", [(8, 8, False), (8, 8, True), (8, 16, True)])
+def test_every_backbone_layer_teacher_forced(w_bits, act_bits, cw):
+    """Each of the 21 VoxelResBackBone8x convs, fed the ORACLE's input for that layer, must reproduce the oracle's
+    QConvNd output (quant/quant.py:36-58 math) to 2e-3 of max|ref| with bit-exact output coordinates."""
+    import qlidar
+    _, feats, coords, grid, c = make_frame("kitti")
+    prog = O.backbone_specs("VoxelResBackBone8x", 4)
+    P = O.init_params(prog)
+    rec = {}
+    O.backbone_forward(prog, P, feats, coords, O.sparse_shape_zyx(grid), 1,
+                       O.QuantCfg(mode="ref", w_bits=w_bits, act_bits=act_bits, cw=cw), rec)
+    worst = 0.0
+    for spec in O.all_conv_specs(prog):
+        x, xc, shape, oc = rec[spec.name + ".in"]
+        cls = qlidar.SubMConv3d if spec.subm else qlidar.SparseConv3d
+        conv = cls(spec.cin, spec.cout, spec.ksize, stride=spec.stride, padding=spec.pad, bias=spec.bias, indice_key="k").cuda()
+        conv.weight.data.copy_(P[spec.name + ".weight"])
+        if spec.bias:
+            conv.bias.data.copy_(P[spec.name + ".bias"])
+        st = qlidar.SparseConvTensor(x.cuda().contiguous(), torch.from_numpy(xc).cuda(), shape, 1)
+        with torch.no_grad():
+            y = qlidar.QConvNd(conv, w_bits, act_bits, cw)(st)
+        assert np.array_equal(y.indices.cpu().numpy(), oc), spec.name
+        e = rel_err(y.features, rec[spec.name])
+        worst = max(worst, e)
+        assert e <= 2e-3, (spec.name, e)

@@ -64,7 +64,8 @@ def test_rulebook_strided_bit_exact(ops, k, s, p):
     table = ops.hash_build(c, None, (B, D, H, W))
     cap = oc_ref.shape[0] + 300
     out_coords, n_out, out_table, nbr, ogrid = ops.rulebook_strided(c, None, (B, D, H, W), k, s, p, table, cap)
-    n = int(n_out.item())
+    n = int(n_out[0].item())
+    assert int(n_out[1].item()) == n
     assert n == oc_ref.shape[0]
     assert list(ogrid[1:]) == list(osh)
     assert np.array_equal(out_coords[:n].cpu().numpy(), oc_ref)          # same first-touch order
@@ -87,7 +88,7 @@ def test_rulebook_strided_overflow_is_safe(ops):
     table = ops.hash_build(c, None, (B, D, H, W))
     cap = oc_ref.shape[0] // 2
     out_coords, n_out, out_table, nbr, ogrid = ops.rulebook_strided(c, None, (B, D, H, W), 3, 2, 1, table, cap)
-    assert int(n_out.item()) == cap
+    assert n_out.tolist() == [cap, oc_ref.shape[0]]                     # (kept, found): overflow is reported
     assert np.array_equal(out_coords.cpu().numpy(), oc_ref[:cap])
     assert nbr.max().item() < coords.shape[0]
 
@@ -102,7 +103,7 @@ def test_voxelize_hard_matches_cpu_voxelizer(ops, cfg, batch):
     f_ref, c_ref, n_ref = O.voxelize_mean_batch(pts, c["pc_range"], c["voxel_size"], c["max_pts"], 10 ** 7)
     cap = c_ref.shape[0] + 100
     feats, coords, npts, n_dev, table = ops.voxelize_mean(dev(pts), c["pc_range"], c["voxel_size"], grid, batch, c["max_pts"], cap)
-    n = int(n_dev.item())
+    n = int(n_dev[0].item())
     assert n == c_ref.shape[0]
     assert np.array_equal(coords[:n].cpu().numpy(), c_ref)               # identical first-touch order
     assert np.array_equal(npts[:n].cpu().numpy(), n_ref)
@@ -120,7 +121,7 @@ def test_voxelize_voxel_cap(ops):
     grid = O.grid_size_xyz(c["pc_range"], c["voxel_size"])
     f_ref, c_ref, n_ref = O.voxelize_mean_batch(pts, c["pc_range"], c["voxel_size"], 3, 1000)
     feats, coords, npts, n_dev, table = ops.voxelize_mean(dev(pts), c["pc_range"], c["voxel_size"], grid, 1, 3, 1000)
-    assert int(n_dev.item()) == 1000 == c_ref.shape[0]
+    assert int(n_dev[0].item()) == 1000 == c_ref.shape[0] and int(n_dev[1].item()) > 1000
     assert np.array_equal(coords.cpu().numpy(), c_ref)
     assert np.array_equal(npts.cpu().numpy(), n_ref)
     np.testing.assert_allclose(feats.cpu().numpy(), f_ref, rtol=1e-6, atol=1e-6)
@@ -132,7 +133,7 @@ def test_voxelize_dynamic_matches_dynamic_mean_vfe(ops):
     grid = O.grid_size_xyz(c["pc_range"], c["voxel_size"])
     f_ref, c_ref, n_ref = O.voxelize_dynamic_mean(pts, c["pc_range"], c["voxel_size"])
     feats, coords, npts, n_dev, _ = ops.voxelize_mean(dev(pts), c["pc_range"], c["voxel_size"], grid, 2, 0, c_ref.shape[0] + 10)
-    n = int(n_dev.item())
+    n = int(n_dev[0].item())
     assert n == c_ref.shape[0]
     got_c = coords[:n].cpu().numpy().astype(np.int64)
     order = np.lexsort((got_c[:, 1], got_c[:, 2], got_c[:, 3], got_c[:, 0]))   # DynamicMeanVFE key: b, x, y, z

@@ -158,3 +158,13 @@ def test_backbone_oracle_runs_small():
     out_q, _ = O.backbone_forward(prog, P, f, coords, [41, 64, 64], 1, O.QuantCfg(mode="w8a8_pt", no_list=("conv_input.0",)), rec)
     rel = (out_q.features - out.features).abs().max() / out.features.abs().max()
     assert rel < 0.2 and "conv1.0.conv1.acc" in rec
+
+
+def test_im2col_conv_equals_per_offset_conv():
+    rng = np.random.default_rng(6)
+    coords = random_coords(rng, 2, 6, 14, 14, 0.2)
+    oc, osh, nbr = O.rulebook_strided(coords, [6, 14, 14], 3, 2, 1)
+    x = torch.randn(len(coords), 16, dtype=torch.float64)
+    w = torch.randn(32, 3, 3, 3, 16, dtype=torch.float64)
+    b = torch.randn(32, dtype=torch.float64)
+    assert (O.sparse_conv(x, nbr, w, b) - O.sparse_conv_im2col(x, nbr, w, b, chunk=100)).abs().max().item() < 1e-10
