@@ -138,8 +138,10 @@ int ql_quantize_rows(const void* x, int32_t in_dtype, int64_t n_cap, const int32
 
 /* ---- BEV hand-off (replaces HeightCompression.forward -> [EXT] SparseConvTensor.dense(),
  *      pcdet/models/backbones_2d/map_to_bev/height_compression.py:20-24): out[b, c*D+d, y, x], zero filled. */
+size_t ql_bev_densify_workspace_bytes(int32_t B, int32_t D, int32_t H, int32_t W);
 int ql_bev_densify(const void* feats, int32_t in_dtype, int32_t c, const uint64_t* table, int64_t table_cap,
-                   int32_t B, int32_t D, int32_t H, int32_t W, void* out, int32_t out_dtype, ql_stream_t stream);
+                   int32_t B, int32_t D, int32_t H, int32_t W, void* out, int32_t out_dtype,
+                   void* workspace, size_t workspace_bytes, ql_stream_t stream);
 
 #ifdef __cplusplus
 }

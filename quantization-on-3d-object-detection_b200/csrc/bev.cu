@@ -2,98 +2,138 @@
 //
 // Replaces HeightCompression.forward -> [EXT] SparseConvTensor.dense() + permute + view
 // (pcdet/models/backbones_2d/map_to_bev/height_compression.py:20-24), i.e. memset + scatter + permute copy.
-// Here every output byte is written exactly once, coalesced along x: a CTA owns one (b, y, x-range) strip,
-// resolves its D*XT cells through the coordinate hash, stages the present feature rows in shared memory
-// (coalesced row reads) and then streams all C*D channel planes of the strip.
+// Here every output byte is written exactly once with vector stores that are contiguous along x:
+//   pass 1  k_bev_index : one hash lookup per grid cell -> idxmap[b][d][y][x] (row or -1), B*D*H*W*4 bytes
+//   pass 2  k_bev_write : a thread owns VEC consecutive x of one (b, d, y) row and CC consecutive channels; it reads
+//                         VEC cell indices (one vector load), one 16/32-byte feature segment per present cell, transposes
+//                         in registers and writes CC plane rows (VEC elements each).  A warp's stores for one plane are
+//                         32*VEC contiguous elements.
 #include "ql_common.cuh"
 
 namespace {
 
-constexpr int kBevThreads = 256;
+__global__ void __launch_bounds__(256) k_bev_index(const uint2* __restrict__ table, uint32_t cap_mask, QlGrid g,
+                                                   int* __restrict__ idxmap) {
+    const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = (int64_t)g.B * g.D * g.H * g.W;
+    if (cell >= n) return;
+    idxmap[cell] = ql_hash_lookup(table, cap_mask, (uint32_t)cell);       // the linear cell index IS the key
+}
+
+template <typename T>
+__device__ __forceinline__ float to_f(T v);
+template <>
+__device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+template <typename TIn, typename TOut, int VEC, int CC>
+__global__ void __launch_bounds__(256) k_bev_write(const TIn* __restrict__ feats, int C, const int* __restrict__ idxmap, QlGrid g,
+                                                   TOut* __restrict__ out) {
+    const int xgroups = g.W / VEC;
+    const int cchunks = C / CC;
+    const int64_t total = (int64_t)cchunks * g.B * g.D * g.H * xgroups;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int xg = (int)(t % xgroups); t /= xgroups;
+    const int y = (int)(t % g.H); t /= g.H;
+    const int d = (int)(t % g.D); t /= g.D;
+    const int b = (int)(t % g.B); t /= g.B;
+    const int c0 = (int)t * CC;
+    const int64_t cell0 = (((int64_t)b * g.D + d) * g.H + y) * g.W + (int64_t)xg * VEC;
+    int idx[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) idx[v] = idxmap[cell0 + v];
+    TOut vals[CC][VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        if (idx[v] >= 0) {
+            const TIn* src = feats + (int64_t)idx[v] * C + c0;
+            TIn seg[CC];
+            if constexpr (CC * sizeof(TIn) == 16) {
+                *reinterpret_cast<uint4*>(seg) = *reinterpret_cast<const uint4*>(src);
+            } else if constexpr (CC * sizeof(TIn) == 32) {
+                reinterpret_cast<uint4*>(seg)[0] = reinterpret_cast<const uint4*>(src)[0];
+                reinterpret_cast<uint4*>(seg)[1] = reinterpret_cast<const uint4*>(src)[1];
+            } else {
+#pragma unroll
+                for (int c = 0; c < CC; ++c) seg[c] = src[c];
+            }
+#pragma unroll
+            for (int c = 0; c < CC; ++c) vals[c][v] = from_f<TOut>(to_f<TIn>(seg[c]));
+        } else {
+#pragma unroll
+            for (int c = 0; c < CC; ++c) vals[c][v] = from_f<TOut>(0.f);
+        }
+    }
+    const int64_t plane_stride = (int64_t)g.H * g.W;
+    TOut* o = out + (((int64_t)b * C + c0) * g.D + d) * plane_stride + (int64_t)y * g.W + (int64_t)xg * VEC;
+#pragma unroll
+    for (int c = 0; c < CC; ++c) {
+        TOut* dst = o + (int64_t)c * g.D * plane_stride;
+        if constexpr (VEC * sizeof(TOut) == 16) {
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(vals[c]);
+        } else if constexpr (VEC * sizeof(TOut) == 8) {
+            *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(vals[c]);
+        } else if constexpr (VEC * sizeof(TOut) == 4) {
+            *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(vals[c]);
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) dst[v] = vals[c][v];
+        }
+    }
+}
+
+template <typename TIn, typename TOut, int VEC, int CC>
+int launch_write(const void* feats, int C, const int* idxmap, QlGrid g, void* out, cudaStream_t st) {
+    const int64_t total = (int64_t)(C / CC) * g.B * g.D * g.H * (g.W / VEC);
+    k_bev_write<TIn, TOut, VEC, CC><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const TIn*)feats, C, idxmap, g, (TOut*)out);
+    return 0;
+}
 
 template <typename TIn, typename TOut>
-__global__ void __launch_bounds__(kBevThreads) k_bev_densify(const TIn* __restrict__ feats, int C, const uint2* __restrict__ table,
-                                                             uint32_t cap_mask, QlGrid g, int XT, int row_pitch_f, TOut* __restrict__ out) {
-    extern __shared__ uint8_t smem_raw[];
-    int* s_slot = reinterpret_cast<int*>(smem_raw);                       // [D*XT] -> staged row slot or -1
-    float* s_rows = reinterpret_cast<float*>(smem_raw + ((g.D * XT * 4 + 15) & ~15));   // [m][row_pitch_f]
-    __shared__ int s_count;
-    const int tiles_x = (g.W + XT - 1) / XT;
-    const int xt = blockIdx.x % tiles_x;
-    const int y = (blockIdx.x / tiles_x) % g.H;
-    const int b = blockIdx.x / (tiles_x * g.H);
-    const int x0 = xt * XT;
-    const int xn = min(XT, g.W - x0);
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
-    // 1. resolve cells, compact the present ones
-    for (int cell = threadIdx.x; cell < g.D * XT; cell += blockDim.x) {
-        const int d = cell / XT, xi = cell % XT;
-        int slot = -1;
-        if (xi < xn) {
-            const int idx = ql_hash_lookup(table, cap_mask, ql_key(g, b, d, y, x0 + xi));
-            if (idx >= 0) {
-                slot = atomicAdd(&s_count, 1);
-                // remember the global row in the first float of the staged row; replaced by data below
-                reinterpret_cast<int*>(s_rows + (size_t)slot * row_pitch_f)[0] = idx;
-            }
-        }
-        s_slot[cell] = slot;
+int dispatch_write(const void* feats, int C, const int* idxmap, QlGrid g, void* out, cudaStream_t st) {
+    constexpr int kMaxVec = 16 / (int)sizeof(TOut);                    // 8 for fp16, 4 for fp32
+    const bool feat_vec = (C % 8 == 0);
+    if (feat_vec) {
+        if (g.W % kMaxVec == 0) return launch_write<TIn, TOut, kMaxVec, 8>(feats, C, idxmap, g, out, st);
+        if (g.W % 4 == 0) return launch_write<TIn, TOut, 4, 8>(feats, C, idxmap, g, out, st);
+        if (g.W % 2 == 0) return launch_write<TIn, TOut, 2, 8>(feats, C, idxmap, g, out, st);
+        return launch_write<TIn, TOut, 1, 8>(feats, C, idxmap, g, out, st);
     }
-    __syncthreads();
-    const int m = s_count;
-    // 2. stage rows (coalesced over channels); the row index sits in element 0 until overwritten, so read it first
-    for (int j = threadIdx.x / 32; j < m; j += blockDim.x / 32) {
-        float* dst = s_rows + (size_t)j * row_pitch_f;
-        const int idx = reinterpret_cast<int*>(dst)[0];
-        __syncwarp();
-        const TIn* src = feats + (int64_t)idx * C;
-        for (int c = threadIdx.x & 31; c < C; c += 32) dst[c] = (float)src[c];
-    }
-    __syncthreads();
-    // 3. stream the C*D planes of this strip
-    const int planes = C * g.D;
-    for (int i = threadIdx.x; i < planes * xn; i += blockDim.x) {
-        const int p = i / xn, xi = i % xn;
-        const int c = p / g.D, d = p % g.D;
-        const int slot = s_slot[d * XT + xi];
-        const float v = slot >= 0 ? s_rows[(size_t)slot * row_pitch_f + c] : 0.f;
-        out[(((int64_t)b * planes + p) * g.H + y) * g.W + x0 + xi] = (TOut)v;
-    }
+    if (g.W % 4 == 0) return launch_write<TIn, TOut, 4, 1>(feats, C, idxmap, g, out, st);
+    return launch_write<TIn, TOut, 1, 1>(feats, C, idxmap, g, out, st);
 }
 
 }  // namespace
 
+extern "C" size_t ql_bev_densify_workspace_bytes(int32_t B, int32_t D, int32_t H, int32_t W) {
+    return (size_t)B * D * H * W * 4;
+}
+
 extern "C" int ql_bev_densify(const void* feats, int32_t in_dtype, int32_t c, const uint64_t* table, int64_t table_cap, int32_t B,
-                              int32_t D, int32_t H, int32_t W, void* out, int32_t out_dtype, ql_stream_t stream_) {
-    if (!feats || !table || !out || c <= 0 || B <= 0 || D <= 0 || H <= 0 || W <= 0) return QL_ERR_INVALID;
+                              int32_t D, int32_t H, int32_t W, void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes,
+                              ql_stream_t stream_) {
+    if (!feats || !table || !out || !workspace || c <= 0 || B <= 0 || D <= 0 || H <= 0 || W <= 0) return QL_ERR_INVALID;
     if (table_cap <= 0 || (table_cap & (table_cap - 1))) return QL_ERR_INVALID;
     if ((in_dtype != QL_F16 && in_dtype != QL_F32) || (out_dtype != QL_F16 && out_dtype != QL_F32)) return QL_ERR_INVALID;
     if ((double)B * D * H * W >= 4294967295.0) return QL_ERR_GRID_TOO_LARGE;
+    if (workspace_bytes < ql_bev_densify_workspace_bytes(B, D, H, W)) return QL_ERR_WORKSPACE;
     QlGrid g{B, D, H, W};
-    const int row_pitch_f = c + 1;                      // odd pitch (C even): conflict-free column reads
-    // strip width: as wide as shared memory allows (worst case every cell present)
-    int XT = W;
-    auto smem_for = [&](int xt) { return (size_t)((D * xt * 4 + 15) & ~15) + (size_t)D * xt * row_pitch_f * 4; };
-    while (XT > 1 && smem_for(XT) > 200 * 1024) XT = (XT + 1) / 2;
-    if (smem_for(XT) > 200 * 1024) return QL_ERR_UNSUPPORTED;
-    size_t smem = smem_for(XT);
-    int tiles_x = (W + XT - 1) / XT;
-    unsigned grid = (unsigned)((int64_t)B * H * tiles_x);
     cudaStream_t st = (cudaStream_t)stream_;
-    uint32_t mask = (uint32_t)(table_cap - 1);
-#define QL_BEV_LAUNCH(TI, TO)                                                                                             \
-    do {                                                                                                                  \
-        if (cudaFuncSetAttribute(k_bev_densify<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
-            return QL_ERR_CUDA;                                                                                           \
-        k_bev_densify<TI, TO><<<grid, kBevThreads, smem, st>>>((const TI*)feats, c, (const uint2*)table, mask, g, XT,     \
-                                                               row_pitch_f, (TO*)out);                                    \
-    } while (0)
-    if (in_dtype == QL_F16 && out_dtype == QL_F16) QL_BEV_LAUNCH(__half, __half);
-    else if (in_dtype == QL_F16 && out_dtype == QL_F32) QL_BEV_LAUNCH(__half, float);
-    else if (in_dtype == QL_F32 && out_dtype == QL_F16) QL_BEV_LAUNCH(float, __half);
-    else QL_BEV_LAUNCH(float, float);
-#undef QL_BEV_LAUNCH
+    int* idxmap = (int*)workspace;
+    const int64_t cells = (int64_t)B * D * H * W;
+    k_bev_index<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>((const uint2*)table, (uint32_t)(table_cap - 1), g, idxmap);
+    if (in_dtype == QL_F16 && out_dtype == QL_F16) dispatch_write<__half, __half>(feats, c, idxmap, g, out, st);
+    else if (in_dtype == QL_F16 && out_dtype == QL_F32) dispatch_write<__half, float>(feats, c, idxmap, g, out, st);
+    else if (in_dtype == QL_F32 && out_dtype == QL_F16) dispatch_write<float, __half>(feats, c, idxmap, g, out, st);
+    else dispatch_write<float, float>(feats, c, idxmap, g, out, st);
     QL_CUDA_CHECK_LAST();
     return QL_OK;
 }

@@ -142,6 +142,13 @@ __device__ __forceinline__ void ql_mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// 32-bit shared-memory load by shared-window address (LDS; no generic-address resolution, freely pipelined)
+__device__ __forceinline__ int ql_lds_s32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 // 16-byte async copy global -> shared with zero fill when !valid (src-size 0 reads nothing).
 __device__ __forceinline__ void ql_cp_async16(uint32_t dst, const void* src, bool valid) {
     uint32_t sz = valid ? 16u : 0u;
@@ -152,6 +159,10 @@ template <int N>
 __device__ __forceinline__ void ql_cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+// arrive on `bar` once all cp.async issued so far by this thread have landed (counts as one expected arrival)
+__device__ __forceinline__ void ql_cp_async_mbar_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 // make generic-proxy shared-memory writes visible to the async proxy (tcgen05.mma / bulk copies)
 __device__ __forceinline__ void ql_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -160,6 +171,13 @@ __device__ __forceinline__ void ql_bulk_g2s(uint32_t dst, const void* src, uint3
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+}
+
+// one lane of the (fully active) warp
+__device__ __forceinline__ bool ql_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 
 // ---- tcgen05 / TMEM ----

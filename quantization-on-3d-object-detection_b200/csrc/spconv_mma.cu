@@ -6,23 +6,28 @@
 // One persistent CTA per SM walks 128-row output tiles.  Per tile the conv is ONE GEMM
 //     D[128, C_out] = A[128, K*C_in] . W[C_out, K*C_in]^T ,   K = kernel volume
 // whose A operand never exists in memory: the K dimension is a flat byte string per row (offset-major,
-// channel-minor), cut into 128-byte pipeline stages.  Roles (320 threads):
-//   warps 0-3  gather producers : cp.async 16 B chunks feats[nbr[k][row]] -> SWIZZLE_128B K-major smem
-//                                 (zero fill for missing neighbours), fence.proxy.async, mbarrier arrive
-//   warps 4-7  epilogue         : tcgen05.ld accumulators -> dequant*BN scale/shift (+residual) (+ReLU)
+// channel-minor), cut into 128-byte pipeline stages.  Roles (448 threads):
+//   warps 0-7  gather producers : cp.async 16 B chunks feats[nbr[k][row]] -> SWIZZLE_128B K-major smem
+//                                 (zero fill for missing neighbours), cp.async.mbarrier.arrive.noinc on the stage barrier
+//   warps 8-11 epilogue         : tcgen05.ld accumulators -> dequant*BN scale/shift (+residual) (+ReLU)
 //                                 -> fp16/fp32 rows (+ int8 re-quantised rows, + per-channel absmax)
-//   warp  8    MMA issuer       : one lane issues tcgen05.mma (kind::f16 or kind::i8), accumulators in TMEM
+//   warp  12   MMA issuer       : one lane issues tcgen05.mma (kind::f16 or kind::i8), accumulators in TMEM
 //                                 (double buffered: tile i+1 accumulates while tile i drains)
-//   warp  9    TMA loader       : cp.async.bulk of the tile's rulebook slab and of each stage's weight slab
+//   warp  13   TMA loader       : cp.async.bulk of the tile's rulebook slab and of each stage's weight slab
 //                                 (pre-swizzled image from ql_pack_weights_host) onto the stage's mbarrier
 #include "ql_common.cuh"
 #include <string.h>
 
 namespace {
 
-constexpr int kProducerThreads = 128;
+constexpr int kProducerWarps = 8;
+constexpr int kProducerThreads = kProducerWarps * 32;   // 256
 constexpr int kEpilogueThreads = 128;
-constexpr int kThreadsTotal = 320;
+constexpr int kEpilogueWarp0 = kProducerWarps;            // warps 8..11 (warp % 4 == TMEM lane quarter)
+constexpr int kMmaWarp = kEpilogueWarp0 + 4;              // 12
+constexpr int kLoaderWarp = kMmaWarp + 1;                 // 13
+constexpr int kThreadsTotal = (kLoaderWarp + 1) * 32;     // 448
+constexpr int kChunksPerThread = QL_TILE_M * 8 / kProducerThreads;   // 4 x 16-byte chunks per stage
 constexpr int kStageABytes = QL_TILE_M * 128;      // 16 KB
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 232448;                // 227 KB opt-in maximum per CTA
@@ -82,14 +87,6 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
     return d;
 }
 
-__device__ __forceinline__ void producer_arrive_lagged(int lag, uint32_t bar) {
-    if (lag >= 3) ql_cp_async_wait<3>();
-    else if (lag == 2) ql_cp_async_wait<2>();
-    else ql_cp_async_wait<1>();
-    ql_fence_proxy_async();
-    ql_mbar_arrive(bar);
-}
-
 template <bool kInt8>
 __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_mma(const ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -132,7 +129,7 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_mma(const ConvParam
             s_qscale[c] = p.out_qscale ? p.out_qscale[c] : 0.f;
         }
     }
-    if (warp == 8) {
+    if (warp == kMmaWarp) {
         ql_tmem_alloc(ql_smem_u32(&misc->tmem_base), (uint32_t)p.tmem_cols);
         ql_tmem_relinquish();
     }
@@ -145,50 +142,50 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_mma(const ConvParam
     const uint32_t b_base = smem_base_u32 + p.off_b;
     const uint32_t b_stage_bytes = (uint32_t)p.c_out * 128u;
     const uint32_t nbr_bytes = (uint32_t)p.kvol * QL_TILE_M * 4u;
-    const int* nbr_s[2] = {reinterpret_cast<const int*>(smem + p.off_nbr),
-                           reinterpret_cast<const int*>(smem + p.off_nbr + nbr_bytes)};
 
-    if (warp < 4) {
+    if (warp < kProducerWarps) {
         // ============================ gather producers ============================
         const int c16 = tid & 7;
-        const int rsub = tid >> 3;                           // rows rsub + 16*i
-        const uint32_t dst_thread = ql_sw128_offset((uint32_t)rsub, (uint32_t)c16);   // + i*2048 for row rsub+16i
-        const int lag = p.lag;
-        uint32_t g = 0;                                      // global stage counter (ring position)
+        const int rsub = tid >> 3;                           // rows rsub + 32*i
+        const uint32_t dst_thread = ql_sw128_offset((uint32_t)rsub, (uint32_t)c16);   // + i*4096 for row rsub+32i
+        uint32_t s = 0, ph = 0;                              // ring slot and its phase
         uint32_t it = 0;
+        const uint32_t nbr_base_u32 = smem_base_u32 + (uint32_t)p.off_nbr + (uint32_t)rsub * 4u;
+        const int64_t row_bytes = p.row_bytes;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int nb = it & 1;
             ql_mbar_wait(ql_smem_u32(&misc->nbr_full[nb]), (it >> 1) & 1);
-            const int* nbrs = nbr_s[nb];
-            for (int ks = 0; ks < p.n_kstages; ++ks, ++g) {
-                const uint32_t s = g % (uint32_t)S;
-                const uint32_t ph = (g / (uint32_t)S) & 1u;
-                ql_mbar_wait(ql_smem_u32(&misc->empty[s]), ph ^ 1u);
-                const int kbyte = ks * 128 + c16 * 16;
-                const int koff = kbyte / p.row_bytes;
-                const int ch = kbyte - koff * p.row_bytes;
+            const uint32_t nbrs = nbr_base_u32 + (uint32_t)nb * nbr_bytes;
+            // (offset, channel byte) of this thread's 16-byte chunk, advanced by 128 bytes of K per stage
+            int koff = 0, ch = c16 * 16;
+            while (ch >= p.row_bytes) { ch -= p.row_bytes; ++koff; }
+            for (int ks = 0; ks < p.n_kstages; ++ks) {
                 const bool kvalid = koff < p.kvol;
-                const uint32_t dst0 = a_base + s * kStageABytes + dst_thread;
-                const int* nrow = nbrs + (kvalid ? koff : 0) * QL_TILE_M + rsub;
+                // all neighbour indices first (independent LDS), then the copies
+                int idx[kChunksPerThread];
+                const uint32_t nrow = nbrs + (uint32_t)(kvalid ? koff : 0) * (QL_TILE_M * 4u);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int idx = kvalid ? nrow[16 * i] : -1;
-                    const bool valid = idx >= 0;
-                    const uint8_t* src = p.feats + (int64_t)(valid ? idx : 0) * p.row_bytes + ch;
-                    ql_cp_async16(dst0 + (uint32_t)i * 2048u, src, valid);
+                for (int i = 0; i < kChunksPerThread; ++i) idx[i] = ql_lds_s32(nrow + (uint32_t)i * 128u);
+                ql_mbar_wait(ql_smem_u32(&misc->empty[s]), ph ^ 1u);
+                const uint32_t dst0 = a_base + s * kStageABytes + dst_thread;
+                const uint8_t* src0 = p.feats + ch;
+#pragma unroll
+                for (int i = 0; i < kChunksPerThread; ++i) {
+                    const bool valid = kvalid && idx[i] >= 0;
+                    ql_cp_async16(dst0 + (uint32_t)i * 4096u, src0 + (valid ? idx[i] : 0) * row_bytes, valid);
                 }
-                ql_cp_async_commit();
-                if (g >= (uint32_t)lag) producer_arrive_lagged(lag, ql_smem_u32(&misc->full[(g - lag) % (uint32_t)S]));
+                // completion of this thread's copies arrives on the stage barrier asynchronously: the producer never
+                // blocks on memory latency, so up to n_stages gathers (n_stages * 16 KB) are in flight per SM
+                ql_cp_async_mbar_arrive_noinc(ql_smem_u32(&misc->full[s]));
+                ch += 128;
+                while (ch >= p.row_bytes) { ch -= p.row_bytes; ++koff; }
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
             }
             ql_mbar_arrive(ql_smem_u32(&misc->nbr_empty[nb]));
         }
-        // drain: every stage committed but not yet signalled
-        ql_cp_async_wait<0>();
-        ql_fence_proxy_async();
-        for (uint32_t a = (g > (uint32_t)lag ? g - lag : 0u); a < g; ++a) ql_mbar_arrive(ql_smem_u32(&misc->full[a % (uint32_t)S]));
-    } else if (warp < 8) {
+    } else if (warp < kMmaWarp) {
         // ================================ epilogue ================================
-        const int w = warp - 4;                              // TMEM lane quarter (warp id % 4)
+        const int w = warp - kEpilogueWarp0;                              // TMEM lane quarter (warp id % 4)
         const int et = tid - kProducerThreads;               // 0..127 == row in tile
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -280,65 +277,73 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_mma(const ConvParam
             ql_tc_fence_before();
             ql_mbar_arrive(ql_smem_u32(&misc->acc_empty[a]));
         }
-    } else if (warp == 8) {
+    } else if (warp == kMmaWarp) {
         // =============================== MMA issuer ===============================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc<kInt8>(p.c_out);
-            uint32_t g = 0, it = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const int a = it & 1;
-                ql_mbar_wait(ql_smem_u32(&misc->acc_empty[a]), ((it >> 1) & 1) ^ 1u);
+        // The whole warp walks the loop (warp-uniform control flow, so the uniform-datapath tcgen05 instructions need no
+        // per-lane election loops); one elected lane issues the MMAs and the commits.
+        const bool leader = ql_elect_one();
+        const uint32_t idesc = make_idesc<kInt8>(p.c_out);
+        const uint64_t adesc0 = ql_umma_desc_sw128(a_base);
+        const uint64_t bdesc0 = ql_umma_desc_sw128(b_base);
+        const uint32_t b_step16 = b_stage_bytes >> 4;
+        uint32_t s = 0, ph = 0, it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int a = it & 1;
+            ql_mbar_wait(ql_smem_u32(&misc->acc_empty[a]), ((it >> 1) & 1) ^ 1u);
+            ql_tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.c_out);
+            for (int ks = 0; ks < p.n_kstages; ++ks) {
+                ql_mbar_wait(ql_smem_u32(&misc->full[s]), ph);
+                ql_fence_proxy_async();              // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
                 ql_tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.c_out);
-                for (int ks = 0; ks < p.n_kstages; ++ks, ++g) {
-                    const uint32_t s = g % (uint32_t)S;
-                    const uint32_t ph = (g / (uint32_t)S) & 1u;
-                    ql_mbar_wait(ql_smem_u32(&misc->full[s]), ph);
-                    ql_tc_fence_after();
-                    const uint64_t adesc = ql_umma_desc_sw128(a_base + s * kStageABytes);
-                    const uint64_t bdesc = ql_umma_desc_sw128(b_base + s * b_stage_bytes);
+                if (leader) {
+                    const uint64_t adesc = adesc0 + (uint64_t)(s * (kStageABytes >> 4));
+                    const uint64_t bdesc = bdesc0 + (uint64_t)(s * b_step16);
                     const int nk = (ks == p.n_kstages - 1) ? p.last_ksteps : 4;
-                    for (int kk = 0; kk < nk; ++kk) {
-                        // advance 32 bytes along K inside the 128-byte swizzle span: +2 in the (addr >> 4) field
-                        ql_tc_mma<kInt8>(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
-                                         (ks > 0 || kk > 0) ? 1u : 0u);
-                    }
+                    // advance 32 bytes along K inside the 128-byte swizzle span: +2 in the (addr >> 4) field
+                    ql_tc_mma<kInt8>(d_tmem, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+                    if (nk > 1) ql_tc_mma<kInt8>(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                    if (nk > 2) ql_tc_mma<kInt8>(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                    if (nk > 3) ql_tc_mma<kInt8>(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
                     ql_tc_commit(ql_smem_u32(&misc->empty[s]));
+                    if (ks == p.n_kstages - 1) ql_tc_commit(ql_smem_u32(&misc->acc_full[a]));
                 }
-                ql_tc_commit(ql_smem_u32(&misc->acc_full[a]));
+                __syncwarp();
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
             }
         }
-        __syncwarp();
     } else {
         // =============================== TMA loader ===============================
-        if (lane == 0) {
-            uint32_t g = 0, it = 0;
-            if ((int64_t)blockIdx.x < n_tiles) {
-                ql_mbar_arrive_expect_tx(ql_smem_u32(&misc->nbr_full[0]), nbr_bytes);
-                ql_bulk_g2s(ql_smem_u32(nbr_s[0]), p.nbr + (int64_t)blockIdx.x * p.kvol * QL_TILE_M, nbr_bytes,
-                            ql_smem_u32(&misc->nbr_full[0]));
-            }
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const int64_t next = tile + gridDim.x;
-                if (next < n_tiles) {
-                    const uint32_t itn = it + 1;
-                    const int nb = itn & 1;
-                    ql_mbar_wait(ql_smem_u32(&misc->nbr_empty[nb]), ((itn >> 1) & 1) ^ 1u);
+        const bool leader = ql_elect_one();
+        uint32_t s = 0, ph = 0, it = 0;
+        if (leader && (int64_t)blockIdx.x < n_tiles) {
+            ql_mbar_arrive_expect_tx(ql_smem_u32(&misc->nbr_full[0]), nbr_bytes);
+            ql_bulk_g2s(smem_base_u32 + (uint32_t)p.off_nbr, p.nbr + (int64_t)blockIdx.x * p.kvol * QL_TILE_M, nbr_bytes,
+                        ql_smem_u32(&misc->nbr_full[0]));
+        }
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int64_t next = tile + gridDim.x;
+            if (next < n_tiles) {
+                const uint32_t itn = it + 1;
+                const int nb = itn & 1;
+                ql_mbar_wait(ql_smem_u32(&misc->nbr_empty[nb]), ((itn >> 1) & 1) ^ 1u);
+                if (leader) {
                     ql_mbar_arrive_expect_tx(ql_smem_u32(&misc->nbr_full[nb]), nbr_bytes);
-                    ql_bulk_g2s(ql_smem_u32(nbr_s[nb]), p.nbr + next * p.kvol * QL_TILE_M, nbr_bytes,
-                                ql_smem_u32(&misc->nbr_full[nb]));
+                    ql_bulk_g2s(smem_base_u32 + (uint32_t)p.off_nbr + (uint32_t)nb * nbr_bytes, p.nbr + next * p.kvol * QL_TILE_M,
+                                nbr_bytes, ql_smem_u32(&misc->nbr_full[nb]));
                 }
-                for (int ks = 0; ks < p.n_kstages; ++ks, ++g) {
-                    const uint32_t s = g % (uint32_t)S;
-                    const uint32_t ph = (g / (uint32_t)S) & 1u;
-                    ql_mbar_wait(ql_smem_u32(&misc->empty[s]), ph ^ 1u);
+            }
+            for (int ks = 0; ks < p.n_kstages; ++ks) {
+                ql_mbar_wait(ql_smem_u32(&misc->empty[s]), ph ^ 1u);
+                if (leader) {
                     ql_mbar_arrive_expect_tx(ql_smem_u32(&misc->full[s]), b_stage_bytes);
                     ql_bulk_g2s(b_base + s * b_stage_bytes, p.w_packed + (int64_t)ks * b_stage_bytes, b_stage_bytes,
                                 ql_smem_u32(&misc->full[s]));
                 }
+                __syncwarp();
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
             }
         }
-        __syncwarp();
     }
 
     ql_tc_fence_before();
@@ -350,7 +355,7 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_mma(const ConvParam
             if (v) atomicMax(reinterpret_cast<unsigned int*>(p.absmax) + c, v);
         }
     }
-    if (warp == 8) ql_tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (warp == kMmaWarp) ql_tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 inline int elem_size(int dtype) { return dtype == QL_S8 ? 1 : (dtype == QL_F16 ? 2 : 0); }

@@ -212,7 +212,7 @@ class BackboneEngine:
             st.coords = z(st.cap, 4, dt=torch.int32)
             st.n_dev = z(2, dt=torch.int32)
             st.table = z(ops.hash_capacity(st.cap), dt=torch.int64)
-        self.rb_ws = z(int(ops.lib().ql_rulebook_strided_workspace_bytes(self.max_voxels, 343)), dt=torch.uint8)
+        self.rb_ws = z(int(ops.lib().ql_rulebook_strided_workspace_bytes(max(st.cap for st in self.stages), 343)), dt=torch.uint8)
         n_abs = sum(L.cout for L in self.layers) + 256
         self.absmax_pool = z(n_abs, dt=torch.float32)
         off = 0
@@ -238,6 +238,7 @@ class BackboneEngine:
         if self.bev:
             B, D, H, W = last.grid
             self.spatial_features = z(B, self.layers[-1].cout * D, H, W, dt=self.bev_dtype)
+            self.bev_ws = z(int(ops.lib().ql_bev_densify_workspace_bytes(B, D, H, W)), dt=torch.uint8)
         self._need_absmax = [i for i, L in enumerate(self.layers[:-1])
                              if self.layers[i + 1].kind in ("i8", "cw") and self.layers[i + 1].act_amax is None]
 
@@ -293,7 +294,7 @@ class BackboneEngine:
             x = L.out
         if self.bev:
             last = self.stages[-1]
-            self._op("bev_densify", 1, ops.bev_densify, x, last.table, last.grid, out=self.spatial_features)
+            self._op("bev_densify", 2, ops.bev_densify, x, last.table, last.grid, out=self.spatial_features, workspace=self.bev_ws)
 
     def _run_from_points(self):
         s0 = self.stages[0]

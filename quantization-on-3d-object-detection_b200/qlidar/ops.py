@@ -231,13 +231,16 @@ def quantize_rows(x: torch.Tensor, absmax: Optional[torch.Tensor], mode: int, bi
 
 
 def bev_densify(feats: torch.Tensor, table: torch.Tensor, grid, out: Optional[torch.Tensor] = None,
-                out_dtype: torch.dtype = torch.float16) -> torch.Tensor:
+                out_dtype: torch.dtype = torch.float16, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """grid = (B, D, H, W) -> out (B, C*D, H, W) with channel index c*D + d (== dense().view(N, C*D, H, W))."""
     _need_cuda(feats, table, out)
     B, D, H, W = [int(v) for v in grid]
     c = feats.shape[1]
     if out is None:
         out = torch.empty((B, c * D, H, W), dtype=out_dtype, device=feats.device)
-    check(lib().ql_bev_densify(_ptr(feats), _DT[feats.dtype], c, _ptr(table), table.numel(), B, D, H, W, _ptr(out), _DT[out.dtype], _stream()),
-          "ql_bev_densify")
+    ws_bytes = int(lib().ql_bev_densify_workspace_bytes(B, D, H, W))
+    if workspace is None or workspace.numel() < ws_bytes:
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=feats.device)
+    check(lib().ql_bev_densify(_ptr(feats), _DT[feats.dtype], c, _ptr(table), table.numel(), B, D, H, W, _ptr(out), _DT[out.dtype],
+                               _ptr(workspace), workspace.numel(), _stream()), "ql_bev_densify")
     return out
