@@ -85,25 +85,34 @@ int ql_mean_vfe(const float* voxels, const void* num_points, int32_t num_points_
  *      SubMConv3d/SparseConv3d.forward; keys at spconv_backbone.py:194-231).
  *      Layout produced: nbr[tile][k][128] int32, tile = row/128: the input row feeding output row
  *      tile*128+r through kernel offset k = (kz*KH+ky)*KW+kx, or -1.  ksize/stride/pad are zyx triples.
- *      Strided: n_out_dev is int32[2] = {rows kept (<= n_out_cap), active output sites found}; [1] > [0] means the
- *      caller's capacity overflowed (the surplus sites are dropped and never referenced). */
+ *      tile_kmask (nullable): uint32 [tiles][ql_rulebook_mask_words(kvol)], bit k set iff some row of the tile has a
+ *      neighbour through offset k (the conv kernel skips the empty slabs).
+ *      Submanifold: outputs == inputs (same rows); neighbours are found by open-addressing hash probes on `table`.
+ *      Strided: active output sites are numbered in ascending order of the linear key ((b*Do+z)*Ho+y)*Wo+x (spconv
+ *      leaves the order implementation-defined); out_table receives out coords -> row for the layers that follow.
+ *      n_out_dev is int32[2] = {rows kept (<= n_out_cap), active output sites found}; [1] > [0] means the caller's
+ *      capacity overflowed (the sites with the largest keys are dropped and never referenced). */
 int64_t ql_rulebook_num_tiles(int64_t n_out_cap);
+int32_t ql_rulebook_mask_words(int32_t kvol);
 int ql_rulebook_subm(const int32_t* coords, int64_t n_cap, const int32_t* n_dev,
                      int32_t B, int32_t D, int32_t H, int32_t W, const int32_t* ksize_host,
-                     const uint64_t* table, int64_t table_cap, int32_t* nbr_out, ql_stream_t stream);
-size_t ql_rulebook_strided_workspace_bytes(int64_t n_in_cap, int32_t kvol);
+                     const uint64_t* table, int64_t table_cap, int32_t* nbr_out, uint32_t* tile_kmask, ql_stream_t stream);
+size_t ql_rulebook_strided_workspace_bytes(int32_t B, int32_t D, int32_t H, int32_t W,
+                                           const int32_t* ksize_host, const int32_t* stride_host, const int32_t* pad_host);
 int ql_rulebook_strided(const int32_t* in_coords, int64_t n_in_cap, const int32_t* n_in_dev,
                         int32_t B, int32_t D, int32_t H, int32_t W,
                         const int32_t* ksize_host, const int32_t* stride_host, const int32_t* pad_host,
-                        const uint64_t* in_table, int64_t in_table_cap,
                         int32_t* out_coords, int64_t n_out_cap, int32_t* n_out_dev,
-                        uint64_t* out_table, int64_t out_table_cap, int32_t* nbr_out,
+                        uint64_t* out_table, int64_t out_table_cap, int32_t* nbr_out, uint32_t* tile_kmask,
                         void* workspace, size_t workspace_bytes, ql_stream_t stream);
 
 /* ---- implicit gather-GEMM-scatter sparse conv on tcgen05 tensor cores (replaces QConvNd.forward ->
  *      [EXT] spconv conv forward, quant/quant.py:36-58, plus the BatchNorm1d/ReLU/residual that follow it in
  *      post_act_block / SparseBasicBlock, spconv_backbone.py:8-27,51-67).
- *      feats: [n_in, c_in] fp16 (kind::f16, fp32 accumulate) or int8 codes (kind::i8, int32 accumulate).
+ *      feats: [n_in, c_in] fp16 (kind::f16, fp32 accumulate) or int8 codes (kind::i8, int32 accumulate); the gathered
+ *      rows go global -> registers -> tensor memory (A operand read from TMEM), never through shared memory.
+ *      nbr / tile_kmask: a rulebook from ql_rulebook_subm / ql_rulebook_strided; tile_kmask may be NULL (every
+ *      offset is visited); kvol <= 128.
  *      w_packed: per-output-channel int8 codes (as fp16 exact integers for the f16 kind) in the shared-memory
  *      image built by ql_pack_weights_host.  Epilogue: y = acc * (scale[oc] * (act_scale_dev ? *act_scale_dev : 1))
  *      + shift[oc] (+ residual) ; optional ReLU; written as out_dtype (QL_F16/QL_F32) -- or the raw
@@ -113,7 +122,8 @@ int ql_rulebook_strided(const int32_t* in_coords, int64_t n_in_cap, const int32_
 size_t ql_packed_weight_bytes(int32_t c_in, int32_t c_out, int32_t kvol, int32_t elem_dtype);
 int ql_pack_weights_host(const void* w_host, int32_t elem_dtype, int32_t c_in, int32_t c_out, int32_t kvol,
                          void* packed_host);
-int ql_spconv_mma(const void* feats, int32_t in_dtype, const int32_t* nbr, int64_t n_out_cap, const int32_t* n_out_dev,
+int ql_spconv_mma(const void* feats, int32_t in_dtype, const int32_t* nbr, const uint32_t* tile_kmask,
+                  int64_t n_out_cap, const int32_t* n_out_dev,
                   int32_t c_in, int32_t c_out, int32_t kvol, const void* w_packed,
                   const float* scale, const float* shift, const float* act_scale_dev,
                   const void* residual_f16, int32_t relu,

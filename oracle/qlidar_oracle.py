@@ -225,7 +225,7 @@ def rulebook_subm(coords: np.ndarray, spatial_shape, ksize) -> np.ndarray:
 def rulebook_strided(coords: np.ndarray, spatial_shape, ksize, stride, pad):
     """Regular (strided) sparse conv rulebook ([EXT] spconv SparseConv3d): an output site is active iff its
     window contains >= 1 active input.  Output ORDER is implementation-defined in spconv; this framework
-    fixes it to first-touch order over the enumeration (input row i, offset k) -> sequence i*K + k.
+    fixes it to ascending linear key ((b*Do + z)*Ho + y)*Wo + x (== np.unique of the candidate keys).
     Returns (out_coords (M,4) int32, out_shape, nbr (K, M) int32) with nbr[k,o] = row of input at
     o*stride - pad + offset_k."""
     k, s, p = _triple(ksize), _triple(stride), _triple(pad)
@@ -235,21 +235,15 @@ def rulebook_strided(coords: np.ndarray, spatial_shape, ksize, stride, pad):
     N = coords.shape[0]
     c = coords.astype(np.int64)
     osh = np.asarray(out_shape, dtype=np.int64)
-    cand_keys, cand_seq = [], []
+    cand_keys = []
     for ki, off in enumerate(offs):
         num = c[:, 1:] + np.asarray(p) - off
         o = num // np.asarray(s)
         ok = np.all((num % np.asarray(s) == 0) & (o >= 0) & (o < osh), axis=1)
         oc = np.concatenate([c[ok, :1], o[ok]], axis=1)
         cand_keys.append(_lin(oc, out_shape))
-        cand_seq.append(np.nonzero(ok)[0].astype(np.int64) * K + ki)
     cand_keys = np.concatenate(cand_keys) if N else np.zeros(0, np.int64)
-    cand_seq = np.concatenate(cand_seq) if N else np.zeros(0, np.int64)
-    srt = np.argsort(cand_seq, kind="stable")
-    cand_keys, cand_seq = cand_keys[srt], cand_seq[srt]
-    uniq, first = np.unique(cand_keys, return_index=True)
-    order = np.argsort(first, kind="stable")
-    okeys = uniq[order]
+    okeys = np.unique(cand_keys)
     M = okeys.size
     W_, H_, D_ = out_shape[2], out_shape[1], out_shape[0]
     out_coords = np.stack([okeys // (D_ * H_ * W_), (okeys // (H_ * W_)) % D_, (okeys // W_) % H_, okeys % W_],
@@ -268,6 +262,19 @@ def rulebook_strided(coords: np.ndarray, spatial_shape, ksize, stride, pad):
             res = _lookup(sk, si, _lin(np.where(ok[:, None], q, 0), spatial_shape))
             nbr[ki] = np.where(ok, res, -1)
     return out_coords, out_shape, nbr
+
+
+def tile_kmask(nbr: np.ndarray, tile_m: int = 128) -> np.ndarray:
+    """Per-tile offset mask of a (K, N) rulebook: uint32 [tiles, ceil(K/32)], bit k set iff any row of the tile has a
+    neighbour through offset k (what the rulebook kernels emit for the conv kernel's slab skipping)."""
+    K, N = nbr.shape
+    tiles = (N + tile_m - 1) // tile_m
+    out = np.zeros((tiles, (K + 31) // 32), dtype=np.uint32)
+    for t in range(tiles):
+        any_k = (nbr[:, t * tile_m:(t + 1) * tile_m] >= 0).any(axis=1)
+        for k in np.nonzero(any_k)[0]:
+            out[t, k >> 5] |= np.uint32(1 << (k & 31))
+    return out
 
 
 def pairs_in_coord_space(nbr: np.ndarray, in_coords: np.ndarray, out_coords: np.ndarray) -> np.ndarray:

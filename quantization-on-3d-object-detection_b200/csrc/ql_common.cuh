@@ -8,10 +8,12 @@
 
 #define QL_TILE_M 128            // output rows per MMA tile == TMEM lanes == rulebook tile height
 #define QL_NUM_SMS_DEFAULT 148
+#define QL_KVOL_MAX 343           // 7^3
+#define QL_MASK_WORDS_MAX 11     // ceil(QL_KVOL_MAX / 32) words of per-tile offset mask
 
 #define QL_CUDA_CHECK_LAST()                                   \
     do {                                                       \
-        cudaError_t e__ = cudaGetLastError();                  \
+        cudaError_t e__ = cudaPeekAtLastError();               \
         if (e__ != cudaSuccess) return QL_ERR_CUDA;            \
     } while (0)
 
@@ -111,11 +113,25 @@ __device__ __forceinline__ void ql_mbar_arrive_expect_tx(uint32_t bar, uint32_t 
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ bool ql_mbar_try_wait(uint32_t bar, uint32_t parity) {
+// Blocking poll: the thread is suspended in hardware until the phase completes or ~`hint_ns` elapse (without the hint the
+// time slice is so short that 16 polling warps took most of the issue slots of the one warp that feeds the tensor core).
+__device__ __forceinline__ bool ql_mbar_try_wait(uint32_t bar, uint32_t parity, uint32_t hint_ns = 20000u) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
+// non-blocking phase test (try_wait may suspend the thread for a hardware-defined time slice, ~4 us measured on B200)
+__device__ __forceinline__ bool ql_mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)

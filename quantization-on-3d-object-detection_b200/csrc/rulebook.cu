@@ -10,9 +10,8 @@
 // coalesced 128-byte rulebook stores per offset) and issue their open-addressing probes for a batch of kernel
 // offsets before resolving any of them, so ~9 independent 8-byte table loads are in flight per lane.
 //
-// Strided conv output numbering is first-touch order over the enumeration (input row i, offset k) -> i*K+k
-// (deterministic, reproducible by the oracle): insert (atomicMin of the sequence number) / count owners /
-// scan / assign, then the same pair-gather kernel as the submanifold case.
+// Every rulebook also emits a per-tile offset mask (bit k of kmask[tile] set iff some row of the tile has a
+// neighbour through offset k): the conv kernel skips the empty (tile, offset) slabs.
 #include "ql_common.cuh"
 #include "ql_scan.cuh"
 
@@ -25,13 +24,13 @@ struct ConvGeom {
 };
 
 constexpr int kProbeBatch = 9;
-#define QL_ID_FLAG 0x80000000u
 
 // nbr for output rows: in = out*stride - pad + offset, looked up in the input table.
 __global__ void __launch_bounds__(QL_TILE_M) k_rb_pairs(const int4* __restrict__ out_coords, int64_t n_cap,
                                                         const int* __restrict__ n_dev, QlGrid gin, ConvGeom cg,
                                                         const uint2* __restrict__ table, uint32_t cap_mask,
-                                                        int* __restrict__ nbr) {
+                                                        int* __restrict__ nbr, uint32_t* __restrict__ kmask) {
+    __shared__ uint32_t s_mask[QL_MASK_WORDS_MAX];
     const int64_t n = n_dev ? (int64_t)*n_dev : n_cap;
     const int64_t tile = blockIdx.x;
     if (tile * QL_TILE_M >= n) return;                       // tiles past the device-side row count are never read
@@ -39,11 +38,11 @@ __global__ void __launch_bounds__(QL_TILE_M) k_rb_pairs(const int4* __restrict__
     const int64_t row = tile * QL_TILE_M + r;
     const int K = cg.kd * cg.kh * cg.kw;
     int* dst = nbr + tile * (int64_t)K * QL_TILE_M + r;
-    if (row >= n) {
-        for (int k = 0; k < K; ++k) dst[(int64_t)k * QL_TILE_M] = -1;
-        return;
-    }
-    const int4 c = out_coords[row];                          // b, z, y, x
+    const int mask_words = (K + 31) >> 5;
+    if (r < mask_words) s_mask[r] = 0u;
+    __syncthreads();
+    const bool live = row < n;
+    const int4 c = live ? out_coords[row] : make_int4(0, 0, 0, 0);      // b, z, y, x
     const int bz = c.y * cg.sd - cg.pd, by = c.z * cg.sh - cg.ph, bx = c.w * cg.sw - cg.pw;
     for (int k0 = 0; k0 < K; k0 += kProbeBatch) {
         uint32_t key[kProbeBatch], slot[kProbeBatch];
@@ -54,7 +53,7 @@ __global__ void __launch_bounds__(QL_TILE_M) k_rb_pairs(const int4* __restrict__
             int k = k0 + j;
             int kz = k / (cg.kh * cg.kw), ky = (k / cg.kw) % cg.kh, kx = k % cg.kw;
             int z = bz + kz, y = by + ky, x = bx + kx;
-            ok[j] = k < K && z >= 0 && z < gin.D && y >= 0 && y < gin.H && x >= 0 && x < gin.W;
+            ok[j] = live && k < K && z >= 0 && z < gin.D && y >= 0 && y < gin.H && x >= 0 && x < gin.W;
             key[j] = ok[j] ? ql_key(gin, c.x, z, y, x) : 0u;
             slot[j] = ql_hash_slot(key[j], cap_mask);
         }
@@ -76,86 +75,164 @@ __global__ void __launch_bounds__(QL_TILE_M) k_rb_pairs(const int4* __restrict__
                 if (ee.x == key[j]) res = (int)ee.y;
             }
             dst[(int64_t)k * QL_TILE_M] = res;
+            const uint32_t any = __ballot_sync(0xffffffffu, res >= 0);
+            if (any && (threadIdx.x & 31) == 0) atomicOr(&s_mask[k >> 5], 1u << (k & 31));
+        }
+    }
+    if (kmask) {
+        __syncthreads();
+        if (r < mask_words) kmask[tile * mask_words + r] = s_mask[r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Strided (regular) sparse conv.  The active output set is built in a bitmap over the output grid
+// (one bit per cell, <= B*Do*Ho*Wo/8 bytes, L2 resident for every backbone stage), numbered by a popcount scan
+// -- so output rows come out SORTED BY LINEAR KEY ((b*Do+z)*Ho+y)*Wo+x: deterministic, reproducible by the oracle
+// with np.unique, and spatially coherent (a 128-row MMA tile is a run along x) -- and the pairs are scattered
+// from the INPUT side: an input row has only prod(ceil(k/s)) candidate outputs (3.4 on average for k=3, s=2)
+// against K probes per output row.  The output hash table (out coords -> row) is filled in the same pass for the
+// submanifold rulebooks / BEV densify that follow on this stage.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWordsPerBlock = QL_SCAN_THREADS;                      // one bitmap word (32 cells) per thread
+
+// calls f(k, out_key) for every kernel offset k through which input coord c feeds an in-range output site:
+// out = (c + pad - k) / stride, exact division (so that in = out*stride - pad + k)
+template <class F>
+__device__ __forceinline__ void for_each_candidate(const int4& c, const ConvGeom& cg, const QlGrid& gout, F&& f) {
+    for (int kz = 0; kz < cg.kd; ++kz) {
+        const int nz = c.y + cg.pd - kz;
+        if (nz < 0 || nz % cg.sd) continue;
+        const int oz = nz / cg.sd;
+        if (oz >= gout.D) continue;
+        for (int ky = 0; ky < cg.kh; ++ky) {
+            const int ny = c.z + cg.ph - ky;
+            if (ny < 0 || ny % cg.sh) continue;
+            const int oy = ny / cg.sh;
+            if (oy >= gout.H) continue;
+            for (int kx = 0; kx < cg.kw; ++kx) {
+                const int nx = c.w + cg.pw - kx;
+                if (nx < 0 || nx % cg.sw) continue;
+                const int ox = nx / cg.sw;
+                if (ox >= gout.W) continue;
+                f((kz * cg.kh + ky) * cg.kw + kx, ql_key(gout, c.x, oz, oy, ox));
+            }
         }
     }
 }
 
-// candidate output of input coord c through offset k (c + pad - k must be divisible by the stride and in range)
-__device__ __forceinline__ bool out_candidate(const int4& c, int k, const ConvGeom& cg, const QlGrid& gout, uint32_t& key) {
-    int kz = k / (cg.kh * cg.kw), ky = (k / cg.kw) % cg.kh, kx = k % cg.kw;
-    int nz = c.y + cg.pd - kz, ny = c.z + cg.ph - ky, nx = c.w + cg.pw - kx;
-    if (nz < 0 || ny < 0 || nx < 0) return false;
-    if (nz % cg.sd || ny % cg.sh || nx % cg.sw) return false;
-    int oz = nz / cg.sd, oy = ny / cg.sh, ox = nx / cg.sw;
-    if (oz >= gout.D || oy >= gout.H || ox >= gout.W) return false;
-    key = ql_key(gout, c.x, oz, oy, ox);
-    return true;
+__global__ void __launch_bounds__(256) k_rb_mark(const int4* __restrict__ in_coords, int64_t n_cap, const int* __restrict__ n_dev,
+                                                 ConvGeom cg, QlGrid gout, uint32_t* __restrict__ bitmap) {
+    const int64_t n = n_dev ? (int64_t)*n_dev : n_cap;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 c = in_coords[i];
+    for_each_candidate(c, cg, gout, [&](int, uint32_t key) {
+        const uint32_t bit = 1u << (key & 31u);
+        // most sites are marked by several inputs: test before the atomic
+        if (!(__ldcg(&bitmap[key >> 5]) & bit)) atomicOr(&bitmap[key >> 5], bit);
+    });
 }
 
-__global__ void k_rb_insert(const int4* __restrict__ in_coords, int64_t n_cap, const int* __restrict__ n_dev, ConvGeom cg,
-                            QlGrid gout, uint2* out_table, uint32_t cap_mask) {
+__global__ void __launch_bounds__(QL_SCAN_THREADS) k_rb_popc(const uint32_t* __restrict__ bitmap, int64_t n_words, int* block_counts) {
+    const int64_t w = (int64_t)blockIdx.x * kWordsPerBlock + threadIdx.x;
+    const int c = w < n_words ? __popc(bitmap[w]) : 0;
+    int total;
+    block_exclusive_scan(c, total);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+}
+
+// rank of every set bit = its output row: write coords, insert (key -> row) into the output hash table, and keep the
+// per-word exclusive prefix for the rank lookups of k_rb_scatter.  The set bits of a warp's 32 words are dealt out
+// evenly to its lanes (item i -> lane i % 32), so dense words do not serialise on one thread.
+__global__ void __launch_bounds__(QL_SCAN_THREADS) k_rb_emit(const uint32_t* __restrict__ bitmap, int64_t n_words,
+                                                            const int* __restrict__ block_offsets, QlGrid gout,
+                                                            uint32_t* __restrict__ word_prefix, int4* __restrict__ out_coords,
+                                                            int64_t n_out_cap, uint2* out_table, uint32_t cap_mask) {
+    const int64_t w = (int64_t)blockIdx.x * kWordsPerBlock + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const uint32_t bits = w < n_words ? bitmap[w] : 0u;
+    const int c = __popc(bits);
+    int total;
+    const uint32_t run = (uint32_t)(block_exclusive_scan(c, total) + block_offsets[blockIdx.x]);
+    if (w < n_words) word_prefix[w] = run;
+    const uint32_t warp_run0 = __shfl_sync(0xffffffffu, run, 0);
+    const uint32_t e = run - warp_run0;                                   // exclusive prefix inside the warp
+    const uint32_t warp_total = __shfl_sync(0xffffffffu, e + (uint32_t)c, 31);
+    const int64_t warp_w0 = w - lane;
+    for (uint32_t i0 = 0; i0 < warp_total; i0 += 32) {
+        const uint32_t i = i0 + (uint32_t)lane;
+        // largest j with e_j <= i (words with no bits share their successor's prefix and are skipped by the search)
+        int j = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const uint32_t ej = __shfl_sync(0xffffffffu, e, (j + step) & 31);
+            if (j + step < 32 && ej <= i) j += step;
+        }
+        const uint32_t bj = __shfl_sync(0xffffffffu, bits, j);
+        const uint32_t ej = __shfl_sync(0xffffffffu, e, j);
+        if (i < warp_total) {
+            const uint32_t rank = warp_run0 + i;
+            if ((int64_t)rank < n_out_cap) {
+                const uint32_t pos = __fns(bj, 0, (int)(i - ej) + 1);
+                const uint32_t key = (uint32_t)(warp_w0 + j) * 32u + pos;
+                out_coords[rank] = ql_unkey(gout, key);
+                const uint32_t s = ql_hash_insert(out_table, cap_mask, key);
+                out_table[s].y = rank;
+            }
+        }
+    }
+}
+
+// nbr := -1 for the live tiles (device-side row count)
+__global__ void __launch_bounds__(256) k_rb_fill(int4* __restrict__ nbr4, int K, const int* __restrict__ n_out_dev,
+                                                 int64_t n_out_cap) {
+    const int64_t n = min((int64_t)*n_out_dev, n_out_cap);
+    const int64_t tiles = (n + QL_TILE_M - 1) / QL_TILE_M;
+    const int64_t total4 = tiles * K * (QL_TILE_M / 4);
+    const int4 m1 = make_int4(-1, -1, -1, -1);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) nbr4[i] = m1;
+}
+
+__global__ void __launch_bounds__(256) k_rb_scatter(const int4* __restrict__ in_coords, int64_t n_cap, const int* __restrict__ n_dev,
+                                                    ConvGeom cg, QlGrid gout, const uint32_t* __restrict__ bitmap,
+                                                    const uint32_t* __restrict__ word_prefix, int64_t n_out_cap,
+                                                    int* __restrict__ nbr) {
     const int64_t n = n_dev ? (int64_t)*n_dev : n_cap;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int4 c = in_coords[i];
     const int K = cg.kd * cg.kh * cg.kw;
-    for (int k = 0; k < K; ++k) {
-        uint32_t key;
-        if (!out_candidate(c, k, cg, gout, key)) continue;
-        uint32_t s = ql_hash_insert(out_table, cap_mask, key);
-        atomicMin(&out_table[s].y, (uint32_t)(i * K + k));
-    }
+    for_each_candidate(c, cg, gout, [&](int k, uint32_t key) {
+        const uint32_t w = key >> 5;
+        const uint32_t rank = __ldg(&word_prefix[w]) + (uint32_t)__popc(__ldg(&bitmap[w]) & ((1u << (key & 31u)) - 1u));
+        if ((int64_t)rank >= n_out_cap) return;                      // site dropped by the caller's capacity
+        nbr[((int64_t)(rank / QL_TILE_M) * K + k) * QL_TILE_M + (rank % QL_TILE_M)] = (int)i;
+    });
 }
 
-// mode 0: count owned candidates per block; mode 1: assign ids, write coords, flag the table value with the id
-template <int kMode>
-__global__ void __launch_bounds__(QL_SCAN_THREADS) k_rb_number(const int4* __restrict__ in_coords, int64_t n_cap,
-                                                              const int* __restrict__ n_dev, ConvGeom cg, QlGrid gout,
-                                                              uint2* out_table, uint32_t cap_mask, int* block_counts,
-                                                              int4* out_coords, int64_t n_out_cap) {
-    const int64_t n = n_dev ? (int64_t)*n_dev : n_cap;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int K = cg.kd * cg.kh * cg.kw;
-    int4 c = make_int4(0, 0, 0, 0);
-    int owned = 0;
-    if (i < n) {
-        c = in_coords[i];
-        for (int k = 0; k < K; ++k) {
-            uint32_t key;
-            if (!out_candidate(c, k, cg, gout, key)) continue;
-            uint32_t s = ql_hash_find_slot(out_table, cap_mask, key);
-            if (s != 0xFFFFFFFFu && out_table[s].y == (uint32_t)(i * K + k)) ++owned;
+// per-tile offset mask of a finished rulebook: one CTA per live tile, thread r reads nbr[tile][k][r] for every k
+__global__ void __launch_bounds__(QL_TILE_M) k_rb_kmask(const int* __restrict__ nbr, int K, const int* __restrict__ n_out_dev,
+                                                        int64_t n_out_cap, uint32_t* __restrict__ kmask, int mask_words) {
+    __shared__ uint32_t s_mask[QL_MASK_WORDS_MAX];
+    const int64_t n = min((int64_t)*n_out_dev, n_out_cap);
+    const int64_t tile = blockIdx.x;
+    if (tile * QL_TILE_M >= n) return;
+    if (threadIdx.x < mask_words) s_mask[threadIdx.x] = 0u;
+    __syncthreads();
+    const int* src = nbr + tile * (int64_t)K * QL_TILE_M + threadIdx.x;
+    for (int k0 = 0; k0 < K; k0 += 9) {
+        int v[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) v[j] = (k0 + j < K) ? __ldcg(src + (int64_t)(k0 + j) * QL_TILE_M) : -1;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            const uint32_t any = __ballot_sync(0xffffffffu, v[j] >= 0);
+            if (any && (threadIdx.x & 31) == 0) atomicOr(&s_mask[(k0 + j) >> 5], 1u << ((k0 + j) & 31));
         }
     }
-    int total;
-    int ex = block_exclusive_scan(owned, total);
-    if (kMode == 0) {
-        if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
-        return;
-    }
-    if (i >= n || owned == 0) return;
-    int id = ex + block_counts[blockIdx.x];
-    for (int k = 0; k < K; ++k) {
-        uint32_t key;
-        if (!out_candidate(c, k, cg, gout, key)) continue;
-        uint32_t s = ql_hash_find_slot(out_table, cap_mask, key);
-        if (s == 0xFFFFFFFFu || out_table[s].y != (uint32_t)(i * K + k)) continue;
-        // sequence numbers are < 2^31, ids carry bit 31: a concurrent owner test on this slot can never match an id
-        if ((int64_t)id < n_out_cap) {
-            out_coords[id] = ql_unkey(gout, key);
-            out_table[s].y = QL_ID_FLAG | (uint32_t)id;
-        } else {
-            out_table[s].y = 0xFFFFFFFFu;                    // overflow: dropped, lookups miss
-        }
-        ++id;
-    }
-}
-
-__global__ void k_rb_strip_flag(uint2* table, int64_t cap) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= cap) return;
-    uint32_t y = table[s].y;
-    if (y != 0xFFFFFFFFu && (y & QL_ID_FLAG)) table[s].y = y & ~QL_ID_FLAG;
+    __syncthreads();
+    if (threadIdx.x < mask_words) kmask[tile * mask_words + threadIdx.x] = s_mask[threadIdx.x];
 }
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -174,10 +251,11 @@ inline bool geom_from_host(const int32_t* k, const int32_t* s, const int32_t* p,
 }  // namespace
 
 extern "C" int64_t ql_rulebook_num_tiles(int64_t n_out_cap) { return (n_out_cap + QL_TILE_M - 1) / QL_TILE_M; }
+extern "C" int32_t ql_rulebook_mask_words(int32_t kvol) { return (kvol + 31) / 32; }
 
 extern "C" int ql_rulebook_subm(const int32_t* coords, int64_t n_cap, const int32_t* n_dev, int32_t B, int32_t D, int32_t H,
                                 int32_t W, const int32_t* ksize, const uint64_t* table, int64_t table_cap, int32_t* nbr_out,
-                                ql_stream_t stream_) {
+                                uint32_t* tile_kmask, ql_stream_t stream_) {
     ConvGeom cg;
     if (!coords || !table || !nbr_out || !geom_from_host(ksize, nullptr, nullptr, cg)) return QL_ERR_INVALID;
     if (!(cg.kd & 1) || !(cg.kh & 1) || !(cg.kw & 1)) return QL_ERR_INVALID;   // submanifold needs odd kernels
@@ -187,56 +265,82 @@ extern "C" int ql_rulebook_subm(const int32_t* coords, int64_t n_cap, const int3
     QlGrid g{B, D, H, W};
     unsigned tiles = (unsigned)ql_rulebook_num_tiles(n_cap);
     k_rb_pairs<<<tiles, QL_TILE_M, 0, (cudaStream_t)stream_>>>((const int4*)coords, n_cap, n_dev, g, cg, (const uint2*)table,
-                                                               (uint32_t)(table_cap - 1), nbr_out);
+                                                               (uint32_t)(table_cap - 1), nbr_out, tile_kmask);
     QL_CUDA_CHECK_LAST();
     return QL_OK;
 }
 
-extern "C" size_t ql_rulebook_strided_workspace_bytes(int64_t n_in_cap, int32_t kvol) {
-    (void)kvol;
-    return align256((size_t)((n_in_cap + QL_SCAN_THREADS - 1) / QL_SCAN_THREADS + 1) * 4) + 256;
+namespace {
+struct StridedWs {
+    size_t bitmap, prefix, blocks, total;
+    int64_t n_words, n_blocks;
+};
+StridedWs strided_ws_layout(const QlGrid& gout) {
+    StridedWs w;
+    const int64_t cells = (int64_t)gout.B * gout.D * gout.H * gout.W;
+    w.n_words = (cells + 31) / 32;
+    w.n_blocks = (w.n_words + kWordsPerBlock - 1) / kWordsPerBlock;
+    size_t o = 0;
+    w.bitmap = o; o += align256((size_t)w.n_words * 4);
+    w.prefix = o; o += align256((size_t)w.n_words * 4);
+    w.blocks = o; o += align256((size_t)(w.n_blocks + 1) * 4);
+    w.total = o;
+    return w;
+}
+bool out_grid(int32_t B, int32_t D, int32_t H, int32_t W, const ConvGeom& cg, QlGrid& gout) {
+    gout = QlGrid{B, (D + 2 * cg.pd - cg.kd) / cg.sd + 1, (H + 2 * cg.ph - cg.kh) / cg.sh + 1, (W + 2 * cg.pw - cg.kw) / cg.sw + 1};
+    return B > 0 && gout.D > 0 && gout.H > 0 && gout.W > 0;
+}
+}  // namespace
+
+extern "C" size_t ql_rulebook_strided_workspace_bytes(int32_t B, int32_t D, int32_t H, int32_t W, const int32_t* ksize,
+                                                      const int32_t* stride, const int32_t* pad) {
+    ConvGeom cg;
+    QlGrid gout;
+    if (!stride || !pad || !geom_from_host(ksize, stride, pad, cg) || !out_grid(B, D, H, W, cg, gout)) return 0;
+    return strided_ws_layout(gout).total;
 }
 
 extern "C" int ql_rulebook_strided(const int32_t* in_coords, int64_t n_in_cap, const int32_t* n_in_dev, int32_t B, int32_t D,
                                    int32_t H, int32_t W, const int32_t* ksize, const int32_t* stride, const int32_t* pad,
-                                   const uint64_t* in_table, int64_t in_table_cap, int32_t* out_coords, int64_t n_out_cap,
-                                   int32_t* n_out_dev, uint64_t* out_table, int64_t out_table_cap, int32_t* nbr_out,
-                                   void* workspace, size_t workspace_bytes, ql_stream_t stream_) {
+                                   int32_t* out_coords, int64_t n_out_cap, int32_t* n_out_dev, uint64_t* out_table,
+                                   int64_t out_table_cap, int32_t* nbr_out, uint32_t* tile_kmask, void* workspace,
+                                   size_t workspace_bytes, ql_stream_t stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     ConvGeom cg;
-    if (!in_coords || !in_table || !out_coords || !n_out_dev || !out_table || !nbr_out || !workspace || !stride || !pad ||
+    if (!in_coords || !out_coords || !n_out_dev || !out_table || !nbr_out || !workspace || !stride || !pad ||
         !geom_from_host(ksize, stride, pad, cg))
         return QL_ERR_INVALID;
-    if (in_table_cap <= 0 || (in_table_cap & (in_table_cap - 1)) || out_table_cap <= 0 ||
-        (out_table_cap & (out_table_cap - 1)) || out_table_cap < 2 * n_out_cap || n_out_cap <= 0)
+    if (out_table_cap <= 0 || (out_table_cap & (out_table_cap - 1)) || out_table_cap < 2 * n_out_cap || n_out_cap <= 0 ||
+        n_out_cap >= 2147483647LL || n_in_cap < 0 || n_in_cap >= 2147483647LL)
         return QL_ERR_INVALID;
     const int K = cg.kd * cg.kh * cg.kw;
-    if ((double)n_in_cap * K >= 2147483648.0) return QL_ERR_UNSUPPORTED;
-    if (workspace_bytes < ql_rulebook_strided_workspace_bytes(n_in_cap, K)) return QL_ERR_WORKSPACE;
-    QlGrid gin{B, D, H, W};
-    QlGrid gout{B, (D + 2 * cg.pd - cg.kd) / cg.sd + 1, (H + 2 * cg.ph - cg.kh) / cg.sh + 1, (W + 2 * cg.pw - cg.kw) / cg.sw + 1};
-    if (gout.D <= 0 || gout.H <= 0 || gout.W <= 0) return QL_ERR_INVALID;
+    QlGrid gout;
+    if (!out_grid(B, D, H, W, cg, gout)) return QL_ERR_INVALID;
     if ((double)B * D * H * W >= 4294967295.0 || (double)B * gout.D * gout.H * gout.W >= 4294967295.0)
         return QL_ERR_GRID_TOO_LARGE;
+    const StridedWs w = strided_ws_layout(gout);
+    if (workspace_bytes < w.total) return QL_ERR_WORKSPACE;
+    char* ws = (char*)workspace;
+    uint32_t* bitmap = (uint32_t*)(ws + w.bitmap);
+    uint32_t* prefix = (uint32_t*)(ws + w.prefix);
+    int* blocks = (int*)(ws + w.blocks);
+    const int mask_words = (K + 31) / 32;
 
-    int* block_counts = (int*)workspace;
     if (cudaMemsetAsync(out_table, 0xFF, (size_t)out_table_cap * 8, st) != cudaSuccess) return QL_ERR_CUDA;
-    if (n_in_cap == 0) {
-        if (cudaMemsetAsync(n_out_dev, 0, 8, st) != cudaSuccess) return QL_ERR_CUDA;
-        return QL_OK;
-    }
-    uint32_t omask = (uint32_t)(out_table_cap - 1);
-    unsigned nb = (unsigned)((n_in_cap + QL_SCAN_THREADS - 1) / QL_SCAN_THREADS);
-    k_rb_insert<<<nb, QL_SCAN_THREADS, 0, st>>>((const int4*)in_coords, n_in_cap, n_in_dev, cg, gout, (uint2*)out_table, omask);
-    k_rb_number<0><<<nb, QL_SCAN_THREADS, 0, st>>>((const int4*)in_coords, n_in_cap, n_in_dev, cg, gout, (uint2*)out_table, omask,
-                                                   block_counts, (int4*)out_coords, n_out_cap);
-    k_scan_blocks<<<1, QL_SCAN_THREADS, 0, st>>>(block_counts, (int)nb, n_out_dev + 1, n_out_dev, n_out_cap);
-    k_rb_number<1><<<nb, QL_SCAN_THREADS, 0, st>>>((const int4*)in_coords, n_in_cap, n_in_dev, cg, gout, (uint2*)out_table, omask,
-                                                   block_counts, (int4*)out_coords, n_out_cap);
-    k_rb_strip_flag<<<(unsigned)((out_table_cap + 255) / 256), 256, 0, st>>>((uint2*)out_table, out_table_cap);
-    unsigned tiles = (unsigned)ql_rulebook_num_tiles(n_out_cap);
-    k_rb_pairs<<<tiles, QL_TILE_M, 0, st>>>((const int4*)out_coords, n_out_cap, n_out_dev, gin, cg, (const uint2*)in_table,
-                                            (uint32_t)(in_table_cap - 1), nbr_out);
+    if (cudaMemsetAsync(bitmap, 0, (size_t)w.n_words * 4, st) != cudaSuccess) return QL_ERR_CUDA;
+    const unsigned gin = (unsigned)((n_in_cap + 255) / 256);
+    if (gin) k_rb_mark<<<gin, 256, 0, st>>>((const int4*)in_coords, n_in_cap, n_in_dev, cg, gout, bitmap);
+    k_rb_popc<<<(unsigned)w.n_blocks, QL_SCAN_THREADS, 0, st>>>(bitmap, w.n_words, blocks);
+    k_scan_blocks<<<1, QL_SCAN_THREADS, 0, st>>>(blocks, (int)w.n_blocks, n_out_dev + 1, n_out_dev, n_out_cap);
+    k_rb_emit<<<(unsigned)w.n_blocks, QL_SCAN_THREADS, 0, st>>>(bitmap, w.n_words, blocks, gout, prefix, (int4*)out_coords, n_out_cap,
+                                                              (uint2*)out_table, (uint32_t)(out_table_cap - 1));
+    k_rb_fill<<<4 * ql_num_sms(), 256, 0, st>>>((int4*)nbr_out, K, n_out_dev, n_out_cap);
+    if (gin)
+        k_rb_scatter<<<gin, 256, 0, st>>>((const int4*)in_coords, n_in_cap, n_in_dev, cg, gout, bitmap, prefix, n_out_cap, nbr_out);
+    if (tile_kmask)
+        k_rb_kmask<<<(unsigned)ql_rulebook_num_tiles(n_out_cap), QL_TILE_M, 0, st>>>(nbr_out, K, n_out_dev, n_out_cap, tile_kmask,
+                                                                                      mask_words);
     QL_CUDA_CHECK_LAST();
     return QL_OK;
 }

@@ -3,44 +3,59 @@
 // Replaces QConvNd.forward -> [EXT] spconv SubMConv3d/SparseConv3d forward (quant/quant.py:36-58) together with
 // the BatchNorm1d / ReLU / residual-add that follow it (spconv_backbone.py:8-27,51-67).
 //
-// One persistent CTA per SM walks 128-row output tiles.  Per tile the conv is ONE GEMM
-//     D[128, C_out] = A[128, K*C_in] . W[C_out, K*C_in]^T ,   K = kernel volume
-// whose A operand never exists in memory: the K dimension is a flat byte string per row (offset-major,
-// channel-minor), cut into 128-byte pipeline stages.  Roles (448 threads):
-//   warps 0-7  gather producers : cp.async 16 B chunks feats[nbr[k][row]] -> SWIZZLE_128B K-major smem
-//                                 (zero fill for missing neighbours), cp.async.mbarrier.arrive.noinc on the stage barrier
-//   warps 8-11 epilogue         : tcgen05.ld accumulators -> dequant*BN scale/shift (+residual) (+ReLU)
-//                                 -> fp16/fp32 rows (+ int8 re-quantised rows, + per-channel absmax)
-//   warp  12   MMA issuer       : one lane issues tcgen05.mma (kind::f16 or kind::i8), accumulators in TMEM
-//                                 (double buffered: tile i+1 accumulates while tile i drains)
-//   warp  13   TMA loader       : cp.async.bulk of the tile's rulebook slab and of each stage's weight slab
-//                                 (pre-swizzled image from ql_pack_weights_host) onto the stage's mbarrier
+// One persistent CTA per SM walks 128-row output tiles.  Per tile the conv is a sum of per-offset GEMMs
+//     D[128, C_out] += A_k[128, C_in] . W_k[C_out, C_in]^T      for every kernel offset k that is non-empty in the tile
+// (the rulebook's per-tile offset mask lists them; empty (tile, offset) slabs cost nothing).  The A operand never
+// exists in memory and never touches shared memory: output row r of the tile is TMEM lane r, and the producer thread
+// that owns lane r loads its neighbour's feature row straight from global memory (L2) into registers and writes it
+// to tensor memory with tcgen05.st; the MMA reads A from TMEM (the ".ts" operand form) and only the weights from
+// shared memory.  ncu on the previous cp.async -> SWIZZLE_128B smem version showed the shared-memory data pipe at
+// 75 % (one write wavefront per returning 32-byte sector plus zero fills plus the tensor core's operand reads) with
+// DRAM at 17 %, see profiles/r01_conv_v2_smem_gather.md; TMEM stores run at 256 B/clk and are off that pipe.
+//
+// K is cut into chunks: one chunk = one kernel offset x one <=128-byte segment of the input row
+// (CH = 32 / 64 / 128 bytes => 1 / 2 / 4 MMA k-steps).  Roles (18 warps):
+//   warps 0-11  gather producers : 3 teams x 4 warps; warp w owns TMEM lanes 32*(w%4)..+31; teams take chunk groups
+//                                  round-robin; per chunk: nbr index (LDS from the tile's rulebook slab), CH bytes of the
+//                                  neighbour row (or zeros), tcgen05.st into the chunk's A slot, mbarrier arrive; the loads
+//                                  of a team's next group are issued before the current group is stored
+//   warps 12-15 epilogue         : tcgen05.ld accumulators -> dequant*BN scale/shift (+residual) (+ReLU)
+//                                  -> fp16/fp32 rows (+ int8 re-quantised rows, + per-channel absmax)
+//   warp  16    MMA issuer       : one lane issues tcgen05.mma (kind::f16 or kind::i8), accumulators in TMEM
+//                                  (double buffered when they fit: tile i+1 accumulates while tile i drains)
+//   warp  17    TMA loader       : cp.async.bulk of each chunk's weight slab (pre-swizzled image from
+//                                  ql_pack_weights_host) into the chunk's B slot -- or, when the whole packed weight tensor
+//                                  fits in shared memory (C <= 32 fp16, C <= 64 int8), of all of it once -- and of the
+//                                  NEXT tile's non-empty rulebook slabs (512 B each) into a double-buffered copy.
+//                                  One UBLKCP instruction costs its issuing warp ~225 ns whatever the size
+//                                  (tools/microbench/bulk_copy_rate.cu), an extra active lane only ~26 ns: copies are issued
+//                                  several lanes at a time, one copy per lane.
 #include "ql_common.cuh"
 #include <string.h>
 
 namespace {
 
-constexpr int kProducerWarps = 8;
-constexpr int kProducerThreads = kProducerWarps * 32;   // 256
+constexpr int kTeams = 3;
+constexpr int kProducerWarps = kTeams * 4;               // 12
 constexpr int kEpilogueThreads = 128;
-constexpr int kEpilogueWarp0 = kProducerWarps;            // warps 8..11 (warp % 4 == TMEM lane quarter)
-constexpr int kMmaWarp = kEpilogueWarp0 + 4;              // 12
-constexpr int kLoaderWarp = kMmaWarp + 1;                 // 13
-constexpr int kThreadsTotal = (kLoaderWarp + 1) * 32;     // 448
-constexpr int kChunksPerThread = QL_TILE_M * 8 / kProducerThreads;   // 4 x 16-byte chunks per stage
-constexpr int kStageABytes = QL_TILE_M * 128;      // 16 KB
-constexpr int kMaxStages = 8;
-constexpr int kSmemBudget = 232448;                // 227 KB opt-in maximum per CTA
+constexpr int kEpilogueWarp0 = kProducerWarps;            // warps 12..15 (warp % 4 == TMEM lane quarter)
+constexpr int kMmaWarp = kEpilogueWarp0 + 4;              // 16
+constexpr int kLoaderWarp = kMmaWarp + 1;                 // 17
+constexpr int kThreadsTotal = (kLoaderWarp + 1) * 32;     // 576
+constexpr int kMaxSlots = 8;
+constexpr int kMaskWords = 4;                             // kernel volumes up to 128 (3^3, 5^3)
+constexpr int kTmemCols = 512;
+constexpr int kSmemBudget = 232448;                       // 227 KB opt-in maximum per CTA
+constexpr int kSmemFloor = 120 * 1024;                    // always ask for > half an SM: one CTA (one TMEM owner) per SM
 
 struct ConvParams {
     const uint8_t* feats;
     const int* nbr;
+    const uint32_t* kmask;  // [tiles][mask_words] or null (every offset)
     const int* n_out_dev;
     int64_t n_out_cap;
     int row_bytes;          // c_in * elem size
-    int c_out, kvol;
-    int n_kstages;          // ceil(kvol*row_bytes / 128)
-    int last_ksteps;        // 32-byte MMA k-steps in the last stage
+    int c_out, kvol, nseg, mask_words;
     const uint8_t* w_packed;
     const float* scale;
     const float* shift;
@@ -52,22 +67,28 @@ struct ConvParams {
     int8_t* out_q;
     const float* out_qscale;
     float* absmax;
-    int n_stages;           // pipeline depth
-    int lag;                // producer arrive lag (cp.async groups in flight)
-    int tmem_cols;          // allocated TMEM columns (power of two >= 2*c_out)
-    // smem offsets from the 1024-aligned base
-    int off_b, off_nbr, off_misc;
+    int n_slots;            // A/B ring depth in groups (power of two)
+    int slot_log2;
+    int n_acc;              // accumulator buffers in TMEM (2, or 1 when 2*c_out does not fit beside the A ring)
+    int a_col0;             // first TMEM column of the A ring
+    int resident;           // 1: every weight chunk lives in shared memory for the whole kernel (no per-chunk B copies)
+    int w_bytes;            // packed weight bytes (resident mode)
+    int off_nbr;            // smem offset of the rulebook buffers: nbr_bufs x {16-byte tile mask, [kvol][128] int32}
+    int nbr_bufs, nbr_log2; // 4 (or 2 when shared memory is short): the loader runs nbr_bufs-1 tiles ahead
+    int nbr_stride;         // bytes per buffer
+    int off_misc;           // smem offset of MiscSmem from the 1024-aligned base
 };
 
 struct MiscSmem {
-    uint64_t full[kMaxStages];
-    uint64_t empty[kMaxStages];
-    uint64_t nbr_full[2];
-    uint64_t nbr_empty[2];
+    uint64_t full[kMaxSlots];
+    uint64_t empty[kMaxSlots];
     uint64_t acc_full[2];
     uint64_t acc_empty[2];
+    uint64_t nbr_full[4];
+    uint64_t nbr_empty[4];
+    uint64_t w_full;
     uint32_t tmem_base;
-    uint32_t pad[3];
+    uint32_t pad[1];
     // followed by: float scale[c_out], float shift[c_out], uint32 absmax[c_out], float qscale[c_out]
 };
 
@@ -87,11 +108,107 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
     return d;
 }
 
+// D[tmem] (+)= A[tmem] * B[smem desc]
 template <bool kInt8>
-__global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_mma(const ConvParams p) {
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (kInt8) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+
+// K-major swizzled shared-memory matrix descriptor for a [rows x CH bytes] weight chunk (CH = 32 / 64 / 128):
+// rows are CH bytes apart inside an 8-row swizzle atom, atoms are SBO = 8*CH bytes apart.
+template <int CH>
+__device__ __forceinline__ uint64_t umma_desc_b(uint32_t smem_addr) {
+    constexpr uint64_t layout = CH == 128 ? 2 : (CH == 64 ? 4 : 6);    // SWIZZLE_128B / 64B / 32B
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                    // LBO (ignored for swizzled K-major)
+    d |= (uint64_t)((8 * CH) >> 4) << 32;      // SBO
+    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+    d |= layout << 61;
+    return d;
+}
+
+__device__ __forceinline__ uint4 ldg16(const uint8_t* p) {
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+template <int NREG>
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&v)[NREG]);
+template <>
+__device__ __forceinline__ void tmem_st<32>(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+        "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+        "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// position of the n-th (0-based) set bit of a tile mask
+__device__ __forceinline__ int nth_set_bit(const uint32_t (&m)[kMaskWords], int n) {
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < kMaskWords; ++i) {
+        const int c = __popc(m[i]);
+        if (n >= 0 && n < c) k = i * 32 + (int)__fns(m[i], 0, n + 1);
+        n -= c;                                          // goes negative once found: later words cannot match
+    }
+    return k;
+}
+
+__device__ __forceinline__ int load_tile_mask(const ConvParams& p, int64_t tile, uint32_t (&mask)[kMaskWords]) {
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < kMaskWords; ++i) {
+        uint32_t w = 0u;
+        if (i < p.mask_words) {
+            if (p.kmask) {
+                w = __ldg(p.kmask + tile * p.mask_words + i);
+            } else {
+                const int rem = p.kvol - 32 * i;
+                w = rem >= 32 ? 0xFFFFFFFFu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
+            }
+        }
+        mask[i] = w;
+        n += __popc(w);
+    }
+    if (n == 0) { mask[0] = 1u; n = 1; }       // a tile without pairs still has to zero its accumulators
+    return n * p.nseg;
+}
+
+// the tile mask as the loader left it in the header of a rulebook buffer
+__device__ __forceinline__ int load_tile_mask_smem(uint32_t addr, int nseg, uint32_t (&mask)[kMaskWords]) {
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < kMaskWords; ++i) {
+        mask[i] = (uint32_t)ql_lds_s32(addr + 4u * i);
+        n += __popc(mask[i]);
+    }
+    return n * nseg;
+}
+
+template <bool kInt8, int CH>
+__global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams p) {
+    constexpr int kAReg = CH / 4;                          // 32-bit TMEM columns (registers) per chunk
+    constexpr int kGroup = 128 / CH;                       // sub-chunks per group == per ring slot (128 bytes of K, 32 TMEM columns)
     extern __shared__ uint8_t smem_raw[];
-    // SWIZZLE_128B operands need 1024-byte alignment
-    const uint32_t smem_base_u32 = (ql_smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_base_u32 = (ql_smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle atoms need 1024-byte alignment
     uint8_t* smem = smem_raw + (smem_base_u32 - ql_smem_u32(smem_raw));
     MiscSmem* misc = reinterpret_cast<MiscSmem*>(smem + p.off_misc);
     float* s_scale = reinterpret_cast<float*>(misc + 1);
@@ -102,22 +219,25 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_mma(const ConvParam
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    const int S = p.n_stages;
+    const int S = p.n_slots;
 
     const int64_t n_out = p.n_out_dev ? (int64_t)*p.n_out_dev : p.n_out_cap;
     const int64_t n_tiles = (n_out + QL_TILE_M - 1) / QL_TILE_M;
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            ql_mbar_init(ql_smem_u32(&misc->full[s]), kProducerThreads + 1);
-            ql_mbar_init(ql_smem_u32(&misc->empty[s]), 1);
+            ql_mbar_init(ql_smem_u32(&misc->full[s]), p.resident ? 4 : 4 + 1);   // one arrive per producer warp of the team (+ the loader's expect_tx)
+            ql_mbar_init(ql_smem_u32(&misc->empty[s]), 1);         // tcgen05.commit
         }
         for (int i = 0; i < 2; ++i) {
-            ql_mbar_init(ql_smem_u32(&misc->nbr_full[i]), 1);
-            ql_mbar_init(ql_smem_u32(&misc->nbr_empty[i]), kProducerThreads);
             ql_mbar_init(ql_smem_u32(&misc->acc_full[i]), 1);
             ql_mbar_init(ql_smem_u32(&misc->acc_empty[i]), kEpilogueThreads);
         }
+        for (int i = 0; i < 4; ++i) {
+            ql_mbar_init(ql_smem_u32(&misc->nbr_full[i]), 1);
+            ql_mbar_init(ql_smem_u32(&misc->nbr_empty[i]), kProducerWarps);
+        }
+        ql_mbar_init(ql_smem_u32(&misc->w_full), 1);
         ql_fence_mbar_init();
     }
     {
@@ -130,67 +250,138 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_mma(const ConvParam
         }
     }
     if (warp == kMmaWarp) {
-        ql_tmem_alloc(ql_smem_u32(&misc->tmem_base), (uint32_t)p.tmem_cols);
+        ql_tmem_alloc(ql_smem_u32(&misc->tmem_base), kTmemCols);
         ql_tmem_relinquish();
     }
     ql_tc_fence_before();
     __syncthreads();
     ql_tc_fence_after();
     const uint32_t tmem_base = misc->tmem_base;
-
-    const uint32_t a_base = smem_base_u32;
-    const uint32_t b_base = smem_base_u32 + p.off_b;
-    const uint32_t b_stage_bytes = (uint32_t)p.c_out * 128u;
-    const uint32_t nbr_bytes = (uint32_t)p.kvol * QL_TILE_M * 4u;
+    const uint32_t b_sub_bytes = (uint32_t)p.c_out * CH;     // one weight sub-chunk: [c_out x CH bytes]
+    const uint32_t smask = (uint32_t)S - 1u;                 // S is a power of two
+    const int slog = p.slot_log2;
 
     if (warp < kProducerWarps) {
         // ============================ gather producers ============================
-        const int c16 = tid & 7;
-        const int rsub = tid >> 3;                           // rows rsub + 32*i
-        const uint32_t dst_thread = ql_sw128_offset((uint32_t)rsub, (uint32_t)c16);   // + i*4096 for row rsub+32i
-        uint32_t s = 0, ph = 0;                              // ring slot and its phase
-        uint32_t it = 0;
-        const uint32_t nbr_base_u32 = smem_base_u32 + (uint32_t)p.off_nbr + (uint32_t)rsub * 4u;
-        const int64_t row_bytes = p.row_bytes;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int nb = it & 1;
-            ql_mbar_wait(ql_smem_u32(&misc->nbr_full[nb]), (it >> 1) & 1);
-            const uint32_t nbrs = nbr_base_u32 + (uint32_t)nb * nbr_bytes;
-            // (offset, channel byte) of this thread's 16-byte chunk, advanced by 128 bytes of K per stage
-            int koff = 0, ch = c16 * 16;
-            while (ch >= p.row_bytes) { ch -= p.row_bytes; ++koff; }
-            for (int ks = 0; ks < p.n_kstages; ++ks) {
-                const bool kvalid = koff < p.kvol;
-                // all neighbour indices first (independent LDS), then the copies
-                int idx[kChunksPerThread];
-                const uint32_t nrow = nbrs + (uint32_t)(kvalid ? koff : 0) * (QL_TILE_M * 4u);
-#pragma unroll
-                for (int i = 0; i < kChunksPerThread; ++i) idx[i] = ql_lds_s32(nrow + (uint32_t)i * 128u);
-                ql_mbar_wait(ql_smem_u32(&misc->empty[s]), ph ^ 1u);
-                const uint32_t dst0 = a_base + s * kStageABytes + dst_thread;
-                const uint8_t* src0 = p.feats + ch;
-#pragma unroll
-                for (int i = 0; i < kChunksPerThread; ++i) {
-                    const bool valid = kvalid && idx[i] >= 0;
-                    ql_cp_async16(dst0 + (uint32_t)i * 4096u, src0 + (valid ? idx[i] : 0) * row_bytes, valid);
+        const int q = warp & 3;                              // TMEM lane quarter
+        const int team = warp >> 2;
+        const int r = q * 32 + lane;                         // row in tile == TMEM lane
+        const uint32_t a_lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.a_col0;
+        const uint32_t nbr_s0 = smem_base_u32 + (uint32_t)p.off_nbr;            // buffer b: mask at +b*stride, slabs at +16
+        const uint32_t nbr_s = nbr_s0 + 16u + (uint32_t)r * 4u;
+        const uint32_t nbr_stride = (uint32_t)p.nbr_stride, nbmask = (uint32_t)p.nbr_bufs - 1u;
+
+        // Walks this team's groups across the CTA's tiles.  Groups are dealt to the teams by a counter (gg) that runs
+        // across tiles, so a team's consecutive groups are kTeams <= n_slots ring positions apart: it can never be two
+        // ring phases ahead of the barrier it polls (mbarrier parity waits alias at a distance of two phases).
+        struct Grp { uint32_t gg; int n; int c0; uint32_t buf_off; };
+        int64_t tile = blockIdx.x;
+        uint32_t it = 0, gg = 0;
+        int n_sub = 0, n_groups = 0, g = 0;
+        bool have_tile = false, ready = false;
+        // returns 1 = group found, 0 = no more work, 2 = the next tile's rulebook slab has not landed yet (only if !blocking)
+        auto next_group = [&](bool blocking, Grp& out) -> int {
+            while (true) {
+                if (!have_tile) {
+                    if (tile >= n_tiles) return 0;
+                    have_tile = true; ready = false;
                 }
-                // completion of this thread's copies arrives on the stage barrier asynchronously: the producer never
-                // blocks on memory latency, so up to n_stages gathers (n_stages * 16 KB) are in flight per SM
-                ql_cp_async_mbar_arrive_noinc(ql_smem_u32(&misc->full[s]));
-                ch += 128;
-                while (ch >= p.row_bytes) { ch -= p.row_bytes; ++koff; }
-                if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+                if (!ready) {
+                    const uint32_t nb = it & nbmask, par = (it >> p.nbr_log2) & 1u;
+                    const uint32_t bar = ql_smem_u32(&misc->nbr_full[nb]);
+                    if (blocking) ql_mbar_wait(bar, par);
+                    else if (!ql_mbar_test_wait(bar, par)) return 2;
+                    uint32_t mask[kMaskWords];
+                    n_sub = load_tile_mask_smem(nbr_s0 + nb * nbr_stride, p.nseg, mask);
+                    n_groups = (n_sub + kGroup - 1) / kGroup;
+                    g = 0; ready = true;
+                }
+                while (g < n_groups) {
+                    const uint32_t mygg = gg++;
+                    const int gi = g++;
+                    if ((int)(mygg % (uint32_t)kTeams) == team) {
+                        out.gg = mygg;
+                        out.c0 = gi * kGroup;
+                        out.n = n_sub - out.c0 < kGroup ? n_sub - out.c0 : kGroup;
+                        out.buf_off = (it & nbmask) * nbr_stride;
+                        return 1;
+                    }
+                }
+                // every index this warp needs from the tile's slab has been read: hand the buffer back
+                __syncwarp();
+                if (lane == 0) ql_mbar_arrive(ql_smem_u32(&misc->nbr_empty[it & nbmask]));
+                tile += gridDim.x; ++it; have_tile = false;
             }
-            ql_mbar_arrive(ql_smem_u32(&misc->nbr_empty[nb]));
+        };
+        // loads of one group: kGroup sub-chunks of CH bytes = 32 registers = the 32 TMEM columns of the group's slot
+        auto issue = [&](const Grp& grp, uint32_t (&v)[32]) {
+            int idx[kGroup], boff[kGroup];
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j) {
+                idx[j] = -1; boff[j] = 0;
+                if (j < grp.n) {
+                    const int lc = grp.c0 + j;
+                    int ord = lc;                            // ordinal of the sub-chunk's offset among the tile's non-empty ones
+                    if (CH == 128 && p.nseg > 1) { ord = lc / p.nseg; boff[j] = (lc - ord * p.nseg) * 128; }
+                    idx[j] = ql_lds_s32(nbr_s + grp.buf_off + (uint32_t)ord * (QL_TILE_M * 4u));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j) {
+                const uint8_t* src = p.feats + (int64_t)(idx[j] < 0 ? 0 : idx[j]) * p.row_bytes + boff[j];
+#pragma unroll
+                for (int t = 0; t < CH / 16; ++t) {
+                    uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                    if (idx[j] >= 0 && boff[j] + t * 16 < p.row_bytes) x = ldg16(src + t * 16);
+                    const int o = j * kAReg + 4 * t;
+                    v[o] = x.x; v[o + 1] = x.y; v[o + 2] = x.z; v[o + 3] = x.w;
+                }
+            }
+        };
+        auto store = [&](const Grp& grp, const uint32_t (&v)[32]) {
+            const uint32_t s = grp.gg & smask, ph = (grp.gg >> slog) & 1u;
+            ql_mbar_wait(ql_smem_u32(&misc->empty[s]), ph ^ 1u);                 // the MMAs that read this slot have completed
+            ql_tc_fence_after();
+            tmem_st<32>(a_lane_base + s * 32u, v);
+            tmem_st_wait();
+            ql_tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ql_mbar_arrive(ql_smem_u32(&misc->full[s]));
+        };
+        // software pipeline, two register buffers: the next group's loads are in flight while the current group waits for
+        // its ring slot.  A group that is still held in registers is never kept waiting on a rulebook slab (that could
+        // deadlock against the loader, which streams weights only as fast as stored groups are consumed): if the next
+        // tile's slab is not there yet the held group is stored first.
+        uint32_t va[32], vb[32];
+        Grp ga, gb;
+        int have_a = next_group(true, ga);
+        if (have_a == 1) issue(ga, va);
+        while (have_a == 1) {
+            int have_b = next_group(false, gb);
+            if (have_b == 1) issue(gb, vb);
+            store(ga, va);
+            if (have_b == 2) {
+                have_b = next_group(true, gb);
+                if (have_b == 1) issue(gb, vb);
+            }
+            if (have_b != 1) break;
+            have_a = next_group(false, ga);
+            if (have_a == 1) issue(ga, va);
+            store(gb, vb);
+            if (have_a == 2) {
+                have_a = next_group(true, ga);
+                if (have_a == 1) issue(ga, va);
+            }
         }
     } else if (warp < kMmaWarp) {
         // ================================ epilogue ================================
-        const int w = warp - kEpilogueWarp0;                              // TMEM lane quarter (warp id % 4)
-        const int et = tid - kProducerThreads;               // 0..127 == row in tile
+        const int w = warp - kEpilogueWarp0;                 // TMEM lane quarter (warp id % 4)
+        const int et = tid - kEpilogueWarp0 * 32;            // 0..127 == row in tile
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int a = it & 1;
-            ql_mbar_wait(ql_smem_u32(&misc->acc_full[a]), (it >> 1) & 1);
+            const int a = p.n_acc == 2 ? (int)(it & 1u) : 0;
+            const uint32_t aph = p.n_acc == 2 ? ((it >> 1) & 1u) : (it & 1u);
+            ql_mbar_wait(ql_smem_u32(&misc->acc_full[a]), aph);
             ql_tc_fence_after();
             const int64_t row = tile * QL_TILE_M + et;
             const bool row_ok = row < n_out;
@@ -203,7 +394,7 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_mma(const ConvParam
                     if (row_ok) {
                         uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(p.out) + row * p.c_out + c0);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) o[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        for (int qd = 0; qd < 4; ++qd) o[qd] = make_uint4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
                     }
                     continue;
                 }
@@ -247,20 +438,20 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_mma(const ConvParam
                     } else {
                         float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.c_out + c0);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) o[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+                        for (int qd = 0; qd < 4; ++qd) o[qd] = make_float4(y[4 * qd], y[4 * qd + 1], y[4 * qd + 2], y[4 * qd + 3]);
                     }
                     if (p.out_q) {
                         uint32_t qq[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
+                        for (int qd = 0; qd < 4; ++qd) {
                             uint32_t word = 0;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                float t = rintf(y[4 * q + j] * s_qscale[c0 + 4 * q + j]);
+                                float t = rintf(y[4 * qd + j] * s_qscale[c0 + 4 * qd + j]);
                                 t = fminf(fmaxf(t, -127.f), 127.f);
                                 word |= ((uint32_t)(uint8_t)(int8_t)(int)t) << (8 * j);
                             }
-                            qq[q] = word;
+                            qq[qd] = word;
                         }
                         *reinterpret_cast<uint4*>(p.out_q + row * p.c_out + c0) = make_uint4(qq[0], qq[1], qq[2], qq[3]);
                     }
@@ -279,70 +470,158 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_mma(const ConvParam
         }
     } else if (warp == kMmaWarp) {
         // =============================== MMA issuer ===============================
-        // The whole warp walks the loop (warp-uniform control flow, so the uniform-datapath tcgen05 instructions need no
-        // per-lane election loops); one elected lane issues the MMAs and the commits.
-        const bool leader = ql_elect_one();
-        const uint32_t idesc = make_idesc<kInt8>(p.c_out);
-        const uint64_t adesc0 = ql_umma_desc_sw128(a_base);
-        const uint64_t bdesc0 = ql_umma_desc_sw128(b_base);
-        const uint32_t b_step16 = b_stage_bytes >> 4;
-        uint32_t s = 0, ph = 0, it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int a = it & 1;
-            ql_mbar_wait(ql_smem_u32(&misc->acc_empty[a]), ((it >> 1) & 1) ^ 1u);
-            ql_tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.c_out);
-            for (int ks = 0; ks < p.n_kstages; ++ks) {
-                ql_mbar_wait(ql_smem_u32(&misc->full[s]), ph);
-                ql_fence_proxy_async();              // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
+        // One elected lane runs the whole loop (nothing in it is warp-collective).  Every group of every tile passes through
+        // this single instruction stream, so it is kept short: ring position and phase are counters, the tile mask is two
+        // 64-bit words walked with ffs, descriptors differ only in their low word.
+        if (ql_elect_one()) {
+            const uint32_t idesc = make_idesc<kInt8>(p.c_out);
+            const uint64_t bdesc0 = umma_desc_b<CH>(smem_base_u32);
+            const uint32_t bdesc_hi = (uint32_t)(bdesc0 >> 32), bdesc_lo0 = (uint32_t)bdesc0;
+            const uint32_t b_sub16 = b_sub_bytes >> 4;
+            const uint32_t a_base = tmem_base + (uint32_t)p.a_col0;
+            const uint32_t full0 = ql_smem_u32(&misc->full[0]), empty0 = ql_smem_u32(&misc->empty[0]);
+            const int nseg = p.nseg, resident = p.resident;
+            uint32_t s = 0, ph = 0, it = 0;
+            if (resident && (int64_t)blockIdx.x < n_tiles) ql_mbar_wait(ql_smem_u32(&misc->w_full), 0);
+            uint32_t mask_next[kMaskWords];
+            int n_sub_next = (int64_t)blockIdx.x < n_tiles ? load_tile_mask(p, blockIdx.x, mask_next) : 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                uint64_t m_lo = (uint64_t)mask_next[0] | ((uint64_t)mask_next[1] << 32);
+                uint64_t m_hi = (uint64_t)mask_next[2] | ((uint64_t)mask_next[3] << 32);
+                const int n_sub = n_sub_next;
+                if (tile + gridDim.x < n_tiles) n_sub_next = load_tile_mask(p, tile + gridDim.x, mask_next);   // in flight during this tile
+                const int a = p.n_acc == 2 ? (int)(it & 1u) : 0;
+                const uint32_t aph = p.n_acc == 2 ? ((it >> 1) & 1u) : (it & 1u);
+                ql_mbar_wait(ql_smem_u32(&misc->acc_empty[a]), aph ^ 1u);
                 ql_tc_fence_after();
-                if (leader) {
-                    const uint64_t adesc = adesc0 + (uint64_t)(s * (kStageABytes >> 4));
-                    const uint64_t bdesc = bdesc0 + (uint64_t)(s * b_step16);
-                    const int nk = (ks == p.n_kstages - 1) ? p.last_ksteps : 4;
-                    // advance 32 bytes along K inside the 128-byte swizzle span: +2 in the (addr >> 4) field
-                    ql_tc_mma<kInt8>(d_tmem, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
-                    if (nk > 1) ql_tc_mma<kInt8>(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-                    if (nk > 2) ql_tc_mma<kInt8>(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-                    if (nk > 3) ql_tc_mma<kInt8>(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
-                    ql_tc_commit(ql_smem_u32(&misc->empty[s]));
-                    if (ks == p.n_kstages - 1) ql_tc_commit(ql_smem_u32(&misc->acc_full[a]));
+                const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.c_out);
+                uint32_t accumulate = 0u;
+                int k = 0, seg = nseg;                           // seg == nseg: take the next offset from the mask
+                for (int c0 = 0; c0 < n_sub; c0 += kGroup) {
+                    ql_mbar_wait(full0 + s * 8u, ph);
+                    ql_tc_fence_after();
+#pragma unroll
+                    for (int j = 0; j < kGroup; ++j) {
+                        if (c0 + j < n_sub) {
+                            uint32_t b_idx = s * kGroup + (uint32_t)j;   // streamed: the sub-chunk's place in the ring slot
+                            if (resident) {                              // resident: its place in the packed tensor
+                                if (seg == nseg) {
+                                    seg = 0;
+                                    if (m_lo) { k = __ffsll((long long)m_lo) - 1; m_lo &= m_lo - 1; }
+                                    else { k = 63 + __ffsll((long long)m_hi); m_hi &= m_hi - 1; }
+                                }
+                                b_idx = (uint32_t)(k * nseg + seg);
+                                ++seg;
+                            }
+                            const uint32_t blo = bdesc_lo0 + b_idx * b_sub16;
+                            const uint32_t a_tmem = a_base + s * 32u + (uint32_t)(j * kAReg);
+#pragma unroll
+                            for (int ks = 0; ks < CH / 32; ++ks) {   // one k-step = 32 bytes of K: +8 TMEM columns, +2 in the desc (addr >> 4)
+                                const uint64_t bdesc = ((uint64_t)bdesc_hi << 32) | (uint64_t)(blo + (uint32_t)(ks * 2));
+                                tc_mma_ts<kInt8>(d_tmem, a_tmem + (uint32_t)(ks * 8), bdesc, idesc, accumulate);
+                                accumulate = 1u;
+                            }
+                        }
+                    }
+                    ql_tc_commit(empty0 + s * 8u);
+                    if (c0 + kGroup >= n_sub) ql_tc_commit(ql_smem_u32(&misc->acc_full[a]));
+                    if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
                 }
-                __syncwarp();
-                if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
             }
         }
+        __syncwarp();
     } else {
         // =============================== TMA loader ===============================
-        const bool leader = ql_elect_one();
-        uint32_t s = 0, ph = 0, it = 0;
-        if (leader && (int64_t)blockIdx.x < n_tiles) {
-            ql_mbar_arrive_expect_tx(ql_smem_u32(&misc->nbr_full[0]), nbr_bytes);
-            ql_bulk_g2s(smem_base_u32 + (uint32_t)p.off_nbr, p.nbr + (int64_t)blockIdx.x * p.kvol * QL_TILE_M, nbr_bytes,
-                        ql_smem_u32(&misc->nbr_full[0]));
-        }
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int64_t next = tile + gridDim.x;
-            if (next < n_tiles) {
-                const uint32_t itn = it + 1;
-                const int nb = itn & 1;
-                ql_mbar_wait(ql_smem_u32(&misc->nbr_empty[nb]), ((itn >> 1) & 1) ^ 1u);
-                if (leader) {
-                    ql_mbar_arrive_expect_tx(ql_smem_u32(&misc->nbr_full[nb]), nbr_bytes);
-                    ql_bulk_g2s(smem_base_u32 + (uint32_t)p.off_nbr + (uint32_t)nb * nbr_bytes, p.nbr + next * p.kvol * QL_TILE_M,
-                                nbr_bytes, ql_smem_u32(&misc->nbr_full[nb]));
-                }
+        const uint32_t nbr_s0 = smem_base_u32 + (uint32_t)p.off_nbr;
+        const uint32_t nbr_stride = (uint32_t)p.nbr_stride, nbmask = (uint32_t)p.nbr_bufs - 1u;
+        // Tile `tile` (the CTA's itn-th) -> rulebook buffer itn % nbr_bufs: its mask into the 16-byte header (so producers
+        // need no global load of their own), its non-empty slabs packed in mask order behind it (slab j = j-th set bit);
+        // lane j copies slabs j, j+32, ...
+        auto prefetch_nbr = [&](int64_t tile, uint32_t itn, const uint32_t (&mask)[kMaskWords], int n_slabs) {
+            const uint32_t nb = itn & nbmask;
+            const uint32_t bar = ql_smem_u32(&misc->nbr_full[nb]);
+            const uint32_t dst = nbr_s0 + nb * nbr_stride;
+            ql_mbar_wait(ql_smem_u32(&misc->nbr_empty[nb]), ((itn >> p.nbr_log2) & 1u) ^ 1u);
+            if (lane < kMaskWords) {
+                uint32_t w = mask[0];
+#pragma unroll
+                for (int i = 1; i < kMaskWords; ++i)
+                    if (lane == i) w = mask[i];
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + 4u * lane), "r"(w) : "memory");
             }
-            for (int ks = 0; ks < p.n_kstages; ++ks) {
-                ql_mbar_wait(ql_smem_u32(&misc->empty[s]), ph ^ 1u);
-                if (leader) {
-                    ql_mbar_arrive_expect_tx(ql_smem_u32(&misc->full[s]), b_stage_bytes);
-                    ql_bulk_g2s(b_base + s * b_stage_bytes, p.w_packed + (int64_t)ks * b_stage_bytes, b_stage_bytes,
-                                ql_smem_u32(&misc->full[s]));
+            __syncwarp();
+            if (lane == 0) ql_mbar_arrive_expect_tx(bar, (uint32_t)n_slabs * (QL_TILE_M * 4u));   // release: orders the header stores
+            __syncwarp();
+            const int* src = p.nbr + tile * (int64_t)p.kvol * QL_TILE_M;
+            for (int j0 = 0; j0 < n_slabs; j0 += 32) {
+                const int j = j0 + lane;
+                if (j < n_slabs) ql_bulk_g2s(dst + 16u + (uint32_t)j * (QL_TILE_M * 4u), src + nth_set_bit(mask, j) * QL_TILE_M, QL_TILE_M * 4u, bar);
+                __syncwarp();
+            }
+        };
+        uint32_t gg = 0, it = 0;
+        if (p.resident && (int64_t)blockIdx.x < n_tiles) {
+            // the whole packed weight tensor, 32 lanes x (w_bytes / 32) bytes
+            const uint32_t bar = ql_smem_u32(&misc->w_full);
+            const uint32_t per_lane = (uint32_t)p.w_bytes / 32u;
+            if (lane == 0) ql_mbar_arrive_expect_tx(bar, (uint32_t)p.w_bytes);
+            __syncwarp();
+            ql_bulk_g2s(smem_base_u32 + (uint32_t)lane * per_lane, p.w_packed + (size_t)lane * per_lane, per_lane, bar);
+            __syncwarp();
+        }
+        // rulebook prefetch runs nbr_bufs-1 tiles ahead of the tile being streamed; pf = next tile to prefetch, its mask is
+        // loaded one step early so the global-load latency is off the path
+        int64_t pf_tile = blockIdx.x;
+        uint32_t pf_it = 0;
+        uint32_t pf_mask[kMaskWords];
+        int pf_sub = pf_tile < n_tiles ? load_tile_mask(p, pf_tile, pf_mask) : 0;
+        auto prefetch_step = [&]() {
+            if (pf_tile >= n_tiles) return;
+            uint32_t m[kMaskWords];
+#pragma unroll
+            for (int i = 0; i < kMaskWords; ++i) m[i] = pf_mask[i];
+            const int n_slabs = pf_sub / p.nseg;
+            const int64_t t = pf_tile;
+            const uint32_t itn = pf_it;
+            pf_tile += gridDim.x; ++pf_it;
+            if (pf_tile < n_tiles) pf_sub = load_tile_mask(p, pf_tile, pf_mask);
+            prefetch_nbr(t, itn, m, n_slabs);
+        };
+        for (int i = 0; i < p.nbr_bufs - 1; ++i) prefetch_step();
+        // streamed weights: a batch of S/2 groups per pass, lane (gl, j) = sub-chunk j of the batch's gl-th group
+        const int lb = S / 2;
+        const int gl = lane / kGroup, j = lane % kGroup;
+        uint32_t mask_next[kMaskWords];
+        int n_sub_next = (!p.resident && (int64_t)blockIdx.x < n_tiles) ? load_tile_mask(p, blockIdx.x, mask_next) : 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            prefetch_step();
+            if (p.resident) continue;
+            uint32_t mask[kMaskWords];
+#pragma unroll
+            for (int i = 0; i < kMaskWords; ++i) mask[i] = mask_next[i];
+            const int n_sub = n_sub_next;
+            if (tile + gridDim.x < n_tiles) n_sub_next = load_tile_mask(p, tile + gridDim.x, mask_next);
+            const int n_groups = (n_sub + kGroup - 1) / kGroup;
+            for (int g0 = 0; g0 < n_groups; g0 += lb) {
+                const int g = g0 + gl, sub = g * kGroup + j;
+                const bool mine = gl < lb && sub < n_sub;
+                const uint32_t ggl = gg + (uint32_t)g, s = ggl & smask;
+                if (mine) ql_mbar_wait(ql_smem_u32(&misc->empty[s]), ((ggl >> slog) & 1u) ^ 1u);
+                __syncwarp();
+                if (mine && j == 0) {
+                    const int n_in = n_sub - g * kGroup < kGroup ? n_sub - g * kGroup : kGroup;
+                    ql_mbar_arrive_expect_tx(ql_smem_u32(&misc->full[s]), (uint32_t)n_in * b_sub_bytes);
                 }
                 __syncwarp();
-                if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+                if (mine) {
+                    const int ord = sub / p.nseg, seg = sub - ord * p.nseg;
+                    const int k = nth_set_bit(mask, ord);
+                    ql_bulk_g2s(smem_base_u32 + (s * kGroup + (uint32_t)j) * b_sub_bytes,
+                                p.w_packed + (int64_t)(k * p.nseg + seg) * b_sub_bytes, b_sub_bytes, ql_smem_u32(&misc->full[s]));
+                }
+                __syncwarp();
             }
+            gg += (uint32_t)n_groups;
         }
     }
 
@@ -355,45 +634,70 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_mma(const ConvParam
             if (v) atomicMax(reinterpret_cast<unsigned int*>(p.absmax) + c, v);
         }
     }
-    if (warp == kMmaWarp) ql_tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (warp == kMmaWarp) ql_tmem_dealloc(tmem_base, kTmemCols);
 }
 
 inline int elem_size(int dtype) { return dtype == QL_S8 ? 1 : (dtype == QL_F16 ? 2 : 0); }
+
+// chunk geometry shared by the packer and the launcher
+struct ChunkGeom {
+    int ch;      // bytes of K per chunk (32 / 64 / 128), zero padded when the row (segment) is shorter
+    int nseg;    // chunks per kernel offset
+};
+inline ChunkGeom chunk_geom(int row_bytes) {
+    ChunkGeom g;
+    if (row_bytes > 128) { g.ch = 128; g.nseg = (row_bytes + 127) / 128; }
+    else { g.ch = row_bytes <= 32 ? 32 : (row_bytes <= 64 ? 64 : 128); g.nseg = 1; }
+    return g;
+}
+// byte offset of 16-byte piece c16 of row r inside a K-major swizzled [rows x ch bytes] chunk image
+inline uint32_t chunk_sw_offset(int ch, uint32_t r, uint32_t c16) {
+    const uint32_t x = ch == 128 ? (r & 7u) : (ch == 64 ? ((r >> 1) & 3u) : ((r >> 2) & 1u));
+    return (r >> 3) * (uint32_t)(8 * ch) + (r & 7u) * (uint32_t)ch + ((c16 ^ x) << 4);
+}
+
+template <bool kInt8, int CH>
+cudaError_t launch(const ConvParams& p, int grid, size_t smem_bytes, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(k_spconv_ts<kInt8, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    k_spconv_ts<kInt8, CH><<<grid, kThreadsTotal, smem_bytes, st>>>(p);
+    return cudaPeekAtLastError();                     // left pending for ql_last_cuda_error()
+}
 
 }  // namespace
 
 extern "C" size_t ql_packed_weight_bytes(int32_t c_in, int32_t c_out, int32_t kvol, int32_t elem_dtype) {
     int es = elem_size(elem_dtype);
     if (es == 0 || c_in <= 0 || c_out <= 0 || kvol <= 0) return 0;
-    size_t kbytes = (size_t)kvol * c_in * es;
-    size_t stages = (kbytes + 127) / 128;
-    return stages * (size_t)c_out * 128;
+    const ChunkGeom g = chunk_geom(c_in * es);
+    return (size_t)kvol * g.nseg * (size_t)c_out * g.ch;
 }
 
 // w_host: [c_out][kvol][c_in] elements (== the reference layout (oc, kd, kh, kw, ic) flattened, quant/quant.py:37-39).
-// packed: per 128-byte K stage one [c_out x 128 B] K-major SWIZZLE_128B image, zero padded -- exactly what the
-// loader warp bulk-copies into shared memory.
+// packed: for every (offset k, segment s) chunk one [c_out x CH bytes] K-major swizzled image (SWIZZLE_32B/64B/128B by
+// CH), zero padded -- exactly what the loader warp bulk-copies into the chunk's shared-memory slot.
 extern "C" int ql_pack_weights_host(const void* w_host, int32_t elem_dtype, int32_t c_in, int32_t c_out, int32_t kvol,
                                     void* packed_host) {
     int es = elem_size(elem_dtype);
     if (!w_host || !packed_host || es == 0 || c_in <= 0 || c_out <= 0 || kvol <= 0) return QL_ERR_INVALID;
     if ((c_in * es) % 16 != 0 || c_out % 16 != 0 || c_out > 256) return QL_ERR_UNSUPPORTED;
-    size_t kbytes = (size_t)kvol * c_in * es;
-    size_t total = ql_packed_weight_bytes(c_in, c_out, kvol, elem_dtype);
-    memset(packed_host, 0, total);
+    const int row_bytes = c_in * es;
+    const ChunkGeom g = chunk_geom(row_bytes);
+    const size_t chunk_bytes = (size_t)c_out * g.ch;
+    memset(packed_host, 0, ql_packed_weight_bytes(c_in, c_out, kvol, elem_dtype));
     const uint8_t* src = (const uint8_t*)w_host;
     uint8_t* dst = (uint8_t*)packed_host;
-    for (int oc = 0; oc < c_out; ++oc) {
-        for (size_t kb = 0; kb < kbytes; kb += 16) {
-            size_t stage = kb / 128;
-            uint32_t c16 = (uint32_t)((kb % 128) / 16);
-            memcpy(dst + stage * (size_t)c_out * 128 + ql_sw128_offset((uint32_t)oc, c16), src + (size_t)oc * kbytes + kb, 16);
-        }
-    }
+    for (int oc = 0; oc < c_out; ++oc)
+        for (int k = 0; k < kvol; ++k)
+            for (int b = 0; b < row_bytes; b += 16) {
+                const int seg = b / 128, c16 = (b % 128) / 16;
+                memcpy(dst + (size_t)(k * g.nseg + seg) * chunk_bytes + chunk_sw_offset(g.ch, (uint32_t)oc, (uint32_t)c16),
+                       src + ((size_t)oc * kvol + k) * row_bytes + b, 16);
+            }
     return QL_OK;
 }
 
-extern "C" int ql_spconv_mma(const void* feats, int32_t in_dtype, const int32_t* nbr, int64_t n_out_cap,
+extern "C" int ql_spconv_mma(const void* feats, int32_t in_dtype, const int32_t* nbr, const uint32_t* tile_kmask, int64_t n_out_cap,
                              const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t kvol, const void* w_packed,
                              const float* scale, const float* shift, const float* act_scale_dev, const void* residual_f16,
                              int32_t relu, void* out, int32_t out_dtype, int8_t* out_q, const float* out_qscale,
@@ -404,51 +708,53 @@ extern "C" int ql_spconv_mma(const void* feats, int32_t in_dtype, const int32_t*
     if (es == 0) return QL_ERR_INVALID;
     if (out_dtype != QL_F16 && out_dtype != QL_F32 && out_dtype != QL_S32) return QL_ERR_INVALID;
     if (out_q && !out_qscale) return QL_ERR_INVALID;
-    if (c_in <= 0 || (c_in * es) % 16 != 0 || c_out < 16 || c_out % 16 != 0 || c_out > 256 || kvol <= 0 || kvol > 343)
+    if (c_in <= 0 || (c_in * es) % 16 != 0 || c_out < 16 || c_out % 16 != 0 || c_out > 256 || kvol <= 0 || kvol > 32 * kMaskWords)
         return QL_ERR_UNSUPPORTED;
     if (n_out_cap <= 0) return QL_OK;
 
     ConvParams p;
-    p.feats = (const uint8_t*)feats; p.nbr = nbr; p.n_out_dev = n_out_dev; p.n_out_cap = n_out_cap;
+    p.feats = (const uint8_t*)feats; p.nbr = nbr; p.kmask = tile_kmask; p.n_out_dev = n_out_dev; p.n_out_cap = n_out_cap;
     p.row_bytes = c_in * es; p.c_out = c_out; p.kvol = kvol;
-    int kbytes = kvol * p.row_bytes;
-    p.n_kstages = (kbytes + 127) / 128;
-    int last_bytes = kbytes - (p.n_kstages - 1) * 128;
-    p.last_ksteps = (last_bytes + 31) / 32;
+    const ChunkGeom g = chunk_geom(p.row_bytes);
+    p.nseg = g.nseg; p.mask_words = (kvol + 31) / 32;
     p.w_packed = (const uint8_t*)w_packed; p.scale = scale; p.shift = shift; p.act_scale_dev = act_scale_dev;
     p.residual = (const __half*)residual_f16; p.relu = relu; p.out = out; p.out_dtype = out_dtype;
     p.out_q = out_q; p.out_qscale = out_qscale; p.absmax = absmax;
 
-    int tm = 32;
-    while (tm < 2 * c_out) tm <<= 1;
-    p.tmem_cols = tm;
-    const int nbr_bytes = 2 * kvol * QL_TILE_M * 4;
+    // ring depth (groups of 128 bytes of K = 32 TMEM columns): bounded by the TMEM columns left beside the accumulators
+    // and, when the weights are streamed, by shared memory; a power of two >= kTeams.
     const int misc_bytes = (int)sizeof(MiscSmem) + 4 * c_out * 4;
-    const int stage_bytes = kStageABytes + c_out * 128;
-    int avail = kSmemBudget - 1024 /*alignment slack*/ - nbr_bytes - ((misc_bytes + 127) & ~127);
-    int S = avail / stage_bytes;
-    if (S > kMaxStages) S = kMaxStages;
-    if (S < 2) return QL_ERR_UNSUPPORTED;
-    p.n_stages = S;
-    p.lag = S - 1 < 3 ? S - 1 : 3;
-    if (p.lag < 1) p.lag = 1;
-    p.off_b = S * kStageABytes;
-    p.off_nbr = p.off_b + S * c_out * 128;
+    const int b_sub = c_out * g.ch;
+    const int b_slot = c_out * 128;                              // a group's weight sub-chunks
+    p.nbr_stride = (16 + kvol * QL_TILE_M * 4 + 127) & ~127;
+    p.nbr_bufs = 4 * p.nbr_stride <= 64 * 1024 ? 4 : 2;
+    p.nbr_log2 = p.nbr_bufs == 4 ? 2 : 1;
+    const int nbr_bytes = p.nbr_bufs * p.nbr_stride;
+    const int smem_free = kSmemBudget - 1024 - nbr_bytes - ((misc_bytes + 127) & ~127);
+    p.w_bytes = kvol * g.nseg * b_sub;
+    p.resident = (p.w_bytes <= smem_free && p.w_bytes % 512 == 0) ? 1 : 0;   // 32 lanes x 16-byte multiples
+    p.n_acc = (kTmemCols - 2 * c_out) / 32 >= 8 ? 2 : 1;
+    int S = (kTmemCols - p.n_acc * c_out) / 32;
+    if (!p.resident && S > smem_free / b_slot) S = smem_free / b_slot;
+    S = S >= 8 ? 8 : (S >= 4 ? 4 : 0);
+    if (S < kTeams) return QL_ERR_UNSUPPORTED;
+    p.n_slots = S;
+    p.slot_log2 = S == 8 ? 3 : 2;
+    p.a_col0 = p.n_acc * c_out;
+    p.off_nbr = p.resident ? ((p.w_bytes + 1023) & ~1023) : S * b_slot;
     p.off_misc = (p.off_nbr + nbr_bytes + 127) & ~127;
     size_t smem_bytes = 1024 + (size_t)p.off_misc + misc_bytes;
+    if (smem_bytes < (size_t)kSmemFloor) smem_bytes = kSmemFloor;
 
     int64_t tiles = (n_out_cap + QL_TILE_M - 1) / QL_TILE_M;
     int grid = (int)(tiles < ql_num_sms() ? tiles : ql_num_sms());
     cudaError_t e;
     if (in_dtype == QL_S8) {
-        e = cudaFuncSetAttribute(k_spconv_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        if (e != cudaSuccess) return QL_ERR_CUDA;
-        k_spconv_mma<true><<<grid, kThreadsTotal, smem_bytes, st>>>(p);
+        e = g.ch == 32 ? launch<true, 32>(p, grid, smem_bytes, st)
+          : g.ch == 64 ? launch<true, 64>(p, grid, smem_bytes, st) : launch<true, 128>(p, grid, smem_bytes, st);
     } else {
-        e = cudaFuncSetAttribute(k_spconv_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        if (e != cudaSuccess) return QL_ERR_CUDA;
-        k_spconv_mma<false><<<grid, kThreadsTotal, smem_bytes, st>>>(p);
+        e = g.ch == 32 ? launch<false, 32>(p, grid, smem_bytes, st)
+          : g.ch == 64 ? launch<false, 64>(p, grid, smem_bytes, st) : launch<false, 128>(p, grid, smem_bytes, st);
     }
-    QL_CUDA_CHECK_LAST();
-    return QL_OK;
+    return e == cudaSuccess ? QL_OK : QL_ERR_CUDA;
 }

@@ -212,7 +212,9 @@ class BackboneEngine:
             st.coords = z(st.cap, 4, dt=torch.int32)
             st.n_dev = z(2, dt=torch.int32)
             st.table = z(ops.hash_capacity(st.cap), dt=torch.int64)
-        self.rb_ws = z(int(ops.lib().ql_rulebook_strided_workspace_bytes(max(st.cap for st in self.stages), 343)), dt=torch.uint8)
+        ws = [ops.rulebook_strided_workspace_bytes(self.stages[L.stage_in].grid, L.ksize, L.stride, L.pad) for L in self.layers if not L.subm]
+        self.rb_ws = z(max(ws + [256]), dt=torch.uint8)
+        self.kmasks: Dict[tuple, torch.Tensor] = {}
         n_abs = sum(L.cout for L in self.layers) + 256
         self.absmax_pool = z(n_abs, dt=torch.float32)
         off = 0
@@ -222,6 +224,7 @@ class BackboneEngine:
             if L.rb_key not in self.rulebooks:
                 K = int(np.prod(L.ksize))
                 self.rulebooks[L.rb_key] = z(ops.num_tiles(so.cap), K, ops.TILE_M, dt=torch.int32)
+                self.kmasks[L.rb_key] = z(ops.num_tiles(so.cap), ops.mask_words(K), dt=torch.int32)
             L.out = z(so.cap, L.cout)
             L.out_absmax = self.absmax_pool[off:off + L.cout]
             off += L.cout
@@ -263,13 +266,13 @@ class BackboneEngine:
             self.absmax_pool.zero_()
         for i, L in enumerate(self.layers):
             si, so = self.stages[L.stage_in], self.stages[L.stage_out]
-            nbr = self.rulebooks[L.rb_key]
+            nbr, kmask = self.rulebooks[L.rb_key], self.kmasks[L.rb_key]
             if L.rb_key not in built:
                 if L.subm:
-                    self._op("rulebook_subm:" + L.name, 1, ops.rulebook_subm, si.coords, si.n_dev, si.grid, L.ksize, si.table, nbr=nbr)
+                    self._op("rulebook_subm:" + L.name, 1, ops.rulebook_subm, si.coords, si.n_dev, si.grid, L.ksize, si.table, nbr=nbr, kmask=kmask)
                 else:
-                    self._op("rulebook_strided:" + L.name, 6, ops.rulebook_strided, si.coords, si.n_dev, si.grid, L.ksize, L.stride, L.pad,
-                             si.table, so.cap, out=(so.coords, so.n_dev, so.table, nbr), workspace=self.rb_ws)
+                    self._op("rulebook_strided:" + L.name, 8, ops.rulebook_strided, si.coords, si.n_dev, si.grid, L.ksize, L.stride, L.pad,
+                             so.cap, out=(so.coords, so.n_dev, so.table, nbr), workspace=self.rb_ws, kmask=kmask)
                 built.add(L.rb_key)
             absmax = L.out_absmax if i in self._need_absmax else None
             if L.block_input:
@@ -279,18 +282,18 @@ class BackboneEngine:
                 self._op("stem:" + L.name, 1, ops.stem_conv, x, nbr, so.cap, so.n_dev, L.w, L.scale, L.shift, relu=L.relu, out=L.out, absmax=absmax)
             elif L.kind == "f16":
                 self._op("conv:" + L.name, 1, ops.spconv_mma, x, nbr, so.cap, so.n_dev, L.cout, L.w, L.scale, L.shift, residual=res,
-                         relu=L.relu, out=L.out, absmax=absmax)
+                         relu=L.relu, out=L.out, absmax=absmax, kmask=kmask)
             elif L.kind == "i8":
                 am = L.act_amax if L.act_amax is not None else L.in_absmax
                 self._op("quantize:" + L.name, 1, ops.quantize_rows, x, am, ops.QL_Q_CODES_PER_TENSOR, L.act_bits, si.n_dev, out=L.q_buf,
                          act_scale=L.act_scale)
                 self._op("conv:" + L.name, 1, ops.spconv_mma, L.q_buf, nbr, so.cap, so.n_dev, L.cout, L.w, L.scale, L.shift, act_scale=L.act_scale, residual=res,
-                               relu=L.relu, out=L.out, absmax=absmax)
+                               relu=L.relu, out=L.out, absmax=absmax, kmask=kmask)
             elif L.kind == "cw":
                 am = L.act_amax if L.act_amax is not None else L.in_absmax
                 self._op("quantize:" + L.name, 1, ops.quantize_rows, x, am, ops.QL_Q_FAKE_PER_CHANNEL, L.act_bits, si.n_dev, out=L.q_buf)
                 self._op("conv:" + L.name, 1, ops.spconv_mma, L.q_buf, nbr, so.cap, so.n_dev, L.cout, L.w, L.scale, L.shift, residual=res, relu=L.relu, out=L.out,
-                               absmax=absmax)
+                               absmax=absmax, kmask=kmask)
             x = L.out
         if self.bev:
             last = self.stages[-1]

@@ -111,25 +111,40 @@ def mean_vfe(voxels: torch.Tensor, num_points: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def mask_words(kvol: int) -> int:
+    return (int(kvol) + 31) // 32
+
+
 def rulebook_subm(coords: torch.Tensor, n_dev: Optional[torch.Tensor], grid, ksize, table: torch.Tensor,
-                  nbr: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """nbr int32 [tiles, K, 128]."""
-    _need_cuda(coords, n_dev, table, nbr)
+                  nbr: Optional[torch.Tensor] = None, kmask: Optional[torch.Tensor] = None, with_mask: bool = False):
+    """nbr int32 [tiles, K, 128]; with_mask (or a kmask buffer) also returns the per-tile offset mask int32 [tiles, ceil(K/32)]."""
+    _need_cuda(coords, n_dev, table, nbr, kmask)
     k = triple(ksize)
     K = k[0] * k[1] * k[2]
     n_cap = coords.shape[0]
     if nbr is None:
         nbr = torch.empty((num_tiles(n_cap), K, TILE_M), dtype=torch.int32, device=coords.device)
+    if kmask is None and with_mask:
+        kmask = torch.zeros((num_tiles(n_cap), mask_words(K)), dtype=torch.int32, device=coords.device)
     B, D, H, W = [int(v) for v in grid]
-    check(lib().ql_rulebook_subm(_ptr(coords), n_cap, _ptr(n_dev), B, D, H, W, _i32x3(k), _ptr(table), table.numel(), _ptr(nbr), _stream()),
-          "ql_rulebook_subm")
-    return nbr
+    check(lib().ql_rulebook_subm(_ptr(coords), n_cap, _ptr(n_dev), B, D, H, W, _i32x3(k), _ptr(table), table.numel(), _ptr(nbr),
+                                 _ptr(kmask), _stream()), "ql_rulebook_subm")
+    return (nbr, kmask) if (with_mask or kmask is not None) else nbr
 
 
-def rulebook_strided(coords: torch.Tensor, n_in_dev: Optional[torch.Tensor], grid, ksize, stride, pad, in_table: torch.Tensor,
-                     n_out_cap: int, out=None, workspace=None):
-    """Returns (out_coords [n_out_cap,4], n_out_dev [2] = (kept, found), out_table, nbr [tiles,K,128], out_grid (B,D,H,W))."""
-    _need_cuda(coords, n_in_dev, in_table)
+def rulebook_strided_workspace_bytes(grid, ksize, stride, pad) -> int:
+    B, D, H, W = [int(v) for v in grid]
+    n = int(lib().ql_rulebook_strided_workspace_bytes(B, D, H, W, _i32x3(triple(ksize)), _i32x3(triple(stride)), _i32x3(triple(pad))))
+    if n == 0:
+        raise QlidarError("invalid strided-conv geometry")
+    return n
+
+
+def rulebook_strided(coords: torch.Tensor, n_in_dev: Optional[torch.Tensor], grid, ksize, stride, pad,
+                     n_out_cap: int, out=None, workspace=None, kmask: Optional[torch.Tensor] = None):
+    """Returns (out_coords [n_out_cap,4] sorted by linear key, n_out_dev [2] = (kept, found), out_table, nbr [tiles,K,128],
+    out_grid (B,D,H,W), kmask [tiles, ceil(K/32)])."""
+    _need_cuda(coords, n_in_dev, kmask)
     k, s, p = triple(ksize), triple(stride), triple(pad)
     K = k[0] * k[1] * k[2]
     n_in_cap = coords.shape[0]
@@ -143,13 +158,15 @@ def rulebook_strided(coords: torch.Tensor, n_in_dev: Optional[torch.Tensor], gri
         nbr = torch.empty((num_tiles(n_out_cap), K, TILE_M), dtype=torch.int32, device=dev)
     else:
         out_coords, n_out_dev, out_table, nbr = out
-    ws_bytes = int(lib().ql_rulebook_strided_workspace_bytes(n_in_cap, K))
+    if kmask is None:
+        kmask = torch.zeros((num_tiles(n_out_cap), mask_words(K)), dtype=torch.int32, device=dev)
+    ws_bytes = rulebook_strided_workspace_bytes(grid, k, s, p)
     if workspace is None or workspace.numel() < ws_bytes:
         workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    check(lib().ql_rulebook_strided(_ptr(coords), n_in_cap, _ptr(n_in_dev), B, D, H, W, _i32x3(k), _i32x3(s), _i32x3(p), _ptr(in_table),
-                                    in_table.numel(), _ptr(out_coords), int(n_out_cap), _ptr(n_out_dev), _ptr(out_table),
-                                    out_table.numel(), _ptr(nbr), _ptr(workspace), workspace.numel(), _stream()), "ql_rulebook_strided")
-    return out_coords, n_out_dev, out_table, nbr, (B, od, oh, ow)
+    check(lib().ql_rulebook_strided(_ptr(coords), n_in_cap, _ptr(n_in_dev), B, D, H, W, _i32x3(k), _i32x3(s), _i32x3(p),
+                                    _ptr(out_coords), int(n_out_cap), _ptr(n_out_dev), _ptr(out_table), out_table.numel(), _ptr(nbr),
+                                    _ptr(kmask), _ptr(workspace), workspace.numel(), _stream()), "ql_rulebook_strided")
+    return out_coords, n_out_dev, out_table, nbr, (B, od, oh, ow), kmask
 
 
 def pack_weights(w: torch.Tensor) -> torch.Tensor:
@@ -173,8 +190,10 @@ def spconv_mma(feats: torch.Tensor, nbr: torch.Tensor, n_out_cap: int, n_out_dev
                w_packed: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, *, act_scale: Optional[torch.Tensor] = None,
                residual: Optional[torch.Tensor] = None, relu: bool = False, out: Optional[torch.Tensor] = None,
                out_dtype: torch.dtype = torch.float16, out_q: Optional[torch.Tensor] = None,
-               out_qscale: Optional[torch.Tensor] = None, absmax: Optional[torch.Tensor] = None) -> torch.Tensor:
-    _need_cuda(feats, nbr, n_out_dev, w_packed, scale, shift, act_scale, residual, out, out_q, out_qscale, absmax)
+               out_qscale: Optional[torch.Tensor] = None, absmax: Optional[torch.Tensor] = None,
+               kmask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """kmask: the rulebook's per-tile offset mask [tiles, ceil(K/32)] int32 (None = visit every offset)."""
+    _need_cuda(feats, nbr, n_out_dev, w_packed, scale, shift, act_scale, residual, out, out_q, out_qscale, absmax, kmask)
     if feats.dtype not in (torch.float16, torch.int8):
         raise QlidarError("spconv_mma gathers float16 rows or int8 codes")
     if residual is not None and residual.dtype != torch.float16:
@@ -186,7 +205,9 @@ def spconv_mma(feats: torch.Tensor, nbr: torch.Tensor, n_out_cap: int, n_out_dev
     raw = out.dtype == torch.int32
     if not raw and out.dtype not in (torch.float16, torch.float32):
         raise QlidarError("out must be float16/float32 (or int32 for the raw accumulators)")
-    check(lib().ql_spconv_mma(_ptr(feats), _DT[feats.dtype], _ptr(nbr), int(n_out_cap), _ptr(n_out_dev), c_in, int(c_out), K,
+    if kmask is not None and (kmask.dtype != torch.int32 or kmask.shape[0] < num_tiles(n_out_cap) or kmask.shape[1] != mask_words(K)):
+        raise QlidarError("kmask must be int32 [tiles, ceil(K/32)]")
+    check(lib().ql_spconv_mma(_ptr(feats), _DT[feats.dtype], _ptr(nbr), _ptr(kmask), int(n_out_cap), _ptr(n_out_dev), c_in, int(c_out), K,
                               _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(act_scale), _ptr(residual), 1 if relu else 0,
                               _ptr(out), _DT[out.dtype], _ptr(out_q), _ptr(out_qscale), _ptr(absmax), _stream()), "ql_spconv_mma")
     return out

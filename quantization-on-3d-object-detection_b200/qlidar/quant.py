@@ -99,7 +99,7 @@ class QConvNd(SparseModule):
             q, act_scale = ops.quantize_rows(f, self._act_absmax(f, n_dev), ops.QL_Q_CODES_PER_TENSOR, bits, n_dev)
             if ic_p != conv.in_channels:
                 q = torch.nn.functional.pad(q, (0, ic_p - conv.in_channels)).contiguous()
-            y = ops.spconv_mma(q, rb.nbr, rb.n_out, rb.n_out_dev, oc_p, packed, w_scale, shift, act_scale=act_scale, out_dtype=out_dtype)
+            y = ops.spconv_mma(q, rb.nbr, rb.n_out, rb.n_out_dev, oc_p, packed, w_scale, shift, act_scale=act_scale, out_dtype=out_dtype, kmask=rb.kmask)
         else:
             packed, ic_p, oc_p, w_scale, shift = self._prepared(f.device, "f16")
             if bits > 8:
@@ -110,7 +110,7 @@ class QConvNd(SparseModule):
                 fh, _ = ops.quantize_rows(f, self._act_absmax(f, n_dev), ops.QL_Q_FAKE_PER_CHANNEL, bits, n_dev)
             if ic_p != conv.in_channels:
                 fh = torch.nn.functional.pad(fh, (0, ic_p - conv.in_channels))
-            y = ops.spconv_mma(fh.contiguous(), rb.nbr, rb.n_out, rb.n_out_dev, oc_p, packed, w_scale, shift, out_dtype=out_dtype)
+            y = ops.spconv_mma(fh.contiguous(), rb.nbr, rb.n_out, rb.n_out_dev, oc_p, packed, w_scale, shift, out_dtype=out_dtype, kmask=rb.kmask)
         if oc_p != conv.out_channels:
             y = y[:, :conv.out_channels].contiguous()
         return _make_output(x, rb, y, conv.ndim)

@@ -18,8 +18,9 @@ from ._lib import QlidarError
 class IndiceData:
     """One cached rulebook ([EXT] spconv indice_dict entry): the tile-major neighbour table plus the output geometry."""
 
-    def __init__(self, nbr, n_out, n_out_dev, out_indices, out_table, out_grid, ksize, stride, pad, subm, in_indices):
+    def __init__(self, nbr, n_out, n_out_dev, out_indices, out_table, out_grid, ksize, stride, pad, subm, in_indices, kmask=None):
         self.nbr = nbr
+        self.kmask = kmask                # per-tile offset mask [tiles, ceil(K/32)] (empty slabs are skipped by the conv)
         self.n_out = n_out                # capacity (== exact row count in the module path)
         self.n_out_dev = n_out_dev        # device-side count or None
         self.out_indices = out_indices
@@ -209,8 +210,8 @@ class SparseConvolution(SparseModule):
         idx4 = x.indices4()
         n = idx4.shape[0]
         if self.subm:
-            nbr = ops.rulebook_subm(idx4, x._n_dev, grid, self._k3(), x.table())
-            data = IndiceData(nbr, n, x._n_dev, x.indices, x.table(), grid, self._k3(), (1, 1, 1), None, True, x.indices)
+            nbr, kmask = ops.rulebook_subm(idx4, x._n_dev, grid, self._k3(), x.table(), with_mask=True)
+            data = IndiceData(nbr, n, x._n_dev, x.indices, x.table(), grid, self._k3(), (1, 1, 1), None, True, x.indices, kmask)
         else:
             k, s, p = self._k3(), self._s3(), self._p3()
             od, oh, ow = ops.conv_out_shape(grid[1:], k, s, p)
@@ -218,12 +219,12 @@ class SparseConvolution(SparseModule):
             for d in range(3):
                 per_in *= -(-k[d] // s[d])
             cap = max(1, min(n * per_in, grid[0] * od * oh * ow))
-            out_c, n_out_dev, out_table, nbr, ogrid = ops.rulebook_strided(idx4, x._n_dev, grid, k, s, p, x.table(), cap)
+            out_c, n_out_dev, out_table, nbr, ogrid, kmask = ops.rulebook_strided(idx4, x._n_dev, grid, k, s, p, cap)
             n_out = int(n_out_dev[0].item())          # module API returns exact shapes (one sync per strided rulebook)
             out_c = out_c[:n_out]
             nbr = nbr[:ops.num_tiles(max(n_out, 1))]
             out_idx = out_c if self.ndim == 3 else out_c[:, [0, 2, 3]].contiguous()
-            data = IndiceData(nbr, n_out, None, out_idx, out_table, ogrid, k, s, p, False, x.indices)
+            data = IndiceData(nbr, n_out, None, out_idx, out_table, ogrid, k, s, p, False, x.indices, kmask)
         if self.indice_key is not None:
             x.indice_dict[self.indice_key] = data
         return data
@@ -261,7 +262,7 @@ class SparseConvolution(SparseModule):
         if self.bias is not None:
             shift[:self.out_channels] = self.bias.detach().float()
         out_dtype = torch.float32 if in_dtype == torch.float32 else torch.float16
-        y = ops.spconv_mma(fh, rb.nbr, rb.n_out, rb.n_out_dev, oc_p, packed, scale, shift, out_dtype=out_dtype)
+        y = ops.spconv_mma(fh, rb.nbr, rb.n_out, rb.n_out_dev, oc_p, packed, scale, shift, out_dtype=out_dtype, kmask=rb.kmask)
         if oc_p != self.out_channels:
             y = y[:, :self.out_channels].contiguous()
         return _make_output(x, rb, y, self.ndim)

@@ -38,35 +38,52 @@ def test_host_only_entry_points():
     assert lib.ql_hash_capacity(1000) == 2048
     assert lib.ql_hash_capacity(600000) == 2 ** 21
     assert lib.ql_rulebook_num_tiles(129) == 2
-    assert lib.ql_packed_weight_bytes(16, 16, 27, _lib.QL_F16) == 7 * 16 * 128
-    assert lib.ql_packed_weight_bytes(16, 16, 27, _lib.QL_S8) == 4 * 16 * 128
+    assert lib.ql_rulebook_mask_words(27) == 1 and lib.ql_rulebook_mask_words(125) == 4
+    # chunk = one kernel offset x one <=128-byte row segment, padded to 32 / 64 / 128 bytes
+    assert lib.ql_packed_weight_bytes(16, 16, 27, _lib.QL_F16) == 27 * 16 * 32
+    assert lib.ql_packed_weight_bytes(16, 16, 27, _lib.QL_S8) == 27 * 16 * 32       # 16-byte rows are zero padded to 32
+    assert lib.ql_packed_weight_bytes(128, 64, 27, _lib.QL_F16) == 27 * 2 * 64 * 128
     assert lib.ql_packed_weight_bytes(15, 16, 27, _lib.QL_F32) == 0
 
 
+def _chunk_geom(row_bytes):
+    if row_bytes > 128:
+        return 128, (row_bytes + 127) // 128
+    return (32 if row_bytes <= 32 else 64 if row_bytes <= 64 else 128), 1
+
+
 def test_pack_weights_host_layout():
-    """The packed image is the K-major SWIZZLE_128B shared-memory layout the tcgen05 descriptors assume:
-    byte (row r, 16B chunk c) of a 128-byte K stage lives at (r//8)*1024 + (r%8)*128 + ((c ^ (r%8))*16)."""
+    """The packed image is, per (kernel offset, 128-byte row segment) chunk, the K-major swizzled [c_out x CH] shared-memory
+    layout the tcgen05 B descriptors assume: 16-byte piece c of row r lives at
+    (r//8)*8*CH + (r%8)*CH + ((c ^ x(r))*16), x(r) = r%8 (SWIZZLE_128B), (r//2)%4 (64B), (r//4)%2 (32B)."""
     from qlidar import ops
     rng = np.random.default_rng(0)
     for dtype, cin, cout, K in [(torch.int8, 16, 16, 27), (torch.int8, 64, 32, 27), (torch.float16, 16, 48, 27),
-                                (torch.float16, 128, 64, 3), (torch.float16, 32, 256, 125)]:
+                                (torch.float16, 128, 64, 3), (torch.float16, 32, 256, 125), (torch.int8, 128, 128, 27),
+                                (torch.float16, 24, 16, 5)]:
         if dtype == torch.int8:
             w = torch.from_numpy(rng.integers(-127, 128, size=(cout, K, cin)).astype(np.int8))
         else:
             w = torch.from_numpy(rng.integers(-127, 128, size=(cout, K, cin)).astype(np.float32)).half()
         packed = ops.pack_weights(w).numpy()
-        raw = w.contiguous().view(torch.uint8).reshape(cout, -1).numpy()
-        kbytes = raw.shape[1]
-        stages = (kbytes + 127) // 128
-        assert packed.size == stages * cout * 128
-        flat = np.zeros((cout, stages * 128), dtype=np.uint8)
-        flat[:, :kbytes] = raw
-        for s in range(stages):
-            img = packed[s * cout * 128:(s + 1) * cout * 128]
-            for r in range(cout):
-                for c in range(8):
-                    off = (r // 8) * 1024 + (r % 8) * 128 + ((c ^ (r % 8)) * 16)
-                    assert np.array_equal(img[off:off + 16], flat[r, s * 128 + c * 16:s * 128 + c * 16 + 16])
+        raw = w.contiguous().view(torch.uint8).reshape(cout, K, -1).numpy()
+        row_bytes = raw.shape[2]
+        ch, nseg = _chunk_geom(row_bytes)
+        assert packed.size == K * nseg * cout * ch
+        seen = np.zeros(packed.size, dtype=bool)
+        for k in range(K):
+            for seg in range(nseg):
+                img = packed[(k * nseg + seg) * cout * ch:(k * nseg + seg + 1) * cout * ch]
+                base = (k * nseg + seg) * cout * ch
+                for r in range(cout):
+                    x = r % 8 if ch == 128 else ((r // 2) % 4 if ch == 64 else (r // 4) % 2)
+                    for c in range(ch // 16):
+                        off = (r // 8) * 8 * ch + (r % 8) * ch + ((c ^ x) * 16)
+                        b0 = seg * 128 + c * 16
+                        want = raw[r, k, b0:b0 + 16] if b0 < row_bytes else np.zeros(16, np.uint8)
+                        assert np.array_equal(img[off:off + 16], want)
+                        seen[base + off:base + off + 16] = True
+        assert seen.all()
 
 
 def test_ops_reject_cpu_tensors():

@@ -32,9 +32,10 @@ def test_rulebook_subm_bit_exact(ops, ksize):
     ref = O.rulebook_subm(coords, [D, H, W], ksize)
     c = dev(coords)
     table = ops.hash_build(c, None, (B, D, H, W))
-    nbr = ops.rulebook_subm(c, None, (B, D, H, W), ksize, table)
+    nbr, kmask = ops.rulebook_subm(c, None, (B, D, H, W), ksize, table, with_mask=True)
     got = tiles_to_nbr(nbr.cpu().numpy(), coords.shape[0])
     assert np.array_equal(got, ref)
+    assert np.array_equal(kmask.cpu().numpy().view(np.uint32), O.tile_kmask(ref))
     # rows of the last tile beyond N are -1
     tail = nbr.cpu().numpy().transpose(1, 0, 2).reshape(ref.shape[0], -1)[:, coords.shape[0]:]
     assert (tail == -1).all()
@@ -61,15 +62,16 @@ def test_rulebook_strided_bit_exact(ops, k, s, p):
     coords = random_coords(rng, B, D, H, W, 0.05)
     oc_ref, osh, nbr_ref = O.rulebook_strided(coords, [D, H, W], k, s, p)
     c = dev(coords)
-    table = ops.hash_build(c, None, (B, D, H, W))
     cap = oc_ref.shape[0] + 300
-    out_coords, n_out, out_table, nbr, ogrid = ops.rulebook_strided(c, None, (B, D, H, W), k, s, p, table, cap)
+    out_coords, n_out, out_table, nbr, ogrid, kmask = ops.rulebook_strided(c, None, (B, D, H, W), k, s, p, cap)
     n = int(n_out[0].item())
     assert int(n_out[1].item()) == n
     assert n == oc_ref.shape[0]
     assert list(ogrid[1:]) == list(osh)
-    assert np.array_equal(out_coords[:n].cpu().numpy(), oc_ref)          # same first-touch order
+    assert np.array_equal(out_coords[:n].cpu().numpy(), oc_ref)          # same order: ascending linear key
     assert np.array_equal(tiles_to_nbr(nbr.cpu().numpy(), n), nbr_ref)
+    tiles = (n + 127) // 128
+    assert np.array_equal(kmask[:tiles].cpu().numpy().view(np.uint32), O.tile_kmask(nbr_ref))
     # order-free form required by the parity gate: (k, in_coord, out_coord) sorted sets
     a = O.pairs_in_coord_space(tiles_to_nbr(nbr.cpu().numpy(), n), coords, out_coords[:n].cpu().numpy())
     b = O.pairs_in_coord_space(nbr_ref, coords, oc_ref)
@@ -85,9 +87,8 @@ def test_rulebook_strided_overflow_is_safe(ops):
     coords = random_coords(rng, B, D, H, W, 0.1)
     oc_ref, _, _ = O.rulebook_strided(coords, [D, H, W], 3, 2, 1)
     c = dev(coords)
-    table = ops.hash_build(c, None, (B, D, H, W))
     cap = oc_ref.shape[0] // 2
-    out_coords, n_out, out_table, nbr, ogrid = ops.rulebook_strided(c, None, (B, D, H, W), 3, 2, 1, table, cap)
+    out_coords, n_out, out_table, nbr, ogrid, kmask = ops.rulebook_strided(c, None, (B, D, H, W), 3, 2, 1, cap)
     assert n_out.tolist() == [cap, oc_ref.shape[0]]                     # (kept, found): overflow is reported
     assert np.array_equal(out_coords.cpu().numpy(), oc_ref[:cap])
     assert nbr.max().item() < coords.shape[0]
@@ -204,6 +205,44 @@ def test_spconv_f16_matches_fp64_oracle(ops, cin, cout, ksize, subm, stride, pad
     # fp16 operands are exact, products exact in fp32, only the fp32 accumulation order differs: 1e-4 of max|ref|
     err = (out.cpu().double() - ref).abs().max().item()
     assert err <= 1e-4 * ref.abs().max().item(), err
+
+
+@pytest.mark.parametrize("cin,cout,int8", [(16, 16, True), (32, 32, False), (64, 64, True), (128, 128, False)])
+def test_spconv_many_tiles_per_cta_with_offset_mask(ops, cin, cout, int8):
+    """> 3 tiles per persistent CTA (148 SMs) so the A/B ring and the accumulator double buffer wrap many times, through
+    the GPU-built rulebook and its per-tile offset mask; int8: accumulators bit-exact, f16: 1e-4 of max|ref|."""
+    rng = np.random.default_rng(70 + cin)
+    S = 250
+    coords = O.synth_surface_sheet(S, seed=7, depth=12)                 # 62 500 sites -> 489 tiles
+    coords = coords[np.argsort(O._lin(coords, [12, S, S]), kind="stable")]
+    N = coords.shape[0]
+    nbr_ref = O.rulebook_subm(coords, [12, S, S], 3)
+    c = dev(coords)
+    table = ops.hash_build(c, None, (1, 12, S, S))
+    nbr, kmask = ops.rulebook_subm(c, None, (1, 12, S, S), 3, table, with_mask=True)
+    assert np.array_equal(tiles_to_nbr(nbr.cpu().numpy(), N), nbr_ref)
+    km = kmask.cpu().numpy().view(np.uint32)
+    assert np.array_equal(km, O.tile_kmask(nbr_ref))
+    assert np.mean([bin(int(v)).count("1") for v in km[:, 0]]) < 24      # the mask really skips slabs on this input
+    one = torch.ones(cout, device="cuda")
+    zero = torch.zeros(cout, device="cuda")
+    if int8:
+        qx = torch.from_numpy(rng.integers(-127, 128, size=(N, cin)).astype(np.int8))
+        qw = torch.from_numpy(rng.integers(-127, 128, size=(cout, 3, 3, 3, cin)).astype(np.int8))
+        ref = O.sparse_conv_int(qx, nbr_ref, qw)
+        out = torch.full((N, cout), -12345, dtype=torch.int32, device="cuda")
+        ops.spconv_mma(dev(qx), nbr, N, None, cout, ops.pack_weights(qw.reshape(cout, 27, cin)).cuda(), one, zero, out=out, kmask=kmask)
+        assert torch.equal(out.cpu(), ref), f"mismatches: {(out.cpu() != ref).sum().item()} of {ref.numel()}"
+        out2 = torch.full((N, cout), -12345, dtype=torch.int32, device="cuda")
+        ops.spconv_mma(dev(qx), nbr, N, None, cout, ops.pack_weights(qw.reshape(cout, 27, cin)).cuda(), one, zero, out=out2)
+        assert torch.equal(out2.cpu(), ref)                              # without the mask: same accumulators
+    else:
+        x = torch.from_numpy(rng.normal(size=(N, cin)).astype(np.float32)).half()
+        qw = torch.from_numpy(rng.integers(-127, 128, size=(cout, 27, cin)).astype(np.int8))
+        ref = O.sparse_conv_auto(x.float(), nbr_ref, qw.float().reshape(cout, 3, 3, 3, cin)).double()
+        out = ops.spconv_mma(dev(x), nbr, N, None, cout, ops.pack_weights(qw.half()).cuda(), one, zero, out_dtype=torch.float32, kmask=kmask)
+        err = (out.cpu().double() - ref).abs().max().item()
+        assert err <= 1e-4 * ref.abs().max().item(), err
 
 
 def test_spconv_epilogue_fusion(ops):

@@ -51,7 +51,7 @@ def test_rulebook_permutation_invariance():
     assert np.array_equal(O.pairs_in_coord_space(n1, coords, oc1), O.pairs_in_coord_space(n2, coords[perm], oc2))
 
 
-def test_strided_first_touch_order_matches_naive_loop():
+def test_strided_sorted_key_order_matches_naive_loop():
     rng = np.random.default_rng(2)
     coords = random_coords(rng, 2, 5, 9, 9, 0.2)
     oc, osh, _ = O.rulebook_strided(coords, [5, 9, 9], 3, 2, 1)
@@ -69,7 +69,9 @@ def test_strided_first_touch_order_matches_naive_loop():
                     if o not in seen:
                         seen[o] = len(order)
                         order.append(o)
-    assert np.array_equal(oc, np.asarray(order, dtype=np.int32))
+    # the numbering rule: ascending linear key ((b*Do+z)*Ho+y)*Wo+x == lexicographic (b, z, y, x)
+    assert np.array_equal(oc, np.asarray(sorted(order), dtype=np.int32))
+    assert len(order) == len(set(order))
 
 
 def test_backbone_shapes_match_reference_comments():
