@@ -13,12 +13,15 @@
 // 75 % (one write wavefront per returning 32-byte sector plus zero fills plus the tensor core's operand reads) with
 // DRAM at 17 %, see profiles/r01_conv_v2_smem_gather.md; TMEM stores run at 256 B/clk and are off that pipe.
 //
-// K is cut into chunks: one chunk = one kernel offset x one <=128-byte segment of the input row
-// (CH = 32 / 64 / 128 bytes => 1 / 2 / 4 MMA k-steps).  Roles (18 warps):
-//   warps 0-11  gather producers : 3 teams x 4 warps; warp w owns TMEM lanes 32*(w%4)..+31; teams take chunk groups
-//                                  round-robin; per chunk: nbr index (LDS from the tile's rulebook slab), CH bytes of the
-//                                  neighbour row (or zeros), tcgen05.st into the chunk's A slot, mbarrier arrive; the loads
-//                                  of a team's next group are issued before the current group is stored
+// K is cut into sub-chunks: one sub-chunk = one kernel offset x one <=128-byte segment of the input row
+// (CH = 32 / 64 / 128 bytes => 1 / 2 / 4 MMA k-steps).  128/CH consecutive sub-chunks form a unit (32 TMEM columns =
+// 32 registers per producer thread), kTeams units form a ring slot: one full/empty mbarrier pair and one pass of the
+// single MMA-issuing thread per slot (that thread's instruction stream is the serial bottleneck of the kernel, so the
+// work per barrier round trip is made as large as TMEM allows).  Roles (18 warps):
+//   warps 0-11  gather producers : 3 teams x 4 warps; warp w owns TMEM lanes 32*(w%4)..+31; team t fills unit t of every
+//                                  slot; per sub-chunk: nbr index (LDS from the tile's rulebook slab), CH bytes of the
+//                                  neighbour row (or zeros); one tcgen05.st.x32 per unit, mbarrier arrive; the loads of a
+//                                  team's next unit are issued before the current unit is stored
 //   warps 12-15 epilogue         : tcgen05.ld accumulators -> dequant*BN scale/shift (+residual) (+ReLU)
 //                                  -> fp16/fp32 rows (+ int8 re-quantised rows, + per-channel absmax)
 //   warp  16    MMA issuer       : one lane issues tcgen05.mma (kind::f16 or kind::i8), accumulators in TMEM
@@ -42,7 +45,8 @@ constexpr int kEpilogueWarp0 = kProducerWarps;            // warps 12..15 (warp 
 constexpr int kMmaWarp = kEpilogueWarp0 + 4;              // 16
 constexpr int kLoaderWarp = kMmaWarp + 1;                 // 17
 constexpr int kThreadsTotal = (kLoaderWarp + 1) * 32;     // 576
-constexpr int kMaxSlots = 8;
+constexpr int kMaxSlots = 4;
+constexpr int kSlotCols = 32 * kTeams;                    // TMEM columns per ring slot
 constexpr int kMaskWords = 4;                             // kernel volumes up to 128 (3^3, 5^3)
 constexpr int kTmemCols = 512;
 constexpr int kSmemBudget = 232448;                       // 227 KB opt-in maximum per CTA
@@ -55,6 +59,7 @@ struct ConvParams {
     const int* n_out_dev;
     int64_t n_out_cap;
     int row_bytes;          // c_in * elem size
+    int wide;               // rows (and the feature base) are 32-byte aligned: gather with 256-bit loads
     int c_out, kvol, nseg, mask_words;
     const uint8_t* w_packed;
     const float* scale;
@@ -67,8 +72,7 @@ struct ConvParams {
     int8_t* out_q;
     const float* out_qscale;
     float* absmax;
-    int n_slots;            // A/B ring depth in groups (power of two)
-    int slot_log2;
+    int n_slots;            // A/B ring depth in slots
     int n_acc;              // accumulator buffers in TMEM (2, or 1 when 2*c_out does not fit beside the A ring)
     int a_col0;             // first TMEM column of the A ring
     int resident;           // 1: every weight chunk lives in shared memory for the whole kernel (no per-chunk B copies)
@@ -140,6 +144,13 @@ __device__ __forceinline__ uint64_t umma_desc_b(uint32_t smem_addr) {
     return d;
 }
 
+// 256-bit load (LDG.E.ENL2.256, sm_100): one full 32-byte sector per lane, half the L1 wavefronts of two 128-bit loads when
+// every lane reads a different row.  Needs 32-byte alignment.
+__device__ __forceinline__ void ldg32(const uint8_t* p, uint32_t (&v)[8]) {
+    asm volatile("ld.global.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+}
 __device__ __forceinline__ uint4 ldg16(const uint8_t* p) {
     uint4 v;
     asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
@@ -203,7 +214,7 @@ __device__ __forceinline__ int load_tile_mask_smem(uint32_t addr, int nseg, uint
     return n * nseg;
 }
 
-template <bool kInt8, int CH>
+template <bool kInt8, int CH, bool kResident>
 __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams p) {
     constexpr int kAReg = CH / 4;                          // 32-bit TMEM columns (registers) per chunk
     constexpr int kGroup = 128 / CH;                       // sub-chunks per group == per ring slot (128 bytes of K, 32 TMEM columns)
@@ -226,7 +237,7 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            ql_mbar_init(ql_smem_u32(&misc->full[s]), p.resident ? 4 : 4 + 1);   // one arrive per producer warp of the team (+ the loader's expect_tx)
+            ql_mbar_init(ql_smem_u32(&misc->full[s]), kProducerWarps + (kResident ? 0 : 1));   // every producer warp (+ the loader's expect_tx)
             ql_mbar_init(ql_smem_u32(&misc->empty[s]), 1);         // tcgen05.commit
         }
         for (int i = 0; i < 2; ++i) {
@@ -258,29 +269,28 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
     ql_tc_fence_after();
     const uint32_t tmem_base = misc->tmem_base;
     const uint32_t b_sub_bytes = (uint32_t)p.c_out * CH;     // one weight sub-chunk: [c_out x CH bytes]
-    const uint32_t smask = (uint32_t)S - 1u;                 // S is a power of two
-    const int slog = p.slot_log2;
+    constexpr int kSlotSubs = kGroup * kTeams;               // sub-chunks per ring slot
 
     if (warp < kProducerWarps) {
         // ============================ gather producers ============================
         const int q = warp & 3;                              // TMEM lane quarter
         const int team = warp >> 2;
         const int r = q * 32 + lane;                         // row in tile == TMEM lane
-        const uint32_t a_lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.a_col0;
+        const uint32_t a_lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.a_col0 + (uint32_t)(team * 32);
         const uint32_t nbr_s0 = smem_base_u32 + (uint32_t)p.off_nbr;            // buffer b: mask at +b*stride, slabs at +16
         const uint32_t nbr_s = nbr_s0 + 16u + (uint32_t)r * 4u;
         const uint32_t nbr_stride = (uint32_t)p.nbr_stride, nbmask = (uint32_t)p.nbr_bufs - 1u;
 
-        // Walks this team's groups across the CTA's tiles.  Groups are dealt to the teams by a counter (gg) that runs
-        // across tiles, so a team's consecutive groups are kTeams <= n_slots ring positions apart: it can never be two
-        // ring phases ahead of the barrier it polls (mbarrier parity waits alias at a distance of two phases).
-        struct Grp { uint32_t gg; int n; int c0; uint32_t buf_off; };
+        // Walks the CTA's tiles slot by slot; this team owns unit `team` of every slot (a unit past the tile's last
+        // sub-chunk is empty: nothing is loaded or stored, but the slot's barriers are still honoured, so every warp
+        // sees every ring phase and the parity waits cannot alias).
+        struct Unit { uint32_t ring, ph; int n; int c0; uint32_t buf_off; };
         int64_t tile = blockIdx.x;
-        uint32_t it = 0, gg = 0;
-        int n_sub = 0, n_groups = 0, g = 0;
+        uint32_t it = 0, ring = 0, ph = 0;
+        int n_sub = 0, n_slot_t = 0, sl = 0;
         bool have_tile = false, ready = false;
-        // returns 1 = group found, 0 = no more work, 2 = the next tile's rulebook slab has not landed yet (only if !blocking)
-        auto next_group = [&](bool blocking, Grp& out) -> int {
+        // returns 1 = unit found, 0 = no more work, 2 = the next tile's rulebook slab has not landed yet (only if !blocking)
+        auto next_unit = [&](bool blocking, Unit& out) -> int {
             while (true) {
                 if (!have_tile) {
                     if (tile >= n_tiles) return 0;
@@ -293,19 +303,18 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
                     else if (!ql_mbar_test_wait(bar, par)) return 2;
                     uint32_t mask[kMaskWords];
                     n_sub = load_tile_mask_smem(nbr_s0 + nb * nbr_stride, p.nseg, mask);
-                    n_groups = (n_sub + kGroup - 1) / kGroup;
-                    g = 0; ready = true;
+                    n_slot_t = (n_sub + kSlotSubs - 1) / kSlotSubs;
+                    sl = 0; ready = true;
                 }
-                while (g < n_groups) {
-                    const uint32_t mygg = gg++;
-                    const int gi = g++;
-                    if ((int)(mygg % (uint32_t)kTeams) == team) {
-                        out.gg = mygg;
-                        out.c0 = gi * kGroup;
-                        out.n = n_sub - out.c0 < kGroup ? n_sub - out.c0 : kGroup;
-                        out.buf_off = (it & nbmask) * nbr_stride;
-                        return 1;
-                    }
+                if (sl < n_slot_t) {
+                    out.ring = ring; out.ph = ph;
+                    out.c0 = (sl * kTeams + team) * kGroup;
+                    const int rem = n_sub - out.c0;
+                    out.n = rem < 0 ? 0 : (rem < kGroup ? rem : kGroup);
+                    out.buf_off = (it & nbmask) * nbr_stride;
+                    ++sl;
+                    if (++ring == (uint32_t)S) { ring = 0; ph ^= 1u; }
+                    return 1;
                 }
                 // every index this warp needs from the tile's slab has been read: hand the buffer back
                 __syncwarp();
@@ -313,64 +322,79 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
                 tile += gridDim.x; ++it; have_tile = false;
             }
         };
-        // loads of one group: kGroup sub-chunks of CH bytes = 32 registers = the 32 TMEM columns of the group's slot
-        auto issue = [&](const Grp& grp, uint32_t (&v)[32]) {
+        // loads of one unit: kGroup sub-chunks of CH bytes = 32 registers = the unit's 32 TMEM columns
+        auto issue = [&](const Unit& u, uint32_t (&v)[32]) {
             int idx[kGroup], boff[kGroup];
 #pragma unroll
             for (int j = 0; j < kGroup; ++j) {
                 idx[j] = -1; boff[j] = 0;
-                if (j < grp.n) {
-                    const int lc = grp.c0 + j;
+                if (j < u.n) {
+                    const int lc = u.c0 + j;
                     int ord = lc;                            // ordinal of the sub-chunk's offset among the tile's non-empty ones
                     if (CH == 128 && p.nseg > 1) { ord = lc / p.nseg; boff[j] = (lc - ord * p.nseg) * 128; }
-                    idx[j] = ql_lds_s32(nbr_s + grp.buf_off + (uint32_t)ord * (QL_TILE_M * 4u));
+                    idx[j] = ql_lds_s32(nbr_s + u.buf_off + (uint32_t)ord * (QL_TILE_M * 4u));
                 }
             }
+            if (p.wide) {                                    // rows are multiples of 32 bytes: 256-bit loads
 #pragma unroll
-            for (int j = 0; j < kGroup; ++j) {
-                const uint8_t* src = p.feats + (int64_t)(idx[j] < 0 ? 0 : idx[j]) * p.row_bytes + boff[j];
+                for (int j = 0; j < kGroup; ++j) {
+                    const uint8_t* src = p.feats + (int64_t)(idx[j] < 0 ? 0 : idx[j]) * p.row_bytes + boff[j];
 #pragma unroll
-                for (int t = 0; t < CH / 16; ++t) {
-                    uint4 x = make_uint4(0u, 0u, 0u, 0u);
-                    if (idx[j] >= 0 && boff[j] + t * 16 < p.row_bytes) x = ldg16(src + t * 16);
-                    const int o = j * kAReg + 4 * t;
-                    v[o] = x.x; v[o + 1] = x.y; v[o + 2] = x.z; v[o + 3] = x.w;
+                    for (int t = 0; t < CH / 32; ++t) {
+                        uint32_t x[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                        if (idx[j] >= 0 && boff[j] + t * 32 < p.row_bytes) ldg32(src + t * 32, x);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[j * kAReg + 8 * t + e] = x[e];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < kGroup; ++j) {
+                    const uint8_t* src = p.feats + (int64_t)(idx[j] < 0 ? 0 : idx[j]) * p.row_bytes + boff[j];
+#pragma unroll
+                    for (int t = 0; t < CH / 16; ++t) {
+                        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                        if (idx[j] >= 0 && boff[j] + t * 16 < p.row_bytes) x = ldg16(src + t * 16);
+                        const int o = j * kAReg + 4 * t;
+                        v[o] = x.x; v[o + 1] = x.y; v[o + 2] = x.z; v[o + 3] = x.w;
+                    }
                 }
             }
         };
-        auto store = [&](const Grp& grp, const uint32_t (&v)[32]) {
-            const uint32_t s = grp.gg & smask, ph = (grp.gg >> slog) & 1u;
-            ql_mbar_wait(ql_smem_u32(&misc->empty[s]), ph ^ 1u);                 // the MMAs that read this slot have completed
-            ql_tc_fence_after();
-            tmem_st<32>(a_lane_base + s * 32u, v);
-            tmem_st_wait();
-            ql_tc_fence_before();
+        auto store = [&](const Unit& u, const uint32_t (&v)[32]) {
+            ql_mbar_wait(ql_smem_u32(&misc->empty[u.ring]), u.ph ^ 1u);         // the MMAs that read this slot have completed
+            if (u.n > 0) {
+                ql_tc_fence_after();
+                tmem_st<32>(a_lane_base + u.ring * (uint32_t)kSlotCols, v);
+                tmem_st_wait();
+                ql_tc_fence_before();
+            }
             __syncwarp();
-            if (lane == 0) ql_mbar_arrive(ql_smem_u32(&misc->full[s]));
+            if (lane == 0) ql_mbar_arrive(ql_smem_u32(&misc->full[u.ring]));
         };
-        // software pipeline, two register buffers: the next group's loads are in flight while the current group waits for
-        // its ring slot.  A group that is still held in registers is never kept waiting on a rulebook slab (that could
-        // deadlock against the loader, which streams weights only as fast as stored groups are consumed): if the next
-        // tile's slab is not there yet the held group is stored first.
+        // software pipeline, two register buffers: the next unit's loads are in flight while the current unit waits for
+        // its ring slot.  A unit that is still held in registers is never kept waiting on a rulebook slab (that could
+        // deadlock against the loader, which streams weights only as fast as stored units are consumed): if the next
+        // tile's slab is not there yet the held unit is stored first.
         uint32_t va[32], vb[32];
-        Grp ga, gb;
-        int have_a = next_group(true, ga);
-        if (have_a == 1) issue(ga, va);
+        Unit ua, ub;
+        int have_a = next_unit(true, ua);
+        if (have_a == 1) issue(ua, va);
         while (have_a == 1) {
-            int have_b = next_group(false, gb);
-            if (have_b == 1) issue(gb, vb);
-            store(ga, va);
+            int have_b = next_unit(false, ub);
+            if (have_b == 1) issue(ub, vb);
+            store(ua, va);
             if (have_b == 2) {
-                have_b = next_group(true, gb);
-                if (have_b == 1) issue(gb, vb);
+                have_b = next_unit(true, ub);
+                if (have_b == 1) issue(ub, vb);
             }
             if (have_b != 1) break;
-            have_a = next_group(false, ga);
-            if (have_a == 1) issue(ga, va);
-            store(gb, vb);
+            have_a = next_unit(false, ua);
+            if (have_a == 1) issue(ua, va);
+            store(ub, vb);
             if (have_a == 2) {
-                have_a = next_group(true, ga);
-                if (have_a == 1) issue(ga, va);
+                have_a = next_unit(true, ua);
+                if (have_a == 1) issue(ua, va);
             }
         }
     } else if (warp < kMmaWarp) {
@@ -470,9 +494,9 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
         }
     } else if (warp == kMmaWarp) {
         // =============================== MMA issuer ===============================
-        // One elected lane runs the whole loop (nothing in it is warp-collective).  Every group of every tile passes through
-        // this single instruction stream, so it is kept short: ring position and phase are counters, the tile mask is two
-        // 64-bit words walked with ffs, descriptors differ only in their low word.
+        // One elected lane runs the whole loop (nothing in it is warp-collective).  Every sub-chunk of every tile passes
+        // through this single instruction stream, so it is kept short: ring position and phase are counters, the tile
+        // mask is walked with ffs, descriptors differ only in their low word.
         if (ql_elect_one()) {
             const uint32_t idesc = make_idesc<kInt8>(p.c_out);
             const uint64_t bdesc0 = umma_desc_b<CH>(smem_base_u32);
@@ -480,12 +504,14 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
             const uint32_t b_sub16 = b_sub_bytes >> 4;
             const uint32_t a_base = tmem_base + (uint32_t)p.a_col0;
             const uint32_t full0 = ql_smem_u32(&misc->full[0]), empty0 = ql_smem_u32(&misc->empty[0]);
-            const int nseg = p.nseg, resident = p.resident;
-            uint32_t s = 0, ph = 0, it = 0;
-            if (resident && (int64_t)blockIdx.x < n_tiles) ql_mbar_wait(ql_smem_u32(&misc->w_full), 0);
+            const int nseg = p.nseg;
+            const bool narrow = p.mask_words == 1;                 // kernel volume <= 32: the mask is one word
+            uint32_t ring = 0, ph = 0, it = 0;
+            if (kResident && (int64_t)blockIdx.x < n_tiles) ql_mbar_wait(ql_smem_u32(&misc->w_full), 0);
             uint32_t mask_next[kMaskWords];
             int n_sub_next = (int64_t)blockIdx.x < n_tiles ? load_tile_mask(p, blockIdx.x, mask_next) : 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                uint32_t m0 = mask_next[0];
                 uint64_t m_lo = (uint64_t)mask_next[0] | ((uint64_t)mask_next[1] << 32);
                 uint64_t m_hi = (uint64_t)mask_next[2] | ((uint64_t)mask_next[3] << 32);
                 const int n_sub = n_sub_next;
@@ -497,35 +523,36 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
                 const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.c_out);
                 uint32_t accumulate = 0u;
                 int k = 0, seg = nseg;                           // seg == nseg: take the next offset from the mask
-                for (int c0 = 0; c0 < n_sub; c0 += kGroup) {
-                    ql_mbar_wait(full0 + s * 8u, ph);
+                for (int c0 = 0; c0 < n_sub; c0 += kSlotSubs) {
+                    ql_mbar_wait(full0 + ring * 8u, ph);
                     ql_tc_fence_after();
-#pragma unroll
-                    for (int j = 0; j < kGroup; ++j) {
-                        if (c0 + j < n_sub) {
-                            uint32_t b_idx = s * kGroup + (uint32_t)j;   // streamed: the sub-chunk's place in the ring slot
-                            if (resident) {                              // resident: its place in the packed tensor
-                                if (seg == nseg) {
-                                    seg = 0;
-                                    if (m_lo) { k = __ffsll((long long)m_lo) - 1; m_lo &= m_lo - 1; }
-                                    else { k = 63 + __ffsll((long long)m_hi); m_hi &= m_hi - 1; }
-                                }
-                                b_idx = (uint32_t)(k * nseg + seg);
-                                ++seg;
+                    const int n_in = n_sub - c0 < kSlotSubs ? n_sub - c0 : kSlotSubs;
+                    const uint32_t a_slot = a_base + ring * (uint32_t)kSlotCols;
+                    const uint32_t b_slot = ring * (uint32_t)kSlotSubs;
+                    for (int j = 0; j < n_in; ++j) {
+                        uint32_t b_idx = b_slot + (uint32_t)j;       // streamed: the sub-chunk's place in the ring slot
+                        if (kResident) {                             // resident: its place in the packed tensor
+                            if (seg == nseg) {
+                                seg = 0;
+                                if (narrow) { k = __ffs((int)m0) - 1; m0 &= m0 - 1u; }
+                                else if (m_lo) { k = __ffsll((long long)m_lo) - 1; m_lo &= m_lo - 1; }
+                                else { k = 63 + __ffsll((long long)m_hi); m_hi &= m_hi - 1; }
                             }
-                            const uint32_t blo = bdesc_lo0 + b_idx * b_sub16;
-                            const uint32_t a_tmem = a_base + s * 32u + (uint32_t)(j * kAReg);
+                            b_idx = (uint32_t)(k * nseg + seg);
+                            ++seg;
+                        }
+                        const uint32_t blo = bdesc_lo0 + b_idx * b_sub16;
+                        const uint32_t a_tmem = a_slot + (uint32_t)(j * kAReg);
 #pragma unroll
-                            for (int ks = 0; ks < CH / 32; ++ks) {   // one k-step = 32 bytes of K: +8 TMEM columns, +2 in the desc (addr >> 4)
-                                const uint64_t bdesc = ((uint64_t)bdesc_hi << 32) | (uint64_t)(blo + (uint32_t)(ks * 2));
-                                tc_mma_ts<kInt8>(d_tmem, a_tmem + (uint32_t)(ks * 8), bdesc, idesc, accumulate);
-                                accumulate = 1u;
-                            }
+                        for (int ks = 0; ks < CH / 32; ++ks) {       // one k-step = 32 bytes of K: +8 TMEM columns, +2 in the desc (addr >> 4)
+                            const uint64_t bdesc = ((uint64_t)bdesc_hi << 32) | (uint64_t)(blo + (uint32_t)(ks * 2));
+                            tc_mma_ts<kInt8>(d_tmem, a_tmem + (uint32_t)(ks * 8), bdesc, idesc, accumulate);
+                            accumulate = 1u;
                         }
                     }
-                    ql_tc_commit(empty0 + s * 8u);
-                    if (c0 + kGroup >= n_sub) ql_tc_commit(ql_smem_u32(&misc->acc_full[a]));
-                    if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+                    ql_tc_commit(empty0 + ring * 8u);
+                    if (c0 + kSlotSubs >= n_sub) ql_tc_commit(ql_smem_u32(&misc->acc_full[a]));
+                    if (++ring == (uint32_t)S) { ring = 0; ph ^= 1u; }
                 }
             }
         }
@@ -559,8 +586,8 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
                 __syncwarp();
             }
         };
-        uint32_t gg = 0, it = 0;
-        if (p.resident && (int64_t)blockIdx.x < n_tiles) {
+        uint32_t it = 0;
+        if (kResident && (int64_t)blockIdx.x < n_tiles) {
             // the whole packed weight tensor, 32 lanes x (w_bytes / 32) bytes
             const uint32_t bar = ql_smem_u32(&misc->w_full);
             const uint32_t per_lane = (uint32_t)p.w_bytes / 32u;
@@ -588,40 +615,37 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
             prefetch_nbr(t, itn, m, n_slabs);
         };
         for (int i = 0; i < p.nbr_bufs - 1; ++i) prefetch_step();
-        // streamed weights: a batch of S/2 groups per pass, lane (gl, j) = sub-chunk j of the batch's gl-th group
-        const int lb = S / 2;
-        const int gl = lane / kGroup, j = lane % kGroup;
+        // streamed weights: one slot per pass, lane j = the slot's j-th sub-chunk
+        uint32_t ring = 0, ph = 0;
         uint32_t mask_next[kMaskWords];
-        int n_sub_next = (!p.resident && (int64_t)blockIdx.x < n_tiles) ? load_tile_mask(p, blockIdx.x, mask_next) : 0;
+        int n_sub_next = (!kResident && (int64_t)blockIdx.x < n_tiles) ? load_tile_mask(p, blockIdx.x, mask_next) : 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             prefetch_step();
-            if (p.resident) continue;
+            if constexpr (!kResident) {
             uint32_t mask[kMaskWords];
 #pragma unroll
             for (int i = 0; i < kMaskWords; ++i) mask[i] = mask_next[i];
             const int n_sub = n_sub_next;
             if (tile + gridDim.x < n_tiles) n_sub_next = load_tile_mask(p, tile + gridDim.x, mask_next);
-            const int n_groups = (n_sub + kGroup - 1) / kGroup;
-            for (int g0 = 0; g0 < n_groups; g0 += lb) {
-                const int g = g0 + gl, sub = g * kGroup + j;
-                const bool mine = gl < lb && sub < n_sub;
-                const uint32_t ggl = gg + (uint32_t)g, s = ggl & smask;
-                if (mine) ql_mbar_wait(ql_smem_u32(&misc->empty[s]), ((ggl >> slog) & 1u) ^ 1u);
-                __syncwarp();
-                if (mine && j == 0) {
-                    const int n_in = n_sub - g * kGroup < kGroup ? n_sub - g * kGroup : kGroup;
-                    ql_mbar_arrive_expect_tx(ql_smem_u32(&misc->full[s]), (uint32_t)n_in * b_sub_bytes);
+            for (int c0 = 0; c0 < n_sub; c0 += kSlotSubs) {
+                const int sub = c0 + lane;
+                const bool mine = lane < kSlotSubs && sub < n_sub;
+                ql_mbar_wait(ql_smem_u32(&misc->empty[ring]), ph ^ 1u);
+                if (lane == 0) {
+                    const int n_in = n_sub - c0 < kSlotSubs ? n_sub - c0 : kSlotSubs;
+                    ql_mbar_arrive_expect_tx(ql_smem_u32(&misc->full[ring]), (uint32_t)n_in * b_sub_bytes);
                 }
                 __syncwarp();
                 if (mine) {
                     const int ord = sub / p.nseg, seg = sub - ord * p.nseg;
                     const int k = nth_set_bit(mask, ord);
-                    ql_bulk_g2s(smem_base_u32 + (s * kGroup + (uint32_t)j) * b_sub_bytes,
-                                p.w_packed + (int64_t)(k * p.nseg + seg) * b_sub_bytes, b_sub_bytes, ql_smem_u32(&misc->full[s]));
+                    ql_bulk_g2s(smem_base_u32 + (ring * (uint32_t)kSlotSubs + (uint32_t)lane) * b_sub_bytes,
+                                p.w_packed + (int64_t)(k * p.nseg + seg) * b_sub_bytes, b_sub_bytes, ql_smem_u32(&misc->full[ring]));
                 }
                 __syncwarp();
+                if (++ring == (uint32_t)S) { ring = 0; ph ^= 1u; }
             }
-            gg += (uint32_t)n_groups;
+            }
         }
     }
 
@@ -656,12 +680,16 @@ inline uint32_t chunk_sw_offset(int ch, uint32_t r, uint32_t c16) {
     return (r >> 3) * (uint32_t)(8 * ch) + (r & 7u) * (uint32_t)ch + ((c16 ^ x) << 4);
 }
 
+template <bool kInt8, int CH, bool kResident>
+cudaError_t launch2(const ConvParams& p, int grid, size_t smem_bytes, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(k_spconv_ts<kInt8, CH, kResident>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    k_spconv_ts<kInt8, CH, kResident><<<grid, kThreadsTotal, smem_bytes, st>>>(p);
+    return cudaPeekAtLastError();                     // left pending for ql_last_cuda_error()
+}
 template <bool kInt8, int CH>
 cudaError_t launch(const ConvParams& p, int grid, size_t smem_bytes, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(k_spconv_ts<kInt8, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) return e;
-    k_spconv_ts<kInt8, CH><<<grid, kThreadsTotal, smem_bytes, st>>>(p);
-    return cudaPeekAtLastError();                     // left pending for ql_last_cuda_error()
+    return p.resident ? launch2<kInt8, CH, true>(p, grid, smem_bytes, st) : launch2<kInt8, CH, false>(p, grid, smem_bytes, st);
 }
 
 }  // namespace
@@ -715,31 +743,36 @@ extern "C" int ql_spconv_mma(const void* feats, int32_t in_dtype, const int32_t*
     ConvParams p;
     p.feats = (const uint8_t*)feats; p.nbr = nbr; p.kmask = tile_kmask; p.n_out_dev = n_out_dev; p.n_out_cap = n_out_cap;
     p.row_bytes = c_in * es; p.c_out = c_out; p.kvol = kvol;
+    p.wide = (p.row_bytes % 32 == 0 && ((uintptr_t)feats & 31) == 0) ? 1 : 0;
     const ChunkGeom g = chunk_geom(p.row_bytes);
     p.nseg = g.nseg; p.mask_words = (kvol + 31) / 32;
     p.w_packed = (const uint8_t*)w_packed; p.scale = scale; p.shift = shift; p.act_scale_dev = act_scale_dev;
     p.residual = (const __half*)residual_f16; p.relu = relu; p.out = out; p.out_dtype = out_dtype;
     p.out_q = out_q; p.out_qscale = out_qscale; p.absmax = absmax;
 
-    // ring depth (groups of 128 bytes of K = 32 TMEM columns): bounded by the TMEM columns left beside the accumulators
-    // and, when the weights are streamed, by shared memory; a power of two >= kTeams.
+    // ring depth in slots (kTeams units of 32 TMEM columns): bounded by the TMEM columns left beside the accumulators
+    // and, when the weights are streamed, by shared memory
     const int misc_bytes = (int)sizeof(MiscSmem) + 4 * c_out * 4;
     const int b_sub = c_out * g.ch;
-    const int b_slot = c_out * 128;                              // a group's weight sub-chunks
+    const int b_slot = kTeams * c_out * 128;                     // a slot's weight sub-chunks
     p.nbr_stride = (16 + kvol * QL_TILE_M * 4 + 127) & ~127;
-    p.nbr_bufs = 4 * p.nbr_stride <= 64 * 1024 ? 4 : 2;
+    p.n_acc = (kTmemCols - 2 * c_out) / kSlotCols >= 2 ? 2 : 1;
+    int S = (kTmemCols - p.n_acc * c_out) / kSlotCols;
+    if (S > kMaxSlots) S = kMaxSlots;
+    p.w_bytes = kvol * g.nseg * b_sub;
+    for (p.nbr_bufs = 4; p.nbr_bufs >= 2; p.nbr_bufs >>= 1) {
+        if (p.nbr_bufs == 4 && 4 * p.nbr_stride > 64 * 1024) continue;
+        const int smem_free = kSmemBudget - 1024 - p.nbr_bufs * p.nbr_stride - ((misc_bytes + 127) & ~127);
+        p.resident = (p.w_bytes <= smem_free && p.w_bytes % 512 == 0) ? 1 : 0;   // 32 lanes x 16-byte multiples
+        if (p.resident || smem_free / b_slot >= 2) {
+            if (!p.resident && S > smem_free / b_slot) S = smem_free / b_slot;
+            break;
+        }
+    }
+    if (p.nbr_bufs < 2 || S < 2) return QL_ERR_UNSUPPORTED;
     p.nbr_log2 = p.nbr_bufs == 4 ? 2 : 1;
     const int nbr_bytes = p.nbr_bufs * p.nbr_stride;
-    const int smem_free = kSmemBudget - 1024 - nbr_bytes - ((misc_bytes + 127) & ~127);
-    p.w_bytes = kvol * g.nseg * b_sub;
-    p.resident = (p.w_bytes <= smem_free && p.w_bytes % 512 == 0) ? 1 : 0;   // 32 lanes x 16-byte multiples
-    p.n_acc = (kTmemCols - 2 * c_out) / 32 >= 8 ? 2 : 1;
-    int S = (kTmemCols - p.n_acc * c_out) / 32;
-    if (!p.resident && S > smem_free / b_slot) S = smem_free / b_slot;
-    S = S >= 8 ? 8 : (S >= 4 ? 4 : 0);
-    if (S < kTeams) return QL_ERR_UNSUPPORTED;
     p.n_slots = S;
-    p.slot_log2 = S == 8 ? 3 : 2;
     p.a_col0 = p.n_acc * c_out;
     p.off_nbr = p.resident ? ((p.w_bytes + 1023) & ~1023) : S * b_slot;
     p.off_misc = (p.off_nbr + nbr_bytes + 127) & ~127;
