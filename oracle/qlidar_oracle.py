@@ -5,16 +5,25 @@ algorithms on the reference's hot path.  Only `tests/`, `__graft_entry__.smoke()
 `cpu_baseline` / `--impl reference` legs of `bench.py` may import it; the product package
 (`quantization-on-3d-object-detection_b200/qlidar`) never does.
 
-PARITY UNPINNED: the reference (BiboyQG/Quantization-on-3D-Object-Detection == OpenPCDet v0.6.0 + quant/)
-ships no tests, golden vectors or fixtures for this path, and the arithmetic lives in two
-un-vendored, un-pinned third-party packages that are not installed in this image:
+PARITY STATUS -- pinned for the code the reference owns, UNPINNED for the third-party arithmetic under it.
+The reference (BiboyQG/Quantization-on-3D-Object-Detection == OpenPCDet v0.6.0 + quant/) ships no tests, golden
+vectors or fixtures for this path, and the arithmetic lives in two un-vendored, un-pinned
+third-party packages that are not installed in this image (and cannot be built here: spconv needs pccm/cumm codegen):
   * spconv 2.x (traveller59/spconv; `pip install spconv-cu116`, unversioned: docker/cu116.Dockerfile:66;
     observed 2.x with ConvAlgo.MaskImplicitGemm: tools/demo.ipynb:255)
   * pytorch_quantization (NVIDIA TensorRT repo; imported at quant/quant.py:1-2, listed nowhere)
-Their *published* algorithms are restated here and anchored on the reference's own call sites (cited per
-function as `file:line` relative to /root/reference).  The oracle earns trust by independent cross-checks in
-tests/test_oracle_*.py: sparse conv vs dense torch.nn.functional.conv3d, int32 path vs float64, and
-property tests (permutation invariance, subm preserves the active set, strided out-set = dilate o subsample).
+What IS pinned: tests/golden/*.npz were produced by tests/golden/make_golden.py, which imports the reference's own
+sources from /root/reference unmodified (pcdet VoxelResBackBone8x / VoxelBackBone8x / MeanVFE / HeightCompression,
+quant/quant.py::QConvNd, quant/quantize.py::q_conv3d / collect_stats / compute_amax) and runs them on CPU with
+oracle/ext_stubs.py standing in for the two absent packages.  tests/test_golden.py holds this file's stand-alone
+restatement (backbone_specs / backbone_forward / QuantCfg) to those vectors at 1e-5 and indices bit-exact -- topology,
+indice_key sharing, the QConvNd permute / fake-quant / restore sequence, BN / ReLU / residual order, no_list handling
+and static calibration are therefore the reference's.  What is NOT pinned: the two packages' *published* algorithms
+(rulebook, gather-GEMM-scatter, TensorQuantizer arithmetic) are restated here, anchored on the reference's call sites
+(cited per function as `file:line` relative to /root/reference), and earn trust only through independent cross-checks
+in tests/test_oracle.py: sparse conv vs dense torch.nn.functional.conv3d for every (k, stride, pad) used, int32
+path vs float64, torch.round half-to-even, and property tests (permutation invariance, subm preserves the active
+set, strided out-set = dilate o subsample).
 """
 from __future__ import annotations
 
@@ -534,6 +543,8 @@ class QuantCfg:
     alpha: float = 0.5
     no_list: Tuple[str, ...] = ()
     fast: bool = False            # CPU-baseline timing: pick the faster of the two equivalent conv formulations
+    act_amax: Optional[Dict[str, torch.Tensor]] = None   # static calibration: conv name -> calibrated activation amax
+                                                         # (quant/quantize.py:175-207); None/missing = dynamic
 
 
 def run_conv(x: SpT, spec: ConvSpec, params: Dict[str, torch.Tensor], q: QuantCfg, record=None) -> SpT:
@@ -553,7 +564,8 @@ def run_conv(x: SpT, spec: ConvSpec, params: Dict[str, torch.Tensor], q: QuantCf
     if mode == "fp32":
         y = conv_fn(x.features, nbr, w, b)
     elif mode == "ref":
-        y = qconv_reference_math(x.features, nbr, w, b, q.w_bits, q.act_bits, q.cw, conv_fn=conv_fn)
+        am = q.act_amax.get(spec.name) if q.act_amax else None
+        y = qconv_reference_math(x.features, nbr, w, b, q.w_bits, q.act_bits, q.cw, act_amax=am, conv_fn=conv_fn)
     elif mode == "w8a8_pt":
         acc, y, _, _ = qconv_w8a8_pt(x.features, nbr, w, b)
         if record is not None:
@@ -570,9 +582,10 @@ def run_conv(x: SpT, spec: ConvSpec, params: Dict[str, torch.Tensor], q: QuantCf
 
 
 def bn_relu(x: SpT, name: str, params, eps: float, relu=True, residual: Optional[torch.Tensor] = None) -> SpT:
-    a, b = bn_fold(params[name + ".weight"], params[name + ".bias"], params[name + ".running_mean"],
-                   params[name + ".running_var"], eps)
-    y = x.features * a + b
+    """nn.BatchNorm1d in eval mode applied to .features by SparseSequential / replace_feature (spconv_backbone.py:16-17,
+    56-65): torch's own batch_norm on the running statistics, so the fp32 rounding is the reference's, not a folded a*x+b."""
+    y = F.batch_norm(x.features, params[name + ".running_mean"], params[name + ".running_var"], params[name + ".weight"],
+                     params[name + ".bias"], False, 0.0, eps)
     if residual is not None:
         y = y + residual
     if relu:
@@ -653,14 +666,20 @@ def init_params(prog, seed: int = 4) -> Dict[str, torch.Tensor]:
     """Random-init weights per SURVEY.md §8d: W ~ N(0, sqrt(2/(K*C_in))) in (oc,kd,kh,kw,ic); bias N(0,.01);
     BN gamma~U(.5,1.5), beta~N(0,.1), mean~N(0,.1), var~U(.5,1.5).  torch.manual_seed(4) is the reference's
     seed (quant/quant_centerpoint.py:174)."""
-    g = torch.Generator().manual_seed(seed)
+    g = np.random.default_rng(seed)                    # numpy PCG64: the same parameters on every machine / torch version
     P: Dict[str, torch.Tensor] = {}
 
+    def randn(*shape):
+        return torch.from_numpy(g.standard_normal(shape, dtype=np.float32))
+
+    def rand(*shape):
+        return torch.from_numpy(g.random(shape, dtype=np.float32))
+
     def bn(name, c):
-        P[name + ".weight"] = torch.rand(c, generator=g) + 0.5
-        P[name + ".bias"] = torch.randn(c, generator=g) * 0.1
-        P[name + ".running_mean"] = torch.randn(c, generator=g) * 0.1
-        P[name + ".running_var"] = torch.rand(c, generator=g) + 0.5
+        P[name + ".weight"] = rand(c) + 0.5
+        P[name + ".bias"] = randn(c) * 0.1
+        P[name + ".running_mean"] = randn(c) * 0.1
+        P[name + ".running_var"] = rand(c) + 0.5
 
     for op in prog:
         convs = []
@@ -671,9 +690,9 @@ def init_params(prog, seed: int = 4) -> Dict[str, torch.Tensor]:
         for spec, bnname in convs:
             K = spec.ksize[0] * spec.ksize[1] * spec.ksize[2]
             std = math.sqrt(2.0 / (K * spec.cin))
-            P[spec.name + ".weight"] = torch.randn((spec.cout,) + spec.ksize + (spec.cin,), generator=g) * std
+            P[spec.name + ".weight"] = randn(spec.cout, *spec.ksize, spec.cin) * std
             if spec.bias:
-                P[spec.name + ".bias"] = torch.randn(spec.cout, generator=g) * 0.01
+                P[spec.name + ".bias"] = randn(spec.cout) * 0.01
             bn(bnname, spec.cout)
     return P
 
