@@ -128,9 +128,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     from qlidar import ops
 
-    # frames r::N (datasets/__init__.py:48): rank r gets seeds 1000 + r + N*i
+    # frames r::N of the job's N*BATCH frames (pcdet/datasets/__init__.py:40-50 via qlidar.shard): frame f has seed 1000 + f
+    from qlidar import shard
+    my_frames = shard.frames_for_rank(world * BATCH, rank, world)
     pts_np = np.concatenate([np.concatenate([np.full((f.shape[0], 1), i, np.float32), f[:, 1:]], axis=1)
-                             for i, f in enumerate(make_batch(1000 + rank + world * i, 1) for i in range(BATCH))])
+                             for i, f in enumerate(make_batch(1000 + fr, 1) for fr in my_frames)])
     P = pts_np.shape[0]
     host_pts = [torch.from_numpy(pts_np).pin_memory(), torch.from_numpy(pts_np.copy()).pin_memory()]
     eng, _ = build_engine(dev, P)
@@ -220,10 +222,10 @@ def run_ours(args):
     # ---- NCCL only gathers detections (here: per-rank stage counts) after the timed regions ----
     gathered = None
     if world > 1:
-        mine = counts_dev.flatten().contiguous()
-        out = torch.empty((world * mine.numel(),), dtype=mine.dtype, device=dev)
-        dist.all_gather_into_tensor(out, mine)
-        gathered = out.view(world, -1).cpu().tolist()
+        # one fixed-shape block per frame of this rank (here the batch's stage counts stand in for padded detections),
+        # merged back into dataset order: common_utils.py:229-250 without the pickle files
+        mine = counts_dev.flatten().to(torch.float32).unsqueeze(0).repeat(BATCH, 1).contiguous()
+        gathered = shard.gather_frame_results(mine, world * BATCH)[::BATCH].to(torch.int64).cpu().tolist()
 
     if rank != 0:
         if world > 1:

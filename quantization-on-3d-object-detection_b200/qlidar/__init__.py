@@ -11,5 +11,6 @@ from .quant import QConvNd, QConv3d, QConv2d, GQConv3d, q_conv3d, collect_stats,
 from .backbones import (Cfg, post_act_block, SparseBasicBlock, VoxelBackBone8x, VoxelResBackBone8x,
                         VoxelResBackBone8xVoxelNeXt, MeanVFE, DynamicMeanVFE, VoxelGeneratorWrapper, HeightCompression)
 from .engine import BackboneEngine
+from . import shard
 
 __all__ = [n for n in dir() if not n.startswith("_")]

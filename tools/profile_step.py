@@ -1,5 +1,5 @@
 """Profiling driver: build the bench workload's engine and run a few eager (non-graph) steps so that ncu sees every
-kernel launch by name.  Usage: python tools/profile_step.py [--steps N] [--batch B] [--beams NB]"""
+kernel launch by name.  Usage: ncu --profile-from-start off ... python tools/profile_step.py [--steps N_WARMUP]"""
 import argparse
 import os
 import sys
@@ -24,9 +24,14 @@ def main():
     eng, _ = bench.build_engine(torch.device("cuda", 0), pts.shape[0])
     eng.use_graph = bool(args.graph)
     eng.set_points(torch.from_numpy(pts))
-    for _ in range(args.steps):
+    for _ in range(args.steps):                        # warm-up (outside the profiled range)
         eng.forward_points()
     torch.cuda.synchronize()
+    # ncu --profile-from-start off: only the launches of this one eager step are profiled
+    torch.cuda.cudart().cudaProfilerStart()
+    eng.forward_points()
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
     print("counts", eng.counts(), "overflow", eng.overflowed(), "kernels/step", eng.kernels_per_forward)
 
 
