@@ -225,7 +225,7 @@ def run_ours(args):
         # one fixed-shape block per frame of this rank (here the batch's stage counts stand in for padded detections),
         # merged back into dataset order: common_utils.py:229-250 without the pickle files
         mine = counts_dev.flatten().to(torch.float32).unsqueeze(0).repeat(BATCH, 1).contiguous()
-        gathered = shard.gather_frame_results(mine, world * BATCH)[::BATCH].to(torch.int64).cpu().tolist()
+        gathered = shard.gather_frame_results(mine, world * BATCH)[:world].to(torch.int64).cpu().tolist()   # frame r belongs to rank r
 
     if rank != 0:
         if world > 1:
