@@ -13,4 +13,16 @@ from .backbones import (Cfg, post_act_block, SparseBasicBlock, VoxelBackBone8x, 
 from .engine import BackboneEngine
 from . import shard
 
+# `import qlidar as spconv` at pcdet/utils/spconv_utils.py:3-10 keeps the reference's attribute paths working:
+# spconv.__version__[2:] (:4), spconv.constants.SPCONV_USE_DIRECT_TABLE (:5), spconv.pytorch (:8), spconv.conv.SparseConvolution (:23),
+# spconv.pytorch.modules.SparseModule (quant/quant.py:3)
+import sys as _sys
+import types as _types
+
+__version__ = "2.3.6"
+constants = _types.SimpleNamespace(SPCONV_USE_DIRECT_TABLE=False)
+conv = _types.SimpleNamespace(SparseConvolution=SparseConvolution)
+modules = _types.SimpleNamespace(SparseModule=SparseModule, SparseSequential=SparseSequential)
+pytorch = _sys.modules[__name__]
+
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -92,3 +92,25 @@ def test_ops_reject_cpu_tensors():
     from qlidar._lib import QlidarError
     with pytest.raises(QlidarError):
         ops.hash_build(torch.zeros((4, 4), dtype=torch.int32), None, (1, 2, 2, 2))
+
+
+def test_spconv_import_alias_surface():
+    """`import qlidar as spconv` satisfies the attribute paths the reference touches
+    (pcdet/utils/spconv_utils.py:3-10,23; quant/quant.py:1-3; spconv_backbone.py:12-17)."""
+    import qlidar as spconv
+    assert float(spconv.__version__[2:]) >= 2.2
+    spconv.constants.SPCONV_USE_DIRECT_TABLE = False
+    sp = spconv.pytorch
+    for name in ("SparseConvTensor", "SparseSequential", "SparseModule", "SubMConv3d", "SparseConv3d", "SubMConv2d",
+                 "SparseConv2d", "SparseInverseConv3d", "replace_feature"):
+        assert hasattr(sp, name), name
+    assert issubclass(sp.SubMConv3d, spconv.conv.SparseConvolution)
+    assert spconv.pytorch.modules.SparseModule is spconv.SparseModule
+    for name in ("QConvNd", "QConv3d", "QConv2d", "GQConv3d", "q_conv3d", "collect_stats", "compute_amax", "TensorQuantizer",
+                 "QuantDescriptor", "MeanVFE", "DynamicMeanVFE", "HeightCompression", "VoxelBackBone8x", "VoxelResBackBone8x",
+                 "VoxelResBackBone8xVoxelNeXt", "VoxelGeneratorWrapper", "BackboneEngine", "shard"):
+        assert hasattr(spconv, name), name
+    conv = sp.SubMConv3d(16, 32, 3, padding=1, bias=False, indice_key="subm1")
+    assert tuple(conv.weight.shape) == (32, 3, 3, 3, 16)            # spconv-2 layout (oc, kd, kh, kw, ic), quant/quant.py:37-39
+    q = spconv.QConvNd(conv, 8, 8, True)
+    assert hasattr(q, "w_quant") and hasattr(q, "act_quant") and q.module is conv   # names end in _quant: quantize.py:178
