@@ -6,51 +6,56 @@
 // One persistent CTA per SM walks 128-row output tiles.  Per tile the conv is a sum of per-offset GEMMs
 //     D[128, C_out] += A_k[128, C_in] . W_k[C_out, C_in]^T      for every kernel offset k that is non-empty in the tile
 // (the rulebook's per-tile offset mask lists them; empty (tile, offset) slabs cost nothing).  The A operand never
-// exists in memory and never touches shared memory: output row r of the tile is TMEM lane r, and the producer thread
-// that owns lane r loads its neighbour's feature row straight from global memory (L2) into registers and writes it
-// to tensor memory with tcgen05.st; the MMA reads A from TMEM (the ".ts" operand form) and only the weights from
-// shared memory.  ncu on the previous cp.async -> SWIZZLE_128B smem version showed the shared-memory data pipe at
-// 75 % (one write wavefront per returning 32-byte sector plus zero fills plus the tensor core's operand reads) with
-// DRAM at 17 %, see profiles/r01_conv_v2_smem_gather.md; TMEM stores run at 256 B/clk and are off that pipe.
+// exists in memory and never touches shared memory: output row r of the tile is TMEM lane r; gather producers load the
+// neighbours' feature rows straight from global memory (L1/L2) into registers and write them to tensor memory with
+// tcgen05.st; the MMA reads A from TMEM (the ".ts" operand form) and only the weights from shared memory.
 //
 // K is cut into sub-chunks: one sub-chunk = one kernel offset x one <=128-byte segment of the input row
-// (CH = 32 / 64 / 128 bytes => 1 / 2 / 4 MMA k-steps).  128/CH consecutive sub-chunks form a unit (32 TMEM columns =
-// 32 registers per producer thread), kTeams units form a ring slot: one full/empty mbarrier pair and one pass of the
-// single MMA-issuing thread per slot (that thread's instruction stream is the serial bottleneck of the kernel, so the
-// work per barrier round trip is made as large as TMEM allows).  Roles (18 warps):
-//   warps 0-11  gather producers : 3 teams x 4 warps; warp w owns TMEM lanes 32*(w%4)..+31; team t fills unit t of every
-//                                  slot; per sub-chunk: nbr index (LDS from the tile's rulebook slab), CH bytes of the
-//                                  neighbour row (or zeros); one tcgen05.st.x32 per unit, mbarrier arrive; the loads of a
-//                                  team's next unit are issued before the current unit is stored
-//   warps 12-15 epilogue         : tcgen05.ld accumulators -> dequant*BN scale/shift (+residual) (+ReLU)
+// (CH = 32 / 64 / 128 bytes => 1 / 2 / 4 MMA k-steps).  128/CH consecutive sub-chunks form a UNIT = 32 TMEM columns x 128
+// lanes (16 KB of A).  Units flow through a ring of up to 8 TMEM slots, each with its own full/empty mbarrier pair, so
+// every producer warp works independently with exactly one unit in flight.  Roles (22 warps):
+//   warps 0-15  gather producers : 4 teams x 4 warps; warp w owns TMEM lanes 32*(w%4)..+31; team t fills units t, t+4, ...
+//                                  (global unit numbering across the CTA's tiles).  ncu on the first version of this kernel
+//                                  (12 fat producer warps, two units in flight each, a slot state machine) showed the
+//                                  producers instruction-latency bound at ~216 warp-instructions per unit and, before
+//                                  that, the L1 data pipe at 79-86 % with one 32-byte sector per wavefront
+//                                  (profiles/r01_conv_v6_*, r01_conv_v8_*).  Hence: thin warps, straight-line unit code,
+//                                  loads that are never predicated (a missing neighbour reads a zero line instead), and
+//                                  for rows >= 64 bytes a QUAD gather -- four lanes read one row's CH contiguous bytes
+//                                  (8 rows / 8 wavefronts per load instruction) and the registers go to TMEM with
+//                                  tcgen05.st.16x256b; the K order this leaves inside a sub-chunk is undone in the weight
+//                                  packing (k_word_src).
+//   warps 16-19 epilogue         : tcgen05.ld accumulators -> dequant*BN scale/shift (+residual) (+ReLU)
 //                                  -> fp16/fp32 rows (+ int8 re-quantised rows, + per-channel absmax)
-//   warp  16    MMA issuer       : one lane issues tcgen05.mma (kind::f16 or kind::i8), accumulators in TMEM
+//   warp  20    MMA issuer       : one lane issues tcgen05.mma (kind::f16 or kind::i8), accumulators in TMEM
 //                                  (double buffered when they fit: tile i+1 accumulates while tile i drains)
-//   warp  17    TMA loader       : cp.async.bulk of each chunk's weight slab (pre-swizzled image from
-//                                  ql_pack_weights_host) into the chunk's B slot -- or, when the whole packed weight tensor
-//                                  fits in shared memory (C <= 32 fp16, C <= 64 int8), of all of it once -- and of the
-//                                  NEXT tile's non-empty rulebook slabs (512 B each) into a double-buffered copy.
-//                                  One UBLKCP instruction costs its issuing warp ~225 ns whatever the size
-//                                  (tools/microbench/bulk_copy_rate.cu), an extra active lane only ~26 ns: copies are issued
-//                                  several lanes at a time, one copy per lane.
+//   warp  21    loader           : cp.async.bulk of each tile's rulebook block ([kvol][128] int32, one copy per 16 KB, plus a
+//                                  header with the tile mask and an ordinal -> offset table) up to 3 tiles ahead, and -- when
+//                                  the packed weights do not fit in shared memory (C <= 32 fp16, C <= 64 int8 do) -- of every
+//                                  unit's weight sub-chunks into the unit's B slot.  One UBLKCP instruction costs its issuing
+//                                  warp ~225 ns whatever the size (tools/microbench/bulk_copy_rate.cu), an extra active lane
+//                                  ~26 ns: weight copies for up to half the ring are issued by one instruction, one per lane.
 #include "ql_common.cuh"
 #include <string.h>
 
 namespace {
 
-constexpr int kTeams = 3;
-constexpr int kProducerWarps = kTeams * 4;               // 12
+constexpr int kTeams = 4;
+constexpr int kProducerWarps = kTeams * 4;               // 16
 constexpr int kEpilogueThreads = 128;
-constexpr int kEpilogueWarp0 = kProducerWarps;            // warps 12..15 (warp % 4 == TMEM lane quarter)
-constexpr int kMmaWarp = kEpilogueWarp0 + 4;              // 16
-constexpr int kLoaderWarp = kMmaWarp + 1;                 // 17
-constexpr int kThreadsTotal = (kLoaderWarp + 1) * 32;     // 576
-constexpr int kMaxSlots = 4;
-constexpr int kSlotCols = 32 * kTeams;                    // TMEM columns per ring slot
+constexpr int kEpilogueWarp0 = kProducerWarps;            // warps 16..19 (warp % 4 == TMEM lane quarter)
+constexpr int kMmaWarp = kEpilogueWarp0 + 4;              // 20
+constexpr int kLoaderWarp = kMmaWarp + 1;                 // 21
+constexpr int kThreadsTotal = (kLoaderWarp + 1) * 32;     // 704
+constexpr int kMaxUnits = 8;                              // ring depth in units
+constexpr int kUnitCols = 32;                             // TMEM columns per unit (128 bytes of K per lane)
 constexpr int kMaskWords = 4;                             // kernel volumes up to 128 (3^3, 5^3)
 constexpr int kTmemCols = 512;
 constexpr int kSmemBudget = 232448;                       // 227 KB opt-in maximum per CTA
 constexpr int kSmemFloor = 120 * 1024;                    // always ask for > half an SM: one CTA (one TMEM owner) per SM
+constexpr int kNbrHeader = 160;                           // rulebook buffer header: 16 B mask, n_off at +16, ord -> k table at +32
+
+__device__ __align__(128) uint8_t g_zero_line[128];       // what a missing neighbour reads (zero-initialised module memory)
 
 struct ConvParams {
     const uint8_t* feats;
@@ -61,6 +66,7 @@ struct ConvParams {
     int row_bytes;          // c_in * elem size
     int wide;               // rows (and the feature base) are 32-byte aligned: gather with 256-bit loads
     int c_out, kvol, nseg, mask_words;
+    uint32_t inv_nseg;      // ceil(65536 / nseg): ord = (sub * inv_nseg) >> 16 for sub < 4096
     const uint8_t* w_packed;
     const float* scale;
     const float* shift;
@@ -72,20 +78,21 @@ struct ConvParams {
     int8_t* out_q;
     const float* out_qscale;
     float* absmax;
-    int n_slots;            // A/B ring depth in slots
+    int n_ring;             // A/B ring depth in units
+    int teams;              // active producer teams (<= n_ring)
     int n_acc;              // accumulator buffers in TMEM (2, or 1 when 2*c_out does not fit beside the A ring)
     int a_col0;             // first TMEM column of the A ring
-    int resident;           // 1: every weight chunk lives in shared memory for the whole kernel (no per-chunk B copies)
+    int resident;           // 1: every weight chunk lives in shared memory for the whole kernel (no per-unit B copies)
     int w_bytes;            // packed weight bytes (resident mode)
-    int off_nbr;            // smem offset of the rulebook buffers: nbr_bufs x {16-byte tile mask, [kvol][128] int32}
+    int off_nbr;            // smem offset of the rulebook buffers: nbr_bufs x {header, [kvol][128] int32}
     int nbr_bufs, nbr_log2; // 4 (or 2 when shared memory is short): the loader runs nbr_bufs-1 tiles ahead
     int nbr_stride;         // bytes per buffer
     int off_misc;           // smem offset of MiscSmem from the 1024-aligned base
 };
 
 struct MiscSmem {
-    uint64_t full[kMaxSlots];
-    uint64_t empty[kMaxSlots];
+    uint64_t full[kMaxUnits];
+    uint64_t empty[kMaxUnits];
     uint64_t acc_full[2];
     uint64_t acc_empty[2];
     uint64_t nbr_full[4];
@@ -144,22 +151,25 @@ __device__ __forceinline__ uint64_t umma_desc_b(uint32_t smem_addr) {
     return d;
 }
 
-// 256-bit load (LDG.E.ENL2.256, sm_100): one full 32-byte sector per lane, half the L1 wavefronts of two 128-bit loads when
-// every lane reads a different row.  Needs 32-byte alignment.
-__device__ __forceinline__ void ldg32(const uint8_t* p, uint32_t (&v)[8]) {
+// 256-bit load (LDG.E.ENL2.256, sm_100).  Needs 32-byte alignment.
+__device__ __forceinline__ void ldg32(const uint8_t* p, uint32_t* v) {
     asm volatile("ld.global.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "l"(p));
 }
-__device__ __forceinline__ uint4 ldg16(const uint8_t* p) {
-    uint4 v;
-    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+__device__ __forceinline__ void ldg16(const uint8_t* p, uint32_t* v) {
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ int lds_u8(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-template <int NREG>
-__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&v)[NREG]);
-template <>
-__device__ __forceinline__ void tmem_st<32>(uint32_t taddr, const uint32_t (&v)[32]) {
+__device__ __forceinline__ void sts_u8(uint32_t addr, int v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// 32 lanes x 32 columns: thread t supplies columns 0..31 of TMEM lane base + t
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t* v) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
         "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
@@ -169,19 +179,26 @@ __device__ __forceinline__ void tmem_st<32>(uint32_t taddr, const uint32_t (&v)[
         "r"(v[31])
         : "memory");
 }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// position of the n-th (0-based) set bit of a tile mask
-__device__ __forceinline__ int nth_set_bit(const uint32_t (&m)[kMaskWords], int n) {
-    int k = 0;
-#pragma unroll
-    for (int i = 0; i < kMaskWords; ++i) {
-        const int c = __popc(m[i]);
-        if (n >= 0 && n < c) k = i * 32 + (int)__fns(m[i], 0, n + 1);
-        n -= c;                                          // goes negative once found: later words cannot match
-    }
-    return k;
+// 16 lanes x (NREP x 256 bits): thread (t0 = lane%4, t1 = lane/4) supplies, for repeat v2 and half v1, the two 32-bit
+// columns 8*v2 + 2*t0 + {0,1} of TMEM lane base + t1 + 8*v1, as registers [4*v2 + 2*v1 + {0,1}].
+template <int NREP>
+__device__ __forceinline__ void tmem_st_16x256b(uint32_t taddr, const uint32_t* v);
+template <>
+__device__ __forceinline__ void tmem_st_16x256b<2>(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
 }
+template <>
+__device__ __forceinline__ void tmem_st_16x256b<4>(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
+            taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ int load_tile_mask(const ConvParams& p, int64_t tile, uint32_t (&mask)[kMaskWords]) {
     int n = 0;
@@ -200,24 +217,16 @@ __device__ __forceinline__ int load_tile_mask(const ConvParams& p, int64_t tile,
         n += __popc(w);
     }
     if (n == 0) { mask[0] = 1u; n = 1; }       // a tile without pairs still has to zero its accumulators
-    return n * p.nseg;
-}
-
-// the tile mask as the loader left it in the header of a rulebook buffer
-__device__ __forceinline__ int load_tile_mask_smem(uint32_t addr, int nseg, uint32_t (&mask)[kMaskWords]) {
-    int n = 0;
-#pragma unroll
-    for (int i = 0; i < kMaskWords; ++i) {
-        mask[i] = (uint32_t)ql_lds_s32(addr + 4u * i);
-        n += __popc(mask[i]);
-    }
-    return n * nseg;
+    return n;                                  // non-empty kernel offsets
 }
 
 template <bool kInt8, int CH, bool kResident>
 __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams p) {
-    constexpr int kAReg = CH / 4;                          // 32-bit TMEM columns (registers) per chunk
-    constexpr int kGroup = 128 / CH;                       // sub-chunks per group == per ring slot (128 bytes of K, 32 TMEM columns)
+    constexpr int kAReg = CH / 4;                          // 32-bit TMEM columns (registers) per sub-chunk
+    constexpr int kGroup = 128 / CH;                       // sub-chunks per unit
+    constexpr int kGroupLog2 = CH == 128 ? 0 : (CH == 64 ? 1 : 2);
+    constexpr bool kQuad = CH >= 64;                       // 4 lanes per row + tcgen05.st.16x256b, else lane per row + 32x32b
+    constexpr int kRep = kQuad ? CH / 32 : 2;              // 256-bit repeats per sub-chunk in the quad form
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base_u32 = (ql_smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle atoms need 1024-byte alignment
     uint8_t* smem = smem_raw + (smem_base_u32 - ql_smem_u32(smem_raw));
@@ -230,15 +239,15 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    const int S = p.n_slots;
+    const uint32_t R = (uint32_t)p.n_ring;
 
     const int64_t n_out = p.n_out_dev ? (int64_t)*p.n_out_dev : p.n_out_cap;
     const int64_t n_tiles = (n_out + QL_TILE_M - 1) / QL_TILE_M;
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) {
-            ql_mbar_init(ql_smem_u32(&misc->full[s]), kProducerWarps + (kResident ? 0 : 1));   // every producer warp (+ the loader's expect_tx)
-            ql_mbar_init(ql_smem_u32(&misc->empty[s]), 1);         // tcgen05.commit
+        for (int s = 0; s < kMaxUnits; ++s) {
+            ql_mbar_init(ql_smem_u32(&misc->full[s]), 4 + (kResident ? 0 : 1));   // the team's 4 warps (+ the loader's expect_tx)
+            ql_mbar_init(ql_smem_u32(&misc->empty[s]), 1);                         // tcgen05.commit
         }
         for (int i = 0; i < 2; ++i) {
             ql_mbar_init(ql_smem_u32(&misc->acc_full[i]), 1);
@@ -246,7 +255,7 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
         }
         for (int i = 0; i < 4; ++i) {
             ql_mbar_init(ql_smem_u32(&misc->nbr_full[i]), 1);
-            ql_mbar_init(ql_smem_u32(&misc->nbr_empty[i]), kProducerWarps);
+            ql_mbar_init(ql_smem_u32(&misc->nbr_empty[i]), 4 * p.teams);
         }
         ql_mbar_init(ql_smem_u32(&misc->w_full), 1);
         ql_fence_mbar_init();
@@ -269,132 +278,116 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
     ql_tc_fence_after();
     const uint32_t tmem_base = misc->tmem_base;
     const uint32_t b_sub_bytes = (uint32_t)p.c_out * CH;     // one weight sub-chunk: [c_out x CH bytes]
-    constexpr int kSlotSubs = kGroup * kTeams;               // sub-chunks per ring slot
+    const uint32_t nbr_s0 = smem_base_u32 + (uint32_t)p.off_nbr;
+    const uint32_t nbr_stride = (uint32_t)p.nbr_stride, nbmask = (uint32_t)p.nbr_bufs - 1u;
+    const uint32_t full0 = ql_smem_u32(&misc->full[0]), empty0 = ql_smem_u32(&misc->empty[0]);
 
     if (warp < kProducerWarps) {
         // ============================ gather producers ============================
         const int q = warp & 3;                              // TMEM lane quarter
-        const int team = warp >> 2;
-        const int r = q * 32 + lane;                         // row in tile == TMEM lane
-        const uint32_t a_lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.a_col0 + (uint32_t)(team * 32);
-        const uint32_t nbr_s0 = smem_base_u32 + (uint32_t)p.off_nbr;            // buffer b: mask at +b*stride, slabs at +16
-        const uint32_t nbr_s = nbr_s0 + 16u + (uint32_t)r * 4u;
-        const uint32_t nbr_stride = (uint32_t)p.nbr_stride, nbmask = (uint32_t)p.nbr_bufs - 1u;
+        const uint32_t team = (uint32_t)(warp >> 2);
+        const uint32_t T = (uint32_t)p.teams;
+        if (team < T) {
+            const uint32_t a_lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.a_col0;
+            const int t0 = lane & 3, t1 = lane >> 2;         // quad form: lane t0 of the quad that serves rows t1 + 8*rr
+            // byte offset of this thread's first row inside a [128] int32 slab
+            const uint32_t row_off = (uint32_t)(q * 32 + (kQuad ? t1 : lane)) * 4u;
+            const int tb0 = kQuad ? t0 * (CH / 4) : 0;       // this thread's bytes inside a sub-chunk's row segment
+            const uint32_t row_bytes = (uint32_t)p.row_bytes;
+            const uint8_t* const feats = p.feats;
+            const uint8_t* const zero = g_zero_line;
+            const bool wide = p.wide != 0;
+            const uint32_t nseg = (uint32_t)p.nseg, inv_nseg = p.inv_nseg;
 
-        // Walks the CTA's tiles slot by slot; this team owns unit `team` of every slot (a unit past the tile's last
-        // sub-chunk is empty: nothing is loaded or stored, but the slot's barriers are still honoured, so every warp
-        // sees every ring phase and the parity waits cannot alias).
-        struct Unit { uint32_t ring, ph; int n; int c0; uint32_t buf_off; };
-        int64_t tile = blockIdx.x;
-        uint32_t it = 0, ring = 0, ph = 0;
-        int n_sub = 0, n_slot_t = 0, sl = 0;
-        bool have_tile = false, ready = false;
-        // returns 1 = unit found, 0 = no more work, 2 = the next tile's rulebook slab has not landed yet (only if !blocking)
-        auto next_unit = [&](bool blocking, Unit& out) -> int {
-            while (true) {
-                if (!have_tile) {
-                    if (tile >= n_tiles) return 0;
-                    have_tile = true; ready = false;
+            uint32_t g = team;                               // next global unit of this team
+            uint32_t G0 = 0;                                 // global number of the current tile's first unit
+            uint32_t u = team, ph = 0;                       // ring slot / pass parity of unit g
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const uint32_t nb = it & nbmask;
+                const uint32_t buf = nbr_s0 + nb * nbr_stride;
+                ql_mbar_wait(ql_smem_u32(&misc->nbr_full[nb]), (it >> p.nbr_log2) & 1u);
+                const uint32_t n_sub = (uint32_t)ql_lds_s32(buf + 16u) * nseg;
+                const uint32_t Gend = G0 + ((n_sub + kGroup - 1) >> kGroupLog2);
+                for (; g < Gend; g += T) {
+                    const uint32_t c0 = (g - G0) << kGroupLog2;      // the unit's first sub-chunk
+                    uint32_t v[32];
+                    if constexpr (kQuad) {
+#pragma unroll
+                        for (int j = 0; j < kGroup; ++j) {
+                            const uint32_t lc = c0 + (uint32_t)j;
+                            int idx[4] = {-1, -1, -1, -1};
+                            uint32_t boff = 0;
+                            if (lc < n_sub) {
+                                uint32_t ord = lc;
+                                if (CH == 128) { ord = (lc * inv_nseg) >> 16; boff = (lc - ord * nseg) * 128u; }
+                                const uint32_t a = buf + (uint32_t)kNbrHeader + (uint32_t)lds_u8(buf + 32u + ord) * (QL_TILE_M * 4u) + row_off;
+#pragma unroll
+                                for (int rr = 0; rr < 4; ++rr) idx[rr] = ql_lds_s32(a + (uint32_t)rr * 32u);
+                            }
+                            const uint32_t tb = boff + (uint32_t)tb0;
+#pragma unroll
+                            for (int rr = 0; rr < 4; ++rr) {
+                                const int h = rr >> 1, v1 = rr & 1;
+                                const bool ok = idx[rr] >= 0 && tb < row_bytes;
+                                const uint8_t* src = ok ? feats + ((uint64_t)(uint32_t)idx[rr] * row_bytes + tb) : zero;
+                                uint32_t x[8];
+                                if constexpr (CH == 128) {
+                                    if (wide) {
+                                        ldg32(src, x);
+                                    } else {
+                                        ldg16(src, x);
+                                        ldg16((ok && tb + 16u < row_bytes) ? src + 16 : zero, x + 4);
+                                    }
+                                } else {
+                                    ldg16(src, x);
+                                }
+#pragma unroll
+                                for (int v2 = 0; v2 < kRep; ++v2) {
+                                    v[j * kAReg + h * (4 * kRep) + 4 * v2 + 2 * v1] = x[2 * v2];
+                                    v[j * kAReg + h * (4 * kRep) + 4 * v2 + 2 * v1 + 1] = x[2 * v2 + 1];
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < kGroup; ++j) {
+                            const uint32_t lc = c0 + (uint32_t)j;            // CH = 32: one sub-chunk per kernel offset
+                            int idx = -1;
+                            if (lc < n_sub)
+                                idx = ql_lds_s32(buf + (uint32_t)kNbrHeader + (uint32_t)lds_u8(buf + 32u + lc) * (QL_TILE_M * 4u) + row_off);
+                            const bool ok = idx >= 0;
+                            const uint8_t* src = ok ? feats + (uint64_t)(uint32_t)idx * row_bytes : zero;
+                            if (wide) {
+                                ldg32(src, v + j * 8);
+                            } else {
+                                ldg16(src, v + j * 8);
+                                ldg16((ok && 16u < row_bytes) ? src + 16 : zero, v + j * 8 + 4);
+                            }
+                        }
+                    }
+                    ql_mbar_wait(empty0 + u * 8u, ph ^ 1u);              // the MMAs that read this ring slot have completed
+                    ql_tc_fence_after();
+                    const uint32_t a_unit = a_lane_base + u * (uint32_t)kUnitCols;
+                    if constexpr (kQuad) {
+#pragma unroll
+                        for (int j = 0; j < kGroup; ++j)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+                                tmem_st_16x256b<kRep>(a_unit + ((uint32_t)(h * 16) << 16) + (uint32_t)(j * kAReg), &v[j * kAReg + h * (4 * kRep)]);
+                    } else {
+                        tmem_st_32x32b_x32(a_unit, v);
+                    }
+                    tmem_st_wait();
+                    ql_tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ql_mbar_arrive(full0 + u * 8u);
+                    u += T;
+                    if (u >= R) { u -= R; ph ^= 1u; }
                 }
-                if (!ready) {
-                    const uint32_t nb = it & nbmask, par = (it >> p.nbr_log2) & 1u;
-                    const uint32_t bar = ql_smem_u32(&misc->nbr_full[nb]);
-                    if (blocking) ql_mbar_wait(bar, par);
-                    else if (!ql_mbar_test_wait(bar, par)) return 2;
-                    uint32_t mask[kMaskWords];
-                    n_sub = load_tile_mask_smem(nbr_s0 + nb * nbr_stride, p.nseg, mask);
-                    n_slot_t = (n_sub + kSlotSubs - 1) / kSlotSubs;
-                    sl = 0; ready = true;
-                }
-                if (sl < n_slot_t) {
-                    out.ring = ring; out.ph = ph;
-                    out.c0 = (sl * kTeams + team) * kGroup;
-                    const int rem = n_sub - out.c0;
-                    out.n = rem < 0 ? 0 : (rem < kGroup ? rem : kGroup);
-                    out.buf_off = (it & nbmask) * nbr_stride;
-                    ++sl;
-                    if (++ring == (uint32_t)S) { ring = 0; ph ^= 1u; }
-                    return 1;
-                }
-                // every index this warp needs from the tile's slab has been read: hand the buffer back
+                G0 = Gend;
                 __syncwarp();
-                if (lane == 0) ql_mbar_arrive(ql_smem_u32(&misc->nbr_empty[it & nbmask]));
-                tile += gridDim.x; ++it; have_tile = false;
-            }
-        };
-        // loads of one unit: kGroup sub-chunks of CH bytes = 32 registers = the unit's 32 TMEM columns
-        auto issue = [&](const Unit& u, uint32_t (&v)[32]) {
-            int idx[kGroup], boff[kGroup];
-#pragma unroll
-            for (int j = 0; j < kGroup; ++j) {
-                idx[j] = -1; boff[j] = 0;
-                if (j < u.n) {
-                    const int lc = u.c0 + j;
-                    int ord = lc;                            // ordinal of the sub-chunk's offset among the tile's non-empty ones
-                    if (CH == 128 && p.nseg > 1) { ord = lc / p.nseg; boff[j] = (lc - ord * p.nseg) * 128; }
-                    idx[j] = ql_lds_s32(nbr_s + u.buf_off + (uint32_t)ord * (QL_TILE_M * 4u));
-                }
-            }
-            if (p.wide) {                                    // rows are multiples of 32 bytes: 256-bit loads
-#pragma unroll
-                for (int j = 0; j < kGroup; ++j) {
-                    const uint8_t* src = p.feats + (int64_t)(idx[j] < 0 ? 0 : idx[j]) * p.row_bytes + boff[j];
-#pragma unroll
-                    for (int t = 0; t < CH / 32; ++t) {
-                        uint32_t x[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-                        if (idx[j] >= 0 && boff[j] + t * 32 < p.row_bytes) ldg32(src + t * 32, x);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[j * kAReg + 8 * t + e] = x[e];
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < kGroup; ++j) {
-                    const uint8_t* src = p.feats + (int64_t)(idx[j] < 0 ? 0 : idx[j]) * p.row_bytes + boff[j];
-#pragma unroll
-                    for (int t = 0; t < CH / 16; ++t) {
-                        uint4 x = make_uint4(0u, 0u, 0u, 0u);
-                        if (idx[j] >= 0 && boff[j] + t * 16 < p.row_bytes) x = ldg16(src + t * 16);
-                        const int o = j * kAReg + 4 * t;
-                        v[o] = x.x; v[o + 1] = x.y; v[o + 2] = x.z; v[o + 3] = x.w;
-                    }
-                }
-            }
-        };
-        auto store = [&](const Unit& u, const uint32_t (&v)[32]) {
-            ql_mbar_wait(ql_smem_u32(&misc->empty[u.ring]), u.ph ^ 1u);         // the MMAs that read this slot have completed
-            if (u.n > 0) {
-                ql_tc_fence_after();
-                tmem_st<32>(a_lane_base + u.ring * (uint32_t)kSlotCols, v);
-                tmem_st_wait();
-                ql_tc_fence_before();
-            }
-            __syncwarp();
-            if (lane == 0) ql_mbar_arrive(ql_smem_u32(&misc->full[u.ring]));
-        };
-        // software pipeline, two register buffers: the next unit's loads are in flight while the current unit waits for
-        // its ring slot.  A unit that is still held in registers is never kept waiting on a rulebook slab (that could
-        // deadlock against the loader, which streams weights only as fast as stored units are consumed): if the next
-        // tile's slab is not there yet the held unit is stored first.
-        uint32_t va[32], vb[32];
-        Unit ua, ub;
-        int have_a = next_unit(true, ua);
-        if (have_a == 1) issue(ua, va);
-        while (have_a == 1) {
-            int have_b = next_unit(false, ub);
-            if (have_b == 1) issue(ub, vb);
-            store(ua, va);
-            if (have_b == 2) {
-                have_b = next_unit(true, ub);
-                if (have_b == 1) issue(ub, vb);
-            }
-            if (have_b != 1) break;
-            have_a = next_unit(false, ua);
-            if (have_a == 1) issue(ua, va);
-            store(ub, vb);
-            if (have_a == 2) {
-                have_a = next_unit(true, ua);
-                if (have_a == 1) issue(ua, va);
+                if (lane == 0) ql_mbar_arrive(ql_smem_u32(&misc->nbr_empty[nb]));   // this warp has read all it needs from the block
             }
         }
     } else if (warp < kMmaWarp) {
@@ -503,19 +496,18 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
             const uint32_t bdesc_hi = (uint32_t)(bdesc0 >> 32), bdesc_lo0 = (uint32_t)bdesc0;
             const uint32_t b_sub16 = b_sub_bytes >> 4;
             const uint32_t a_base = tmem_base + (uint32_t)p.a_col0;
-            const uint32_t full0 = ql_smem_u32(&misc->full[0]), empty0 = ql_smem_u32(&misc->empty[0]);
             const int nseg = p.nseg;
             const bool narrow = p.mask_words == 1;                 // kernel volume <= 32: the mask is one word
-            uint32_t ring = 0, ph = 0, it = 0;
+            uint32_t u = 0, ph = 0, it = 0;
             if (kResident && (int64_t)blockIdx.x < n_tiles) ql_mbar_wait(ql_smem_u32(&misc->w_full), 0);
             uint32_t mask_next[kMaskWords];
-            int n_sub_next = (int64_t)blockIdx.x < n_tiles ? load_tile_mask(p, blockIdx.x, mask_next) : 0;
+            int n_sub_next = (int64_t)blockIdx.x < n_tiles ? load_tile_mask(p, blockIdx.x, mask_next) * nseg : 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 uint32_t m0 = mask_next[0];
                 uint64_t m_lo = (uint64_t)mask_next[0] | ((uint64_t)mask_next[1] << 32);
                 uint64_t m_hi = (uint64_t)mask_next[2] | ((uint64_t)mask_next[3] << 32);
                 const int n_sub = n_sub_next;
-                if (tile + gridDim.x < n_tiles) n_sub_next = load_tile_mask(p, tile + gridDim.x, mask_next);   // in flight during this tile
+                if (tile + gridDim.x < n_tiles) n_sub_next = load_tile_mask(p, tile + gridDim.x, mask_next) * nseg;   // in flight during this tile
                 const int a = p.n_acc == 2 ? (int)(it & 1u) : 0;
                 const uint32_t aph = p.n_acc == 2 ? ((it >> 1) & 1u) : (it & 1u);
                 ql_mbar_wait(ql_smem_u32(&misc->acc_empty[a]), aph ^ 1u);
@@ -523,70 +515,70 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
                 const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.c_out);
                 uint32_t accumulate = 0u;
                 int k = 0, seg = nseg;                           // seg == nseg: take the next offset from the mask
-                for (int c0 = 0; c0 < n_sub; c0 += kSlotSubs) {
-                    ql_mbar_wait(full0 + ring * 8u, ph);
+                for (int c0 = 0; c0 < n_sub; c0 += kGroup) {
+                    ql_mbar_wait(full0 + u * 8u, ph);
                     ql_tc_fence_after();
-                    const int n_in = n_sub - c0 < kSlotSubs ? n_sub - c0 : kSlotSubs;
-                    const uint32_t a_slot = a_base + ring * (uint32_t)kSlotCols;
-                    const uint32_t b_slot = ring * (uint32_t)kSlotSubs;
-                    for (int j = 0; j < n_in; ++j) {
-                        uint32_t b_idx = b_slot + (uint32_t)j;       // streamed: the sub-chunk's place in the ring slot
-                        if (kResident) {                             // resident: its place in the packed tensor
-                            if (seg == nseg) {
-                                seg = 0;
-                                if (narrow) { k = __ffs((int)m0) - 1; m0 &= m0 - 1u; }
-                                else if (m_lo) { k = __ffsll((long long)m_lo) - 1; m_lo &= m_lo - 1; }
-                                else { k = 63 + __ffsll((long long)m_hi); m_hi &= m_hi - 1; }
-                            }
-                            b_idx = (uint32_t)(k * nseg + seg);
-                            ++seg;
-                        }
-                        const uint32_t blo = bdesc_lo0 + b_idx * b_sub16;
-                        const uint32_t a_tmem = a_slot + (uint32_t)(j * kAReg);
+                    const int n_in = n_sub - c0 < kGroup ? n_sub - c0 : kGroup;
+                    const uint32_t a_unit = a_base + u * (uint32_t)kUnitCols;
+                    const uint32_t b_unit = u * (uint32_t)kGroup;
 #pragma unroll
-                        for (int ks = 0; ks < CH / 32; ++ks) {       // one k-step = 32 bytes of K: +8 TMEM columns, +2 in the desc (addr >> 4)
-                            const uint64_t bdesc = ((uint64_t)bdesc_hi << 32) | (uint64_t)(blo + (uint32_t)(ks * 2));
-                            tc_mma_ts<kInt8>(d_tmem, a_tmem + (uint32_t)(ks * 8), bdesc, idesc, accumulate);
-                            accumulate = 1u;
+                    for (int j = 0; j < kGroup; ++j) {
+                        if (j < n_in) {
+                            uint32_t b_idx = b_unit + (uint32_t)j;       // streamed: the sub-chunk's place in the unit's B slot
+                            if (kResident) {                             // resident: its place in the packed tensor
+                                if (seg == nseg) {
+                                    seg = 0;
+                                    if (narrow) { k = __ffs((int)m0) - 1; m0 &= m0 - 1u; }
+                                    else if (m_lo) { k = __ffsll((long long)m_lo) - 1; m_lo &= m_lo - 1; }
+                                    else { k = 63 + __ffsll((long long)m_hi); m_hi &= m_hi - 1; }
+                                }
+                                b_idx = (uint32_t)(k * nseg + seg);
+                                ++seg;
+                            }
+                            const uint32_t blo = bdesc_lo0 + b_idx * b_sub16;
+                            const uint32_t a_tmem = a_unit + (uint32_t)(j * kAReg);
+#pragma unroll
+                            for (int ks = 0; ks < CH / 32; ++ks) {       // one k-step = 32 bytes of K: +8 TMEM columns, +2 in the desc (addr >> 4)
+                                const uint64_t bdesc = ((uint64_t)bdesc_hi << 32) | (uint64_t)(blo + (uint32_t)(ks * 2));
+                                tc_mma_ts<kInt8>(d_tmem, a_tmem + (uint32_t)(ks * 8), bdesc, idesc, accumulate);
+                                accumulate = 1u;
+                            }
                         }
                     }
-                    ql_tc_commit(empty0 + ring * 8u);
-                    if (c0 + kSlotSubs >= n_sub) ql_tc_commit(ql_smem_u32(&misc->acc_full[a]));
-                    if (++ring == (uint32_t)S) { ring = 0; ph ^= 1u; }
+                    ql_tc_commit(empty0 + u * 8u);
+                    if (c0 + kGroup >= n_sub) ql_tc_commit(ql_smem_u32(&misc->acc_full[a]));
+                    if (++u == R) { u = 0; ph ^= 1u; }
                 }
             }
         }
         __syncwarp();
     } else {
-        // =============================== TMA loader ===============================
-        const uint32_t nbr_s0 = smem_base_u32 + (uint32_t)p.off_nbr;
-        const uint32_t nbr_stride = (uint32_t)p.nbr_stride, nbmask = (uint32_t)p.nbr_bufs - 1u;
-        // Tile `tile` (the CTA's itn-th) -> rulebook buffer itn % nbr_bufs: its mask into the 16-byte header (so producers
-        // need no global load of their own), its non-empty slabs packed in mask order behind it (slab j = j-th set bit);
-        // lane j copies slabs j, j+32, ...
-        auto prefetch_nbr = [&](int64_t tile, uint32_t itn, const uint32_t (&mask)[kMaskWords], int n_slabs) {
+        // ================================= loader =================================
+        // Tile `tile` (the CTA's itn-th) -> rulebook buffer itn % nbr_bufs: header {mask, n_off, ord -> k table} written with
+        // plain stores (released by the arrive below), then the tile's whole [kvol][128] block, one bulk copy per 16 KB.
+        auto prefetch_nbr = [&](int64_t tile, uint32_t itn, const uint32_t (&mask)[kMaskWords], int n_off) {
             const uint32_t nb = itn & nbmask;
             const uint32_t bar = ql_smem_u32(&misc->nbr_full[nb]);
             const uint32_t dst = nbr_s0 + nb * nbr_stride;
             ql_mbar_wait(ql_smem_u32(&misc->nbr_empty[nb]), ((itn >> p.nbr_log2) & 1u) ^ 1u);
-            if (lane < kMaskWords) {
-                uint32_t w = mask[0];
+            int prefix = 0;
 #pragma unroll
-                for (int i = 1; i < kMaskWords; ++i)
-                    if (lane == i) w = mask[i];
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + 4u * lane), "r"(w) : "memory");
+            for (int i = 0; i < kMaskWords; ++i) {
+                const uint32_t w = mask[i];
+                if (lane == i) sts_u32(dst + 4u * i, w);
+                if ((w >> lane) & 1u) sts_u8(dst + 32u + (uint32_t)(prefix + __popc(w & ((1u << lane) - 1u))), i * 32 + lane);
+                prefix += __popc(w);
             }
+            if (lane == 0) sts_u32(dst + 16u, (uint32_t)n_off);
             __syncwarp();
-            if (lane == 0) ql_mbar_arrive_expect_tx(bar, (uint32_t)n_slabs * (QL_TILE_M * 4u));   // release: orders the header stores
+            const uint32_t total = (uint32_t)p.kvol * (QL_TILE_M * 4u);
+            if (lane == 0) ql_mbar_arrive_expect_tx(bar, total);     // release: orders the header stores
             __syncwarp();
-            const int* src = p.nbr + tile * (int64_t)p.kvol * QL_TILE_M;
-            for (int j0 = 0; j0 < n_slabs; j0 += 32) {
-                const int j = j0 + lane;
-                if (j < n_slabs) ql_bulk_g2s(dst + 16u + (uint32_t)j * (QL_TILE_M * 4u), src + nth_set_bit(mask, j) * QL_TILE_M, QL_TILE_M * 4u, bar);
-                __syncwarp();
-            }
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.nbr + tile * (int64_t)p.kvol * QL_TILE_M);
+            const uint32_t off = (uint32_t)lane * 16384u;
+            if (off < total) ql_bulk_g2s(dst + (uint32_t)kNbrHeader + off, src + off, total - off < 16384u ? total - off : 16384u, bar);
+            __syncwarp();
         };
-        uint32_t it = 0;
         if (kResident && (int64_t)blockIdx.x < n_tiles) {
             // the whole packed weight tensor, 32 lanes x (w_bytes / 32) bytes
             const uint32_t bar = ql_smem_u32(&misc->w_full);
@@ -601,50 +593,54 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
         int64_t pf_tile = blockIdx.x;
         uint32_t pf_it = 0;
         uint32_t pf_mask[kMaskWords];
-        int pf_sub = pf_tile < n_tiles ? load_tile_mask(p, pf_tile, pf_mask) : 0;
+        int pf_off = pf_tile < n_tiles ? load_tile_mask(p, pf_tile, pf_mask) : 0;
         auto prefetch_step = [&]() {
             if (pf_tile >= n_tiles) return;
             uint32_t m[kMaskWords];
 #pragma unroll
             for (int i = 0; i < kMaskWords; ++i) m[i] = pf_mask[i];
-            const int n_slabs = pf_sub / p.nseg;
+            const int n_off = pf_off;
             const int64_t t = pf_tile;
             const uint32_t itn = pf_it;
             pf_tile += gridDim.x; ++pf_it;
-            if (pf_tile < n_tiles) pf_sub = load_tile_mask(p, pf_tile, pf_mask);
-            prefetch_nbr(t, itn, m, n_slabs);
+            if (pf_tile < n_tiles) pf_off = load_tile_mask(p, pf_tile, pf_mask);
+            prefetch_nbr(t, itn, m, n_off);
         };
         for (int i = 0; i < p.nbr_bufs - 1; ++i) prefetch_step();
-        // streamed weights: one slot per pass, lane j = the slot's j-th sub-chunk
-        uint32_t ring = 0, ph = 0;
-        uint32_t mask_next[kMaskWords];
-        int n_sub_next = (!kResident && (int64_t)blockIdx.x < n_tiles) ? load_tile_mask(p, blockIdx.x, mask_next) : 0;
+        // streamed weights: up to half the ring per pass, lane l = sub-chunk l of the pass (unit l / kGroup)
+        uint32_t u = 0, ph = 0, it = 0;
+        const uint32_t batch_subs = (R / 2u > 0u ? R / 2u : 1u) << kGroupLog2;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             prefetch_step();
             if constexpr (!kResident) {
-            uint32_t mask[kMaskWords];
-#pragma unroll
-            for (int i = 0; i < kMaskWords; ++i) mask[i] = mask_next[i];
-            const int n_sub = n_sub_next;
-            if (tile + gridDim.x < n_tiles) n_sub_next = load_tile_mask(p, tile + gridDim.x, mask_next);
-            for (int c0 = 0; c0 < n_sub; c0 += kSlotSubs) {
-                const int sub = c0 + lane;
-                const bool mine = lane < kSlotSubs && sub < n_sub;
-                ql_mbar_wait(ql_smem_u32(&misc->empty[ring]), ph ^ 1u);
-                if (lane == 0) {
-                    const int n_in = n_sub - c0 < kSlotSubs ? n_sub - c0 : kSlotSubs;
-                    ql_mbar_arrive_expect_tx(ql_smem_u32(&misc->full[ring]), (uint32_t)n_in * b_sub_bytes);
+                const uint32_t buf = nbr_s0 + (it & nbmask) * nbr_stride;     // this tile's header (already resident: prefetched earlier)
+                const uint32_t n_sub = (uint32_t)ql_lds_s32(buf + 16u) * (uint32_t)p.nseg;
+                for (uint32_t c0 = 0; c0 < n_sub; c0 += batch_subs) {
+                    const uint32_t sub = c0 + (uint32_t)lane;
+                    const bool mine = (uint32_t)lane < batch_subs && sub < n_sub;
+                    const uint32_t bu = (uint32_t)lane >> kGroupLog2, j = (uint32_t)lane & (uint32_t)(kGroup - 1);
+                    uint32_t uu = u + bu, pp = ph;
+                    if (uu >= R) { uu -= R; pp ^= 1u; }
+                    const uint32_t fbar = full0 + uu * 8u;
+                    if (mine && j == 0) {
+                        ql_mbar_wait(empty0 + uu * 8u, pp ^ 1u);
+                        const uint32_t left = n_sub - sub;
+                        ql_mbar_arrive_expect_tx(fbar, (left < (uint32_t)kGroup ? left : (uint32_t)kGroup) * b_sub_bytes);
+                    }
+                    __syncwarp();
+                    if (mine) {
+                        uint32_t ord = sub, seg = 0;
+                        if (CH == 128) { ord = (sub * p.inv_nseg) >> 16; seg = sub - ord * (uint32_t)p.nseg; }
+                        const uint32_t k = (uint32_t)lds_u8(buf + 32u + ord);
+                        ql_bulk_g2s(smem_base_u32 + (uu * (uint32_t)kGroup + j) * b_sub_bytes,
+                                    p.w_packed + (size_t)(k * (uint32_t)p.nseg + seg) * b_sub_bytes, b_sub_bytes, fbar);
+                    }
+                    __syncwarp();
+                    const uint32_t left = n_sub - c0;
+                    const uint32_t nu = ((left < batch_subs ? left : batch_subs) + (uint32_t)kGroup - 1u) >> kGroupLog2;
+                    u += nu;
+                    if (u >= R) { u -= R; ph ^= 1u; }
                 }
-                __syncwarp();
-                if (mine) {
-                    const int ord = sub / p.nseg, seg = sub - ord * p.nseg;
-                    const int k = nth_set_bit(mask, ord);
-                    ql_bulk_g2s(smem_base_u32 + (ring * (uint32_t)kSlotSubs + (uint32_t)lane) * b_sub_bytes,
-                                p.w_packed + (int64_t)(k * p.nseg + seg) * b_sub_bytes, b_sub_bytes, ql_smem_u32(&misc->full[ring]));
-                }
-                __syncwarp();
-                if (++ring == (uint32_t)S) { ring = 0; ph ^= 1u; }
-            }
             }
         }
     }
@@ -680,6 +676,15 @@ inline uint32_t chunk_sw_offset(int ch, uint32_t r, uint32_t c16) {
     return (r >> 3) * (uint32_t)(8 * ch) + (r & 7u) * (uint32_t)ch + ((c16 ^ x) << 4);
 }
 
+// K order inside a sub-chunk: TMEM column c (4 bytes of K) of the A operand holds source word k_word_src(ch, c) of the
+// row segment -- the identity for the lane-per-row gather (CH = 32), the 16x256b quad-gather order for CH >= 64.
+inline int k_word_src(int ch, int c) {
+    if (ch < 64) return c;
+    const int krep = ch / 32;
+    const int v2 = c >> 3, t0 = (c >> 1) & 3, e = c & 1;
+    return 2 * krep * t0 + 2 * v2 + e;
+}
+
 template <bool kInt8, int CH, bool kResident>
 cudaError_t launch2(const ConvParams& p, int grid, size_t smem_bytes, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(k_spconv_ts<kInt8, CH, kResident>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
@@ -703,7 +708,8 @@ extern "C" size_t ql_packed_weight_bytes(int32_t c_in, int32_t c_out, int32_t kv
 
 // w_host: [c_out][kvol][c_in] elements (== the reference layout (oc, kd, kh, kw, ic) flattened, quant/quant.py:37-39).
 // packed: for every (offset k, segment s) chunk one [c_out x CH bytes] K-major swizzled image (SWIZZLE_32B/64B/128B by
-// CH), zero padded -- exactly what the loader warp bulk-copies into the chunk's shared-memory slot.
+// CH), zero padded -- exactly what the loader warp bulk-copies into the chunk's shared-memory slot.  Inside a chunk row
+// the 4-byte K words follow the order in which the gather leaves them in tensor memory (k_word_src).
 extern "C" int ql_pack_weights_host(const void* w_host, int32_t elem_dtype, int32_t c_in, int32_t c_out, int32_t kvol,
                                     void* packed_host) {
     int es = elem_size(elem_dtype);
@@ -717,11 +723,13 @@ extern "C" int ql_pack_weights_host(const void* w_host, int32_t elem_dtype, int3
     uint8_t* dst = (uint8_t*)packed_host;
     for (int oc = 0; oc < c_out; ++oc)
         for (int k = 0; k < kvol; ++k)
-            for (int b = 0; b < row_bytes; b += 16) {
-                const int seg = b / 128, c16 = (b % 128) / 16;
-                memcpy(dst + (size_t)(k * g.nseg + seg) * chunk_bytes + chunk_sw_offset(g.ch, (uint32_t)oc, (uint32_t)c16),
-                       src + ((size_t)oc * kvol + k) * row_bytes + b, 16);
-            }
+            for (int seg = 0; seg < g.nseg; ++seg)
+                for (int c = 0; c < g.ch / 4; ++c) {
+                    const int b = seg * 128 + 4 * k_word_src(g.ch, c);          // source byte of this 4-byte K word
+                    if (b >= row_bytes) continue;                                // zero padding
+                    memcpy(dst + (size_t)(k * g.nseg + seg) * chunk_bytes + chunk_sw_offset(g.ch, (uint32_t)oc, (uint32_t)(c >> 2)) + 4 * (c & 3),
+                           src + ((size_t)oc * kvol + k) * row_bytes + b, 4);
+                }
     return QL_OK;
 }
 
@@ -750,31 +758,33 @@ extern "C" int ql_spconv_mma(const void* feats, int32_t in_dtype, const int32_t*
     p.residual = (const __half*)residual_f16; p.relu = relu; p.out = out; p.out_dtype = out_dtype;
     p.out_q = out_q; p.out_qscale = out_qscale; p.absmax = absmax;
 
-    // ring depth in slots (kTeams units of 32 TMEM columns): bounded by the TMEM columns left beside the accumulators
-    // and, when the weights are streamed, by shared memory
+    // ring depth in units (32 TMEM columns each): bounded by the TMEM columns left beside the accumulators and, when
+    // the weights are streamed, by shared memory (a unit's B slot = its 128/CH weight sub-chunks = c_out x 128 bytes)
     const int misc_bytes = (int)sizeof(MiscSmem) + 4 * c_out * 4;
     const int b_sub = c_out * g.ch;
-    const int b_slot = kTeams * c_out * 128;                     // a slot's weight sub-chunks
-    p.nbr_stride = (16 + kvol * QL_TILE_M * 4 + 127) & ~127;
-    p.n_acc = (kTmemCols - 2 * c_out) / kSlotCols >= 2 ? 2 : 1;
-    int S = (kTmemCols - p.n_acc * c_out) / kSlotCols;
-    if (S > kMaxSlots) S = kMaxSlots;
+    const int b_unit = c_out * 128;
+    p.inv_nseg = (uint32_t)((65536 + g.nseg - 1) / g.nseg);
+    p.nbr_stride = (kNbrHeader + kvol * QL_TILE_M * 4 + 127) & ~127;
+    p.n_acc = (kTmemCols - 2 * c_out) / kUnitCols >= kTeams ? 2 : 1;
+    int R = (kTmemCols - p.n_acc * c_out) / kUnitCols;
+    if (R > kMaxUnits) R = kMaxUnits;
     p.w_bytes = kvol * g.nseg * b_sub;
     for (p.nbr_bufs = 4; p.nbr_bufs >= 2; p.nbr_bufs >>= 1) {
         if (p.nbr_bufs == 4 && 4 * p.nbr_stride > 64 * 1024) continue;
         const int smem_free = kSmemBudget - 1024 - p.nbr_bufs * p.nbr_stride - ((misc_bytes + 127) & ~127);
         p.resident = (p.w_bytes <= smem_free && p.w_bytes % 512 == 0) ? 1 : 0;   // 32 lanes x 16-byte multiples
-        if (p.resident || smem_free / b_slot >= 2) {
-            if (!p.resident && S > smem_free / b_slot) S = smem_free / b_slot;
+        if (p.resident || smem_free / b_unit >= 2) {
+            if (!p.resident && R > smem_free / b_unit) R = smem_free / b_unit;
             break;
         }
     }
-    if (p.nbr_bufs < 2 || S < 2) return QL_ERR_UNSUPPORTED;
+    if (p.nbr_bufs < 2 || R < 2) return QL_ERR_UNSUPPORTED;
     p.nbr_log2 = p.nbr_bufs == 4 ? 2 : 1;
     const int nbr_bytes = p.nbr_bufs * p.nbr_stride;
-    p.n_slots = S;
+    p.n_ring = R;
+    p.teams = R < kTeams ? R : kTeams;
     p.a_col0 = p.n_acc * c_out;
-    p.off_nbr = p.resident ? ((p.w_bytes + 1023) & ~1023) : S * b_slot;
+    p.off_nbr = p.resident ? ((p.w_bytes + 1023) & ~1023) : ((R * b_unit + 1023) & ~1023);
     p.off_misc = (p.off_nbr + nbr_bytes + 127) & ~127;
     size_t smem_bytes = 1024 + (size_t)p.off_misc + misc_bytes;
     if (smem_bytes < (size_t)kSmemFloor) smem_bytes = kSmemFloor;

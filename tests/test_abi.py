@@ -52,10 +52,20 @@ def _chunk_geom(row_bytes):
     return (32 if row_bytes <= 32 else 64 if row_bytes <= 64 else 128), 1
 
 
+def _k_word_src(ch, c):
+    """K order inside a chunk row: identity for CH = 32 (lane-per-row gather); for CH >= 64 the order in which the
+    quad gather + tcgen05.st.16x256b leaves a row segment in tensor memory: column 8*v2 + 2*t0 + e <- word 2*(CH/32)*t0 + 2*v2 + e."""
+    if ch < 64:
+        return c
+    v2, t0, e = c >> 3, (c >> 1) & 3, c & 1
+    return 2 * (ch // 32) * t0 + 2 * v2 + e
+
+
 def test_pack_weights_host_layout():
     """The packed image is, per (kernel offset, 128-byte row segment) chunk, the K-major swizzled [c_out x CH] shared-memory
     layout the tcgen05 B descriptors assume: 16-byte piece c of row r lives at
-    (r//8)*8*CH + (r%8)*CH + ((c ^ x(r))*16), x(r) = r%8 (SWIZZLE_128B), (r//2)%4 (64B), (r//4)%2 (32B)."""
+    (r//8)*8*CH + (r%8)*CH + ((c ^ x(r))*16), x(r) = r%8 (SWIZZLE_128B), (r//2)%4 (64B), (r//4)%2 (32B); the 4-byte K words
+    of a row are in the gather's TMEM column order (_k_word_src)."""
     from qlidar import ops
     rng = np.random.default_rng(0)
     for dtype, cin, cout, K in [(torch.int8, 16, 16, 27), (torch.int8, 64, 32, 27), (torch.float16, 16, 48, 27),
@@ -77,12 +87,12 @@ def test_pack_weights_host_layout():
                 base = (k * nseg + seg) * cout * ch
                 for r in range(cout):
                     x = r % 8 if ch == 128 else ((r // 2) % 4 if ch == 64 else (r // 4) % 2)
-                    for c in range(ch // 16):
-                        off = (r // 8) * 8 * ch + (r % 8) * ch + ((c ^ x) * 16)
-                        b0 = seg * 128 + c * 16
-                        want = raw[r, k, b0:b0 + 16] if b0 < row_bytes else np.zeros(16, np.uint8)
-                        assert np.array_equal(img[off:off + 16], want)
-                        seen[base + off:base + off + 16] = True
+                    for c in range(ch // 4):                     # 4-byte K word c of the chunk row == TMEM column c of A
+                        off = (r // 8) * 8 * ch + (r % 8) * ch + (((c // 4) ^ x) * 16) + 4 * (c % 4)
+                        b0 = seg * 128 + 4 * _k_word_src(ch, c)
+                        want = raw[r, k, b0:b0 + 4] if b0 < row_bytes else np.zeros(4, np.uint8)
+                        assert np.array_equal(img[off:off + 4], want)
+                        seen[base + off:base + off + 4] = True
         assert seen.all()
 
 
