@@ -53,7 +53,9 @@ constexpr int kMaskWords = 4;                             // kernel volumes up t
 constexpr int kTmemCols = 512;
 constexpr int kSmemBudget = 232448;                       // 227 KB opt-in maximum per CTA
 constexpr int kSmemFloor = 120 * 1024;                    // always ask for > half an SM: one CTA (one TMEM owner) per SM
-constexpr int kNbrHeader = 160;                           // rulebook buffer header: 16 B mask, n_off at +16, ord -> k table at +32
+constexpr int kNbrHeaderMin = 160;                        // rulebook buffer header: 16 B mask, n_off at +16, n_sub at +20, ord -> k
+                                                          // table (u8) at +32, then (resident weights) one B-descriptor low
+                                                          // word per sub-chunk at +160
 
 __device__ __align__(128) uint8_t g_zero_line[128];       // what a missing neighbour reads (zero-initialised module memory)
 
@@ -87,6 +89,7 @@ struct ConvParams {
     int off_nbr;            // smem offset of the rulebook buffers: nbr_bufs x {header, [kvol][128] int32}
     int nbr_bufs, nbr_log2; // 4 (or 2 when shared memory is short): the loader runs nbr_bufs-1 tiles ahead
     int nbr_stride;         // bytes per buffer
+    int nbr_hdr;            // header bytes in front of the [kvol][128] block
     int off_misc;           // smem offset of MiscSmem from the 1024-aligned base
 };
 
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
         }
         for (int i = 0; i < 4; ++i) {
             ql_mbar_init(ql_smem_u32(&misc->nbr_full[i]), 1);
-            ql_mbar_init(ql_smem_u32(&misc->nbr_empty[i]), 4 * p.teams);
+            ql_mbar_init(ql_smem_u32(&misc->nbr_empty[i]), 4 * p.teams + 1);   // producer warps + the MMA issuer
         }
         ql_mbar_init(ql_smem_u32(&misc->w_full), 1);
         ql_fence_mbar_init();
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
             const uint8_t* const feats = p.feats;
             const uint8_t* const zero = g_zero_line;
             const bool wide = p.wide != 0;
-            const uint32_t nseg = (uint32_t)p.nseg, inv_nseg = p.inv_nseg;
+            const uint32_t nseg = (uint32_t)p.nseg, inv_nseg = p.inv_nseg, hdr = (uint32_t)p.nbr_hdr;
 
             uint32_t g = team;                               // next global unit of this team
             uint32_t G0 = 0;                                 // global number of the current tile's first unit
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
                 const uint32_t nb = it & nbmask;
                 const uint32_t buf = nbr_s0 + nb * nbr_stride;
                 ql_mbar_wait(ql_smem_u32(&misc->nbr_full[nb]), (it >> p.nbr_log2) & 1u);
-                const uint32_t n_sub = (uint32_t)ql_lds_s32(buf + 16u) * nseg;
+                const uint32_t n_sub = (uint32_t)ql_lds_s32(buf + 20u);
                 const uint32_t Gend = G0 + ((n_sub + kGroup - 1) >> kGroupLog2);
                 for (; g < Gend; g += T) {
                     const uint32_t c0 = (g - G0) << kGroupLog2;      // the unit's first sub-chunk
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
                             if (lc < n_sub) {
                                 uint32_t ord = lc;
                                 if (CH == 128) { ord = (lc * inv_nseg) >> 16; boff = (lc - ord * nseg) * 128u; }
-                                const uint32_t a = buf + (uint32_t)kNbrHeader + (uint32_t)lds_u8(buf + 32u + ord) * (QL_TILE_M * 4u) + row_off;
+                                const uint32_t a = buf + hdr + (uint32_t)lds_u8(buf + 32u + ord) * (QL_TILE_M * 4u) + row_off;
 #pragma unroll
                                 for (int rr = 0; rr < 4; ++rr) idx[rr] = ql_lds_s32(a + (uint32_t)rr * 32u);
                             }
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
                             const uint32_t lc = c0 + (uint32_t)j;            // CH = 32: one sub-chunk per kernel offset
                             int idx = -1;
                             if (lc < n_sub)
-                                idx = ql_lds_s32(buf + (uint32_t)kNbrHeader + (uint32_t)lds_u8(buf + 32u + lc) * (QL_TILE_M * 4u) + row_off);
+                                idx = ql_lds_s32(buf + hdr + (uint32_t)lds_u8(buf + 32u + lc) * (QL_TILE_M * 4u) + row_off);
                             const bool ok = idx >= 0;
                             const uint8_t* src = ok ? feats + (uint64_t)(uint32_t)idx * row_bytes : zero;
                             if (wide) {
@@ -496,59 +499,57 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
             const uint32_t bdesc_hi = (uint32_t)(bdesc0 >> 32), bdesc_lo0 = (uint32_t)bdesc0;
             const uint32_t b_sub16 = b_sub_bytes >> 4;
             const uint32_t a_base = tmem_base + (uint32_t)p.a_col0;
-            const int nseg = p.nseg;
-            const bool narrow = p.mask_words == 1;                 // kernel volume <= 32: the mask is one word
+            const uint32_t n_acc = (uint32_t)p.n_acc, c_out = (uint32_t)p.c_out;
             uint32_t u = 0, ph = 0, it = 0;
             if (kResident && (int64_t)blockIdx.x < n_tiles) ql_mbar_wait(ql_smem_u32(&misc->w_full), 0);
-            uint32_t mask_next[kMaskWords];
-            int n_sub_next = (int64_t)blockIdx.x < n_tiles ? load_tile_mask(p, blockIdx.x, mask_next) * nseg : 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                uint32_t m0 = mask_next[0];
-                uint64_t m_lo = (uint64_t)mask_next[0] | ((uint64_t)mask_next[1] << 32);
-                uint64_t m_hi = (uint64_t)mask_next[2] | ((uint64_t)mask_next[3] << 32);
-                const int n_sub = n_sub_next;
-                if (tile + gridDim.x < n_tiles) n_sub_next = load_tile_mask(p, tile + gridDim.x, mask_next) * nseg;   // in flight during this tile
-                const int a = p.n_acc == 2 ? (int)(it & 1u) : 0;
-                const uint32_t aph = p.n_acc == 2 ? ((it >> 1) & 1u) : (it & 1u);
+                // the tile's header in the rulebook buffer: n_sub and (resident weights) the B descriptor of every sub-chunk,
+                // prepared by the loader's 32 lanes so that this one thread only loads and issues
+                const uint32_t nb = it & nbmask;
+                const uint32_t buf = nbr_s0 + nb * nbr_stride;
+                ql_mbar_wait(ql_smem_u32(&misc->nbr_full[nb]), (it >> p.nbr_log2) & 1u);
+                const uint32_t n_sub = (uint32_t)ql_lds_s32(buf + 20u);
+                const uint32_t a = n_acc == 2 ? (it & 1u) : 0u;
+                const uint32_t aph = n_acc == 2 ? ((it >> 1) & 1u) : (it & 1u);
                 ql_mbar_wait(ql_smem_u32(&misc->acc_empty[a]), aph ^ 1u);
                 ql_tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.c_out);
+                const uint32_t d_tmem = tmem_base + a * c_out;
+                const uint32_t acc_bar = ql_smem_u32(&misc->acc_full[a]);
                 uint32_t accumulate = 0u;
-                int k = 0, seg = nseg;                           // seg == nseg: take the next offset from the mask
-                for (int c0 = 0; c0 < n_sub; c0 += kGroup) {
+                for (uint32_t c0 = 0; c0 < n_sub; c0 += kGroup) {
+                    uint32_t blo[kGroup];
+                    if constexpr (kResident) {
+                        const uint32_t ta = buf + (uint32_t)kNbrHeaderMin + 4u * c0;
+                        if constexpr (kGroup == 4) {
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(blo[0]), "=r"(blo[1]), "=r"(blo[2]), "=r"(blo[3]) : "r"(ta));
+                        } else if constexpr (kGroup == 2) {
+                            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(blo[0]), "=r"(blo[1]) : "r"(ta));
+                        } else {
+                            blo[0] = (uint32_t)ql_lds_s32(ta);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < kGroup; ++j) blo[j] = bdesc_lo0 + (u * (uint32_t)kGroup + (uint32_t)j) * b_sub16;
+                    }
                     ql_mbar_wait(full0 + u * 8u, ph);
                     ql_tc_fence_after();
-                    const int n_in = n_sub - c0 < kGroup ? n_sub - c0 : kGroup;
                     const uint32_t a_unit = a_base + u * (uint32_t)kUnitCols;
-                    const uint32_t b_unit = u * (uint32_t)kGroup;
 #pragma unroll
                     for (int j = 0; j < kGroup; ++j) {
-                        if (j < n_in) {
-                            uint32_t b_idx = b_unit + (uint32_t)j;       // streamed: the sub-chunk's place in the unit's B slot
-                            if (kResident) {                             // resident: its place in the packed tensor
-                                if (seg == nseg) {
-                                    seg = 0;
-                                    if (narrow) { k = __ffs((int)m0) - 1; m0 &= m0 - 1u; }
-                                    else if (m_lo) { k = __ffsll((long long)m_lo) - 1; m_lo &= m_lo - 1; }
-                                    else { k = 63 + __ffsll((long long)m_hi); m_hi &= m_hi - 1; }
-                                }
-                                b_idx = (uint32_t)(k * nseg + seg);
-                                ++seg;
-                            }
-                            const uint32_t blo = bdesc_lo0 + b_idx * b_sub16;
-                            const uint32_t a_tmem = a_unit + (uint32_t)(j * kAReg);
+                        if (j == 0 || c0 + (uint32_t)j < n_sub) {
 #pragma unroll
                             for (int ks = 0; ks < CH / 32; ++ks) {       // one k-step = 32 bytes of K: +8 TMEM columns, +2 in the desc (addr >> 4)
-                                const uint64_t bdesc = ((uint64_t)bdesc_hi << 32) | (uint64_t)(blo + (uint32_t)(ks * 2));
-                                tc_mma_ts<kInt8>(d_tmem, a_tmem + (uint32_t)(ks * 8), bdesc, idesc, accumulate);
+                                const uint64_t bdesc = ((uint64_t)bdesc_hi << 32) | (uint64_t)(blo[j] + (uint32_t)(ks * 2));
+                                tc_mma_ts<kInt8>(d_tmem, a_unit + (uint32_t)(j * kAReg + ks * 8), bdesc, idesc, accumulate);
                                 accumulate = 1u;
                             }
                         }
                     }
                     ql_tc_commit(empty0 + u * 8u);
-                    if (c0 + kGroup >= n_sub) ql_tc_commit(ql_smem_u32(&misc->acc_full[a]));
+                    if (c0 + kGroup >= n_sub) ql_tc_commit(acc_bar);
                     if (++u == R) { u = 0; ph ^= 1u; }
                 }
+                ql_mbar_arrive(ql_smem_u32(&misc->nbr_empty[nb]));
             }
         }
         __syncwarp();
@@ -569,14 +570,26 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
                 if ((w >> lane) & 1u) sts_u8(dst + 32u + (uint32_t)(prefix + __popc(w & ((1u << lane) - 1u))), i * 32 + lane);
                 prefix += __popc(w);
             }
-            if (lane == 0) sts_u32(dst + 16u, (uint32_t)n_off);
+            const uint32_t n_sub = (uint32_t)n_off * (uint32_t)p.nseg;
+            if (lane == 0) { sts_u32(dst + 16u, (uint32_t)n_off); sts_u32(dst + 20u, n_sub); }
             __syncwarp();
+            if constexpr (kResident) {
+                // B descriptor (low word) of every sub-chunk of the tile, in processing order, for the MMA issuer
+                const uint32_t bdesc_lo0 = (uint32_t)umma_desc_b<CH>(smem_base_u32);
+                for (uint32_t sub = (uint32_t)lane; sub < n_sub; sub += 32u) {
+                    uint32_t ord = sub, seg = 0;
+                    if (CH == 128) { ord = (sub * p.inv_nseg) >> 16; seg = sub - ord * (uint32_t)p.nseg; }
+                    const uint32_t k = (uint32_t)lds_u8(dst + 32u + ord);
+                    sts_u32(dst + (uint32_t)kNbrHeaderMin + 4u * sub, bdesc_lo0 + (k * (uint32_t)p.nseg + seg) * (b_sub_bytes >> 4));
+                }
+                __syncwarp();
+            }
             const uint32_t total = (uint32_t)p.kvol * (QL_TILE_M * 4u);
             if (lane == 0) ql_mbar_arrive_expect_tx(bar, total);     // release: orders the header stores
             __syncwarp();
             const uint8_t* src = reinterpret_cast<const uint8_t*>(p.nbr + tile * (int64_t)p.kvol * QL_TILE_M);
             const uint32_t off = (uint32_t)lane * 16384u;
-            if (off < total) ql_bulk_g2s(dst + (uint32_t)kNbrHeader + off, src + off, total - off < 16384u ? total - off : 16384u, bar);
+            if (off < total) ql_bulk_g2s(dst + (uint32_t)p.nbr_hdr + off, src + off, total - off < 16384u ? total - off : 16384u, bar);
             __syncwarp();
         };
         if (kResident && (int64_t)blockIdx.x < n_tiles) {
@@ -614,7 +627,7 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
             prefetch_step();
             if constexpr (!kResident) {
                 const uint32_t buf = nbr_s0 + (it & nbmask) * nbr_stride;     // this tile's header (already resident: prefetched earlier)
-                const uint32_t n_sub = (uint32_t)ql_lds_s32(buf + 16u) * (uint32_t)p.nseg;
+                const uint32_t n_sub = (uint32_t)ql_lds_s32(buf + 20u);
                 for (uint32_t c0 = 0; c0 < n_sub; c0 += batch_subs) {
                     const uint32_t sub = c0 + (uint32_t)lane;
                     const bool mine = (uint32_t)lane < batch_subs && sub < n_sub;
@@ -764,15 +777,23 @@ extern "C" int ql_spconv_mma(const void* feats, int32_t in_dtype, const int32_t*
     const int b_sub = c_out * g.ch;
     const int b_unit = c_out * 128;
     p.inv_nseg = (uint32_t)((65536 + g.nseg - 1) / g.nseg);
-    p.nbr_stride = (kNbrHeader + kvol * QL_TILE_M * 4 + 127) & ~127;
     p.n_acc = (kTmemCols - 2 * c_out) / kUnitCols >= kTeams ? 2 : 1;
     int R = (kTmemCols - p.n_acc * c_out) / kUnitCols;
     if (R > kMaxUnits) R = kMaxUnits;
     p.w_bytes = kvol * g.nseg * b_sub;
+    const int hdr_resident = kNbrHeaderMin + ((4 * kvol * g.nseg + 15) & ~15);
     for (p.nbr_bufs = 4; p.nbr_bufs >= 2; p.nbr_bufs >>= 1) {
+        // try with the resident-weights header first; fall back to streamed weights (short header) if they do not fit
+        p.nbr_hdr = hdr_resident;
+        p.nbr_stride = (p.nbr_hdr + kvol * QL_TILE_M * 4 + 127) & ~127;
         if (p.nbr_bufs == 4 && 4 * p.nbr_stride > 64 * 1024) continue;
-        const int smem_free = kSmemBudget - 1024 - p.nbr_bufs * p.nbr_stride - ((misc_bytes + 127) & ~127);
+        int smem_free = kSmemBudget - 1024 - p.nbr_bufs * p.nbr_stride - ((misc_bytes + 127) & ~127);
         p.resident = (p.w_bytes <= smem_free && p.w_bytes % 512 == 0) ? 1 : 0;   // 32 lanes x 16-byte multiples
+        if (!p.resident) {
+            p.nbr_hdr = kNbrHeaderMin;
+            p.nbr_stride = (p.nbr_hdr + kvol * QL_TILE_M * 4 + 127) & ~127;
+            smem_free = kSmemBudget - 1024 - p.nbr_bufs * p.nbr_stride - ((misc_bytes + 127) & ~127);
+        }
         if (p.resident || smem_free / b_unit >= 2) {
             if (!p.resident && R > smem_free / b_unit) R = smem_free / b_unit;
             break;
