@@ -106,6 +106,21 @@ int ql_rulebook_strided(const int32_t* in_coords, int64_t n_in_cap, const int32_
                         uint64_t* out_table, int64_t out_table_cap, int32_t* nbr_out, uint32_t* tile_kmask,
                         void* workspace, size_t workspace_bytes, ql_stream_t stream);
 
+/* ---- rank index of a key-sorted site list (no reference counterpart: it replaces the hash probes spconv does for the
+ *      layers that FOLLOW a strided conv on the same stage).  ql_rulebook_strided leaves, in its workspace, a bitmap over
+ *      the output grid's cells and an exclusive popcount prefix per 32-cell word; for the rows it produced (ascending key
+ *      order) row(key) = word_prefix[key/32] + popc(bitmap[key/32] & ((1 << key%32) - 1)).  `out_table` of
+ *      ql_rulebook_strided may be NULL when every consumer of the stage uses the rank index instead of the hash.
+ *      ql_rulebook_strided_index (host only) returns the two device pointers inside `workspace`; they stay valid until the
+ *      workspace is reused.  ql_rulebook_subm_ranked == ql_rulebook_subm on such a stage. */
+int ql_rulebook_strided_index(int32_t B, int32_t D, int32_t H, int32_t W,
+                              const int32_t* ksize_host, const int32_t* stride_host, const int32_t* pad_host,
+                              void* workspace, const uint32_t** bitmap, const uint32_t** word_prefix, int64_t* n_words);
+int ql_rulebook_subm_ranked(const int32_t* coords, int64_t n_cap, const int32_t* n_dev,
+                            int32_t B, int32_t D, int32_t H, int32_t W, const int32_t* ksize_host,
+                            const uint32_t* bitmap, const uint32_t* word_prefix,
+                            int32_t* nbr_out, uint32_t* tile_kmask, ql_stream_t stream);
+
 /* ---- implicit gather-GEMM-scatter sparse conv on tcgen05 tensor cores (replaces QConvNd.forward ->
  *      [EXT] spconv conv forward, quant/quant.py:36-58, plus the BatchNorm1d/ReLU/residual that follow it in
  *      post_act_block / SparseBasicBlock, spconv_backbone.py:8-27,51-67).
@@ -152,6 +167,11 @@ size_t ql_bev_densify_workspace_bytes(int32_t B, int32_t D, int32_t H, int32_t W
 int ql_bev_densify(const void* feats, int32_t in_dtype, int32_t c, const uint64_t* table, int64_t table_cap,
                    int32_t B, int32_t D, int32_t H, int32_t W, void* out, int32_t out_dtype,
                    void* workspace, size_t workspace_bytes, ql_stream_t stream);
+
+/* same hand-off for a key-sorted stage, cell -> row taken from the stage's rank index (rows >= min(n_cap, *n_dev) are absent) */
+int ql_bev_densify_ranked(const void* feats, int32_t in_dtype, int32_t c, const uint32_t* bitmap, const uint32_t* word_prefix,
+                          int64_t n_cap, const int32_t* n_dev, int32_t B, int32_t D, int32_t H, int32_t W, void* out,
+                          int32_t out_dtype, void* workspace, size_t workspace_bytes, ql_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -20,6 +20,37 @@ __global__ void __launch_bounds__(256) k_bev_index(const uint2* __restrict__ tab
     idxmap[cell] = ql_hash_lookup(table, cap_mask, (uint32_t)cell);       // the linear cell index IS the key
 }
 
+// the same cell -> row map from a rank index (key-sorted rows: row == rank), one thread per 32-cell bitmap word
+__global__ void __launch_bounds__(256) k_bev_index_ranked(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_prefix,
+                                                          int64_t n_cells, int64_t n_rows, const int* __restrict__ n_dev,
+                                                          int* __restrict__ idxmap) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t cell0 = w * 32;
+    if (cell0 >= n_cells) return;
+    const int64_t n = n_dev ? min((int64_t)*n_dev, n_rows) : n_rows;
+    const uint32_t bits = bitmap[w];
+    uint32_t rank = bits ? word_prefix[w] : 0u;
+    const int lim = (int)min((int64_t)32, n_cells - cell0);
+    if (lim == 32) {
+        int v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const bool on = (bits >> i) & 1u;
+            v[i] = (on && (int64_t)rank < n) ? (int)rank : -1;
+            rank += on ? 1u : 0u;
+        }
+        int4* o = reinterpret_cast<int4*>(idxmap + cell0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = make_int4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+        for (int i = 0; i < lim; ++i) {
+            const bool on = (bits >> i) & 1u;
+            idxmap[cell0 + i] = (on && (int64_t)rank < n) ? (int)rank : -1;
+            rank += on ? 1u : 0u;
+        }
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ float to_f(T v);
 template <>
@@ -130,6 +161,28 @@ extern "C" int ql_bev_densify(const void* feats, int32_t in_dtype, int32_t c, co
     int* idxmap = (int*)workspace;
     const int64_t cells = (int64_t)B * D * H * W;
     k_bev_index<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>((const uint2*)table, (uint32_t)(table_cap - 1), g, idxmap);
+    if (in_dtype == QL_F16 && out_dtype == QL_F16) dispatch_write<__half, __half>(feats, c, idxmap, g, out, st);
+    else if (in_dtype == QL_F16 && out_dtype == QL_F32) dispatch_write<__half, float>(feats, c, idxmap, g, out, st);
+    else if (in_dtype == QL_F32 && out_dtype == QL_F16) dispatch_write<float, __half>(feats, c, idxmap, g, out, st);
+    else dispatch_write<float, float>(feats, c, idxmap, g, out, st);
+    QL_CUDA_CHECK_LAST();
+    return QL_OK;
+}
+
+extern "C" int ql_bev_densify_ranked(const void* feats, int32_t in_dtype, int32_t c, const uint32_t* bitmap, const uint32_t* word_prefix,
+                                     int64_t n_cap, const int32_t* n_dev, int32_t B, int32_t D, int32_t H, int32_t W, void* out,
+                                     int32_t out_dtype, void* workspace, size_t workspace_bytes, ql_stream_t stream_) {
+    if (!feats || !bitmap || !word_prefix || !out || !workspace || c <= 0 || B <= 0 || D <= 0 || H <= 0 || W <= 0 || n_cap < 0)
+        return QL_ERR_INVALID;
+    if ((in_dtype != QL_F16 && in_dtype != QL_F32) || (out_dtype != QL_F16 && out_dtype != QL_F32)) return QL_ERR_INVALID;
+    if ((double)B * D * H * W >= 4294967295.0) return QL_ERR_GRID_TOO_LARGE;
+    if (workspace_bytes < ql_bev_densify_workspace_bytes(B, D, H, W)) return QL_ERR_WORKSPACE;
+    QlGrid g{B, D, H, W};
+    cudaStream_t st = (cudaStream_t)stream_;
+    int* idxmap = (int*)workspace;
+    const int64_t cells = (int64_t)B * D * H * W;
+    const int64_t words = (cells + 31) / 32;
+    k_bev_index_ranked<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(bitmap, word_prefix, cells, n_cap, n_dev, idxmap);
     if (in_dtype == QL_F16 && out_dtype == QL_F16) dispatch_write<__half, __half>(feats, c, idxmap, g, out, st);
     else if (in_dtype == QL_F16 && out_dtype == QL_F32) dispatch_write<__half, float>(feats, c, idxmap, g, out, st);
     else if (in_dtype == QL_F32 && out_dtype == QL_F16) dispatch_write<float, __half>(feats, c, idxmap, g, out, st);

@@ -85,6 +85,63 @@ __global__ void __launch_bounds__(QL_TILE_M) k_rb_pairs(const int4* __restrict__
     }
 }
 
+// Submanifold rulebook over a KEY-SORTED site list (every stage a strided conv produced): the neighbour lookup is a rank
+// query on the stage's bitmap -- row(key) = word_prefix[key / 32] + popc(bitmap[key / 32] below the bit) -- instead of a hash
+// probe.  The kw cells of one (kz, ky) line are adjacent bits, mostly of ONE bitmap word, so an output row costs ~kd*kh
+// bitmap/prefix word pairs (dense, L1/L2 resident) rather than K random 8-byte table probes.
+__global__ void __launch_bounds__(QL_TILE_M) k_rb_pairs_ranked(const int4* __restrict__ coords, int64_t n_cap,
+                                                               const int* __restrict__ n_dev, QlGrid g, ConvGeom cg,
+                                                               const uint32_t* __restrict__ bitmap,
+                                                               const uint32_t* __restrict__ word_prefix, int* __restrict__ nbr,
+                                                               uint32_t* __restrict__ kmask) {
+    __shared__ uint32_t s_mask[QL_MASK_WORDS_MAX];
+    const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
+    const int64_t tile = blockIdx.x;
+    if (tile * QL_TILE_M >= n) return;
+    const int r = threadIdx.x;
+    const int64_t row = tile * QL_TILE_M + r;
+    const int K = cg.kd * cg.kh * cg.kw;
+    int* dst = nbr + tile * (int64_t)K * QL_TILE_M + r;
+    const int mask_words = (K + 31) >> 5;
+    if (r < mask_words) s_mask[r] = 0u;
+    __syncthreads();
+    const bool live = row < n;
+    const int4 c = live ? coords[row] : make_int4(0, 0, 0, 0);      // b, z, y, x
+    const int bz = c.y - cg.pd, by = c.z - cg.ph, bx = c.w - cg.pw;
+    for (int kz = 0; kz < cg.kd; ++kz) {
+        for (int ky = 0; ky < cg.kh; ++ky) {
+            const int z = bz + kz, y = by + ky;
+            const bool line_ok = live && z >= 0 && z < g.D && y >= 0 && y < g.H;
+            // key of the line's first cell (x = bx, possibly negative: only in-range cells are looked at)
+            const uint32_t key0 = ql_key(g, c.x, line_ok ? z : 0, line_ok ? y : 0, 0) + (uint32_t)bx;
+            uint32_t w_cached = 0xFFFFFFFFu, bits = 0u, pre = 0u;
+            for (int kx = 0; kx < cg.kw; ++kx) {
+                const int x = bx + kx;
+                int res = -1;
+                if (line_ok && x >= 0 && x < g.W) {
+                    const uint32_t key = key0 + (uint32_t)kx;
+                    const uint32_t w = key >> 5;
+                    if (w != w_cached) { bits = __ldg(bitmap + w); w_cached = w; pre = 0xFFFFFFFFu; }
+                    const uint32_t bit = 1u << (key & 31u);
+                    if (bits & bit) {
+                        if (pre == 0xFFFFFFFFu) pre = __ldg(word_prefix + w);
+                        const uint32_t rank = pre + (uint32_t)__popc(bits & (bit - 1u));
+                        if ((int64_t)rank < n) res = (int)rank;
+                    }
+                }
+                const int k = (kz * cg.kh + ky) * cg.kw + kx;
+                dst[(int64_t)k * QL_TILE_M] = res;
+                const uint32_t any = __ballot_sync(0xffffffffu, res >= 0);
+                if (any && (threadIdx.x & 31) == 0) atomicOr(&s_mask[k >> 5], 1u << (k & 31));
+            }
+        }
+    }
+    if (kmask) {
+        __syncthreads();
+        if (r < mask_words) kmask[tile * mask_words + r] = s_mask[r];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Strided (regular) sparse conv.  The active output set is built in a bitmap over the output grid
 // (one bit per cell, <= B*Do*Ho*Wo/8 bytes, L2 resident for every backbone stage), numbered by a popcount scan
@@ -177,8 +234,10 @@ __global__ void __launch_bounds__(QL_SCAN_THREADS) k_rb_emit(const uint32_t* __r
                 const uint32_t pos = __fns(bj, 0, (int)(i - ej) + 1);
                 const uint32_t key = (uint32_t)(warp_w0 + j) * 32u + pos;
                 out_coords[rank] = ql_unkey(gout, key);
-                const uint32_t s = ql_hash_insert(out_table, cap_mask, key);
-                out_table[s].y = rank;
+                if (out_table) {
+                    const uint32_t s = ql_hash_insert(out_table, cap_mask, key);
+                    out_table[s].y = rank;
+                }
             }
         }
     }
@@ -308,12 +367,12 @@ extern "C" int ql_rulebook_strided(const int32_t* in_coords, int64_t n_in_cap, c
                                    size_t workspace_bytes, ql_stream_t stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     ConvGeom cg;
-    if (!in_coords || !out_coords || !n_out_dev || !out_table || !nbr_out || !workspace || !stride || !pad ||
+    if (!in_coords || !out_coords || !n_out_dev || !nbr_out || !workspace || !stride || !pad ||
         !geom_from_host(ksize, stride, pad, cg))
         return QL_ERR_INVALID;
-    if (out_table_cap <= 0 || (out_table_cap & (out_table_cap - 1)) || out_table_cap < 2 * n_out_cap || n_out_cap <= 0 ||
-        n_out_cap >= 2147483647LL || n_in_cap < 0 || n_in_cap >= 2147483647LL)
+    if (out_table && (out_table_cap <= 0 || (out_table_cap & (out_table_cap - 1)) || out_table_cap < 2 * n_out_cap))
         return QL_ERR_INVALID;
+    if (n_out_cap <= 0 || n_out_cap >= 2147483647LL || n_in_cap < 0 || n_in_cap >= 2147483647LL) return QL_ERR_INVALID;
     const int K = cg.kd * cg.kh * cg.kw;
     QlGrid gout;
     if (!out_grid(B, D, H, W, cg, gout)) return QL_ERR_INVALID;
@@ -327,20 +386,51 @@ extern "C" int ql_rulebook_strided(const int32_t* in_coords, int64_t n_in_cap, c
     int* blocks = (int*)(ws + w.blocks);
     const int mask_words = (K + 31) / 32;
 
-    if (cudaMemsetAsync(out_table, 0xFF, (size_t)out_table_cap * 8, st) != cudaSuccess) return QL_ERR_CUDA;
+    if (out_table && cudaMemsetAsync(out_table, 0xFF, (size_t)out_table_cap * 8, st) != cudaSuccess) return QL_ERR_CUDA;
     if (cudaMemsetAsync(bitmap, 0, (size_t)w.n_words * 4, st) != cudaSuccess) return QL_ERR_CUDA;
     const unsigned gin = (unsigned)((n_in_cap + 255) / 256);
     if (gin) k_rb_mark<<<gin, 256, 0, st>>>((const int4*)in_coords, n_in_cap, n_in_dev, cg, gout, bitmap);
     k_rb_popc<<<(unsigned)w.n_blocks, QL_SCAN_THREADS, 0, st>>>(bitmap, w.n_words, blocks);
     k_scan_blocks<<<1, QL_SCAN_THREADS, 0, st>>>(blocks, (int)w.n_blocks, n_out_dev + 1, n_out_dev, n_out_cap);
     k_rb_emit<<<(unsigned)w.n_blocks, QL_SCAN_THREADS, 0, st>>>(bitmap, w.n_words, blocks, gout, prefix, (int4*)out_coords, n_out_cap,
-                                                              (uint2*)out_table, (uint32_t)(out_table_cap - 1));
+                                                              (uint2*)out_table, out_table ? (uint32_t)(out_table_cap - 1) : 0u);
     k_rb_fill<<<4 * ql_num_sms(), 256, 0, st>>>((int4*)nbr_out, K, n_out_dev, n_out_cap);
     if (gin)
         k_rb_scatter<<<gin, 256, 0, st>>>((const int4*)in_coords, n_in_cap, n_in_dev, cg, gout, bitmap, prefix, n_out_cap, nbr_out);
     if (tile_kmask)
         k_rb_kmask<<<(unsigned)ql_rulebook_num_tiles(n_out_cap), QL_TILE_M, 0, st>>>(nbr_out, K, n_out_dev, n_out_cap, tile_kmask,
                                                                                       mask_words);
+    QL_CUDA_CHECK_LAST();
+    return QL_OK;
+}
+
+extern "C" int ql_rulebook_strided_index(int32_t B, int32_t D, int32_t H, int32_t W, const int32_t* ksize, const int32_t* stride,
+                                         const int32_t* pad, void* workspace, const uint32_t** bitmap, const uint32_t** word_prefix,
+                                         int64_t* n_words) {
+    ConvGeom cg;
+    QlGrid gout;
+    if (!workspace || !bitmap || !word_prefix || !stride || !pad || !geom_from_host(ksize, stride, pad, cg) ||
+        !out_grid(B, D, H, W, cg, gout))
+        return QL_ERR_INVALID;
+    const StridedWs w = strided_ws_layout(gout);
+    *bitmap = (const uint32_t*)((char*)workspace + w.bitmap);
+    *word_prefix = (const uint32_t*)((char*)workspace + w.prefix);
+    if (n_words) *n_words = w.n_words;
+    return QL_OK;
+}
+
+extern "C" int ql_rulebook_subm_ranked(const int32_t* coords, int64_t n_cap, const int32_t* n_dev, int32_t B, int32_t D, int32_t H,
+                                       int32_t W, const int32_t* ksize, const uint32_t* bitmap, const uint32_t* word_prefix,
+                                       int32_t* nbr_out, uint32_t* tile_kmask, ql_stream_t stream_) {
+    ConvGeom cg;
+    if (!coords || !bitmap || !word_prefix || !nbr_out || !geom_from_host(ksize, nullptr, nullptr, cg)) return QL_ERR_INVALID;
+    if (!(cg.kd & 1) || !(cg.kh & 1) || !(cg.kw & 1)) return QL_ERR_INVALID;   // submanifold needs odd kernels
+    if ((double)B * D * H * W >= 4294967295.0) return QL_ERR_GRID_TOO_LARGE;
+    if (n_cap <= 0) return QL_OK;
+    QlGrid g{B, D, H, W};
+    unsigned tiles = (unsigned)ql_rulebook_num_tiles(n_cap);
+    k_rb_pairs_ranked<<<tiles, QL_TILE_M, 0, (cudaStream_t)stream_>>>((const int4*)coords, n_cap, n_dev, g, cg, bitmap, word_prefix,
+                                                                      nbr_out, tile_kmask);
     QL_CUDA_CHECK_LAST();
     return QL_OK;
 }

@@ -33,6 +33,8 @@ SIGNATURES = {
     "ql_rulebook_subm": (C.c_int, [_p, _i64, _p, _i32, _i32, _i32, _i32, _p, _p, _i64, _p, _p, _p]),
     "ql_rulebook_strided_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _p, _p, _p]),
     "ql_rulebook_strided": (C.c_int, [_p, _i64, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _i64, _p, _p, _i64, _p, _p, _p, _sz, _p]),
+    "ql_rulebook_strided_index": (C.c_int, [_i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    "ql_rulebook_subm_ranked": (C.c_int, [_p, _i64, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "ql_packed_weight_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ql_pack_weights_host": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p]),
     "ql_spconv_mma": (C.c_int, [_p, _i32, _p, _p, _i64, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _p]),
@@ -41,6 +43,7 @@ SIGNATURES = {
     "ql_quantize_rows": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p, _i32, _i32, _p, _p, _p]),
     "ql_bev_densify_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ql_bev_densify": (C.c_int, [_p, _i32, _i32, _p, _i64, _i32, _i32, _i32, _i32, _p, _i32, _p, _sz, _p]),
+    "ql_bev_densify_ranked": (C.c_int, [_p, _i32, _i32, _p, _p, _i64, _p, _i32, _i32, _i32, _i32, _p, _i32, _p, _sz, _p]),
 }
 
 _lib = None

@@ -62,6 +62,7 @@ class Stage:
     coords: Optional[torch.Tensor] = None
     n_dev: Optional[torch.Tensor] = None
     table: Optional[torch.Tensor] = None
+    rank: Optional[object] = None  # ops.RankIndex of a key-sorted stage (every stage a strided conv produced)
 
 
 def _bn_fold(bn: nn.BatchNorm1d):
@@ -211,9 +212,14 @@ class BackboneEngine:
         for st in self.stages[1:]:
             st.coords = z(st.cap, 4, dt=torch.int32)
             st.n_dev = z(2, dt=torch.int32)
-            st.table = z(ops.hash_capacity(st.cap), dt=torch.int64)
-        ws = [ops.rulebook_strided_workspace_bytes(self.stages[L.stage_in].grid, L.ksize, L.stride, L.pad) for L in self.layers if not L.subm]
-        self.rb_ws = z(max(ws + [256]), dt=torch.uint8)
+            st.table = None                                   # key-sorted stages are indexed by rank (bitmap + prefix), not by hash
+        # one strided-rulebook workspace per produced stage: its bitmap + prefix is that stage's rank index, used by the
+        # submanifold rulebooks (and the BEV hand-off) that follow instead of a hash table
+        for L in self.layers:
+            if not L.subm and self.stages[L.stage_out].rank is None:
+                gi = self.stages[L.stage_in].grid
+                w = z(ops.rulebook_strided_workspace_bytes(gi, L.ksize, L.stride, L.pad), dt=torch.uint8)
+                self.stages[L.stage_out].rank = ops.rulebook_strided_index(gi, L.ksize, L.stride, L.pad, w)
         self.kmasks: Dict[tuple, torch.Tensor] = {}
         n_abs = sum(L.cout for L in self.layers) + 256
         self.absmax_pool = z(n_abs, dt=torch.float32)
@@ -268,11 +274,13 @@ class BackboneEngine:
             si, so = self.stages[L.stage_in], self.stages[L.stage_out]
             nbr, kmask = self.rulebooks[L.rb_key], self.kmasks[L.rb_key]
             if L.rb_key not in built:
-                if L.subm:
+                if L.subm and si.rank is not None:
+                    self._op("rulebook_subm:" + L.name, 1, ops.rulebook_subm_ranked, si.coords, si.n_dev, si.grid, L.ksize, si.rank, nbr=nbr, kmask=kmask)
+                elif L.subm:
                     self._op("rulebook_subm:" + L.name, 1, ops.rulebook_subm, si.coords, si.n_dev, si.grid, L.ksize, si.table, nbr=nbr, kmask=kmask)
                 else:
                     self._op("rulebook_strided:" + L.name, 8, ops.rulebook_strided, si.coords, si.n_dev, si.grid, L.ksize, L.stride, L.pad,
-                             so.cap, out=(so.coords, so.n_dev, so.table, nbr), workspace=self.rb_ws, kmask=kmask)
+                             so.cap, out=(so.coords, so.n_dev, None, nbr), workspace=so.rank.workspace, kmask=kmask)
                 built.add(L.rb_key)
             absmax = L.out_absmax if i in self._need_absmax else None
             if L.block_input:
@@ -297,7 +305,10 @@ class BackboneEngine:
             x = L.out
         if self.bev:
             last = self.stages[-1]
-            self._op("bev_densify", 2, ops.bev_densify, x, last.table, last.grid, out=self.spatial_features, workspace=self.bev_ws)
+            if last.rank is not None:
+                self._op("bev_densify", 2, ops.bev_densify_ranked, x, last.rank, last.n_dev, last.grid, out=self.spatial_features, workspace=self.bev_ws)
+            else:
+                self._op("bev_densify", 2, ops.bev_densify, x, last.table, last.grid, out=self.spatial_features, workspace=self.bev_ws)
 
     def _run_from_points(self):
         s0 = self.stages[0]

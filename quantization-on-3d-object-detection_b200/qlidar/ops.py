@@ -132,6 +132,39 @@ def rulebook_subm(coords: torch.Tensor, n_dev: Optional[torch.Tensor], grid, ksi
     return (nbr, kmask) if (with_mask or kmask is not None) else nbr
 
 
+class RankIndex:
+    """(bitmap, word_prefix) device pointers inside a strided-rulebook workspace: the rank index of the stage that build
+    produced (include/qlidar.h).  Holds the workspace tensor so the memory outlives the pointers."""
+    def __init__(self, workspace: torch.Tensor, bitmap_ptr: int, prefix_ptr: int, n_words: int):
+        self.workspace, self.bitmap_ptr, self.prefix_ptr, self.n_words = workspace, bitmap_ptr, prefix_ptr, n_words
+
+
+def rulebook_strided_index(in_grid, ksize, stride, pad, workspace: torch.Tensor) -> RankIndex:
+    _need_cuda(workspace)
+    B, D, H, W = [int(v) for v in in_grid]
+    bm, pf, nw = C.c_void_p(), C.c_void_p(), C.c_int64()
+    check(lib().ql_rulebook_strided_index(B, D, H, W, _i32x3(triple(ksize)), _i32x3(triple(stride)), _i32x3(triple(pad)),
+                                          _ptr(workspace), C.byref(bm), C.byref(pf), C.byref(nw)), "ql_rulebook_strided_index")
+    return RankIndex(workspace, bm.value, pf.value, nw.value)
+
+
+def rulebook_subm_ranked(coords: torch.Tensor, n_dev: Optional[torch.Tensor], grid, ksize, index: RankIndex,
+                         nbr: Optional[torch.Tensor] = None, kmask: Optional[torch.Tensor] = None):
+    """Submanifold rulebook of a key-sorted stage through its rank index (no hash).  Returns (nbr, kmask)."""
+    _need_cuda(coords, n_dev, nbr, kmask)
+    k = triple(ksize)
+    K = k[0] * k[1] * k[2]
+    n_cap = coords.shape[0]
+    if nbr is None:
+        nbr = torch.empty((num_tiles(n_cap), K, TILE_M), dtype=torch.int32, device=coords.device)
+    if kmask is None:
+        kmask = torch.zeros((num_tiles(n_cap), mask_words(K)), dtype=torch.int32, device=coords.device)
+    B, D, H, W = [int(v) for v in grid]
+    check(lib().ql_rulebook_subm_ranked(_ptr(coords), n_cap, _ptr(n_dev), B, D, H, W, _i32x3(k), C.c_void_p(index.bitmap_ptr),
+                                        C.c_void_p(index.prefix_ptr), _ptr(nbr), _ptr(kmask), _stream()), "ql_rulebook_subm_ranked")
+    return nbr, kmask
+
+
 def rulebook_strided_workspace_bytes(grid, ksize, stride, pad) -> int:
     B, D, H, W = [int(v) for v in grid]
     n = int(lib().ql_rulebook_strided_workspace_bytes(B, D, H, W, _i32x3(triple(ksize)), _i32x3(triple(stride)), _i32x3(triple(pad))))
@@ -157,16 +190,33 @@ def rulebook_strided(coords: torch.Tensor, n_in_dev: Optional[torch.Tensor], gri
         out_table = torch.empty(hash_capacity(n_out_cap), dtype=torch.int64, device=dev)
         nbr = torch.empty((num_tiles(n_out_cap), K, TILE_M), dtype=torch.int32, device=dev)
     else:
-        out_coords, n_out_dev, out_table, nbr = out
+        out_coords, n_out_dev, out_table, nbr = out                   # out_table may be None: rank-index consumers only
     if kmask is None:
         kmask = torch.zeros((num_tiles(n_out_cap), mask_words(K)), dtype=torch.int32, device=dev)
     ws_bytes = rulebook_strided_workspace_bytes(grid, k, s, p)
     if workspace is None or workspace.numel() < ws_bytes:
         workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     check(lib().ql_rulebook_strided(_ptr(coords), n_in_cap, _ptr(n_in_dev), B, D, H, W, _i32x3(k), _i32x3(s), _i32x3(p),
-                                    _ptr(out_coords), int(n_out_cap), _ptr(n_out_dev), _ptr(out_table), out_table.numel(), _ptr(nbr),
+                                    _ptr(out_coords), int(n_out_cap), _ptr(n_out_dev), _ptr(out_table), 0 if out_table is None else out_table.numel(), _ptr(nbr),
                                     _ptr(kmask), _ptr(workspace), workspace.numel(), _stream()), "ql_rulebook_strided")
     return out_coords, n_out_dev, out_table, nbr, (B, od, oh, ow), kmask
+
+
+def bev_densify_ranked(feats: torch.Tensor, index: RankIndex, n_dev: Optional[torch.Tensor], grid, out: Optional[torch.Tensor] = None,
+                       out_dtype: torch.dtype = torch.float16, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bev_densify for a key-sorted stage: cell -> row from the stage's rank index."""
+    _need_cuda(feats, n_dev, out)
+    B, D, H, W = [int(v) for v in grid]
+    c = feats.shape[1]
+    if out is None:
+        out = torch.empty((B, c * D, H, W), dtype=out_dtype, device=feats.device)
+    ws_bytes = int(lib().ql_bev_densify_workspace_bytes(B, D, H, W))
+    if workspace is None or workspace.numel() < ws_bytes:
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=feats.device)
+    check(lib().ql_bev_densify_ranked(_ptr(feats), _DT[feats.dtype], c, C.c_void_p(index.bitmap_ptr), C.c_void_p(index.prefix_ptr),
+                                      feats.shape[0], _ptr(n_dev), B, D, H, W, _ptr(out), _DT[out.dtype], _ptr(workspace),
+                                      workspace.numel(), _stream()), "ql_bev_densify_ranked")
+    return out
 
 
 def pack_weights(w: torch.Tensor) -> torch.Tensor:

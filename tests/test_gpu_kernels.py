@@ -81,6 +81,48 @@ def test_rulebook_strided_bit_exact(ops, k, s, p):
     assert np.array_equal(tiles_to_nbr(nbr2.cpu().numpy(), n)[0], np.arange(n))
 
 
+@pytest.mark.parametrize("k,s,p,ksub", [(3, 2, 1, 3), (3, 2, (0, 1, 1), 3), ((3, 1, 1), (2, 1, 1), 0, (1, 3, 3)), (5, 2, 2, 5), (3, 2, 1, (3, 1, 1))])
+def test_rank_index_subm_rulebook_and_bev_bit_exact(ops, k, s, p, ksub):
+    """A strided build WITHOUT a hash table (out_table NULL) leaves the stage's rank index (bitmap + prefix) in its
+    workspace; the submanifold rulebook and the BEV hand-off taken through it equal the hash-based ones and the oracle."""
+    rng = np.random.default_rng(31)
+    B, D, H, W = 2, 11, 35, 70
+    coords = random_coords(rng, B, D, H, W, 0.07)
+    oc_ref, osh, nbr_ref = O.rulebook_strided(coords, [D, H, W], k, s, p)
+    n = oc_ref.shape[0]
+    cap = n + 77
+    ws = torch.zeros(ops.rulebook_strided_workspace_bytes((B, D, H, W), k, s, p), dtype=torch.uint8, device="cuda")
+    out_coords = torch.zeros((cap, 4), dtype=torch.int32, device="cuda")
+    n_out = torch.zeros(2, dtype=torch.int32, device="cuda")
+    K = int(np.prod(O._triple(k)))
+    nbr = torch.zeros(((cap + 127) // 128, K, 128), dtype=torch.int32, device="cuda")
+    _, _, tbl, _, ogrid, _ = ops.rulebook_strided(dev(coords), None, (B, D, H, W), k, s, p, cap, out=(out_coords, n_out, None, nbr), workspace=ws)
+    assert tbl is None and n_out.tolist() == [n, n]
+    assert np.array_equal(out_coords[:n].cpu().numpy(), oc_ref)
+    assert np.array_equal(tiles_to_nbr(nbr.cpu().numpy(), n), nbr_ref)
+    index = ops.rulebook_strided_index((B, D, H, W), k, s, p, ws)
+    sub_ref = O.rulebook_subm(oc_ref, osh, ksub)
+    nbr2, kmask2 = ops.rulebook_subm_ranked(out_coords, n_out, ogrid, ksub, index)
+    assert np.array_equal(tiles_to_nbr(nbr2.cpu().numpy(), n), sub_ref)
+    tiles = (n + 127) // 128
+    assert np.array_equal(kmask2[:tiles].cpu().numpy().view(np.uint32), O.tile_kmask(sub_ref))
+    # identical to the hash path
+    table = ops.hash_build(out_coords, n_out, ogrid)
+    nbr3, kmask3 = ops.rulebook_subm(out_coords, n_out, ogrid, ksub, table, with_mask=True)
+    assert torch.equal(nbr2[:tiles], nbr3[:tiles]) and torch.equal(kmask2[:tiles], kmask3[:tiles])
+    # BEV hand-off through the rank index
+    C = 64
+    f = torch.from_numpy(rng.normal(size=(cap, C)).astype(np.float32)).half()
+    ref = O.height_compression(f[:n].float(), oc_ref, osh, B)
+    out = ops.bev_densify_ranked(dev(f), index, n_out, ogrid)
+    assert torch.equal(out.cpu().float(), ref)
+    # a row cap below the number of sites: the dropped (largest-key) sites are absent everywhere
+    n_small = torch.tensor([n - 40, n], dtype=torch.int32, device="cuda")
+    nbr4, _ = ops.rulebook_subm_ranked(out_coords, n_small, ogrid, ksub, index)
+    ref4 = O.rulebook_subm(oc_ref[:n - 40], osh, ksub)
+    assert np.array_equal(tiles_to_nbr(nbr4.cpu().numpy(), n - 40), ref4)
+
+
 def test_rulebook_strided_overflow_is_safe(ops):
     rng = np.random.default_rng(4)
     B, D, H, W = 1, 8, 20, 20
