@@ -110,61 +110,118 @@ __global__ void __launch_bounds__(256) k_fake_quant_per_row(const void* x, int i
     }
 }
 
-// fp32 SIMT stem conv: one thread per output row, C_OUT accumulators in registers, weights in smem.
-template <int C_OUT>
-__global__ void __launch_bounds__(QL_TILE_M) k_stem_conv(const float* __restrict__ feats, int c_in, const int* __restrict__ nbr,
+// fp32 SIMT stem conv.  A warp owns one 128-row rulebook tile and every thread FOUR of its rows (lane, lane+32, lane+64,
+// lane+96), a CTA of 4 warps four tiles.  The first form of this kernel (one row per thread) was bound by the shared-memory
+// pipe: every FMA group re-read its weights, 20 LDS.128 (80 scalar LDS) per kernel offset per warp against 80 FMAs.
+// With 4 rows per thread a weight vector read once feeds 16 FMAs; an offset no row of the warp uses is skipped, a row that
+// lacks it accumulates x = 0 (exact: fmaf(0, w, acc) == acc), so every row keeps the (k, ic) summation order of the
+// reference loop.  kRow8: rows are 8 floats apart and 32-byte aligned (the engine's padded voxel features): one 256-bit
+// load per neighbour instead of C_IN scalar loads.  C_IN == 0: generic width, scalar loads.
+template <int C_OUT, int C_IN, bool kRow8>
+__global__ void __launch_bounds__(QL_TILE_M) k_stem_conv(const float* __restrict__ feats, int fstride, int c_in, const int* __restrict__ nbr,
                                                          int64_t n_cap, const int* __restrict__ n_dev, int kvol,
                                                          const float* __restrict__ w, const float* __restrict__ scale,
                                                          const float* __restrict__ shift, int relu, void* out, int out_dtype,
                                                          float* absmax) {
+    constexpr int R = 4;
+    constexpr int CI = C_IN > 0 ? C_IN : 16;           // register rows sized for the widest generic input
     extern __shared__ float s_w[];                     // [kvol][c_in][C_OUT] then uint32 absmax[C_OUT]
     uint32_t* s_absmax = reinterpret_cast<uint32_t*>(s_w + kvol * c_in * C_OUT);
     const int64_t n = n_dev ? (int64_t)*n_dev : n_cap;
-    const int64_t tile = blockIdx.x;
-    if (tile * QL_TILE_M >= n) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * 4 + warp;
+    if ((int64_t)blockIdx.x * 4 * QL_TILE_M >= n) return;             // whole CTA past the device-side row count
     for (int i = threadIdx.x; i < kvol * c_in * C_OUT; i += blockDim.x) s_w[i] = w[i];
     if (threadIdx.x < C_OUT) s_absmax[threadIdx.x] = 0u;
     __syncthreads();
-    const int r = threadIdx.x;
-    const int64_t row = tile * QL_TILE_M + r;
-    float acc[C_OUT];
+    const bool tile_live = tile * QL_TILE_M < n;
+    float acc[R][C_OUT];
 #pragma unroll
-    for (int j = 0; j < C_OUT; ++j) acc[j] = 0.f;
-    const int* nb = nbr + tile * (int64_t)kvol * QL_TILE_M + r;
-    for (int k = 0; k < kvol; ++k) {
-        const int idx = nb[k * QL_TILE_M];
-        if (idx < 0) continue;
-        const float* xr = feats + (int64_t)idx * c_in;
-        const float* wk = s_w + k * c_in * C_OUT;
-        for (int ic = 0; ic < c_in; ++ic) {
-            const float xv = xr[ic];
+    for (int j = 0; j < R; ++j)
 #pragma unroll
-            for (int j = 0; j < C_OUT; ++j) acc[j] = fmaf(xv, wk[ic * C_OUT + j], acc[j]);
+        for (int c = 0; c < C_OUT; ++c) acc[j][c] = 0.f;
+    if (tile_live) {
+        const int* nb = nbr + tile * (int64_t)kvol * QL_TILE_M + lane;
+        int idx_next[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) idx_next[j] = __ldg(nb + j * 32);
+        for (int k = 0; k < kvol; ++k) {
+            int idx[R];
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                idx[j] = idx_next[j];
+                any |= idx[j] >= 0;
+            }
+            if (k + 1 < kvol) {
+#pragma unroll
+                for (int j = 0; j < R; ++j) idx_next[j] = __ldg(nb + (k + 1) * QL_TILE_M + j * 32);
+            }
+            if (!__any_sync(0xffffffffu, any)) continue;
+            float x[R][kRow8 ? 8 : CI];
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                if constexpr (kRow8) {
+                    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+                    if (idx[j] >= 0) {
+                        asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                     : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+                                     : "l"(feats + (int64_t)idx[j] * 8));
+                    }
+                    x[j][0] = lo.x; x[j][1] = lo.y; x[j][2] = lo.z; x[j][3] = lo.w;
+                    x[j][4] = hi.x; x[j][5] = hi.y; x[j][6] = hi.z; x[j][7] = hi.w;
+                } else {
+#pragma unroll
+                    for (int ic = 0; ic < CI; ++ic)
+                        x[j][ic] = (idx[j] >= 0 && ic < c_in) ? __ldg(feats + (int64_t)idx[j] * fstride + ic) : 0.f;
+                }
+            }
+            const float4* wk = reinterpret_cast<const float4*>(s_w + k * c_in * C_OUT);
+#pragma unroll
+            for (int ic = 0; ic < CI; ++ic) {
+                if (C_IN == 0 && ic >= c_in) break;
+#pragma unroll
+                for (int c4 = 0; c4 < C_OUT / 4; ++c4) {
+                    const float4 wv = wk[ic * (C_OUT / 4) + c4];
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        const float xv = x[j][ic];
+                        acc[j][4 * c4] = fmaf(xv, wv.x, acc[j][4 * c4]);
+                        acc[j][4 * c4 + 1] = fmaf(xv, wv.y, acc[j][4 * c4 + 1]);
+                        acc[j][4 * c4 + 2] = fmaf(xv, wv.z, acc[j][4 * c4 + 2]);
+                        acc[j][4 * c4 + 3] = fmaf(xv, wv.w, acc[j][4 * c4 + 3]);
+                    }
+                }
+            }
         }
-    }
-    if (row < n) {
 #pragma unroll
-        for (int j = 0; j < C_OUT; ++j) {
-            float y = fmaf(acc[j], scale[j], shift[j]);
-            if (relu) y = fmaxf(y, 0.f);
-            acc[j] = y;
-        }
-        if (out_dtype == QL_F16) {
-            __half2* o = reinterpret_cast<__half2*>(reinterpret_cast<__half*>(out) + row * C_OUT);
+        for (int j = 0; j < R; ++j) {
+            const int64_t row = tile * QL_TILE_M + j * 32 + lane;
+            const bool row_ok = row < n;
 #pragma unroll
-            for (int j = 0; j < C_OUT / 2; ++j) o[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
-        } else {
-            float* o = reinterpret_cast<float*>(out) + row * C_OUT;
+            for (int c = 0; c < C_OUT; ++c) {
+                float y = fmaf(acc[j][c], scale[c], shift[c]);
+                if (relu) y = fmaxf(y, 0.f);
+                acc[j][c] = y;
+            }
+            if (row_ok) {
+                if (out_dtype == QL_F16) {
+                    __half2* o = reinterpret_cast<__half2*>(reinterpret_cast<__half*>(out) + row * C_OUT);
 #pragma unroll
-            for (int j = 0; j < C_OUT; ++j) o[j] = acc[j];
-        }
-    }
-    if (absmax) {
-        const int lane = threadIdx.x & 31;
+                    for (int c = 0; c < C_OUT / 2; ++c) o[c] = __floats2half2_rn(acc[j][2 * c], acc[j][2 * c + 1]);
+                } else {
+                    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row * C_OUT);
 #pragma unroll
-        for (int j = 0; j < C_OUT; ++j) {
-            const uint32_t m = __reduce_max_sync(0xffffffffu, row < n ? __float_as_uint(fabsf(acc[j])) : 0u);
-            if (lane == (j & 31)) atomicMax(&s_absmax[j], m);
+                    for (int c = 0; c < C_OUT / 4; ++c) o[c] = make_float4(acc[j][4 * c], acc[j][4 * c + 1], acc[j][4 * c + 2], acc[j][4 * c + 3]);
+                }
+            }
+            if (absmax) {
+#pragma unroll
+                for (int c = 0; c < C_OUT; ++c) {
+                    const uint32_t m = __reduce_max_sync(0xffffffffu, row_ok ? __float_as_uint(fabsf(acc[j][c])) : 0u);
+                    if (lane == (c & 31)) atomicMax(&s_absmax[c], m);
+                }
+            }
         }
     }
     if (absmax) {
@@ -178,7 +235,7 @@ thread_local char g_last_cuda_error[256] = "";
 
 }  // namespace
 
-extern "C" int ql_abi_version(void) { return 1; }
+extern "C" int ql_abi_version(void) { return 2; }
 
 extern "C" const char* ql_error_string(int code) {
     switch (code) {
@@ -233,29 +290,42 @@ extern "C" int ql_quantize_rows(const void* x, int32_t in_dtype, int64_t n_cap, 
     return QL_OK;
 }
 
-extern "C" int ql_stem_conv(const float* feats, int32_t c_in, const int32_t* nbr, int64_t n_out_cap, const int32_t* n_out_dev,
+extern "C" int ql_stem_conv(const float* feats, int32_t feat_stride, int32_t c_in, const int32_t* nbr, int64_t n_out_cap, const int32_t* n_out_dev,
                             int32_t c_out, int32_t kvol, const float* w, const float* scale, const float* shift, int32_t relu,
                             void* out, int32_t out_dtype, float* absmax, ql_stream_t stream_) {
     if (!feats || !nbr || !w || !scale || !shift || !out) return QL_ERR_INVALID;
-    if (c_in <= 0 || c_in > 16 || kvol <= 0 || kvol > 343 || (out_dtype != QL_F16 && out_dtype != QL_F32)) return QL_ERR_INVALID;
+    if (c_in <= 0 || c_in > 16 || feat_stride < c_in || kvol <= 0 || kvol > 343 || (out_dtype != QL_F16 && out_dtype != QL_F32))
+        return QL_ERR_INVALID;
+    const bool row8 = feat_stride == 8 && ((uintptr_t)feats & 31) == 0;
     if (c_out != 16 && c_out != 32) return QL_ERR_UNSUPPORTED;
     if (n_out_cap <= 0) return QL_OK;
-    unsigned tiles = (unsigned)((n_out_cap + QL_TILE_M - 1) / QL_TILE_M);
+    unsigned tiles = (unsigned)((n_out_cap + 4 * QL_TILE_M - 1) / (4 * QL_TILE_M));       // 4 rulebook tiles per CTA
     size_t smem = (size_t)kvol * c_in * c_out * 4 + (size_t)c_out * 4;
     cudaStream_t st = (cudaStream_t)stream_;
+#define QL_STEM_LAUNCH(CO, CI, R8)                                                                                                 \
+    do {                                                                                                                           \
+        if (smem > 48 * 1024 &&                                                                                                    \
+            cudaFuncSetAttribute(k_stem_conv<CO, CI, R8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)  \
+            return QL_ERR_CUDA;                                                                                                    \
+        k_stem_conv<CO, CI, R8><<<tiles, QL_TILE_M, smem, st>>>(feats, feat_stride, c_in, nbr, n_out_cap, n_out_dev, kvol, w, scale, \
+                                                                shift, relu, out, out_dtype, absmax);                              \
+    } while (0)
+#define QL_STEM_CI(CO, CI)                     \
+    do {                                       \
+        if (row8) QL_STEM_LAUNCH(CO, CI, true); \
+        else QL_STEM_LAUNCH(CO, CI, false);    \
+    } while (0)
     if (c_out == 16) {
-        if (smem > 48 * 1024 &&
-            cudaFuncSetAttribute(k_stem_conv<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return QL_ERR_CUDA;
-        k_stem_conv<16><<<tiles, QL_TILE_M, smem, st>>>(feats, c_in, nbr, n_out_cap, n_out_dev, kvol, w, scale, shift, relu, out,
-                                                       out_dtype, absmax);
+        if (c_in == 5) QL_STEM_CI(16, 5);
+        else if (c_in == 4) QL_STEM_CI(16, 4);
+        else QL_STEM_LAUNCH(16, 0, false);
     } else {
-        if (smem > 48 * 1024 &&
-            cudaFuncSetAttribute(k_stem_conv<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return QL_ERR_CUDA;
-        k_stem_conv<32><<<tiles, QL_TILE_M, smem, st>>>(feats, c_in, nbr, n_out_cap, n_out_dev, kvol, w, scale, shift, relu, out,
-                                                       out_dtype, absmax);
+        if (c_in == 5) QL_STEM_CI(32, 5);
+        else if (c_in == 4) QL_STEM_CI(32, 4);
+        else QL_STEM_LAUNCH(32, 0, false);
     }
+#undef QL_STEM_CI
+#undef QL_STEM_LAUNCH
     QL_CUDA_CHECK_LAST();
     return QL_OK;
 }

@@ -35,20 +35,31 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int& total) {
     return base + inc - v;
 }
 
-// single CTA: exclusive scan of block_counts[0..nb) in place, total -> *n_total, min(total, cap) -> *n_out
+// single CTA: exclusive scan of block_counts[0..nb) in place, total -> *n_total, min(total, cap) -> *n_out.
+// 8 consecutive counts per thread per pass (2048 per pass): the strided rulebook of the finest stage scans ~6 k counts.
 __global__ void k_scan_blocks(int* block_counts, int nb, int* n_total, int* n_out, int64_t cap) {
+    constexpr int kPer = 8;
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < nb; base += kScanThreads) {
-        int i = base + threadIdx.x;
-        int v = i < nb ? block_counts[i] : 0;
+    for (int base = 0; base < nb; base += kScanThreads * kPer) {
+        const int i0 = base + threadIdx.x * kPer;
+        int v[kPer];
+        int sum = 0;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            v[j] = i0 + j < nb ? block_counts[i0 + j] : 0;
+            sum += v[j];
+        }
         int total;
-        int ex = block_exclusive_scan(v, total);
-        int c = carry;
-        if (i < nb) block_counts[i] = c + ex;
+        int run = block_exclusive_scan(sum, total) + carry;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            if (i0 + j < nb) block_counts[i0 + j] = run;
+            run += v[j];
+        }
         __syncthreads();
-        if (threadIdx.x == 0) carry = c + total;
+        if (threadIdx.x == 0) carry += total;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
@@ -56,6 +67,5 @@ __global__ void k_scan_blocks(int* block_counts, int nb, int* n_total, int* n_ou
         if (n_out) *n_out = (int)((int64_t)carry < cap ? (int64_t)carry : cap);
     }
 }
-
 
 }  // namespace

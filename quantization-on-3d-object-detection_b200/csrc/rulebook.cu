@@ -155,23 +155,28 @@ constexpr int kWordsPerBlock = QL_SCAN_THREADS;                      // one bitm
 
 // calls f(k, out_key) for every kernel offset k through which input coord c feeds an in-range output site:
 // out = (c + pad - k) / stride, exact division (so that in = out*stride - pad + k)
+// exact division by the stride: strides 1 and 2 (every conv of the backbones) avoid the integer-division sequence
+__device__ __forceinline__ bool div_exact(int n, int s, int& q) {
+    if (s == 1) { q = n; return true; }
+    if (s == 2) { q = n >> 1; return !(n & 1); }
+    q = n / s;
+    return q * s == n;
+}
+
 template <class F>
 __device__ __forceinline__ void for_each_candidate(const int4& c, const ConvGeom& cg, const QlGrid& gout, F&& f) {
     for (int kz = 0; kz < cg.kd; ++kz) {
         const int nz = c.y + cg.pd - kz;
-        if (nz < 0 || nz % cg.sd) continue;
-        const int oz = nz / cg.sd;
-        if (oz >= gout.D) continue;
+        int oz;
+        if (nz < 0 || !div_exact(nz, cg.sd, oz) || oz >= gout.D) continue;
         for (int ky = 0; ky < cg.kh; ++ky) {
             const int ny = c.z + cg.ph - ky;
-            if (ny < 0 || ny % cg.sh) continue;
-            const int oy = ny / cg.sh;
-            if (oy >= gout.H) continue;
+            int oy;
+            if (ny < 0 || !div_exact(ny, cg.sh, oy) || oy >= gout.H) continue;
             for (int kx = 0; kx < cg.kw; ++kx) {
                 const int nx = c.w + cg.pw - kx;
-                if (nx < 0 || nx % cg.sw) continue;
-                const int ox = nx / cg.sw;
-                if (ox >= gout.W) continue;
+                int ox;
+                if (nx < 0 || !div_exact(nx, cg.sw, ox) || ox >= gout.W) continue;
                 f((kz * cg.kh + ky) * cg.kw + kx, ql_key(gout, c.x, oz, oy, ox));
             }
         }

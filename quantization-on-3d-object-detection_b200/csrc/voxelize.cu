@@ -30,6 +30,7 @@ struct VoxParams {
     QlGrid grid;                                // B, D=gz (caller's sparse_shape may be gz+1; key uses gz... see host)
     int max_pts;
     int64_t max_voxels;
+    int out_stride;                             // floats per out_feats row (>= n_feat; the pad columns are written as zeros)
 };
 
 __device__ __forceinline__ bool point_cell(const VoxParams& P, int64_t p, int& b, int& cz, int& cy, int& cx) {
@@ -149,13 +150,14 @@ __global__ void k_vox_finalize(VoxParams P, uint2* table, const uint32_t* pt_slo
         float d = (float)(n > 0 ? n : 1);
 #pragma unroll
         for (int f = 0; f < 16; ++f)
-            if (f < P.n_feat) out_feats[(int64_t)vid * P.n_feat + f] = __fdiv_rn(acc[f], d);
+            if (f < P.n_feat) out_feats[(int64_t)vid * P.out_stride + f] = __fdiv_rn(acc[f], d);
     } else {
         n = cnt[vid];
         float d = (float)(n > 0 ? n : 1);
         for (int f = 0; f < P.n_feat; ++f)
-            out_feats[(int64_t)vid * P.n_feat + f] = __fdiv_rn(sums[(int64_t)vid * P.n_feat + f], d);
+            out_feats[(int64_t)vid * P.out_stride + f] = __fdiv_rn(sums[(int64_t)vid * P.n_feat + f], d);
     }
+    for (int f = P.n_feat; f < P.out_stride; ++f) out_feats[(int64_t)vid * P.out_stride + f] = 0.f;
     out_npts[vid] = n;
     table[pt_slot[vox_first[vid]]].y = (uint32_t)vid;          // coords -> row for the stage-1 rulebook
 }
@@ -240,14 +242,14 @@ extern "C" size_t ql_voxelize_workspace_bytes(int64_t max_points, int64_t max_vo
 extern "C" int ql_voxelize_mean(const float* points, int64_t n_points, int32_t point_stride, int32_t has_batch_col,
                                 int32_t n_feat, const float* range_min, const float* vsize, const int32_t* grid_xyz,
                                 int32_t batch_size, int32_t max_pts, int64_t max_voxels, float* out_feats,
-                                int32_t* out_coords, int32_t* out_npts, int32_t* n_voxels_dev, uint64_t* table,
+                                int32_t out_feat_stride, int32_t* out_coords, int32_t* out_npts, int32_t* n_voxels_dev, uint64_t* table,
                                 int64_t table_cap, void* workspace, size_t workspace_bytes, ql_stream_t stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (!points || !range_min || !vsize || !grid_xyz || !out_feats || !out_coords || !out_npts || !n_voxels_dev || !table ||
         !workspace)
         return QL_ERR_INVALID;
     if (n_feat < 3 || n_feat > 16 || point_stride < n_feat + (has_batch_col ? 1 : 0) || max_pts < 0 || max_voxels <= 0 ||
-        batch_size <= 0 || n_points < 0 || n_points >= 2147483647LL)
+        batch_size <= 0 || n_points < 0 || n_points >= 2147483647LL || out_feat_stride < n_feat)
         return QL_ERR_INVALID;
     if (table_cap <= 0 || (table_cap & (table_cap - 1)) || table_cap < 2 * (n_points < max_voxels ? n_points : n_points))
         return QL_ERR_INVALID;  // the table must hold every distinct cell the points touch (<= n_points)
@@ -260,6 +262,7 @@ extern "C" int ql_voxelize_mean(const float* points, int64_t n_points, int32_t p
 
     VoxParams P;
     P.points = points; P.n_points = n_points; P.stride = point_stride; P.has_b = has_batch_col; P.n_feat = n_feat;
+    P.out_stride = out_feat_stride;
     P.mnx = range_min[0]; P.mny = range_min[1]; P.mnz = range_min[2];
     P.vsx = vsize[0]; P.vsy = vsize[1]; P.vsz = vsize[2];
     P.gx = grid_xyz[0]; P.gy = grid_xyz[1]; P.gz = grid_xyz[2];

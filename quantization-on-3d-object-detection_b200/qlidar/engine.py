@@ -200,7 +200,8 @@ class BackboneEngine:
         s0 = self.stages[0]
         s0.coords = z(s0.cap, 4, dt=torch.int32)
         s0.n_dev = z(2, dt=torch.int32)
-        self.vox_feats = z(s0.cap, self.nfeat, dt=torch.float32)
+        # rows padded to 8 floats (32 bytes): the stem conv fetches a neighbour row with one 256-bit load
+        self.vox_feats = z(s0.cap, 8 if self.nfeat <= 8 else self.nfeat, dt=torch.float32)
         self.vox_npts = z(s0.cap, dt=torch.int32)
         if self.max_points is not None:
             self.points = torch.full((self.max_points, 1 + self.nfeat), 1e30, dtype=torch.float32, device=dev)
@@ -355,7 +356,7 @@ class BackboneEngine:
         V = voxel_features.shape[0]
         if V > s0.cap:
             raise QlidarError("more voxels than the engine capacity")
-        self.vox_feats[:V].copy_(voxel_features)
+        self.vox_feats[:V, :voxel_features.shape[1]].copy_(voxel_features)
         s0.coords[:V].copy_(voxel_coords.int() if voxel_coords.dtype != torch.int32 else voxel_coords)
         s0.n_dev.fill_(V)
         ops.hash_build(s0.coords, s0.n_dev, s0.grid, table=s0.table)

@@ -73,7 +73,8 @@ def hash_build(coords: torch.Tensor, n_dev: Optional[torch.Tensor], grid: Sequen
 def voxelize_mean(points: torch.Tensor, pc_range, voxel_size, grid_xyz, batch_size: int, max_pts: int, max_voxels: int,
                   has_batch_col: bool = True, n_feat: Optional[int] = None, out=None, workspace=None):
     """Fused hard voxelization + mean VFE (+ DynamicMeanVFE semantics when max_pts == 0).
-    Returns (feats [max_voxels,F] f32, coords [max_voxels,4] i32, npts [max_voxels] i32, n_dev [2] i32 = (kept, found), table)."""
+    Returns (feats [max_voxels,F] f32, coords [max_voxels,4] i32, npts [max_voxels] i32, n_dev [2] i32 = (kept, found), table).
+    A caller-provided feats buffer may be wider than F (row stride = its second dimension, pad columns written as zeros)."""
     _need_cuda(points)
     if points.dtype != torch.float32 or points.dim() != 2:
         raise QlidarError("points must be a float32 (P, stride) tensor")
@@ -95,7 +96,7 @@ def voxelize_mean(points: torch.Tensor, pc_range, voxel_size, grid_xyz, batch_si
     vs = (C.c_float * 3)(*[float(v) for v in voxel_size])
     g = (C.c_int32 * 3)(*[int(v) for v in grid_xyz])
     check(lib().ql_voxelize_mean(_ptr(points), P, stride, 1 if has_batch_col else 0, F, rmin, vs, g, int(batch_size), int(max_pts),
-                                 int(max_voxels), _ptr(feats), _ptr(coords), _ptr(npts), _ptr(n_dev), _ptr(table), table.numel(),
+                                 int(max_voxels), _ptr(feats), int(feats.shape[1]), _ptr(coords), _ptr(npts), _ptr(n_dev), _ptr(table), table.numel(),
                                  _ptr(workspace), workspace.numel(), _stream()), "ql_voxelize_mean")
     return feats, coords, npts, n_dev, table
 
@@ -266,14 +267,16 @@ def spconv_mma(feats: torch.Tensor, nbr: torch.Tensor, n_out_cap: int, n_out_dev
 def stem_conv(feats: torch.Tensor, nbr: torch.Tensor, n_out_cap: int, n_out_dev: Optional[torch.Tensor], w_kio: torch.Tensor,
               scale: torch.Tensor, shift: torch.Tensor, relu: bool = True, out: Optional[torch.Tensor] = None,
               out_dtype: torch.dtype = torch.float16, absmax: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """w_kio: (K, c_in, c_out) fp32."""
+    """w_kio: (K, c_in, c_out) fp32; feats (N, stride >= c_in) fp32 (stride 8 = the engine's padded rows, one 256-bit load each)."""
     _need_cuda(feats, nbr, n_out_dev, w_kio, scale, shift, out, absmax)
     if feats.dtype != torch.float32 or w_kio.dtype != torch.float32:
         raise QlidarError("stem_conv is the fp32 path")
     K, c_in, c_out = w_kio.shape
+    if feats.shape[1] < c_in:
+        raise QlidarError("stem_conv: feature rows narrower than c_in")
     if out is None:
         out = torch.empty((n_out_cap, c_out), dtype=out_dtype, device=feats.device)
-    check(lib().ql_stem_conv(_ptr(feats), c_in, _ptr(nbr), int(n_out_cap), _ptr(n_out_dev), c_out, K, _ptr(w_kio), _ptr(scale), _ptr(shift),
+    check(lib().ql_stem_conv(_ptr(feats), int(feats.shape[1]), c_in, _ptr(nbr), int(n_out_cap), _ptr(n_out_dev), c_out, K, _ptr(w_kio), _ptr(scale), _ptr(shift),
                              1 if relu else 0, _ptr(out), _DT[out.dtype], _ptr(absmax), _stream()), "ql_stem_conv")
     return out
 

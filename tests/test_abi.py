@@ -32,7 +32,7 @@ def test_header_symbols_are_exported_and_bound():
 def test_host_only_entry_points():
     from qlidar import _lib
     lib = _lib.lib()
-    assert lib.ql_abi_version() == 1
+    assert lib.ql_abi_version() == 2
     assert lib.ql_error_string(0) == b"ok"
     assert b"workspace" in lib.ql_error_string(-4)
     assert lib.ql_hash_capacity(1000) == 2048

@@ -158,6 +158,21 @@ def test_voxelize_hard_matches_cpu_voxelizer(ops, cfg, batch):
     assert np.array_equal(tiles_to_nbr(nbr.cpu().numpy(), n)[0], np.arange(n))
 
 
+def test_voxelize_padded_feature_rows(ops):
+    """out_feats wider than n_feat: same means in the first columns, zeros in the pad (the engine uses a stride of 8)."""
+    c = O.CONFIGS["waymo"]
+    pts = O.synth_batch("waymo", 1, n_beams=16, n_az=400)
+    grid = O.grid_size_xyz(c["pc_range"], c["voxel_size"])
+    f0, c0, n0, nd0, _ = ops.voxelize_mean(dev(pts), c["pc_range"], c["voxel_size"], grid, 1, c["max_pts"], 20000)
+    n = int(nd0[0].item())
+    out = (torch.full((20000, 8), 7.0, device="cuda"), torch.zeros((20000, 4), dtype=torch.int32, device="cuda"),
+           torch.zeros(20000, dtype=torch.int32, device="cuda"), torch.zeros(2, dtype=torch.int32, device="cuda"),
+           torch.empty(ops.hash_capacity(pts.shape[0]), dtype=torch.int64, device="cuda"))
+    f1, c1, n1, nd1, _ = ops.voxelize_mean(dev(pts), c["pc_range"], c["voxel_size"], grid, 1, c["max_pts"], 20000, out=out)
+    assert int(nd1[0].item()) == n and torch.equal(c1[:n], c0[:n])
+    assert torch.equal(f1[:n, :5], f0[:n]) and (f1[:n, 5:] == 0).all()
+
+
 def test_voxelize_voxel_cap(ops):
     c = O.CONFIGS["kitti"]
     pts = O.synth_batch("kitti", 1, n_az=400)
@@ -335,6 +350,19 @@ def test_stem_conv(ops):
                         out_dtype=torch.float32, absmax=absmax)
     assert (out.cpu().double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
     np.testing.assert_allclose(absmax.cpu().numpy(), ref.abs().amax(dim=0).numpy(), rtol=1e-5)
+    # rows padded to 8 floats (the engine's voxel-feature layout): the 256-bit-load form gives the same bits
+    x8 = torch.zeros((N, 8))
+    x8[:, :5] = x
+    out8 = ops.stem_conv(dev(x8), dev(nbr_to_tiles(nbr)), N, None, dev(w_kio), dev(scale), dev(shift), relu=True, out_dtype=torch.float32)
+    assert torch.equal(out8, out)
+    # 4 raw features (KITTI) and a width the specialised kernels do not cover
+    for cin in (4, 7):
+        xc = torch.from_numpy(rng.normal(size=(N, cin)).astype(np.float32))
+        wc = torch.from_numpy(rng.normal(size=(16, 3, 3, 3, cin)).astype(np.float32))
+        refc = torch.relu(O.sparse_conv(xc.double(), nbr, wc.double()) * scale.double() + shift.double())
+        outc = ops.stem_conv(dev(xc), dev(nbr_to_tiles(nbr)), N, None, dev(wc.reshape(16, 27, cin).permute(1, 2, 0).contiguous()),
+                             dev(scale), dev(shift), relu=True, out_dtype=torch.float32)
+        assert (outc.cpu().double() - refc).abs().max().item() <= 1e-5 * refc.abs().max().item()
 
 
 # ------------------------------------------------------------------------------------------------ quantizer
