@@ -137,6 +137,108 @@ class GQConv3d(QConvNd):
         self.n = n
 
 
+class SQConv3d(SparseModule):
+    """SmoothQuant for the sparse 3-D convs: W8A8 with the per-input-channel smoothing scale folded into the activation
+    quantiser (the gather then reads int8 codes) and into the weights.
+
+    Mirrors the two SQConv3d classes of the reference:
+      * SQConv3d(spconv3d)                      quant/collect_act_conv3d.py:68-110, the only functional one: a SCALAR
+        s = sqrt(max|x| / max|w|), x /= s, w *= s, per-tensor act / per-oc weight fake-quant.  A scalar cancels in both
+        quantisers, so the int8 codes -- and this module's output -- equal QConvNd(8, 8, cw=False) (W8A8-pt).
+      * SQConv3d(spconv3d, scaling_factor=a)    quant/quant_conv3d.py:141-236 (non-functional as shipped: dense unfold on
+        the CPU with prints): its intent with the quant/smoothquant.py:72-79 formula, per input channel,
+        s[ic] = amax_x[ic]^a / (max_{oc,k} |w[oc,k,ic]|)^(1-a), zeros -> 1; x' = x / s, w' = w * s; W8A8-pt on (x', w').
+    act_amax: optional calibrated per-channel |x| maxima (static SmoothQuant; weights are then prepared once).  Without it
+    the maxima are taken from the incoming features on every call and the smoothed weights are re-quantised and
+    re-packed per call (a host round trip: the eager module path, not the engine)."""
+
+    def __init__(self, spconv3d: SparseConvolution = None, scaling_factor: Optional[float] = None, module: SparseConvolution = None,
+                 w_bits: int = 8, act_bits: int = 8, act_amax: Optional[torch.Tensor] = None):
+        super().__init__()
+        self.spconv3d = spconv3d if spconv3d is not None else module
+        if self.spconv3d is None:
+            raise ValueError("SQConv3d needs the conv to wrap")
+        if act_bits > 8 or w_bits > 8:
+            raise ValueError("SQConv3d is the W8A8 integer path")
+        self.scaling_factor = scaling_factor
+        self.w_quant = TensorQuantizer(QuantDescriptor(num_bits=w_bits, axis=(0)))
+        self.act_quant = TensorQuantizer(QuantDescriptor(num_bits=act_bits))
+        self.original_weight = self.spconv3d.weight.data.clone()
+        self.act_amax = None if act_amax is None else act_amax.detach().float().reshape(-1).clone()
+        self._cache = None
+
+    def smoothing_scale(self, amax_ic: torch.Tensor) -> Optional[torch.Tensor]:
+        """fp32 on the host, the oracle's arithmetic (oracle smoothquant_scale), so that codes are reproducible bit for bit."""
+        if self.scaling_factor is None:
+            return None
+        a = float(self.scaling_factor)
+        w = self.spconv3d.weight.detach().float().cpu()
+        w_ic = w.abs().amax(dim=tuple(range(w.dim() - 1)))
+        s = amax_ic.float().cpu().view(-1) ** a / w_ic ** (1.0 - a)
+        return torch.where((s == 0) | ~torch.isfinite(s), torch.ones_like(s), s)
+
+    def _prepare(self, dev, s: Optional[torch.Tensor]):
+        conv = self.spconv3d
+        wt = conv.weight.detach().float().cpu()
+        if s is not None:
+            wt = wt * s.view(*([1] * (wt.dim() - 1)), -1)
+        oc, ic = wt.shape[0], wt.shape[-1]
+        wm = wt.reshape(oc, -1, ic)
+        bound = float(2 ** (self.w_quant.num_bits - 1) - 1)
+        amax = wm.abs().amax(dim=(1, 2))
+        tiny = amax <= (1.0 / (1 << 24))
+        scale = torch.where(tiny, torch.zeros_like(amax), bound / torch.where(tiny, torch.ones_like(amax), amax))
+        codes = torch.round(wm * scale.view(-1, 1, 1)).clamp_(-bound, bound)
+        ic_p, oc_p = _round_up(ic, 16), _round_up(oc, 16)
+        w8 = torch.zeros((oc_p, wm.shape[1], ic_p), dtype=torch.int8)
+        w8[:oc, :, :ic] = codes.to(torch.int8)
+        packed = ops.pack_weights(w8).to(dev)
+        w_scale = torch.zeros(oc_p, dtype=torch.float32, device=dev)
+        w_scale[:oc] = (amax / bound).to(dev)
+        shift = torch.zeros(oc_p, dtype=torch.float32, device=dev)
+        if conv.bias is not None:
+            shift[:oc] = conv.bias.detach().float().to(dev)
+        return packed, ic_p, oc_p, w_scale, shift
+
+    def forward(self, x: SparseConvTensor) -> SparseConvTensor:
+        conv = self.spconv3d
+        rb = conv.get_rulebook(x)
+        f = x.features
+        in_dtype = f.dtype
+        f = (f if f.dtype in (torch.float16, torch.float32) else f.float()).contiguous()
+        n_dev = x._n_dev
+        static = self.act_amax is not None
+        amax_ic = self.act_amax.to(f.device) if static else ops.absmax_cols(f, n_dev)
+        if static and self._cache is not None:
+            s_dev, prep = self._cache
+        else:
+            s = self.smoothing_scale(amax_ic)
+            s_dev = None if s is None else s.to(f.device).contiguous()
+            prep = self._prepare(f.device, s)
+            if static:
+                self._cache = (s_dev, prep)
+        packed, ic_p, oc_p, w_scale, shift = prep
+        q, act_scale = ops.quantize_rows(f, amax_ic.contiguous(), ops.QL_Q_CODES_PER_TENSOR, self.act_quant.num_bits, n_dev, smooth=s_dev)
+        if ic_p != conv.in_channels:
+            q = torch.nn.functional.pad(q, (0, ic_p - conv.in_channels)).contiguous()
+        out_dtype = torch.float32 if in_dtype == torch.float32 else torch.float16
+        y = ops.spconv_mma(q, rb.nbr, rb.n_out, rb.n_out_dev, oc_p, packed, w_scale, shift, act_scale=act_scale, out_dtype=out_dtype, kmask=rb.kmask)
+        if oc_p != conv.out_channels:
+            y = y[:, :conv.out_channels].contiguous()
+        return _make_output(x, rb, y, conv.ndim)
+
+
+def sq_conv3d(model, module_dict, curr_path, alpha, w_bits, act_bits, src, no_list) -> None:
+    """Surgery for the 3-D SmoothQuant wrapper, the walk of quant/quantize.py:46-77 (`smoothquant`) applied to the sparse
+    convs the way quant/quant_conv3d.py:286-292 / quant_second.py:84 intend: swap `src` instances not in no_list."""
+    for name, module in model.named_children():
+        path = f"{curr_path}.{name}" if curr_path else name
+        sq_conv3d(module, module_dict, path, alpha, w_bits, act_bits, src, no_list)
+        if isinstance(module, src) and path not in no_list:
+            model._modules[name] = SQConv3d(spconv3d=module, scaling_factor=alpha, w_bits=w_bits, act_bits=act_bits)
+    return
+
+
 def q_conv3d(model, module_dict, curr_path, w_bits, act_bits, cw, src, no_list) -> None:
     """quant/quantize.py:13-43: recursive named_children walk; swap `src` instances whose dotted path is not in no_list."""
     for name, module in model.named_children():

@@ -34,10 +34,10 @@ class SparseConvTensor:
     """features (N, C) + indices (N, 1+ndim) int32 [b, z, y, x] (or [b, y, x] for 2-D)."""
 
     def __init__(self, features: torch.Tensor, indices: torch.Tensor, spatial_shape: Sequence[int], batch_size: int,
-                 grid=None, voxel_num=None, indice_dict: Optional[dict] = None, benchmark: bool = False):
+                 grid=None, voxel_num=None, indice_dict: Optional[dict] = None, benchmark: bool = False, _check: bool = True):
         if indices.dtype != torch.int32:
             raise QlidarError("indices must be int32 (the reference passes voxel_coords.int(), spconv_backbone.py:258)")
-        if features.shape[0] != indices.shape[0]:
+        if _check and features.shape[0] != indices.shape[0]:
             raise QlidarError("features and indices disagree on the number of active sites")
         self.features = features
         self.indices = indices
@@ -65,9 +65,11 @@ class SparseConvTensor:
         return self.indice_dict.get(key)
 
     def replace_feature(self, feature: torch.Tensor) -> "SparseConvTensor":
-        """New tensor sharing indices, the rulebook cache and the hash table (pcdet/utils/spconv_utils.py:32-38)."""
+        """New tensor sharing indices, the rulebook cache and the hash table (pcdet/utils/spconv_utils.py:32-38).
+        Like spconv's, it does not insist that the row counts agree: VoxelNeXt replaces the features with a concatenation
+        first and assigns the matching indices afterwards (spconv_backbone_voxelnext.py:196-197)."""
         t = SparseConvTensor(feature, self.indices, self.spatial_shape, self.batch_size, self.grid, self.voxel_num,
-                             self.indice_dict, self.benchmark)
+                             self.indice_dict, self.benchmark, _check=False)
         t._table, t._table_src, t._n_dev = self._table, self._table_src, self._n_dev
         return t
 

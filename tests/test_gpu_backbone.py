@@ -237,3 +237,122 @@ def test_every_backbone_layer_teacher_forced(w_bits, act_bits, cw):
         e = rel_err(y.features, rec[spec.name])
         worst = max(worst, e)
         assert e <= 2e-3, (spec.name, e)
+
+
+# ------------------------------------------------------------------------------------------------ SmoothQuant (W8A8-sq)
+@pytest.mark.parametrize("alpha", [None, 0.5, 0.8])
+def test_sqconv3d_matches_oracle(alpha):
+    """SQConv3d: alpha=None is the scalar SmoothQuant of quant/collect_act_conv3d.py:68-110 (== W8A8-pt, the scalar cancels);
+    alpha=a the per-input-channel SmoothQuant of SURVEY.md 8a-Q (intent of quant/quant_conv3d.py:141-236 with the
+    quant/smoothquant.py:72-79 formula).  Activations carry x20 outliers in two channels."""
+    import qlidar
+    rng = np.random.default_rng(21)
+    coords = O.synth_surface_sheet(50, seed=15, depth=12)
+    x = torch.from_numpy(rng.normal(size=(coords.shape[0], 64)).astype(np.float32))
+    x[::100, 5] *= 20
+    x[::100, 40] *= 20
+    x = x.half().float()                                               # the features the kernel sees
+    for subm in (True, False):
+        conv = (qlidar.SubMConv3d(64, 64, 3, padding=1, bias=True, indice_key="k") if subm
+                else qlidar.SparseConv3d(64, 32, 3, stride=2, padding=1, bias=False, indice_key="k")).cuda()
+        w = conv.weight.detach().cpu()
+        b = None if conv.bias is None else conv.bias.detach().cpu()
+        if subm:
+            nbr, oc = O.rulebook_subm(coords, [12, 50, 50], 3), coords
+        else:
+            oc, _, nbr = O.rulebook_strided(coords, [12, 50, 50], 3, 2, 1)
+        if alpha is None:
+            _, ref, _, _ = O.qconv_w8a8_pt(x, nbr, w, b)
+        else:
+            _, ref, _, _ = O.qconv_w8a8_sq(x, nbr, w, b, alpha)
+        q = qlidar.SQConv3d(conv) if alpha is None else qlidar.SQConv3d(conv, scaling_factor=alpha)
+        st = qlidar.SparseConvTensor(x.cuda().half(), torch.from_numpy(coords).cuda(), [12, 50, 50], 1)
+        with torch.no_grad():
+            y = q(st)
+        assert np.array_equal(y.indices.cpu().numpy(), oc)
+        # identical int8 codes and INT32 accumulators (s is computed with the oracle's host arithmetic): only the fp16 store differs
+        assert rel_err(y.features, ref) <= 1e-3, (alpha, subm, rel_err(y.features, ref))
+        if alpha is not None:
+            # static SmoothQuant: calibrated per-channel maxima, weights prepared once
+            amax = x.abs().amax(dim=0)
+            qs = qlidar.SQConv3d(conv, scaling_factor=alpha, act_amax=amax)
+            with torch.no_grad():
+                y1, y2 = qs(st), qs(st)
+            assert torch.equal(y1.features, y2.features) and torch.equal(y1.features, y.features)
+
+
+def test_smoothquant_helps_with_channel_outliers():
+    """The point of SmoothQuant: with per-channel outliers the W8A8-sq error against the un-quantised conv is lower than W8A8-pt's."""
+    import qlidar
+    rng = np.random.default_rng(22)
+    coords = O.synth_surface_sheet(50, seed=16, depth=12)
+    x = torch.from_numpy(rng.normal(size=(coords.shape[0], 64)).astype(np.float32))
+    x[:, 5] *= 30
+    x[:, 40] *= 30
+    conv = qlidar.SubMConv3d(64, 64, 3, padding=1, bias=False, indice_key="k").cuda()
+    ref = O.sparse_conv(x, O.rulebook_subm(coords, [12, 50, 50], 3), conv.weight.detach().cpu())
+    st = qlidar.SparseConvTensor(x.cuda().half(), torch.from_numpy(coords).cuda(), [12, 50, 50], 1)
+    with torch.no_grad():
+        e_pt = rel_err(qlidar.QConvNd(conv, 8, 8, False)(st).features, ref)
+        e_sq = rel_err(qlidar.SQConv3d(conv, scaling_factor=0.5)(st).features, ref)
+    assert e_sq < 0.6 * e_pt, (e_sq, e_pt)
+
+
+def test_second_backbone_w8a8_smoothquant_surgery():
+    """BASELINE config 3: SECOND's sparse middle extractor (VoxelBackBone8x, kitti_models/second.yaml:13-14) W8A8 with
+    SmoothQuant on KITTI-shaped frames; sq_conv3d swaps every sparse conv but the stem (quant_second.py no_list)."""
+    import qlidar
+    _, feats, coords, grid, c = make_frame("kitti", batch=2, n_az=260)
+    prog, P, bb = build("VoxelBackBone8x", 4, grid)
+    no_list = ["conv_input.0"]
+    qlidar.sq_conv3d(bb, {}, "", 0.5, 8, 8, (qlidar.SubMConv3d, qlidar.SparseConv3d), no_list)
+    assert sum(isinstance(m, qlidar.SQConv3d) for m in bb.modules()) == len(O.all_conv_specs(prog)) - 1
+    ref, taps = O.backbone_forward(prog, P, feats, coords, O.sparse_shape_zyx(grid), 2,
+                                   O.QuantCfg(mode="w8a8_sq", alpha=0.5, no_list=tuple(no_list)))
+    with torch.no_grad():
+        out = bb(batch_dict(feats, coords, 2))
+    enc = out["encoded_spconv_tensor"]
+    assert np.array_equal(enc.indices.cpu().numpy(), ref.coords)
+    check_feats(enc.features, ref.features, True)
+    for k, t in out["multi_scale_3d_features"].items():
+        assert np.array_equal(t.indices.cpu().numpy(), taps[k].coords)
+
+
+# ------------------------------------------------------------------------------------------------ VoxelNeXt (config 4)
+@pytest.mark.parametrize("quant", [None, (8, 8, False)])
+def test_voxelnext_backbone_module_path(quant):
+    """VoxelResBackBone8xVoxelNeXt (spconv_backbone_voxelnext.py:70-225) with the Waymo-large kernel sizes [5,5,3,3]: six 3-D
+    stages, stage-5/6 indices scaled onto the stage-4 grid, 2-D merge of duplicate (b,y,x) rows, SparseConv2d + SubMConv2d tail."""
+    import qlidar
+    cfg = dict(SPCONV_KERNEL_SIZES=[5, 5, 3, 3], CHANNELS=[16, 32, 64, 128, 128], OUT_CHANNEL=128)
+    c = O.CONFIGS["kitti"]
+    pc_range = [0.0, -12.8, -3.0, 25.6, 12.8, 1.0]                     # 512 x 512 x 40 crop: keeps all six stage shapes non-trivial
+    pts = O.synth_batch("kitti", 2, n_az=500)
+    m = (pts[:, 1] >= 0) & (pts[:, 1] < 25.6) & (pts[:, 2] >= -12.8) & (pts[:, 2] < 12.8)
+    pts = pts[m]
+    feats, coords, _ = O.voxelize_mean_batch(pts, pc_range, c["voxel_size"], c["max_pts"], c["max_voxels"])
+    grid = O.grid_size_xyz(pc_range, c["voxel_size"])
+    prog = O.backbone_specs("VoxelResBackBone8xVoxelNeXt", 4, cfg["CHANNELS"], cfg["SPCONV_KERNEL_SIZES"], cfg["OUT_CHANNEL"])
+    P = O.init_params(prog)
+    bb = qlidar.VoxelResBackBone8xVoxelNeXt(cfg, 4, np.asarray(grid))
+    sd = {k: (v.reshape(v.shape[0], *v.shape[2:]) if k in ("conv_out.0.weight", "shared_conv.0.weight") else v) for k, v in P.items()}
+    missing, unexpected = bb.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.endswith("num_batches_tracked") for k in missing), (missing, unexpected)
+    bb = bb.cuda().eval()
+    qc = O.QuantCfg()
+    if quant is not None:
+        w_bits, act_bits, cw = quant
+        qlidar.q_conv3d(bb, {}, "", w_bits, act_bits, cw, (qlidar.SubMConv3d, qlidar.SparseConv3d), ["conv_input.0"])
+        no_list = ("conv_input.0", "conv_out.0", "shared_conv.0")                      # the 2-D tail is not a 3-D conv: not swapped
+        qc = O.QuantCfg(mode="ref", w_bits=w_bits, act_bits=act_bits, cw=cw, no_list=no_list)
+        assert sum(isinstance(mm, qlidar.QConvNd) for mm in bb.modules()) == 5 * 5 + 4
+    ref, taps = O.backbone_forward(prog, P, torch.from_numpy(feats), coords, O.sparse_shape_zyx(grid), 2, qc)
+    with torch.no_grad():
+        out = bb(batch_dict(torch.from_numpy(feats), coords, 2))
+    enc = out["encoded_spconv_tensor"]
+    got_idx = enc.indices.cpu().numpy()
+    assert np.array_equal(got_idx, ref.coords[:, [0, 2, 3]])                            # 2-D indices [b, y, x], same (sorted) order
+    check_feats(enc.features, ref.features, quant is not None)
+    assert out["encoded_spconv_tensor_stride"] == 8
+    for k in ("x_conv1", "x_conv2", "x_conv3"):
+        assert np.array_equal(out["multi_scale_3d_features"][k].indices.cpu().numpy(), taps[k].coords)
