@@ -261,9 +261,16 @@ def run_ours(args):
     per_layer = [dict(name=n, ms=round(conv_ms[n], 4), gbs=round(acct[n]["bytes_alg"] / (conv_ms[n] / 1e3) / 1e9, 1),
                       tflops=round(acct[n]["flops_alg"] / (conv_ms[n] / 1e3) / 1e12, 2), cin=acct[n]["cin"], cout=acct[n]["cout"],
                       n_out=acct[n]["n_out"], pairs=acct[n]["pairs"]) for n in conv_ms]
-    roofline = {"kernel": "k_spconv_mma<f16> (20 launches/step aggregated)", "bound": "hbm",
+    # measured DRAM traffic of the same 20 launches from the committed ncu capture (profiles/, not measured in this run)
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic, traffic_src = int(tj["traffic_bytes_per_step"]), "profiles/r01_conv_traffic.json (ncu --set full, dram__bytes_read+write over the 20 launches)"
+    roofline = {"kernel": "k_spconv_ts<f16> (the 20 tcgen05 sparse-conv launches of one step, aggregated)", "bound": "hbm",
                 "achieved": round(conv_bytes / conv_t / 1e9, 1), "peak": pk["hbm"], "unit": "GB/s",
-                "frac": round(conv_bytes / conv_t / 1e9 / pk["hbm"], 4), "traffic": None, "peak_source": pk["src"],
+                "frac": round(conv_bytes / conv_t / 1e9 / pk["hbm"], 4), "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": pk["src"],
                 "alg_bytes_per_step": conv_bytes, "kernel_ms_per_step": round(conv_t * 1e3, 3),
                 "share_of_step": round(conv_t * 1e3 / eager_total, 3),
                 "tensor_tflops_alg": round(conv_flops / conv_t / 1e12, 2), "tensor_frac_of_bf16_peak": round(conv_flops / conv_t / 1e12 / pk["bf16"], 4)}

@@ -175,6 +175,16 @@ int ql_bev_densify_ranked(const void* feats, int32_t in_dtype, int32_t c, const 
                           int64_t n_cap, const int32_t* n_dev, int32_t B, int32_t D, int32_t H, int32_t W, void* out,
                           int32_t out_dtype, void* workspace, size_t workspace_bytes, ql_stream_t stream);
 
+/* ---- VoxelNeXt 2-D merge (replaces VoxelResBackBone8xVoxelNeXt.bev_out, spconv_backbone_voxelnext.py:149-164:
+ *      indices[:, [0, 2, 3]] -> torch.unique(dim=0, return_inverse) -> index_add_).  coords: [n, 4] int32 [b, z, y, x] (z is
+ *      dropped; the caller has already scaled the coarser stages onto the target grid, :194-197).  Outputs: out_coords
+ *      [n_out_cap, 3] int32 [b, y, x] in ascending (b, y, x) order, out_feats [n_out_cap, c] (QL_F32 or QL_F16; c % 4 == 0) =
+ *      the sum of the rows that fall on each site (fp32 atomics), n_out_dev int32[2] = {rows kept, sites found}. */
+size_t ql_bev_merge2d_workspace_bytes(int32_t B, int32_t H, int32_t W, int64_t n_out_cap, int32_t c, int32_t out_dtype);
+int ql_bev_merge2d(const void* feats, int32_t in_dtype, int32_t c, const int32_t* coords, int64_t n_cap, const int32_t* n_dev,
+                   int32_t B, int32_t H, int32_t W, void* out_feats, int32_t out_dtype, int32_t* out_coords,
+                   int64_t n_out_cap, int32_t* n_out_dev, void* workspace, size_t workspace_bytes, ql_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,37 @@ __global__ void __launch_bounds__(256) k_absmax_cols(const void* x, int dtype, i
         if (s_max[j]) atomicMax(reinterpret_cast<unsigned int*>(absmax) + j, s_max[j]);
 }
 
+// fp16 rows, c % 8 == 0, 256 % (c / 8) == 0: a thread owns one 8-channel group (one 16-byte load per row) and walks rows
+__global__ void __launch_bounds__(256) k_absmax_cols_h8(const __half* __restrict__ x, int64_t n_cap, const int* __restrict__ n_dev, int c,
+                                                        float* absmax) {
+    extern __shared__ uint32_t s_max[];
+    const int64_t n = n_dev ? (int64_t)*n_dev : n_cap;
+    for (int j = threadIdx.x; j < c; j += blockDim.x) s_max[j] = 0u;
+    __syncthreads();
+    const int groups = c >> 3;
+    const int g = threadIdx.x % groups;
+    const int rows_per_step = 256 / groups;
+    const int64_t stride = (int64_t)gridDim.x * rows_per_step;
+    __half2 m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m[j] = __float2half2_rn(0.f);
+    for (int64_t r = (int64_t)blockIdx.x * rows_per_step + threadIdx.x / groups; r < n; r += stride) {
+        const uint4 v = *reinterpret_cast<const uint4*>(x + r * c + g * 8);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], __habs2(h[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(m[j]);
+        atomicMax(&s_max[g * 8 + 2 * j], __float_as_uint(f.x));
+        atomicMax(&s_max[g * 8 + 2 * j + 1], __float_as_uint(f.y));
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < c; j += blockDim.x)
+        if (s_max[j]) atomicMax(reinterpret_cast<unsigned int*>(absmax) + j, s_max[j]);
+}
+
 __device__ __forceinline__ float quant_scale_of(float amax, float bound) {
     // scale = bound / amax; amax <= 2^-24 -> 0 ([EXT] fake_tensor_quant epsilon rule)
     return amax <= (1.0f / 16777216.0f) ? 0.f : __fdiv_rn(bound, amax);
@@ -87,6 +118,72 @@ __global__ void __launch_bounds__(256) k_quantize_rows(const void* x, int in_dty
             ((int8_t*)out)[i] = (int8_t)(int)q;
         } else {
             ((__half*)out)[i] = __float2half_rn(sc == 0.f ? 0.f : __fdiv_rn(q, sc));
+        }
+    }
+}
+
+// fp16 rows, c % 8 == 0: one thread per 8 consecutive channels (16-byte load, 8- or 16-byte store); same arithmetic
+__global__ void __launch_bounds__(256) k_quantize_rows_h8(const __half* __restrict__ x, int64_t n_cap, const int* __restrict__ n_dev, int c,
+                                                          const float* absmax, const float* smooth, float bound, int mode,
+                                                          void* out, float* act_scale_out) {
+    extern __shared__ float s_par[];                   // [c] scale, [c] smooth
+    float* s_scale = s_par;
+    float* s_smooth = s_par + c;
+    const int64_t n = n_dev ? (int64_t)*n_dev : n_cap;
+    __shared__ float s_tensor_amax;
+    if (threadIdx.x == 0) {
+        float m = 0.f;
+        if (mode == QL_Q_CODES_PER_TENSOR || mode == QL_Q_FAKE_PER_TENSOR)
+            for (int j = 0; j < c; ++j) m = fmaxf(m, smooth ? __fdiv_rn(absmax[j], smooth[j]) : absmax[j]);
+        s_tensor_amax = m;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < c; j += blockDim.x) {
+        float am = (mode == QL_Q_FAKE_PER_CHANNEL) ? (smooth ? __fdiv_rn(absmax[j], smooth[j]) : absmax[j]) : s_tensor_amax;
+        s_scale[j] = quant_scale_of(am, bound);
+        s_smooth[j] = smooth ? smooth[j] : 1.0f;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && act_scale_out) act_scale_out[0] = __fdiv_rn(s_tensor_amax, bound);
+    __syncthreads();
+    const int groups = c >> 3;
+    const int64_t total = n * groups;
+    const bool has_smooth = smooth != nullptr;
+    const bool pow2 = (groups & (groups - 1)) == 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ch0 = (pow2 ? (int)(i & (int64_t)(groups - 1)) : (int)(i % groups)) * 8;
+        const uint4 raw = *reinterpret_cast<const uint4*>(x + i * 8);
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h[j]);
+            v[2 * j] = f.x; v[2 * j + 1] = f.y;
+        }
+        float q[8], sc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (has_smooth) v[j] = __fdiv_rn(v[j], s_smooth[ch0 + j]);
+            sc[j] = s_scale[ch0 + j];
+            q[j] = quant_code(v[j], sc[j], bound);
+        }
+        if (mode == QL_Q_CODES_PER_TENSOR) {
+            uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                w0 |= ((uint32_t)(uint8_t)(int8_t)(int)q[j]) << (8 * j);
+                w1 |= ((uint32_t)(uint8_t)(int8_t)(int)q[4 + j]) << (8 * j);
+            }
+            *reinterpret_cast<uint2*>((int8_t*)out + i * 8) = make_uint2(w0, w1);
+        } else {
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float a = sc[2 * j] == 0.f ? 0.f : __fdiv_rn(q[2 * j], sc[2 * j]);
+                const float b = sc[2 * j + 1] == 0.f ? 0.f : __fdiv_rn(q[2 * j + 1], sc[2 * j + 1]);
+                const __half2 hh = __floats2half2_rn(a, b);
+                o[j] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+            *reinterpret_cast<uint4*>((__half*)out + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
         }
     }
 }
@@ -263,7 +360,14 @@ extern "C" int ql_absmax_cols(const void* x, int32_t dtype, int64_t n_cap, const
     if (n_cap <= 0) return QL_OK;
     int64_t blocks = (n_cap * c + 256 * 16 - 1) / (256 * 16);
     int grid = (int)(blocks < 1 ? 1 : (blocks > 4 * ql_num_sms() ? 4 * ql_num_sms() : blocks));
-    k_absmax_cols<<<grid, 256, (size_t)c * 4, (cudaStream_t)stream_>>>(x, dtype, n_cap, n_dev, c, absmax);
+    if (dtype == QL_F16 && c % 8 == 0 && 256 % (c / 8) == 0 && ((uintptr_t)x & 15) == 0) {
+        const int rows_per_step = 256 / (c / 8);
+        int64_t want = (n_cap + (int64_t)rows_per_step * 8 - 1) / ((int64_t)rows_per_step * 8);
+        grid = (int)(want < 1 ? 1 : (want > 8 * ql_num_sms() ? 8 * ql_num_sms() : want));
+        k_absmax_cols_h8<<<grid, 256, (size_t)c * 4, (cudaStream_t)stream_>>>((const __half*)x, n_cap, n_dev, c, absmax);
+    } else {
+        k_absmax_cols<<<grid, 256, (size_t)c * 4, (cudaStream_t)stream_>>>(x, dtype, n_cap, n_dev, c, absmax);
+    }
     QL_CUDA_CHECK_LAST();
     return QL_OK;
 }
@@ -282,6 +386,11 @@ extern "C" int ql_quantize_rows(const void* x, int32_t in_dtype, int64_t n_cap, 
     int grid = (int)(blocks < 1 ? 1 : (blocks > 8 * ql_num_sms() ? 8 * ql_num_sms() : blocks));
     if (mode == QL_Q_FAKE_PER_ROW) {
         k_fake_quant_per_row<<<grid, 256, 0, (cudaStream_t)stream_>>>(x, in_dtype, n_cap, n_dev, c, bound, (__half*)out);
+    } else if (in_dtype == QL_F16 && c % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0) {
+        int64_t want = (n_cap * (c / 8) + 256 * 4 - 1) / (256 * 4);
+        grid = (int)(want < 1 ? 1 : (want > 16 * ql_num_sms() ? 16 * ql_num_sms() : want));
+        k_quantize_rows_h8<<<grid, 256, (size_t)c * 8, (cudaStream_t)stream_>>>((const __half*)x, n_cap, n_dev, c, absmax, smooth, bound,
+                                                                               mode, out, act_scale_out);
     } else {
         k_quantize_rows<<<grid, 256, (size_t)c * 12, (cudaStream_t)stream_>>>(x, in_dtype, n_cap, n_dev, c, absmax, smooth, bound,
                                                                             mode, out, act_scale_out);

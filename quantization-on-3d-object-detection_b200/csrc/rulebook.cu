@@ -439,3 +439,145 @@ extern "C" int ql_rulebook_subm_ranked(const int32_t* coords, int64_t n_cap, con
     QL_CUDA_CHECK_LAST();
     return QL_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// VoxelNeXt 2-D merge (VoxelResBackBone8xVoxelNeXt.bev_out, spconv_backbone_voxelnext.py:149-164): drop z, keep the
+// unique (b, y, x) rows in ascending order (== torch.unique(dim=0)) and sum the features of the rows that collapse
+// onto the same site (index_add_).  Same bitmap + popcount-scan numbering as the strided rulebook; the sums are fp32
+// atomics (like index_add_ on the GPU, the order of the <= D additions per site is not fixed).
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Merge2dWs {
+    size_t bitmap, prefix, blocks, acc, total;
+    int64_t n_words, n_blocks;
+};
+Merge2dWs merge2d_ws_layout(int B, int H, int W, int64_t n_out_cap, int c, bool need_acc) {
+    Merge2dWs w;
+    const int64_t cells = (int64_t)B * H * W;
+    w.n_words = (cells + 31) / 32;
+    w.n_blocks = (w.n_words + kWordsPerBlock - 1) / kWordsPerBlock;
+    size_t o = 0;
+    w.bitmap = o; o += align256((size_t)w.n_words * 4);
+    w.prefix = o; o += align256((size_t)w.n_words * 4);
+    w.blocks = o; o += align256((size_t)(w.n_blocks + 1) * 4);
+    w.acc = o; o += need_acc ? align256((size_t)n_out_cap * c * 4) : 0;
+    w.total = o;
+    return w;
+}
+
+__global__ void __launch_bounds__(256) k_m2d_mark(const int4* __restrict__ coords, int64_t n_cap, const int* __restrict__ n_dev, int B,
+                                                  int H, int W, uint32_t* __restrict__ bitmap) {
+    const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 c = coords[i];                                             // b, z, y, x
+    if (c.x < 0 || c.x >= B || c.z < 0 || c.z >= H || c.w < 0 || c.w >= W) return;
+    const uint32_t key = (uint32_t)((c.x * H + c.z) * W + c.w);
+    const uint32_t bit = 1u << (key & 31u);
+    if (!(__ldcg(&bitmap[key >> 5]) & bit)) atomicOr(&bitmap[key >> 5], bit);
+}
+
+__global__ void __launch_bounds__(QL_SCAN_THREADS) k_m2d_emit(const uint32_t* __restrict__ bitmap, int64_t n_words,
+                                                             const int* __restrict__ block_offsets, int H, int W,
+                                                             uint32_t* __restrict__ word_prefix, int* __restrict__ out_coords,
+                                                             int64_t n_out_cap) {
+    const int64_t w = (int64_t)blockIdx.x * kWordsPerBlock + threadIdx.x;
+    uint32_t bits = w < n_words ? bitmap[w] : 0u;
+    int total;
+    uint32_t rank = (uint32_t)(block_exclusive_scan(__popc(bits), total) + block_offsets[blockIdx.x]);
+    if (w < n_words) word_prefix[w] = rank;
+    while (bits) {
+        const uint32_t pos = (uint32_t)__ffs((int)bits) - 1u;
+        bits &= bits - 1u;
+        if ((int64_t)rank < n_out_cap) {
+            uint32_t key = (uint32_t)w * 32u + pos;
+            const int x = (int)(key % (uint32_t)W); key /= (uint32_t)W;
+            const int y = (int)(key % (uint32_t)H); key /= (uint32_t)H;
+            out_coords[3 * (int64_t)rank] = (int)key;
+            out_coords[3 * (int64_t)rank + 1] = y;
+            out_coords[3 * (int64_t)rank + 2] = x;
+        }
+        ++rank;
+    }
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) k_m2d_add(const TIn* __restrict__ feats, int c, const int4* __restrict__ coords, int64_t n_cap,
+                                                 const int* __restrict__ n_dev, int B, int H, int W,
+                                                 const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_prefix,
+                                                 int64_t n_out_cap, float* __restrict__ acc) {
+    const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
+    const int groups = c >> 2;                                            // c % 4 == 0 (checked on the host)
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * groups) return;
+    const int64_t row = t / groups;
+    const int g4 = (int)(t - row * groups) * 4;
+    const int4 cc = coords[row];
+    if (cc.x < 0 || cc.x >= B || cc.z < 0 || cc.z >= H || cc.w < 0 || cc.w >= W) return;
+    const uint32_t key = (uint32_t)((cc.x * H + cc.z) * W + cc.w);
+    const uint32_t wd = key >> 5;
+    const uint32_t rank = __ldg(word_prefix + wd) + (uint32_t)__popc(__ldg(bitmap + wd) & ((1u << (key & 31u)) - 1u));
+    if ((int64_t)rank >= n_out_cap) return;
+    float v[4];
+    if constexpr (sizeof(TIn) == 2) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(feats + row * c + g4);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+        const float4 f = *reinterpret_cast<const float4*>(feats + row * c + g4);
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    }
+    float* dst = acc + (int64_t)rank * c + g4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(dst + j, v[j]);
+}
+
+__global__ void __launch_bounds__(256) k_m2d_to_half(const float* __restrict__ acc, int64_t n_elems_cap, int c, const int* __restrict__ n_out_dev,
+                                                     __half* __restrict__ out) {
+    const int64_t total = min((int64_t)n_out_dev[0] * c, n_elems_cap);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __float2half_rn(acc[i]);
+}
+}  // namespace
+
+extern "C" size_t ql_bev_merge2d_workspace_bytes(int32_t B, int32_t H, int32_t W, int64_t n_out_cap, int32_t c, int32_t out_dtype) {
+    if (B <= 0 || H <= 0 || W <= 0 || n_out_cap <= 0 || c <= 0) return 0;
+    return merge2d_ws_layout(B, H, W, n_out_cap, c, out_dtype != QL_F32).total;
+}
+
+extern "C" int ql_bev_merge2d(const void* feats, int32_t in_dtype, int32_t c, const int32_t* coords, int64_t n_cap, const int32_t* n_dev,
+                              int32_t B, int32_t H, int32_t W, void* out_feats, int32_t out_dtype, int32_t* out_coords,
+                              int64_t n_out_cap, int32_t* n_out_dev, void* workspace, size_t workspace_bytes, ql_stream_t stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (!feats || !coords || !out_feats || !out_coords || !n_out_dev || !workspace) return QL_ERR_INVALID;
+    if ((in_dtype != QL_F16 && in_dtype != QL_F32) || (out_dtype != QL_F16 && out_dtype != QL_F32)) return QL_ERR_INVALID;
+    if (c <= 0 || c % 4 != 0 || B <= 0 || H <= 0 || W <= 0 || n_cap < 0 || n_out_cap <= 0 || n_cap >= 2147483647LL) return QL_ERR_INVALID;
+    if ((double)B * H * W >= 4294967295.0) return QL_ERR_GRID_TOO_LARGE;
+    const Merge2dWs w = merge2d_ws_layout(B, H, W, n_out_cap, c, out_dtype != QL_F32);
+    if (workspace_bytes < w.total) return QL_ERR_WORKSPACE;
+    char* ws = (char*)workspace;
+    uint32_t* bitmap = (uint32_t*)(ws + w.bitmap);
+    uint32_t* prefix = (uint32_t*)(ws + w.prefix);
+    int* blocks = (int*)(ws + w.blocks);
+    float* acc = out_dtype == QL_F32 ? (float*)out_feats : (float*)(ws + w.acc);
+    if (cudaMemsetAsync(bitmap, 0, (size_t)w.n_words * 4, st) != cudaSuccess) return QL_ERR_CUDA;
+    if (cudaMemsetAsync(acc, 0, (size_t)n_out_cap * c * 4, st) != cudaSuccess) return QL_ERR_CUDA;
+    if (n_cap > 0) k_m2d_mark<<<(unsigned)((n_cap + 255) / 256), 256, 0, st>>>((const int4*)coords, n_cap, n_dev, B, H, W, bitmap);
+    k_rb_popc<<<(unsigned)w.n_blocks, QL_SCAN_THREADS, 0, st>>>(bitmap, w.n_words, blocks);
+    k_scan_blocks<<<1, QL_SCAN_THREADS, 0, st>>>(blocks, (int)w.n_blocks, n_out_dev + 1, n_out_dev, n_out_cap);
+    k_m2d_emit<<<(unsigned)w.n_blocks, QL_SCAN_THREADS, 0, st>>>(bitmap, w.n_words, blocks, H, W, prefix, out_coords, n_out_cap);
+    if (n_cap > 0) {
+        const int64_t threads = n_cap * (c / 4);
+        if (in_dtype == QL_F16)
+            k_m2d_add<__half><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const __half*)feats, c, (const int4*)coords, n_cap, n_dev, B, H,
+                                                                                 W, bitmap, prefix, n_out_cap, acc);
+        else
+            k_m2d_add<float><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const float*)feats, c, (const int4*)coords, n_cap, n_dev, B, H, W,
+                                                                                bitmap, prefix, n_out_cap, acc);
+    }
+    if (out_dtype == QL_F16)
+        k_m2d_to_half<<<4 * ql_num_sms(), 256, 0, st>>>(acc, n_out_cap * (int64_t)c, c, n_out_dev, (__half*)out_feats);
+    QL_CUDA_CHECK_LAST();
+    return QL_OK;
+}

@@ -217,16 +217,15 @@ class VoxelResBackBone8xVoxelNeXt(_BackboneBase):
         self.backbone_channels = {'x_conv1': ch[0], 'x_conv2': ch[1], 'x_conv3': ch[2], 'x_conv4': ch[3]}
 
     def bev_out(self, x_conv):
-        """spconv_backbone_voxelnext.py:149-164: drop z, merge duplicate (b,y,x) rows by summation.  The unique/
-        index_add_ pair is torch plumbing here; the fused CUDA merge is a SURVEY.md 8(a13) follow-up."""
-        features_cat = x_conv.features
-        indices_cat = x_conv.indices[:, [0, 2, 3]]
+        """spconv_backbone_voxelnext.py:149-164: drop z, merge duplicate (b,y,x) rows by summation -- one fused CUDA op
+        (ql_bev_merge2d: bitmap numbering in ascending (b,y,x) order == torch.unique(dim=0), fp32 atomic sums == index_add_)."""
         spatial_shape = x_conv.spatial_shape[1:]
-        indices_unique, _inv = torch.unique(indices_cat, dim=0, return_inverse=True)
-        features_unique = features_cat.new_zeros((indices_unique.shape[0], features_cat.shape[1]))
-        features_unique.index_add_(0, _inv, features_cat)
-        return SparseConvTensor(features=features_unique, indices=indices_unique.int().contiguous(), spatial_shape=spatial_shape,
-                                batch_size=x_conv.batch_size)
+        feats = x_conv.features.contiguous()
+        if feats.dtype not in (torch.float16, torch.float32):
+            feats = feats.float()
+        f, c3, n_out = ops.bev_merge2d(feats, x_conv.indices.contiguous(), None, (x_conv.batch_size, spatial_shape[0], spatial_shape[1]))
+        n = int(n_out[0].item())                                     # module (eager) path: the row count comes back to the host
+        return SparseConvTensor(features=f[:n], indices=c3[:n], spatial_shape=spatial_shape, batch_size=x_conv.batch_size)
 
     def forward(self, batch_dict):
         x = self.conv_input(self._input_tensor(batch_dict))

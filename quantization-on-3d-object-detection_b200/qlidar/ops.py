@@ -220,6 +220,27 @@ def bev_densify_ranked(feats: torch.Tensor, index: RankIndex, n_dev: Optional[to
     return out
 
 
+def bev_merge2d(feats: torch.Tensor, coords: torch.Tensor, n_dev: Optional[torch.Tensor], grid_bhw, n_out_cap: Optional[int] = None,
+                out_dtype: Optional[torch.dtype] = None):
+    """VoxelNeXt bev_out: drop z, unique (b, y, x) rows in ascending order, duplicates summed.
+    Returns (out_feats [n_out_cap, c], out_coords [n_out_cap, 3] int32, n_out_dev [2] = (kept, found))."""
+    _need_cuda(feats, coords, n_dev)
+    if coords.dtype != torch.int32 or coords.shape[1] != 4:
+        raise QlidarError("bev_merge2d expects int32 [n, 4] coords [b, z, y, x]")
+    n, c = feats.shape
+    B, H, W = [int(v) for v in grid_bhw]
+    cap = int(n_out_cap) if n_out_cap is not None else max(int(n), 1)
+    out_dtype = out_dtype or feats.dtype
+    dev = feats.device
+    out_feats = torch.empty((cap, c), dtype=out_dtype, device=dev)
+    out_coords = torch.zeros((cap, 3), dtype=torch.int32, device=dev)
+    n_out = torch.zeros((2,), dtype=torch.int32, device=dev)
+    ws = torch.empty(int(lib().ql_bev_merge2d_workspace_bytes(B, H, W, cap, c, _DT[out_dtype])), dtype=torch.uint8, device=dev)
+    check(lib().ql_bev_merge2d(_ptr(feats), _DT[feats.dtype], c, _ptr(coords), n, _ptr(n_dev), B, H, W, _ptr(out_feats), _DT[out_dtype],
+                               _ptr(out_coords), cap, _ptr(n_out), _ptr(ws), ws.numel(), _stream()), "ql_bev_merge2d")
+    return out_feats, out_coords, n_out
+
+
 def pack_weights(w: torch.Tensor) -> torch.Tensor:
     """w: CPU tensor (c_out, K, c_in) int8 codes or float16 -> CPU uint8 tensor with the shared-memory image."""
     if w.is_cuda:

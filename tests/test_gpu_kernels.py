@@ -413,3 +413,28 @@ def test_bev_densify(ops, D, H, W, C):
     assert torch.equal(out.cpu().float(), ref)
     out32 = ops.bev_densify(dev(f.float()), table, (B, D, H, W), out_dtype=torch.float32)
     assert torch.equal(out32.cpu(), ref)
+
+
+# ------------------------------------------------------------------------------------------------ VoxelNeXt 2-D merge
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_bev_merge2d_matches_torch_unique_index_add(ops, dtype):
+    """ql_bev_merge2d == VoxelResBackBone8xVoxelNeXt.bev_out (spconv_backbone_voxelnext.py:149-164) restated by the oracle
+    (drop z, unique (b,y,x) ascending, duplicates summed): coordinates bit-exact, sums within fp32 re-association."""
+    rng = np.random.default_rng(70)
+    B, D, H, W, C = 2, 6, 47, 52, 64
+    coords = random_coords(rng, B, D, H, W, 0.2)                      # many (b,y,x) duplicates across z
+    f = torch.from_numpy(rng.normal(size=(coords.shape[0], C)).astype(np.float32)).to(dtype)
+    ref_f, ref_c = O.bev_merge2d(f.float(), coords)
+    out_f, out_c, n_out = ops.bev_merge2d(dev(f), dev(coords), None, (B, H, W))
+    n = int(n_out[0].item())
+    assert n == ref_c.shape[0] and int(n_out[1].item()) == n
+    assert np.array_equal(out_c[:n].cpu().numpy(), ref_c)
+    tol = 1e-6 if dtype == torch.float32 else 2e-3
+    assert (out_f[:n].float().cpu() - ref_f).abs().max().item() <= tol * ref_f.abs().max().item()
+    # device-side row count and an output cap below the number of sites
+    n_dev = torch.tensor([coords.shape[0] - 500], dtype=torch.int32, device="cuda")
+    ref_f2, ref_c2 = O.bev_merge2d(f[:coords.shape[0] - 500].float(), coords[:coords.shape[0] - 500])
+    out_f2, out_c2, n_out2 = ops.bev_merge2d(dev(f), dev(coords), n_dev, (B, H, W), n_out_cap=ref_c2.shape[0] - 10)
+    assert n_out2.tolist() == [ref_c2.shape[0] - 10, ref_c2.shape[0]]
+    assert np.array_equal(out_c2.cpu().numpy(), ref_c2[:-10])
+    assert (out_f2.float().cpu() - ref_f2[:-10]).abs().max().item() <= tol * ref_f2.abs().max().item()
