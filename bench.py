@@ -108,7 +108,9 @@ def build_engine(device, max_points):
                 m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.1); m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
     bb = bb.to(device).eval()
     qlidar.q_conv3d(bb, {}, "", W_BITS, ACT_BITS, CW, (qlidar.SubMConv3d, qlidar.SparseConv3d), NO_LIST)
-    cap = BATCH * c["max_voxels"]
+    # engine capacities are per BATCH (the reference caps each frame at MAX_NUMBER_OF_VOXELS = 150 000 in its CPU voxeliser);
+    # the synthetic frames hold 98 k - 160 k voxels depending on the seed, so leave 15 % head room: no frame is truncated
+    cap = int(1.15 * BATCH * c["max_voxels"])
     eng = qlidar.BackboneEngine(bb, BATCH, cap, max_points=max_points, pc_range=c["pc_range"], voxel_size=c["voxel_size"],
                                 max_pts_per_voxel=c["max_pts"], use_graph=True, device=device,
                                 stage_caps=[cap, int(1.25 * cap), int(0.75 * cap), int(0.5 * cap), int(0.5 * cap)])
@@ -147,7 +149,7 @@ def run_ours(args):
         eng.forward_points()
     torch.cuda.synchronize()
     if eng.overflowed():
-        raise SystemExit("bench.py: a stage capacity overflowed; raise stage_caps")
+        raise SystemExit(f"bench.py: a stage capacity overflowed (rank {rank}, (kept, found) per stage {[st.n_dev.tolist() for st in eng.stages]}); raise stage_caps")
     counts = eng.counts()
     kernels_per_step = eng.kernels_per_forward
 

@@ -155,28 +155,27 @@ constexpr int kWordsPerBlock = QL_SCAN_THREADS;                      // one bitm
 
 // calls f(k, out_key) for every kernel offset k through which input coord c feeds an in-range output site:
 // out = (c + pad - k) / stride, exact division (so that in = out*stride - pad + k)
-// exact division by the stride: strides 1 and 2 (every conv of the backbones) avoid the integer-division sequence
-__device__ __forceinline__ bool div_exact(int n, int s, int& q) {
-    if (s == 1) { q = n; return true; }
-    if (s == 2) { q = n >> 1; return !(n & 1); }
-    q = n / s;
-    return q * s == n;
+// Per axis the kernel taps k through which input coordinate c reaches an output are k == (c + pad) mod stride, i.e.
+// k = r, r + s, r + 2s, ... < K with out = (c + pad - k) / s: walk only those (1-2 per axis for k=3, s=2) instead of testing
+// all K taps for divisibility.  Strides 1 and 2 (every conv of the backbones) avoid the integer-division sequence.
+__device__ __forceinline__ void axis_first(int n, int s, int& k0, int& o0) {   // n = c + pad >= 0
+    if (s == 1) { k0 = 0; o0 = n; }
+    else if (s == 2) { k0 = n & 1; o0 = n >> 1; }
+    else { k0 = n % s; o0 = n / s; }
 }
 
 template <class F>
 __device__ __forceinline__ void for_each_candidate(const int4& c, const ConvGeom& cg, const QlGrid& gout, F&& f) {
-    for (int kz = 0; kz < cg.kd; ++kz) {
-        const int nz = c.y + cg.pd - kz;
-        int oz;
-        if (nz < 0 || !div_exact(nz, cg.sd, oz) || oz >= gout.D) continue;
-        for (int ky = 0; ky < cg.kh; ++ky) {
-            const int ny = c.z + cg.ph - ky;
-            int oy;
-            if (ny < 0 || !div_exact(ny, cg.sh, oy) || oy >= gout.H) continue;
-            for (int kx = 0; kx < cg.kw; ++kx) {
-                const int nx = c.w + cg.pw - kx;
-                int ox;
-                if (nx < 0 || !div_exact(nx, cg.sw, ox) || ox >= gout.W) continue;
+    int kz0, oz0, ky0, oy0, kx0, ox0;
+    axis_first(c.y + cg.pd, cg.sd, kz0, oz0);
+    axis_first(c.z + cg.ph, cg.sh, ky0, oy0);
+    axis_first(c.w + cg.pw, cg.sw, kx0, ox0);
+    for (int kz = kz0, oz = oz0; kz < cg.kd && oz >= 0; kz += cg.sd, --oz) {
+        if (oz >= gout.D) continue;
+        for (int ky = ky0, oy = oy0; ky < cg.kh && oy >= 0; ky += cg.sh, --oy) {
+            if (oy >= gout.H) continue;
+            for (int kx = kx0, ox = ox0; kx < cg.kw && ox >= 0; kx += cg.sw, --ox) {
+                if (ox >= gout.W) continue;
                 f((kz * cg.kh + ky) * cg.kw + kx, ql_key(gout, c.x, oz, oy, ox));
             }
         }
