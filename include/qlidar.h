@@ -117,6 +117,16 @@ int ql_rulebook_strided(const int32_t* in_coords, int64_t n_in_cap, const int32_
 int ql_rulebook_strided_index(int32_t B, int32_t D, int32_t H, int32_t W,
                               const int32_t* ksize_host, const int32_t* stride_host, const int32_t* pad_host,
                               void* workspace, const uint32_t** bitmap, const uint32_t** word_prefix, int64_t* n_words);
+/* ql_rulebook_strided for a KEY-SORTED input stage: the pairs are taken from the output side through the input stage's rank
+ * index (in_bitmap / in_word_prefix over the INPUT grid B,D,H,W), so no -1 fill / scatter / mask pass is needed.  Same
+ * outputs and workspace as ql_rulebook_strided (whose rank index of the OUTPUT stage it also leaves behind); no hash. */
+int ql_rulebook_strided_ranked(const int32_t* in_coords, int64_t n_in_cap, const int32_t* n_in_dev,
+                               int32_t B, int32_t D, int32_t H, int32_t W,
+                               const int32_t* ksize_host, const int32_t* stride_host, const int32_t* pad_host,
+                               const uint32_t* in_bitmap, const uint32_t* in_word_prefix,
+                               int32_t* out_coords, int64_t n_out_cap, int32_t* n_out_dev,
+                               int32_t* nbr_out, uint32_t* tile_kmask,
+                               void* workspace, size_t workspace_bytes, ql_stream_t stream);
 int ql_rulebook_subm_ranked(const int32_t* coords, int64_t n_cap, const int32_t* n_dev,
                             int32_t B, int32_t D, int32_t H, int32_t W, const int32_t* ksize_host,
                             const uint32_t* bitmap, const uint32_t* word_prefix,

@@ -89,13 +89,17 @@ __global__ void __launch_bounds__(QL_TILE_M) k_rb_pairs(const int4* __restrict__
 // query on the stage's bitmap -- row(key) = word_prefix[key / 32] + popc(bitmap[key / 32] below the bit) -- instead of a hash
 // probe.  The kw cells of one (kz, ky) line are adjacent bits, mostly of ONE bitmap word, so an output row costs ~kd*kh
 // bitmap/prefix word pairs (dense, L1/L2 resident) rather than K random 8-byte table probes.
+// Also the pair pass of a STRIDED conv whose input stage is key-sorted: rows = output sites, in = out * stride - pad + k is
+// looked up in the INPUT stage's rank index (n_in_* bound the valid input rows); no -1 fill, no scatter, no mask pass.
 __global__ void __launch_bounds__(QL_TILE_M) k_rb_pairs_ranked(const int4* __restrict__ coords, int64_t n_cap,
                                                                const int* __restrict__ n_dev, QlGrid g, ConvGeom cg,
                                                                const uint32_t* __restrict__ bitmap,
                                                                const uint32_t* __restrict__ word_prefix, int* __restrict__ nbr,
-                                                               uint32_t* __restrict__ kmask) {
+                                                               uint32_t* __restrict__ kmask, int64_t n_in_cap,
+                                                               const int* __restrict__ n_in_dev) {
     __shared__ uint32_t s_mask[QL_MASK_WORDS_MAX];
     const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
+    const int64_t n_in = n_in_dev ? min((int64_t)*n_in_dev, n_in_cap) : n_in_cap;
     const int64_t tile = blockIdx.x;
     if (tile * QL_TILE_M >= n) return;
     const int r = threadIdx.x;
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(QL_TILE_M) k_rb_pairs_ranked(const int4* __res
     __syncthreads();
     const bool live = row < n;
     const int4 c = live ? coords[row] : make_int4(0, 0, 0, 0);      // b, z, y, x
-    const int bz = c.y - cg.pd, by = c.z - cg.ph, bx = c.w - cg.pw;
+    const int bz = c.y * cg.sd - cg.pd, by = c.z * cg.sh - cg.ph, bx = c.w * cg.sw - cg.pw;
     for (int kz = 0; kz < cg.kd; ++kz) {
         for (int ky = 0; ky < cg.kh; ++ky) {
             const int z = bz + kz, y = by + ky;
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(QL_TILE_M) k_rb_pairs_ranked(const int4* __res
                     if (bits & bit) {
                         if (pre == 0xFFFFFFFFu) pre = __ldg(word_prefix + w);
                         const uint32_t rank = pre + (uint32_t)__popc(bits & (bit - 1u));
-                        if ((int64_t)rank < n) res = (int)rank;
+                        if ((int64_t)rank < n_in) res = (int)rank;
                     }
                 }
                 const int k = (kz * cg.kh + ky) * cg.kw + kx;
@@ -434,7 +438,7 @@ extern "C" int ql_rulebook_subm_ranked(const int32_t* coords, int64_t n_cap, con
     QlGrid g{B, D, H, W};
     unsigned tiles = (unsigned)ql_rulebook_num_tiles(n_cap);
     k_rb_pairs_ranked<<<tiles, QL_TILE_M, 0, (cudaStream_t)stream_>>>((const int4*)coords, n_cap, n_dev, g, cg, bitmap, word_prefix,
-                                                                      nbr_out, tile_kmask);
+                                                                      nbr_out, tile_kmask, n_cap, n_dev);
     QL_CUDA_CHECK_LAST();
     return QL_OK;
 }
@@ -577,6 +581,43 @@ extern "C" int ql_bev_merge2d(const void* feats, int32_t in_dtype, int32_t c, co
     }
     if (out_dtype == QL_F16)
         k_m2d_to_half<<<4 * ql_num_sms(), 256, 0, st>>>(acc, n_out_cap * (int64_t)c, c, n_out_dev, (__half*)out_feats);
+    QL_CUDA_CHECK_LAST();
+    return QL_OK;
+}
+
+extern "C" int ql_rulebook_strided_ranked(const int32_t* in_coords, int64_t n_in_cap, const int32_t* n_in_dev, int32_t B, int32_t D,
+                                          int32_t H, int32_t W, const int32_t* ksize, const int32_t* stride, const int32_t* pad,
+                                          const uint32_t* in_bitmap, const uint32_t* in_word_prefix, int32_t* out_coords,
+                                          int64_t n_out_cap, int32_t* n_out_dev, int32_t* nbr_out, uint32_t* tile_kmask,
+                                          void* workspace, size_t workspace_bytes, ql_stream_t stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    ConvGeom cg;
+    if (!in_coords || !in_bitmap || !in_word_prefix || !out_coords || !n_out_dev || !nbr_out || !workspace || !stride || !pad ||
+        !geom_from_host(ksize, stride, pad, cg))
+        return QL_ERR_INVALID;
+    if (n_out_cap <= 0 || n_out_cap >= 2147483647LL || n_in_cap < 0 || n_in_cap >= 2147483647LL) return QL_ERR_INVALID;
+    QlGrid gout;
+    if (!out_grid(B, D, H, W, cg, gout)) return QL_ERR_INVALID;
+    if ((double)B * D * H * W >= 4294967295.0 || (double)B * gout.D * gout.H * gout.W >= 4294967295.0)
+        return QL_ERR_GRID_TOO_LARGE;
+    const StridedWs w = strided_ws_layout(gout);
+    if (workspace_bytes < w.total) return QL_ERR_WORKSPACE;
+    char* ws = (char*)workspace;
+    uint32_t* bitmap = (uint32_t*)(ws + w.bitmap);
+    uint32_t* prefix = (uint32_t*)(ws + w.prefix);
+    int* blocks = (int*)(ws + w.blocks);
+    if (cudaMemsetAsync(bitmap, 0, (size_t)w.n_words * 4, st) != cudaSuccess) return QL_ERR_CUDA;
+    const unsigned gin = (unsigned)((n_in_cap + 255) / 256);
+    if (gin) k_rb_mark<<<gin, 256, 0, st>>>((const int4*)in_coords, n_in_cap, n_in_dev, cg, gout, bitmap);
+    k_rb_popc<<<(unsigned)w.n_blocks, QL_SCAN_THREADS, 0, st>>>(bitmap, w.n_words, blocks);
+    k_scan_blocks<<<1, QL_SCAN_THREADS, 0, st>>>(blocks, (int)w.n_blocks, n_out_dev + 1, n_out_dev, n_out_cap);
+    k_rb_emit<<<(unsigned)w.n_blocks, QL_SCAN_THREADS, 0, st>>>(bitmap, w.n_words, blocks, gout, prefix, (int4*)out_coords, n_out_cap,
+                                                              nullptr, 0u);
+    // pairs from the output side through the INPUT stage's rank index: every (tile, offset) slab is written exactly once
+    QlGrid gin_grid{B, D, H, W};
+    k_rb_pairs_ranked<<<(unsigned)ql_rulebook_num_tiles(n_out_cap), QL_TILE_M, 0, st>>>((const int4*)out_coords, n_out_cap, n_out_dev,
+                                                                                        gin_grid, cg, in_bitmap, in_word_prefix, nbr_out,
+                                                                                        tile_kmask, n_in_cap, n_in_dev);
     QL_CUDA_CHECK_LAST();
     return QL_OK;
 }

@@ -34,6 +34,7 @@ SIGNATURES = {
     "ql_rulebook_strided_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _p, _p, _p]),
     "ql_rulebook_strided": (C.c_int, [_p, _i64, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _i64, _p, _p, _i64, _p, _p, _p, _sz, _p]),
     "ql_rulebook_strided_index": (C.c_int, [_i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    "ql_rulebook_strided_ranked": (C.c_int, [_p, _i64, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
     "ql_rulebook_subm_ranked": (C.c_int, [_p, _i64, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "ql_packed_weight_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ql_pack_weights_host": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p]),

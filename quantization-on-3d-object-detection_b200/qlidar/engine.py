@@ -280,8 +280,9 @@ class BackboneEngine:
                 elif L.subm:
                     self._op("rulebook_subm:" + L.name, 1, ops.rulebook_subm, si.coords, si.n_dev, si.grid, L.ksize, si.table, nbr=nbr, kmask=kmask)
                 else:
-                    self._op("rulebook_strided:" + L.name, 8, ops.rulebook_strided, si.coords, si.n_dev, si.grid, L.ksize, L.stride, L.pad,
-                             so.cap, out=(so.coords, so.n_dev, None, nbr), workspace=so.rank.workspace, kmask=kmask)
+                    # kernels: mark, popc, scan, emit + (fill, scatter, kmask | ranked pairs)
+                    self._op("rulebook_strided:" + L.name, 5 if si.rank is not None else 7, ops.rulebook_strided, si.coords, si.n_dev, si.grid, L.ksize, L.stride, L.pad,
+                             so.cap, out=(so.coords, so.n_dev, None, nbr), workspace=so.rank.workspace, kmask=kmask, in_index=si.rank)
                 built.add(L.rb_key)
             absmax = L.out_absmax if i in self._need_absmax else None
             if L.block_input:

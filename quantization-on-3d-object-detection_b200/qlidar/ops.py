@@ -175,9 +175,11 @@ def rulebook_strided_workspace_bytes(grid, ksize, stride, pad) -> int:
 
 
 def rulebook_strided(coords: torch.Tensor, n_in_dev: Optional[torch.Tensor], grid, ksize, stride, pad,
-                     n_out_cap: int, out=None, workspace=None, kmask: Optional[torch.Tensor] = None):
+                     n_out_cap: int, out=None, workspace=None, kmask: Optional[torch.Tensor] = None,
+                     in_index: Optional["RankIndex"] = None):
     """Returns (out_coords [n_out_cap,4] sorted by linear key, n_out_dev [2] = (kept, found), out_table, nbr [tiles,K,128],
-    out_grid (B,D,H,W), kmask [tiles, ceil(K/32)])."""
+    out_grid (B,D,H,W), kmask [tiles, ceil(K/32)]).  in_index: the rank index of a key-sorted INPUT stage -> the pairs come
+    from the output side through it (ql_rulebook_strided_ranked; no hash table is produced, out_table must be None)."""
     _need_cuda(coords, n_in_dev, kmask)
     k, s, p = triple(ksize), triple(stride), triple(pad)
     K = k[0] * k[1] * k[2]
@@ -188,7 +190,7 @@ def rulebook_strided(coords: torch.Tensor, n_in_dev: Optional[torch.Tensor], gri
     if out is None:
         out_coords = torch.empty((n_out_cap, 4), dtype=torch.int32, device=dev)
         n_out_dev = torch.zeros((2,), dtype=torch.int32, device=dev)
-        out_table = torch.empty(hash_capacity(n_out_cap), dtype=torch.int64, device=dev)
+        out_table = None if in_index is not None else torch.empty(hash_capacity(n_out_cap), dtype=torch.int64, device=dev)
         nbr = torch.empty((num_tiles(n_out_cap), K, TILE_M), dtype=torch.int32, device=dev)
     else:
         out_coords, n_out_dev, out_table, nbr = out                   # out_table may be None: rank-index consumers only
@@ -197,6 +199,14 @@ def rulebook_strided(coords: torch.Tensor, n_in_dev: Optional[torch.Tensor], gri
     ws_bytes = rulebook_strided_workspace_bytes(grid, k, s, p)
     if workspace is None or workspace.numel() < ws_bytes:
         workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    if in_index is not None:
+        if out_table is not None:
+            raise QlidarError("rulebook_strided(in_index=...) produces no hash table: pass out_table=None")
+        check(lib().ql_rulebook_strided_ranked(_ptr(coords), n_in_cap, _ptr(n_in_dev), B, D, H, W, _i32x3(k), _i32x3(s), _i32x3(p),
+                                               C.c_void_p(in_index.bitmap_ptr), C.c_void_p(in_index.prefix_ptr), _ptr(out_coords),
+                                               int(n_out_cap), _ptr(n_out_dev), _ptr(nbr), _ptr(kmask), _ptr(workspace),
+                                               workspace.numel(), _stream()), "ql_rulebook_strided_ranked")
+        return out_coords, n_out_dev, None, nbr, (B, od, oh, ow), kmask
     check(lib().ql_rulebook_strided(_ptr(coords), n_in_cap, _ptr(n_in_dev), B, D, H, W, _i32x3(k), _i32x3(s), _i32x3(p),
                                     _ptr(out_coords), int(n_out_cap), _ptr(n_out_dev), _ptr(out_table), 0 if out_table is None else out_table.numel(), _ptr(nbr),
                                     _ptr(kmask), _ptr(workspace), workspace.numel(), _stream()), "ql_rulebook_strided")

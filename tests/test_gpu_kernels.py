@@ -116,6 +116,15 @@ def test_rank_index_subm_rulebook_and_bev_bit_exact(ops, k, s, p, ksub):
     ref = O.height_compression(f[:n].float(), oc_ref, osh, B)
     out = ops.bev_densify_ranked(dev(f), index, n_out, ogrid)
     assert torch.equal(out.cpu().float(), ref)
+    # a second strided conv ON this key-sorted stage, pairs taken through its rank index: identical to the scatter-form build
+    for k2, s2, p2 in [(3, 2, 1), ((3, 1, 1), (2, 1, 1), 0)]:
+        oc2_ref, osh2, nbr2_ref = O.rulebook_strided(oc_ref, osh, k2, s2, p2)
+        m = oc2_ref.shape[0]
+        oc2, n2, t2, nb2, og2, km2 = ops.rulebook_strided(out_coords, n_out, ogrid, k2, s2, p2, m + 50, in_index=index)
+        assert t2 is None and n2.tolist() == [m, m]
+        assert np.array_equal(oc2[:m].cpu().numpy(), oc2_ref) and list(og2[1:]) == list(osh2)
+        assert np.array_equal(tiles_to_nbr(nb2.cpu().numpy(), m), nbr2_ref)
+        assert np.array_equal(km2[:(m + 127) // 128].cpu().numpy().view(np.uint32), O.tile_kmask(nbr2_ref))
     # a row cap below the number of sites: the dropped (largest-key) sites are absent everywhere
     n_small = torch.tensor([n - 40, n], dtype=torch.int32, device="cuda")
     nbr4, _ = ops.rulebook_subm_ranked(out_coords, n_small, ogrid, ksub, index)
