@@ -312,28 +312,53 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
                 ql_mbar_wait(ql_smem_u32(&misc->nbr_full[nb]), (it >> p.nbr_log2) & 1u);
                 const uint32_t n_sub = (uint32_t)ql_lds_s32(buf + 20u);
                 const uint32_t Gend = G0 + ((n_sub + kGroup - 1) >> kGroupLog2);
+                // The rulebook indices of a unit (table byte -> slab -> row index: two dependent shared-memory loads) are fetched
+                // one unit ahead, right after the previous unit's gathers have been issued, so that chain hides under them.
+                constexpr int kIdx = kQuad ? 4 * kGroup : kGroup;
+                int idx[kIdx];
+                uint32_t boff[kGroup];
+                auto fetch_idx = [&](uint32_t c0) {
+                    // the unit's kGroup table bytes (ordinal -> kernel offset) in one load
+                    uint32_t tbl;
+                    if constexpr (kGroup == 4) tbl = (uint32_t)ql_lds_s32(buf + 32u + c0);
+                    else if constexpr (kGroup == 2) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(tbl) : "r"(buf + 32u + c0));
+                    else {
+                        uint32_t ord = c0;
+                        boff[0] = 0;
+                        if (nseg > 1) { ord = (c0 * inv_nseg) >> 16; boff[0] = (c0 - ord * nseg) * 128u; }
+                        tbl = (uint32_t)lds_u8(buf + 32u + ord);
+                    }
+#pragma unroll
+                    for (int j = 0; j < kGroup; ++j) {
+                        const bool live = c0 + (uint32_t)j < n_sub;
+                        const uint32_t k = live ? ((tbl >> (8 * j)) & 0xFFu) : 0u;
+                        const uint32_t a = buf + hdr + k * (QL_TILE_M * 4u) + row_off;
+                        if constexpr (kGroup > 1) boff[j] = 0;
+                        if constexpr (kQuad) {
+#pragma unroll
+                            for (int rr = 0; rr < 4; ++rr) {
+                                const int v = ql_lds_s32(a + (uint32_t)rr * 32u);
+                                idx[4 * j + rr] = live ? v : -1;
+                            }
+                        } else {
+                            const int v = ql_lds_s32(a);
+                            idx[j] = live ? v : -1;
+                        }
+                    }
+                };
+                if (g < Gend) fetch_idx((g - G0) << kGroupLog2);
                 for (; g < Gend; g += T) {
-                    const uint32_t c0 = (g - G0) << kGroupLog2;      // the unit's first sub-chunk
                     uint32_t v[32];
                     if constexpr (kQuad) {
 #pragma unroll
                         for (int j = 0; j < kGroup; ++j) {
-                            const uint32_t lc = c0 + (uint32_t)j;
-                            int idx[4] = {-1, -1, -1, -1};
-                            uint32_t boff = 0;
-                            if (lc < n_sub) {
-                                uint32_t ord = lc;
-                                if (CH == 128) { ord = (lc * inv_nseg) >> 16; boff = (lc - ord * nseg) * 128u; }
-                                const uint32_t a = buf + hdr + (uint32_t)lds_u8(buf + 32u + ord) * (QL_TILE_M * 4u) + row_off;
-#pragma unroll
-                                for (int rr = 0; rr < 4; ++rr) idx[rr] = ql_lds_s32(a + (uint32_t)rr * 32u);
-                            }
-                            const uint32_t tb = boff + (uint32_t)tb0;
+                            const uint32_t tb = boff[j] + (uint32_t)tb0;
 #pragma unroll
                             for (int rr = 0; rr < 4; ++rr) {
                                 const int h = rr >> 1, v1 = rr & 1;
-                                const bool ok = idx[rr] >= 0 && tb < row_bytes;
-                                const uint8_t* src = ok ? feats + ((uint64_t)(uint32_t)idx[rr] * row_bytes + tb) : zero;
+                                const int id = idx[4 * j + rr];
+                                const bool ok = id >= 0 && tb < row_bytes;
+                                const uint8_t* src = ok ? feats + ((uint64_t)(uint32_t)id * row_bytes + tb) : zero;
                                 uint32_t x[8];
                                 if constexpr (CH == 128) {
                                     if (wide) {
@@ -355,12 +380,9 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
                     } else {
 #pragma unroll
                         for (int j = 0; j < kGroup; ++j) {
-                            const uint32_t lc = c0 + (uint32_t)j;            // CH = 32: one sub-chunk per kernel offset
-                            int idx = -1;
-                            if (lc < n_sub)
-                                idx = ql_lds_s32(buf + hdr + (uint32_t)lds_u8(buf + 32u + lc) * (QL_TILE_M * 4u) + row_off);
-                            const bool ok = idx >= 0;
-                            const uint8_t* src = ok ? feats + (uint64_t)(uint32_t)idx * row_bytes : zero;
+                            const int id = idx[j];                                       // CH = 32: one sub-chunk per kernel offset
+                            const bool ok = id >= 0;
+                            const uint8_t* src = ok ? feats + (uint64_t)(uint32_t)id * row_bytes : zero;
                             if (wide) {
                                 ldg32(src, v + j * 8);
                             } else {
@@ -369,6 +391,7 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
                             }
                         }
                     }
+                    if (g + T < Gend) fetch_idx((g + T - G0) << kGroupLog2);             // next unit's indices, under this unit's gathers
                     ql_mbar_wait(empty0 + u * 8u, ph ^ 1u);              // the MMAs that read this ring slot have completed
                     ql_tc_fence_after();
                     const uint32_t a_unit = a_lane_base + u * (uint32_t)kUnitCols;
