@@ -53,6 +53,9 @@ class Layer:
     act_scale: Optional[torch.Tensor] = None
     in_absmax: Optional[torch.Tensor] = None
     out_absmax: Optional[torch.Tensor] = None
+    out_q: Optional[torch.Tensor] = None         # static mode: this layer's epilogue also writes the NEXT layer's int8 codes here
+    out_qscale: Optional[torch.Tensor] = None    # ... with these per-channel quantisation scales (bound / calibrated amax)
+    fused_q: bool = False                        # this layer's codes come from the previous layer's epilogue
 
 
 @dataclass
@@ -244,6 +247,21 @@ class BackboneEngine:
                 L.q_buf = z(self.stages[L.stage_in].cap, L.cin)
             if L.act_amax is not None:
                 L.act_amax = (L.act_amax.expand(L.cin) if L.act_amax.numel() == 1 else L.act_amax).contiguous().to(dev)
+        # static calibration (collect_stats / compute_amax, quant/quantize.py:175-207): a per-tensor-quantised layer whose input
+        # is the previous layer's output gets its int8 codes straight from that layer's epilogue (out_q) -- no quantise pass,
+        # no abs-max pass; its de-quantisation scale amax/bound is a constant
+        for i, L in enumerate(self.layers):
+            L.fused_q = False
+            if L.kind == "i8" and L.act_amax is not None:
+                bound = float(2 ** (L.act_bits - 1) - 1)
+                amax = L.act_amax.float()
+                L.act_scale.copy_((amax.max() / bound).reshape(1))
+                prev = self.layers[i - 1] if i > 0 else None
+                if prev is not None and prev.kind in ("f16", "i8", "cw") and L.act_bits == 8:
+                    tiny = amax <= (1.0 / (1 << 24))
+                    prev.out_qscale = torch.where(tiny, torch.zeros_like(amax), bound / torch.where(tiny, torch.ones_like(amax), amax)).contiguous()
+                    prev.out_q = L.q_buf
+                    L.fused_q = True
         last = self.stages[-1]
         if self.bev:
             B, D, H, W = last.grid
@@ -292,18 +310,19 @@ class BackboneEngine:
                 self._op("stem:" + L.name, 1, ops.stem_conv, x, nbr, so.cap, so.n_dev, L.w, L.scale, L.shift, relu=L.relu, out=L.out, absmax=absmax)
             elif L.kind == "f16":
                 self._op("conv:" + L.name, 1, ops.spconv_mma, x, nbr, so.cap, so.n_dev, L.cout, L.w, L.scale, L.shift, residual=res,
-                         relu=L.relu, out=L.out, absmax=absmax, kmask=kmask)
+                         relu=L.relu, out=L.out, absmax=absmax, kmask=kmask, out_q=L.out_q, out_qscale=L.out_qscale)
             elif L.kind == "i8":
-                am = L.act_amax if L.act_amax is not None else L.in_absmax
-                self._op("quantize:" + L.name, 1, ops.quantize_rows, x, am, ops.QL_Q_CODES_PER_TENSOR, L.act_bits, si.n_dev, out=L.q_buf,
-                         act_scale=L.act_scale)
+                if not L.fused_q:
+                    am = L.act_amax if L.act_amax is not None else L.in_absmax
+                    self._op("quantize:" + L.name, 1, ops.quantize_rows, x, am, ops.QL_Q_CODES_PER_TENSOR, L.act_bits, si.n_dev, out=L.q_buf,
+                             act_scale=L.act_scale)
                 self._op("conv:" + L.name, 1, ops.spconv_mma, L.q_buf, nbr, so.cap, so.n_dev, L.cout, L.w, L.scale, L.shift, act_scale=L.act_scale, residual=res,
-                               relu=L.relu, out=L.out, absmax=absmax, kmask=kmask)
+                               relu=L.relu, out=L.out, absmax=absmax, kmask=kmask, out_q=L.out_q, out_qscale=L.out_qscale)
             elif L.kind == "cw":
                 am = L.act_amax if L.act_amax is not None else L.in_absmax
                 self._op("quantize:" + L.name, 1, ops.quantize_rows, x, am, ops.QL_Q_FAKE_PER_CHANNEL, L.act_bits, si.n_dev, out=L.q_buf)
                 self._op("conv:" + L.name, 1, ops.spconv_mma, L.q_buf, nbr, so.cap, so.n_dev, L.cout, L.w, L.scale, L.shift, residual=res, relu=L.relu, out=L.out,
-                               absmax=absmax, kmask=kmask)
+                               absmax=absmax, kmask=kmask, out_q=L.out_q, out_qscale=L.out_qscale)
             x = L.out
         if self.bev:
             last = self.stages[-1]

@@ -356,3 +356,43 @@ def test_voxelnext_backbone_module_path(quant):
     assert out["encoded_spconv_tensor_stride"] == 8
     for k in ("x_conv1", "x_conv2", "x_conv3"):
         assert np.array_equal(out["multi_scale_3d_features"][k].indices.cpu().numpy(), taps[k].coords)
+
+
+def test_engine_static_calibration_fuses_requantisation():
+    """static=True flow of the reference drivers (collect_stats -> compute_amax, quant/quantize.py:175-207) through the engine:
+    with frozen per-tensor amax every W8A8 layer but the first receives its int8 codes from the previous layer's epilogue."""
+    import qlidar
+    pts, feats, coords, grid, c = make_frame("waymo", batch=2)
+    prog, P, bb = build("VoxelResBackBone8x", 5, grid)
+    no_list = ["conv_input.0"]
+    qlidar.q_conv3d(bb, {}, "", 8, 8, False, (qlidar.SubMConv3d, qlidar.SparseConv3d), no_list)
+
+    class Pipe(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.backbone_3d = bb
+
+        def forward(self, bd):
+            return self.backbone_3d(bd)
+
+    qlidar.collect_stats(Pipe(), [batch_dict(feats, coords, 2)], n_batches=0)
+    qlidar.compute_amax(bb, torch.device("cuda"))
+    amax = {n[:-len(".act_quant")]: m.amax.detach().float().cpu().reshape(-1) for n, m in bb.named_modules() if n.endswith("act_quant")}
+    assert len(amax) == 20 and all(v.numel() == 1 and v.item() > 0 for v in amax.values())
+    ref, taps = O.backbone_forward(prog, P, feats, coords, O.sparse_shape_zyx(grid), 2,
+                                   O.QuantCfg(mode="ref", w_bits=8, act_bits=8, cw=False, no_list=tuple(no_list), act_amax=amax))
+    eng = qlidar.BackboneEngine(bb, 2, coords.shape[0] + 1000, max_points=pts.shape[0] + 500, pc_range=c["pc_range"],
+                                voxel_size=c["voxel_size"], max_pts_per_voxel=c["max_pts"], use_graph=True, stage_cap_ratio=4.0)
+    assert sum(L.fused_q for L in eng.layers) == 19                        # all but the first quantised layer (its input is the stem)
+    for _ in range(2):
+        out = eng.forward_points(torch.from_numpy(pts))
+    torch.cuda.synchronize()
+    counts = eng.counts()
+    assert not eng.overflowed() and counts[-1] == ref.coords.shape[0]
+    n = counts[-1]
+    assert np.array_equal(out["encoded_coords"][:n].cpu().numpy(), ref.coords)
+    check_feats(out["encoded_features"][:n], ref.features, True)
+    # and the eager module path with the same frozen amax agrees with the engine to the same bound
+    with torch.no_grad():
+        mod = bb(batch_dict(feats, coords, 2))["encoded_spconv_tensor"]
+    check_feats(out["encoded_features"][:n], mod.features.float().cpu(), True)
