@@ -111,11 +111,12 @@ def build_engine(device, max_points, w_bits=None, act_bits=None, cw=None):
                 m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.1); m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
     bb = bb.to(device).eval()
     qlidar.q_conv3d(bb, {}, "", w_bits, act_bits, cw, (qlidar.SubMConv3d, qlidar.SparseConv3d), NO_LIST)
-    # engine capacities are per BATCH (the reference caps each frame at MAX_NUMBER_OF_VOXELS = 150 000 in its CPU voxeliser);
-    # the synthetic frames hold 98 k - 160 k voxels depending on the seed, so leave 15 % head room: no frame is truncated
-    cap = int(1.15 * BATCH * c["max_voxels"])
+    # every frame is capped at MAX_NUMBER_OF_VOXELS = 150 000 voxels in first-touch order like the reference's per-frame CPU
+    # voxeliser (waymo_dataset.yaml:79-84; the synthetic frames hold 98 k - 160 k voxels depending on the seed), so the batch
+    # capacity BATCH * 150 000 can never overflow
+    cap = BATCH * c["max_voxels"]
     eng = qlidar.BackboneEngine(bb, BATCH, cap, max_points=max_points, pc_range=c["pc_range"], voxel_size=c["voxel_size"],
-                                max_pts_per_voxel=c["max_pts"], use_graph=True, device=device,
+                                max_pts_per_voxel=c["max_pts"], use_graph=True, device=device, max_voxels_per_frame=c["max_voxels"],
                                 stage_caps=[cap, int(1.25 * cap), int(0.75 * cap), int(0.5 * cap), int(0.5 * cap)])
     return eng, bb
 
@@ -332,9 +333,9 @@ def run_ours(args):
         qlidar.collect_stats(_Pipe(bb8), [calib], n_batches=0)
         qlidar.compute_amax(bb8, dev)
         c = __import__("qlidar").synth.CONFIGS["waymo"]
-        cap = int(1.15 * BATCH * c["max_voxels"])
+        cap = BATCH * c["max_voxels"]
         eng8s = qlidar.BackboneEngine(bb8, BATCH, cap, max_points=P, pc_range=c["pc_range"], voxel_size=c["voxel_size"],
-                                      max_pts_per_voxel=c["max_pts"], use_graph=True, device=dev,
+                                      max_pts_per_voxel=c["max_pts"], use_graph=True, device=dev, max_voxels_per_frame=c["max_voxels"],
                                       stage_caps=[cap, int(1.25 * cap), int(0.75 * cap), int(0.5 * cap), int(0.5 * cap)])
         sta = time_engine(eng8s)
         sta["fused_requantised_layers"] = int(sum(L.fused_q for L in eng8s.layers))

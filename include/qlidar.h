@@ -67,14 +67,16 @@ int ql_hash_build(const int32_t* coords, int64_t n_cap, const int32_t* n_dev,
  *      points: [n_points, point_stride] fp32; column 0 is the batch index when has_batch_col != 0, then x,y,z,
  *      then the remaining features (n_feat counts x,y,z).  Voxels are numbered in first-touch order over the
  *      point array (== spconv's CPU voxelizer); a voxel keeps its first `max_pts_per_voxel` points; voxels
- *      numbered >= max_voxels are dropped.  Outputs: out_feats [max_voxels, out_feat_stride >= n_feat] fp32 (mean; the pad
+ *      numbered >= max_voxels are dropped.  max_voxels_per_frame > 0 additionally keeps only the first that many voxels of
+ *      every frame (the reference voxelises frame by frame with MAX_NUMBER_OF_VOXELS each, data_processor.py:151-153); it needs
+ *      the points of a frame to be contiguous and the frames in ascending order (collate_batch's layout).  Outputs: out_feats [max_voxels, out_feat_stride >= n_feat] fp32 (mean; the pad
  *      columns are zero -- a stride of 8 lets ql_stem_conv fetch a row with one 256-bit load), out_coords
  *      [max_voxels, 4] int32, out_npts [max_voxels] int32, n_voxels_dev int32[2] = {rows kept, voxels found before
  *      the cap}, and the hash table coords -> row. */
 size_t ql_voxelize_workspace_bytes(int64_t max_points, int64_t max_voxels, int32_t n_feat, int32_t max_pts_per_voxel);
 int ql_voxelize_mean(const float* points, int64_t n_points, int32_t point_stride, int32_t has_batch_col, int32_t n_feat,
                      const float* range_min_xyz_host, const float* voxel_size_xyz_host, const int32_t* grid_xyz_host,
-                     int32_t batch_size, int32_t max_pts_per_voxel, int64_t max_voxels,
+                     int32_t batch_size, int32_t max_pts_per_voxel, int64_t max_voxels, int64_t max_voxels_per_frame,
                      float* out_feats, int32_t out_feat_stride, int32_t* out_coords, int32_t* out_npts, int32_t* n_voxels_dev,
                      uint64_t* table, int64_t table_cap, void* workspace, size_t workspace_bytes, ql_stream_t stream);
 /* MeanVFE on an already voxelized (V,T,F) tensor (mean_vfe.py:25-29); num_points is float32 when

@@ -20,6 +20,7 @@ namespace {
 constexpr int kThreads = QL_SCAN_THREADS;
 constexpr int kItems = 4;                       // points per thread in the scan passes
 constexpr int kBlockPts = kThreads * kItems;
+constexpr int kMaxFrames = 4096;                // frames per batch the per-frame voxel cap can track
 
 struct VoxParams {
     const float* points;
@@ -31,6 +32,8 @@ struct VoxParams {
     int max_pts;
     int64_t max_voxels;
     int out_stride;                             // floats per out_feats row (>= n_feat; the pad columns are written as zeros)
+    int64_t frame_cap;                          // > 0: at most this many voxels per frame (MAX_NUMBER_OF_VOXELS, first-touch order)
+    int* frames;                                // [3][B] ints: voxels found per frame, first provisional id, id shift
 };
 
 __device__ __forceinline__ bool point_cell(const VoxParams& P, int64_t p, int& b, int& cz, int& cy, int& cx) {
@@ -66,14 +69,68 @@ __device__ __forceinline__ bool is_first(const uint2* table, const uint32_t* pt_
     return s != 0xFFFFFFFFu && table[s].y == (uint32_t)p;
 }
 
-__global__ void k_vox_count(int64_t n, const uint2* table, const uint32_t* pt_slot, int* block_counts) {
+__global__ void k_vox_count(VoxParams P, const uint2* table, const uint32_t* pt_slot, int* block_counts) {
+    const int64_t n = P.n_points;
     int64_t base = (int64_t)blockIdx.x * kBlockPts + threadIdx.x * kItems;
     int c = 0;
+    bool f[kItems];
 #pragma unroll
-    for (int i = 0; i < kItems; ++i) c += is_first(table, pt_slot, base + i, n) ? 1 : 0;
+    for (int i = 0; i < kItems; ++i) {
+        f[i] = is_first(table, pt_slot, base + i, n);
+        c += f[i] ? 1 : 0;
+    }
+    if (P.frame_cap > 0) {
+        // voxels found per frame: runs of equal frame index are merged per thread, then per CTA in shared memory, so the
+        // global counters see a handful of atomics per CTA (a CTA's points belong to one or two frames)
+        constexpr int kHist = 64;
+        __shared__ int s_hist[kHist];
+        const int B = P.grid.B;
+        const bool use_smem = B <= kHist;
+        if (use_smem) {
+            for (int j = threadIdx.x; j < B; j += blockDim.x) s_hist[j] = 0;
+            __syncthreads();
+        }
+        int run_b = -1, run_c = 0;
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) {
+            if (!f[i]) continue;
+            const int b = P.has_b ? (int)P.points[(base + i) * P.stride] : 0;
+            if (b != run_b) {
+                if (run_c) atomicAdd(use_smem ? &s_hist[run_b] : &P.frames[run_b], run_c);
+                run_b = b; run_c = 0;
+            }
+            ++run_c;
+        }
+        if (run_c) atomicAdd(use_smem ? &s_hist[run_b] : &P.frames[run_b], run_c);
+        if (use_smem) {
+            __syncthreads();
+            for (int j = threadIdx.x; j < B; j += blockDim.x)
+                if (s_hist[j]) atomicAdd(&P.frames[j], s_hist[j]);
+        }
+    }
     int total;
     block_exclusive_scan(c, total);
     if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+}
+
+// per-frame cap: frame b's voxels hold the provisional (global first-touch) ids [F_b, F_b + cnt_b) when the points arrive
+// frame by frame; it keeps the first min(cnt_b, cap) of them and every kept id moves down by the voxels dropped before it
+__global__ void k_vox_frames(VoxParams P, int* n_voxels_dev) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int B = P.grid.B;
+    int* cnt = P.frames;
+    int* first = P.frames + B;
+    int* shift = P.frames + 2 * B;
+    int64_t run = 0, dropped = 0;
+    for (int b = 0; b < B; ++b) {
+        first[b] = (int)run;
+        shift[b] = (int)dropped;
+        const int64_t c = cnt[b];
+        run += c;
+        dropped += c > P.frame_cap ? c - P.frame_cap : 0;
+    }
+    const int64_t kept = run - dropped;
+    n_voxels_dev[0] = (int)(kept < P.max_voxels ? kept : P.max_voxels);
 }
 
 __global__ void k_vox_assign(VoxParams P, const uint2* table, const uint32_t* pt_slot, const int* block_offsets,
@@ -93,6 +150,11 @@ __global__ void k_vox_assign(VoxParams P, const uint2* table, const uint32_t* pt
         if (!f[i]) continue;
         int64_t p = base + i;
         int vid = ex++;
+        if (P.frame_cap > 0) {
+            const int b = P.has_b ? (int)P.points[p * P.stride] : 0;
+            const int64_t r = (int64_t)vid - P.frames[P.grid.B + b];
+            vid = (r >= 0 && r < P.frame_cap) ? vid - P.frames[2 * P.grid.B + b] : 0x7FFFFFFF;   // beyond the frame's cap: dropped
+        }
         pt_vid[p] = vid;
         if ((int64_t)vid < P.max_voxels) {
             vox_first[vid] = (uint32_t)p;
@@ -193,7 +255,7 @@ __global__ void k_hash_build(const int4* coords, int64_t n_cap, const int* n_dev
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct VoxWs {
-    size_t pt_slot, pt_vid, blocks, vox_first, tmin, sums, cnt, ntotal, total;
+    size_t pt_slot, pt_vid, blocks, vox_first, tmin, sums, cnt, ntotal, frames, total;
 };
 
 VoxWs vox_ws_layout(int64_t max_points, int64_t max_voxels, int n_feat, int max_pts) {
@@ -208,6 +270,7 @@ VoxWs vox_ws_layout(int64_t max_points, int64_t max_voxels, int n_feat, int max_
     w.sums = o; o += align256(max_pts > 0 ? 0 : (size_t)max_voxels * n_feat * 4);
     w.cnt = o; o += align256(max_pts > 0 ? 0 : (size_t)max_voxels * 4);
     w.ntotal = o; o += 256;
+    w.frames = o; o += align256((size_t)3 * kMaxFrames * 4);
     w.total = o;
     return w;
 }
@@ -241,15 +304,16 @@ extern "C" size_t ql_voxelize_workspace_bytes(int64_t max_points, int64_t max_vo
 
 extern "C" int ql_voxelize_mean(const float* points, int64_t n_points, int32_t point_stride, int32_t has_batch_col,
                                 int32_t n_feat, const float* range_min, const float* vsize, const int32_t* grid_xyz,
-                                int32_t batch_size, int32_t max_pts, int64_t max_voxels, float* out_feats,
-                                int32_t out_feat_stride, int32_t* out_coords, int32_t* out_npts, int32_t* n_voxels_dev, uint64_t* table,
+                                int32_t batch_size, int32_t max_pts, int64_t max_voxels, int64_t max_voxels_per_frame,
+                                float* out_feats, int32_t out_feat_stride, int32_t* out_coords, int32_t* out_npts, int32_t* n_voxels_dev, uint64_t* table,
                                 int64_t table_cap, void* workspace, size_t workspace_bytes, ql_stream_t stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (!points || !range_min || !vsize || !grid_xyz || !out_feats || !out_coords || !out_npts || !n_voxels_dev || !table ||
         !workspace)
         return QL_ERR_INVALID;
     if (n_feat < 3 || n_feat > 16 || point_stride < n_feat + (has_batch_col ? 1 : 0) || max_pts < 0 || max_voxels <= 0 ||
-        batch_size <= 0 || n_points < 0 || n_points >= 2147483647LL || out_feat_stride < n_feat)
+        batch_size <= 0 || n_points < 0 || n_points >= 2147483647LL || out_feat_stride < n_feat || max_voxels_per_frame < 0 ||
+        (max_voxels_per_frame > 0 && batch_size > kMaxFrames))
         return QL_ERR_INVALID;
     if (table_cap <= 0 || (table_cap & (table_cap - 1)) || table_cap < 2 * (n_points < max_voxels ? n_points : n_points))
         return QL_ERR_INVALID;  // the table must hold every distinct cell the points touch (<= n_points)
@@ -268,6 +332,8 @@ extern "C" int ql_voxelize_mean(const float* points, int64_t n_points, int32_t p
     P.gx = grid_xyz[0]; P.gy = grid_xyz[1]; P.gz = grid_xyz[2];
     P.grid = QlGrid{batch_size, D, grid_xyz[1], grid_xyz[0]};
     P.max_pts = max_pts; P.max_voxels = max_voxels;
+    P.frame_cap = max_voxels_per_frame;
+    P.frames = (int*)((char*)workspace + w.frames);
 
     char* ws = (char*)workspace;
     uint32_t* pt_slot = (uint32_t*)(ws + w.pt_slot);
@@ -294,8 +360,10 @@ extern "C" int ql_voxelize_mean(const float* points, int64_t n_points, int32_t p
     unsigned gp = (unsigned)((n_points + kThreads - 1) / kThreads);
     unsigned nb = (unsigned)((n_points + kBlockPts - 1) / kBlockPts);
     k_vox_insert<<<gp, kThreads, 0, st>>>(P, (uint2*)table, cap_mask, pt_slot);
-    k_vox_count<<<nb, kThreads, 0, st>>>(n_points, (const uint2*)table, pt_slot, blocks);
+    if (max_voxels_per_frame > 0 && cudaMemsetAsync(P.frames, 0, (size_t)3 * batch_size * 4, st) != cudaSuccess) return QL_ERR_CUDA;
+    k_vox_count<<<nb, kThreads, 0, st>>>(P, (const uint2*)table, pt_slot, blocks);
     k_scan_blocks<<<1, kThreads, 0, st>>>(blocks, (int)nb, n_voxels_dev + 1, n_voxels_dev, max_voxels);
+    if (max_voxels_per_frame > 0) k_vox_frames<<<1, 32, 0, st>>>(P, n_voxels_dev);
     k_vox_assign<<<nb, kThreads, 0, st>>>(P, (const uint2*)table, pt_slot, blocks, pt_vid, vox_first, out_coords);
     k_vox_gather<<<gp, kThreads, 0, st>>>(P, (const uint2*)table, pt_slot, pt_vid, tmin, sums, cnt);
     k_vox_drop<<<gp, kThreads, 0, st>>>(P, (uint2*)table, pt_slot, pt_vid);

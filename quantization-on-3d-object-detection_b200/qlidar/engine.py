@@ -85,10 +85,11 @@ class BackboneEngine:
     def __init__(self, backbone: nn.Module, batch_size: int, max_voxels: int, *, max_points: Optional[int] = None,
                  pc_range=None, voxel_size=None, max_pts_per_voxel: int = 5, n_point_features: Optional[int] = None,
                  bev: bool = True, bev_dtype=torch.float16, use_graph: bool = True, stage_cap_ratio: float = 1.0, stage_caps=None,
-                 device="cuda"):
+                 device="cuda", max_voxels_per_frame: int = 0):
         self.dev = torch.device(device)
         self.B = int(batch_size)
-        self.max_voxels = int(max_voxels)                 # total over the batch
+        self.max_voxels = int(max_voxels)                 # capacity, total over the batch
+        self.max_voxels_per_frame = int(max_voxels_per_frame)   # the reference's MAX_NUMBER_OF_VOXELS (0 = only the batch capacity)
         self.max_points = max_points
         self.pc_range, self.voxel_size, self.max_pts = pc_range, voxel_size, int(max_pts_per_voxel)
         self.bev, self.bev_dtype, self.use_graph = bev, bev_dtype, use_graph
@@ -334,8 +335,9 @@ class BackboneEngine:
     def _run_from_points(self):
         s0 = self.stages[0]
         self.kernels_per_forward = 0
-        self._op("voxelize_mean", 7, ops.voxelize_mean, self.points, self.pc_range, self.voxel_size, self.grid_xyz, self.B, self.max_pts, s0.cap,
-                 out=(self.vox_feats, s0.coords, self.vox_npts, s0.n_dev, s0.table), workspace=self.vox_ws)
+        self._op("voxelize_mean", 8 if self.max_voxels_per_frame else 7, ops.voxelize_mean, self.points, self.pc_range, self.voxel_size,
+                 self.grid_xyz, self.B, self.max_pts, s0.cap, out=(self.vox_feats, s0.coords, self.vox_npts, s0.n_dev, s0.table),
+                 workspace=self.vox_ws, max_voxels_per_frame=self.max_voxels_per_frame)
         self._run_backbone()
 
     def _replay(self, fn):
@@ -397,7 +399,10 @@ class BackboneEngine:
     def overflowed(self) -> bool:
         """True when a stage found more active sites than its capacity (rows were dropped): raise the capacities."""
         c = torch.stack([st.n_dev for st in self.stages]).cpu()
-        return bool((c[:, 1] > c[:, 0]).any().item())
+        over = c[:, 1] > c[:, 0]
+        if self.max_voxels_per_frame and self.stages[0].cap >= self.B * self.max_voxels_per_frame:
+            over[0] = False           # voxels beyond a frame's MAX_NUMBER_OF_VOXELS are dropped by design; the batch capacity cannot overflow
+        return bool(over.any().item())
 
     def profile_ops(self, from_points: bool = True, iters: int = 5, flush=None):
         """Eager (no graph) passes with every op bracketed by CUDA events on the launching stream.  A long spin kernel is

@@ -182,6 +182,28 @@ def test_voxelize_padded_feature_rows(ops):
     assert torch.equal(f1[:n, :5], f0[:n]) and (f1[:n, 5:] == 0).all()
 
 
+def test_voxelize_per_frame_voxel_cap(ops):
+    """MAX_NUMBER_OF_VOXELS is a per-FRAME cap in the reference (each frame goes through the CPU voxeliser on its own,
+    data_processor.py:151-153, then collate_batch concatenates): frames over the cap keep their first voxels in first-touch
+    order, frames under it are untouched, ids stay dense."""
+    c = O.CONFIGS["waymo"]
+    pts = O.synth_batch("waymo", 3, n_beams=20, n_az=400)
+    grid = O.grid_size_xyz(c["pc_range"], c["voxel_size"])
+    per_frame = [O.voxelize_hard(pts[pts[:, 0] == b][:, 1:], c["pc_range"], c["voxel_size"], c["max_pts"], 10 ** 7)[1].shape[0] for b in range(3)]
+    cap = sorted(per_frame)[1] - 7                                      # two frames over the cap, one under it
+    assert sum(v > cap for v in per_frame) == 2
+    feats_ref, coords_ref, _ = O.voxelize_mean_batch(pts, c["pc_range"], c["voxel_size"], c["max_pts"], cap)
+    f, co, npts, nd, table = ops.voxelize_mean(dev(pts), c["pc_range"], c["voxel_size"], grid, 3, c["max_pts"], 3 * cap + 100,
+                                               max_voxels_per_frame=cap)
+    n = int(nd[0].item())
+    assert n == coords_ref.shape[0] == sum(min(v, cap) for v in per_frame) and int(nd[1].item()) == sum(per_frame)
+    assert np.array_equal(co[:n].cpu().numpy(), coords_ref)
+    assert torch.equal(f[:n].cpu(), torch.from_numpy(feats_ref))
+    # the table knows exactly the kept voxels: a (1,1,1) submanifold rulebook hits every centre, and a dropped cell misses
+    nbr = ops.rulebook_subm(co, nd, (3, *O.sparse_shape_zyx(grid)), (1, 1, 1), table)
+    assert np.array_equal(tiles_to_nbr(nbr.cpu().numpy(), n)[0], np.arange(n))
+
+
 def test_voxelize_voxel_cap(ops):
     c = O.CONFIGS["kitti"]
     pts = O.synth_batch("kitti", 1, n_az=400)
