@@ -69,6 +69,7 @@ struct ConvParams {
     int wide;               // rows (and the feature base) are 32-byte aligned: gather with 256-bit loads
     int c_out, kvol, nseg, mask_words;
     uint32_t inv_nseg;      // ceil(65536 / nseg): ord = (sub * inv_nseg) >> 16 for sub < 4096
+    int pair;               // 16-byte rows (int8, C_in = 16): a sub-chunk holds TWO kernel offsets, 2j in bytes 0-15 and 2j+1 in 16-31
     const uint8_t* w_packed;
     const float* scale;
     const float* shift;
@@ -300,7 +301,8 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
             const uint8_t* const feats = p.feats;
             const uint8_t* const zero = g_zero_line;
             const bool wide = p.wide != 0;
-            const uint32_t nseg = (uint32_t)p.nseg, inv_nseg = p.inv_nseg, hdr = (uint32_t)p.nbr_hdr;
+            const uint32_t nseg = (uint32_t)p.nseg, inv_nseg = p.inv_nseg, hdr = (uint32_t)p.nbr_hdr, kvol = (uint32_t)p.kvol;
+            const bool pair = !kQuad && p.pair != 0;
 
             uint32_t g = team;                               // next global unit of this team
             uint32_t G0 = 0;                                 // global number of the current tile's first unit
@@ -316,6 +318,7 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
                 // one unit ahead, right after the previous unit's gathers have been issued, so that chain hides under them.
                 constexpr int kIdx = kQuad ? 4 * kGroup : kGroup;
                 int idx[kIdx];
+                int idx2[kQuad ? 1 : kGroup];                                         // pair mode: the row of kernel offset 2j+1
                 uint32_t boff[kGroup];
                 auto fetch_idx = [&](uint32_t c0) {
                     // the unit's kGroup table bytes (ordinal -> kernel offset) in one load
@@ -340,9 +343,16 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
                                 const int v = ql_lds_s32(a + (uint32_t)rr * 32u);
                                 idx[4 * j + rr] = live ? v : -1;
                             }
-                        } else {
+                        } else if (!pair) {
                             const int v = ql_lds_s32(a);
                             idx[j] = live ? v : -1;
+                        } else {
+                            // k is a PAIR of kernel offsets (2k, 2k+1): two slabs, two rows
+                            const uint32_t a2 = buf + hdr + (2u * k) * (QL_TILE_M * 4u) + row_off;
+                            const int v0 = ql_lds_s32(a2);
+                            const int v1 = (2u * k + 1u < kvol) ? ql_lds_s32(a2 + QL_TILE_M * 4u) : -1;
+                            idx[j] = live ? v0 : -1;
+                            idx2[j] = live ? v1 : -1;
                         }
                     }
                 };
@@ -385,9 +395,12 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
                             const uint8_t* src = ok ? feats + (uint64_t)(uint32_t)id * row_bytes : zero;
                             if (wide) {
                                 ldg32(src, v + j * 8);
-                            } else {
+                            } else if (!pair) {
                                 ldg16(src, v + j * 8);
                                 ldg16((ok && 16u < row_bytes) ? src + 16 : zero, v + j * 8 + 4);
+                            } else {
+                                ldg16(src, v + j * 8);
+                                ldg16(idx2[j] >= 0 ? feats + (uint64_t)(uint32_t)idx2[j] * row_bytes : zero, v + j * 8 + 4);
                             }
                         }
                     }
@@ -580,15 +593,36 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
         // ================================= loader =================================
         // Tile `tile` (the CTA's itn-th) -> rulebook buffer itn % nbr_bufs: header {mask, n_off, ord -> k table} written with
         // plain stores (released by the arrive below), then the tile's whole [kvol][128] block, one bulk copy per 16 KB.
-        auto prefetch_nbr = [&](int64_t tile, uint32_t itn, const uint32_t (&mask)[kMaskWords], int n_off) {
+        auto prefetch_nbr = [&](int64_t tile, uint32_t itn, const uint32_t (&mask)[kMaskWords], int n_off) {   // n_off: live offsets (pairs in pair mode)
             const uint32_t nb = itn & nbmask;
             const uint32_t bar = ql_smem_u32(&misc->nbr_full[nb]);
             const uint32_t dst = nbr_s0 + nb * nbr_stride;
             ql_mbar_wait(ql_smem_u32(&misc->nbr_empty[nb]), ((itn >> p.nbr_log2) & 1u) ^ 1u);
+            uint32_t vmask[kMaskWords];
+#pragma unroll
+            for (int i = 0; i < kMaskWords; ++i) vmask[i] = mask[i];
+            if (p.pair) {
+                // pair j is live when kernel offset 2j or 2j+1 is: lane l of pass i looks at pair 32*i + l
+                n_off = 0;
+#pragma unroll
+                for (int i = 0; i < kMaskWords; ++i) {
+                    const int vj = 32 * i + lane;                      // pair index; its two bits never straddle a word
+                    uint32_t word = 0u;
+                    if (2 * vj < 32 * kMaskWords) {
+                        word = mask[0];
+#pragma unroll
+                        for (int q2 = 1; q2 < kMaskWords; ++q2)
+                            if (((2 * vj) >> 5) == q2) word = mask[q2];
+                    }
+                    const bool on = 2 * vj < 32 * kMaskWords && ((word >> ((2 * vj) & 31)) & 3u) != 0u;
+                    vmask[i] = __ballot_sync(0xffffffffu, on);
+                    n_off += __popc(vmask[i]);
+                }
+            }
             int prefix = 0;
 #pragma unroll
             for (int i = 0; i < kMaskWords; ++i) {
-                const uint32_t w = mask[i];
+                const uint32_t w = vmask[i];
                 if (lane == i) sts_u32(dst + 4u * i, w);
                 if ((w >> lane) & 1u) sts_u8(dst + 32u + (uint32_t)(prefix + __popc(w & ((1u << lane) - 1u))), i * 32 + lane);
                 prefix += __popc(w);
@@ -699,11 +733,13 @@ inline int elem_size(int dtype) { return dtype == QL_S8 ? 1 : (dtype == QL_F16 ?
 struct ChunkGeom {
     int ch;      // bytes of K per chunk (32 / 64 / 128), zero padded when the row (segment) is shorter
     int nseg;    // chunks per kernel offset
+    int pair;    // 16-byte rows: one 32-byte chunk holds two consecutive kernel offsets (2j | 2j+1)
 };
 inline ChunkGeom chunk_geom(int row_bytes) {
     ChunkGeom g;
     if (row_bytes > 128) { g.ch = 128; g.nseg = (row_bytes + 127) / 128; }
     else { g.ch = row_bytes <= 32 ? 32 : (row_bytes <= 64 ? 64 : 128); g.nseg = 1; }
+    g.pair = row_bytes == 16 ? 1 : 0;
     return g;
 }
 // byte offset of 16-byte piece c16 of row r inside a K-major swizzled [rows x ch bytes] chunk image
@@ -739,7 +775,7 @@ extern "C" size_t ql_packed_weight_bytes(int32_t c_in, int32_t c_out, int32_t kv
     int es = elem_size(elem_dtype);
     if (es == 0 || c_in <= 0 || c_out <= 0 || kvol <= 0) return 0;
     const ChunkGeom g = chunk_geom(c_in * es);
-    return (size_t)kvol * g.nseg * (size_t)c_out * g.ch;
+    return (size_t)(g.pair ? (kvol + 1) / 2 : kvol) * g.nseg * (size_t)c_out * g.ch;
 }
 
 // w_host: [c_out][kvol][c_in] elements (== the reference layout (oc, kd, kh, kw, ic) flattened, quant/quant.py:37-39).
@@ -763,7 +799,10 @@ extern "C" int ql_pack_weights_host(const void* w_host, int32_t elem_dtype, int3
                 for (int c = 0; c < g.ch / 4; ++c) {
                     const int b = seg * 128 + 4 * k_word_src(g.ch, c);          // source byte of this 4-byte K word
                     if (b >= row_bytes) continue;                                // zero padding
-                    memcpy(dst + (size_t)(k * g.nseg + seg) * chunk_bytes + chunk_sw_offset(g.ch, (uint32_t)oc, (uint32_t)(c >> 2)) + 4 * (c & 3),
+                    // pair mode: offset k lives in chunk k/2, bytes 16*(k%2) .. +15 of the chunk row
+                    const size_t chunk = g.pair ? (size_t)(k / 2) : (size_t)(k * g.nseg + seg);
+                    const int cc = g.pair ? c + 4 * (k & 1) : c;
+                    memcpy(dst + chunk * chunk_bytes + chunk_sw_offset(g.ch, (uint32_t)oc, (uint32_t)(cc >> 2)) + 4 * (cc & 3),
                            src + ((size_t)oc * kvol + k) * row_bytes + b, 4);
                 }
     return QL_OK;
@@ -789,7 +828,8 @@ extern "C" int ql_spconv_mma(const void* feats, int32_t in_dtype, const int32_t*
     p.row_bytes = c_in * es; p.c_out = c_out; p.kvol = kvol;
     p.wide = (p.row_bytes % 32 == 0 && ((uintptr_t)feats & 31) == 0) ? 1 : 0;
     const ChunkGeom g = chunk_geom(p.row_bytes);
-    p.nseg = g.nseg; p.mask_words = (kvol + 31) / 32;
+    p.nseg = g.nseg; p.mask_words = (kvol + 31) / 32; p.pair = g.pair;
+    const int kv = g.pair ? (kvol + 1) / 2 : kvol;            // kernel offsets as the weight tensor / B descriptors see them
     p.w_packed = (const uint8_t*)w_packed; p.scale = scale; p.shift = shift; p.act_scale_dev = act_scale_dev;
     p.residual = (const __half*)residual_f16; p.relu = relu; p.out = out; p.out_dtype = out_dtype;
     p.out_q = out_q; p.out_qscale = out_qscale; p.absmax = absmax;
@@ -803,8 +843,8 @@ extern "C" int ql_spconv_mma(const void* feats, int32_t in_dtype, const int32_t*
     p.n_acc = (kTmemCols - 2 * c_out) / kUnitCols >= kTeams ? 2 : 1;
     int R = (kTmemCols - p.n_acc * c_out) / kUnitCols;
     if (R > kMaxUnits) R = kMaxUnits;
-    p.w_bytes = kvol * g.nseg * b_sub;
-    const int hdr_resident = kNbrHeaderMin + ((4 * kvol * g.nseg + 15) & ~15);
+    p.w_bytes = kv * g.nseg * b_sub;
+    const int hdr_resident = kNbrHeaderMin + ((4 * kv * g.nseg + 15) & ~15);
     for (p.nbr_bufs = 4; p.nbr_bufs >= 2; p.nbr_bufs >>= 1) {
         // try with the resident-weights header first; fall back to streamed weights (short header) if they do not fit
         p.nbr_hdr = hdr_resident;

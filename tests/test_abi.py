@@ -41,7 +41,7 @@ def test_host_only_entry_points():
     assert lib.ql_rulebook_mask_words(27) == 1 and lib.ql_rulebook_mask_words(125) == 4
     # chunk = one kernel offset x one <=128-byte row segment, padded to 32 / 64 / 128 bytes
     assert lib.ql_packed_weight_bytes(16, 16, 27, _lib.QL_F16) == 27 * 16 * 32
-    assert lib.ql_packed_weight_bytes(16, 16, 27, _lib.QL_S8) == 27 * 16 * 32       # 16-byte rows are zero padded to 32
+    assert lib.ql_packed_weight_bytes(16, 16, 27, _lib.QL_S8) == 14 * 16 * 32       # 16-byte rows: two kernel offsets per 32-byte chunk
     assert lib.ql_packed_weight_bytes(128, 64, 27, _lib.QL_F16) == 27 * 2 * 64 * 128
     assert lib.ql_packed_weight_bytes(15, 16, 27, _lib.QL_F32) == 0
 
@@ -79,6 +79,20 @@ def test_pack_weights_host_layout():
         raw = w.contiguous().view(torch.uint8).reshape(cout, K, -1).numpy()
         row_bytes = raw.shape[2]
         ch, nseg = _chunk_geom(row_bytes)
+        if row_bytes == 16:
+            # pair mode: chunk j = kernel offsets (2j | 2j+1), 16 bytes each, so that a K = 32 int8 MMA carries no padding
+            KV = (K + 1) // 2
+            assert packed.size == KV * cout * 32
+            for j in range(KV):
+                img = packed[j * cout * 32:(j + 1) * cout * 32]
+                for r in range(cout):
+                    x = (r // 4) % 2
+                    for half in range(2):
+                        off = (r // 8) * 256 + (r % 8) * 32 + ((half ^ x) * 16)
+                        k = 2 * j + half
+                        want = raw[r, k, :16] if k < K else np.zeros(16, np.uint8)
+                        assert np.array_equal(img[off:off + 16], want)
+            continue
         assert packed.size == K * nseg * cout * ch
         seen = np.zeros(packed.size, dtype=bool)
         for k in range(K):
