@@ -134,6 +134,20 @@ int ql_rulebook_subm_ranked(const int32_t* coords, int64_t n_cap, const int32_t*
                             const uint32_t* bitmap, const uint32_t* word_prefix,
                             int32_t* nbr_out, uint32_t* tile_kmask, ql_stream_t stream);
 
+/* ---- GROUPED submanifold rulebook (the counterpart of spconv's MaskImplicitGemm mask argsort, the GPU default the
+ *      reference runs with -- ConvAlgo.MaskImplicitGemm, tools/demo.ipynb:255).  The output rows are binned by a 9-bit line
+ *      key (which of the 3 x 3 kernel x-lines around the site hold any active cell), so that the rows of one 128-row MMA
+ *      tile share their live kernel offsets and the conv kernel skips the rest.  row_perm_out [tiles * 128]: tile slot ->
+ *      output row (-1 = padding of the last tile); nbr_out / tile_kmask are laid out by SLOT and must be consumed through
+ *      ql_spconv_mma_rows / ql_stem_conv_rows with the same row_perm.  Feature and coordinate arrays keep their row order:
+ *      results are bit-identical to the ungrouped rulebook's.  The slot order inside a bin is not deterministic. */
+size_t ql_rulebook_group_workspace_bytes(int64_t n_cap);
+int ql_rulebook_subm_ranked_grouped(const int32_t* coords, int64_t n_cap, const int32_t* n_dev,
+                                    int32_t B, int32_t D, int32_t H, int32_t W, const int32_t* ksize_host,
+                                    const uint32_t* bitmap, const uint32_t* word_prefix,
+                                    int32_t* nbr_out, uint32_t* tile_kmask, int32_t* row_perm_out,
+                                    void* workspace, size_t workspace_bytes, ql_stream_t stream);
+
 /* ---- implicit gather-GEMM-scatter sparse conv on tcgen05 tensor cores (replaces QConvNd.forward ->
  *      [EXT] spconv conv forward, quant/quant.py:36-58, plus the BatchNorm1d/ReLU/residual that follow it in
  *      post_act_block / SparseBasicBlock, spconv_backbone.py:8-27,51-67).
@@ -157,6 +171,21 @@ int ql_spconv_mma(const void* feats, int32_t in_dtype, const int32_t* nbr, const
                   const void* residual_f16, int32_t relu,
                   void* out, int32_t out_dtype, int8_t* out_q, const float* out_qscale, float* absmax,
                   ql_stream_t stream);
+/* the same through a grouped rulebook: row_perm [tiles * 128] maps a tile slot to the output row it computes (out,
+ * out_q, residual are indexed by ROW; nbr / tile_kmask by slot); row_perm == NULL is ql_spconv_mma.
+ * w_dtype: element type of w_packed -- in_dtype, or QL_S8 with in_dtype == QL_F16: COMPACT code weights
+ * (ql_compact_weights_host), accepted where the kernel streams the weights (ql_spconv_weights_streamed): W8A16 / W8A8-cw
+ * weights are int8 codes (quant/quant.py:42-44), so the per-tile weight stream, which paces the C >= 64 layers, moves one byte per
+ * element and two extra warps expand each sub-chunk to its fp16 shared-memory image (exact). */
+int32_t ql_spconv_weights_streamed(int32_t c_in, int32_t c_out, int32_t kvol, int32_t elem_dtype);
+int ql_compact_weights_host(const void* packed_f16_host, size_t packed_bytes, void* compact_host);
+int ql_spconv_mma_rows(const void* feats, int32_t in_dtype, const int32_t* nbr, const uint32_t* tile_kmask,
+                       const int32_t* row_perm, int64_t n_out_cap, const int32_t* n_out_dev,
+                       int32_t c_in, int32_t c_out, int32_t kvol, const void* w_packed, int32_t w_dtype,
+                       const float* scale, const float* shift, const float* act_scale_dev,
+                       const void* residual_f16, int32_t relu,
+                       void* out, int32_t out_dtype, int8_t* out_q, const float* out_qscale, float* absmax,
+                       ql_stream_t stream);
 
 /* ---- fp32 SIMT stem conv for the un-quantized conv_input (C_in = 4/5 raw point features; quant_centerpoint.py
  *      backbone_no_list = ['backbone_3d.conv_input.0'], :24-26).  feats rows are feat_stride floats apart;

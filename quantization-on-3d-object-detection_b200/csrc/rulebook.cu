@@ -96,20 +96,22 @@ __global__ void __launch_bounds__(QL_TILE_M) k_rb_pairs_ranked(const int4* __res
                                                                const uint32_t* __restrict__ bitmap,
                                                                const uint32_t* __restrict__ word_prefix, int* __restrict__ nbr,
                                                                uint32_t* __restrict__ kmask, int64_t n_in_cap,
-                                                               const int* __restrict__ n_in_dev) {
+                                                               const int* __restrict__ n_in_dev,
+                                                               const int* __restrict__ row_perm) {
     __shared__ uint32_t s_mask[QL_MASK_WORDS_MAX];
     const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
     const int64_t n_in = n_in_dev ? min((int64_t)*n_in_dev, n_in_cap) : n_in_cap;
     const int64_t tile = blockIdx.x;
     if (tile * QL_TILE_M >= n) return;
     const int r = threadIdx.x;
-    const int64_t row = tile * QL_TILE_M + r;
+    int64_t row = tile * QL_TILE_M + r;                              // tile slot; a grouped rulebook maps it to its output row
+    bool live = row < n;
+    if (row_perm && live) { row = row_perm[row]; live = row >= 0 && row < n; }
     const int K = cg.kd * cg.kh * cg.kw;
     int* dst = nbr + tile * (int64_t)K * QL_TILE_M + r;
     const int mask_words = (K + 31) >> 5;
     if (r < mask_words) s_mask[r] = 0u;
     __syncthreads();
-    const bool live = row < n;
     const int4 c = live ? coords[row] : make_int4(0, 0, 0, 0);      // b, z, y, x
     const int bz = c.y * cg.sd - cg.pd, by = c.z * cg.sh - cg.ph, bx = c.w * cg.sw - cg.pw;
     for (int kz = 0; kz < cg.kd; ++kz) {
@@ -438,7 +440,122 @@ extern "C" int ql_rulebook_subm_ranked(const int32_t* coords, int64_t n_cap, con
     QlGrid g{B, D, H, W};
     unsigned tiles = (unsigned)ql_rulebook_num_tiles(n_cap);
     k_rb_pairs_ranked<<<tiles, QL_TILE_M, 0, (cudaStream_t)stream_>>>((const int4*)coords, n_cap, n_dev, g, cg, bitmap, word_prefix,
-                                                                      nbr_out, tile_kmask, n_cap, n_dev);
+                                                                      nbr_out, tile_kmask, n_cap, n_dev, nullptr);
+    QL_CUDA_CHECK_LAST();
+    return QL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GROUPED submanifold rulebook.  The conv kernel's cost is the number of non-empty (tile, kernel offset) slabs, and with
+// 128 consecutive rows per tile nearly every offset is live in nearly every tile although a row has only 7-15 of its 27
+// neighbours.  spconv's MaskImplicitGemm sorts the outputs by their neighbour mask for the same reason.  Here the rows
+// are binned (counting sort, 512 bins) by a 9-bit LINE key -- bit (dz, dy) set iff any cell of the kernel's x-line at
+// (z + dz, y + dy) is active, dz, dy in {-1, 0, 1} -- which on LiDAR surfaces recovers almost all of what a full 27-bit
+// mask sort gives (synthetic Waymo frame, live offsets per tile: stage 1 27 -> 10.8 (full sort 9.5), stage 2 21.3 -> 17.7
+// (15.9)), costs 9 bitmap words per row, and needs no multi-pass radix sort.  Tile slot -> output row goes to row_perm;
+// the feature / coordinate arrays keep their order, only the tiling of the output rows changes, so results are
+// bit-identical to the ungrouped rulebook's (skipped slabs only ever added exact zeros).
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kGroupBins = 512;
+
+__device__ __forceinline__ uint32_t line_key(const int4& c, const QlGrid& g, const ConvGeom& cg, const uint32_t* __restrict__ bitmap) {
+    const int hx = cg.kw >> 1;
+    uint32_t key = 0u;
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz) {
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            if ((dz != 0 && cg.kd < 3) || (dy != 0 && cg.kh < 3)) continue;
+            const int z = c.y + dz, y = c.z + dy;
+            if (z < 0 || z >= g.D || y < 0 || y >= g.H) continue;
+            const int x0 = max(c.w - hx, 0), x1 = min(c.w + hx, g.W - 1);
+            const uint32_t k0 = ql_key(g, c.x, z, y, x0), k1 = k0 + (uint32_t)(x1 - x0);
+            // cells k0..k1 of the bitmap (at most two words for kw <= 32)
+            const uint32_t w0 = k0 >> 5, w1 = k1 >> 5;
+            uint32_t any;
+            if (w0 == w1) {
+                const uint32_t m = (0xFFFFFFFFu >> (31u - (k1 & 31u))) & (0xFFFFFFFFu << (k0 & 31u));
+                any = __ldg(bitmap + w0) & m;
+            } else {
+                any = (__ldg(bitmap + w0) & (0xFFFFFFFFu << (k0 & 31u))) | (__ldg(bitmap + w1) & (0xFFFFFFFFu >> (31u - (k1 & 31u))));
+            }
+            if (any) key |= 1u << ((dz + 1) * 3 + (dy + 1));
+        }
+    }
+    return key;
+}
+
+__global__ void __launch_bounds__(256) k_rb_linekey(const int4* __restrict__ coords, int64_t n_cap, const int* __restrict__ n_dev,
+                                                    QlGrid g, ConvGeom cg, const uint32_t* __restrict__ bitmap,
+                                                    uint16_t* __restrict__ keys, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_hist[kGroupBins];
+    const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
+    if ((int64_t)blockIdx.x * blockDim.x >= n) return;
+    for (int i = threadIdx.x; i < kGroupBins; i += blockDim.x) s_hist[i] = 0u;
+    __syncthreads();
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row < n) {
+        const uint32_t key = line_key(coords[row], g, cg, bitmap);
+        keys[row] = (uint16_t)key;
+        // neighbouring rows mostly share a key: one shared-memory atomic per distinct key of the warp
+        const uint32_t peers = __match_any_sync(__activemask(), key);
+        if ((threadIdx.x & 31) == __ffs((int)peers) - 1) atomicAdd(&s_hist[key], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kGroupBins; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
+}
+
+// hist holds the bins' first slots after the scan; every row takes the next slot of its bin
+__global__ void __launch_bounds__(256) k_rb_group_scatter(const uint16_t* __restrict__ keys, int64_t n_cap, const int* __restrict__ n_dev,
+                                                          uint32_t* __restrict__ cursor, int* __restrict__ row_perm) {
+    const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t slots = (n + QL_TILE_M - 1) / QL_TILE_M * QL_TILE_M;
+    if (row >= n) {
+        if (row < slots) row_perm[row] = -1;                         // padding of the last tile
+        return;
+    }
+    const uint32_t key = keys[row];
+    const uint32_t peers = __match_any_sync(__activemask(), key);
+    const int leader = __ffs((int)peers) - 1, lane = threadIdx.x & 31;
+    uint32_t base = 0u;
+    if (lane == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    row_perm[base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = (int)row;
+}
+}  // namespace
+
+extern "C" size_t ql_rulebook_group_workspace_bytes(int64_t n_cap) {
+    if (n_cap <= 0) return 0;
+    return align256((size_t)n_cap * 2) + align256((size_t)kGroupBins * 4);
+}
+
+extern "C" int ql_rulebook_subm_ranked_grouped(const int32_t* coords, int64_t n_cap, const int32_t* n_dev, int32_t B, int32_t D,
+                                               int32_t H, int32_t W, const int32_t* ksize, const uint32_t* bitmap,
+                                               const uint32_t* word_prefix, int32_t* nbr_out, uint32_t* tile_kmask,
+                                               int32_t* row_perm_out, void* workspace, size_t workspace_bytes, ql_stream_t stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    ConvGeom cg;
+    if (!coords || !bitmap || !word_prefix || !nbr_out || !row_perm_out || !workspace || !geom_from_host(ksize, nullptr, nullptr, cg))
+        return QL_ERR_INVALID;
+    if (!(cg.kd & 1) || !(cg.kh & 1) || !(cg.kw & 1) || cg.kw > 31) return QL_ERR_INVALID;
+    if ((double)B * D * H * W >= 4294967295.0) return QL_ERR_GRID_TOO_LARGE;
+    if (n_cap <= 0) return QL_OK;
+    if (n_cap >= 2147483647LL) return QL_ERR_INVALID;
+    if (workspace_bytes < ql_rulebook_group_workspace_bytes(n_cap)) return QL_ERR_WORKSPACE;
+    uint16_t* keys = (uint16_t*)workspace;
+    uint32_t* hist = (uint32_t*)((char*)workspace + align256((size_t)n_cap * 2));
+    QlGrid g{B, D, H, W};
+    const unsigned tiles = (unsigned)ql_rulebook_num_tiles(n_cap);
+    const unsigned blocks = (unsigned)((tiles * (int64_t)QL_TILE_M + 255) / 256);       // covers the padding slots of the last tile
+    if (cudaMemsetAsync(hist, 0, (size_t)kGroupBins * 4, st) != cudaSuccess) return QL_ERR_CUDA;
+    k_rb_linekey<<<blocks, 256, 0, st>>>((const int4*)coords, n_cap, n_dev, g, cg, bitmap, keys, hist);
+    k_scan_blocks<<<1, QL_SCAN_THREADS, 0, st>>>((int*)hist, kGroupBins, nullptr, nullptr, 0);
+    k_rb_group_scatter<<<blocks, 256, 0, st>>>(keys, n_cap, n_dev, hist, row_perm_out);
+    k_rb_pairs_ranked<<<tiles, QL_TILE_M, 0, st>>>((const int4*)coords, n_cap, n_dev, g, cg, bitmap, word_prefix, nbr_out, tile_kmask,
+                                                   n_cap, n_dev, row_perm_out);
     QL_CUDA_CHECK_LAST();
     return QL_OK;
 }
@@ -617,7 +734,7 @@ extern "C" int ql_rulebook_strided_ranked(const int32_t* in_coords, int64_t n_in
     QlGrid gin_grid{B, D, H, W};
     k_rb_pairs_ranked<<<(unsigned)ql_rulebook_num_tiles(n_out_cap), QL_TILE_M, 0, st>>>((const int4*)out_coords, n_out_cap, n_out_dev,
                                                                                         gin_grid, cg, in_bitmap, in_word_prefix, nbr_out,
-                                                                                        tile_kmask, n_in_cap, n_in_dev);
+                                                                                        tile_kmask, n_in_cap, n_in_dev, nullptr);
     QL_CUDA_CHECK_LAST();
     return QL_OK;
 }

@@ -85,7 +85,7 @@ class BackboneEngine:
     def __init__(self, backbone: nn.Module, batch_size: int, max_voxels: int, *, max_points: Optional[int] = None,
                  pc_range=None, voxel_size=None, max_pts_per_voxel: int = 5, n_point_features: Optional[int] = None,
                  bev: bool = True, bev_dtype=torch.float16, use_graph: bool = True, stage_cap_ratio: float = 1.0, stage_caps=None,
-                 device="cuda", max_voxels_per_frame: int = 0):
+                 device="cuda", max_voxels_per_frame: int = 0, group_rows: bool = False, compact_weights: bool = False):
         self.dev = torch.device(device)
         self.B = int(batch_size)
         self.max_voxels = int(max_voxels)                 # capacity, total over the batch
@@ -93,6 +93,12 @@ class BackboneEngine:
         self.max_points = max_points
         self.pc_range, self.voxel_size, self.max_pts = pc_range, voxel_size, int(max_pts_per_voxel)
         self.bev, self.bev_dtype, self.use_graph = bev, bev_dtype, use_graph
+        # Two measured options, both OFF by default: grouped submanifold rulebooks on the ranked stages (fewer live
+        # (tile, offset) slabs, but the gathers lose their L1 locality and the binning costs ~28 us per stage: net loss on the
+        # Waymo batch) and int8 storage of streamed code weights for fp16 activations (halves the L2 -> SM weight stream, but
+        # the shared-memory expansion pass is slower than the stream it replaces).
+        self.group_rows = bool(group_rows)
+        self.compact_weights = bool(compact_weights)
         self.sparse_shape = list(backbone.sparse_shape)
         self.grid_xyz = [self.sparse_shape[2], self.sparse_shape[1], self.sparse_shape[0] - 1]
         self.layers: List[Layer] = []
@@ -142,10 +148,10 @@ class BackboneEngine:
             if qw is None or L.act_bits > 8:
                 L.kind = "f16"
                 wt = conv.weight.detach().float().reshape(cout, K, cin).cpu() if codes is None else codes.cpu()
-                L.w = ops.pack_weights(wt.to(torch.float16)).to(self.dev)
+                L.w = self._pack_f16(wt, cin, cout, K, codes is not None)
             elif qw.cw or qw.per_row:
                 L.kind = "cw"
-                L.w = ops.pack_weights(codes.cpu().to(torch.float16)).to(self.dev)
+                L.w = self._pack_f16(codes.cpu(), cin, cout, K, True)
             else:
                 L.kind = "i8"
                 L.w = ops.pack_weights(codes.cpu().to(torch.int8)).to(self.dev)
@@ -167,6 +173,13 @@ class BackboneEngine:
             L.rb_key = ("strided", L.stage_in, L.ksize, L.stride, L.pad)
         self.layers.append(L)
         return L
+
+    def _pack_f16(self, wt, cin, cout, K, is_codes):
+        """fp16 weight image; int8-code weights of a layer whose weights are streamed are stored compact (one byte per code)."""
+        packed = ops.pack_weights(wt.to(torch.float16))
+        if is_codes and self.compact_weights and ops.weights_streamed(cin, cout, K, torch.float16):
+            packed = ops.compact_weights(packed)
+        return packed.to(self.dev)
 
     def _compile(self, bb):
         def seq_conv_bn_relu(prefix, seq):
@@ -226,6 +239,8 @@ class BackboneEngine:
                 w = z(ops.rulebook_strided_workspace_bytes(gi, L.ksize, L.stride, L.pad), dt=torch.uint8)
                 self.stages[L.stage_out].rank = ops.rulebook_strided_index(gi, L.ksize, L.stride, L.pad, w)
         self.kmasks: Dict[tuple, torch.Tensor] = {}
+        self.row_perms: Dict[tuple, Optional[torch.Tensor]] = {}
+        self.group_ws = None
         n_abs = sum(L.cout for L in self.layers) + 256
         self.absmax_pool = z(n_abs, dt=torch.float32)
         off = 0
@@ -236,6 +251,12 @@ class BackboneEngine:
                 K = int(np.prod(L.ksize))
                 self.rulebooks[L.rb_key] = z(ops.num_tiles(so.cap), K, ops.TILE_M, dt=torch.int32)
                 self.kmasks[L.rb_key] = z(ops.num_tiles(so.cap), ops.mask_words(K), dt=torch.int32)
+                self.row_perms[L.rb_key] = None
+                if self.group_rows and L.subm and self.stages[L.stage_in].rank is not None and L.ksize[2] <= 31:
+                    self.row_perms[L.rb_key] = z(ops.num_tiles(so.cap) * ops.TILE_M, dt=torch.int32)
+                    nb = int(ops.lib().ql_rulebook_group_workspace_bytes(so.cap))
+                    if self.group_ws is None or self.group_ws.numel() < nb:
+                        self.group_ws = z(nb, dt=torch.uint8)
             L.out = z(so.cap, L.cout)
             L.out_absmax = self.absmax_pool[off:off + L.cout]
             off += L.cout
@@ -292,9 +313,13 @@ class BackboneEngine:
             self.absmax_pool.zero_()
         for i, L in enumerate(self.layers):
             si, so = self.stages[L.stage_in], self.stages[L.stage_out]
-            nbr, kmask = self.rulebooks[L.rb_key], self.kmasks[L.rb_key]
+            nbr, kmask, perm = self.rulebooks[L.rb_key], self.kmasks[L.rb_key], self.row_perms[L.rb_key]
             if L.rb_key not in built:
-                if L.subm and si.rank is not None:
+                if perm is not None:
+                    # kernels: line keys + histogram, bin scan, slot scatter, ranked pairs
+                    self._op("rulebook_subm:" + L.name, 4, ops.rulebook_subm_ranked_grouped, si.coords, si.n_dev, si.grid, L.ksize, si.rank,
+                             nbr=nbr, kmask=kmask, row_perm=perm, workspace=self.group_ws)
+                elif L.subm and si.rank is not None:
                     self._op("rulebook_subm:" + L.name, 1, ops.rulebook_subm_ranked, si.coords, si.n_dev, si.grid, L.ksize, si.rank, nbr=nbr, kmask=kmask)
                 elif L.subm:
                     self._op("rulebook_subm:" + L.name, 1, ops.rulebook_subm, si.coords, si.n_dev, si.grid, L.ksize, si.table, nbr=nbr, kmask=kmask)
@@ -308,22 +333,24 @@ class BackboneEngine:
                 block_in = x
             res = block_in if L.residual else None
             if L.kind == "stem":
+                if perm is not None:
+                    raise QlidarError("the stem conv does not take a grouped rulebook")
                 self._op("stem:" + L.name, 1, ops.stem_conv, x, nbr, so.cap, so.n_dev, L.w, L.scale, L.shift, relu=L.relu, out=L.out, absmax=absmax)
             elif L.kind == "f16":
                 self._op("conv:" + L.name, 1, ops.spconv_mma, x, nbr, so.cap, so.n_dev, L.cout, L.w, L.scale, L.shift, residual=res,
-                         relu=L.relu, out=L.out, absmax=absmax, kmask=kmask, out_q=L.out_q, out_qscale=L.out_qscale)
+                         relu=L.relu, out=L.out, absmax=absmax, kmask=kmask, out_q=L.out_q, out_qscale=L.out_qscale, row_perm=perm)
             elif L.kind == "i8":
                 if not L.fused_q:
                     am = L.act_amax if L.act_amax is not None else L.in_absmax
                     self._op("quantize:" + L.name, 1, ops.quantize_rows, x, am, ops.QL_Q_CODES_PER_TENSOR, L.act_bits, si.n_dev, out=L.q_buf,
                              act_scale=L.act_scale)
                 self._op("conv:" + L.name, 1, ops.spconv_mma, L.q_buf, nbr, so.cap, so.n_dev, L.cout, L.w, L.scale, L.shift, act_scale=L.act_scale, residual=res,
-                               relu=L.relu, out=L.out, absmax=absmax, kmask=kmask, out_q=L.out_q, out_qscale=L.out_qscale)
+                               relu=L.relu, out=L.out, absmax=absmax, kmask=kmask, out_q=L.out_q, out_qscale=L.out_qscale, row_perm=perm)
             elif L.kind == "cw":
                 am = L.act_amax if L.act_amax is not None else L.in_absmax
                 self._op("quantize:" + L.name, 1, ops.quantize_rows, x, am, ops.QL_Q_FAKE_PER_CHANNEL, L.act_bits, si.n_dev, out=L.q_buf)
                 self._op("conv:" + L.name, 1, ops.spconv_mma, L.q_buf, nbr, so.cap, so.n_dev, L.cout, L.w, L.scale, L.shift, residual=res, relu=L.relu, out=L.out,
-                               absmax=absmax, kmask=kmask, out_q=L.out_q, out_qscale=L.out_qscale)
+                               absmax=absmax, kmask=kmask, out_q=L.out_q, out_qscale=L.out_qscale, row_perm=perm)
             x = L.out
         if self.bev:
             last = self.stages[-1]

@@ -168,6 +168,32 @@ def rulebook_subm_ranked(coords: torch.Tensor, n_dev: Optional[torch.Tensor], gr
     return nbr, kmask
 
 
+def rulebook_subm_ranked_grouped(coords: torch.Tensor, n_dev: Optional[torch.Tensor], grid, ksize, index: RankIndex,
+                                 nbr: Optional[torch.Tensor] = None, kmask: Optional[torch.Tensor] = None,
+                                 row_perm: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
+    """Grouped submanifold rulebook (rows binned by their 9-bit line key so a tile's rows share live offsets).
+    Returns (nbr, kmask, row_perm): nbr / kmask are indexed by tile SLOT, row_perm [tiles * 128] maps slot -> output row."""
+    _need_cuda(coords, n_dev, nbr, kmask, row_perm, workspace)
+    k = triple(ksize)
+    K = k[0] * k[1] * k[2]
+    n_cap = coords.shape[0]
+    dev = coords.device
+    if nbr is None:
+        nbr = torch.empty((num_tiles(n_cap), K, TILE_M), dtype=torch.int32, device=dev)
+    if kmask is None:
+        kmask = torch.zeros((num_tiles(n_cap), mask_words(K)), dtype=torch.int32, device=dev)
+    if row_perm is None:
+        row_perm = torch.empty((num_tiles(n_cap) * TILE_M,), dtype=torch.int32, device=dev)
+    ws_bytes = int(lib().ql_rulebook_group_workspace_bytes(n_cap))
+    if workspace is None or workspace.numel() < ws_bytes:
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    B, D, H, W = [int(v) for v in grid]
+    check(lib().ql_rulebook_subm_ranked_grouped(_ptr(coords), n_cap, _ptr(n_dev), B, D, H, W, _i32x3(k), C.c_void_p(index.bitmap_ptr),
+                                                C.c_void_p(index.prefix_ptr), _ptr(nbr), _ptr(kmask), _ptr(row_perm), _ptr(workspace),
+                                                workspace.numel(), _stream()), "ql_rulebook_subm_ranked_grouped")
+    return nbr, kmask, row_perm
+
+
 def rulebook_strided_workspace_bytes(grid, ksize, stride, pad) -> int:
     B, D, H, W = [int(v) for v in grid]
     n = int(lib().ql_rulebook_strided_workspace_bytes(B, D, H, W, _i32x3(triple(ksize)), _i32x3(triple(stride)), _i32x3(triple(pad))))
@@ -270,14 +296,37 @@ def pack_weights(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def weights_streamed(c_in: int, c_out: int, kvol: int, dtype: torch.dtype = torch.float16) -> bool:
+    """True when the conv kernel streams this layer's weights per tile (they do not fit in shared memory)."""
+    return bool(lib().ql_spconv_weights_streamed(int(c_in), int(c_out), int(kvol), _DT[dtype]))
+
+
+def compact_weights(packed_f16: torch.Tensor) -> torch.Tensor:
+    """Packed fp16 image of integer CODE weights (pack_weights of a float16 tensor) -> the same image with one int8 per
+    element (dtype torch.int8, half the bytes): the form ql_spconv_mma_rows takes with w_dtype = QL_S8 for fp16 activations."""
+    if packed_f16.is_cuda:
+        packed_f16 = packed_f16.cpu()
+    packed_f16 = packed_f16.contiguous()
+    if packed_f16.dtype != torch.uint8:
+        raise QlidarError("compact_weights expects the uint8 image returned by pack_weights")
+    out = torch.empty(packed_f16.numel() // 2, dtype=torch.int8)
+    check(lib().ql_compact_weights_host(C.c_void_p(packed_f16.data_ptr()), packed_f16.numel(), C.c_void_p(out.data_ptr())),
+          "ql_compact_weights_host")
+    return out
+
+
 def spconv_mma(feats: torch.Tensor, nbr: torch.Tensor, n_out_cap: int, n_out_dev: Optional[torch.Tensor], c_out: int,
                w_packed: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, *, act_scale: Optional[torch.Tensor] = None,
                residual: Optional[torch.Tensor] = None, relu: bool = False, out: Optional[torch.Tensor] = None,
                out_dtype: torch.dtype = torch.float16, out_q: Optional[torch.Tensor] = None,
                out_qscale: Optional[torch.Tensor] = None, absmax: Optional[torch.Tensor] = None,
-               kmask: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """kmask: the rulebook's per-tile offset mask [tiles, ceil(K/32)] int32 (None = visit every offset)."""
-    _need_cuda(feats, nbr, n_out_dev, w_packed, scale, shift, act_scale, residual, out, out_q, out_qscale, absmax, kmask)
+               kmask: Optional[torch.Tensor] = None, row_perm: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """kmask: the rulebook's per-tile offset mask [tiles, ceil(K/32)] int32 (None = visit every offset).
+    row_perm: slot -> output row table of a grouped rulebook (rulebook_subm_ranked_grouped).
+    w_packed: the uint8 image from pack_weights, or (fp16 activations) the int8 image from compact_weights."""
+    _need_cuda(feats, nbr, n_out_dev, w_packed, scale, shift, act_scale, residual, out, out_q, out_qscale, absmax, kmask, row_perm)
+    if row_perm is not None and (row_perm.dtype != torch.int32 or row_perm.numel() < num_tiles(n_out_cap) * TILE_M):
+        raise QlidarError("row_perm must be int32 [tiles * 128]")
     if feats.dtype not in (torch.float16, torch.int8):
         raise QlidarError("spconv_mma gathers float16 rows or int8 codes")
     if residual is not None and residual.dtype != torch.float16:
@@ -291,9 +340,10 @@ def spconv_mma(feats: torch.Tensor, nbr: torch.Tensor, n_out_cap: int, n_out_dev
         raise QlidarError("out must be float16/float32 (or int32 for the raw accumulators)")
     if kmask is not None and (kmask.dtype != torch.int32 or kmask.shape[0] < num_tiles(n_out_cap) or kmask.shape[1] != mask_words(K)):
         raise QlidarError("kmask must be int32 [tiles, ceil(K/32)]")
-    check(lib().ql_spconv_mma(_ptr(feats), _DT[feats.dtype], _ptr(nbr), _ptr(kmask), int(n_out_cap), _ptr(n_out_dev), c_in, int(c_out), K,
-                              _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(act_scale), _ptr(residual), 1 if relu else 0,
-                              _ptr(out), _DT[out.dtype], _ptr(out_q), _ptr(out_qscale), _ptr(absmax), _stream()), "ql_spconv_mma")
+    check(lib().ql_spconv_mma_rows(_ptr(feats), _DT[feats.dtype], _ptr(nbr), _ptr(kmask), _ptr(row_perm), int(n_out_cap), _ptr(n_out_dev),
+                                   c_in, int(c_out), K, _ptr(w_packed), QL_S8 if w_packed.dtype == torch.int8 else _DT[feats.dtype], _ptr(scale), _ptr(shift), _ptr(act_scale), _ptr(residual),
+                                   1 if relu else 0, _ptr(out), _DT[out.dtype], _ptr(out_q), _ptr(out_qscale), _ptr(absmax), _stream()),
+          "ql_spconv_mma_rows")
     return out
 
 

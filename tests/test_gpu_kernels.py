@@ -295,6 +295,89 @@ def test_spconv_f16_matches_fp64_oracle(ops, cin, cout, ksize, subm, stride, pad
     assert err <= 1e-4 * ref.abs().max().item(), err
 
 
+def _ranked_stage(ops, coords, grid):
+    """Key-sorted stage + rank index from a 1x1x1 stride-1 'strided' build over the given sites."""
+    B, D, H, W = grid
+    n = coords.shape[0]
+    ws = torch.zeros(ops.rulebook_strided_workspace_bytes(grid, 1, 1, 0), dtype=torch.uint8, device="cuda")
+    oc, n_out, _, _, ogrid, _ = ops.rulebook_strided(dev(coords), None, grid, 1, 1, 0, n, out=None, workspace=ws)
+    assert n_out.tolist() == [n, n] and tuple(ogrid) == tuple(grid)
+    return oc, n_out, ops.rulebook_strided_index(grid, 1, 1, 0, ws)
+
+
+@pytest.mark.parametrize("ksub", [3, (3, 1, 1), (1, 3, 3), 5])
+def test_rulebook_subm_grouped_is_a_row_permutation_of_the_plain_rulebook(ops, ksub):
+    """Grouped rulebook (rows binned by line key): row_perm is a permutation of the live rows (-1 padding), slot s holds
+    exactly the plain rulebook's column of row row_perm[s] (so the pairs, compared in row space, are bit-exact against
+    the oracle), the per-tile masks match the slots, and on a surface-like input the tiles need fewer live offsets."""
+    S = 180
+    coords = O.synth_surface_sheet(S, seed=11, depth=12)
+    grid = (1, 12, S, S)
+    oc, n_out, index = _ranked_stage(ops, coords, grid)
+    n = coords.shape[0]
+    oc_np = oc[:n].cpu().numpy()
+    ref = O.rulebook_subm(oc_np, list(grid[1:]), ksub)                       # (K, n), rows in key order
+    nbr_p, kmask_p = ops.rulebook_subm_ranked(oc, n_out, grid, ksub, index)
+    assert np.array_equal(tiles_to_nbr(nbr_p.cpu().numpy(), n), ref)
+    nbr_g, kmask_g, perm = ops.rulebook_subm_ranked_grouped(oc, n_out, grid, ksub, index)
+    tiles = (n + 127) // 128
+    perm_np = perm[:tiles * 128].cpu().numpy()
+    assert np.array_equal(np.sort(perm_np[:n]), np.arange(n)) and (perm_np[n:] == -1).all()
+    g = tiles_to_nbr(nbr_g.cpu().numpy(), tiles * 128)                       # (K, slots)
+    assert np.array_equal(g[:, :n], ref[:, perm_np[:n]]) and (g[:, n:] == -1).all()
+    km = kmask_g[:tiles].cpu().numpy().view(np.uint32)
+    assert np.array_equal(km, O.tile_kmask(g))
+    live = lambda m: sum(bin(int(v)).count("1") for v in m.ravel())
+    if np.prod(O._triple(ksub)) == 27:
+        assert live(km) < 0.8 * live(kmask_p[:tiles].cpu().numpy().view(np.uint32)), (live(km), live(kmask_p[:tiles].cpu().numpy().view(np.uint32)))
+    # a device-side row count below the capacity: only the live rows are placed
+    n_small = torch.tensor([n - 300, n], dtype=torch.int32, device="cuda")
+    _, _, perm2 = ops.rulebook_subm_ranked_grouped(oc, n_small, grid, ksub, index)
+    p2 = perm2.cpu().numpy()
+    t2 = (n - 300 + 127) // 128
+    assert np.array_equal(np.sort(p2[:n - 300]), np.arange(n - 300)) and (p2[n - 300:t2 * 128] == -1).all()
+
+
+@pytest.mark.parametrize("cin,cout,int8", [(16, 16, True), (16, 16, False), (32, 32, False), (64, 64, True), (128, 128, False)])
+def test_spconv_through_grouped_rulebook_is_bit_identical(ops, cin, cout, int8):
+    """ql_spconv_mma_rows through a grouped rulebook == ql_spconv_mma through the plain one, bit for bit (outputs, fused
+    int8 re-quantisation, residual, abs-max), and the int32 accumulators equal the oracle's."""
+    rng = np.random.default_rng(5 + cin)
+    S = 200
+    coords = O.synth_surface_sheet(S, seed=3, depth=10)
+    grid = (1, 10, S, S)
+    oc, n_out, index = _ranked_stage(ops, coords, grid)
+    n = coords.shape[0]
+    nbr_p, kmask_p = ops.rulebook_subm_ranked(oc, n_out, grid, 3, index)
+    nbr_g, kmask_g, perm = ops.rulebook_subm_ranked_grouped(oc, n_out, grid, 3, index)
+    scale = torch.from_numpy(rng.uniform(0.5, 1.5, cout).astype(np.float32)).cuda() * 1e-3
+    shift = torch.from_numpy(rng.normal(size=cout).astype(np.float32)).cuda()
+    qw = torch.from_numpy(rng.integers(-127, 128, size=(cout, 27, cin)).astype(np.int8))
+    if int8:
+        x = torch.from_numpy(rng.integers(-127, 128, size=(n, cin)).astype(np.int8)).cuda()
+        w = ops.pack_weights(qw).cuda()
+        acc = torch.zeros((n, cout), dtype=torch.int32, device="cuda")
+        ops.spconv_mma(x, nbr_g, n, n_out, cout, w, torch.ones(cout, device="cuda"), torch.zeros(cout, device="cuda"), out=acc, kmask=kmask_g, row_perm=perm)
+        ref = O.sparse_conv_int(x.cpu(), tiles_to_nbr(nbr_p.cpu().numpy(), n), qw.reshape(cout, 3, 3, 3, cin))
+        assert torch.equal(acc.cpu(), ref)
+    else:
+        x = torch.from_numpy(rng.normal(size=(n, cin)).astype(np.float32)).half().cuda()
+        w = ops.pack_weights(qw.half()).cuda()
+    res = torch.from_numpy(rng.normal(size=(n, cout)).astype(np.float32)).half().cuda()
+    qs = torch.full((cout,), 20.0, device="cuda")
+    outs = []
+    for nbr, km, pm in ((nbr_p, kmask_p, None), (nbr_g, kmask_g, perm)):
+        out = torch.zeros((n, cout), dtype=torch.float16, device="cuda")
+        out_q = torch.zeros((n, cout), dtype=torch.int8, device="cuda")
+        am = torch.zeros(cout, device="cuda")
+        ops.spconv_mma(x, nbr, n, n_out, cout, w, scale, shift, residual=res, relu=True, out=out, out_q=out_q, out_qscale=qs, absmax=am,
+                       kmask=km, row_perm=pm)
+        outs.append((out, out_q, am))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    assert outs[0][0].abs().sum().item() > 0
+
+
 @pytest.mark.parametrize("cin,cout,int8", [(16, 16, True), (32, 32, False), (64, 64, True), (128, 128, False)])
 def test_spconv_many_tiles_per_cta_with_offset_mask(ops, cin, cout, int8):
     """> 3 tiles per persistent CTA (148 SMs) so the A/B ring and the accumulator double buffer wrap many times, through
@@ -331,6 +414,47 @@ def test_spconv_many_tiles_per_cta_with_offset_mask(ops, cin, cout, int8):
         out = ops.spconv_mma(dev(x), nbr, N, None, cout, ops.pack_weights(qw.half()).cuda(), one, zero, out_dtype=torch.float32, kmask=kmask)
         err = (out.cpu().double() - ref).abs().max().item()
         assert err <= 1e-4 * ref.abs().max().item(), err
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 64), (128, 128), (64, 128), (128, 256), (256, 256)])
+def test_spconv_compact_code_weights_are_bit_identical(ops, cin, cout):
+    """Streamed layers: int8-stored code weights (ql_compact_weights_host), expanded to fp16 in the kernel, give the
+    same bits as the fp16 image; resident layers refuse the compact form."""
+    rng = np.random.default_rng(90 + cin + cout)
+    S = 160
+    coords = O.synth_surface_sheet(S, seed=5, depth=8)
+    N = coords.shape[0]
+    c = dev(coords)
+    table = ops.hash_build(c, None, (1, 8, S, S))
+    nbr, kmask = ops.rulebook_subm(c, None, (1, 8, S, S), 3, table, with_mask=True)
+    x = torch.from_numpy(rng.normal(size=(N, cin)).astype(np.float32)).half().cuda()
+    qw = torch.from_numpy(rng.integers(-127, 128, size=(cout, 27, cin)).astype(np.int8))
+    qw[0, 0, 0], qw[1, 0, 0], qw[2, 0, 0] = 127, -127, 0
+    scale = torch.full((cout,), 1e-3, device="cuda")
+    shift = torch.zeros(cout, device="cuda")
+    assert ops.weights_streamed(cin, cout, 27)
+    w16 = ops.pack_weights(qw.half())
+    w8 = ops.compact_weights(w16)
+    assert w8.dtype == torch.int8 and w8.numel() * 2 == w16.numel()
+    a = ops.spconv_mma(x, nbr, N, None, cout, w16.cuda(), scale, shift, out_dtype=torch.float32, kmask=kmask)
+    b = ops.spconv_mma(x, nbr, N, None, cout, w8.cuda(), scale, shift, out_dtype=torch.float32, kmask=kmask)
+    assert torch.equal(a, b) and a.abs().sum().item() > 0
+    ref = O.sparse_conv_auto(x.cpu().float(), tiles_to_nbr(nbr.cpu().numpy(), N), qw.float().reshape(cout, 3, 3, 3, cin)).double() * 1e-3
+    assert (b.cpu().double() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+
+
+def test_compact_weights_reject_non_codes_and_resident_layers(ops):
+    from qlidar import QlidarError
+    w = torch.randn(32, 27, 32).half()
+    with pytest.raises(QlidarError):
+        ops.compact_weights(ops.pack_weights(w))                            # not integer codes
+    qw = torch.randint(-127, 128, (32, 27, 32)).half()
+    assert not ops.weights_streamed(32, 32, 27)
+    w8 = ops.compact_weights(ops.pack_weights(qw))
+    nbr = torch.full((1, 27, 128), -1, dtype=torch.int32, device="cuda")
+    x = torch.zeros((128, 32), dtype=torch.float16, device="cuda")
+    with pytest.raises(QlidarError):
+        ops.spconv_mma(x, nbr, 128, None, 32, w8.cuda(), torch.ones(32, device="cuda"), torch.zeros(32, device="cuda"))
 
 
 def test_spconv_epilogue_fusion(ops):
