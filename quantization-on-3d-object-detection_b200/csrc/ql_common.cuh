@@ -55,11 +55,15 @@ __device__ __forceinline__ int4 ql_unkey(const QlGrid& g, uint32_t key) {
 // ------------------------------------------------------------------------------------------------
 #define QL_HASH_EMPTY 0xFFFFFFFFu
 
+// BUCKETISED: the four cells key & ~3 .. key | 3 (adjacent along x, the fastest axis of the key) hash to the four 8-byte
+// slots of ONE 32-byte sector, so the kw = 3 probes of a rulebook line touch one or two sectors instead of three random
+// ones (the probe kernels are bound by L2 random-sector rate).  Collisions step a whole bucket (ql_hash_next).
 __device__ __forceinline__ uint32_t ql_hash_slot(uint32_t key, uint32_t cap_mask) {
-    uint32_t h = key * 0x9E3779B1u;
+    uint32_t h = (key >> 2) * 0x9E3779B1u;
     h ^= h >> 15;
-    return h & cap_mask;
+    return ((h << 2) | (key & 3u)) & cap_mask;
 }
+__device__ __forceinline__ uint32_t ql_hash_next(uint32_t s, uint32_t cap_mask) { return (s + 4u) & cap_mask; }
 
 // returns the slot index that holds `key` (inserting it if absent); value word untouched.
 __device__ __forceinline__ uint32_t ql_hash_insert(uint2* __restrict__ table, uint32_t cap_mask, uint32_t key) {
@@ -67,7 +71,7 @@ __device__ __forceinline__ uint32_t ql_hash_insert(uint2* __restrict__ table, ui
     while (true) {
         uint32_t prev = atomicCAS(&table[s].x, QL_HASH_EMPTY, key);
         if (prev == QL_HASH_EMPTY || prev == key) return s;
-        s = (s + 1) & cap_mask;
+        s = ql_hash_next(s, cap_mask);
     }
 }
 
@@ -78,7 +82,7 @@ __device__ __forceinline__ uint32_t ql_hash_find_slot(const uint2* __restrict__ 
         uint32_t k = __ldg(&table[s].x);
         if (k == key) return s;
         if (k == QL_HASH_EMPTY) return 0xFFFFFFFFu;
-        s = (s + 1) & cap_mask;
+        s = ql_hash_next(s, cap_mask);
     }
 }
 
@@ -89,7 +93,7 @@ __device__ __forceinline__ int ql_hash_lookup(const uint2* __restrict__ table, u
         uint2 e = __ldg(&table[s]);
         if (e.x == key) return (int)e.y;
         if (e.x == QL_HASH_EMPTY) return -1;
-        s = (s + 1) & cap_mask;
+        s = ql_hash_next(s, cap_mask);
     }
 }
 

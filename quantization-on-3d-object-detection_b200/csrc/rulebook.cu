@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(QL_TILE_M) k_rb_pairs(const int4* __restrict__
                 uint2 ee = e[j];
                 uint32_t s = slot[j];
                 while (ee.x != key[j] && ee.x != QL_HASH_EMPTY) {
-                    s = (s + 1) & cap_mask;
+                    s = ql_hash_next(s, cap_mask);
                     ee = __ldg(&table[s]);
                 }
                 if (ee.x == key[j]) res = (int)ee.y;
