@@ -51,6 +51,11 @@ def peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback (B200_PROFILING.md)")
 
 
+# tcgen05.mma kind::i8 ceiling of this pool's B200s (M = 128, N >= 128, A in TMEM, all 148 SMs issuing back to back):
+# tools/microbench/mma_peak.cu, output committed as profiles/r01_mma_peak_microbench.txt (kind::f16: 2233 TFLOP/s)
+I8_MMA_PEAK_TOPS = 4596.0
+
+
 class ClockSampler:
     """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).  NVML in-process
     (a 2 ms polling thread: the timed region is only ~50-100 ms, too short for an `nvidia-smi -lms` child to start up --
@@ -351,7 +356,8 @@ def run_ours(args):
             q8 = sum(v for k, v in t8.items() if k.startswith("quantize:")) / 1e3
             return {"frames_per_sec": round(BATCH / (ms8 / 1e3), 2), "ms_per_step": round(ms8, 4), "conv_ms_per_step": round(tc8 * 1e3, 4),
                     "quantize_ms_per_step": round(q8 * 1e3, 4), "tops_alg": round(ops8 / tc8 / 1e12, 2),
-                    "frac_of_2x_bf16_peak": round(ops8 / tc8 / 1e12 / (2 * pk["bf16"]), 4)}
+                    "frac_of_2x_bf16_peak": round(ops8 / tc8 / 1e12 / (2 * pk["bf16"]), 4),
+                    "frac_of_i8_mma_peak": round(ops8 / tc8 / 1e12 / I8_MMA_PEAK_TOPS, 4)}
 
         eng8, bb8 = build_engine(dev, P, 8, 8, False)
         dyn = time_engine(eng8)
@@ -381,7 +387,8 @@ def run_ours(args):
         sta["fused_requantised_layers"] = int(sum(L.fused_q for L in eng8s.layers))
         int8_leg = {"mode": "QConvNd(w_bits=8, act_bits=8, cw=False): W8A8 per-tensor, INT32 accumulate (tcgen05 kind::i8)",
                     "dynamic_amax": dyn, "static_calibration": sta,
-                    "note": "INT8 peak is not in MEASURED_PEAKS.json; fraction against 2x the measured bf16 peak (nominal dense INT8 = 2x bf16). "
+                    "note": "INT8 peak is not in MEASURED_PEAKS.json; fractions against 2x the measured bf16 (cuBLAS) peak and against the "
+                            "measured tcgen05 kind::i8 issue ceiling (4596 TOPS, profiles/r01_mma_peak_microbench.txt). "
                             "static = collect_stats/compute_amax on one batch, int8 codes written by the producing layer's epilogue"}
     except Exception as e:                                     # the headline line must not depend on the extra leg
         int8_leg = {"error": repr(e)[:200]}

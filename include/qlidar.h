@@ -173,15 +173,12 @@ int ql_spconv_mma(const void* feats, int32_t in_dtype, const int32_t* nbr, const
                   ql_stream_t stream);
 /* the same through a grouped rulebook: row_perm [tiles * 128] maps a tile slot to the output row it computes (out,
  * out_q, residual are indexed by ROW; nbr / tile_kmask by slot); row_perm == NULL is ql_spconv_mma.
- * w_dtype: element type of w_packed -- in_dtype, or QL_S8 with in_dtype == QL_F16: COMPACT code weights
- * (ql_compact_weights_host), accepted where the kernel streams the weights (ql_spconv_weights_streamed): W8A16 / W8A8-cw
- * weights are int8 codes (quant/quant.py:42-44), so the per-tile weight stream, which paces the C >= 64 layers, moves one byte per
- * element and two extra warps expand each sub-chunk to its fp16 shared-memory image (exact). */
+ * ql_spconv_weights_streamed (host only): 1 when the kernel streams this layer's packed weights per unit because they do
+ * not fit in shared memory (fp16 C >= 64, int8 C >= 128) -- those launches are paced by the L2 -> SM weight stream. */
 int32_t ql_spconv_weights_streamed(int32_t c_in, int32_t c_out, int32_t kvol, int32_t elem_dtype);
-int ql_compact_weights_host(const void* packed_f16_host, size_t packed_bytes, void* compact_host);
 int ql_spconv_mma_rows(const void* feats, int32_t in_dtype, const int32_t* nbr, const uint32_t* tile_kmask,
                        const int32_t* row_perm, int64_t n_out_cap, const int32_t* n_out_dev,
-                       int32_t c_in, int32_t c_out, int32_t kvol, const void* w_packed, int32_t w_dtype,
+                       int32_t c_in, int32_t c_out, int32_t kvol, const void* w_packed,
                        const float* scale, const float* shift, const float* act_scale_dev,
                        const void* residual_f16, int32_t relu,
                        void* out, int32_t out_dtype, int8_t* out_q, const float* out_qscale, float* absmax,

@@ -46,9 +46,7 @@ constexpr int kEpilogueThreads = 128;
 constexpr int kEpilogueWarp0 = kProducerWarps;            // warps 16..19 (warp % 4 == TMEM lane quarter)
 constexpr int kMmaWarp = kEpilogueWarp0 + 4;              // 20
 constexpr int kLoaderWarp = kMmaWarp + 1;                 // 21
-constexpr int kExpandWarp0 = kLoaderWarp + 1;             // 22, 23: weight expanders (compact int8 codes -> fp16 B slots)
-constexpr int kExpandWarps = 2;
-constexpr int kThreadsTotal = (kExpandWarp0 + kExpandWarps) * 32;   // 768 (<= 80 registers per thread)
+constexpr int kThreadsTotal = (kLoaderWarp + 1) * 32;     // 704
 constexpr int kMaxUnits = 8;                              // ring depth in units
 constexpr int kUnitCols = 32;                             // TMEM columns per unit (128 bytes of K per lane)
 constexpr int kMaskWords = 4;                             // kernel volumes up to 128 (3^3, 5^3)
@@ -89,10 +87,7 @@ struct ConvParams {
     int n_acc;              // accumulator buffers in TMEM (2, or 1 when 2*c_out does not fit beside the A ring)
     int a_col0;             // first TMEM column of the A ring
     int resident;           // 1: every weight chunk lives in shared memory for the whole kernel (no per-unit B copies)
-    int w_compact;          // streamed f16-kind weights are stored as int8 CODES (half the L2 -> SM weight stream): the expander
-                            // warps turn each sub-chunk into its fp16 shared-memory image instead of the loader's bulk copies
     int w_bytes;            // packed weight bytes (resident mode)
-    int off_stage;          // smem offset of the compact-weight staging ring: n_ring x (c_out x 64 bytes)
     int off_nbr;            // smem offset of the rulebook buffers: nbr_bufs x {header, [kvol][128] int32}
     int nbr_bufs, nbr_log2; // 4 (or 2 when shared memory is short): the loader runs nbr_bufs-1 tiles ahead
     int nbr_stride;         // bytes per buffer
@@ -108,7 +103,6 @@ struct MiscSmem {
     uint64_t nbr_full[4];
     uint64_t nbr_empty[4];
     uint64_t w_full;
-    uint64_t stage_full[kMaxUnits];   // compact weights: the unit's int8 sub-chunks have landed in its staging slot
     uint32_t tmem_base;
     uint32_t pad[1];
     // followed by: float scale[c_out], float shift[c_out], uint32 absmax[c_out], float qscale[c_out]
@@ -257,10 +251,8 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
 
     if (tid == 0) {
         for (int s = 0; s < kMaxUnits; ++s) {
-            // the team's 4 warps + (streamed weights) the loader's expect_tx or the expander warps
-            ql_mbar_init(ql_smem_u32(&misc->full[s]), 4 + (kResident ? 0 : (p.w_compact ? kExpandWarps : 1)));
+            ql_mbar_init(ql_smem_u32(&misc->full[s]), 4 + (kResident ? 0 : 1));   // the team's 4 warps (+ the loader's expect_tx)
             ql_mbar_init(ql_smem_u32(&misc->empty[s]), 1);                         // tcgen05.commit
-            ql_mbar_init(ql_smem_u32(&misc->stage_full[s]), 1);                    // the loader's expect_tx
         }
         for (int i = 0; i < 2; ++i) {
             ql_mbar_init(ql_smem_u32(&misc->acc_full[i]), 1);
@@ -268,8 +260,7 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
         }
         for (int i = 0; i < 4; ++i) {
             ql_mbar_init(ql_smem_u32(&misc->nbr_full[i]), 1);
-            // producer warps + the MMA issuer (+ the expander warps, which read the tile header too)
-            ql_mbar_init(ql_smem_u32(&misc->nbr_empty[i]), 4 * p.teams + 1 + ((!kResident && p.w_compact) ? kExpandWarps : 0));
+            ql_mbar_init(ql_smem_u32(&misc->nbr_empty[i]), 4 * p.teams + 1);   // producer warps + the MMA issuer
         }
         ql_mbar_init(ql_smem_u32(&misc->w_full), 1);
         ql_fence_mbar_init();
@@ -602,75 +593,6 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
             }
         }
         __syncwarp();
-    } else if (warp >= kExpandWarp0) {
-        // ============================ weight expanders ============================
-        // Streamed weights of the f16 kind stored as int8 codes (W8A16 / W8A8-cw: the codes ARE the weights): the loader's bulk
-        // copies bring a unit's compact sub-chunks into its staging slot; byte i of a compact chunk is element i of the chunk's
-        // fp16 shared-memory image, so 16 codes (one 16-byte shared load) become two 16-byte shared stores at twice the offset and
-        // the swizzle is preserved.  fp16(code) = (0x6400 | (code ^ 0x80)) - 1152, exact.  (Expanding straight from global memory
-        // was tried first: one L2 round trip per unit per warp, 3.5x slower than the fp16 stream it replaced.)
-        if constexpr (!kResident && !kInt8) {
-            if (p.w_compact) {
-                const uint32_t et = (uint32_t)(warp - kExpandWarp0) * 32u + (uint32_t)lane;     // 0 .. 32 * kExpandWarps - 1
-                constexpr uint32_t kET = 32u * kExpandWarps;
-                const uint32_t pieces = b_sub_bytes >> 5;                                        // 32-byte fp16 pieces per sub-chunk
-                const uint32_t src_sub = b_sub_bytes >> 1;
-                const uint32_t stage_s0 = smem_base_u32 + (uint32_t)p.off_stage;
-                const uint32_t stage0 = ql_smem_u32(&misc->stage_full[0]);
-                uint32_t u = 0, ph = 0, it = 0;
-                for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                    const uint32_t nb = it & nbmask;
-                    const uint32_t buf = nbr_s0 + nb * nbr_stride;
-                    ql_mbar_wait(ql_smem_u32(&misc->nbr_full[nb]), (it >> p.nbr_log2) & 1u);
-                    const uint32_t n_sub = (uint32_t)ql_lds_s32(buf + 20u);
-                    for (uint32_t c0 = 0; c0 < n_sub; c0 += kGroup) {
-                        // the unit's compact sub-chunks are in its staging slot (the loader waited for the slot's MMAs to finish)
-                        ql_mbar_wait(stage0 + u * 8u, ph);
-#pragma unroll
-                        for (int j = 0; j < kGroup; ++j) {
-                            if (c0 + (uint32_t)j >= n_sub) break;
-                            const uint32_t src = stage_s0 + (u * (uint32_t)kGroup + (uint32_t)j) * src_sub;
-                            const uint32_t dst = smem_base_u32 + (u * (uint32_t)kGroup + (uint32_t)j) * b_sub_bytes;
-                            for (uint32_t i0 = et; i0 < pieces; i0 += 4u * kET) {
-                                uint32_t x[4][4];
-#pragma unroll
-                                for (int q4 = 0; q4 < 4; ++q4)
-                                    if (i0 + (uint32_t)q4 * kET < pieces)
-                                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                                     : "=r"(x[q4][0]), "=r"(x[q4][1]), "=r"(x[q4][2]), "=r"(x[q4][3])
-                                                     : "r"(src + (i0 + (uint32_t)q4 * kET) * 16u));
-#pragma unroll
-                                for (int q4 = 0; q4 < 4; ++q4) {
-                                    const uint32_t i = i0 + (uint32_t)q4 * kET;
-                                    if (i >= pieces) break;
-                                    uint32_t h[8];
-#pragma unroll
-                                    for (int w4 = 0; w4 < 4; ++w4) {
-                                        const uint32_t t = x[q4][w4] ^ 0x80808080u;
-                                        uint32_t lo, hi;
-                                        asm("prmt.b32 %0, %1, %2, 0x4140;" : "=r"(lo) : "r"(t), "r"(0x64646464u));
-                                        asm("prmt.b32 %0, %1, %2, 0x4342;" : "=r"(hi) : "r"(t), "r"(0x64646464u));
-                                        const __half2 bias = __half2half2(__ushort_as_half((unsigned short)0x6480));   // 1152
-                                        __half2 a = __hsub2(*reinterpret_cast<__half2*>(&lo), bias);
-                                        __half2 b = __hsub2(*reinterpret_cast<__half2*>(&hi), bias);
-                                        h[2 * w4] = *reinterpret_cast<uint32_t*>(&a);
-                                        h[2 * w4 + 1] = *reinterpret_cast<uint32_t*>(&b);
-                                    }
-                                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + i * 32u), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-                                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + i * 32u + 16u), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
-                                }
-                            }
-                        }
-                        ql_fence_proxy_async();                          // generic-proxy stores -> visible to the tensor core's reads
-                        __syncwarp();
-                        if (lane == 0) ql_mbar_arrive(full0 + u * 8u);
-                        if (++u == R) { u = 0; ph ^= 1u; }
-                    }
-                    __syncwarp();
-                    if (lane == 0) ql_mbar_arrive(ql_smem_u32(&misc->nbr_empty[nb]));
-                }
-            }
-        }
     } else {
         // ================================= loader =================================
         // Tile `tile` (the CTA's itn-th) -> rulebook buffer itn % nbr_bufs: header {mask, n_off, ord -> k table} written with
@@ -765,11 +687,6 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             prefetch_step();
             if constexpr (!kResident) {
-                // compact code weights: the copies land in the staging ring (half the bytes) and complete on stage_full; the
-                // expander warps turn them into the fp16 B slots
-                const uint32_t cbytes = p.w_compact ? (b_sub_bytes >> 1) : b_sub_bytes;
-                const uint32_t dst0 = smem_base_u32 + (p.w_compact ? (uint32_t)p.off_stage : 0u);
-                const uint32_t bar0 = p.w_compact ? ql_smem_u32(&misc->stage_full[0]) : full0;
                 const uint32_t buf = nbr_s0 + (it & nbmask) * nbr_stride;     // this tile's header (already resident: prefetched earlier)
                 const uint32_t n_sub = (uint32_t)ql_lds_s32(buf + 20u);
                 for (uint32_t c0 = 0; c0 < n_sub; c0 += batch_subs) {
@@ -778,19 +695,19 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
                     const uint32_t bu = (uint32_t)lane >> kGroupLog2, j = (uint32_t)lane & (uint32_t)(kGroup - 1);
                     uint32_t uu = u + bu, pp = ph;
                     if (uu >= R) { uu -= R; pp ^= 1u; }
-                    const uint32_t fbar = bar0 + uu * 8u;
+                    const uint32_t fbar = full0 + uu * 8u;
                     if (mine && j == 0) {
                         ql_mbar_wait(empty0 + uu * 8u, pp ^ 1u);
                         const uint32_t left = n_sub - sub;
-                        ql_mbar_arrive_expect_tx(fbar, (left < (uint32_t)kGroup ? left : (uint32_t)kGroup) * cbytes);
+                        ql_mbar_arrive_expect_tx(fbar, (left < (uint32_t)kGroup ? left : (uint32_t)kGroup) * b_sub_bytes);
                     }
                     __syncwarp();
                     if (mine) {
                         uint32_t ord = sub, seg = 0;
                         if (CH == 128) { ord = (sub * p.inv_nseg) >> 16; seg = sub - ord * (uint32_t)p.nseg; }
                         const uint32_t k = (uint32_t)lds_u8(buf + 32u + ord);
-                        ql_bulk_g2s(dst0 + (uu * (uint32_t)kGroup + j) * cbytes,
-                                    p.w_packed + (size_t)(k * (uint32_t)p.nseg + seg) * cbytes, cbytes, fbar);
+                        ql_bulk_g2s(smem_base_u32 + (uu * (uint32_t)kGroup + j) * b_sub_bytes,
+                                    p.w_packed + (size_t)(k * (uint32_t)p.nseg + seg) * b_sub_bytes, b_sub_bytes, fbar);
                     }
                     __syncwarp();
                     const uint32_t left = n_sub - c0;
@@ -859,13 +776,13 @@ cudaError_t launch(const ConvParams& p, int grid, size_t smem_bytes, cudaStream_
 
 // Shared-memory / TMEM plan of one launch (also answers "are this layer's weights streamed?" for the host).
 // Returns the dynamic shared-memory bytes, or 0 when the shape is unsupported.
-size_t plan_conv(ConvParams& p, const ChunkGeom& g, int c_out, int kvol, int compact) {
+size_t plan_conv(ConvParams& p, const ChunkGeom& g, int c_out, int kvol) {
     const int kv = g.pair ? (kvol + 1) / 2 : kvol;            // kernel offsets as the weight tensor / B descriptors see them
     // ring depth in units (32 TMEM columns each): bounded by the TMEM columns left beside the accumulators and, when
     // the weights are streamed, by shared memory (a unit's B slot = its 128/CH weight sub-chunks = c_out x 128 bytes)
     const int misc_bytes = (int)sizeof(MiscSmem) + 4 * c_out * 4;
     const int b_sub = c_out * g.ch;
-    const int b_unit = c_out * 128 + (compact ? c_out * 64 : 0);      // B slot (+ its compact staging slot)
+    const int b_unit = c_out * 128;
     p.inv_nseg = (uint32_t)((65536 + g.nseg - 1) / g.nseg);
     p.n_acc = (kTmemCols - 2 * c_out) / kUnitCols >= kTeams ? 2 : 1;
     int R = (kTmemCols - p.n_acc * c_out) / kUnitCols;
@@ -895,7 +812,6 @@ size_t plan_conv(ConvParams& p, const ChunkGeom& g, int c_out, int kvol, int com
     p.n_ring = R;
     p.teams = R < kTeams ? R : kTeams;
     p.a_col0 = p.n_acc * c_out;
-    p.off_stage = R * c_out * 128;                                   // staging ring right behind the B ring
     p.off_nbr = p.resident ? ((p.w_bytes + 1023) & ~1023) : ((R * b_unit + 1023) & ~1023);
     p.off_misc = (p.off_nbr + nbr_bytes + 127) & ~127;
     size_t smem_bytes = 1024 + (size_t)p.off_misc + misc_bytes;
@@ -948,13 +864,13 @@ extern "C" int ql_spconv_mma(const void* feats, int32_t in_dtype, const int32_t*
                              const float* scale, const float* shift, const float* act_scale_dev, const void* residual_f16,
                              int32_t relu, void* out, int32_t out_dtype, int8_t* out_q, const float* out_qscale,
                              float* absmax, ql_stream_t stream_) {
-    return ql_spconv_mma_rows(feats, in_dtype, nbr, tile_kmask, nullptr, n_out_cap, n_out_dev, c_in, c_out, kvol, w_packed, in_dtype, scale, shift,
+    return ql_spconv_mma_rows(feats, in_dtype, nbr, tile_kmask, nullptr, n_out_cap, n_out_dev, c_in, c_out, kvol, w_packed, scale, shift,
                               act_scale_dev, residual_f16, relu, out, out_dtype, out_q, out_qscale, absmax, stream_);
 }
 
 extern "C" int ql_spconv_mma_rows(const void* feats, int32_t in_dtype, const int32_t* nbr, const uint32_t* tile_kmask,
                                   const int32_t* row_perm, int64_t n_out_cap, const int32_t* n_out_dev, int32_t c_in, int32_t c_out,
-                                  int32_t kvol, const void* w_packed, int32_t w_dtype, const float* scale, const float* shift,
+                                  int32_t kvol, const void* w_packed, const float* scale, const float* shift,
                                   const float* act_scale_dev, const void* residual_f16, int32_t relu, void* out, int32_t out_dtype,
                                   int8_t* out_q, const float* out_qscale, float* absmax, ql_stream_t stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
@@ -975,15 +891,10 @@ extern "C" int ql_spconv_mma_rows(const void* feats, int32_t in_dtype, const int
     p.nseg = g.nseg; p.mask_words = (kvol + 31) / 32; p.pair = g.pair;
     p.w_packed = (const uint8_t*)w_packed; p.scale = scale; p.shift = shift; p.act_scale_dev = act_scale_dev;
     p.residual = (const __half*)residual_f16; p.relu = relu; p.out = out; p.out_dtype = out_dtype;
-    p.out_q = out_q; p.out_qscale = out_qscale; p.absmax = absmax; p.w_compact = 0;
+    p.out_q = out_q; p.out_qscale = out_qscale; p.absmax = absmax;
 
-    if (w_dtype != in_dtype) {
-        if (!(w_dtype == QL_S8 && in_dtype == QL_F16)) return QL_ERR_UNSUPPORTED;
-        p.w_compact = 1;
-    }
-    const size_t smem_bytes = plan_conv(p, g, c_out, kvol, p.w_compact);
+    const size_t smem_bytes = plan_conv(p, g, c_out, kvol);
     if (smem_bytes == 0) return QL_ERR_UNSUPPORTED;
-    if (p.w_compact && p.resident) return QL_ERR_UNSUPPORTED;        // compact codes only where the weights are streamed
 
     int64_t tiles = (n_out_cap + QL_TILE_M - 1) / QL_TILE_M;
     int grid = (int)(tiles < ql_num_sms() ? tiles : ql_num_sms());
@@ -998,8 +909,8 @@ extern "C" int ql_spconv_mma_rows(const void* feats, int32_t in_dtype, const int
     return e == cudaSuccess ? QL_OK : QL_ERR_CUDA;
 }
 
-// 1 when ql_spconv_mma streams this layer's weights per unit (they do not fit in shared memory): compact int8 storage of
-// f16-kind code weights (ql_compact_weights_host) then halves the L2 -> SM weight stream.
+// 1 when ql_spconv_mma streams this layer's weights per unit (they do not fit in shared memory) -- the layers whose L2 -> SM
+// traffic is dominated by the weight stream.
 extern "C" int32_t ql_spconv_weights_streamed(int32_t c_in, int32_t c_out, int32_t kvol, int32_t elem_dtype) {
     int es = elem_size(elem_dtype);
     if (es == 0 || c_in <= 0 || (c_in * es) % 16 != 0 || c_out < 16 || c_out % 16 != 0 || c_out > 256 || kvol <= 0 || kvol > 32 * kMaskWords)
@@ -1009,32 +920,6 @@ extern "C" int32_t ql_spconv_weights_streamed(int32_t c_in, int32_t c_out, int32
     p.row_bytes = c_in * es; p.c_out = c_out; p.kvol = kvol;
     const ChunkGeom g = chunk_geom(p.row_bytes);
     p.nseg = g.nseg; p.pair = g.pair;
-    if (plan_conv(p, g, c_out, kvol, 0) == 0) return 0;
+    if (plan_conv(p, g, c_out, kvol) == 0) return 0;
     return p.resident ? 0 : 1;
-}
-
-// fp16 packed image (ql_pack_weights_host, elem_dtype QL_F16) whose elements are integer codes in [-127, 127] -> the same
-// image with one int8 per element (half the bytes).  QL_ERR_INVALID if an element is not such a code.
-extern "C" int ql_compact_weights_host(const void* packed_f16_host, size_t packed_bytes, void* compact_host) {
-    if (!packed_f16_host || !compact_host || packed_bytes % 32 != 0) return QL_ERR_INVALID;
-    const uint16_t* src = (const uint16_t*)packed_f16_host;
-    int8_t* dst = (int8_t*)compact_host;
-    for (size_t i = 0; i < packed_bytes / 2; ++i) {
-        const uint16_t h = src[i];
-        const int sign = h >> 15, ex = (h >> 10) & 31, man = h & 1023;
-        int v;
-        if (ex == 0) {
-            if (man != 0) return QL_ERR_INVALID;           // subnormal: not an integer
-            v = 0;
-        } else {
-            const int e = ex - 15;                          // value = (1024 + man) * 2^(e - 10)
-            if (e < 0 || e > 6) return QL_ERR_INVALID;
-            const int full = 1024 + man, sh = 10 - e;
-            if (full & ((1 << sh) - 1)) return QL_ERR_INVALID;
-            v = full >> sh;
-            if (v > 127) return QL_ERR_INVALID;
-        }
-        dst[i] = (int8_t)(sign ? -v : v);
-    }
-    return QL_OK;
 }

@@ -308,7 +308,7 @@ extern "C" int ql_voxelize_mean(const float* points, int64_t n_points, int32_t p
                                 float* out_feats, int32_t out_feat_stride, int32_t* out_coords, int32_t* out_npts, int32_t* n_voxels_dev, uint64_t* table,
                                 int64_t table_cap, void* workspace, size_t workspace_bytes, ql_stream_t stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
-    if (!points || !range_min || !vsize || !grid_xyz || !out_feats || !out_coords || !out_npts || !n_voxels_dev || !table ||
+    if ((!points && n_points > 0) || !range_min || !vsize || !grid_xyz || !out_feats || !out_coords || !out_npts || !n_voxels_dev || !table ||
         !workspace)
         return QL_ERR_INVALID;
     if (n_feat < 3 || n_feat > 16 || point_stride < n_feat + (has_batch_col ? 1 : 0) || max_pts < 0 || max_voxels <= 0 ||

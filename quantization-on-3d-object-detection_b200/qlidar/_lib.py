@@ -41,9 +41,8 @@ SIGNATURES = {
     "ql_packed_weight_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ql_pack_weights_host": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p]),
     "ql_spconv_mma": (C.c_int, [_p, _i32, _p, _p, _i64, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _p]),
-    "ql_spconv_mma_rows": (C.c_int, [_p, _i32, _p, _p, _p, _i64, _p, _i32, _i32, _i32, _p, _i32, _p, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _p]),
+    "ql_spconv_mma_rows": (C.c_int, [_p, _i32, _p, _p, _p, _i64, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _p]),
     "ql_spconv_weights_streamed": (_i32, [_i32, _i32, _i32, _i32]),
-    "ql_compact_weights_host": (C.c_int, [_p, _sz, _p]),
     "ql_stem_conv": (C.c_int, [_p, _i32, _i32, _p, _i64, _p, _i32, _i32, _p, _p, _p, _i32, _p, _i32, _p, _p]),
     "ql_absmax_cols": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p]),
     "ql_quantize_rows": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p, _i32, _i32, _p, _p, _p]),

@@ -85,7 +85,7 @@ class BackboneEngine:
     def __init__(self, backbone: nn.Module, batch_size: int, max_voxels: int, *, max_points: Optional[int] = None,
                  pc_range=None, voxel_size=None, max_pts_per_voxel: int = 5, n_point_features: Optional[int] = None,
                  bev: bool = True, bev_dtype=torch.float16, use_graph: bool = True, stage_cap_ratio: float = 1.0, stage_caps=None,
-                 device="cuda", max_voxels_per_frame: int = 0, group_rows: bool = False, compact_weights: bool = False):
+                 device="cuda", max_voxels_per_frame: int = 0, group_rows: bool = False):
         self.dev = torch.device(device)
         self.B = int(batch_size)
         self.max_voxels = int(max_voxels)                 # capacity, total over the batch
@@ -93,12 +93,9 @@ class BackboneEngine:
         self.max_points = max_points
         self.pc_range, self.voxel_size, self.max_pts = pc_range, voxel_size, int(max_pts_per_voxel)
         self.bev, self.bev_dtype, self.use_graph = bev, bev_dtype, use_graph
-        # Two measured options, both OFF by default: grouped submanifold rulebooks on the ranked stages (fewer live
-        # (tile, offset) slabs, but the gathers lose their L1 locality and the binning costs ~28 us per stage: net loss on the
-        # Waymo batch) and int8 storage of streamed code weights for fp16 activations (halves the L2 -> SM weight stream, but
-        # the shared-memory expansion pass is slower than the stream it replaces).
+        # grouped submanifold rulebooks on the ranked stages: fewer live (tile, offset) slabs, but the gathers lose their L1
+        # locality and the binning costs ~28 us per stage -- a net loss on the Waymo batch, so OFF by default
         self.group_rows = bool(group_rows)
-        self.compact_weights = bool(compact_weights)
         self.sparse_shape = list(backbone.sparse_shape)
         self.grid_xyz = [self.sparse_shape[2], self.sparse_shape[1], self.sparse_shape[0] - 1]
         self.layers: List[Layer] = []
@@ -148,10 +145,10 @@ class BackboneEngine:
             if qw is None or L.act_bits > 8:
                 L.kind = "f16"
                 wt = conv.weight.detach().float().reshape(cout, K, cin).cpu() if codes is None else codes.cpu()
-                L.w = self._pack_f16(wt, cin, cout, K, codes is not None)
+                L.w = ops.pack_weights(wt.to(torch.float16)).to(self.dev)
             elif qw.cw or qw.per_row:
                 L.kind = "cw"
-                L.w = self._pack_f16(codes.cpu(), cin, cout, K, True)
+                L.w = ops.pack_weights(codes.cpu().to(torch.float16)).to(self.dev)
             else:
                 L.kind = "i8"
                 L.w = ops.pack_weights(codes.cpu().to(torch.int8)).to(self.dev)
@@ -173,13 +170,6 @@ class BackboneEngine:
             L.rb_key = ("strided", L.stage_in, L.ksize, L.stride, L.pad)
         self.layers.append(L)
         return L
-
-    def _pack_f16(self, wt, cin, cout, K, is_codes):
-        """fp16 weight image; int8-code weights of a layer whose weights are streamed are stored compact (one byte per code)."""
-        packed = ops.pack_weights(wt.to(torch.float16))
-        if is_codes and self.compact_weights and ops.weights_streamed(cin, cout, K, torch.float16):
-            packed = ops.compact_weights(packed)
-        return packed.to(self.dev)
 
     def _compile(self, bb):
         def seq_conv_bn_relu(prefix, seq):

@@ -301,20 +301,6 @@ def weights_streamed(c_in: int, c_out: int, kvol: int, dtype: torch.dtype = torc
     return bool(lib().ql_spconv_weights_streamed(int(c_in), int(c_out), int(kvol), _DT[dtype]))
 
 
-def compact_weights(packed_f16: torch.Tensor) -> torch.Tensor:
-    """Packed fp16 image of integer CODE weights (pack_weights of a float16 tensor) -> the same image with one int8 per
-    element (dtype torch.int8, half the bytes): the form ql_spconv_mma_rows takes with w_dtype = QL_S8 for fp16 activations."""
-    if packed_f16.is_cuda:
-        packed_f16 = packed_f16.cpu()
-    packed_f16 = packed_f16.contiguous()
-    if packed_f16.dtype != torch.uint8:
-        raise QlidarError("compact_weights expects the uint8 image returned by pack_weights")
-    out = torch.empty(packed_f16.numel() // 2, dtype=torch.int8)
-    check(lib().ql_compact_weights_host(C.c_void_p(packed_f16.data_ptr()), packed_f16.numel(), C.c_void_p(out.data_ptr())),
-          "ql_compact_weights_host")
-    return out
-
-
 def spconv_mma(feats: torch.Tensor, nbr: torch.Tensor, n_out_cap: int, n_out_dev: Optional[torch.Tensor], c_out: int,
                w_packed: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, *, act_scale: Optional[torch.Tensor] = None,
                residual: Optional[torch.Tensor] = None, relu: bool = False, out: Optional[torch.Tensor] = None,
@@ -322,8 +308,7 @@ def spconv_mma(feats: torch.Tensor, nbr: torch.Tensor, n_out_cap: int, n_out_dev
                out_qscale: Optional[torch.Tensor] = None, absmax: Optional[torch.Tensor] = None,
                kmask: Optional[torch.Tensor] = None, row_perm: Optional[torch.Tensor] = None) -> torch.Tensor:
     """kmask: the rulebook's per-tile offset mask [tiles, ceil(K/32)] int32 (None = visit every offset).
-    row_perm: slot -> output row table of a grouped rulebook (rulebook_subm_ranked_grouped).
-    w_packed: the uint8 image from pack_weights, or (fp16 activations) the int8 image from compact_weights."""
+    row_perm: slot -> output row table of a grouped rulebook (rulebook_subm_ranked_grouped)."""
     _need_cuda(feats, nbr, n_out_dev, w_packed, scale, shift, act_scale, residual, out, out_q, out_qscale, absmax, kmask, row_perm)
     if row_perm is not None and (row_perm.dtype != torch.int32 or row_perm.numel() < num_tiles(n_out_cap) * TILE_M):
         raise QlidarError("row_perm must be int32 [tiles * 128]")
@@ -341,7 +326,7 @@ def spconv_mma(feats: torch.Tensor, nbr: torch.Tensor, n_out_cap: int, n_out_dev
     if kmask is not None and (kmask.dtype != torch.int32 or kmask.shape[0] < num_tiles(n_out_cap) or kmask.shape[1] != mask_words(K)):
         raise QlidarError("kmask must be int32 [tiles, ceil(K/32)]")
     check(lib().ql_spconv_mma_rows(_ptr(feats), _DT[feats.dtype], _ptr(nbr), _ptr(kmask), _ptr(row_perm), int(n_out_cap), _ptr(n_out_dev),
-                                   c_in, int(c_out), K, _ptr(w_packed), QL_S8 if w_packed.dtype == torch.int8 else _DT[feats.dtype], _ptr(scale), _ptr(shift), _ptr(act_scale), _ptr(residual),
+                                   c_in, int(c_out), K, _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(act_scale), _ptr(residual),
                                    1 if relu else 0, _ptr(out), _DT[out.dtype], _ptr(out_q), _ptr(out_qscale), _ptr(absmax), _stream()),
           "ql_spconv_mma_rows")
     return out

@@ -44,6 +44,11 @@ def test_host_only_entry_points():
     assert lib.ql_packed_weight_bytes(16, 16, 27, _lib.QL_S8) == 14 * 16 * 32       # 16-byte rows: two kernel offsets per 32-byte chunk
     assert lib.ql_packed_weight_bytes(128, 64, 27, _lib.QL_F16) == 27 * 2 * 64 * 128
     assert lib.ql_packed_weight_bytes(15, 16, 27, _lib.QL_F32) == 0
+    # weights are shared-memory resident up to C = 32 (fp16) / C = 64 (int8) for a 3^3 kernel, streamed per unit above
+    assert lib.ql_spconv_weights_streamed(32, 32, 27, _lib.QL_F16) == 0 and lib.ql_spconv_weights_streamed(64, 64, 27, _lib.QL_F16) == 1
+    assert lib.ql_spconv_weights_streamed(64, 64, 27, _lib.QL_S8) == 0 and lib.ql_spconv_weights_streamed(128, 128, 27, _lib.QL_S8) == 1
+    assert lib.ql_spconv_weights_streamed(128, 128, 3, _lib.QL_F16) == 0           # conv_out: 3 offsets fit
+    assert lib.ql_rulebook_group_workspace_bytes(1000) >= 2000 + 512 * 4
 
 
 def _chunk_geom(row_bytes):

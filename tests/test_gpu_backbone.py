@@ -396,3 +396,61 @@ def test_engine_static_calibration_fuses_requantisation():
     with torch.no_grad():
         mod = bb(batch_dict(feats, coords, 2))["encoded_spconv_tensor"]
     check_feats(out["encoded_features"][:n], mod.features.float().cpu(), True)
+
+
+def test_engine_grouped_rulebooks_give_identical_outputs():
+    """group_rows=True (submanifold rulebooks of the ranked stages binned by line key) changes the tiling only: every
+    output of the engine is bit-identical to the ungrouped run."""
+    import qlidar
+    pts, feats, coords, grid, c = make_frame("waymo", batch=2)
+    prog, P, bb = build("VoxelResBackBone8x", 5, grid)
+    qlidar.q_conv3d(bb, {}, "", 8, 16, True, (qlidar.SubMConv3d, qlidar.SparseConv3d), ["conv_input.0"])
+    outs = []
+    for grouped in (False, True):
+        eng = qlidar.BackboneEngine(bb, 2, coords.shape[0] + 1000, max_points=pts.shape[0] + 500, pc_range=c["pc_range"],
+                                    voxel_size=c["voxel_size"], max_pts_per_voxel=c["max_pts"], stage_cap_ratio=4.0, group_rows=grouped)
+        for _ in range(2):
+            out = eng.forward_points(torch.from_numpy(pts))
+        torch.cuda.synchronize()
+        assert any(p is not None for p in eng.row_perms.values()) == grouped
+        outs.append({"enc": out["encoded_features"].clone(), "bev": out["spatial_features"].clone(),
+                     **{k: f.clone() for k, (f, _) in out["taps"].items()}})
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+def test_engine_empty_ragged_and_single_voxel_inputs():
+    """Edge cases of the batch contract: no in-range point at all (every stage empty, BEV all zero), a batch whose second
+    frame is empty (ragged), and a single voxel -- each against the oracle, through the same captured graph."""
+    import qlidar
+    pts, feats, coords, grid, c = make_frame("waymo", batch=2)
+    prog, P, bb = build("VoxelResBackBone8x", 5, grid)
+    eng = qlidar.BackboneEngine(bb, 2, coords.shape[0] + 1000, max_points=pts.shape[0] + 500, pc_range=c["pc_range"],
+                                voxel_size=c["voxel_size"], max_pts_per_voxel=c["max_pts"], stage_cap_ratio=4.0)
+    shape = O.sparse_shape_zyx(grid)
+
+    def run(p):
+        out = eng.forward_points(torch.from_numpy(p))
+        torch.cuda.synchronize()
+        return out, eng.counts()
+
+    # (1) nothing in range
+    far = pts.copy()
+    far[:, 1:4] += 1e4
+    out, counts = run(far)
+    assert counts == [0] * len(counts) and not eng.overflowed()
+    assert out["spatial_features"].abs().sum().item() == 0
+    # (2) ragged batch: frame 1 has no points; (3) one voxel (two points in the same cell of frame 0)
+    one = pts[pts[:, 0] == 0][:1].copy()
+    one = np.concatenate([one, one + np.array([0, 1e-3, 1e-3, 0, 0.1, 0.1], np.float32)])
+    for p in (pts[pts[:, 0] == 0], one):
+        f, co, _ = O.voxelize_mean_batch(p, c["pc_range"], c["voxel_size"], c["max_pts"], c["max_voxels"])
+        ref, _ = O.backbone_forward(prog, P, torch.from_numpy(f), co, shape, 2, O.QuantCfg(), {})
+        out, counts = run(p)
+        assert counts[0] == co.shape[0] and counts[-1] == ref.coords.shape[0]
+        n = counts[-1]
+        assert np.array_equal(out["encoded_coords"][:n].cpu().numpy(), ref.coords)
+        check_feats(out["encoded_features"][:n], ref.features, False)
+        ref_bev = O.height_compression(ref.features, ref.coords, ref.spatial_shape, 2)
+        check_feats(out["spatial_features"], ref_bev, False)
+        assert out["spatial_features"][1].abs().sum().item() == 0          # the empty frame's BEV map

@@ -416,47 +416,6 @@ def test_spconv_many_tiles_per_cta_with_offset_mask(ops, cin, cout, int8):
         assert err <= 1e-4 * ref.abs().max().item(), err
 
 
-@pytest.mark.parametrize("cin,cout", [(64, 64), (128, 128), (64, 128), (128, 256), (256, 256)])
-def test_spconv_compact_code_weights_are_bit_identical(ops, cin, cout):
-    """Streamed layers: int8-stored code weights (ql_compact_weights_host), expanded to fp16 in the kernel, give the
-    same bits as the fp16 image; resident layers refuse the compact form."""
-    rng = np.random.default_rng(90 + cin + cout)
-    S = 160
-    coords = O.synth_surface_sheet(S, seed=5, depth=8)
-    N = coords.shape[0]
-    c = dev(coords)
-    table = ops.hash_build(c, None, (1, 8, S, S))
-    nbr, kmask = ops.rulebook_subm(c, None, (1, 8, S, S), 3, table, with_mask=True)
-    x = torch.from_numpy(rng.normal(size=(N, cin)).astype(np.float32)).half().cuda()
-    qw = torch.from_numpy(rng.integers(-127, 128, size=(cout, 27, cin)).astype(np.int8))
-    qw[0, 0, 0], qw[1, 0, 0], qw[2, 0, 0] = 127, -127, 0
-    scale = torch.full((cout,), 1e-3, device="cuda")
-    shift = torch.zeros(cout, device="cuda")
-    assert ops.weights_streamed(cin, cout, 27)
-    w16 = ops.pack_weights(qw.half())
-    w8 = ops.compact_weights(w16)
-    assert w8.dtype == torch.int8 and w8.numel() * 2 == w16.numel()
-    a = ops.spconv_mma(x, nbr, N, None, cout, w16.cuda(), scale, shift, out_dtype=torch.float32, kmask=kmask)
-    b = ops.spconv_mma(x, nbr, N, None, cout, w8.cuda(), scale, shift, out_dtype=torch.float32, kmask=kmask)
-    assert torch.equal(a, b) and a.abs().sum().item() > 0
-    ref = O.sparse_conv_auto(x.cpu().float(), tiles_to_nbr(nbr.cpu().numpy(), N), qw.float().reshape(cout, 3, 3, 3, cin)).double() * 1e-3
-    assert (b.cpu().double() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
-
-
-def test_compact_weights_reject_non_codes_and_resident_layers(ops):
-    from qlidar import QlidarError
-    w = torch.randn(32, 27, 32).half()
-    with pytest.raises(QlidarError):
-        ops.compact_weights(ops.pack_weights(w))                            # not integer codes
-    qw = torch.randint(-127, 128, (32, 27, 32)).half()
-    assert not ops.weights_streamed(32, 32, 27)
-    w8 = ops.compact_weights(ops.pack_weights(qw))
-    nbr = torch.full((1, 27, 128), -1, dtype=torch.int32, device="cuda")
-    x = torch.zeros((128, 32), dtype=torch.float16, device="cuda")
-    with pytest.raises(QlidarError):
-        ops.spconv_mma(x, nbr, 128, None, 32, w8.cuda(), torch.ones(32, device="cuda"), torch.zeros(32, device="cuda"))
-
-
 def test_spconv_epilogue_fusion(ops):
     """dequant scale * BN scale/shift + residual + ReLU, fp16 out, int8 re-quantised out, per-channel absmax, device count."""
     rng = np.random.default_rng(30)
@@ -593,3 +552,34 @@ def test_bev_merge2d_matches_torch_unique_index_add(ops, dtype):
     assert n_out2.tolist() == [ref_c2.shape[0] - 10, ref_c2.shape[0]]
     assert np.array_equal(out_c2.cpu().numpy(), ref_c2[:-10])
     assert (out_f2.float().cpu() - ref_f2[:-10]).abs().max().item() <= tol * ref_f2.abs().max().item()
+
+
+def test_zero_rows_are_safe_everywhere(ops):
+    """Device-side row count 0 (an empty batch): every op returns without touching its outputs' live rows or faulting."""
+    B, D, H, W = 1, 5, 16, 16
+    cap = 256
+    coords = torch.zeros((cap, 4), dtype=torch.int32, device="cuda")
+    n0 = torch.zeros(2, dtype=torch.int32, device="cuda")
+    table = ops.hash_build(coords, n0, (B, D, H, W))
+    nbr, kmask = ops.rulebook_subm(coords, n0, (B, D, H, W), 3, table, with_mask=True)
+    oc, n_out, _, nbr_s, ogrid, _ = ops.rulebook_strided(coords, n0, (B, D, H, W), 3, 2, 1, cap)
+    assert n_out.tolist() == [0, 0]
+    ws = torch.zeros(ops.rulebook_strided_workspace_bytes((B, D, H, W), 3, 2, 1), dtype=torch.uint8, device="cuda")
+    oc2, n_out2, _, _, ogrid2, _ = ops.rulebook_strided(coords, n0, (B, D, H, W), 3, 2, 1, cap, workspace=ws)
+    index = ops.rulebook_strided_index((B, D, H, W), 3, 2, 1, ws)
+    nbr_g, km_g, perm = ops.rulebook_subm_ranked_grouped(oc2, n_out2, ogrid2, 3, index)
+    x = torch.ones((cap, 16), dtype=torch.float16, device="cuda")
+    w = ops.pack_weights(torch.ones(16, 27, 16).half()).cuda()
+    out = torch.full((cap, 16), 7.0, dtype=torch.float16, device="cuda")
+    ops.spconv_mma(x, nbr, cap, n0, 16, w, torch.ones(16, device="cuda"), torch.zeros(16, device="cuda"), out=out, kmask=kmask)
+    ops.spconv_mma(x, nbr_g, cap, n_out2, 16, w, torch.ones(16, device="cuda"), torch.zeros(16, device="cuda"), out=out, kmask=km_g, row_perm=perm)
+    torch.cuda.synchronize()
+    assert (out == 7.0).all()
+    bev = ops.bev_densify_ranked(x, index, n_out2, ogrid2)
+    assert bev.abs().sum().item() == 0
+    pts = torch.full((10, 6), 1e9, dtype=torch.float32, device="cuda")
+    pts[:, 0] = 0
+    f, c, npts, nd, _ = ops.voxelize_mean(pts, [0, -40, -3, 70.4, 40, 1], [0.05, 0.05, 0.1], [1408, 1600, 40], 1, 5, 100)
+    assert nd.tolist() == [0, 0]
+    f, c, npts, nd, _ = ops.voxelize_mean(pts[:0], [0, -40, -3, 70.4, 40, 1], [0.05, 0.05, 0.1], [1408, 1600, 40], 1, 5, 100)
+    assert nd.tolist() == [0, 0]
