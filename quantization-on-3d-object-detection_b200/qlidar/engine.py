@@ -85,7 +85,7 @@ class BackboneEngine:
     def __init__(self, backbone: nn.Module, batch_size: int, max_voxels: int, *, max_points: Optional[int] = None,
                  pc_range=None, voxel_size=None, max_pts_per_voxel: int = 5, n_point_features: Optional[int] = None,
                  bev: bool = True, bev_dtype=torch.float16, use_graph: bool = True, stage_cap_ratio: float = 1.0, stage_caps=None,
-                 device="cuda", max_voxels_per_frame: int = 0, group_rows: bool = False):
+                 device="cuda", max_voxels_per_frame: int = 0, group_rows: bool = False, overlap_rulebooks: bool = True):
         self.dev = torch.device(device)
         self.B = int(batch_size)
         self.max_voxels = int(max_voxels)                 # capacity, total over the batch
@@ -96,6 +96,10 @@ class BackboneEngine:
         # grouped submanifold rulebooks on the ranked stages: fewer live (tile, offset) slabs, but the gathers lose their L1
         # locality and the binning costs ~28 us per stage -- a net loss on the Waymo batch, so OFF by default
         self.group_rows = bool(group_rows)
+        # Rulebooks depend on coordinates only, never on features: in graph mode every build after the first runs on a side
+        # stream (a fork/join inside the captured graph) while the main stream runs the stem and the convs of earlier stages
+        self.overlap_rulebooks = bool(overlap_rulebooks)
+        self._side = None
         self.sparse_shape = list(backbone.sparse_shape)
         self.grid_xyz = [self.sparse_shape[2], self.sparse_shape[1], self.sparse_shape[0] - 1]
         self.layers: List[Layer] = []
@@ -295,28 +299,59 @@ class BackboneEngine:
         self._timing.append((label, e0, e1))
         return r
 
+    def _build_rulebook(self, L):
+        si, so = self.stages[L.stage_in], self.stages[L.stage_out]
+        nbr, kmask, perm = self.rulebooks[L.rb_key], self.kmasks[L.rb_key], self.row_perms[L.rb_key]
+        if perm is not None:
+            # kernels: line keys + histogram, bin scan, slot scatter, ranked pairs
+            self._op("rulebook_subm:" + L.name, 4, ops.rulebook_subm_ranked_grouped, si.coords, si.n_dev, si.grid, L.ksize, si.rank,
+                     nbr=nbr, kmask=kmask, row_perm=perm, workspace=self.group_ws)
+        elif L.subm and si.rank is not None:
+            self._op("rulebook_subm:" + L.name, 1, ops.rulebook_subm_ranked, si.coords, si.n_dev, si.grid, L.ksize, si.rank, nbr=nbr, kmask=kmask)
+        elif L.subm:
+            self._op("rulebook_subm:" + L.name, 1, ops.rulebook_subm, si.coords, si.n_dev, si.grid, L.ksize, si.table, nbr=nbr, kmask=kmask)
+        else:
+            # kernels: mark, popc, scan, emit + (fill, scatter, kmask | ranked pairs)
+            self._op("rulebook_strided:" + L.name, 5 if si.rank is not None else 7, ops.rulebook_strided, si.coords, si.n_dev, si.grid, L.ksize, L.stride, L.pad,
+                     so.cap, out=(so.coords, so.n_dev, None, nbr), workspace=so.rank.workspace, kmask=kmask, in_index=si.rank)
+
+    def _fork_rulebooks(self):
+        """Issue every rulebook build except the first layer's on the side stream, in layer order (a strided build produces the
+        stage its successors index); returns {rb_key: event}."""
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        self._side.wait_event(fork)
+        ready, seen = {}, {self.layers[0].rb_key}
+        with torch.cuda.stream(self._side):
+            for L in self.layers:
+                if L.rb_key in seen:
+                    continue
+                seen.add(L.rb_key)
+                self._build_rulebook(L)
+                ev = torch.cuda.Event()
+                ev.record(self._side)
+                ready[L.rb_key] = ev
+        return ready
+
     def _run_backbone(self):
         built = set()
         x = self.vox_feats
         block_in = None
         if self._need_absmax:
             self.absmax_pool.zero_()
+        overlap = self.overlap_rulebooks and self._timing is None and len({L.rb_key for L in self.layers}) > 1
+        ready = self._fork_rulebooks() if overlap else {}
         for i, L in enumerate(self.layers):
             si, so = self.stages[L.stage_in], self.stages[L.stage_out]
             nbr, kmask, perm = self.rulebooks[L.rb_key], self.kmasks[L.rb_key], self.row_perms[L.rb_key]
             if L.rb_key not in built:
-                if perm is not None:
-                    # kernels: line keys + histogram, bin scan, slot scatter, ranked pairs
-                    self._op("rulebook_subm:" + L.name, 4, ops.rulebook_subm_ranked_grouped, si.coords, si.n_dev, si.grid, L.ksize, si.rank,
-                             nbr=nbr, kmask=kmask, row_perm=perm, workspace=self.group_ws)
-                elif L.subm and si.rank is not None:
-                    self._op("rulebook_subm:" + L.name, 1, ops.rulebook_subm_ranked, si.coords, si.n_dev, si.grid, L.ksize, si.rank, nbr=nbr, kmask=kmask)
-                elif L.subm:
-                    self._op("rulebook_subm:" + L.name, 1, ops.rulebook_subm, si.coords, si.n_dev, si.grid, L.ksize, si.table, nbr=nbr, kmask=kmask)
+                if L.rb_key in ready:
+                    torch.cuda.current_stream().wait_event(ready[L.rb_key])      # built on the side stream
                 else:
-                    # kernels: mark, popc, scan, emit + (fill, scatter, kmask | ranked pairs)
-                    self._op("rulebook_strided:" + L.name, 5 if si.rank is not None else 7, ops.rulebook_strided, si.coords, si.n_dev, si.grid, L.ksize, L.stride, L.pad,
-                             so.cap, out=(so.coords, so.n_dev, None, nbr), workspace=so.rank.workspace, kmask=kmask, in_index=si.rank)
+                    self._build_rulebook(L)
                 built.add(L.rb_key)
             absmax = L.out_absmax if i in self._need_absmax else None
             if L.block_input:
@@ -342,6 +377,8 @@ class BackboneEngine:
                 self._op("conv:" + L.name, 1, ops.spconv_mma, L.q_buf, nbr, so.cap, so.n_dev, L.cout, L.w, L.scale, L.shift, residual=res, relu=L.relu, out=L.out,
                                absmax=absmax, kmask=kmask, out_q=L.out_q, out_qscale=L.out_qscale, row_perm=perm)
             x = L.out
+        if overlap:
+            torch.cuda.current_stream().wait_stream(self._side)               # join (every event was already waited for)
         if self.bev:
             last = self.stages[-1]
             if last.rank is not None:
