@@ -85,7 +85,7 @@ class BackboneEngine:
     def __init__(self, backbone: nn.Module, batch_size: int, max_voxels: int, *, max_points: Optional[int] = None,
                  pc_range=None, voxel_size=None, max_pts_per_voxel: int = 5, n_point_features: Optional[int] = None,
                  bev: bool = True, bev_dtype=torch.float16, use_graph: bool = True, stage_cap_ratio: float = 1.0, stage_caps=None,
-                 device="cuda", max_voxels_per_frame: int = 0, group_rows: bool = False, overlap_rulebooks: bool = True):
+                 device="cuda", max_voxels_per_frame: int = 0, group_rows="auto", overlap_rulebooks: bool = True):
         self.dev = torch.device(device)
         self.B = int(batch_size)
         self.max_voxels = int(max_voxels)                 # capacity, total over the batch
@@ -93,9 +93,12 @@ class BackboneEngine:
         self.max_points = max_points
         self.pc_range, self.voxel_size, self.max_pts = pc_range, voxel_size, int(max_pts_per_voxel)
         self.bev, self.bev_dtype, self.use_graph = bev, bev_dtype, use_graph
-        # grouped submanifold rulebooks on the ranked stages: fewer live (tile, offset) slabs, but the gathers lose their L1
-        # locality and the binning costs ~28 us per stage -- a net loss on the Waymo batch, so OFF by default
-        self.group_rows = bool(group_rows)
+        # Grouped submanifold rulebooks on the ranked stages (rows binned by line key: fewer live (tile, offset) slabs, but the
+        # gathers lose the L1 locality of key-consecutive rows).  True / False, or "auto": only where the layers STREAM their
+        # weights (every skipped slab then also saves a 16-32 KB weight copy, which is what paces those launches) -- measured
+        # +9-13 % on the C >= 64 submanifold layers, -7 % on the C = 32 residual layers.  The binning itself runs on
+        # the side stream with the other rulebook work.
+        self.group_rows = group_rows
         # Rulebooks depend on coordinates only, never on features: in graph mode every build after the first runs on a side
         # stream (a fork/join inside the captured graph) while the main stream runs the stem and the convs of earlier stages
         self.overlap_rulebooks = bool(overlap_rulebooks)
@@ -246,7 +249,10 @@ class BackboneEngine:
                 self.rulebooks[L.rb_key] = z(ops.num_tiles(so.cap), K, ops.TILE_M, dt=torch.int32)
                 self.kmasks[L.rb_key] = z(ops.num_tiles(so.cap), ops.mask_words(K), dt=torch.int32)
                 self.row_perms[L.rb_key] = None
-                if self.group_rows and L.subm and self.stages[L.stage_in].rank is not None and L.ksize[2] <= 31:
+                grp = self.group_rows
+                if grp == "auto":
+                    grp = L.kind != "stem" and ops.weights_streamed(L.cin, L.cout, K, torch.int8 if L.kind == "i8" else torch.float16)
+                if grp and L.subm and self.stages[L.stage_in].rank is not None and L.ksize[2] <= 31:
                     self.row_perms[L.rb_key] = z(ops.num_tiles(so.cap) * ops.TILE_M, dt=torch.int32)
                     nb = int(ops.lib().ql_rulebook_group_workspace_bytes(so.cap))
                     if self.group_ws is None or self.group_ws.numel() < nb:
