@@ -54,6 +54,8 @@ def peaks():
 # tcgen05.mma kind::i8 ceiling of this pool's B200s (M = 128, N >= 128, A in TMEM, all 148 SMs issuing back to back):
 # tools/microbench/mma_peak.cu, output committed as profiles/r01_mma_peak_microbench.txt (kind::f16: 2233 TFLOP/s)
 I8_MMA_PEAK_TOPS = 4596.0
+# experiment switch: extra BackboneEngine keyword arguments as JSON, e.g. QL_ENGINE_KW='{"group_rows": false}' (default: none)
+ENGINE_KW = json.loads(os.environ.get("QL_ENGINE_KW", "{}"))
 
 
 class ClockSampler:
@@ -162,7 +164,7 @@ def build_engine(device, max_points, w_bits=None, act_bits=None, cw=None):
     cap = BATCH * c["max_voxels"]
     eng = qlidar.BackboneEngine(bb, BATCH, cap, max_points=max_points, pc_range=c["pc_range"], voxel_size=c["voxel_size"],
                                 max_pts_per_voxel=c["max_pts"], use_graph=True, device=device, max_voxels_per_frame=c["max_voxels"],
-                                stage_caps=[cap, int(1.25 * cap), int(0.75 * cap), int(0.5 * cap), int(0.5 * cap)])
+                                stage_caps=[cap, int(1.25 * cap), int(0.75 * cap), int(0.5 * cap), int(0.5 * cap)], **ENGINE_KW)
     return eng, bb
 
 
@@ -382,7 +384,7 @@ def run_ours(args):
         cap = BATCH * c["max_voxels"]
         eng8s = qlidar.BackboneEngine(bb8, BATCH, cap, max_points=P, pc_range=c["pc_range"], voxel_size=c["voxel_size"],
                                       max_pts_per_voxel=c["max_pts"], use_graph=True, device=dev, max_voxels_per_frame=c["max_voxels"],
-                                      stage_caps=[cap, int(1.25 * cap), int(0.75 * cap), int(0.5 * cap), int(0.5 * cap)])
+                                      stage_caps=[cap, int(1.25 * cap), int(0.75 * cap), int(0.5 * cap), int(0.5 * cap)], **ENGINE_KW)
         sta = time_engine(eng8s)
         sta["fused_requantised_layers"] = int(sum(L.fused_q for L in eng8s.layers))
         int8_leg = {"mode": "QConvNd(w_bits=8, act_bits=8, cw=False): W8A8 per-tensor, INT32 accumulate (tcgen05 kind::i8)",

@@ -129,6 +129,16 @@ int ql_rulebook_strided_ranked(const int32_t* in_coords, int64_t n_in_cap, const
                                int32_t* out_coords, int64_t n_out_cap, int32_t* n_out_dev,
                                int32_t* nbr_out, uint32_t* tile_kmask,
                                void* workspace, size_t workspace_bytes, ql_stream_t stream);
+/* Renumber a list of DISTINCT sites (any order, e.g. the voxeliser's first-touch order == the reference's CPU voxeliser order,
+ * data_processor.py:151-153) by ascending linear key: out_coords [n] sorted, n_out_dev = (n, n), src_row[r] = input row of
+ * output row r (optional), and -- optional payload -- rows_out[r] = rows_in[src_row[r]] (rows of row_bytes = 16 m bytes).
+ * Leaves the stage's rank index in `workspace` in the layout of a 1x1x1 stride-1 ql_rulebook_strided over (B, D, H, W):
+ * ql_rulebook_strided_workspace_bytes / ql_rulebook_strided_index with ksize = stride = {1,1,1}, pad = {0,0,0}. */
+int ql_renumber_by_key(const int32_t* in_coords, int64_t n_cap, const int32_t* n_dev,
+                       int32_t B, int32_t D, int32_t H, int32_t W,
+                       int32_t* out_coords, int32_t* n_out_dev, int32_t* src_row,
+                       const void* rows_in, void* rows_out, int32_t row_bytes,
+                       void* workspace, size_t workspace_bytes, ql_stream_t stream);
 int ql_rulebook_subm_ranked(const int32_t* coords, int64_t n_cap, const int32_t* n_dev,
                             int32_t B, int32_t D, int32_t H, int32_t W, const int32_t* ksize_host,
                             const uint32_t* bitmap, const uint32_t* word_prefix,
@@ -183,6 +193,13 @@ int ql_spconv_mma_rows(const void* feats, int32_t in_dtype, const int32_t* nbr, 
                        const void* residual_f16, int32_t relu,
                        void* out, int32_t out_dtype, int8_t* out_q, const float* out_qscale, float* absmax,
                        ql_stream_t stream);
+
+/* ---- row permutation out[r] = in[src_row[r]] (rows of row_bytes = 16 m bytes, 16-byte aligned; src_row < 0 -> zero row).
+ *      No reference counterpart: the engine renumbers the voxeliser's first-touch-ordered voxels (== the reference's CPU
+ *      voxeliser order, data_processor.py:151-153) into ascending-key order with a 1x1x1 ql_rulebook_strided build, whose
+ *      rulebook is src_row, so that stage 1 is indexed by rank (bitmap + prefix) like the stages strided convs produce. */
+int ql_permute_rows(const void* in, void* out, int32_t row_bytes, const int32_t* src_row, int64_t n_cap,
+                    const int32_t* n_dev, ql_stream_t stream);
 
 /* ---- fp32 SIMT stem conv for the un-quantized conv_input (C_in = 4/5 raw point features; quant_centerpoint.py
  *      backbone_no_list = ['backbone_3d.conv_input.0'], :24-26).  feats rows are feat_stride floats apart;

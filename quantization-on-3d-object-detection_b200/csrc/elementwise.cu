@@ -438,3 +438,35 @@ extern "C" int ql_stem_conv(const float* feats, int32_t feat_stride, int32_t c_i
     QL_CUDA_CHECK_LAST();
     return QL_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// Row permutation: out[r] = in[src_row[r]] for r < n (rows of row_bytes = 16 * m bytes; src_row < 0 -> zeros).  Used by the
+// engine to bring the voxeliser's first-touch-ordered rows into ascending-key order (src_row = the 1x1x1 rulebook of the
+// renumbering build), after which stage 1 is indexed by rank like every later stage.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_permute_rows(const uint4* __restrict__ in, uint4* __restrict__ out, int chunks,
+                                                      const int* __restrict__ src_row, int64_t n_cap, const int* __restrict__ n_dev) {
+    const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = t / chunks;
+    if (r >= n) return;
+    const int c = (int)(t - r * chunks);
+    const int s = __ldg(src_row + r);
+    out[r * chunks + c] = s >= 0 ? __ldg(in + (int64_t)s * chunks + c) : make_uint4(0u, 0u, 0u, 0u);
+}
+}  // namespace
+
+extern "C" int ql_permute_rows(const void* in, void* out, int32_t row_bytes, const int32_t* src_row, int64_t n_cap,
+                               const int32_t* n_dev, ql_stream_t stream_) {
+    if (!in || !out || !src_row || row_bytes <= 0 || row_bytes % 16 != 0 || n_cap < 0 || in == out) return QL_ERR_INVALID;
+    if (((uintptr_t)in | (uintptr_t)out) & 15) return QL_ERR_INVALID;
+    if (n_cap == 0) return QL_OK;
+    const int chunks = row_bytes / 16;
+    const int64_t threads = n_cap * chunks;
+    k_permute_rows<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const uint4*)in, (uint4*)out, chunks, src_row,
+                                                                                         n_cap, n_dev);
+    QL_CUDA_CHECK_LAST();
+    return QL_OK;
+}

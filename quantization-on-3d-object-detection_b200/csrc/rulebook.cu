@@ -253,6 +253,60 @@ __global__ void __launch_bounds__(QL_SCAN_THREADS) k_rb_emit(const uint32_t* __r
     }
 }
 
+// ---- renumbering of a site list by ascending key (the stage-1 grid: 371 M cells = 11.6 M bitmap words for ~0.6 M sites) ----
+// The bitmap is huge and almost empty, and the coordinates are already known per input row, so nothing is decoded from the
+// bits: four words per thread (16-byte loads) for the popcount and prefix passes, then every input row looks its rank up.
+__global__ void __launch_bounds__(256) k_rn_mark(const int4* __restrict__ coords, int64_t n_cap, const int* __restrict__ n_dev, QlGrid g,
+                                                 uint32_t* __restrict__ bitmap) {
+    const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 c = coords[i];
+    const uint32_t key = ql_key(g, c.x, c.y, c.z, c.w);
+    atomicOr(&bitmap[key >> 5], 1u << (key & 31u));
+}
+
+__global__ void __launch_bounds__(QL_SCAN_THREADS) k_rn_popc4(const uint4* __restrict__ bitmap4, int64_t n_words4, int* block_counts) {
+    const int64_t i = (int64_t)blockIdx.x * QL_SCAN_THREADS + threadIdx.x;
+    int c = 0;
+    if (i < n_words4) {
+        const uint4 w = bitmap4[i];
+        c = __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+    }
+    int total;
+    block_exclusive_scan(c, total);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(QL_SCAN_THREADS) k_rn_prefix4(const uint4* __restrict__ bitmap4, int64_t n_words4,
+                                                               const int* __restrict__ block_offsets, uint4* __restrict__ word_prefix4) {
+    const int64_t i = (int64_t)blockIdx.x * QL_SCAN_THREADS + threadIdx.x;
+    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+    if (i < n_words4) w = bitmap4[i];
+    const int c0 = __popc(w.x), c1 = __popc(w.y), c2 = __popc(w.z), c3 = __popc(w.w);
+    int total;
+    const uint32_t run = (uint32_t)(block_exclusive_scan(c0 + c1 + c2 + c3, total) + block_offsets[blockIdx.x]);
+    if (i < n_words4) word_prefix4[i] = make_uint4(run, run + (uint32_t)c0, run + (uint32_t)(c0 + c1), run + (uint32_t)(c0 + c1 + c2));
+}
+
+// every input row takes its rank: coordinates, source row and (optionally) a payload row of chunks x 16 bytes move there
+__global__ void __launch_bounds__(256) k_rn_assign(const int4* __restrict__ coords, int64_t n_cap, const int* __restrict__ n_dev, QlGrid g,
+                                                   const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_prefix,
+                                                   int4* __restrict__ out_coords, int* __restrict__ src_row,
+                                                   const uint4* __restrict__ rows_in, uint4* __restrict__ rows_out, int chunks) {
+    const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 c = coords[i];
+    const uint32_t key = ql_key(g, c.x, c.y, c.z, c.w);
+    const uint32_t w = key >> 5;
+    const uint32_t rank = __ldg(word_prefix + w) + (uint32_t)__popc(__ldg(bitmap + w) & ((1u << (key & 31u)) - 1u));
+    out_coords[rank] = c;
+    if (src_row) src_row[rank] = (int)i;
+    if (rows_in)
+        for (int j = 0; j < chunks; ++j) rows_out[(int64_t)rank * chunks + j] = __ldg(rows_in + i * chunks + j);
+}
+
 // nbr := -1 for the live tiles (device-side row count)
 __global__ void __launch_bounds__(256) k_rb_fill(int4* __restrict__ nbr4, int K, const int* __restrict__ n_out_dev,
                                                  int64_t n_out_cap) {
@@ -347,7 +401,7 @@ struct StridedWs {
 StridedWs strided_ws_layout(const QlGrid& gout) {
     StridedWs w;
     const int64_t cells = (int64_t)gout.B * gout.D * gout.H * gout.W;
-    w.n_words = (cells + 31) / 32;
+    w.n_words = ((cells + 31) / 32 + 3) & ~(int64_t)3;                 // multiple of 4 words: the large-bitmap passes load 16 bytes
     w.n_blocks = (w.n_words + kWordsPerBlock - 1) / kWordsPerBlock;
     size_t o = 0;
     w.bitmap = o; o += align256((size_t)w.n_words * 4);
@@ -426,6 +480,41 @@ extern "C" int ql_rulebook_strided_index(int32_t B, int32_t D, int32_t H, int32_
     *bitmap = (const uint32_t*)((char*)workspace + w.bitmap);
     *word_prefix = (const uint32_t*)((char*)workspace + w.prefix);
     if (n_words) *n_words = w.n_words;
+    return QL_OK;
+}
+
+// Renumber a site list (distinct coordinates, any order) by ascending linear key and leave its rank index -- the same
+// (bitmap, word_prefix) pair, in the same workspace layout, that a 1x1x1 stride-1 ql_rulebook_strided over the grid would
+// leave (ql_rulebook_strided_index(B, D, H, W, {1,1,1}, {1,1,1}, {0,0,0}, workspace) returns the pointers).
+extern "C" int ql_renumber_by_key(const int32_t* in_coords, int64_t n_cap, const int32_t* n_dev, int32_t B, int32_t D, int32_t H,
+                                  int32_t W, int32_t* out_coords, int32_t* n_out_dev, int32_t* src_row, const void* rows_in,
+                                  void* rows_out, int32_t row_bytes, void* workspace, size_t workspace_bytes, ql_stream_t stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (!in_coords || !out_coords || !n_out_dev || !workspace || n_cap <= 0 || n_cap >= 2147483647LL || in_coords == out_coords)
+        return QL_ERR_INVALID;
+    if ((rows_in != nullptr) != (rows_out != nullptr) || (rows_in && (row_bytes <= 0 || row_bytes % 16 != 0 || rows_in == rows_out)))
+        return QL_ERR_INVALID;
+    if (rows_in && ((((uintptr_t)rows_in) | ((uintptr_t)rows_out)) & 15)) return QL_ERR_INVALID;
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return QL_ERR_INVALID;
+    if ((double)B * D * H * W >= 4294967295.0) return QL_ERR_GRID_TOO_LARGE;
+    const QlGrid g{B, D, H, W};
+    const StridedWs w = strided_ws_layout(g);
+    if (workspace_bytes < w.total) return QL_ERR_WORKSPACE;
+    char* ws = (char*)workspace;
+    uint32_t* bitmap = (uint32_t*)(ws + w.bitmap);
+    uint32_t* prefix = (uint32_t*)(ws + w.prefix);
+    int* blocks = (int*)(ws + w.blocks);
+    const int64_t n4 = w.n_words / 4;                                    // the layout pads the word count to a multiple of 4
+    const unsigned nb4 = (unsigned)((n4 + QL_SCAN_THREADS - 1) / QL_SCAN_THREADS);
+    const unsigned gin = (unsigned)((n_cap + 255) / 256);
+    if (cudaMemsetAsync(bitmap, 0, (size_t)w.n_words * 4, st) != cudaSuccess) return QL_ERR_CUDA;
+    k_rn_mark<<<gin, 256, 0, st>>>((const int4*)in_coords, n_cap, n_dev, g, bitmap);
+    k_rn_popc4<<<nb4, QL_SCAN_THREADS, 0, st>>>((const uint4*)bitmap, n4, blocks);
+    k_scan_blocks<<<1, QL_SCAN_THREADS, 0, st>>>(blocks, (int)nb4, n_out_dev + 1, n_out_dev, n_cap);
+    k_rn_prefix4<<<nb4, QL_SCAN_THREADS, 0, st>>>((const uint4*)bitmap, n4, blocks, (uint4*)prefix);
+    k_rn_assign<<<gin, 256, 0, st>>>((const int4*)in_coords, n_cap, n_dev, g, bitmap, prefix, (int4*)out_coords, src_row,
+                                     (const uint4*)rows_in, (uint4*)rows_out, rows_in ? row_bytes / 16 : 0);
+    QL_CUDA_CHECK_LAST();
     return QL_OK;
 }
 

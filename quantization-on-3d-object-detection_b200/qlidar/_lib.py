@@ -35,6 +35,7 @@ SIGNATURES = {
     "ql_rulebook_strided": (C.c_int, [_p, _i64, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _i64, _p, _p, _i64, _p, _p, _p, _sz, _p]),
     "ql_rulebook_strided_index": (C.c_int, [_i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "ql_rulebook_strided_ranked": (C.c_int, [_p, _i64, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
+    "ql_renumber_by_key": (C.c_int, [_p, _i64, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _i32, _p, _sz, _p]),
     "ql_rulebook_subm_ranked": (C.c_int, [_p, _i64, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "ql_rulebook_group_workspace_bytes": (_sz, [_i64]),
     "ql_rulebook_subm_ranked_grouped": (C.c_int, [_p, _i64, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
@@ -43,6 +44,7 @@ SIGNATURES = {
     "ql_spconv_mma": (C.c_int, [_p, _i32, _p, _p, _i64, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _p]),
     "ql_spconv_mma_rows": (C.c_int, [_p, _i32, _p, _p, _p, _i64, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _p]),
     "ql_spconv_weights_streamed": (_i32, [_i32, _i32, _i32, _i32]),
+    "ql_permute_rows": (C.c_int, [_p, _p, _i32, _p, _i64, _p, _p]),
     "ql_stem_conv": (C.c_int, [_p, _i32, _i32, _p, _i64, _p, _i32, _i32, _p, _p, _p, _i32, _p, _i32, _p, _p]),
     "ql_absmax_cols": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p]),
     "ql_quantize_rows": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p, _i32, _i32, _p, _p, _p]),

@@ -85,7 +85,7 @@ class BackboneEngine:
     def __init__(self, backbone: nn.Module, batch_size: int, max_voxels: int, *, max_points: Optional[int] = None,
                  pc_range=None, voxel_size=None, max_pts_per_voxel: int = 5, n_point_features: Optional[int] = None,
                  bev: bool = True, bev_dtype=torch.float16, use_graph: bool = True, stage_cap_ratio: float = 1.0, stage_caps=None,
-                 device="cuda", max_voxels_per_frame: int = 0, group_rows="auto", overlap_rulebooks: bool = True):
+                 device="cuda", max_voxels_per_frame: int = 0, group_rows="auto", overlap_rulebooks: bool = True, sort_stage1: bool = True):
         self.dev = torch.device(device)
         self.B = int(batch_size)
         self.max_voxels = int(max_voxels)                 # capacity, total over the batch
@@ -103,6 +103,11 @@ class BackboneEngine:
         # stream (a fork/join inside the captured graph) while the main stream runs the stem and the convs of earlier stages
         self.overlap_rulebooks = bool(overlap_rulebooks)
         self._side = None
+        # The voxeliser numbers voxels in first-touch order (the reference's CPU voxeliser order, random for shuffled points): a
+        # 128-row tile then touches all 27 kernel offsets and stage 1 needs the hash.  sort_stage1 renumbers the kept voxels in
+        # ascending-key order (1x1x1 bitmap build + row permutation), which makes stage 1 a ranked stage like the others: its
+        # tiles are runs along x, its rulebooks come from the rank index, and x_conv1 rows are returned in key order.
+        self.sort_stage1 = bool(sort_stage1)
         self.sparse_shape = list(backbone.sparse_shape)
         self.grid_xyz = [self.sparse_shape[2], self.sparse_shape[1], self.sparse_shape[0] - 1]
         self.layers: List[Layer] = []
@@ -165,7 +170,15 @@ class BackboneEngine:
         L.stage_in = len(self.stages) - 1
         if conv.subm:
             L.stage_out = L.stage_in
-            L.rb_key = ("subm", L.stage_in, L.ksize)
+            # grouped (rows binned by line key) or plain rulebook; the SIMT stem always takes the plain one, so a grouped
+            # stage 1 builds two rulebooks (the second on the side stream, under the stem)
+            grp = self.group_rows
+            if isinstance(grp, str):
+                streamed = L.kind != "stem" and ops.weights_streamed(cin, cout, K, torch.int8 if L.kind == "i8" else torch.float16)
+                grp = streamed                                  # "auto": only where the weights are streamed
+            ranked = L.stage_in > 0 or self.sort_stage1
+            grp = bool(grp) and ranked and L.kind != "stem" and L.ksize[2] <= 31
+            L.rb_key = ("subm", L.stage_in, L.ksize, "grouped" if grp else "plain")
         else:
             g = self.stages[-1].grid
             od, oh, ow = ops.conv_out_shape(g[1:], L.ksize, L.stride, L.pad)
@@ -224,6 +237,13 @@ class BackboneEngine:
             self.vox_ws = z(int(ops.lib().ql_voxelize_workspace_bytes(self.max_points, s0.cap, self.nfeat, self.max_pts)), dt=torch.uint8)
         else:
             s0.table = z(ops.hash_capacity(s0.cap), dt=torch.int64)
+        if self.sort_stage1:
+            self.vox_feats_ft = torch.zeros_like(self.vox_feats)           # first-touch order, as the voxeliser writes them
+            self.coords_ft = z(s0.cap, 4, dt=torch.int32)
+            self.n_ft = z(2, dt=torch.int32)
+            w0 = z(ops.rulebook_strided_workspace_bytes(s0.grid, 1, 1, 0), dt=torch.uint8)
+            s0.rank = ops.rulebook_strided_index(s0.grid, 1, 1, 0, w0)
+            self.sort_src = z(s0.cap, dt=torch.int32)                      # sorted row -> first-touch row
         for st in self.stages[1:]:
             st.coords = z(st.cap, 4, dt=torch.int32)
             st.n_dev = z(2, dt=torch.int32)
@@ -249,10 +269,7 @@ class BackboneEngine:
                 self.rulebooks[L.rb_key] = z(ops.num_tiles(so.cap), K, ops.TILE_M, dt=torch.int32)
                 self.kmasks[L.rb_key] = z(ops.num_tiles(so.cap), ops.mask_words(K), dt=torch.int32)
                 self.row_perms[L.rb_key] = None
-                grp = self.group_rows
-                if grp == "auto":
-                    grp = L.kind != "stem" and ops.weights_streamed(L.cin, L.cout, K, torch.int8 if L.kind == "i8" else torch.float16)
-                if grp and L.subm and self.stages[L.stage_in].rank is not None and L.ksize[2] <= 31:
+                if L.rb_key[-1] == "grouped":
                     self.row_perms[L.rb_key] = z(ops.num_tiles(so.cap) * ops.TILE_M, dt=torch.int32)
                     nb = int(ops.lib().ql_rulebook_group_workspace_bytes(so.cap))
                     if self.group_ws is None or self.group_ws.numel() < nb:
@@ -344,6 +361,10 @@ class BackboneEngine:
 
     def _run_backbone(self):
         built = set()
+        if self.sort_stage1:
+            s0 = self.stages[0]
+            # kernels: mark, popc, scan, prefix, assign (coordinates + feature rows move to their rank)
+            self._op("sort_stage1", 5, self._sort_stage1, s0)
         x = self.vox_feats
         block_in = None
         if self._need_absmax:
@@ -392,12 +413,17 @@ class BackboneEngine:
             else:
                 self._op("bev_densify", 2, ops.bev_densify, x, last.table, last.grid, out=self.spatial_features, workspace=self.bev_ws)
 
+    def _sort_stage1(self, s0):
+        ops.renumber_by_key(self.coords_ft, self.n_ft, s0.grid, s0.rank.workspace, out_coords=s0.coords, n_out_dev=s0.n_dev,
+                            src_row=self.sort_src, rows_in=self.vox_feats_ft, rows_out=self.vox_feats)
+
     def _run_from_points(self):
         s0 = self.stages[0]
         self.kernels_per_forward = 0
+        out = (self.vox_feats_ft, self.coords_ft, self.vox_npts, self.n_ft, s0.table) if self.sort_stage1 else \
+              (self.vox_feats, s0.coords, self.vox_npts, s0.n_dev, s0.table)
         self._op("voxelize_mean", 8 if self.max_voxels_per_frame else 7, ops.voxelize_mean, self.points, self.pc_range, self.voxel_size,
-                 self.grid_xyz, self.B, self.max_pts, s0.cap, out=(self.vox_feats, s0.coords, self.vox_npts, s0.n_dev, s0.table),
-                 workspace=self.vox_ws, max_voxels_per_frame=self.max_voxels_per_frame)
+                 self.grid_xyz, self.B, self.max_pts, s0.cap, out=out, workspace=self.vox_ws, max_voxels_per_frame=self.max_voxels_per_frame)
         self._run_backbone()
 
     def _replay(self, fn):
@@ -438,10 +464,16 @@ class BackboneEngine:
         V = voxel_features.shape[0]
         if V > s0.cap:
             raise QlidarError("more voxels than the engine capacity")
-        self.vox_feats[:V, :voxel_features.shape[1]].copy_(voxel_features)
-        s0.coords[:V].copy_(voxel_coords.int() if voxel_coords.dtype != torch.int32 else voxel_coords)
-        s0.n_dev.fill_(V)
-        ops.hash_build(s0.coords, s0.n_dev, s0.grid, table=s0.table)
+        vc = voxel_coords.int() if voxel_coords.dtype != torch.int32 else voxel_coords
+        if self.sort_stage1:
+            self.vox_feats_ft[:V, :voxel_features.shape[1]].copy_(voxel_features)
+            self.coords_ft[:V].copy_(vc)
+            self.n_ft.fill_(V)
+        else:
+            self.vox_feats[:V, :voxel_features.shape[1]].copy_(voxel_features)
+            s0.coords[:V].copy_(vc)
+            s0.n_dev.fill_(V)
+            ops.hash_build(s0.coords, s0.n_dev, s0.grid, table=s0.table)
         self._replay(self._run_backbone)
         return self.outputs()
 
@@ -459,6 +491,8 @@ class BackboneEngine:
     def overflowed(self) -> bool:
         """True when a stage found more active sites than its capacity (rows were dropped): raise the capacities."""
         c = torch.stack([st.n_dev for st in self.stages]).cpu()
+        if self.sort_stage1:
+            c[0] = self.n_ft.cpu()                                   # (kept, found) of the voxeliser, not of the renumbering build
         over = c[:, 1] > c[:, 0]
         if self.max_voxels_per_frame and self.stages[0].cap >= self.B * self.max_voxels_per_frame:
             over[0] = False           # voxels beyond a frame's MAX_NUMBER_OF_VOXELS are dropped by design; the batch capacity cannot overflow

@@ -151,6 +151,29 @@ def rulebook_strided_index(in_grid, ksize, stride, pad, workspace: torch.Tensor)
     return RankIndex(workspace, bm.value, pf.value, nw.value)
 
 
+def renumber_by_key(coords: torch.Tensor, n_dev: Optional[torch.Tensor], grid, workspace: torch.Tensor, out_coords: Optional[torch.Tensor] = None,
+                    n_out_dev: Optional[torch.Tensor] = None, src_row: Optional[torch.Tensor] = None, rows_in: Optional[torch.Tensor] = None,
+                    rows_out: Optional[torch.Tensor] = None):
+    """Sort a list of distinct sites by linear key; the workspace (rulebook_strided_workspace_bytes(grid, 1, 1, 0)) keeps the
+    stage's rank index (rulebook_strided_index(grid, 1, 1, 0, workspace)).  Returns (out_coords, n_out_dev, src_row, rows_out)."""
+    _need_cuda(coords, n_dev, workspace, out_coords, n_out_dev, src_row, rows_in, rows_out)
+    n_cap = coords.shape[0]
+    dev = coords.device
+    if out_coords is None:
+        out_coords = torch.empty_like(coords)
+    if n_out_dev is None:
+        n_out_dev = torch.zeros((2,), dtype=torch.int32, device=dev)
+    if src_row is None:
+        src_row = torch.empty((n_cap,), dtype=torch.int32, device=dev)
+    if rows_in is not None and rows_out is None:
+        rows_out = torch.empty_like(rows_in)
+    B, D, H, W = [int(v) for v in grid]
+    row_bytes = 0 if rows_in is None else rows_in.shape[1] * rows_in.element_size()
+    check(lib().ql_renumber_by_key(_ptr(coords), n_cap, _ptr(n_dev), B, D, H, W, _ptr(out_coords), _ptr(n_out_dev), _ptr(src_row),
+                                   _ptr(rows_in), _ptr(rows_out), row_bytes, _ptr(workspace), workspace.numel(), _stream()), "ql_renumber_by_key")
+    return out_coords, n_out_dev, src_row, rows_out
+
+
 def rulebook_subm_ranked(coords: torch.Tensor, n_dev: Optional[torch.Tensor], grid, ksize, index: RankIndex,
                          nbr: Optional[torch.Tensor] = None, kmask: Optional[torch.Tensor] = None):
     """Submanifold rulebook of a key-sorted stage through its rank index (no hash).  Returns (nbr, kmask)."""
@@ -204,7 +227,7 @@ def rulebook_strided_workspace_bytes(grid, ksize, stride, pad) -> int:
 
 def rulebook_strided(coords: torch.Tensor, n_in_dev: Optional[torch.Tensor], grid, ksize, stride, pad,
                      n_out_cap: int, out=None, workspace=None, kmask: Optional[torch.Tensor] = None,
-                     in_index: Optional["RankIndex"] = None):
+                     in_index: Optional["RankIndex"] = None, want_kmask: bool = True):
     """Returns (out_coords [n_out_cap,4] sorted by linear key, n_out_dev [2] = (kept, found), out_table, nbr [tiles,K,128],
     out_grid (B,D,H,W), kmask [tiles, ceil(K/32)]).  in_index: the rank index of a key-sorted INPUT stage -> the pairs come
     from the output side through it (ql_rulebook_strided_ranked; no hash table is produced, out_table must be None)."""
@@ -222,7 +245,7 @@ def rulebook_strided(coords: torch.Tensor, n_in_dev: Optional[torch.Tensor], gri
         nbr = torch.empty((num_tiles(n_out_cap), K, TILE_M), dtype=torch.int32, device=dev)
     else:
         out_coords, n_out_dev, out_table, nbr = out                   # out_table may be None: rank-index consumers only
-    if kmask is None:
+    if kmask is None and want_kmask:
         kmask = torch.zeros((num_tiles(n_out_cap), mask_words(K)), dtype=torch.int32, device=dev)
     ws_bytes = rulebook_strided_workspace_bytes(grid, k, s, p)
     if workspace is None or workspace.numel() < ws_bytes:
@@ -346,6 +369,17 @@ def stem_conv(feats: torch.Tensor, nbr: torch.Tensor, n_out_cap: int, n_out_dev:
         out = torch.empty((n_out_cap, c_out), dtype=out_dtype, device=feats.device)
     check(lib().ql_stem_conv(_ptr(feats), int(feats.shape[1]), c_in, _ptr(nbr), int(n_out_cap), _ptr(n_out_dev), c_out, K, _ptr(w_kio), _ptr(scale), _ptr(shift),
                              1 if relu else 0, _ptr(out), _DT[out.dtype], _ptr(absmax), _stream()), "ql_stem_conv")
+    return out
+
+
+def permute_rows(x: torch.Tensor, src_row: torch.Tensor, n_dev: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[r] = x[src_row[r]] for r < n (src_row int32, e.g. the [tiles, 1, 128] rulebook of a 1x1x1 renumbering build)."""
+    _need_cuda(x, src_row, n_dev, out)
+    if out is None:
+        out = torch.empty_like(x)
+    row_bytes = x.shape[1] * x.element_size()
+    n_cap = min(x.shape[0], out.shape[0], src_row.numel())
+    check(lib().ql_permute_rows(_ptr(x), _ptr(out), row_bytes, _ptr(src_row), n_cap, _ptr(n_dev), _stream()), "ql_permute_rows")
     return out
 
 
