@@ -79,6 +79,19 @@ int ql_voxelize_mean(const float* points, int64_t n_points, int32_t point_stride
                      int32_t batch_size, int32_t max_pts_per_voxel, int64_t max_voxels, int64_t max_voxels_per_frame,
                      float* out_feats, int32_t out_feat_stride, int32_t* out_coords, int32_t* out_npts, int32_t* n_voxels_dev,
                      uint64_t* table, int64_t table_cap, void* workspace, size_t workspace_bytes, ql_stream_t stream);
+/* The two halves of ql_voxelize_mean (same arguments and workspace): ql_voxelize_coords runs the hash insert and the
+ * numbering passes -- out_coords and n_voxels_dev are final after it -- and ql_voxelize_features, stream-ordered after it, the point
+ * selection and the means (out_feats, out_npts, table values).  Work that needs only coordinates (rulebooks) can overlap it. */
+int ql_voxelize_coords(const float* points, int64_t n_points, int32_t point_stride, int32_t has_batch_col, int32_t n_feat,
+                     const float* range_min_xyz_host, const float* voxel_size_xyz_host, const int32_t* grid_xyz_host,
+                     int32_t batch_size, int32_t max_pts_per_voxel, int64_t max_voxels, int64_t max_voxels_per_frame,
+                     float* out_feats, int32_t out_feat_stride, int32_t* out_coords, int32_t* out_npts, int32_t* n_voxels_dev,
+                     uint64_t* table, int64_t table_cap, void* workspace, size_t workspace_bytes, ql_stream_t stream);
+int ql_voxelize_features(const float* points, int64_t n_points, int32_t point_stride, int32_t has_batch_col, int32_t n_feat,
+                     const float* range_min_xyz_host, const float* voxel_size_xyz_host, const int32_t* grid_xyz_host,
+                     int32_t batch_size, int32_t max_pts_per_voxel, int64_t max_voxels, int64_t max_voxels_per_frame,
+                     float* out_feats, int32_t out_feat_stride, int32_t* out_coords, int32_t* out_npts, int32_t* n_voxels_dev,
+                     uint64_t* table, int64_t table_cap, void* workspace, size_t workspace_bytes, ql_stream_t stream);
 /* MeanVFE on an already voxelized (V,T,F) tensor (mean_vfe.py:25-29); num_points is float32 when
  * num_points_is_float (pcdet/models/__init__.py:36 casts everything to float) else int32. */
 int ql_mean_vfe(const float* voxels, const void* num_points, int32_t num_points_is_float, int64_t V, int32_t T, int32_t F,

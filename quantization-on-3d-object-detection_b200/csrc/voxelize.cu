@@ -302,11 +302,13 @@ extern "C" size_t ql_voxelize_workspace_bytes(int64_t max_points, int64_t max_vo
     return vox_ws_layout(max_points, max_voxels, n_feat, max_pts).total;
 }
 
-extern "C" int ql_voxelize_mean(const float* points, int64_t n_points, int32_t point_stride, int32_t has_batch_col,
-                                int32_t n_feat, const float* range_min, const float* vsize, const int32_t* grid_xyz,
-                                int32_t batch_size, int32_t max_pts, int64_t max_voxels, int64_t max_voxels_per_frame,
-                                float* out_feats, int32_t out_feat_stride, int32_t* out_coords, int32_t* out_npts, int32_t* n_voxels_dev, uint64_t* table,
-                                int64_t table_cap, void* workspace, size_t workspace_bytes, ql_stream_t stream_) {
+// phases: 1 = passes 1-4 (hash insert, first-touch numbering: out_coords and n_voxels_dev are final), 2 = passes 5-7 (point
+// selection, means, num_points, table values), 3 = both.  Phase 2 must follow phase 1 with the same arguments and workspace.
+static int voxelize_phases(int phases, const float* points, int64_t n_points, int32_t point_stride, int32_t has_batch_col,
+                           int32_t n_feat, const float* range_min, const float* vsize, const int32_t* grid_xyz,
+                           int32_t batch_size, int32_t max_pts, int64_t max_voxels, int64_t max_voxels_per_frame,
+                           float* out_feats, int32_t out_feat_stride, int32_t* out_coords, int32_t* out_npts, int32_t* n_voxels_dev, uint64_t* table,
+                           int64_t table_cap, void* workspace, size_t workspace_bytes, ql_stream_t stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if ((!points && n_points > 0) || !range_min || !vsize || !grid_xyz || !out_feats || !out_coords || !out_npts || !n_voxels_dev || !table ||
         !workspace)
@@ -344,34 +346,59 @@ extern "C" int ql_voxelize_mean(const float* points, int64_t n_points, int32_t p
     float* sums = (float*)(ws + w.sums);
     int* cnt = (int*)(ws + w.cnt);
 
-    if (cudaMemsetAsync(table, 0xFF, (size_t)table_cap * 8, st) != cudaSuccess) return QL_ERR_CUDA;
-    if (cudaMemsetAsync(pt_vid, 0xFF, (size_t)(n_points > 0 ? n_points : 1) * 4, st) != cudaSuccess) return QL_ERR_CUDA;
-    if (max_pts > 0) {
-        if (cudaMemsetAsync(tmin, 0xFF, (size_t)max_voxels * max_pts * 4, st) != cudaSuccess) return QL_ERR_CUDA;
-    } else {
-        if (cudaMemsetAsync(sums, 0, (size_t)max_voxels * n_feat * 4, st) != cudaSuccess) return QL_ERR_CUDA;
-        if (cudaMemsetAsync(cnt, 0, (size_t)max_voxels * 4, st) != cudaSuccess) return QL_ERR_CUDA;
+    if (phases & 1) {
+        if (cudaMemsetAsync(table, 0xFF, (size_t)table_cap * 8, st) != cudaSuccess) return QL_ERR_CUDA;
+        if (cudaMemsetAsync(pt_vid, 0xFF, (size_t)(n_points > 0 ? n_points : 1) * 4, st) != cudaSuccess) return QL_ERR_CUDA;
+    }
+    if (phases & 2) {
+        if (max_pts > 0) {
+            if (cudaMemsetAsync(tmin, 0xFF, (size_t)max_voxels * max_pts * 4, st) != cudaSuccess) return QL_ERR_CUDA;
+        } else {
+            if (cudaMemsetAsync(sums, 0, (size_t)max_voxels * n_feat * 4, st) != cudaSuccess) return QL_ERR_CUDA;
+            if (cudaMemsetAsync(cnt, 0, (size_t)max_voxels * 4, st) != cudaSuccess) return QL_ERR_CUDA;
+        }
     }
     if (n_points == 0) {
-        if (cudaMemsetAsync(n_voxels_dev, 0, 8, st) != cudaSuccess) return QL_ERR_CUDA;
+        if ((phases & 1) && cudaMemsetAsync(n_voxels_dev, 0, 8, st) != cudaSuccess) return QL_ERR_CUDA;
         return QL_OK;
     }
     uint32_t cap_mask = (uint32_t)(table_cap - 1);
     unsigned gp = (unsigned)((n_points + kThreads - 1) / kThreads);
     unsigned nb = (unsigned)((n_points + kBlockPts - 1) / kBlockPts);
-    k_vox_insert<<<gp, kThreads, 0, st>>>(P, (uint2*)table, cap_mask, pt_slot);
-    if (max_voxels_per_frame > 0 && cudaMemsetAsync(P.frames, 0, (size_t)3 * batch_size * 4, st) != cudaSuccess) return QL_ERR_CUDA;
-    k_vox_count<<<nb, kThreads, 0, st>>>(P, (const uint2*)table, pt_slot, blocks);
-    k_scan_blocks<<<1, kThreads, 0, st>>>(blocks, (int)nb, n_voxels_dev + 1, n_voxels_dev, max_voxels);
-    if (max_voxels_per_frame > 0) k_vox_frames<<<1, 32, 0, st>>>(P, n_voxels_dev);
-    k_vox_assign<<<nb, kThreads, 0, st>>>(P, (const uint2*)table, pt_slot, blocks, pt_vid, vox_first, out_coords);
-    k_vox_gather<<<gp, kThreads, 0, st>>>(P, (const uint2*)table, pt_slot, pt_vid, tmin, sums, cnt);
-    k_vox_drop<<<gp, kThreads, 0, st>>>(P, (uint2*)table, pt_slot, pt_vid);
-    k_vox_finalize<<<(unsigned)((max_voxels + kThreads - 1) / kThreads), kThreads, 0, st>>>(
-        P, (uint2*)table, pt_slot, vox_first, tmin, sums, cnt, n_voxels_dev, out_feats, out_npts);
+    if (phases & 1) {
+        k_vox_insert<<<gp, kThreads, 0, st>>>(P, (uint2*)table, cap_mask, pt_slot);
+        if (max_voxels_per_frame > 0 && cudaMemsetAsync(P.frames, 0, (size_t)3 * batch_size * 4, st) != cudaSuccess) return QL_ERR_CUDA;
+        k_vox_count<<<nb, kThreads, 0, st>>>(P, (const uint2*)table, pt_slot, blocks);
+        k_scan_blocks<<<1, kThreads, 0, st>>>(blocks, (int)nb, n_voxels_dev + 1, n_voxels_dev, max_voxels);
+        if (max_voxels_per_frame > 0) k_vox_frames<<<1, 32, 0, st>>>(P, n_voxels_dev);
+        k_vox_assign<<<nb, kThreads, 0, st>>>(P, (const uint2*)table, pt_slot, blocks, pt_vid, vox_first, out_coords);
+    }
+    if (phases & 2) {
+        k_vox_gather<<<gp, kThreads, 0, st>>>(P, (const uint2*)table, pt_slot, pt_vid, tmin, sums, cnt);
+        k_vox_drop<<<gp, kThreads, 0, st>>>(P, (uint2*)table, pt_slot, pt_vid);
+        k_vox_finalize<<<(unsigned)((max_voxels + kThreads - 1) / kThreads), kThreads, 0, st>>>(
+            P, (uint2*)table, pt_slot, vox_first, tmin, sums, cnt, n_voxels_dev, out_feats, out_npts);
+    }
     QL_CUDA_CHECK_LAST();
     return QL_OK;
 }
+
+#define QL_VOX_ARGS points, n_points, point_stride, has_batch_col, n_feat, range_min, vsize, grid_xyz, batch_size, max_pts, max_voxels, \
+                    max_voxels_per_frame, out_feats, out_feat_stride, out_coords, out_npts, n_voxels_dev, table, table_cap, workspace,     \
+                    workspace_bytes, stream_
+#define QL_VOX_PARAMS                                                                                                                     \
+    const float *points, int64_t n_points, int32_t point_stride, int32_t has_batch_col, int32_t n_feat, const float *range_min,           \
+        const float *vsize, const int32_t *grid_xyz, int32_t batch_size, int32_t max_pts, int64_t max_voxels,                            \
+        int64_t max_voxels_per_frame, float *out_feats, int32_t out_feat_stride, int32_t *out_coords, int32_t *out_npts,                 \
+        int32_t *n_voxels_dev, uint64_t *table, int64_t table_cap, void *workspace, size_t workspace_bytes, ql_stream_t stream_
+extern "C" int ql_voxelize_mean(QL_VOX_PARAMS) { return voxelize_phases(3, QL_VOX_ARGS); }
+// the two halves of ql_voxelize_mean, for callers that overlap work needing only the coordinates (rulebooks) with the
+// feature passes: ql_voxelize_coords leaves out_coords / n_voxels_dev final; ql_voxelize_features (same arguments, same
+// workspace, stream-ordered after it) fills out_feats / out_npts and the table values
+extern "C" int ql_voxelize_coords(QL_VOX_PARAMS) { return voxelize_phases(1, QL_VOX_ARGS); }
+extern "C" int ql_voxelize_features(QL_VOX_PARAMS) { return voxelize_phases(2, QL_VOX_ARGS); }
+#undef QL_VOX_ARGS
+#undef QL_VOX_PARAMS
 
 extern "C" int ql_mean_vfe(const float* voxels, const void* num_points, int32_t is_float, int64_t V, int32_t T, int32_t F,
                            float* out, ql_stream_t stream_) {

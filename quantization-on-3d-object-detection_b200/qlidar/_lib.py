@@ -27,6 +27,8 @@ SIGNATURES = {
     "ql_hash_build": (C.c_int, [_p, _i64, _p, _i32, _i32, _i32, _i32, _p, _i64, _p]),
     "ql_voxelize_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "ql_voxelize_mean": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _i64, _i64, _p, _i32, _p, _p, _p, _p, _i64, _p, _sz, _p]),
+    "ql_voxelize_coords": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _i64, _i64, _p, _i32, _p, _p, _p, _p, _i64, _p, _sz, _p]),
+    "ql_voxelize_features": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _i64, _i64, _p, _i32, _p, _p, _p, _p, _i64, _p, _sz, _p]),
     "ql_mean_vfe": (C.c_int, [_p, _p, _i32, _i64, _i32, _i32, _p, _p]),
     "ql_rulebook_num_tiles": (_i64, [_i64]),
     "ql_rulebook_mask_words": (_i32, [_i32]),

@@ -338,17 +338,26 @@ class BackboneEngine:
             self._op("rulebook_strided:" + L.name, 5 if si.rank is not None else 7, ops.rulebook_strided, si.coords, si.n_dev, si.grid, L.ksize, L.stride, L.pad,
                      so.cap, out=(so.coords, so.n_dev, None, nbr), workspace=so.rank.workspace, kmask=kmask, in_index=si.rank)
 
-    def _fork_rulebooks(self):
+    def _fork_rulebooks(self, with_first=False):
         """Issue every rulebook build except the first layer's on the side stream, in layer order (a strided build produces the
-        stage its successors index); returns {rb_key: event}."""
+        stage its successors index); returns {rb_key: event}.  with_first (the from-points schedule): the fork happens right
+        after the voxeliser's coordinate passes, and the side stream also renumbers stage 1 (coordinates only; event
+        "sorted") and builds the first rulebook, all under the voxeliser's feature passes on the main stream."""
         main = torch.cuda.current_stream()
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.dev)
         fork = torch.cuda.Event()
         fork.record(main)
         self._side.wait_event(fork)
-        ready, seen = {}, {self.layers[0].rb_key}
+        ready, seen = {}, (set() if with_first else {self.layers[0].rb_key})
         with torch.cuda.stream(self._side):
+            if with_first:
+                s0 = self.stages[0]
+                self._op("sort_stage1", 5, ops.renumber_by_key, self.coords_ft, self.n_ft, s0.grid, s0.rank.workspace, out_coords=s0.coords,
+                         n_out_dev=s0.n_dev, src_row=self.sort_src)
+                ev = torch.cuda.Event()
+                ev.record(self._side)
+                ready["sorted"] = ev
             for L in self.layers:
                 if L.rb_key in seen:
                     continue
@@ -359,9 +368,9 @@ class BackboneEngine:
                 ready[L.rb_key] = ev
         return ready
 
-    def _run_backbone(self):
+    def _run_backbone(self, ready=None):
         built = set()
-        if self.sort_stage1:
+        if self.sort_stage1 and ready is None:
             s0 = self.stages[0]
             # kernels: mark, popc, scan, prefix, assign (coordinates + feature rows move to their rank)
             self._op("sort_stage1", 5, self._sort_stage1, s0)
@@ -370,7 +379,10 @@ class BackboneEngine:
         if self._need_absmax:
             self.absmax_pool.zero_()
         overlap = self.overlap_rulebooks and self._timing is None and len({L.rb_key for L in self.layers}) > 1
-        ready = self._fork_rulebooks() if overlap else {}
+        if ready is None:
+            ready = self._fork_rulebooks() if overlap else {}
+        else:
+            overlap = True
         for i, L in enumerate(self.layers):
             si, so = self.stages[L.stage_in], self.stages[L.stage_out]
             nbr, kmask, perm = self.rulebooks[L.rb_key], self.kmasks[L.rb_key], self.row_perms[L.rb_key]
@@ -422,9 +434,21 @@ class BackboneEngine:
         self.kernels_per_forward = 0
         out = (self.vox_feats_ft, self.coords_ft, self.vox_npts, self.n_ft, s0.table) if self.sort_stage1 else \
               (self.vox_feats, s0.coords, self.vox_npts, s0.n_dev, s0.table)
-        self._op("voxelize_mean", 8 if self.max_voxels_per_frame else 7, ops.voxelize_mean, self.points, self.pc_range, self.voxel_size,
-                 self.grid_xyz, self.B, self.max_pts, s0.cap, out=out, workspace=self.vox_ws, max_voxels_per_frame=self.max_voxels_per_frame)
-        self._run_backbone()
+        vox = lambda label, nk, phase: self._op(label, nk, ops.voxelize_mean, self.points, self.pc_range, self.voxel_size, self.grid_xyz, self.B,
+                                                 self.max_pts, s0.cap, out=out, workspace=self.vox_ws,
+                                                 max_voxels_per_frame=self.max_voxels_per_frame, phase=phase)
+        if self.sort_stage1 and self.overlap_rulebooks and self._timing is None:
+            # coordinates are final after the numbering passes: renumbering, the first rulebook and every later rulebook run on the
+            # side stream under the voxeliser's feature passes (point selection + means), then the feature rows move to their rank
+            vox("voxelize_mean", 5 if self.max_voxels_per_frame else 4, "coords")
+            ready = self._fork_rulebooks(with_first=True)
+            vox("voxelize_mean", 3, "features")
+            torch.cuda.current_stream().wait_event(ready["sorted"])
+            self._op("sort_stage1", 1, ops.permute_rows, self.vox_feats_ft, self.sort_src, s0.n_dev, out=self.vox_feats)
+            self._run_backbone(ready=ready)
+        else:
+            vox("voxelize_mean", 8 if self.max_voxels_per_frame else 7, "mean")
+            self._run_backbone()
 
     def _replay(self, fn):
         if not self.use_graph:

@@ -72,11 +72,12 @@ def hash_build(coords: torch.Tensor, n_dev: Optional[torch.Tensor], grid: Sequen
 
 def voxelize_mean(points: torch.Tensor, pc_range, voxel_size, grid_xyz, batch_size: int, max_pts: int, max_voxels: int,
                   has_batch_col: bool = True, n_feat: Optional[int] = None, out=None, workspace=None,
-                  max_voxels_per_frame: int = 0):
+                  max_voxels_per_frame: int = 0, phase: str = "mean"):
     """Fused hard voxelization + mean VFE (+ DynamicMeanVFE semantics when max_pts == 0).
     Returns (feats [max_voxels,F] f32, coords [max_voxels,4] i32, npts [max_voxels] i32, n_dev [2] i32 = (kept, found), table).
     A caller-provided feats buffer may be wider than F (row stride = its second dimension, pad columns written as zeros).
-    max_voxels_per_frame > 0: the reference's per-frame MAX_NUMBER_OF_VOXELS (points frame-contiguous, frames ascending)."""
+    max_voxels_per_frame > 0: the reference's per-frame MAX_NUMBER_OF_VOXELS (points frame-contiguous, frames ascending).
+    phase: "mean" (everything), or "coords" then "features" with the same buffers (coords / n_dev are final after "coords")."""
     _need_cuda(points)
     if points.dtype != torch.float32 or points.dim() != 2:
         raise QlidarError("points must be a float32 (P, stride) tensor")
@@ -97,9 +98,10 @@ def voxelize_mean(points: torch.Tensor, pc_range, voxel_size, grid_xyz, batch_si
     rmin = (C.c_float * 3)(*[float(v) for v in pc_range[:3]])
     vs = (C.c_float * 3)(*[float(v) for v in voxel_size])
     g = (C.c_int32 * 3)(*[int(v) for v in grid_xyz])
-    check(lib().ql_voxelize_mean(_ptr(points), P, stride, 1 if has_batch_col else 0, F, rmin, vs, g, int(batch_size), int(max_pts),
+    fn = {"mean": lib().ql_voxelize_mean, "coords": lib().ql_voxelize_coords, "features": lib().ql_voxelize_features}[phase]
+    check(fn(_ptr(points), P, stride, 1 if has_batch_col else 0, F, rmin, vs, g, int(batch_size), int(max_pts),
                                  int(max_voxels), int(max_voxels_per_frame), _ptr(feats), int(feats.shape[1]), _ptr(coords), _ptr(npts), _ptr(n_dev), _ptr(table), table.numel(),
-                                 _ptr(workspace), workspace.numel(), _stream()), "ql_voxelize_mean")
+                                 _ptr(workspace), workspace.numel(), _stream()), "ql_voxelize_" + phase)
     return feats, coords, npts, n_dev, table
 
 
