@@ -22,7 +22,12 @@ def main():
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     h, units = rows[0], rows[1]
-    idx = [(h.index(k), n, units[h.index(k)]) for k, n in WANT if k in h]
+    def find(k):                                       # some sections prefix their metrics ("TPC.TriageCompute.sm__pipe_tensor...")
+        if k in h:
+            return h.index(k)
+        m = [i for i, x in enumerate(h) if x.endswith("." + k)]
+        return m[0] if m else None
+    idx = [(find(k), n, units[find(k)]) for k, n in WANT if find(k) is not None]
     md = "--md" in sys.argv
     names = [n for _, n, _ in idx]
     print(("| " + " | ".join(names) + " |") if md else "\t".join(names))
