@@ -55,6 +55,59 @@ __global__ void __launch_bounds__(128, 1) k_peak(int n, int iters) {
     if (threadIdx.x < 32) ql_tmem_dealloc(tmem, 512);
 }
 
+// The conv kernel's issue pattern: per UNIT one mbarrier wait (already complete), tcgen05.fence::after_thread_sync, 4 MMAs and one
+// tcgen05.commit -- what does the single issuing thread pay per unit beyond the 4 MMAs?
+template <bool kInt8>
+__global__ void __launch_bounds__(128, 1) k_unit_pattern(int n, int units, int with_wait, int with_commit, int issuers, long long* cycles_out) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_done, bar_sink[16], bar_final[2];
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t base = (ql_smem_u32(smem_raw) + 1023u) & ~1023u;
+    if (threadIdx.x == 0) {
+        ql_mbar_init(ql_smem_u32(&bar_done), 1);
+        for (int i = 0; i < 16; ++i) ql_mbar_init(ql_smem_u32(&bar_sink[i]), 1);
+        ql_mbar_init(ql_smem_u32(&bar_final[0]), 1);
+        ql_mbar_init(ql_smem_u32(&bar_final[1]), 1);
+        ql_fence_mbar_init();
+    }
+    if (threadIdx.x < 32) { ql_tmem_alloc(ql_smem_u32(&tmem_base_s), 512); ql_tmem_relinquish(); }
+    ql_tc_fence_before();
+    __syncthreads();
+    ql_tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const int w = threadIdx.x >> 5;                        // issuer w (warp w, lane 0) accumulates into columns w * 128 ..
+    if ((threadIdx.x & 31) == 0 && w < issuers) {
+        uint32_t idesc = 0;
+        if (kInt8) idesc |= (2u << 4) | (1u << 7) | (1u << 10); else idesc |= 1u << 4;
+        idesc |= (uint32_t)(n >> 3) << 17;
+        idesc |= (uint32_t)(128 >> 4) << 24;
+        uint64_t bd = 0;
+        bd |= (uint64_t)((base & 0x3FFFFu) >> 4);
+        bd |= (uint64_t)1 << 16;
+        bd |= (uint64_t)(1024 >> 4) << 32;
+        bd |= (uint64_t)1 << 46;
+        bd |= (uint64_t)2 << 61;
+        const uint32_t d = tmem + (uint32_t)(w * 128), a0 = tmem + 256u + (uint32_t)(w * 32);
+        const long long t0 = clock64();
+        for (int u = 0; u < units; ++u) {
+            if (with_wait) { ql_mbar_wait(ql_smem_u32(&bar_done), 1u); ql_tc_fence_after(); }   // parity 1 of a fresh barrier: complete
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                mma_ts<kInt8>(d, a0 + (uint32_t)(j * 8), bd + (uint64_t)(j * 2), idesc, 1u);
+            if (with_commit) ql_tc_commit(ql_smem_u32(&bar_sink[(u & 7) + 8 * w]));                // arrivals just flip phases
+        }
+        const long long t1 = clock64();
+        ql_tc_commit(ql_smem_u32(&bar_final[w]));
+        ql_mbar_wait(ql_smem_u32(&bar_final[w]), 0u);
+        const long long t2 = clock64();
+        if (blockIdx.x == 0 && w == 0) { cycles_out[0] = t1 - t0; cycles_out[1] = t2 - t0; }
+    }
+    ql_tc_fence_before();
+    __syncthreads();
+    ql_tc_fence_after();
+    if (threadIdx.x < 32) ql_tmem_dealloc(tmem, 512);
+}
+
 template <bool kInt8>
 static double run(int n, int iters, int sms) {
     const size_t smem = 1024 + 256 * 128;
@@ -82,6 +135,30 @@ int main() {
     for (int n : {16, 32, 64, 128, 256}) {
         const double f = run<false>(n, iters, sms), i = run<true>(n, iters, sms);
         printf("%6d %14.1f %14.1f\n", n, f, i);
+    }
+    long long* cyc;
+    cudaMalloc(&cyc, 16);
+    const size_t smem = 1024 + 256 * 128;
+    cudaFuncSetAttribute(k_unit_pattern<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    printf("\nper-UNIT cost for the issuing thread (4 MMAs per unit, kind::f16), cycles per unit: issue loop / until retired\n");
+    printf("%6s %22s %22s %22s\n", "N", "4 MMAs only", "+ wait + fence", "+ wait + fence + commit");
+    for (int n : {16, 64, 128}) {
+        long long h[3][2];
+        for (int v = 0; v < 3; ++v) {
+            k_unit_pattern<false><<<sms, 128, smem>>>(n, 16384, v >= 1, v >= 2, 1, cyc);
+            cudaMemcpy(h[v], cyc, 16, cudaMemcpyDeviceToHost);
+        }
+        printf("%6d %10.1f /%10.1f %10.1f /%10.1f %10.1f /%10.1f\n", n, h[0][0] / 16384.0, h[0][1] / 16384.0, h[1][0] / 16384.0, h[1][1] / 16384.0,
+               h[2][0] / 16384.0, h[2][1] / 16384.0);
+    }
+    printf("\nTWO issuing threads (warps 0 and 1, separate accumulators), each 16384 units of 4 MMAs + wait + fence + commit: cycles per unit per thread\n");
+    for (int n : {16, 64, 128}) {
+        long long h1[2], h2[2];
+        k_unit_pattern<false><<<sms, 128, smem>>>(n, 16384, 1, 1, 1, cyc);
+        cudaMemcpy(h1, cyc, 16, cudaMemcpyDeviceToHost);
+        k_unit_pattern<false><<<sms, 128, smem>>>(n, 16384, 1, 1, 2, cyc);
+        cudaMemcpy(h2, cyc, 16, cudaMemcpyDeviceToHost);
+        printf("%6d   one issuer %8.1f   two issuers %8.1f (x%.2f MMA rate)\n", n, h1[1] / 16384.0, h2[1] / 16384.0, 2.0 * h1[1] / h2[1]);
     }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
