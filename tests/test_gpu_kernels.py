@@ -583,3 +583,59 @@ def test_zero_rows_are_safe_everywhere(ops):
     assert nd.tolist() == [0, 0]
     f, c, npts, nd, _ = ops.voxelize_mean(pts[:0], [0, -40, -3, 70.4, 40, 1], [0.05, 0.05, 0.1], [1408, 1600, 40], 1, 5, 100)
     assert nd.tolist() == [0, 0]
+
+
+def test_renumber_by_key_sorts_and_leaves_a_rank_index(ops):
+    """ql_renumber_by_key: distinct sites in random order -> ascending linear key (bit-exact vs numpy), src_row is the sorting
+    permutation, payload rows move with it, and the rank index it leaves serves the ranked submanifold rulebook (== oracle)."""
+    rng = np.random.default_rng(77)
+    B, D, H, W = 2, 9, 150, 170
+    coords = random_coords(rng, B, D, H, W, 0.02)                      # random order
+    n = coords.shape[0]
+    cap = n + 333
+    grid = (B, D, H, W)
+    feats = torch.from_numpy(rng.normal(size=(cap, 8)).astype(np.float32)).cuda()
+    c_in = torch.zeros((cap, 4), dtype=torch.int32, device="cuda")
+    c_in[:n] = dev(coords)
+    n_dev = torch.tensor([n, n], dtype=torch.int32, device="cuda")
+    ws = torch.zeros(ops.rulebook_strided_workspace_bytes(grid, 1, 1, 0), dtype=torch.uint8, device="cuda")
+    oc, n_out, src, rows = ops.renumber_by_key(c_in, n_dev, grid, ws, rows_in=feats)
+    order = np.argsort(O._lin(coords, [D, H, W]), kind="stable")
+    assert n_out.tolist() == [n, n]
+    assert np.array_equal(oc[:n].cpu().numpy(), coords[order])
+    assert np.array_equal(src[:n].cpu().numpy(), order.astype(np.int32))
+    assert torch.equal(rows[:n].cpu(), feats[:n].cpu()[torch.from_numpy(order)])
+    index = ops.rulebook_strided_index(grid, 1, 1, 0, ws)
+    nbr, kmask = ops.rulebook_subm_ranked(oc, n_out, grid, 3, index)
+    ref = O.rulebook_subm(coords[order], [D, H, W], 3)
+    assert np.array_equal(tiles_to_nbr(nbr.cpu().numpy(), n), ref)
+    # coordinates only (no payload), and an empty list
+    oc2, n2, src2, r2 = ops.renumber_by_key(c_in, n_dev, grid, ws)
+    assert r2 is None and torch.equal(oc2[:n], oc[:n]) and torch.equal(src2[:n], src[:n])
+    zero = torch.zeros(2, dtype=torch.int32, device="cuda")
+    _, n3, _, _ = ops.renumber_by_key(c_in, zero, grid, ws)
+    assert n3.tolist() == [0, 0]
+    # permute_rows with the same table
+    moved = ops.permute_rows(feats, src, n_out)
+    assert torch.equal(moved[:n], rows[:n])
+
+
+def test_voxelize_phases_equal_the_single_call(ops):
+    """ql_voxelize_coords followed by ql_voxelize_features (same buffers) == ql_voxelize_mean; coordinates and the voxel count
+    are already final after the first phase."""
+    c = O.CONFIGS["waymo"]
+    pts = O.synth_batch("waymo", 2, n_beams=24, n_az=400)
+    grid = O.grid_size_xyz(c["pc_range"], c["voxel_size"])
+    p = dev(pts)
+    cap = 60000
+    a = ops.voxelize_mean(p, c["pc_range"], c["voxel_size"], grid, 2, c["max_pts"], cap)
+    ws = torch.zeros(int(ops.lib().ql_voxelize_workspace_bytes(pts.shape[0], cap, 5, c["max_pts"])), dtype=torch.uint8, device="cuda")
+    out = (torch.full((cap, 5), -7.0, device="cuda"), torch.zeros((cap, 4), dtype=torch.int32, device="cuda"),
+           torch.zeros(cap, dtype=torch.int32, device="cuda"), torch.zeros(2, dtype=torch.int32, device="cuda"),
+           torch.empty(ops.hash_capacity(pts.shape[0]), dtype=torch.int64, device="cuda"))
+    ops.voxelize_mean(p, c["pc_range"], c["voxel_size"], grid, 2, c["max_pts"], cap, out=out, workspace=ws, phase="coords")
+    n = int(a[3][0].item())
+    assert out[3].tolist() == a[3].tolist() and torch.equal(out[1][:n], a[1][:n])
+    assert (out[0][:n] == -7.0).all()                                   # features untouched so far
+    ops.voxelize_mean(p, c["pc_range"], c["voxel_size"], grid, 2, c["max_pts"], cap, out=out, workspace=ws, phase="features")
+    assert torch.equal(out[0][:n], a[0][:n]) and torch.equal(out[2][:n], a[2][:n]) and torch.equal(out[1][:n], a[1][:n])
