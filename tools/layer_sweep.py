@@ -40,8 +40,8 @@ def main():
     hbm, bf16, src = peaks()
     flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     rng = np.random.default_rng(2000)
-    lines = ["| N | pairs/row | C | mode | conv us | +quantise us | GB/s alg | frac HBM | TFLOP/s (TOPS) alg | frac tensor |",
-             "|---|---|---|---|---|---|---|---|---|---|"]
+    lines = ["| N | pairs/row | live offsets per tile (raster / key-sorted / grouped) | C | mode | conv us (raster order) | key-sorted us | grouped us | +quantise us | GB/s alg (best) | frac HBM | TFLOP/s (TOPS) alg (best) | frac tensor |",
+             "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
     rows = []
     for N in [int(v) for v in args.sizes.split(",")]:
         S = int(round(N ** 0.5))
@@ -52,6 +52,15 @@ def main():
         table = ops.hash_build(coords, None, grid)
         nbr, kmask = ops.rulebook_subm(coords, None, grid, 3, table, with_mask=True)
         pairs = int((nbr >= 0).sum().item())
+        # the same sites renumbered by key (what the engine does for stage 1) and, on top, the grouped rulebook
+        ws = torch.zeros(ops.rulebook_strided_workspace_bytes(grid, 1, 1, 0), dtype=torch.uint8, device=dev)
+        oc, n_out, _, _ = ops.renumber_by_key(coords, None, grid, ws)
+        index = ops.rulebook_strided_index(grid, 1, 1, 0, ws)
+        nbr_s, kmask_s = ops.rulebook_subm_ranked(oc, n_out, grid, 3, index)
+        nbr_g, kmask_g, perm_g = ops.rulebook_subm_ranked_grouped(oc, n_out, grid, 3, index)
+        tiles = ops.num_tiles(n)
+        live = lambda km: float(sum(bin(int(v) & 0xFFFFFFFF).count("1") for v in km[:tiles].cpu().numpy().ravel())) / tiles
+        live_txt = f"{live(kmask):.1f} / {live(kmask_s):.1f} / {live(kmask_g):.1f}"
         for C in [int(v) for v in args.channels.split(",")]:
             x = rng.normal(size=(n, C)).astype(np.float32)
             x[::100, 1 % C] *= 20
@@ -85,17 +94,34 @@ def main():
                         t_q.append(e[0].elapsed_time(e[1]) * 1e3)
                         t_conv.append(e[1].elapsed_time(e[2]) * 1e3)
                 tc, tq = float(np.median(t_conv)), float(np.median(t_q))
+                # tilings: key-sorted rows, and key-sorted + grouped by line key (bit-identical results)
+                alt = []
+                for nb_, km_, pm_ in ((nbr_s, kmask_s, None), (nbr_g, kmask_g, perm_g)):
+                    ts = []
+                    for it in range(args.iters + 1):
+                        flush_buf.zero_()
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record()
+                        ops.spconv_mma(feats, nb_, n, None, C, packed, scale, shift, act_scale=act_scale if i8 else None, relu=True, out=out, kmask=km_, row_perm=pm_)
+                        b.record()
+                        torch.cuda.synchronize()
+                        if it >= 1:
+                            ts.append(a.elapsed_time(b) * 1e3)
+                    alt.append(float(np.median(ts)))
                 b_act = 1 if i8 else 2
                 bytes_alg = n * C * b_act + n * C * 2 + 27 * C * C * b_act + 4 * pairs
                 flops = 2.0 * pairs * C * C
-                gbs = bytes_alg / (tc * 1e-6) / 1e9
-                tf = flops / (tc * 1e-6) / 1e12
+                tb = min(tc, alt[0], alt[1])
+                gbs = bytes_alg / (tb * 1e-6) / 1e9
+                tf = flops / (tb * 1e-6) / 1e12
                 tpk = 2 * bf16 if i8 else bf16
-                rows.append(dict(N=n, C=C, mode=mode, conv_us=tc, quant_us=tq, gbs=gbs, tflops=tf))
-                lines.append(f"| {n} | {pairs / n:.1f} | {C} | {mode} | {tc:.1f} | {tq:.1f} | {gbs:.0f} | {gbs / hbm:.3f} | {tf:.1f} | {tf / tpk:.3f} |")
+                rows.append(dict(N=n, C=C, mode=mode, conv_us=tc, sorted_us=alt[0], grouped_us=alt[1], quant_us=tq, gbs=gbs, tflops=tf))
+                lines.append(f"| {n} | {pairs / n:.1f} | {live_txt} | {C} | {mode} | {tc:.1f} | {alt[0]:.1f} | {alt[1]:.1f} | {tq:.1f} | {gbs:.0f} | {gbs / hbm:.3f} | {tf:.1f} | {tf / tpk:.3f} |")
                 print(lines[-1], flush=True)
     head = (f"# r01 - SubMConv3d layer sweep (BASELINE config 5), B200\n\n`python tools/layer_sweep.py --iters {args.iters}`; peaks ({src}): HBM {hbm} GB/s, "
             f"bf16 {bf16} TFLOP/s (INT8 fraction against 2x that); kernel = `k_spconv_ts`, L2 flushed between iterations, medians.\n"
+            "Three tilings of the same sites (bit-identical results): the generator's raster order (hash rulebook), rows renumbered by key (`ql_renumber_by_key`, "
+            "what the engine does for stage 1) and key-sorted + grouped by line key (`ql_rulebook_subm_ranked_grouped`); GB/s and TFLOP/s use the best of the three.\n"
             "GB/s and TFLOP/s are ALGORITHMIC (SURVEY.md 8d): every distinct input row once, every output row once, weights once, 4 B per pair; 2*pairs*C*C flops.\n\n")
     if args.md:
         open(args.md, "w").write(head + "\n".join(lines) + "\n")
