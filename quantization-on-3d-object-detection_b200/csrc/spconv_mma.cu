@@ -443,22 +443,27 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
             int64_t row = slot;
             if (p.row_perm) row = slot < n_out ? (int64_t)__ldg(p.row_perm + slot) : -1;
             const bool row_ok = row >= 0 && row < n_out;
-            // The residual row does not depend on the MMAs: its first 32 bytes are requested BEFORE the accumulator wait and every
-            // further chunk one iteration ahead, so the global-load latency is off the epilogue's critical path (the role trace,
-            // profiles/r01_conv_role_waits.md, showed the epilogue 80-90 % busy on every residual layer and the MMA thread waiting
-            // for accumulators up to 26 % of its time).
+            // The residual row does not depend on the MMAs: (kind::f16 instantiations) its first 32 bytes are requested BEFORE the
+            // accumulator wait and every further chunk one iteration ahead, so the global-load latency is off the epilogue's critical
+            // path (the role trace, profiles/r01_conv_role_waits.md, showed the epilogue 80-90 % busy on every residual layer and the
+            // MMA thread waiting for accumulators up to 26 % of its time).  The kind::i8 instantiations keep the load inside the
+            // column loop: with the early loads their abs-max epilogue (dynamic W8A8) ran 25 % slower on every layer.
             const bool has_res = p.residual != nullptr && row_ok;
             const uint4* res4 = has_res ? reinterpret_cast<const uint4*>(p.residual + row * p.c_out) : nullptr;
             uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
-            if (has_res) { ra = __ldg(res4); rb = __ldg(res4 + 1); }
+            if constexpr (!kInt8) {
+                if (has_res) { ra = __ldg(res4); rb = __ldg(res4 + 1); }
+            }
             ql_mbar_wait(ql_smem_u32(&misc->acc_full[a]), aph);
             ql_tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(a * p.c_out);
             for (int c0 = 0; c0 < p.c_out; c0 += 16) {
                 uint32_t v[16];
                 ql_tmem_ld16(taddr + (uint32_t)c0, v);
-                const uint4 rc = ra, rd = rb;                          // this iteration's residual chunk; request the next one now
-                if (has_res && c0 + 16 < p.c_out) { ra = __ldg(res4 + (c0 + 16) / 8); rb = __ldg(res4 + (c0 + 16) / 8 + 1); }
+                uint4 rc = ra, rd = rb;                                // this iteration's residual chunk
+                if constexpr (!kInt8) {                                // ... and the next one requested now
+                    if (has_res && c0 + 16 < p.c_out) { ra = __ldg(res4 + (c0 + 16) / 8); rb = __ldg(res4 + (c0 + 16) / 8 + 1); }
+                }
                 ql_tmem_ld_wait();
                 if (p.out_dtype == QL_S32) {
                     if (row_ok) {
@@ -475,6 +480,7 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
                     y[j] = fmaf(acc, s_scale[c0 + j], s_shift[c0 + j]);
                 }
                 if (has_res) {
+                    if constexpr (kInt8) { rc = res4[c0 / 8]; rd = res4[c0 / 8 + 1]; }
                     const __half2* h = reinterpret_cast<const __half2*>(&rc);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
