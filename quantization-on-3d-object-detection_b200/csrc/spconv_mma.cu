@@ -205,6 +205,31 @@ __device__ __forceinline__ void tmem_st_16x256b<4>(uint32_t taddr, const uint32_
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// the two halves of load_tile_mask: issue the loads now, use them (count / fix-up) later -- a warp issues in order, so a popcount
+// right behind its load costs the loader one global round trip per tile
+__device__ __forceinline__ void load_tile_mask_raw(const ConvParams& p, int64_t tile, uint32_t (&mask)[kMaskWords]) {
+#pragma unroll
+    for (int i = 0; i < kMaskWords; ++i) {
+        uint32_t w = 0u;
+        if (i < p.mask_words) {
+            if (p.kmask) {
+                w = __ldg(p.kmask + tile * p.mask_words + i);
+            } else {
+                const int rem = p.kvol - 32 * i;
+                w = rem >= 32 ? 0xFFFFFFFFu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
+            }
+        }
+        mask[i] = w;
+    }
+}
+__device__ __forceinline__ int finish_tile_mask(uint32_t (&mask)[kMaskWords]) {
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < kMaskWords; ++i) n += __popc(mask[i]);
+    if (n == 0) { mask[0] = 1u; n = 1; }       // a tile without pairs still has to zero its accumulators
+    return n;
+}
+
 __device__ __forceinline__ int load_tile_mask(const ConvParams& p, int64_t tile, uint32_t (&mask)[kMaskWords]) {
     int n = 0;
 #pragma unroll
@@ -681,17 +706,19 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
         int64_t pf_tile = blockIdx.x;
         uint32_t pf_it = 0;
         uint32_t pf_mask[kMaskWords];
-        int pf_off = pf_tile < n_tiles ? load_tile_mask(p, pf_tile, pf_mask) : 0;
+#pragma unroll
+        for (int i = 0; i < kMaskWords; ++i) pf_mask[i] = 0u;
+        if (pf_tile < n_tiles) load_tile_mask_raw(p, pf_tile, pf_mask);
         auto prefetch_step = [&]() {
             if (pf_tile >= n_tiles) return;
             uint32_t m[kMaskWords];
 #pragma unroll
             for (int i = 0; i < kMaskWords; ++i) m[i] = pf_mask[i];
-            const int n_off = pf_off;
+            const int n_off = finish_tile_mask(m);                 // first use of the words requested one step ago
             const int64_t t = pf_tile;
             const uint32_t itn = pf_it;
             pf_tile += gridDim.x; ++pf_it;
-            if (pf_tile < n_tiles) pf_off = load_tile_mask(p, pf_tile, pf_mask);
+            if (pf_tile < n_tiles) load_tile_mask_raw(p, pf_tile, pf_mask);   // the next tile's words: requested, not looked at
             prefetch_nbr(t, itn, m, n_off);
         };
         for (int i = 0; i < p.nbr_bufs - 1; ++i) prefetch_step();
