@@ -102,7 +102,10 @@ int ql_mean_vfe(const float* voxels, const void* num_points, int32_t num_points_
  *      Layout produced: nbr[tile][k][128] int32, tile = row/128: the input row feeding output row
  *      tile*128+r through kernel offset k = (kz*KH+ky)*KW+kx, or -1.  ksize/stride/pad are zyx triples.
  *      tile_kmask (nullable): uint32 [tiles][ql_rulebook_mask_words(kvol)], bit k set iff some row of the tile has a
- *      neighbour through offset k (the conv kernel skips the empty slabs).
+ *      neighbour through offset k.  WITH a mask the rulebook is COMPACT: only a tile's live slabs are written, first in
+ *      the tile's block and in ascending k -- nbr[tile][j][128], j = number of set mask bits below k; the block keeps its
+ *      kvol*512-byte stride and the slabs past popc(mask) are undefined.  The conv kernels take (nbr, tile_kmask) pairs
+ *      in exactly this form (tile_kmask == NULL: the dense layout, every offset visited).
  *      Submanifold: outputs == inputs (same rows); neighbours are found by open-addressing hash probes on `table`.
  *      Strided: active output sites are numbered in ascending order of the linear key ((b*Do+z)*Ho+y)*Wo+x (spconv
  *      leaves the order implementation-defined); out_table receives out coords -> row for the layers that follow.
@@ -176,8 +179,8 @@ int ql_rulebook_subm_ranked_grouped(const int32_t* coords, int64_t n_cap, const 
  *      post_act_block / SparseBasicBlock, spconv_backbone.py:8-27,51-67).
  *      feats: [n_in, c_in] fp16 (kind::f16, fp32 accumulate) or int8 codes (kind::i8, int32 accumulate); the gathered
  *      rows go global -> registers -> tensor memory (A operand read from TMEM), never through shared memory.
- *      nbr / tile_kmask: a rulebook from ql_rulebook_subm / ql_rulebook_strided; tile_kmask may be NULL (every
- *      offset is visited); kvol <= 128.
+ *      nbr / tile_kmask: a rulebook from ql_rulebook_subm / ql_rulebook_strided (compact when tile_kmask is given);
+ *      tile_kmask may be NULL (dense rulebook, every offset is visited); kvol <= 128.
  *      w_packed: per-output-channel int8 codes (as fp16 exact integers for the f16 kind) in the shared-memory
  *      image built by ql_pack_weights_host.  Epilogue: y = acc * (scale[oc] * (act_scale_dev ? *act_scale_dev : 1))
  *      + shift[oc] (+ residual) ; optional ReLU; written as out_dtype (QL_F16/QL_F32) -- or the raw
@@ -217,7 +220,7 @@ int ql_permute_rows(const void* in, void* out, int32_t row_bytes, const int32_t*
 /* ---- fp32 SIMT stem conv for the un-quantized conv_input (C_in = 4/5 raw point features; quant_centerpoint.py
  *      backbone_no_list = ['backbone_3d.conv_input.0'], :24-26).  feats rows are feat_stride floats apart;
  *      w: [kvol][c_in][c_out] fp32. */
-int ql_stem_conv(const float* feats, int32_t feat_stride, int32_t c_in, const int32_t* nbr, int64_t n_out_cap, const int32_t* n_out_dev,
+int ql_stem_conv(const float* feats, int32_t feat_stride, int32_t c_in, const int32_t* nbr, const uint32_t* tile_kmask, int64_t n_out_cap, const int32_t* n_out_dev,
                  int32_t c_out, int32_t kvol, const float* w, const float* scale, const float* shift, int32_t relu,
                  void* out, int32_t out_dtype, float* absmax, ql_stream_t stream);
 

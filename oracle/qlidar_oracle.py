@@ -28,6 +28,7 @@ set, strided out-set = dilate o subsample).
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -798,3 +799,153 @@ def synth_surface_sheet(S: int, seed: int = 2000, depth: int = 40) -> np.ndarray
     z = np.clip(depth // 2 + steps_y + steps_x, 0, depth - 1)
     yy, xx = np.meshgrid(np.arange(S), np.arange(S), indexing="ij")
     return np.stack([np.zeros(S * S, np.int64), z.ravel(), yy.ravel(), xx.ravel()], axis=1).astype(np.int32)
+
+
+# ----------------------------------------------------------------------------------------------
+# Kernel-numerics mirror (W8A8 per-tensor): the SAME network as backbone_forward(mode="w8a8_pt"), with the inter-layer
+# arithmetic restated the way the device performs it, so that int8 CODES and INT32 accumulators can be compared with the
+# CUDA path bit for bit through all 21 layers (a plain fp32 restatement diverges chaotically: one fp16-vs-fp32 ulp flips a
+# round-half-even decision, and every flipped code is 0.8 % of amax).  What is mirrored -- and nothing else differs from
+# qconv_w8a8_pt + bn_relu:
+#   * activations are STORED as fp16 between layers (round-to-nearest-even of the fp32 epilogue value);
+#   * de-quantisation + BatchNorm1d (eval, spconv_backbone.py:16-17,56-65) are one folded fp32 FMA per element,
+#     y = fmaf(float(acc), (amax_w[oc]/127 * a[oc]) * (amax_x/127), bias[oc]*a[oc] + b[oc]), a = gamma/sqrt(var+eps), b = beta - a*mean,
+#     then + fp16 residual (SparseBasicBlock, :64), then ReLU;
+#   * dynamic amax (quant/quant.py:28-32, axis=None) is the max of the PRODUCING layer's fp32 values before the fp16 store;
+#     static amax (quantize.py:175-207) is the calibrated scalar, and a layer fed by another conv takes its codes from that
+#     conv's fp32 epilogue values, rint(y * (127/amax)), instead of re-reading the fp16 rows;
+#   * the un-quantised stem (no_list, quant_centerpoint.py:24-26) accumulates in fp32 FMAs over (k, ic) ascending.
+# The exact-FMA pieces are C (oracle/qloracle_c.c).
+# ----------------------------------------------------------------------------------------------
+_QLO = None
+
+
+def _qlo():
+    global _QLO
+    if _QLO is None:
+        import ctypes
+        import subprocess
+        here = os.path.dirname(os.path.abspath(__file__))
+        so = os.path.join(here, "libqloracle.so")
+        if not os.path.exists(so):
+            subprocess.run(["make", "-s", "-C", here], check=True)
+        lib = ctypes.CDLL(so)
+        vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+        lib.qlo_stem_conv.argtypes = [vp, i64, i32, vp, i32, i64, vp, i32, vp, vp, i32, vp]
+        lib.qlo_stem_conv.restype = None
+        lib.qlo_epilogue.argtypes = [vp, i64, i32, vp, vp, vp, i32, vp]
+        lib.qlo_epilogue.restype = None
+        _QLO = lib
+    return _QLO
+
+
+def _f32c(a) -> np.ndarray:
+    return np.ascontiguousarray(a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a, dtype=np.float32)
+
+
+def mirror_codes(x32: np.ndarray, amax: np.float32, bits: int = 8) -> np.ndarray:
+    """int8 codes the way the device computes them: scale = fl(bound / amax) (0 if amax <= 2^-24), q = clamp(rint(fl(x * scale)))."""
+    bound = np.float32(quant_bound(bits))
+    amax = np.float32(amax)
+    scale = np.float32(0.0) if amax <= np.float32(1.0 / (1 << 24)) else np.float32(bound / amax)
+    q = np.rint(x32.astype(np.float32) * scale)
+    return np.clip(q, -bound, bound).astype(np.int8)
+
+
+def mirror_stem(x: np.ndarray, nbr: np.ndarray, weight: torch.Tensor, scale, shift, relu=True) -> np.ndarray:
+    oc, ic = weight.shape[0], weight.shape[-1]
+    K, n = nbr.shape
+    w_kio = _f32c(weight.reshape(oc, K, ic).permute(1, 2, 0))
+    x = _f32c(x)
+    nb = np.ascontiguousarray(nbr, dtype=np.int32)
+    sc, sh = _f32c(scale), _f32c(shift)
+    y = np.empty((n, oc), dtype=np.float32)
+    _qlo().qlo_stem_conv(x.ctypes.data, x.shape[1], ic, nb.ctypes.data, K, n, w_kio.ctypes.data, oc, sc.ctypes.data, sh.ctypes.data,
+                         1 if relu else 0, y.ctypes.data)
+    return y
+
+
+def mirror_epilogue(acc: np.ndarray, s, shift, residual_h: Optional[np.ndarray], relu=True) -> np.ndarray:
+    acc = np.ascontiguousarray(acc, dtype=np.int32)
+    n, c = acc.shape
+    s, sh = _f32c(s), _f32c(shift)
+    res = None if residual_h is None else np.ascontiguousarray(residual_h.astype(np.float32))
+    y = np.empty((n, c), dtype=np.float32)
+    _qlo().qlo_epilogue(acc.ctypes.data, n, c, s.ctypes.data, sh.ctypes.data, None if res is None else res.ctypes.data, 1 if relu else 0,
+                        y.ctypes.data)
+    return y
+
+
+def mirror_backbone_w8a8_pt(prog, params, features, coords: np.ndarray, sparse_shape, batch_size: int,
+                            no_list=("conv_input.0",), act_amax: Optional[Dict[str, float]] = None, bits: int = 8):
+    """Returns (record, encoded SpT with fp16-valued features).  record[name] = dict(codes int8 (N_in, C_in) or None for the
+    stem, acc int32 or None, y32 fp32 epilogue values, out fp16, out_coords, amax_in).  act_amax: calibrated per-layer scalar
+    amax (static); None = dynamic."""
+    x = SpT(None, coords.astype(np.int32), list(sparse_shape), batch_size)
+    x_h = None                                   # stored activations (fp16) of the current tensor
+    y32_prev = None                              # fp32 epilogue values they were rounded from
+    prev_was_conv = False                        # the previous layer is a tensor-core conv (its epilogue can emit codes)
+    rec: Dict[str, dict] = {}
+    feats32 = _f32c(features)
+    bound = np.float32(quant_bound(bits))
+
+    def one_conv(x: SpT, spec: ConvSpec, bnname: str, eps: float, residual_h):
+        nonlocal x_h, y32_prev, prev_was_conv
+        if spec.key in x.rulebooks:
+            out_coords, out_shape, nbr = x.rulebooks[spec.key]
+        else:
+            if spec.subm:
+                out_coords, out_shape, nbr = x.coords, x.spatial_shape, rulebook_subm(x.coords, x.spatial_shape, spec.ksize)
+            else:
+                out_coords, out_shape, nbr = rulebook_strided(x.coords, x.spatial_shape, spec.ksize, spec.stride, spec.pad)
+            x.rulebooks[spec.key] = (out_coords, out_shape, nbr)
+        w = params[spec.name + ".weight"].float()
+        a, b = bn_fold(params[bnname + ".weight"].float(), params[bnname + ".bias"].float(), params[bnname + ".running_mean"].float(),
+                       params[bnname + ".running_var"].float(), eps)
+        bias = params[spec.name + ".bias"].float() if spec.bias else torch.zeros(spec.cout)
+        shift = bias * a + b
+        if spec.name in no_list:
+            if x_h is not None:
+                raise ValueError("only the stem may be left un-quantised in the mirror")
+            y32 = mirror_stem(feats32, nbr, w, a, shift)
+            r = dict(codes=None, acc=None, amax_in=None)
+            prev_conv_now = False
+        else:
+            static = act_amax is not None and spec.name in act_amax
+            if static:
+                m = np.float32(act_amax[spec.name])
+            else:
+                m = np.float32(np.abs(y32_prev).max()) if y32_prev.size else np.float32(0)
+            if static and prev_was_conv:
+                qscale = np.float32(0.0) if m <= np.float32(1.0 / (1 << 24)) else np.float32(bound / m)
+                codes = np.clip(np.rint(y32_prev * qscale), -bound, bound).astype(np.int8)     # the producing epilogue's out_q
+            else:
+                codes = mirror_codes(x_h.astype(np.float32), m, bits)
+            act_scale = np.float32(m / bound)
+            qw, amax_w = quantize_weight_per_oc(w, 8)
+            acc = sparse_conv_int(torch.from_numpy(codes), nbr, qw).numpy()
+            s = _f32c((amax_w / quant_bound(8)) * a) * act_scale
+            y32 = mirror_epilogue(acc, s, shift, residual_h)
+            r = dict(codes=codes, acc=acc, amax_in=m)
+            prev_conv_now = True
+        out_h = y32.astype(np.float16)
+        r.update(y32=y32, out=out_h, out_coords=out_coords)
+        rec[spec.name] = r
+        x_h, y32_prev, prev_was_conv = out_h, y32, prev_conv_now
+        return SpT(None, out_coords, list(out_shape), x.batch_size, x.rulebooks if spec.subm else {})
+
+    taps = {}
+    for op in prog:
+        kind = op["op"]
+        if kind == "conv_bn_relu":
+            x = one_conv(x, op["conv"], op["bn"], op.get("bn_eps", 1e-3), None)
+        elif kind == "basic_block":
+            identity_h = x_h
+            x = one_conv(x, op["conv1"], op["bn1"], 1e-3, None)
+            x = one_conv(x, op["conv2"], op["bn2"], 1e-3, identity_h)
+        elif kind == "tap":
+            taps[op["name"]] = (x.coords, x_h)
+        else:
+            raise ValueError(f"mirror: unsupported op {kind}")
+    out = SpT(torch.from_numpy(x_h.astype(np.float32)), x.coords, x.spatial_shape, batch_size)
+    return rec, out, taps

@@ -25,7 +25,17 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, ablate: bool = False) -> str:
+    """ablate=True builds the TEST-TIME variant libqlidar_b200_ablate.so (-DQL_SPCONV_ABLATE: the conv kernel's stages can be
+    switched off one by one, tools/conv_sweep.py); the product library never contains those switches."""
+    if ablate:
+        out = OUT.replace(".so", "_ablate.so")
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        r = subprocess.run([nvcc] + NVCC_FLAGS + ["-DQL_SPCONV_ABLATE", "-o", out] + [os.path.join(CSRC, s) for s in SOURCES], capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed building the ablation variant")
+        return out
     if not force and not _stale():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -39,4 +49,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, ablate="--ablate" in sys.argv))

@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256) k_fake_quant_per_row(const void* x, int i
 // load per neighbour instead of C_IN scalar loads.  C_IN == 0: generic width, scalar loads.
 template <int C_OUT, int C_IN, bool kRow8>
 __global__ void __launch_bounds__(QL_TILE_M) k_stem_conv(const float* __restrict__ feats, int fstride, int c_in, const int* __restrict__ nbr,
-                                                         int64_t n_cap, const int* __restrict__ n_dev, int kvol,
+                                                         const uint32_t* __restrict__ kmask, int64_t n_cap, const int* __restrict__ n_dev, int kvol,
                                                          const float* __restrict__ w, const float* __restrict__ scale,
                                                          const float* __restrict__ shift, int relu, void* out, int out_dtype,
                                                          float* absmax) {
@@ -238,11 +238,36 @@ __global__ void __launch_bounds__(QL_TILE_M) k_stem_conv(const float* __restrict
 #pragma unroll
         for (int c = 0; c < C_OUT; ++c) acc[j][c] = 0.f;
     if (tile_live) {
+        // compact rulebook: the tile's live offsets (bits of its mask, ascending k) are slabs 0, 1, ...; no mask = every offset
         const int* nb = nbr + tile * (int64_t)kvol * QL_TILE_M + lane;
+        const int mask_words = (kvol + 31) >> 5;
+        uint32_t mw[QL_MASK_WORDS_MAX];
+        int n_live = 0;
+#pragma unroll
+        for (int i = 0; i < QL_MASK_WORDS_MAX; ++i) {
+            uint32_t w = 0u;
+            if (i < mask_words) {
+                const int rem = kvol - 32 * i;
+                w = kmask ? __ldg(kmask + tile * mask_words + i) : (rem >= 32 ? 0xFFFFFFFFu : ((1u << rem) - 1u));
+            }
+            mw[i] = w;
+            n_live += __popc(w);
+        }
         int idx_next[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) idx_next[j] = __ldg(nb + j * 32);
-        for (int k = 0; k < kvol; ++k) {
+        for (int j = 0; j < R; ++j) idx_next[j] = n_live > 0 ? __ldg(nb + j * 32) : -1;
+        int wi = 0;
+        uint32_t cur = mw[0];
+        for (int s = 0; s < n_live; ++s) {
+            while (cur == 0u) {
+                ++wi;
+                cur = 0u;
+#pragma unroll
+                for (int i = 1; i < QL_MASK_WORDS_MAX; ++i)
+                    if (i == wi) cur = mw[i];
+            }
+            const int k = wi * 32 + __ffs((int)cur) - 1;
+            cur &= cur - 1u;
             int idx[R];
             bool any = false;
 #pragma unroll
@@ -250,9 +275,9 @@ __global__ void __launch_bounds__(QL_TILE_M) k_stem_conv(const float* __restrict
                 idx[j] = idx_next[j];
                 any |= idx[j] >= 0;
             }
-            if (k + 1 < kvol) {
+            if (s + 1 < n_live) {
 #pragma unroll
-                for (int j = 0; j < R; ++j) idx_next[j] = __ldg(nb + (k + 1) * QL_TILE_M + j * 32);
+                for (int j = 0; j < R; ++j) idx_next[j] = __ldg(nb + (s + 1) * QL_TILE_M + j * 32);
             }
             if (!__any_sync(0xffffffffu, any)) continue;
             float x[R][kRow8 ? 8 : CI];
@@ -332,7 +357,7 @@ thread_local char g_last_cuda_error[256] = "";
 
 }  // namespace
 
-extern "C" int ql_abi_version(void) { return 2; }
+extern "C" int ql_abi_version(void) { return 3; }
 
 extern "C" const char* ql_error_string(int code) {
     switch (code) {
@@ -399,7 +424,7 @@ extern "C" int ql_quantize_rows(const void* x, int32_t in_dtype, int64_t n_cap, 
     return QL_OK;
 }
 
-extern "C" int ql_stem_conv(const float* feats, int32_t feat_stride, int32_t c_in, const int32_t* nbr, int64_t n_out_cap, const int32_t* n_out_dev,
+extern "C" int ql_stem_conv(const float* feats, int32_t feat_stride, int32_t c_in, const int32_t* nbr, const uint32_t* tile_kmask, int64_t n_out_cap, const int32_t* n_out_dev,
                             int32_t c_out, int32_t kvol, const float* w, const float* scale, const float* shift, int32_t relu,
                             void* out, int32_t out_dtype, float* absmax, ql_stream_t stream_) {
     if (!feats || !nbr || !w || !scale || !shift || !out) return QL_ERR_INVALID;
@@ -416,7 +441,7 @@ extern "C" int ql_stem_conv(const float* feats, int32_t feat_stride, int32_t c_i
         if (smem > 48 * 1024 &&                                                                                                    \
             cudaFuncSetAttribute(k_stem_conv<CO, CI, R8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)  \
             return QL_ERR_CUDA;                                                                                                    \
-        k_stem_conv<CO, CI, R8><<<tiles, QL_TILE_M, smem, st>>>(feats, feat_stride, c_in, nbr, n_out_cap, n_out_dev, kvol, w, scale, \
+        k_stem_conv<CO, CI, R8><<<tiles, QL_TILE_M, smem, st>>>(feats, feat_stride, c_in, nbr, tile_kmask, n_out_cap, n_out_dev, kvol, w, scale, \
                                                                 shift, relu, out, out_dtype, absmax);                              \
     } while (0)
 #define QL_STEM_CI(CO, CI)                     \

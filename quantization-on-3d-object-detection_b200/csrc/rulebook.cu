@@ -11,7 +11,11 @@
 // offsets before resolving any of them, so ~9 independent 8-byte table loads are in flight per lane.
 //
 // Every rulebook also emits a per-tile offset mask (bit k of kmask[tile] set iff some row of the tile has a
-// neighbour through offset k): the conv kernel skips the empty (tile, offset) slabs.
+// neighbour through offset k), and with a mask the rulebook is COMPACT: a tile's live slabs are stored first, in
+// ascending k ([tile][j][128], j = rank of k among the mask's set bits; the tile's block keeps its K*512-byte stride).
+// The empty (tile, offset) slabs -- 60 % of them on the backbone's key-sorted stages -- are neither written here nor
+// read by the conv kernel, whose loader fetches a unit's slabs with one contiguous bulk copy.  Without a mask
+// (tile_kmask == NULL) the layout is the dense nbr[tile][k][128].
 #include "ql_common.cuh"
 #include "ql_scan.cuh"
 
@@ -25,13 +29,32 @@ struct ConvGeom {
 
 constexpr int kProbeBatch = 9;
 
+// Compact write-out of one tile: thread r holds its column of the dense [K][128] block in the shared-memory stash
+// s_res[k * 128 + r]; the live offsets (bits of s_mask, complete after the barrier) go to slabs 0, 1, ... of the tile.
+__device__ __forceinline__ void write_compact_tile(const int* s_res, const uint32_t* s_mask, int mask_words, int r, int* dst,
+                                                   uint32_t* kmask_tile) {
+    __syncthreads();
+    int j = 0;
+    for (int w = 0; w < mask_words; ++w) {
+        uint32_t m = s_mask[w];
+        while (m) {
+            const int b = __ffs((int)m) - 1;
+            m &= m - 1u;
+            dst[(int64_t)j * QL_TILE_M] = s_res[(w * 32 + b) * QL_TILE_M + r];
+            ++j;
+        }
+    }
+    if (r < mask_words) kmask_tile[r] = s_mask[r];
+}
+
 // nbr for output rows: in = out*stride - pad + offset, looked up in the input table.
 __global__ void __launch_bounds__(QL_TILE_M) k_rb_pairs(const int4* __restrict__ out_coords, int64_t n_cap,
                                                         const int* __restrict__ n_dev, QlGrid gin, ConvGeom cg,
                                                         const uint2* __restrict__ table, uint32_t cap_mask,
                                                         int* __restrict__ nbr, uint32_t* __restrict__ kmask) {
     __shared__ uint32_t s_mask[QL_MASK_WORDS_MAX];
-    const int64_t n = n_dev ? (int64_t)*n_dev : n_cap;
+    extern __shared__ int s_res[];                           // [K][128] stash of the tile when the output is compact (kmask)
+    const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
     const int64_t tile = blockIdx.x;
     if (tile * QL_TILE_M >= n) return;                       // tiles past the device-side row count are never read
     const int r = threadIdx.x;
@@ -74,15 +97,13 @@ __global__ void __launch_bounds__(QL_TILE_M) k_rb_pairs(const int4* __restrict__
                 }
                 if (ee.x == key[j]) res = (int)ee.y;
             }
-            dst[(int64_t)k * QL_TILE_M] = res;
+            if (kmask) s_res[k * QL_TILE_M + r] = res;
+            else dst[(int64_t)k * QL_TILE_M] = res;
             const uint32_t any = __ballot_sync(0xffffffffu, res >= 0);
             if (any && (threadIdx.x & 31) == 0) atomicOr(&s_mask[k >> 5], 1u << (k & 31));
         }
     }
-    if (kmask) {
-        __syncthreads();
-        if (r < mask_words) kmask[tile * mask_words + r] = s_mask[r];
-    }
+    if (kmask) write_compact_tile(s_res, s_mask, mask_words, r, dst, kmask + tile * mask_words);
 }
 
 // Submanifold rulebook over a KEY-SORTED site list (every stage a strided conv produced): the neighbour lookup is a rank
@@ -99,6 +120,7 @@ __global__ void __launch_bounds__(QL_TILE_M) k_rb_pairs_ranked(const int4* __res
                                                                const int* __restrict__ n_in_dev,
                                                                const int* __restrict__ row_perm) {
     __shared__ uint32_t s_mask[QL_MASK_WORDS_MAX];
+    extern __shared__ int s_res[];                                   // [K][128] stash of the tile when the output is compact (kmask)
     const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
     const int64_t n_in = n_in_dev ? min((int64_t)*n_in_dev, n_in_cap) : n_in_cap;
     const int64_t tile = blockIdx.x;
@@ -136,16 +158,14 @@ __global__ void __launch_bounds__(QL_TILE_M) k_rb_pairs_ranked(const int4* __res
                     }
                 }
                 const int k = (kz * cg.kh + ky) * cg.kw + kx;
-                dst[(int64_t)k * QL_TILE_M] = res;
+                if (kmask) s_res[k * QL_TILE_M + r] = res;
+                else dst[(int64_t)k * QL_TILE_M] = res;
                 const uint32_t any = __ballot_sync(0xffffffffu, res >= 0);
                 if (any && (threadIdx.x & 31) == 0) atomicOr(&s_mask[k >> 5], 1u << (k & 31));
             }
         }
     }
-    if (kmask) {
-        __syncthreads();
-        if (r < mask_words) kmask[tile * mask_words + r] = s_mask[r];
-    }
+    if (kmask) write_compact_tile(s_res, s_mask, mask_words, r, dst, kmask + tile * mask_words);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -334,8 +354,10 @@ __global__ void __launch_bounds__(256) k_rb_scatter(const int4* __restrict__ in_
     });
 }
 
-// per-tile offset mask of a finished rulebook: one CTA per live tile, thread r reads nbr[tile][k][r] for every k
-__global__ void __launch_bounds__(QL_TILE_M) k_rb_kmask(const int* __restrict__ nbr, int K, const int* __restrict__ n_out_dev,
+// per-tile offset mask of a finished DENSE rulebook, which is then compacted in place: one CTA per live tile, thread r
+// reads nbr[tile][k][r] for every k; afterwards it moves its column's live entries to slabs 0, 1, ... (slab j <= k is
+// written after slab k was read and is never read again, and a thread only touches its own column: in place is safe)
+__global__ void __launch_bounds__(QL_TILE_M) k_rb_kmask(int* nbr, int K, const int* __restrict__ n_out_dev,
                                                         int64_t n_out_cap, uint32_t* __restrict__ kmask, int mask_words) {
     __shared__ uint32_t s_mask[QL_MASK_WORDS_MAX];
     const int64_t n = min((int64_t)*n_out_dev, n_out_cap);
@@ -343,7 +365,7 @@ __global__ void __launch_bounds__(QL_TILE_M) k_rb_kmask(const int* __restrict__ 
     if (tile * QL_TILE_M >= n) return;
     if (threadIdx.x < mask_words) s_mask[threadIdx.x] = 0u;
     __syncthreads();
-    const int* src = nbr + tile * (int64_t)K * QL_TILE_M + threadIdx.x;
+    int* src = nbr + tile * (int64_t)K * QL_TILE_M + threadIdx.x;
     for (int k0 = 0; k0 < K; k0 += 9) {
         int v[9];
 #pragma unroll
@@ -356,6 +378,24 @@ __global__ void __launch_bounds__(QL_TILE_M) k_rb_kmask(const int* __restrict__ 
     }
     __syncthreads();
     if (threadIdx.x < mask_words) kmask[tile * mask_words + threadIdx.x] = s_mask[threadIdx.x];
+    int j = 0;
+    for (int w = 0; w < mask_words; ++w) {
+        uint32_t m = s_mask[w];
+        while (m) {
+            const int k = w * 32 + __ffs((int)m) - 1;
+            m &= m - 1u;
+            if (j != k) src[(int64_t)j * QL_TILE_M] = __ldcg(src + (int64_t)k * QL_TILE_M);
+            ++j;
+        }
+    }
+}
+
+// dynamic shared memory of the pair kernels: the [K][128] stash of a compact build (opt-in above 48 KB)
+template <class Kern>
+inline bool stash_smem(Kern kern, int K, bool compact, size_t& bytes) {
+    bytes = compact ? (size_t)K * QL_TILE_M * sizeof(int) : 0;
+    if (bytes > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return false;
+    return true;
 }
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -387,7 +427,9 @@ extern "C" int ql_rulebook_subm(const int32_t* coords, int64_t n_cap, const int3
     if (n_cap <= 0) return QL_OK;
     QlGrid g{B, D, H, W};
     unsigned tiles = (unsigned)ql_rulebook_num_tiles(n_cap);
-    k_rb_pairs<<<tiles, QL_TILE_M, 0, (cudaStream_t)stream_>>>((const int4*)coords, n_cap, n_dev, g, cg, (const uint2*)table,
+    size_t stash;
+    if (!stash_smem(k_rb_pairs, cg.kd * cg.kh * cg.kw, tile_kmask != nullptr, stash)) return QL_ERR_CUDA;
+    k_rb_pairs<<<tiles, QL_TILE_M, stash, (cudaStream_t)stream_>>>((const int4*)coords, n_cap, n_dev, g, cg, (const uint2*)table,
                                                                (uint32_t)(table_cap - 1), nbr_out, tile_kmask);
     QL_CUDA_CHECK_LAST();
     return QL_OK;
@@ -528,7 +570,9 @@ extern "C" int ql_rulebook_subm_ranked(const int32_t* coords, int64_t n_cap, con
     if (n_cap <= 0) return QL_OK;
     QlGrid g{B, D, H, W};
     unsigned tiles = (unsigned)ql_rulebook_num_tiles(n_cap);
-    k_rb_pairs_ranked<<<tiles, QL_TILE_M, 0, (cudaStream_t)stream_>>>((const int4*)coords, n_cap, n_dev, g, cg, bitmap, word_prefix,
+    size_t stash;
+    if (!stash_smem(k_rb_pairs_ranked, cg.kd * cg.kh * cg.kw, tile_kmask != nullptr, stash)) return QL_ERR_CUDA;
+    k_rb_pairs_ranked<<<tiles, QL_TILE_M, stash, (cudaStream_t)stream_>>>((const int4*)coords, n_cap, n_dev, g, cg, bitmap, word_prefix,
                                                                       nbr_out, tile_kmask, n_cap, n_dev, nullptr);
     QL_CUDA_CHECK_LAST();
     return QL_OK;
@@ -643,7 +687,9 @@ extern "C" int ql_rulebook_subm_ranked_grouped(const int32_t* coords, int64_t n_
     k_rb_linekey<<<blocks, 256, 0, st>>>((const int4*)coords, n_cap, n_dev, g, cg, bitmap, keys, hist);
     k_scan_blocks<<<1, QL_SCAN_THREADS, 0, st>>>((int*)hist, kGroupBins, nullptr, nullptr, 0);
     k_rb_group_scatter<<<blocks, 256, 0, st>>>(keys, n_cap, n_dev, hist, row_perm_out);
-    k_rb_pairs_ranked<<<tiles, QL_TILE_M, 0, st>>>((const int4*)coords, n_cap, n_dev, g, cg, bitmap, word_prefix, nbr_out, tile_kmask,
+    size_t stash;
+    if (!stash_smem(k_rb_pairs_ranked, cg.kd * cg.kh * cg.kw, tile_kmask != nullptr, stash)) return QL_ERR_CUDA;
+    k_rb_pairs_ranked<<<tiles, QL_TILE_M, stash, st>>>((const int4*)coords, n_cap, n_dev, g, cg, bitmap, word_prefix, nbr_out, tile_kmask,
                                                    n_cap, n_dev, row_perm_out);
     QL_CUDA_CHECK_LAST();
     return QL_OK;
@@ -821,7 +867,9 @@ extern "C" int ql_rulebook_strided_ranked(const int32_t* in_coords, int64_t n_in
                                                               nullptr, 0u);
     // pairs from the output side through the INPUT stage's rank index: every (tile, offset) slab is written exactly once
     QlGrid gin_grid{B, D, H, W};
-    k_rb_pairs_ranked<<<(unsigned)ql_rulebook_num_tiles(n_out_cap), QL_TILE_M, 0, st>>>((const int4*)out_coords, n_out_cap, n_out_dev,
+    size_t stash;
+    if (!stash_smem(k_rb_pairs_ranked, cg.kd * cg.kh * cg.kw, tile_kmask != nullptr, stash)) return QL_ERR_CUDA;
+    k_rb_pairs_ranked<<<(unsigned)ql_rulebook_num_tiles(n_out_cap), QL_TILE_M, stash, st>>>((const int4*)out_coords, n_out_cap, n_out_dev,
                                                                                         gin_grid, cg, in_bitmap, in_word_prefix, nbr_out,
                                                                                         tile_kmask, n_in_cap, n_in_dev, nullptr);
     QL_CUDA_CHECK_LAST();

@@ -5,64 +5,68 @@
 //
 // One persistent CTA per SM walks 128-row output tiles.  Per tile the conv is a sum of per-offset GEMMs
 //     D[128, C_out] += A_k[128, C_in] . W_k[C_out, C_in]^T      for every kernel offset k that is non-empty in the tile
-// (the rulebook's per-tile offset mask lists them; empty (tile, offset) slabs cost nothing).  The A operand never
-// exists in memory and never touches shared memory: output row r of the tile is TMEM lane r; gather producers load the
-// neighbours' feature rows straight from global memory (L1/L2) into registers and write them to tensor memory with
-// tcgen05.st; the MMA reads A from TMEM (the ".ts" operand form) and only the weights from shared memory.
+// (the rulebook's per-tile offset mask lists them; the rulebook is COMPACT: only the live (tile, offset) slabs exist).
+// The A operand never exists in memory and never touches shared memory: output row r of the tile is TMEM lane r; gather
+// producers load the neighbours' feature rows straight from global memory (L1/L2) into registers and write them to
+// tensor memory with tcgen05.st; the MMA reads A from TMEM (the ".ts" operand form) and only the weights from shared memory.
 //
 // K is cut into sub-chunks: one sub-chunk = one kernel offset x one <=128-byte segment of the input row
-// (CH = 32 / 64 / 128 bytes => 1 / 2 / 4 MMA k-steps).  128/CH consecutive sub-chunks form a UNIT = 32 TMEM columns x 128
-// lanes (16 KB of A).  Units flow through a ring of up to 8 TMEM slots, each with its own full/empty mbarrier pair, so
-// every producer warp works independently with exactly one unit in flight.  Roles (22 warps):
-//   warps 0-15  gather producers : 4 teams x 4 warps; warp w owns TMEM lanes 32*(w%4)..+31; team t fills units t, t+4, ...
-//                                  (global unit numbering across the CTA's tiles).  ncu on the first version of this kernel
-//                                  (12 fat producer warps, two units in flight each, a slot state machine) showed the
-//                                  producers instruction-latency bound at ~216 warp-instructions per unit and, before
-//                                  that, the L1 data pipe at 79-86 % with one 32-byte sector per wavefront
-//                                  (profiles/r01_conv_v6_*, r01_conv_v8_*).  Hence: thin warps, straight-line unit code,
-//                                  loads that are never predicated (a missing neighbour reads a zero line instead), and
-//                                  for rows >= 64 bytes a QUAD gather -- four lanes read one row's CH contiguous bytes
-//                                  (8 rows / 8 wavefronts per load instruction) and the registers go to TMEM with
-//                                  tcgen05.st.16x256b; the K order this leaves inside a sub-chunk is undone in the weight
-//                                  packing (k_word_src).
-//   warps 16-19 epilogue         : tcgen05.ld accumulators -> dequant*BN scale/shift (+residual) (+ReLU)
-//                                  -> fp16/fp32 rows (+ int8 re-quantised rows, + per-channel absmax)
-//   warp  20    MMA issuer       : one lane issues tcgen05.mma (kind::f16 or kind::i8), accumulators in TMEM
-//                                  (double buffered when they fit: tile i+1 accumulates while tile i drains)
-//   warp  21    loader           : cp.async.bulk of each tile's rulebook block ([kvol][128] int32, one copy per 16 KB, plus a
-//                                  header with the tile mask and an ordinal -> offset table) up to 3 tiles ahead, and -- when
-//                                  the packed weights do not fit in shared memory (C <= 32 fp16, C <= 64 int8 do) -- of every
-//                                  unit's weight sub-chunks into the unit's B slot.  One UBLKCP instruction costs its issuing
-//                                  warp ~225 ns whatever the size (tools/microbench/bulk_copy_rate.cu), an extra active lane
-//                                  ~26 ns: weight copies for up to half the ring are issued by one instruction, one per lane.
+// (CH = 32 / 64 / 128 bytes => 1 / 2 / 4 MMA k-steps, CH/4 TMEM columns).  The hand-off between the roles is the UNIT:
+// up to U consecutive live sub-chunks of one tile = one SLOT of U*CH/4 TMEM columns (up to 224: a whole C = 16 tile, half a
+// C = 32 tile, 6 offsets of C = 64, 2 of C = 128) with ONE full/empty mbarrier pair.  Round 1 handed over 32 columns at a
+// time and spent two thirds of its time in that protocol (profiles/r01_conv_ablation.md: ~400 cycles per hand-off for the
+// in-order MMA thread: mbarrier wait + tcgen05 fence + tcgen05.commit, plus the slot round trip of the producers); a unit
+// now carries 4-7x the work per hand-off.  Roles (6 + 4T warps, T = 4 teams by default):
+//   warps 0-3       epilogue    : tcgen05.ld accumulators -> dequant*BN scale/shift (+residual) (+ReLU)
+//                                 -> fp16/fp32 rows (+ int8 re-quantised rows, + per-channel absmax)
+//   warps 4..3+4T   gather      : warp = (team, TMEM lane quarter).  A unit's 32-column PIECES are dealt round-robin to the
+//                                 teams; every producer warp arrives once per unit.  Loads are never predicated (a missing
+//                                 neighbour reads a zero line); rows >= 64 bytes use a QUAD gather (four lanes read one
+//                                 row's CH contiguous bytes, registers go to TMEM with tcgen05.st.16x256b; the K order this
+//                                 leaves inside a sub-chunk is undone in the weight packing, k_word_src).
+//   warp  4+4T      MMA issuer  : one lane; per unit one wait, all the unit's tcgen05.mma back to back, one commit.
+//                                 Accumulators in TMEM, double buffered when they fit (tile i+1 accumulates while i drains).
+//   warp  5+4T      loader      : turns the tile list into a STREAM OF UNIT DESCRIPTORS in a 4-deep shared-memory ring: header
+//                                 {n_sub, first/last-of-tile flags, B descriptors} + the unit's rulebook slabs (one contiguous
+//                                 cp.async.bulk of n_offsets x 512 bytes out of the compact rulebook).  Producers and the MMA
+//                                 thread only ever look at the ring: no per-tile header work is left on the MMA thread's path.
+//                                 When the packed weights do not fit in shared memory it also streams every unit's weight
+//                                 sub-chunks into the slot's B area (one bulk copy per lane, two units behind the descriptors).
 #include "ql_common.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
 
-constexpr int kTeams = 4;
-constexpr int kProducerWarps = kTeams * 4;               // 16
+constexpr int kMaxTeams = 4;
 constexpr int kEpilogueThreads = 128;
-constexpr int kEpilogueWarp0 = kProducerWarps;            // warps 16..19 (warp % 4 == TMEM lane quarter)
-constexpr int kMmaWarp = kEpilogueWarp0 + 4;              // 20
-constexpr int kLoaderWarp = kMmaWarp + 1;                 // 21
-constexpr int kThreadsTotal = (kLoaderWarp + 1) * 32;     // 704
-constexpr int kMaxUnits = 8;                              // ring depth in units
-constexpr int kUnitCols = 32;                             // TMEM columns per unit (128 bytes of K per lane)
+constexpr int kProducerWarp0 = 4;                         // warps 0-3: epilogue (warp % 4 == TMEM lane quarter for both roles)
+constexpr int kThreadsMax = (6 + 4 * kMaxTeams) * 32;     // 704
+constexpr int kMaxSlots = 4;                              // A/B slot ring depth
+constexpr int kUbufs = 4;                                 // unit-descriptor ring depth (power of two)
+constexpr int kMaxUnitSubs = 32;                          // sub-chunks per unit: one loader lane each
 constexpr int kMaskWords = 4;                             // kernel volumes up to 128 (3^3, 5^3)
 constexpr int kTmemCols = 512;
 constexpr int kSmemBudget = 232448;                       // 227 KB opt-in maximum per CTA
 constexpr int kSmemFloor = 120 * 1024;                    // always ask for > half an SM: one CTA (one TMEM owner) per SM
-constexpr int kNbrHeaderMin = 160;                        // rulebook buffer header: 16 B mask, n_off at +16, n_sub at +20, ord -> k
-                                                          // table (u8) at +32, then (resident weights) one B-descriptor low
-                                                          // word per sub-chunk at +160
+constexpr int kUbHdr = 16 + 4 * kMaxUnitSubs + 16;        // unit descriptor: n_sub, flags, sub0, pad | blo[32] | pad -> slabs at +160
+constexpr uint32_t kFlagFirst = 1u, kFlagLast = 2u;
+
+#ifdef QL_SPCONV_ABLATE
+// test-time build flag (never in the product library): bit 1 = no gather loads, 2 = no tcgen05.st, 4 = no tcgen05.mma,
+// 8 = no epilogue global traffic, 16 = no rulebook slab copies, 64 = no tcgen05.ld / epilogue arithmetic
+__device__ int g_ablate = 0;
+#define QL_ABL(bit) ((g_ablate & (bit)) != 0)
+#else
+#define QL_ABL(bit) false
+#endif
 
 __device__ __align__(128) uint8_t g_zero_line[128];       // what a missing neighbour reads (zero-initialised module memory)
 
 struct ConvParams {
     const uint8_t* feats;
-    const int* nbr;
-    const uint32_t* kmask;  // [tiles][mask_words] or null (every offset)
+    const int* nbr;         // compact rulebook [tiles][kvol][128]: the first popc(kmask[tile]) slabs of a tile are its live offsets
+    const uint32_t* kmask;  // [tiles][mask_words] or null (every offset live: the dense rulebook)
     const int* row_perm;    // [tiles][128] tile slot -> output row (-1 = padding) of a GROUPED rulebook, or null (slot == row)
     const int* n_out_dev;
     int64_t n_out_cap;
@@ -70,7 +74,6 @@ struct ConvParams {
     int wide;               // rows (and the feature base) are 32-byte aligned: gather with 256-bit loads
     int c_out, kvol, nseg, mask_words;
     uint32_t inv_nseg;      // ceil(65536 / nseg): ord = (sub * inv_nseg) >> 16 for sub < 4096
-    int pair;               // 16-byte rows (int8, C_in = 16): a sub-chunk holds TWO kernel offsets, 2j in bytes 0-15 and 2j+1 in 16-31
     const uint8_t* w_packed;
     const float* scale;
     const float* shift;
@@ -82,26 +85,27 @@ struct ConvParams {
     int8_t* out_q;
     const float* out_qscale;
     float* absmax;
-    int n_ring;             // A/B ring depth in units
-    int teams;              // active producer teams (<= n_ring)
-    int n_acc;              // accumulator buffers in TMEM (2, or 1 when 2*c_out does not fit beside the A ring)
-    int a_col0;             // first TMEM column of the A ring
+    int teams;              // producer teams (4 warps each)
+    int n_slots;            // A (TMEM) / B (shared memory, streamed weights) slot ring depth
+    int unit_subs;          // U: sub-chunks per unit
+    int unit_cols;          // S = U * CH / 4 TMEM columns per slot
+    int n_acc;              // accumulator buffers in TMEM (2, or 1 when 2*c_out does not fit beside the A slots)
+    int a_col0;             // first TMEM column of the A slots
     int resident;           // 1: every weight chunk lives in shared memory for the whole kernel (no per-unit B copies)
     int w_bytes;            // packed weight bytes (resident mode)
-    int off_nbr;            // smem offset of the rulebook buffers: nbr_bufs x {header, [kvol][128] int32}
-    int nbr_bufs, nbr_log2; // 4 (or 2 when shared memory is short): the loader runs nbr_bufs-1 tiles ahead
-    int nbr_stride;         // bytes per buffer
-    int nbr_hdr;            // header bytes in front of the [kvol][128] block
+    int off_ub;             // smem offset of the unit-descriptor ring
+    int ub_stride;          // bytes per ring entry
+    int off_tab;            // smem offset of the loader's ordinal -> offset table (128 bytes)
     int off_misc;           // smem offset of MiscSmem from the 1024-aligned base
 };
 
 struct MiscSmem {
-    uint64_t full[kMaxUnits];
-    uint64_t empty[kMaxUnits];
+    uint64_t full[kMaxSlots];
+    uint64_t empty[kMaxSlots];
+    uint64_t ub_full[kUbufs];
+    uint64_t ub_empty[kUbufs];
     uint64_t acc_full[2];
     uint64_t acc_empty[2];
-    uint64_t nbr_full[4];
-    uint64_t nbr_empty[4];
     uint64_t w_full;
     uint32_t tmem_base;
     uint32_t pad[1];
@@ -205,8 +209,8 @@ __device__ __forceinline__ void tmem_st_16x256b<4>(uint32_t taddr, const uint32_
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// the two halves of load_tile_mask: issue the loads now, use them (count / fix-up) later -- a warp issues in order, so a popcount
-// right behind its load costs the loader one global round trip per tile
+// the two halves of reading a tile's offset mask: issue the loads now, use them (count / fix-up) later -- a warp issues in order,
+// so a popcount right behind its load costs the loader one global round trip per tile
 __device__ __forceinline__ void load_tile_mask_raw(const ConvParams& p, int64_t tile, uint32_t (&mask)[kMaskWords]) {
 #pragma unroll
     for (int i = 0; i < kMaskWords; ++i) {
@@ -222,38 +226,11 @@ __device__ __forceinline__ void load_tile_mask_raw(const ConvParams& p, int64_t 
         mask[i] = w;
     }
 }
-__device__ __forceinline__ int finish_tile_mask(uint32_t (&mask)[kMaskWords]) {
-    int n = 0;
-#pragma unroll
-    for (int i = 0; i < kMaskWords; ++i) n += __popc(mask[i]);
-    if (n == 0) { mask[0] = 1u; n = 1; }       // a tile without pairs still has to zero its accumulators
-    return n;
-}
-
-__device__ __forceinline__ int load_tile_mask(const ConvParams& p, int64_t tile, uint32_t (&mask)[kMaskWords]) {
-    int n = 0;
-#pragma unroll
-    for (int i = 0; i < kMaskWords; ++i) {
-        uint32_t w = 0u;
-        if (i < p.mask_words) {
-            if (p.kmask) {
-                w = __ldg(p.kmask + tile * p.mask_words + i);
-            } else {
-                const int rem = p.kvol - 32 * i;
-                w = rem >= 32 ? 0xFFFFFFFFu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
-            }
-        }
-        mask[i] = w;
-        n += __popc(w);
-    }
-    if (n == 0) { mask[0] = 1u; n = 1; }       // a tile without pairs still has to zero its accumulators
-    return n;                                  // non-empty kernel offsets
-}
 
 template <bool kInt8, int CH, bool kResident>
-__global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams p) {
+__global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p) {
     constexpr int kAReg = CH / 4;                          // 32-bit TMEM columns (registers) per sub-chunk
-    constexpr int kGroup = 128 / CH;                       // sub-chunks per unit
+    constexpr int kGroup = 128 / CH;                       // sub-chunks per 32-column piece
     constexpr int kGroupLog2 = CH == 128 ? 0 : (CH == 64 ? 1 : 2);
     constexpr bool kQuad = CH >= 64;                       // 4 lanes per row + tcgen05.st.16x256b, else lane per row + 32x32b
     constexpr int kRep = kQuad ? CH / 32 : 2;              // 256-bit repeats per sub-chunk in the quad form
@@ -269,37 +246,40 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    const uint32_t R = (uint32_t)p.n_ring;
+    const int T = p.teams;
+    const int mma_warp = kProducerWarp0 + 4 * T, loader_warp = mma_warp + 1;
+    const uint32_t n_slots = (uint32_t)p.n_slots;
+    const uint32_t S = (uint32_t)p.unit_cols;
 
-    const int64_t n_out = p.n_out_dev ? (int64_t)*p.n_out_dev : p.n_out_cap;
+    const int64_t n_out = p.n_out_dev ? min((int64_t)*p.n_out_dev, p.n_out_cap) : p.n_out_cap;
     const int64_t n_tiles = (n_out + QL_TILE_M - 1) / QL_TILE_M;
 
     if (tid == 0) {
-        for (int s = 0; s < kMaxUnits; ++s) {
-            ql_mbar_init(ql_smem_u32(&misc->full[s]), 4 + (kResident ? 0 : 1));   // the team's 4 warps (+ the loader's expect_tx)
-            ql_mbar_init(ql_smem_u32(&misc->empty[s]), 1);                         // tcgen05.commit
+        for (int s = 0; s < kMaxSlots; ++s) {
+            ql_mbar_init(ql_smem_u32(&misc->full[s]), 4 * T + (kResident ? 0 : 1));   // every producer warp (+ the loader's expect_tx)
+            ql_mbar_init(ql_smem_u32(&misc->empty[s]), 1);                             // tcgen05.commit
+        }
+        for (int i = 0; i < kUbufs; ++i) {
+            ql_mbar_init(ql_smem_u32(&misc->ub_full[i]), 1);
+            ql_mbar_init(ql_smem_u32(&misc->ub_empty[i]), 4 * T + 1);                  // producer warps + the MMA issuer
         }
         for (int i = 0; i < 2; ++i) {
             ql_mbar_init(ql_smem_u32(&misc->acc_full[i]), 1);
             ql_mbar_init(ql_smem_u32(&misc->acc_empty[i]), kEpilogueThreads);
-        }
-        for (int i = 0; i < 4; ++i) {
-            ql_mbar_init(ql_smem_u32(&misc->nbr_full[i]), 1);
-            ql_mbar_init(ql_smem_u32(&misc->nbr_empty[i]), 4 * p.teams + 1);   // producer warps + the MMA issuer
         }
         ql_mbar_init(ql_smem_u32(&misc->w_full), 1);
         ql_fence_mbar_init();
     }
     {
         const float act = p.act_scale_dev ? *p.act_scale_dev : 1.0f;
-        for (int c = tid; c < p.c_out; c += kThreadsTotal) {
+        for (int c = tid; c < p.c_out; c += blockDim.x) {
             s_scale[c] = p.scale[c] * act;
             s_shift[c] = p.shift[c];
             s_absmax[c] = 0u;
             s_qscale[c] = p.out_qscale ? p.out_qscale[c] : 0.f;
         }
     }
-    if (warp == kMmaWarp) {
+    if (warp == mma_warp) {
         ql_tmem_alloc(ql_smem_u32(&misc->tmem_base), kTmemCols);
         ql_tmem_relinquish();
     }
@@ -308,157 +288,15 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
     ql_tc_fence_after();
     const uint32_t tmem_base = misc->tmem_base;
     const uint32_t b_sub_bytes = (uint32_t)p.c_out * CH;     // one weight sub-chunk: [c_out x CH bytes]
-    const uint32_t nbr_s0 = smem_base_u32 + (uint32_t)p.off_nbr;
-    const uint32_t nbr_stride = (uint32_t)p.nbr_stride, nbmask = (uint32_t)p.nbr_bufs - 1u;
+    const uint32_t ub_s0 = smem_base_u32 + (uint32_t)p.off_ub;
+    const uint32_t ub_stride = (uint32_t)p.ub_stride;
     const uint32_t full0 = ql_smem_u32(&misc->full[0]), empty0 = ql_smem_u32(&misc->empty[0]);
+    const uint32_t ubfull0 = ql_smem_u32(&misc->ub_full[0]), ubempty0 = ql_smem_u32(&misc->ub_empty[0]);
 
-    if (warp < kProducerWarps) {
-        // ============================ gather producers ============================
-        const int q = warp & 3;                              // TMEM lane quarter
-        const uint32_t team = (uint32_t)(warp >> 2);
-        const uint32_t T = (uint32_t)p.teams;
-        if (team < T) {
-            const uint32_t a_lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.a_col0;
-            const int t0 = lane & 3, t1 = lane >> 2;         // quad form: lane t0 of the quad that serves rows t1 + 8*rr
-            // byte offset of this thread's first row inside a [128] int32 slab
-            const uint32_t row_off = (uint32_t)(q * 32 + (kQuad ? t1 : lane)) * 4u;
-            const int tb0 = kQuad ? t0 * (CH / 4) : 0;       // this thread's bytes inside a sub-chunk's row segment
-            const uint32_t row_bytes = (uint32_t)p.row_bytes;
-            const uint8_t* const feats = p.feats;
-            const uint8_t* const zero = g_zero_line;
-            const bool wide = p.wide != 0;
-            const uint32_t nseg = (uint32_t)p.nseg, inv_nseg = p.inv_nseg, hdr = (uint32_t)p.nbr_hdr, kvol = (uint32_t)p.kvol;
-            const bool pair = !kQuad && p.pair != 0;
-
-            uint32_t g = team;                               // next global unit of this team
-            uint32_t G0 = 0;                                 // global number of the current tile's first unit
-            uint32_t u = team, ph = 0;                       // ring slot / pass parity of unit g
-            uint32_t it = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const uint32_t nb = it & nbmask;
-                const uint32_t buf = nbr_s0 + nb * nbr_stride;
-                ql_mbar_wait(ql_smem_u32(&misc->nbr_full[nb]), (it >> p.nbr_log2) & 1u);
-                const uint32_t n_sub = (uint32_t)ql_lds_s32(buf + 20u);
-                const uint32_t Gend = G0 + ((n_sub + kGroup - 1) >> kGroupLog2);
-                // The rulebook indices of a unit (table byte -> slab -> row index: two dependent shared-memory loads) are fetched
-                // one unit ahead, right after the previous unit's gathers have been issued, so that chain hides under them.
-                constexpr int kIdx = kQuad ? 4 * kGroup : kGroup;
-                int idx[kIdx];
-                int idx2[kQuad ? 1 : kGroup];                                         // pair mode: the row of kernel offset 2j+1
-                uint32_t boff[kGroup];
-                auto fetch_idx = [&](uint32_t c0) {
-                    // the unit's kGroup table bytes (ordinal -> kernel offset) in one load
-                    uint32_t tbl;
-                    if constexpr (kGroup == 4) tbl = (uint32_t)ql_lds_s32(buf + 32u + c0);
-                    else if constexpr (kGroup == 2) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(tbl) : "r"(buf + 32u + c0));
-                    else {
-                        uint32_t ord = c0;
-                        boff[0] = 0;
-                        if (nseg > 1) { ord = (c0 * inv_nseg) >> 16; boff[0] = (c0 - ord * nseg) * 128u; }
-                        tbl = (uint32_t)lds_u8(buf + 32u + ord);
-                    }
-#pragma unroll
-                    for (int j = 0; j < kGroup; ++j) {
-                        const bool live = c0 + (uint32_t)j < n_sub;
-                        const uint32_t k = live ? ((tbl >> (8 * j)) & 0xFFu) : 0u;
-                        const uint32_t a = buf + hdr + k * (QL_TILE_M * 4u) + row_off;
-                        if constexpr (kGroup > 1) boff[j] = 0;
-                        if constexpr (kQuad) {
-#pragma unroll
-                            for (int rr = 0; rr < 4; ++rr) {
-                                const int v = ql_lds_s32(a + (uint32_t)rr * 32u);
-                                idx[4 * j + rr] = live ? v : -1;
-                            }
-                        } else if (!pair) {
-                            const int v = ql_lds_s32(a);
-                            idx[j] = live ? v : -1;
-                        } else {
-                            // k is a PAIR of kernel offsets (2k, 2k+1): two slabs, two rows
-                            const uint32_t a2 = buf + hdr + (2u * k) * (QL_TILE_M * 4u) + row_off;
-                            const int v0 = ql_lds_s32(a2);
-                            const int v1 = (2u * k + 1u < kvol) ? ql_lds_s32(a2 + QL_TILE_M * 4u) : -1;
-                            idx[j] = live ? v0 : -1;
-                            idx2[j] = live ? v1 : -1;
-                        }
-                    }
-                };
-                if (g < Gend) fetch_idx((g - G0) << kGroupLog2);
-                for (; g < Gend; g += T) {
-                    uint32_t v[32];
-                    if constexpr (kQuad) {
-#pragma unroll
-                        for (int j = 0; j < kGroup; ++j) {
-                            const uint32_t tb = boff[j] + (uint32_t)tb0;
-#pragma unroll
-                            for (int rr = 0; rr < 4; ++rr) {
-                                const int h = rr >> 1, v1 = rr & 1;
-                                const int id = idx[4 * j + rr];
-                                const bool ok = id >= 0 && tb < row_bytes;
-                                const uint8_t* src = ok ? feats + ((uint64_t)(uint32_t)id * row_bytes + tb) : zero;
-                                uint32_t x[8];
-                                if constexpr (CH == 128) {
-                                    if (wide) {
-                                        ldg32(src, x);
-                                    } else {
-                                        ldg16(src, x);
-                                        ldg16((ok && tb + 16u < row_bytes) ? src + 16 : zero, x + 4);
-                                    }
-                                } else {
-                                    ldg16(src, x);
-                                }
-#pragma unroll
-                                for (int v2 = 0; v2 < kRep; ++v2) {
-                                    v[j * kAReg + h * (4 * kRep) + 4 * v2 + 2 * v1] = x[2 * v2];
-                                    v[j * kAReg + h * (4 * kRep) + 4 * v2 + 2 * v1 + 1] = x[2 * v2 + 1];
-                                }
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < kGroup; ++j) {
-                            const int id = idx[j];                                       // CH = 32: one sub-chunk per kernel offset
-                            const bool ok = id >= 0;
-                            const uint8_t* src = ok ? feats + (uint64_t)(uint32_t)id * row_bytes : zero;
-                            if (wide) {
-                                ldg32(src, v + j * 8);
-                            } else if (!pair) {
-                                ldg16(src, v + j * 8);
-                                ldg16((ok && 16u < row_bytes) ? src + 16 : zero, v + j * 8 + 4);
-                            } else {
-                                ldg16(src, v + j * 8);
-                                ldg16(idx2[j] >= 0 ? feats + (uint64_t)(uint32_t)idx2[j] * row_bytes : zero, v + j * 8 + 4);
-                            }
-                        }
-                    }
-                    if (g + T < Gend) fetch_idx((g + T - G0) << kGroupLog2);             // next unit's indices, under this unit's gathers
-                    ql_mbar_wait(empty0 + u * 8u, ph ^ 1u);              // the MMAs that read this ring slot have completed
-                    ql_tc_fence_after();
-                    const uint32_t a_unit = a_lane_base + u * (uint32_t)kUnitCols;
-                    if constexpr (kQuad) {
-#pragma unroll
-                        for (int j = 0; j < kGroup; ++j)
-#pragma unroll
-                            for (int h = 0; h < 2; ++h)
-                                tmem_st_16x256b<kRep>(a_unit + ((uint32_t)(h * 16) << 16) + (uint32_t)(j * kAReg), &v[j * kAReg + h * (4 * kRep)]);
-                    } else {
-                        tmem_st_32x32b_x32(a_unit, v);
-                    }
-                    tmem_st_wait();
-                    ql_tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) ql_mbar_arrive(full0 + u * 8u);
-                    u += T;
-                    if (u >= R) { u -= R; ph ^= 1u; }
-                }
-                G0 = Gend;
-                __syncwarp();
-                if (lane == 0) ql_mbar_arrive(ql_smem_u32(&misc->nbr_empty[nb]));   // this warp has read all it needs from the block
-            }
-        }
-    } else if (warp < kMmaWarp) {
+    if (warp < kProducerWarp0) {
         // ================================ epilogue ================================
-        const int w = warp - kEpilogueWarp0;                 // TMEM lane quarter (warp id % 4)
-        const int et = tid - kEpilogueWarp0 * 32;            // 0..127 == row in tile
+        const int w = warp;                                  // TMEM lane quarter (warp id % 4)
+        const int et = tid;                                  // 0..127 == row in tile
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int a = p.n_acc == 2 ? (int)(it & 1u) : 0;
@@ -467,12 +305,11 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
             const int64_t slot = tile * QL_TILE_M + et;
             int64_t row = slot;
             if (p.row_perm) row = slot < n_out ? (int64_t)__ldg(p.row_perm + slot) : -1;
-            const bool row_ok = row >= 0 && row < n_out;
+            const bool row_ok = row >= 0 && row < n_out && !QL_ABL(8);
             // The residual row does not depend on the MMAs: (kind::f16 instantiations) its first 32 bytes are requested BEFORE the
             // accumulator wait and every further chunk one iteration ahead, so the global-load latency is off the epilogue's critical
-            // path (the role trace, profiles/r01_conv_role_waits.md, showed the epilogue 80-90 % busy on every residual layer and the
-            // MMA thread waiting for accumulators up to 26 % of its time).  The kind::i8 instantiations keep the load inside the
-            // column loop: with the early loads their abs-max epilogue (dynamic W8A8) ran 25 % slower on every layer.
+            // path.  The kind::i8 instantiations keep the load inside the column loop: with the early loads their abs-max epilogue
+            // (dynamic W8A8) ran 25 % slower on every layer (round 1).
             const bool has_res = p.residual != nullptr && row_ok;
             const uint4* res4 = has_res ? reinterpret_cast<const uint4*>(p.residual + row * p.c_out) : nullptr;
             uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
@@ -483,6 +320,7 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
             ql_tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(a * p.c_out);
             for (int c0 = 0; c0 < p.c_out; c0 += 16) {
+                if (QL_ABL(64)) break;
                 uint32_t v[16];
                 ql_tmem_ld16(taddr + (uint32_t)c0, v);
                 uint4 rc = ra, rd = rb;                                // this iteration's residual chunk
@@ -567,131 +405,217 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
             ql_tc_fence_before();
             ql_mbar_arrive(ql_smem_u32(&misc->acc_empty[a]));
         }
-    } else if (warp == kMmaWarp) {
+    } else if (warp < mma_warp) {
+        // ============================ gather producers ============================
+        const int q = warp & 3;                              // TMEM lane quarter
+        const uint32_t team = (uint32_t)((warp - kProducerWarp0) >> 2);
+        const uint32_t Tu = (uint32_t)T;
+        const uint32_t a_lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.a_col0;
+        const int t0 = lane & 3, t1 = lane >> 2;             // quad form: lane t0 of the quad that serves rows t1 + 8*rr
+        // byte offset of this thread's first row inside a [128] int32 slab
+        const uint32_t row_off = (uint32_t)(q * 32 + (kQuad ? t1 : lane)) * 4u;
+        const int tb0 = kQuad ? t0 * (CH / 4) : 0;           // this thread's bytes inside a sub-chunk's row segment
+        const uint32_t row_bytes = (uint32_t)p.row_bytes;
+        const uint8_t* const feats = p.feats;
+        const uint8_t* const zero = g_zero_line;
+        const bool wide = p.wide != 0;
+        const uint32_t nseg = (uint32_t)p.nseg, inv_nseg = p.inv_nseg;
+
+        uint32_t slot = 0, sph = 0;                          // slot ring position / pass parity
+        uint32_t gmod = 0;                                   // (pieces handed out so far) mod T: piece g goes to team g mod T
+        for (uint32_t u = 0;; ++u) {
+            const uint32_t ub = u & (uint32_t)(kUbufs - 1);
+            const uint32_t ubuf = ub_s0 + ub * ub_stride;
+            ql_mbar_wait(ubfull0 + ub * 8u, (u / kUbufs) & 1u);
+            const uint32_t n_sub = (uint32_t)ql_lds_s32(ubuf);
+            if (n_sub == 0u) break;                          // end of the unit stream
+            const uint32_t sub0 = (uint32_t)ql_lds_s32(ubuf + 8u);
+            const uint32_t ord0 = CH == 128 ? ((sub0 * inv_nseg) >> 16) : sub0;
+            const uint32_t pieces = (n_sub + kGroup - 1) >> kGroupLog2;
+            uint32_t pc = team >= gmod ? team - gmod : team + Tu - gmod;      // this team's first piece of the unit
+            // The rulebook indices of a piece (slab -> row index) are fetched one piece ahead, right after the previous piece's
+            // gathers have been issued, so the shared-memory round trip hides under them.
+            constexpr int kIdx = kQuad ? 4 * kGroup : kGroup;
+            int idx[kIdx];
+            uint32_t boff[kGroup];
+            auto fetch_idx = [&](uint32_t piece) {
+                const uint32_t c0 = piece << kGroupLog2;                      // first sub-chunk of the piece inside the unit
+#pragma unroll
+                for (int j = 0; j < kGroup; ++j) {
+                    const uint32_t cl = c0 + (uint32_t)j;
+                    const bool live = cl < n_sub;
+                    uint32_t slab = live ? cl : 0u;
+                    boff[j] = 0;
+                    if constexpr (CH == 128) {
+                        if (nseg > 1) {
+                            const uint32_t c = sub0 + slab;
+                            const uint32_t ord = (c * inv_nseg) >> 16;
+                            boff[j] = (c - ord * nseg) * 128u;
+                            slab = ord - ord0;
+                        }
+                    }
+                    const uint32_t a = ubuf + (uint32_t)kUbHdr + slab * (QL_TILE_M * 4u) + row_off;
+                    if constexpr (kQuad) {
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr) {
+                            const int v = ql_lds_s32(a + (uint32_t)rr * 32u);
+                            idx[4 * j + rr] = live ? v : -1;
+                        }
+                    } else {
+                        const int v = ql_lds_s32(a);
+                        idx[j] = live ? v : -1;
+                    }
+                }
+            };
+            bool waited = false;
+            if (pc < pieces) fetch_idx(pc);
+            for (; pc < pieces; pc += Tu) {
+                uint32_t v[32];
+                if constexpr (kQuad) {
+#pragma unroll
+                    for (int j = 0; j < kGroup; ++j) {
+                        const uint32_t tb = boff[j] + (uint32_t)tb0;
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr) {
+                            const int h = rr >> 1, v1 = rr & 1;
+                            const int id = idx[4 * j + rr];
+                            const bool ok = id >= 0 && tb < row_bytes && !QL_ABL(1);
+                            const uint8_t* src = ok ? feats + ((uint64_t)(uint32_t)id * row_bytes + tb) : zero;
+                            uint32_t x[8];
+                            if constexpr (CH == 128) {
+                                if (wide) {
+                                    ldg32(src, x);
+                                } else {
+                                    ldg16(src, x);
+                                    ldg16((ok && tb + 16u < row_bytes) ? src + 16 : zero, x + 4);
+                                }
+                            } else {
+                                ldg16(src, x);
+                            }
+#pragma unroll
+                            for (int v2 = 0; v2 < kRep; ++v2) {
+                                v[j * kAReg + h * (4 * kRep) + 4 * v2 + 2 * v1] = x[2 * v2];
+                                v[j * kAReg + h * (4 * kRep) + 4 * v2 + 2 * v1 + 1] = x[2 * v2 + 1];
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kGroup; ++j) {
+                        const int id = idx[j];                                       // CH = 32: one sub-chunk per kernel offset
+                        const bool ok = id >= 0 && !QL_ABL(1);
+                        const uint8_t* src = ok ? feats + (uint64_t)(uint32_t)id * row_bytes : zero;
+                        if (wide) {
+                            ldg32(src, v + j * 8);
+                        } else {
+                            ldg16(src, v + j * 8);
+                            ldg16((ok && 16u < row_bytes) ? src + 16 : zero, v + j * 8 + 4);
+                        }
+                    }
+                }
+                const uint32_t a_piece = a_lane_base + slot * S + pc * 32u;
+                if (pc + Tu < pieces) fetch_idx(pc + Tu);                            // next piece's indices, under this piece's gathers
+                if (!waited) {
+                    ql_mbar_wait(empty0 + slot * 8u, sph ^ 1u);                      // the MMAs that read this slot have completed
+                    ql_tc_fence_after();
+                    waited = true;
+                }
+                if (!QL_ABL(2)) {
+                    if constexpr (kQuad) {
+#pragma unroll
+                        for (int j = 0; j < kGroup; ++j)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+                                tmem_st_16x256b<kRep>(a_piece + ((uint32_t)(h * 16) << 16) + (uint32_t)(j * kAReg), &v[j * kAReg + h * (4 * kRep)]);
+                    } else {
+                        tmem_st_32x32b_x32(a_piece, v);
+                    }
+                }
+            }
+            // a warp without a piece in this unit still arrives, and must do so inside the slot's current phase
+            if (!waited) ql_mbar_wait(empty0 + slot * 8u, sph ^ 1u);
+            tmem_st_wait();
+            ql_tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                ql_mbar_arrive(full0 + slot * 8u);
+                ql_mbar_arrive(ubempty0 + ub * 8u);          // this warp has read all it needs from the descriptor
+            }
+            gmod += pieces;                                  // pieces <= 32, T <= 4
+            gmod = T == 4 ? (gmod & 3u) : gmod % Tu;
+            if (++slot == n_slots) { slot = 0; sph ^= 1u; }
+        }
+    } else if (warp == mma_warp) {
         // =============================== MMA issuer ===============================
-        // One elected lane runs the whole loop (nothing in it is warp-collective).  Every sub-chunk of every tile passes
-        // through this single instruction stream, so it is kept short: ring position and phase are counters, the tile
-        // mask is walked with ffs, descriptors differ only in their low word.
+        // One elected lane runs the whole loop (nothing in it is warp-collective): per unit one descriptor wait, one slot wait,
+        // the unit's MMAs back to back, one commit.
         if (ql_elect_one()) {
             const uint32_t idesc = make_idesc<kInt8>(p.c_out);
             const uint64_t bdesc0 = umma_desc_b<CH>(smem_base_u32);
             const uint32_t bdesc_hi = (uint32_t)(bdesc0 >> 32), bdesc_lo0 = (uint32_t)bdesc0;
             const uint32_t b_sub16 = b_sub_bytes >> 4;
             const uint32_t a_base = tmem_base + (uint32_t)p.a_col0;
-            const uint32_t n_acc = (uint32_t)p.n_acc, c_out = (uint32_t)p.c_out;
-            uint32_t u = 0, ph = 0, it = 0;
+            const uint32_t n_acc = (uint32_t)p.n_acc, c_out = (uint32_t)p.c_out, U = (uint32_t)p.unit_subs;
+            uint32_t slot = 0, sph = 0, it = 0, accumulate = 0u, d_tmem = tmem_base, acc_bar = 0;
             if (kResident && (int64_t)blockIdx.x < n_tiles) ql_mbar_wait(ql_smem_u32(&misc->w_full), 0);
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                // the tile's header in the rulebook buffer: n_sub and (resident weights) the B descriptor of every sub-chunk,
-                // prepared by the loader's 32 lanes so that this one thread only loads and issues
-                const uint32_t nb = it & nbmask;
-                const uint32_t buf = nbr_s0 + nb * nbr_stride;
-                ql_mbar_wait(ql_smem_u32(&misc->nbr_full[nb]), (it >> p.nbr_log2) & 1u);
-                const uint32_t n_sub = (uint32_t)ql_lds_s32(buf + 20u);
-                const uint32_t a = n_acc == 2 ? (it & 1u) : 0u;
-                const uint32_t aph = n_acc == 2 ? ((it >> 1) & 1u) : (it & 1u);
-                ql_mbar_wait(ql_smem_u32(&misc->acc_empty[a]), aph ^ 1u);
-                ql_tc_fence_after();
-                const uint32_t d_tmem = tmem_base + a * c_out;
-                const uint32_t acc_bar = ql_smem_u32(&misc->acc_full[a]);
-                uint32_t accumulate = 0u;
-                for (uint32_t c0 = 0; c0 < n_sub; c0 += kGroup) {
-                    uint32_t blo[kGroup];
+            for (uint32_t u = 0;; ++u) {
+                const uint32_t ub = u & (uint32_t)(kUbufs - 1);
+                const uint32_t ubuf = ub_s0 + ub * ub_stride;
+                ql_mbar_wait(ubfull0 + ub * 8u, (u / kUbufs) & 1u);
+                uint32_t n_sub, flags;
+                asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(n_sub), "=r"(flags) : "r"(ubuf));
+                if (n_sub == 0u) break;
+                uint32_t blo[4];
+                auto load_blo = [&](uint32_t j0) {
                     if constexpr (kResident) {
-                        const uint32_t ta = buf + (uint32_t)kNbrHeaderMin + 4u * c0;
-                        if constexpr (kGroup == 4) {
-                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(blo[0]), "=r"(blo[1]), "=r"(blo[2]), "=r"(blo[3]) : "r"(ta));
-                        } else if constexpr (kGroup == 2) {
-                            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(blo[0]), "=r"(blo[1]) : "r"(ta));
-                        } else {
-                            blo[0] = (uint32_t)ql_lds_s32(ta);
-                        }
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(blo[0]), "=r"(blo[1]), "=r"(blo[2]), "=r"(blo[3]) : "r"(ubuf + 16u + 4u * j0));
                     } else {
 #pragma unroll
-                        for (int j = 0; j < kGroup; ++j) blo[j] = bdesc_lo0 + (u * (uint32_t)kGroup + (uint32_t)j) * b_sub16;
+                        for (int i = 0; i < 4; ++i) blo[i] = bdesc_lo0 + (slot * U + j0 + (uint32_t)i) * b_sub16;
                     }
-                    ql_mbar_wait(full0 + u * 8u, ph);
-                    ql_tc_fence_after();
-                    const uint32_t a_unit = a_base + u * (uint32_t)kUnitCols;
+                };
+                load_blo(0);
+                if (flags & kFlagFirst) {
+                    const uint32_t a = n_acc == 2 ? (it & 1u) : 0u;
+                    const uint32_t aph = n_acc == 2 ? ((it >> 1) & 1u) : (it & 1u);
+                    ql_mbar_wait(ql_smem_u32(&misc->acc_empty[a]), aph ^ 1u);
+                    d_tmem = tmem_base + a * c_out;
+                    acc_bar = ql_smem_u32(&misc->acc_full[a]);
+                    accumulate = 0u;
+                }
+                ql_mbar_wait(full0 + slot * 8u, sph);
+                ql_tc_fence_after();
+                const uint32_t a_unit = a_base + slot * S;
+                for (uint32_t j0 = 0; j0 < n_sub; j0 += 4) {
+                    uint32_t cur[4];
 #pragma unroll
-                    for (int j = 0; j < kGroup; ++j) {
-                        if (j == 0 || c0 + (uint32_t)j < n_sub) {
+                    for (int i = 0; i < 4; ++i) cur[i] = blo[i];
+                    if (j0 + 4 < n_sub) load_blo(j0 + 4);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (i == 0 || j0 + (uint32_t)i < n_sub) {
 #pragma unroll
                             for (int ks = 0; ks < CH / 32; ++ks) {       // one k-step = 32 bytes of K: +8 TMEM columns, +2 in the desc (addr >> 4)
-                                const uint64_t bdesc = ((uint64_t)bdesc_hi << 32) | (uint64_t)(blo[j] + (uint32_t)(ks * 2));
-                                tc_mma_ts<kInt8>(d_tmem, a_unit + (uint32_t)(j * kAReg + ks * 8), bdesc, idesc, accumulate);
+                                const uint64_t bdesc = ((uint64_t)bdesc_hi << 32) | (uint64_t)(cur[i] + (uint32_t)(ks * 2));
+                                if (!QL_ABL(4)) tc_mma_ts<kInt8>(d_tmem, a_unit + (j0 + (uint32_t)i) * (uint32_t)kAReg + (uint32_t)(ks * 8), bdesc, idesc, accumulate);
                                 accumulate = 1u;
                             }
                         }
                     }
-                    ql_tc_commit(empty0 + u * 8u);
-                    if (c0 + kGroup >= n_sub) ql_tc_commit(acc_bar);
-                    if (++u == R) { u = 0; ph ^= 1u; }
                 }
-                ql_mbar_arrive(ql_smem_u32(&misc->nbr_empty[nb]));
+                ql_tc_commit(empty0 + slot * 8u);
+                if (flags & kFlagLast) { ql_tc_commit(acc_bar); ++it; }
+                ql_mbar_arrive(ubempty0 + ub * 8u);
+                if (++slot == n_slots) { slot = 0; sph ^= 1u; }
             }
         }
         __syncwarp();
-    } else {
+    } else if (warp == loader_warp) {
         // ================================= loader =================================
-        // Tile `tile` (the CTA's itn-th) -> rulebook buffer itn % nbr_bufs: header {mask, n_off, ord -> k table} written with
-        // plain stores (released by the arrive below), then the tile's whole [kvol][128] block, one bulk copy per 16 KB.
-        auto prefetch_nbr = [&](int64_t tile, uint32_t itn, const uint32_t (&mask)[kMaskWords], int n_off) {   // n_off: live offsets (pairs in pair mode)
-            const uint32_t nb = itn & nbmask;
-            const uint32_t bar = ql_smem_u32(&misc->nbr_full[nb]);
-            const uint32_t dst = nbr_s0 + nb * nbr_stride;
-            ql_mbar_wait(ql_smem_u32(&misc->nbr_empty[nb]), ((itn >> p.nbr_log2) & 1u) ^ 1u);
-            uint32_t vmask[kMaskWords];
-#pragma unroll
-            for (int i = 0; i < kMaskWords; ++i) vmask[i] = mask[i];
-            if (p.pair) {
-                // pair j is live when kernel offset 2j or 2j+1 is: lane l of pass i looks at pair 32*i + l
-                n_off = 0;
-#pragma unroll
-                for (int i = 0; i < kMaskWords; ++i) {
-                    const int vj = 32 * i + lane;                      // pair index; its two bits never straddle a word
-                    uint32_t word = 0u;
-                    if (2 * vj < 32 * kMaskWords) {
-                        word = mask[0];
-#pragma unroll
-                        for (int q2 = 1; q2 < kMaskWords; ++q2)
-                            if (((2 * vj) >> 5) == q2) word = mask[q2];
-                    }
-                    const bool on = 2 * vj < 32 * kMaskWords && ((word >> ((2 * vj) & 31)) & 3u) != 0u;
-                    vmask[i] = __ballot_sync(0xffffffffu, on);
-                    n_off += __popc(vmask[i]);
-                }
-            }
-            int prefix = 0;
-#pragma unroll
-            for (int i = 0; i < kMaskWords; ++i) {
-                const uint32_t w = vmask[i];
-                if (lane == i) sts_u32(dst + 4u * i, w);
-                if ((w >> lane) & 1u) sts_u8(dst + 32u + (uint32_t)(prefix + __popc(w & ((1u << lane) - 1u))), i * 32 + lane);
-                prefix += __popc(w);
-            }
-            const uint32_t n_sub = (uint32_t)n_off * (uint32_t)p.nseg;
-            if (lane == 0) { sts_u32(dst + 16u, (uint32_t)n_off); sts_u32(dst + 20u, n_sub); }
-            __syncwarp();
-            if constexpr (kResident) {
-                // B descriptor (low word) of every sub-chunk of the tile, in processing order, for the MMA issuer
-                const uint32_t bdesc_lo0 = (uint32_t)umma_desc_b<CH>(smem_base_u32);
-                for (uint32_t sub = (uint32_t)lane; sub < n_sub; sub += 32u) {
-                    uint32_t ord = sub, seg = 0;
-                    if (CH == 128) { ord = (sub * p.inv_nseg) >> 16; seg = sub - ord * (uint32_t)p.nseg; }
-                    const uint32_t k = (uint32_t)lds_u8(dst + 32u + ord);
-                    sts_u32(dst + (uint32_t)kNbrHeaderMin + 4u * sub, bdesc_lo0 + (k * (uint32_t)p.nseg + seg) * (b_sub_bytes >> 4));
-                }
-                __syncwarp();
-            }
-            const uint32_t total = (uint32_t)p.kvol * (QL_TILE_M * 4u);
-            if (lane == 0) ql_mbar_arrive_expect_tx(bar, total);     // release: orders the header stores
-            __syncwarp();
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.nbr + tile * (int64_t)p.kvol * QL_TILE_M);
-            const uint32_t off = (uint32_t)lane * 16384u;
-            if (off < total) ql_bulk_g2s(dst + (uint32_t)p.nbr_hdr + off, src + off, total - off < 16384u ? total - off : 16384u, bar);
-            __syncwarp();
-        };
+        const uint32_t tab = smem_base_u32 + (uint32_t)p.off_tab;          // ordinal -> kernel offset of the tile being cut into units
+        const uint32_t U = (uint32_t)p.unit_subs, nseg = (uint32_t)p.nseg, inv_nseg = p.inv_nseg;
+        const uint32_t bdesc_lo0 = (uint32_t)umma_desc_b<CH>(smem_base_u32);
+        const uint32_t b_sub16 = b_sub_bytes >> 4;
         if (kResident && (int64_t)blockIdx.x < n_tiles) {
             // the whole packed weight tensor, 32 lanes x (w_bytes / 32) bytes
             const uint32_t bar = ql_smem_u32(&misc->w_full);
@@ -701,61 +625,109 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
             ql_bulk_g2s(smem_base_u32 + (uint32_t)lane * per_lane, p.w_packed + (size_t)lane * per_lane, per_lane, bar);
             __syncwarp();
         }
-        // rulebook prefetch runs nbr_bufs-1 tiles ahead of the tile being streamed; pf = next tile to prefetch, its mask is
-        // loaded one step early so the global-load latency is off the path
-        int64_t pf_tile = blockIdx.x;
-        uint32_t pf_it = 0;
+        // descriptor cursor: tile state
+        int64_t next_tile = blockIdx.x;                 // next tile to start
+        int64_t cur_tile = 0;
+        uint32_t s0 = 0, n_sub_tile = 0;                // next sub-chunk of the current tile / its total (s0 >= total: start a tile)
+        bool synth = false;                             // the current tile has no pairs: one all -1 slab is synthesised
         uint32_t pf_mask[kMaskWords];
 #pragma unroll
         for (int i = 0; i < kMaskWords; ++i) pf_mask[i] = 0u;
-        if (pf_tile < n_tiles) load_tile_mask_raw(p, pf_tile, pf_mask);
-        auto prefetch_step = [&]() {
-            if (pf_tile >= n_tiles) return;
-            uint32_t m[kMaskWords];
-#pragma unroll
-            for (int i = 0; i < kMaskWords; ++i) m[i] = pf_mask[i];
-            const int n_off = finish_tile_mask(m);                 // first use of the words requested one step ago
-            const int64_t t = pf_tile;
-            const uint32_t itn = pf_it;
-            pf_tile += gridDim.x; ++pf_it;
-            if (pf_tile < n_tiles) load_tile_mask_raw(p, pf_tile, pf_mask);   // the next tile's words: requested, not looked at
-            prefetch_nbr(t, itn, m, n_off);
-        };
-        for (int i = 0; i < p.nbr_bufs - 1; ++i) prefetch_step();
-        // streamed weights: up to half the ring per pass, lane l = sub-chunk l of the pass (unit l / kGroup)
-        uint32_t u = 0, ph = 0, it = 0;
-        const uint32_t batch_subs = (R / 2u > 0u ? R / 2u : 1u) << kGroupLog2;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            prefetch_step();
-            if constexpr (!kResident) {
-                const uint32_t buf = nbr_s0 + (it & nbmask) * nbr_stride;     // this tile's header (already resident: prefetched earlier)
-                const uint32_t n_sub = (uint32_t)ql_lds_s32(buf + 20u);
-                for (uint32_t c0 = 0; c0 < n_sub; c0 += batch_subs) {
-                    const uint32_t sub = c0 + (uint32_t)lane;
-                    const bool mine = (uint32_t)lane < batch_subs && sub < n_sub;
-                    const uint32_t bu = (uint32_t)lane >> kGroupLog2, j = (uint32_t)lane & (uint32_t)(kGroup - 1);
-                    uint32_t uu = u + bu, pp = ph;
-                    if (uu >= R) { uu -= R; pp ^= 1u; }
-                    const uint32_t fbar = full0 + uu * 8u;
-                    if (mine && j == 0) {
-                        ql_mbar_wait(empty0 + uu * 8u, pp ^ 1u);
-                        const uint32_t left = n_sub - sub;
-                        ql_mbar_arrive_expect_tx(fbar, (left < (uint32_t)kGroup ? left : (uint32_t)kGroup) * b_sub_bytes);
-                    }
+        if (next_tile < n_tiles) load_tile_mask_raw(p, next_tile, pf_mask);
+        uint32_t ur = 0;                                // units described so far
+        // returns true when it pushed the end-of-stream descriptor
+        auto push_desc = [&]() -> bool {
+            const uint32_t ub = ur & (uint32_t)(kUbufs - 1);
+            const uint32_t ubuf = ub_s0 + ub * ub_stride;
+            const uint32_t bar = ubfull0 + ub * 8u;
+            if (s0 >= n_sub_tile) {
+                if (next_tile >= n_tiles) {
+                    ql_mbar_wait(ubempty0 + ub * 8u, ((ur / kUbufs) & 1u) ^ 1u);
+                    if (lane == 0) { sts_u32(ubuf, 0u); sts_u32(ubuf + 4u, 0u); ql_mbar_arrive(bar); }
                     __syncwarp();
-                    if (mine) {
-                        uint32_t ord = sub, seg = 0;
-                        if (CH == 128) { ord = (sub * p.inv_nseg) >> 16; seg = sub - ord * (uint32_t)p.nseg; }
-                        const uint32_t k = (uint32_t)lds_u8(buf + 32u + ord);
-                        ql_bulk_g2s(smem_base_u32 + (uu * (uint32_t)kGroup + j) * b_sub_bytes,
-                                    p.w_packed + (size_t)(k * (uint32_t)p.nseg + seg) * b_sub_bytes, b_sub_bytes, fbar);
-                    }
-                    __syncwarp();
-                    const uint32_t left = n_sub - c0;
-                    const uint32_t nu = ((left < batch_subs ? left : batch_subs) + (uint32_t)kGroup - 1u) >> kGroupLog2;
-                    u += nu;
-                    if (u >= R) { u -= R; ph ^= 1u; }
+                    ++ur;
+                    return true;
                 }
+                // start the next tile: first use of the mask words requested one step ago
+                uint32_t m[kMaskWords];
+                int n_live = 0;
+#pragma unroll
+                for (int i = 0; i < kMaskWords; ++i) { m[i] = pf_mask[i]; n_live += __popc(m[i]); }
+                synth = n_live == 0;
+                if (synth) { m[0] = 1u; n_live = 1; }          // a tile without pairs still has to zero its accumulators
+                cur_tile = next_tile;
+                next_tile += gridDim.x;
+                if (next_tile < n_tiles) load_tile_mask_raw(p, next_tile, pf_mask);   // the next tile's words: requested, not looked at
+                __syncwarp();
+                int prefix = 0;
+#pragma unroll
+                for (int i = 0; i < kMaskWords; ++i) {
+                    const uint32_t w = m[i];
+                    if ((w >> lane) & 1u) sts_u8(tab + (uint32_t)(prefix + __popc(w & ((1u << lane) - 1u))), i * 32 + lane);
+                    prefix += __popc(w);
+                }
+                __syncwarp();
+                s0 = 0;
+                n_sub_tile = (uint32_t)n_live * nseg;
+            }
+            const uint32_t left = n_sub_tile - s0;
+            const uint32_t n_sub = left < U ? left : U;
+            const uint32_t ord_first = CH == 128 ? ((s0 * inv_nseg) >> 16) : s0;
+            const uint32_t ord_last = CH == 128 ? (((s0 + n_sub - 1u) * inv_nseg) >> 16) : s0 + n_sub - 1u;
+            const uint32_t slab_bytes = (ord_last - ord_first + 1u) * (QL_TILE_M * 4u);
+            ql_mbar_wait(ubempty0 + ub * 8u, ((ur / kUbufs) & 1u) ^ 1u);
+            if ((uint32_t)lane < n_sub) {
+                const uint32_t c = s0 + (uint32_t)lane;
+                uint32_t ord = c, seg = 0;
+                if (CH == 128) { ord = (c * inv_nseg) >> 16; seg = c - ord * nseg; }
+                const uint32_t chunk = (uint32_t)lds_u8(tab + ord) * nseg + seg;
+                // resident weights: the B descriptor (low word) of the sub-chunk; streamed: the chunk number for the weight cursor
+                sts_u32(ubuf + 16u + 4u * (uint32_t)lane, kResident ? bdesc_lo0 + chunk * b_sub16 : chunk);
+            }
+            if (lane == 0) {
+                sts_u32(ubuf, n_sub);
+                sts_u32(ubuf + 4u, (s0 == 0u ? kFlagFirst : 0u) | (s0 + n_sub >= n_sub_tile ? kFlagLast : 0u));
+                sts_u32(ubuf + 8u, s0);
+            }
+            if (synth || QL_ABL(16)) {
+                asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ubuf + (uint32_t)kUbHdr + 16u * (uint32_t)lane), "r"(-1) : "memory");
+                __syncwarp();
+                if (lane == 0) ql_mbar_arrive(bar);
+            } else {
+                __syncwarp();
+                if (lane == 0) {
+                    ql_mbar_arrive_expect_tx(bar, slab_bytes);         // release: orders the header stores
+                    ql_bulk_g2s(ubuf + (uint32_t)kUbHdr, p.nbr + (cur_tile * (int64_t)p.kvol + ord_first) * QL_TILE_M, slab_bytes, bar);
+                }
+            }
+            __syncwarp();
+            s0 += n_sub;
+            ++ur;
+            return false;
+        };
+        if constexpr (kResident) {
+            while (!push_desc()) {}
+        } else {
+            // streamed weights: the descriptors (and their rulebook copies) run up to 2 units ahead of the weight copies, which
+            // are bound to the slot ring (a unit's B area is free once the MMAs of the unit n_slots earlier have completed)
+            bool done = false;
+            uint32_t uw = 0, slot = 0, sph = 0;
+            for (;;) {
+                while (!done && ur < uw + 3u) done = push_desc();
+                const uint32_t ubuf = ub_s0 + (uw & (uint32_t)(kUbufs - 1)) * ub_stride;
+                const uint32_t n_sub = (uint32_t)ql_lds_s32(ubuf);
+                if (n_sub == 0u) break;
+                const uint32_t fbar = full0 + slot * 8u;
+                ql_mbar_wait(empty0 + slot * 8u, sph ^ 1u);
+                if (lane == 0) ql_mbar_arrive_expect_tx(fbar, n_sub * b_sub_bytes);
+                __syncwarp();
+                if ((uint32_t)lane < n_sub) {
+                    const uint32_t chunk = (uint32_t)ql_lds_s32(ubuf + 16u + 4u * (uint32_t)lane);
+                    ql_bulk_g2s(smem_base_u32 + (slot * U + (uint32_t)lane) * b_sub_bytes, p.w_packed + (size_t)chunk * b_sub_bytes, b_sub_bytes, fbar);
+                }
+                __syncwarp();
+                ++uw;
+                if (++slot == n_slots) { slot = 0; sph ^= 1u; }
             }
         }
     }
@@ -764,12 +736,12 @@ __global__ void __launch_bounds__(kThreadsTotal, 1) k_spconv_ts(const ConvParams
     __syncthreads();
     ql_tc_fence_after();
     if (p.absmax) {
-        for (int c = tid; c < p.c_out; c += kThreadsTotal) {
+        for (int c = tid; c < p.c_out; c += blockDim.x) {
             uint32_t v = s_absmax[c];
             if (v) atomicMax(reinterpret_cast<unsigned int*>(p.absmax) + c, v);
         }
     }
-    if (warp == kMmaWarp) ql_tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == mma_warp) ql_tmem_dealloc(tmem_base, kTmemCols);
 }
 
 inline int elem_size(int dtype) { return dtype == QL_S8 ? 1 : (dtype == QL_F16 ? 2 : 0); }
@@ -778,13 +750,11 @@ inline int elem_size(int dtype) { return dtype == QL_S8 ? 1 : (dtype == QL_F16 ?
 struct ChunkGeom {
     int ch;      // bytes of K per chunk (32 / 64 / 128), zero padded when the row (segment) is shorter
     int nseg;    // chunks per kernel offset
-    int pair;    // 16-byte rows: one 32-byte chunk holds two consecutive kernel offsets (2j | 2j+1)
 };
 inline ChunkGeom chunk_geom(int row_bytes) {
     ChunkGeom g;
     if (row_bytes > 128) { g.ch = 128; g.nseg = (row_bytes + 127) / 128; }
     else { g.ch = row_bytes <= 32 ? 32 : (row_bytes <= 64 ? 64 : 128); g.nseg = 1; }
-    g.pair = row_bytes == 16 ? 1 : 0;
     return g;
 }
 // byte offset of 16-byte piece c16 of row r inside a K-major swizzled [rows x ch bytes] chunk image
@@ -806,7 +776,7 @@ template <bool kInt8, int CH, bool kResident>
 cudaError_t launch2(const ConvParams& p, int grid, size_t smem_bytes, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(k_spconv_ts<kInt8, CH, kResident>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
-    k_spconv_ts<kInt8, CH, kResident><<<grid, kThreadsTotal, smem_bytes, st>>>(p);
+    k_spconv_ts<kInt8, CH, kResident><<<grid, (6 + 4 * p.teams) * 32, smem_bytes, st>>>(p);
     return cudaPeekAtLastError();                     // left pending for ql_last_cuda_error()
 }
 template <bool kInt8, int CH>
@@ -814,50 +784,70 @@ cudaError_t launch(const ConvParams& p, int grid, size_t smem_bytes, cudaStream_
     return p.resident ? launch2<kInt8, CH, true>(p, grid, smem_bytes, st) : launch2<kInt8, CH, false>(p, grid, smem_bytes, st);
 }
 
+int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
 
 // Shared-memory / TMEM plan of one launch (also answers "are this layer's weights streamed?" for the host).
 // Returns the dynamic shared-memory bytes, or 0 when the shape is unsupported.
+//   TMEM: n_acc accumulators of c_out columns, then n_slots A slots of S = U * CH/4 columns (S a multiple of 32).
+//   smem: [resident weights | n_slots x U streamed weight sub-chunks] [4 unit descriptors: 160-byte header + the unit's
+//         rulebook slabs] [ordinal table] [barriers, scale/shift/absmax/qscale]
 size_t plan_conv(ConvParams& p, const ChunkGeom& g, int c_out, int kvol) {
-    const int kv = g.pair ? (kvol + 1) / 2 : kvol;            // kernel offsets as the weight tensor / B descriptors see them
-    // ring depth in units (32 TMEM columns each): bounded by the TMEM columns left beside the accumulators and, when
-    // the weights are streamed, by shared memory (a unit's B slot = its 128/CH weight sub-chunks = c_out x 128 bytes)
+    // tuning overrides (tools/conv_sweep.py); read per call so that one process can sweep them
+    const int force_u = env_int("QL_SPCONV_UNIT_SUBS", 0), force_slots = env_int("QL_SPCONV_SLOTS", 0),
+              force_teams = env_int("QL_SPCONV_TEAMS", 0), force_stream = env_int("QL_SPCONV_STREAM", 0);
+    const int group = 128 / g.ch, areg = g.ch / 4;
     const int misc_bytes = (int)sizeof(MiscSmem) + 4 * c_out * 4;
     const int b_sub = c_out * g.ch;
-    const int b_unit = c_out * 128;
     p.inv_nseg = (uint32_t)((65536 + g.nseg - 1) / g.nseg);
-    p.n_acc = (kTmemCols - 2 * c_out) / kUnitCols >= kTeams ? 2 : 1;
-    int R = (kTmemCols - p.n_acc * c_out) / kUnitCols;
-    if (R > kMaxUnits) R = kMaxUnits;
-    p.w_bytes = kv * g.nseg * b_sub;
-    const int hdr_resident = kNbrHeaderMin + ((4 * kv * g.nseg + 15) & ~15);
-    for (p.nbr_bufs = 4; p.nbr_bufs >= 2; p.nbr_bufs >>= 1) {
-        // try with the resident-weights header first; fall back to streamed weights (short header) if they do not fit
-        p.nbr_hdr = hdr_resident;
-        p.nbr_stride = (p.nbr_hdr + kvol * QL_TILE_M * 4 + 127) & ~127;
-        if (p.nbr_bufs == 4 && 4 * p.nbr_stride > 64 * 1024) continue;
-        int smem_free = kSmemBudget - 1024 - p.nbr_bufs * p.nbr_stride - ((misc_bytes + 127) & ~127);
-        p.resident = (p.w_bytes <= smem_free && p.w_bytes % 512 == 0) ? 1 : 0;   // 32 lanes x 16-byte multiples
-        if (!p.resident) {
-            p.nbr_hdr = kNbrHeaderMin;
-            p.nbr_stride = (p.nbr_hdr + kvol * QL_TILE_M * 4 + 127) & ~127;
-            smem_free = kSmemBudget - 1024 - p.nbr_bufs * p.nbr_stride - ((misc_bytes + 127) & ~127);
-        }
-        if (p.resident || smem_free / b_unit >= 2) {
-            if (!p.resident && R > smem_free / b_unit) R = smem_free / b_unit;
-            break;
-        }
+    p.teams = force_teams > 0 && force_teams <= kMaxTeams ? force_teams : kMaxTeams;
+    p.n_acc = 2 * c_out <= 256 ? 2 : 1;
+    const int cols_left = kTmemCols - p.n_acc * c_out;
+    const int tile_subs = (kvol * g.nseg + group - 1) / group * group;        // a whole tile's sub-chunks, in whole pieces
+    int n_slots = 2;
+    int U = cols_left / n_slots / 32 * group;                                  // pieces per slot x sub-chunks per piece
+    if (U > kMaxUnitSubs) U = kMaxUnitSubs / group * group;
+    if (U > tile_subs) U = tile_subs;
+    if (force_u > 0) {
+        U = (force_u + group - 1) / group * group;
+        if (U > cols_left / n_slots / 32 * group) U = cols_left / n_slots / 32 * group;
+        if (U > kMaxUnitSubs) U = kMaxUnitSubs / group * group;
     }
-    if (p.nbr_bufs < 2 || R < 2) return 0;
-    p.nbr_log2 = p.nbr_bufs == 4 ? 2 : 1;
-    const int nbr_bytes = p.nbr_bufs * p.nbr_stride;
-    p.n_ring = R;
-    p.teams = R < kTeams ? R : kTeams;
+    if (U < group) return 0;
+    p.w_bytes = kvol * g.nseg * b_sub;
+    auto ub_stride_of = [&](int u) {
+        const int offs = g.nseg > 1 ? (u + g.nseg - 2) / g.nseg + 1 : u;       // kernel offsets a unit of u sub-chunks can span
+        return (kUbHdr + offs * QL_TILE_M * 4 + 127) & ~127;
+    };
+    const int fixed = 1024 + 128 + ((misc_bytes + 127) & ~127);
+    int smem_free = kSmemBudget - fixed - kUbufs * ub_stride_of(U);
+    p.resident = (!force_stream && p.w_bytes <= smem_free && p.w_bytes % 512 == 0) ? 1 : 0;   // 32 lanes x 16-byte multiples
+    if (!p.resident) {
+        // the B slots hold n_slots x U sub-chunks
+        while (U > group && n_slots * U * b_sub > kSmemBudget - fixed - kUbufs * ub_stride_of(U)) U -= group;
+        smem_free = kSmemBudget - fixed - kUbufs * ub_stride_of(U);
+        if (n_slots * U * b_sub > smem_free) return 0;
+    }
+    // more, smaller-or-equal slots when TMEM (and the B area) allow: the producers run further ahead of the MMA thread
+    while (n_slots < kMaxSlots && (n_slots + 1) * U * areg <= cols_left &&
+           (p.resident || (n_slots + 1) * U * b_sub <= smem_free))
+        ++n_slots;
+    if (force_slots >= 2 && force_slots <= kMaxSlots && force_slots * U * areg <= cols_left &&
+        (p.resident || force_slots * U * b_sub <= smem_free))
+        n_slots = force_slots;
+    p.n_slots = n_slots;
+    p.unit_subs = U;
+    p.unit_cols = U * areg;
     p.a_col0 = p.n_acc * c_out;
-    p.off_nbr = p.resident ? ((p.w_bytes + 1023) & ~1023) : ((R * b_unit + 1023) & ~1023);
-    p.off_misc = (p.off_nbr + nbr_bytes + 127) & ~127;
+    p.ub_stride = ub_stride_of(U);
+    p.off_ub = p.resident ? ((p.w_bytes + 1023) & ~1023) : ((n_slots * U * b_sub + 1023) & ~1023);
+    p.off_tab = p.off_ub + kUbufs * p.ub_stride;
+    p.off_misc = p.off_tab + 128;
     size_t smem_bytes = 1024 + (size_t)p.off_misc + misc_bytes;
+    if (smem_bytes > (size_t)kSmemBudget) return 0;
     if (smem_bytes < (size_t)kSmemFloor) smem_bytes = kSmemFloor;
-
     return smem_bytes;
 }
 
@@ -867,7 +857,7 @@ extern "C" size_t ql_packed_weight_bytes(int32_t c_in, int32_t c_out, int32_t kv
     int es = elem_size(elem_dtype);
     if (es == 0 || c_in <= 0 || c_out <= 0 || kvol <= 0) return 0;
     const ChunkGeom g = chunk_geom(c_in * es);
-    return (size_t)(g.pair ? (kvol + 1) / 2 : kvol) * g.nseg * (size_t)c_out * g.ch;
+    return (size_t)kvol * g.nseg * (size_t)c_out * g.ch;
 }
 
 // w_host: [c_out][kvol][c_in] elements (== the reference layout (oc, kd, kh, kw, ic) flattened, quant/quant.py:37-39).
@@ -891,10 +881,8 @@ extern "C" int ql_pack_weights_host(const void* w_host, int32_t elem_dtype, int3
                 for (int c = 0; c < g.ch / 4; ++c) {
                     const int b = seg * 128 + 4 * k_word_src(g.ch, c);          // source byte of this 4-byte K word
                     if (b >= row_bytes) continue;                                // zero padding
-                    // pair mode: offset k lives in chunk k/2, bytes 16*(k%2) .. +15 of the chunk row
-                    const size_t chunk = g.pair ? (size_t)(k / 2) : (size_t)(k * g.nseg + seg);
-                    const int cc = g.pair ? c + 4 * (k & 1) : c;
-                    memcpy(dst + chunk * chunk_bytes + chunk_sw_offset(g.ch, (uint32_t)oc, (uint32_t)(cc >> 2)) + 4 * (cc & 3),
+                    const size_t chunk = (size_t)(k * g.nseg + seg);
+                    memcpy(dst + chunk * chunk_bytes + chunk_sw_offset(g.ch, (uint32_t)oc, (uint32_t)(c >> 2)) + 4 * (c & 3),
                            src + ((size_t)oc * kvol + k) * row_bytes + b, 4);
                 }
     return QL_OK;
@@ -925,11 +913,12 @@ extern "C" int ql_spconv_mma_rows(const void* feats, int32_t in_dtype, const int
     if (n_out_cap <= 0) return QL_OK;
 
     ConvParams p;
+    memset(&p, 0, sizeof(p));
     p.feats = (const uint8_t*)feats; p.nbr = nbr; p.kmask = tile_kmask; p.row_perm = row_perm; p.n_out_dev = n_out_dev; p.n_out_cap = n_out_cap;
     p.row_bytes = c_in * es; p.c_out = c_out; p.kvol = kvol;
     p.wide = (p.row_bytes % 32 == 0 && ((uintptr_t)feats & 31) == 0) ? 1 : 0;
     const ChunkGeom g = chunk_geom(p.row_bytes);
-    p.nseg = g.nseg; p.mask_words = (kvol + 31) / 32; p.pair = g.pair;
+    p.nseg = g.nseg; p.mask_words = (kvol + 31) / 32;
     p.w_packed = (const uint8_t*)w_packed; p.scale = scale; p.shift = shift; p.act_scale_dev = act_scale_dev;
     p.residual = (const __half*)residual_f16; p.relu = relu; p.out = out; p.out_dtype = out_dtype;
     p.out_q = out_q; p.out_qscale = out_qscale; p.absmax = absmax;
@@ -960,7 +949,13 @@ extern "C" int32_t ql_spconv_weights_streamed(int32_t c_in, int32_t c_out, int32
     memset(&p, 0, sizeof(p));
     p.row_bytes = c_in * es; p.c_out = c_out; p.kvol = kvol;
     const ChunkGeom g = chunk_geom(p.row_bytes);
-    p.nseg = g.nseg; p.pair = g.pair;
+    p.nseg = g.nseg;
     if (plan_conv(p, g, c_out, kvol) == 0) return 0;
     return p.resident ? 0 : 1;
 }
+
+#ifdef QL_SPCONV_ABLATE
+extern "C" int ql_debug_set_ablate(int32_t mask) {
+    return cudaMemcpyToSymbol(g_ablate, &mask, sizeof(int)) == cudaSuccess ? QL_OK : QL_ERR_CUDA;
+}
+#endif

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqlidar_b200.so")
+# QLIDAR_LIB: test-time override (the ablation build of tools/conv_sweep.py); the product always loads the library next to this file
+LIB_PATH = os.environ.get("QLIDAR_LIB") or os.path.join(_HERE, "libqlidar_b200.so")
 
 QL_OK = 0
 QL_F16, QL_F32, QL_S8, QL_S32 = 0, 1, 2, 3
@@ -47,7 +48,7 @@ SIGNATURES = {
     "ql_spconv_mma_rows": (C.c_int, [_p, _i32, _p, _p, _p, _i64, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _p]),
     "ql_spconv_weights_streamed": (_i32, [_i32, _i32, _i32, _i32]),
     "ql_permute_rows": (C.c_int, [_p, _p, _i32, _p, _i64, _p, _p]),
-    "ql_stem_conv": (C.c_int, [_p, _i32, _i32, _p, _i64, _p, _i32, _i32, _p, _p, _p, _i32, _p, _i32, _p, _p]),
+    "ql_stem_conv": (C.c_int, [_p, _i32, _i32, _p, _p, _i64, _p, _i32, _i32, _p, _p, _p, _i32, _p, _i32, _p, _p]),
     "ql_absmax_cols": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p]),
     "ql_quantize_rows": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p, _i32, _i32, _p, _p, _p]),
     "ql_bev_densify_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),

@@ -29,7 +29,7 @@ from .backbones import SparseBasicBlock
 @dataclass
 class Layer:
     name: str
-    kind: str                      # 'stem' | 'f16' | 'i8' | 'cw'
+    kind: str                      # 'stem' | 'f16' | 'i8' | 'cw' | 'row'
     cin: int
     cout: int
     ksize: tuple
@@ -158,7 +158,10 @@ class BackboneEngine:
                 L.kind = "f16"
                 wt = conv.weight.detach().float().reshape(cout, K, cin).cpu() if codes is None else codes.cpu()
                 L.w = ops.pack_weights(wt.to(torch.float16)).to(self.dev)
-            elif qw.cw or qw.per_row:
+            elif qw.per_row:
+                L.kind = "row"                     # GQConv3d: per-voxel-row fake-quant (no abs-max input), then the cw kernel
+                L.w = ops.pack_weights(codes.cpu().to(torch.float16)).to(self.dev)
+            elif qw.cw:
                 L.kind = "cw"
                 L.w = ops.pack_weights(codes.cpu().to(torch.float16)).to(self.dev)
             else:
@@ -282,7 +285,7 @@ class BackboneEngine:
             if L.kind == "i8":
                 L.q_buf = z(self.stages[L.stage_in].cap, L.cin, dt=torch.int8)
                 L.act_scale = z(1, dt=torch.float32)
-            elif L.kind == "cw":
+            elif L.kind in ("cw", "row"):
                 L.q_buf = z(self.stages[L.stage_in].cap, L.cin)
             if L.act_amax is not None:
                 L.act_amax = (L.act_amax.expand(L.cin) if L.act_amax.numel() == 1 else L.act_amax).contiguous().to(dev)
@@ -296,7 +299,7 @@ class BackboneEngine:
                 amax = L.act_amax.float()
                 L.act_scale.copy_((amax.max() / bound).reshape(1))
                 prev = self.layers[i - 1] if i > 0 else None
-                if prev is not None and prev.kind in ("f16", "i8", "cw") and L.act_bits == 8:
+                if prev is not None and prev.kind in ("f16", "i8", "cw", "row") and L.act_bits == 8:
                     tiny = amax <= (1.0 / (1 << 24))
                     prev.out_qscale = torch.where(tiny, torch.zeros_like(amax), bound / torch.where(tiny, torch.ones_like(amax), amax)).contiguous()
                     prev.out_q = L.q_buf
@@ -399,7 +402,7 @@ class BackboneEngine:
             if L.kind == "stem":
                 if perm is not None:
                     raise QlidarError("the stem conv does not take a grouped rulebook")
-                self._op("stem:" + L.name, 1, ops.stem_conv, x, nbr, so.cap, so.n_dev, L.w, L.scale, L.shift, relu=L.relu, out=L.out, absmax=absmax)
+                self._op("stem:" + L.name, 1, ops.stem_conv, x, nbr, so.cap, so.n_dev, L.w, L.scale, L.shift, relu=L.relu, out=L.out, absmax=absmax, kmask=kmask)
             elif L.kind == "f16":
                 self._op("conv:" + L.name, 1, ops.spconv_mma, x, nbr, so.cap, so.n_dev, L.cout, L.w, L.scale, L.shift, residual=res,
                          relu=L.relu, out=L.out, absmax=absmax, kmask=kmask, out_q=L.out_q, out_qscale=L.out_qscale, row_perm=perm)
@@ -410,9 +413,12 @@ class BackboneEngine:
                              act_scale=L.act_scale)
                 self._op("conv:" + L.name, 1, ops.spconv_mma, L.q_buf, nbr, so.cap, so.n_dev, L.cout, L.w, L.scale, L.shift, act_scale=L.act_scale, residual=res,
                                relu=L.relu, out=L.out, absmax=absmax, kmask=kmask, out_q=L.out_q, out_qscale=L.out_qscale, row_perm=perm)
-            elif L.kind == "cw":
-                am = L.act_amax if L.act_amax is not None else L.in_absmax
-                self._op("quantize:" + L.name, 1, ops.quantize_rows, x, am, ops.QL_Q_FAKE_PER_CHANNEL, L.act_bits, si.n_dev, out=L.q_buf)
+            elif L.kind in ("cw", "row"):
+                if L.kind == "row":
+                    self._op("quantize:" + L.name, 1, ops.quantize_rows, x, None, ops.QL_Q_FAKE_PER_ROW, L.act_bits, si.n_dev, out=L.q_buf)
+                else:
+                    am = L.act_amax if L.act_amax is not None else L.in_absmax
+                    self._op("quantize:" + L.name, 1, ops.quantize_rows, x, am, ops.QL_Q_FAKE_PER_CHANNEL, L.act_bits, si.n_dev, out=L.q_buf)
                 self._op("conv:" + L.name, 1, ops.spconv_mma, L.q_buf, nbr, so.cap, so.n_dev, L.cout, L.w, L.scale, L.shift, residual=res, relu=L.relu, out=L.out,
                                absmax=absmax, kmask=kmask, out_q=L.out_q, out_qscale=L.out_qscale, row_perm=perm)
             x = L.out
@@ -549,16 +555,19 @@ class BackboneEngine:
         """Algorithmic bytes / flops per launch: call after a forward; reads counts and pair counts back."""
         counts = self.counts()
         acct = []
-        pairs = {k: int((v >= 0).sum().item()) for k, v in self.rulebooks.items()}
+        pairs = {}
         for L in self.layers:
             n_in, n_out = counts[L.stage_in], counts[L.stage_out]
             K = int(np.prod(L.ksize))
             tiles = ops.num_tiles(n_out)
             # rows past n_out in the last tile are -1 already; tiles past the live count hold stale data -> recount live ones
-            P = int((self.rulebooks[L.rb_key][:tiles] >= 0).sum().item())
+            if L.rb_key not in pairs:
+                pairs[L.rb_key] = (int((ops.expand_rulebook(self.rulebooks[L.rb_key][:tiles], self.kmasks[L.rb_key][:tiles]) >= 0).sum().item()),
+                                   int(sum(bin(int(w) & 0xFFFFFFFF).count("1") for w in self.kmasks[L.rb_key][:tiles].flatten().cpu().tolist())))
+            P, live_slabs = pairs[L.rb_key]
             b_act = 4 if L.kind == "stem" else (1 if L.kind == "i8" else 2)
             b_w = 4 if L.kind == "stem" else (1 if L.kind == "i8" else 2)
             by = n_in * L.cin * b_act + n_out * L.cout * 2 + K * L.cin * L.cout * b_w + 4 * P + (n_out * L.cout * 2 if L.residual else 0)
             acct.append(dict(name=L.name, kind=L.kind, n_in=n_in, n_out=n_out, pairs=P, cin=L.cin, cout=L.cout, K=K,
-                             bytes_alg=by, flops_alg=2 * P * L.cin * L.cout, rulebook_bytes_read=tiles * K * 512))
+                             bytes_alg=by, flops_alg=2 * P * L.cin * L.cout, rulebook_bytes_read=live_slabs * 512, live_slabs=live_slabs, tiles=tiles))
         return acct

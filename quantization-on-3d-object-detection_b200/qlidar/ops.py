@@ -120,9 +120,26 @@ def mask_words(kvol: int) -> int:
     return (int(kvol) + 31) // 32
 
 
+def expand_rulebook(nbr: torch.Tensor, kmask: Optional[torch.Tensor]) -> torch.Tensor:
+    """Dense [tiles, K, 128] view (-1 = no neighbour) of a COMPACT rulebook (include/qlidar.h: with a mask only the live
+    slabs of a tile are stored, first in its block).  For tests and accounting -- the kernels consume the compact form."""
+    if kmask is None:
+        return nbr
+    tiles, K, _ = nbr.shape
+    km = kmask[:tiles]
+    sh = torch.arange(32, device=nbr.device, dtype=torch.int32)
+    bits = ((km.unsqueeze(-1) >> sh) & 1).reshape(tiles, -1)[:, :K].bool()
+    pos = bits.long().cumsum(1) - 1
+    dense = torch.full_like(nbr, -1)
+    t_idx, k_idx = bits.nonzero(as_tuple=True)
+    dense[t_idx, k_idx] = nbr[t_idx, pos[t_idx, k_idx]]
+    return dense
+
+
 def rulebook_subm(coords: torch.Tensor, n_dev: Optional[torch.Tensor], grid, ksize, table: torch.Tensor,
                   nbr: Optional[torch.Tensor] = None, kmask: Optional[torch.Tensor] = None, with_mask: bool = False):
-    """nbr int32 [tiles, K, 128]; with_mask (or a kmask buffer) also returns the per-tile offset mask int32 [tiles, ceil(K/32)]."""
+    """nbr int32 [tiles, K, 128]; with_mask (or a kmask buffer) also returns the per-tile offset mask int32 [tiles, ceil(K/32)]
+    and makes the rulebook COMPACT (expand_rulebook gives the dense view)."""
     _need_cuda(coords, n_dev, table, nbr, kmask)
     k = triple(ksize)
     K = k[0] * k[1] * k[2]
@@ -359,9 +376,11 @@ def spconv_mma(feats: torch.Tensor, nbr: torch.Tensor, n_out_cap: int, n_out_dev
 
 def stem_conv(feats: torch.Tensor, nbr: torch.Tensor, n_out_cap: int, n_out_dev: Optional[torch.Tensor], w_kio: torch.Tensor,
               scale: torch.Tensor, shift: torch.Tensor, relu: bool = True, out: Optional[torch.Tensor] = None,
-              out_dtype: torch.dtype = torch.float16, absmax: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """w_kio: (K, c_in, c_out) fp32; feats (N, stride >= c_in) fp32 (stride 8 = the engine's padded rows, one 256-bit load each)."""
-    _need_cuda(feats, nbr, n_out_dev, w_kio, scale, shift, out, absmax)
+              out_dtype: torch.dtype = torch.float16, absmax: Optional[torch.Tensor] = None,
+              kmask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """w_kio: (K, c_in, c_out) fp32; feats (N, stride >= c_in) fp32 (stride 8 = the engine's padded rows, one 256-bit load each).
+    kmask: the rulebook's per-tile offset mask (the rulebook is then compact), None = dense rulebook."""
+    _need_cuda(feats, nbr, n_out_dev, w_kio, scale, shift, out, absmax, kmask)
     if feats.dtype != torch.float32 or w_kio.dtype != torch.float32:
         raise QlidarError("stem_conv is the fp32 path")
     K, c_in, c_out = w_kio.shape
@@ -369,7 +388,9 @@ def stem_conv(feats: torch.Tensor, nbr: torch.Tensor, n_out_cap: int, n_out_dev:
         raise QlidarError("stem_conv: feature rows narrower than c_in")
     if out is None:
         out = torch.empty((n_out_cap, c_out), dtype=out_dtype, device=feats.device)
-    check(lib().ql_stem_conv(_ptr(feats), int(feats.shape[1]), c_in, _ptr(nbr), int(n_out_cap), _ptr(n_out_dev), c_out, K, _ptr(w_kio), _ptr(scale), _ptr(shift),
+    if kmask is not None and (kmask.dtype != torch.int32 or kmask.shape[0] < num_tiles(n_out_cap) or kmask.shape[1] != mask_words(K)):
+        raise QlidarError("kmask must be int32 [tiles, ceil(K/32)]")
+    check(lib().ql_stem_conv(_ptr(feats), int(feats.shape[1]), c_in, _ptr(nbr), _ptr(kmask), int(n_out_cap), _ptr(n_out_dev), c_out, K, _ptr(w_kio), _ptr(scale), _ptr(shift),
                              1 if relu else 0, _ptr(out), _DT[out.dtype], _ptr(absmax), _stream()), "ql_stem_conv")
     return out
 

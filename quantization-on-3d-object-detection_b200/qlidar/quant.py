@@ -27,6 +27,13 @@ class QConvNd(SparseModule):
 
     def __init__(self, module: SparseConvolution, w_bits: int, act_bits: int, cw: bool, per_row: bool = False):
         super().__init__()
+        # The reference's fake-quant accepts any bit width; the real-integer kernels hold weight codes in int8 (kind::i8) or as
+        # exact fp16 integers (kind::f16, exact only to 2048), so wider weights would be silently corrupted: refuse them.
+        if not 2 <= int(w_bits) <= 8:
+            raise ValueError(f"QConvNd: weight codes are 8-bit integers on this path (w_bits={w_bits}); the reference's "
+                             "configurations are W8A8 and W8A16 (quant/quant_centerpoint.py)")
+        if int(act_bits) < 2:
+            raise ValueError(f"QConvNd: act_bits={act_bits}")
         self.module = module
         self.w = self.module.weight.data.clone()
         self.w_quant = TensorQuantizer(QuantDescriptor(num_bits=w_bits, axis=(0)))
@@ -130,11 +137,32 @@ class QConv2d(QConvNd):
 
 class GQConv3d(QConvNd):
     """quant/quant_conv3d.py:70-138: per-voxel-row activation amax (axis=0 on <=64-row groups; grouping does not
-    change the values).  The reference writes the fake-quantised rows back in place (a bug); not mirrored."""
+    change the values).  The reference writes the fake-quantised rows back in place (a bug); not mirrored.
+    Same constructor as the reference -- GQConv3d(spconv3d, act_bits, w_bits, n), called with keywords at
+    quant/quant_conv3d.py:290 -- and the same attribute names (.spconv3d, .orig_w)."""
 
-    def __init__(self, module, w_bits=8, act_bits=8, n=64):
-        super().__init__(module, w_bits, act_bits, cw=False, per_row=True)
+    def __init__(self, spconv3d, act_bits=8, w_bits=8, n=64):
+        super().__init__(spconv3d, w_bits, act_bits, cw=False, per_row=True)
         self.n = n
+
+    @property
+    def spconv3d(self):
+        return self.module
+
+    @property
+    def orig_w(self):
+        return self.w
+
+
+def gq_conv3d(model, module_dict, curr_path, w_bits, act_bits, n) -> None:
+    """The group-quantisation surgery of quant/quant_conv3d.py:280-292 (its own `q_conv3d`): every SubMConv3d/SparseConv3d
+    except backbone_3d.conv_input.0 becomes GQConv3d(spconv3d=module, w_bits=..., act_bits=..., n=n)."""
+    for name, module in model.named_children():
+        path = f"{curr_path}.{name}" if curr_path else name
+        gq_conv3d(module, module_dict, path, w_bits, act_bits, n)
+        if isinstance(module, (SubMConv3d, SparseConv3d)) and path != "backbone_3d.conv_input.0":
+            model._modules[name] = GQConv3d(spconv3d=module, w_bits=w_bits, act_bits=act_bits, n=n)
+    return
 
 
 class SQConv3d(SparseModule):

@@ -26,3 +26,10 @@ def random_coords(rng, B, D, H, W, density):
     occ = rng.random((B, D, H, W)) < density
     c = np.argwhere(occ).astype(np.int32)
     return c[rng.permutation(len(c))]
+
+
+def dense_nbr(ops, nbr, kmask, n: int) -> np.ndarray:
+    """(K, n) oracle-form rulebook out of the kernels' COMPACT [tiles, K, 128] + per-tile mask form (include/qlidar.h)."""
+    tiles = max(1, (int(n) + TILE_M - 1) // TILE_M)
+    d = ops.expand_rulebook(nbr[:tiles], None if kmask is None else kmask[:tiles])
+    return tiles_to_nbr(d.cpu().numpy(), int(n))

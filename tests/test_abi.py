@@ -32,7 +32,7 @@ def test_header_symbols_are_exported_and_bound():
 def test_host_only_entry_points():
     from qlidar import _lib
     lib = _lib.lib()
-    assert lib.ql_abi_version() == 2
+    assert lib.ql_abi_version() == 3
     assert lib.ql_error_string(0) == b"ok"
     assert b"workspace" in lib.ql_error_string(-4)
     assert lib.ql_hash_capacity(1000) == 2048
@@ -41,7 +41,7 @@ def test_host_only_entry_points():
     assert lib.ql_rulebook_mask_words(27) == 1 and lib.ql_rulebook_mask_words(125) == 4
     # chunk = one kernel offset x one <=128-byte row segment, padded to 32 / 64 / 128 bytes
     assert lib.ql_packed_weight_bytes(16, 16, 27, _lib.QL_F16) == 27 * 16 * 32
-    assert lib.ql_packed_weight_bytes(16, 16, 27, _lib.QL_S8) == 14 * 16 * 32       # 16-byte rows: two kernel offsets per 32-byte chunk
+    assert lib.ql_packed_weight_bytes(16, 16, 27, _lib.QL_S8) == 27 * 16 * 32       # 16-byte rows are zero padded to the 32-byte k-step
     assert lib.ql_packed_weight_bytes(128, 64, 27, _lib.QL_F16) == 27 * 2 * 64 * 128
     assert lib.ql_packed_weight_bytes(15, 16, 27, _lib.QL_F32) == 0
     # weights are shared-memory resident up to C = 32 (fp16) / C = 64 (int8) for a 3^3 kernel, streamed per unit above
@@ -84,20 +84,6 @@ def test_pack_weights_host_layout():
         raw = w.contiguous().view(torch.uint8).reshape(cout, K, -1).numpy()
         row_bytes = raw.shape[2]
         ch, nseg = _chunk_geom(row_bytes)
-        if row_bytes == 16:
-            # pair mode: chunk j = kernel offsets (2j | 2j+1), 16 bytes each, so that a K = 32 int8 MMA carries no padding
-            KV = (K + 1) // 2
-            assert packed.size == KV * cout * 32
-            for j in range(KV):
-                img = packed[j * cout * 32:(j + 1) * cout * 32]
-                for r in range(cout):
-                    x = (r // 4) % 2
-                    for half in range(2):
-                        off = (r // 8) * 256 + (r % 8) * 32 + ((half ^ x) * 16)
-                        k = 2 * j + half
-                        want = raw[r, k, :16] if k < K else np.zeros(16, np.uint8)
-                        assert np.array_equal(img[off:off + 16], want)
-            continue
         assert packed.size == K * nseg * cout * ch
         seen = np.zeros(packed.size, dtype=bool)
         for k in range(K):

@@ -207,7 +207,7 @@ def test_engine_int32_accumulators_match_oracle_on_first_quantized_layer():
     rb = conv.get_rulebook(st)
     codes, act_scale = ops.quantize_rows(x.cuda(), ops.absmax_cols(x.cuda()), ops.QL_Q_CODES_PER_TENSOR)
     acc = torch.zeros((coords.shape[0], 64), dtype=torch.int32, device="cuda")
-    ops.spconv_mma(codes, rb.nbr, rb.n_out, None, 64, packed, w_scale, shift, out=acc)
+    ops.spconv_mma(codes, rb.nbr, rb.n_out, None, 64, packed, w_scale, shift, out=acc, kmask=rb.kmask)
     assert torch.equal(acc.cpu(), acc_ref)
     with torch.no_grad():
         y = q(st)

@@ -54,7 +54,7 @@ def test_subm_rulebook_identity_and_symmetry(frame):
     ops, n = frame["ops"], frame["n"]
     nbr, kmask = ops.rulebook_subm(frame["coords"], frame["n_dev"], frame["grid"], 3, frame["table"], with_mask=True)
     tiles = (n + 127) // 128
-    flat = nbr[:tiles].permute(1, 0, 2).reshape(27, -1)[:, :n]          # (K, n)
+    flat = ops.expand_rulebook(nbr[:tiles], kmask[:tiles]).permute(1, 0, 2).reshape(27, -1)[:, :n]          # (K, n)
     rows = torch.arange(n, device="cuda", dtype=torch.int32)
     assert torch.equal(flat[13], rows)                                  # centre tap
     for k in (0, 4, 9, 12):
@@ -75,7 +75,7 @@ def test_strided_outputs_sorted_unique_and_ranked_paths_match_hash(frame):
     assert bool((keys[1:] > keys[:-1]).all())                           # ascending, unique
     # out-set == { (c + pad - k) / stride exact, in range }: every pair's output coordinate is consistent with its input's
     tiles = (m + 127) // 128
-    flat = nbr[:tiles].permute(1, 0, 2).reshape(27, -1)[:, :m]
+    flat = ops.expand_rulebook(nbr[:tiles], kmask[:tiles]).permute(1, 0, 2).reshape(27, -1)[:, :m]
     assert bool(((flat >= 0).sum(dim=0) > 0).all())                     # every output site has at least one input
     ins = frame["coords"][:frame["n"]].long()
     for k in (0, 13, 26):
@@ -92,18 +92,19 @@ def test_strided_outputs_sorted_unique_and_ranked_paths_match_hash(frame):
     # rank-index paths on this key-sorted stage == hash paths, bit for bit
     ws = torch.zeros(ops.rulebook_strided_workspace_bytes(grid, 3, 2, 1), dtype=torch.uint8, device="cuda")
     oc2 = torch.zeros_like(oc); n2 = torch.zeros_like(n_out); nbr2 = torch.zeros_like(nbr)
-    ops.rulebook_strided(frame["coords"], frame["n_dev"], grid, 3, 2, 1, cap, out=(oc2, n2, None, nbr2), workspace=ws)
-    assert torch.equal(oc2[:m], oc[:m]) and torch.equal(nbr2[:tiles], nbr[:tiles])
+    km2 = ops.rulebook_strided(frame["coords"], frame["n_dev"], grid, 3, 2, 1, cap, out=(oc2, n2, None, nbr2), workspace=ws)[-1]
+    ex = ops.expand_rulebook
+    assert torch.equal(oc2[:m], oc[:m]) and torch.equal(ex(nbr2[:tiles], km2[:tiles]), ex(nbr[:tiles], kmask[:tiles]))
     index = ops.rulebook_strided_index(grid, 3, 2, 1, ws)
     a, ka = ops.rulebook_subm_ranked(oc, n_out, ogrid, 3, index)
     b, kb = ops.rulebook_subm(oc, n_out, ogrid, 3, table, with_mask=True)
-    assert torch.equal(a[:tiles], b[:tiles]) and torch.equal(ka[:tiles], kb[:tiles])
+    assert torch.equal(ex(a[:tiles], ka[:tiles]), ex(b[:tiles], kb[:tiles])) and torch.equal(ka[:tiles], kb[:tiles])
     oc3_h, n3_h, _, nbr3_h, og3, km3_h = ops.rulebook_strided(oc, n_out, ogrid, 3, 2, 1, 400000)
     oc3_r, n3_r, _, nbr3_r, _, km3_r = ops.rulebook_strided(oc, n_out, ogrid, 3, 2, 1, 400000, in_index=index)
     m3 = int(n3_h[0].item())
     t3 = (m3 + 127) // 128
     assert n3_r.tolist() == n3_h.tolist() and torch.equal(oc3_r[:m3], oc3_h[:m3])
-    assert torch.equal(nbr3_r[:t3], nbr3_h[:t3]) and torch.equal(km3_r[:t3], km3_h[:t3])
+    assert torch.equal(ex(nbr3_r[:t3], km3_r[:t3]), ex(nbr3_h[:t3], km3_h[:t3])) and torch.equal(km3_r[:t3], km3_h[:t3])
 
 
 @pytest.mark.parametrize("C", [16, 64, 128])
@@ -119,7 +120,7 @@ def test_int8_accumulator_checksum_of_checksums(frame, C):
     ops.spconv_mma(x, nbr, frame["coords"].shape[0], frame["n_dev"], C, packed, one, torch.zeros(C, device="cuda"), out=acc, kmask=kmask)
     got = acc[:n].long().sum(dim=0)                                     # per output channel, exact
     tiles = (n + 127) // 128
-    flat = nbr[:tiles].permute(1, 0, 2).reshape(27, -1)[:, :n]
+    flat = ops.expand_rulebook(nbr[:tiles], kmask[:tiles]).permute(1, 0, 2).reshape(27, -1)[:, :n]
     want = torch.zeros(C, dtype=torch.int64, device="cuda")
     for k in range(27):
         idx = flat[k][flat[k] >= 0].long()

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 import qlidar_oracle as O
-from helpers import nbr_to_tiles, tiles_to_nbr, random_coords
+from helpers import nbr_to_tiles, tiles_to_nbr, random_coords, dense_nbr
 
 pytestmark = pytest.mark.gpu
 
@@ -33,12 +33,15 @@ def test_rulebook_subm_bit_exact(ops, ksize):
     c = dev(coords)
     table = ops.hash_build(c, None, (B, D, H, W))
     nbr, kmask = ops.rulebook_subm(c, None, (B, D, H, W), ksize, table, with_mask=True)
-    got = tiles_to_nbr(nbr.cpu().numpy(), coords.shape[0])
+    got = dense_nbr(ops, nbr, kmask, coords.shape[0])
     assert np.array_equal(got, ref)
     assert np.array_equal(kmask.cpu().numpy().view(np.uint32), O.tile_kmask(ref))
     # rows of the last tile beyond N are -1
-    tail = nbr.cpu().numpy().transpose(1, 0, 2).reshape(ref.shape[0], -1)[:, coords.shape[0]:]
+    tail = ops.expand_rulebook(nbr, kmask).cpu().numpy().transpose(1, 0, 2).reshape(ref.shape[0], -1)[:, coords.shape[0]:]
     assert (tail == -1).all()
+    # the same build without a mask is the dense layout
+    nbr_d = ops.rulebook_subm(c, None, (B, D, H, W), ksize, table)
+    assert np.array_equal(tiles_to_nbr(nbr_d.cpu().numpy(), coords.shape[0]), ref)
 
 
 def test_rulebook_subm_device_count(ops):
@@ -69,11 +72,11 @@ def test_rulebook_strided_bit_exact(ops, k, s, p):
     assert n == oc_ref.shape[0]
     assert list(ogrid[1:]) == list(osh)
     assert np.array_equal(out_coords[:n].cpu().numpy(), oc_ref)          # same order: ascending linear key
-    assert np.array_equal(tiles_to_nbr(nbr.cpu().numpy(), n), nbr_ref)
+    assert np.array_equal(dense_nbr(ops, nbr, kmask, n), nbr_ref)
     tiles = (n + 127) // 128
     assert np.array_equal(kmask[:tiles].cpu().numpy().view(np.uint32), O.tile_kmask(nbr_ref))
     # order-free form required by the parity gate: (k, in_coord, out_coord) sorted sets
-    a = O.pairs_in_coord_space(tiles_to_nbr(nbr.cpu().numpy(), n), coords, out_coords[:n].cpu().numpy())
+    a = O.pairs_in_coord_space(dense_nbr(ops, nbr, kmask, n), coords, out_coords[:n].cpu().numpy())
     b = O.pairs_in_coord_space(nbr_ref, coords, oc_ref)
     assert np.array_equal(a, b)
     # the output table maps out coords -> rows: a submanifold rulebook on the outputs must hit every centre
@@ -96,20 +99,20 @@ def test_rank_index_subm_rulebook_and_bev_bit_exact(ops, k, s, p, ksub):
     n_out = torch.zeros(2, dtype=torch.int32, device="cuda")
     K = int(np.prod(O._triple(k)))
     nbr = torch.zeros(((cap + 127) // 128, K, 128), dtype=torch.int32, device="cuda")
-    _, _, tbl, _, ogrid, _ = ops.rulebook_strided(dev(coords), None, (B, D, H, W), k, s, p, cap, out=(out_coords, n_out, None, nbr), workspace=ws)
+    _, _, tbl, _, ogrid, kmask = ops.rulebook_strided(dev(coords), None, (B, D, H, W), k, s, p, cap, out=(out_coords, n_out, None, nbr), workspace=ws)
     assert tbl is None and n_out.tolist() == [n, n]
     assert np.array_equal(out_coords[:n].cpu().numpy(), oc_ref)
-    assert np.array_equal(tiles_to_nbr(nbr.cpu().numpy(), n), nbr_ref)
+    assert np.array_equal(dense_nbr(ops, nbr, kmask, n), nbr_ref)
     index = ops.rulebook_strided_index((B, D, H, W), k, s, p, ws)
     sub_ref = O.rulebook_subm(oc_ref, osh, ksub)
     nbr2, kmask2 = ops.rulebook_subm_ranked(out_coords, n_out, ogrid, ksub, index)
-    assert np.array_equal(tiles_to_nbr(nbr2.cpu().numpy(), n), sub_ref)
+    assert np.array_equal(dense_nbr(ops, nbr2, kmask2, n), sub_ref)
     tiles = (n + 127) // 128
     assert np.array_equal(kmask2[:tiles].cpu().numpy().view(np.uint32), O.tile_kmask(sub_ref))
     # identical to the hash path
     table = ops.hash_build(out_coords, n_out, ogrid)
     nbr3, kmask3 = ops.rulebook_subm(out_coords, n_out, ogrid, ksub, table, with_mask=True)
-    assert torch.equal(nbr2[:tiles], nbr3[:tiles]) and torch.equal(kmask2[:tiles], kmask3[:tiles])
+    assert torch.equal(ops.expand_rulebook(nbr2[:tiles], kmask2[:tiles]), ops.expand_rulebook(nbr3[:tiles], kmask3[:tiles])) and torch.equal(kmask2[:tiles], kmask3[:tiles])
     # BEV hand-off through the rank index
     C = 64
     f = torch.from_numpy(rng.normal(size=(cap, C)).astype(np.float32)).half()
@@ -123,13 +126,13 @@ def test_rank_index_subm_rulebook_and_bev_bit_exact(ops, k, s, p, ksub):
         oc2, n2, t2, nb2, og2, km2 = ops.rulebook_strided(out_coords, n_out, ogrid, k2, s2, p2, m + 50, in_index=index)
         assert t2 is None and n2.tolist() == [m, m]
         assert np.array_equal(oc2[:m].cpu().numpy(), oc2_ref) and list(og2[1:]) == list(osh2)
-        assert np.array_equal(tiles_to_nbr(nb2.cpu().numpy(), m), nbr2_ref)
+        assert np.array_equal(dense_nbr(ops, nb2, km2, m), nbr2_ref)
         assert np.array_equal(km2[:(m + 127) // 128].cpu().numpy().view(np.uint32), O.tile_kmask(nbr2_ref))
     # a row cap below the number of sites: the dropped (largest-key) sites are absent everywhere
     n_small = torch.tensor([n - 40, n], dtype=torch.int32, device="cuda")
-    nbr4, _ = ops.rulebook_subm_ranked(out_coords, n_small, ogrid, ksub, index)
+    nbr4, km4 = ops.rulebook_subm_ranked(out_coords, n_small, ogrid, ksub, index)
     ref4 = O.rulebook_subm(oc_ref[:n - 40], osh, ksub)
-    assert np.array_equal(tiles_to_nbr(nbr4.cpu().numpy(), n - 40), ref4)
+    assert np.array_equal(dense_nbr(ops, nbr4, km4, n - 40), ref4)
 
 
 def test_rulebook_strided_overflow_is_safe(ops):
@@ -142,7 +145,7 @@ def test_rulebook_strided_overflow_is_safe(ops):
     out_coords, n_out, out_table, nbr, ogrid, kmask = ops.rulebook_strided(c, None, (B, D, H, W), 3, 2, 1, cap)
     assert n_out.tolist() == [cap, oc_ref.shape[0]]                     # (kept, found): overflow is reported
     assert np.array_equal(out_coords.cpu().numpy(), oc_ref[:cap])
-    assert nbr.max().item() < coords.shape[0]
+    assert ops.expand_rulebook(nbr[:(cap + 127) // 128], kmask[:(cap + 127) // 128]).max().item() < coords.shape[0]
 
 
 # ------------------------------------------------------------------------------------------------ voxelization
@@ -318,12 +321,12 @@ def test_rulebook_subm_grouped_is_a_row_permutation_of_the_plain_rulebook(ops, k
     oc_np = oc[:n].cpu().numpy()
     ref = O.rulebook_subm(oc_np, list(grid[1:]), ksub)                       # (K, n), rows in key order
     nbr_p, kmask_p = ops.rulebook_subm_ranked(oc, n_out, grid, ksub, index)
-    assert np.array_equal(tiles_to_nbr(nbr_p.cpu().numpy(), n), ref)
+    assert np.array_equal(dense_nbr(ops, nbr_p, kmask_p, n), ref)
     nbr_g, kmask_g, perm = ops.rulebook_subm_ranked_grouped(oc, n_out, grid, ksub, index)
     tiles = (n + 127) // 128
     perm_np = perm[:tiles * 128].cpu().numpy()
     assert np.array_equal(np.sort(perm_np[:n]), np.arange(n)) and (perm_np[n:] == -1).all()
-    g = tiles_to_nbr(nbr_g.cpu().numpy(), tiles * 128)                       # (K, slots)
+    g = dense_nbr(ops, nbr_g, kmask_g, tiles * 128)                          # (K, slots)
     assert np.array_equal(g[:, :n], ref[:, perm_np[:n]]) and (g[:, n:] == -1).all()
     km = kmask_g[:tiles].cpu().numpy().view(np.uint32)
     assert np.array_equal(km, O.tile_kmask(g))
@@ -358,7 +361,7 @@ def test_spconv_through_grouped_rulebook_is_bit_identical(ops, cin, cout, int8):
         w = ops.pack_weights(qw).cuda()
         acc = torch.zeros((n, cout), dtype=torch.int32, device="cuda")
         ops.spconv_mma(x, nbr_g, n, n_out, cout, w, torch.ones(cout, device="cuda"), torch.zeros(cout, device="cuda"), out=acc, kmask=kmask_g, row_perm=perm)
-        ref = O.sparse_conv_int(x.cpu(), tiles_to_nbr(nbr_p.cpu().numpy(), n), qw.reshape(cout, 3, 3, 3, cin))
+        ref = O.sparse_conv_int(x.cpu(), dense_nbr(ops, nbr_p, kmask_p, n), qw.reshape(cout, 3, 3, 3, cin))
         assert torch.equal(acc.cpu(), ref)
     else:
         x = torch.from_numpy(rng.normal(size=(n, cin)).astype(np.float32)).half().cuda()
@@ -391,7 +394,7 @@ def test_spconv_many_tiles_per_cta_with_offset_mask(ops, cin, cout, int8):
     c = dev(coords)
     table = ops.hash_build(c, None, (1, 12, S, S))
     nbr, kmask = ops.rulebook_subm(c, None, (1, 12, S, S), 3, table, with_mask=True)
-    assert np.array_equal(tiles_to_nbr(nbr.cpu().numpy(), N), nbr_ref)
+    assert np.array_equal(dense_nbr(ops, nbr, kmask, N), nbr_ref)
     km = kmask.cpu().numpy().view(np.uint32)
     assert np.array_equal(km, O.tile_kmask(nbr_ref))
     assert np.mean([bin(int(v)).count("1") for v in km[:, 0]]) < 24      # the mask really skips slabs on this input
@@ -405,8 +408,8 @@ def test_spconv_many_tiles_per_cta_with_offset_mask(ops, cin, cout, int8):
         ops.spconv_mma(dev(qx), nbr, N, None, cout, ops.pack_weights(qw.reshape(cout, 27, cin)).cuda(), one, zero, out=out, kmask=kmask)
         assert torch.equal(out.cpu(), ref), f"mismatches: {(out.cpu() != ref).sum().item()} of {ref.numel()}"
         out2 = torch.full((N, cout), -12345, dtype=torch.int32, device="cuda")
-        ops.spconv_mma(dev(qx), nbr, N, None, cout, ops.pack_weights(qw.reshape(cout, 27, cin)).cuda(), one, zero, out=out2)
-        assert torch.equal(out2.cpu(), ref)                              # without the mask: same accumulators
+        ops.spconv_mma(dev(qx), ops.expand_rulebook(nbr, kmask), N, None, cout, ops.pack_weights(qw.reshape(cout, 27, cin)).cuda(), one, zero, out=out2)
+        assert torch.equal(out2.cpu(), ref)                              # dense rulebook, no mask: same accumulators
     else:
         x = torch.from_numpy(rng.normal(size=(N, cin)).astype(np.float32)).half()
         qw = torch.from_numpy(rng.integers(-127, 128, size=(cout, 27, cin)).astype(np.int8))
@@ -469,6 +472,14 @@ def test_stem_conv(ops):
     x8[:, :5] = x
     out8 = ops.stem_conv(dev(x8), dev(nbr_to_tiles(nbr)), N, None, dev(w_kio), dev(scale), dev(shift), relu=True, out_dtype=torch.float32)
     assert torch.equal(out8, out)
+    # the compact (masked) rulebook of the same sites gives the same bits
+    c = dev(coords)
+    S = int(np.sqrt(3000))
+    table = ops.hash_build(c, None, (1, 12, S, S))
+    nbr_c, km_c = ops.rulebook_subm(c, None, (1, 12, S, S), 3, table, with_mask=True)
+    assert np.array_equal(dense_nbr(ops, nbr_c, km_c, N), nbr)
+    outc8 = ops.stem_conv(dev(x8), nbr_c, N, None, dev(w_kio), dev(scale), dev(shift), relu=True, out_dtype=torch.float32, kmask=km_c)
+    assert torch.equal(outc8, out)
     # 4 raw features (KITTI) and a width the specialised kernels do not cover
     for cin in (4, 7):
         xc = torch.from_numpy(rng.normal(size=(N, cin)).astype(np.float32))
@@ -608,7 +619,7 @@ def test_renumber_by_key_sorts_and_leaves_a_rank_index(ops):
     index = ops.rulebook_strided_index(grid, 1, 1, 0, ws)
     nbr, kmask = ops.rulebook_subm_ranked(oc, n_out, grid, 3, index)
     ref = O.rulebook_subm(coords[order], [D, H, W], 3)
-    assert np.array_equal(tiles_to_nbr(nbr.cpu().numpy(), n), ref)
+    assert np.array_equal(dense_nbr(ops, nbr, kmask, n), ref)
     # coordinates only (no payload), and an empty list
     oc2, n2, src2, r2 = ops.renumber_by_key(c_in, n_dev, grid, ws)
     assert r2 is None and torch.equal(oc2[:n], oc[:n]) and torch.equal(src2[:n], src[:n])
