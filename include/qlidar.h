@@ -179,6 +179,10 @@ int ql_rulebook_subm_ranked_grouped(const int32_t* coords, int64_t n_cap, const 
  *      post_act_block / SparseBasicBlock, spconv_backbone.py:8-27,51-67).
  *      feats: [n_in, c_in] fp16 (kind::f16, fp32 accumulate) or int8 codes (kind::i8, int32 accumulate); the gathered
  *      rows go global -> registers -> tensor memory (A operand read from TMEM), never through shared memory.
+ *      ZERO-ROW CONTRACT: the row in front of the features -- the c_in * elem_size bytes at feats - c_in * elem_size --
+ *      must be readable and all zero.  A missing neighbour is rulebook index -1, and the gather reads row -1 for it
+ *      without a predicate or a select (round 2: the kernel was bound by instruction issue, profiles/r02_conv_ablation.md).
+ *      qlidar.ops.zero_led_rows allocates such buffers; qlidar.ops.spconv_mma copies any other tensor into one.
  *      nbr / tile_kmask: a rulebook from ql_rulebook_subm / ql_rulebook_strided (compact when tile_kmask is given);
  *      tile_kmask may be NULL (dense rulebook, every offset is visited); kvol <= 128.
  *      w_packed: per-output-channel int8 codes (as fp16 exact integers for the f16 kind) in the shared-memory

@@ -321,7 +321,9 @@ def quant_scale(amax: torch.Tensor, bits: int) -> torch.Tensor:
     bound = quant_bound(bits)
     amax = amax.to(torch.float32)
     tiny = amax <= (1.0 / (1 << 24))
-    return torch.where(tiny, torch.zeros_like(amax), bound / torch.where(tiny, torch.ones_like(amax), amax))
+    # ONE correctly rounded division per element, like the library (`max_bound / amax`, both tensors).  NOT `bound / tensor`:
+    # Python evaluates that as tensor.reciprocal() * bound -- two roundings, an ulp off in a quarter of the cases.
+    return torch.where(tiny, torch.zeros_like(amax), torch.full_like(amax, bound) / torch.where(tiny, torch.ones_like(amax), amax))
 
 
 def quantize_codes(t: torch.Tensor, amax: torch.Tensor, bits: int) -> torch.Tensor:

@@ -57,14 +57,22 @@ constexpr uint32_t kFlagFirst = 1u, kFlagLast = 2u;
 // 8 = no epilogue global traffic, 16 = no rulebook slab copies, 64 = no tcgen05.ld / epilogue arithmetic
 __device__ int g_ablate = 0;
 #define QL_ABL(bit) ((g_ablate & (bit)) != 0)
+// role trace of the same test-time build: clock64() around every wait / work phase of each role's lead thread, summed over
+// the CTAs of a launch into g_trace[launch % 64][role * 8 + counter] (tools/conv_sweep.py TRACE=1 prints the shares)
+__device__ unsigned long long g_trace[64][32];
+#define QL_TR_DECL(n) long long tr_[n] = {}; long long tr_t0_ = clock64(); const long long tr_start_ = tr_t0_
+#define QL_TR(i) do { const long long t_ = clock64(); tr_[i] += t_ - tr_t0_; tr_t0_ = t_; } while (0)
+#define QL_TR_FLUSH(role, n, lead) do { if (lead) { tr_[(n) - 1] = clock64() - tr_start_; \
+        for (int i_ = 0; i_ < (n); ++i_) atomicAdd(&g_trace[p.trace_id & 63][(role) * 8 + i_], (unsigned long long)tr_[i_]); } } while (0)
 #else
 #define QL_ABL(bit) false
+#define QL_TR_DECL(n)
+#define QL_TR(i)
+#define QL_TR_FLUSH(role, n, lead)
 #endif
 
-__device__ __align__(128) uint8_t g_zero_line[128];       // what a missing neighbour reads (zero-initialised module memory)
-
 struct ConvParams {
-    const uint8_t* feats;
+    const uint8_t* feats;   // [n_in][row_bytes], preceded by one all-zero row: feats[-1] is what a missing neighbour (index -1) reads
     const int* nbr;         // compact rulebook [tiles][kvol][128]: the first popc(kmask[tile]) slabs of a tile are its live offsets
     const uint32_t* kmask;  // [tiles][mask_words] or null (every offset live: the dense rulebook)
     const int* row_perm;    // [tiles][128] tile slot -> output row (-1 = padding) of a GROUPED rulebook, or null (slot == row)
@@ -97,6 +105,7 @@ struct ConvParams {
     int ub_stride;          // bytes per ring entry
     int off_tab;            // smem offset of the loader's ordinal -> offset table (128 bytes)
     int off_misc;           // smem offset of MiscSmem from the 1024-aligned base
+    int trace_id;           // (test-time build) launch number for the role trace
 };
 
 struct MiscSmem {
@@ -168,6 +177,12 @@ __device__ __forceinline__ void ldg32(const uint8_t* p, uint32_t* v) {
 }
 __device__ __forceinline__ void ldg16(const uint8_t* p, uint32_t* v) {
     asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p));
+}
+// base + id * mul in ONE instruction (IMAD.WIDE, signed 32 x 32 + 64): the address of gathered row `id` (-1 = the zero row)
+__device__ __forceinline__ const uint8_t* row_ptr(const uint8_t* base, int id, int mul) {
+    uint64_t r;
+    asm volatile("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(id), "r"(mul), "l"(base));
+    return reinterpret_cast<const uint8_t*>(r);
 }
 __device__ __forceinline__ int lds_u8(uint32_t addr) {
     int v;
@@ -298,6 +313,7 @@ __global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p
         const int w = warp;                                  // TMEM lane quarter (warp id % 4)
         const int et = tid;                                  // 0..127 == row in tile
         uint32_t it = 0;
+        QL_TR_DECL(8);
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int a = p.n_acc == 2 ? (int)(it & 1u) : 0;
             const uint32_t aph = p.n_acc == 2 ? ((it >> 1) & 1u) : (it & 1u);
@@ -316,7 +332,9 @@ __global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p
             if constexpr (!kInt8) {
                 if (has_res) { ra = __ldg(res4); rb = __ldg(res4 + 1); }
             }
+            QL_TR(1);
             ql_mbar_wait(ql_smem_u32(&misc->acc_full[a]), aph);
+            QL_TR(0);
             ql_tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(a * p.c_out);
             for (int c0 = 0; c0 < p.c_out; c0 += 16) {
@@ -404,9 +422,17 @@ __global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p
             }
             ql_tc_fence_before();
             ql_mbar_arrive(ql_smem_u32(&misc->acc_empty[a]));
+            QL_TR(1);
         }
+        QL_TR_FLUSH(0, 8, tid == 0);
     } else if (warp < mma_warp) {
         // ============================ gather producers ============================
+        // Instruction diet (profiles/r02_conv_ablation.md: with loads, tcgen05.st, MMAs and the epilogue's traffic all switched
+        // off the launches still took 71 % of their time, and halving the producer warps cost only +23 %: the kernel was bound by
+        // instruction issue, ~160 SASS instructions per 4 KB piece).  Per gathered 16/32 bytes a thread now issues one LDS (row
+        // index), one IMAD.WIDE (address) and the load: a missing neighbour (index -1) reads the all-zero row the caller keeps in
+        // front of the feature rows (include/qlidar.h), so nothing is predicated or selected; units always hold whole pieces (the
+        // loader pads with all -1 slabs), so nothing depends on the sub-chunk count.
         const int q = warp & 3;                              // TMEM lane quarter
         const uint32_t team = (uint32_t)((warp - kProducerWarp0) >> 2);
         const uint32_t Tu = (uint32_t)T;
@@ -414,80 +440,69 @@ __global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p
         const int t0 = lane & 3, t1 = lane >> 2;             // quad form: lane t0 of the quad that serves rows t1 + 8*rr
         // byte offset of this thread's first row inside a [128] int32 slab
         const uint32_t row_off = (uint32_t)(q * 32 + (kQuad ? t1 : lane)) * 4u;
-        const int tb0 = kQuad ? t0 * (CH / 4) : 0;           // this thread's bytes inside a sub-chunk's row segment
         const uint32_t row_bytes = (uint32_t)p.row_bytes;
-        const uint8_t* const feats = p.feats;
-        const uint8_t* const zero = g_zero_line;
-        const bool wide = p.wide != 0;
         const uint32_t nseg = (uint32_t)p.nseg, inv_nseg = p.inv_nseg;
+        const bool wide = p.wide != 0;
+        // this thread's bytes inside a row segment; a thread whose bytes lie past the end of a short row (row_bytes < CH, one
+        // segment) always reads the zero row: multiplier 0, base = the zero row
+        const uint32_t tb0 = kQuad ? (uint32_t)t0 * (CH / 4) : 0u;
+        const bool dead0 = nseg == 1u && tb0 >= row_bytes;
+        const uint8_t* const feats = p.feats;
+        const uint8_t* const zrow = feats - row_bytes;
+        const uint8_t* base0 = dead0 ? zrow : feats + tb0;
+        asm volatile("mov.b64 %0, %0;" : "+l"(base0));     // one 64-bit register pair: the addend of the IMAD.WIDE of every gather
+        const int mul0 = dead0 ? 0 : (int)row_bytes;
 
         uint32_t slot = 0, sph = 0;                          // slot ring position / pass parity
         uint32_t gmod = 0;                                   // (pieces handed out so far) mod T: piece g goes to team g mod T
+        QL_TR_DECL(8);
         for (uint32_t u = 0;; ++u) {
             const uint32_t ub = u & (uint32_t)(kUbufs - 1);
             const uint32_t ubuf = ub_s0 + ub * ub_stride;
+            QL_TR(3);
             ql_mbar_wait(ubfull0 + ub * 8u, (u / kUbufs) & 1u);
+            QL_TR(0);
             const uint32_t n_sub = (uint32_t)ql_lds_s32(ubuf);
             if (n_sub == 0u) break;                          // end of the unit stream
             const uint32_t sub0 = (uint32_t)ql_lds_s32(ubuf + 8u);
-            const uint32_t ord0 = CH == 128 ? ((sub0 * inv_nseg) >> 16) : sub0;
+            const uint32_t ord0 = (CH == 128 && nseg > 1u) ? ((sub0 * inv_nseg) >> 16) : sub0;
             const uint32_t pieces = (n_sub + kGroup - 1) >> kGroupLog2;
             uint32_t pc = team >= gmod ? team - gmod : team + Tu - gmod;      // this team's first piece of the unit
-            // The rulebook indices of a piece (slab -> row index) are fetched one piece ahead, right after the previous piece's
-            // gathers have been issued, so the shared-memory round trip hides under them.
-            constexpr int kIdx = kQuad ? 4 * kGroup : kGroup;
-            int idx[kIdx];
-            uint32_t boff[kGroup];
-            auto fetch_idx = [&](uint32_t piece) {
-                const uint32_t c0 = piece << kGroupLog2;                      // first sub-chunk of the piece inside the unit
-#pragma unroll
-                for (int j = 0; j < kGroup; ++j) {
-                    const uint32_t cl = c0 + (uint32_t)j;
-                    const bool live = cl < n_sub;
-                    uint32_t slab = live ? cl : 0u;
-                    boff[j] = 0;
-                    if constexpr (CH == 128) {
-                        if (nseg > 1) {
-                            const uint32_t c = sub0 + slab;
-                            const uint32_t ord = (c * inv_nseg) >> 16;
-                            boff[j] = (c - ord * nseg) * 128u;
-                            slab = ord - ord0;
-                        }
-                    }
-                    const uint32_t a = ubuf + (uint32_t)kUbHdr + slab * (QL_TILE_M * 4u) + row_off;
-                    if constexpr (kQuad) {
-#pragma unroll
-                        for (int rr = 0; rr < 4; ++rr) {
-                            const int v = ql_lds_s32(a + (uint32_t)rr * 32u);
-                            idx[4 * j + rr] = live ? v : -1;
-                        }
-                    } else {
-                        const int v = ql_lds_s32(a);
-                        idx[j] = live ? v : -1;
-                    }
-                }
-            };
+            const uint32_t slabs = ubuf + (uint32_t)kUbHdr + row_off;
             bool waited = false;
-            if (pc < pieces) fetch_idx(pc);
             for (; pc < pieces; pc += Tu) {
                 uint32_t v[32];
                 if constexpr (kQuad) {
 #pragma unroll
                     for (int j = 0; j < kGroup; ++j) {
-                        const uint32_t tb = boff[j] + (uint32_t)tb0;
+                        uint32_t slab = (pc << kGroupLog2) + (uint32_t)j;        // sub-chunk inside the unit == slab for one-segment rows
+                        const uint8_t* base = base0;
+                        int mul = mul0;
+                        uint32_t tb = tb0;
+                        if constexpr (CH == 128) {
+                            if (nseg > 1u) {                                     // rows longer than 128 bytes: (offset, segment) -> slab, byte offset
+                                const uint32_t c = sub0 + slab;
+                                const uint32_t ord = (c * inv_nseg) >> 16;
+                                tb = (c - ord * nseg) * 128u + tb0;
+                                slab = ord - ord0;
+                                const bool dead = tb >= row_bytes;
+                                base = dead ? zrow : feats + tb;
+                                mul = dead ? 0 : (int)row_bytes;
+                            }
+                        }
+                        const uint32_t a = slabs + slab * (QL_TILE_M * 4u);
 #pragma unroll
                         for (int rr = 0; rr < 4; ++rr) {
                             const int h = rr >> 1, v1 = rr & 1;
-                            const int id = idx[4 * j + rr];
-                            const bool ok = id >= 0 && tb < row_bytes && !QL_ABL(1);
-                            const uint8_t* src = ok ? feats + ((uint64_t)(uint32_t)id * row_bytes + tb) : zero;
+                            const int id = QL_ABL(1) ? -1 : ql_lds_s32(a + (uint32_t)rr * 32u);
+                            const uint8_t* src = row_ptr(base, id, mul);
                             uint32_t x[8];
                             if constexpr (CH == 128) {
                                 if (wide) {
                                     ldg32(src, x);
                                 } else {
                                     ldg16(src, x);
-                                    ldg16((ok && tb + 16u < row_bytes) ? src + 16 : zero, x + 4);
+                                    ldg16(tb + 16u < row_bytes ? src + 16 : zrow, x + 4);   // rows of an odd number of 16-byte pieces
                                 }
                             } else {
                                 ldg16(src, x);
@@ -500,26 +515,34 @@ __global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p
                         }
                     }
                 } else {
+                    const uint32_t a = slabs + (pc << kGroupLog2) * (QL_TILE_M * 4u);
 #pragma unroll
                     for (int j = 0; j < kGroup; ++j) {
-                        const int id = idx[j];                                       // CH = 32: one sub-chunk per kernel offset
-                        const bool ok = id >= 0 && !QL_ABL(1);
-                        const uint8_t* src = ok ? feats + (uint64_t)(uint32_t)id * row_bytes : zero;
+                        const int id = QL_ABL(1) ? -1 : ql_lds_s32(a + (uint32_t)j * (QL_TILE_M * 4u));   // CH = 32: one sub-chunk per kernel offset
+                        const uint8_t* src = row_ptr(feats, id, (int)row_bytes);
                         if (wide) {
                             ldg32(src, v + j * 8);
-                        } else {
+                        } else if (row_bytes > 16u) {
                             ldg16(src, v + j * 8);
-                            ldg16((ok && 16u < row_bytes) ? src + 16 : zero, v + j * 8 + 4);
+                            ldg16(src + 16, v + j * 8 + 4);
+                        } else {
+                            ldg16(src, v + j * 8);                                // 16-byte rows: the upper half of the k-step is padding
+                            v[j * 8 + 4] = 0u; v[j * 8 + 5] = 0u; v[j * 8 + 6] = 0u; v[j * 8 + 7] = 0u;
                         }
                     }
                 }
                 const uint32_t a_piece = a_lane_base + slot * S + pc * 32u;
-                if (pc + Tu < pieces) fetch_idx(pc + Tu);                            // next piece's indices, under this piece's gathers
                 if (!waited) {
+                    QL_TR(1);
                     ql_mbar_wait(empty0 + slot * 8u, sph ^ 1u);                      // the MMAs that read this slot have completed
+                    QL_TR(2);
                     ql_tc_fence_after();
                     waited = true;
                 }
+#ifdef QL_SPCONV_ABLATE
+                asm volatile("" ::"r"(v[0]), "r"(v[31]));                           // (trace) the loads have landed before the clock is read
+                QL_TR(1);
+#endif
                 if (!QL_ABL(2)) {
                     if constexpr (kQuad) {
 #pragma unroll
@@ -533,7 +556,9 @@ __global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p
                 }
             }
             // a warp without a piece in this unit still arrives, and must do so inside the slot's current phase
+            QL_TR(3);
             if (!waited) ql_mbar_wait(empty0 + slot * 8u, sph ^ 1u);
+            QL_TR(2);
             tmem_st_wait();
             ql_tc_fence_before();
             __syncwarp();
@@ -545,6 +570,7 @@ __global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p
             gmod = T == 4 ? (gmod & 3u) : gmod % Tu;
             if (++slot == n_slots) { slot = 0; sph ^= 1u; }
         }
+        QL_TR_FLUSH(1, 8, warp == kProducerWarp0 && lane == 0);
     } else if (warp == mma_warp) {
         // =============================== MMA issuer ===============================
         // One elected lane runs the whole loop (nothing in it is warp-collective): per unit one descriptor wait, one slot wait,
@@ -558,10 +584,13 @@ __global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p
             const uint32_t n_acc = (uint32_t)p.n_acc, c_out = (uint32_t)p.c_out, U = (uint32_t)p.unit_subs;
             uint32_t slot = 0, sph = 0, it = 0, accumulate = 0u, d_tmem = tmem_base, acc_bar = 0;
             if (kResident && (int64_t)blockIdx.x < n_tiles) ql_mbar_wait(ql_smem_u32(&misc->w_full), 0);
+            QL_TR_DECL(8);
             for (uint32_t u = 0;; ++u) {
                 const uint32_t ub = u & (uint32_t)(kUbufs - 1);
                 const uint32_t ubuf = ub_s0 + ub * ub_stride;
+                QL_TR(4);
                 ql_mbar_wait(ubfull0 + ub * 8u, (u / kUbufs) & 1u);
+                QL_TR(0);
                 uint32_t n_sub, flags;
                 asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(n_sub), "=r"(flags) : "r"(ubuf));
                 if (n_sub == 0u) break;
@@ -578,12 +607,16 @@ __global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p
                 if (flags & kFlagFirst) {
                     const uint32_t a = n_acc == 2 ? (it & 1u) : 0u;
                     const uint32_t aph = n_acc == 2 ? ((it >> 1) & 1u) : (it & 1u);
+                    QL_TR(4);
                     ql_mbar_wait(ql_smem_u32(&misc->acc_empty[a]), aph ^ 1u);
+                    QL_TR(1);
                     d_tmem = tmem_base + a * c_out;
                     acc_bar = ql_smem_u32(&misc->acc_full[a]);
                     accumulate = 0u;
                 }
+                QL_TR(4);
                 ql_mbar_wait(full0 + slot * 8u, sph);
+                QL_TR(2);
                 ql_tc_fence_after();
                 const uint32_t a_unit = a_base + slot * S;
                 for (uint32_t j0 = 0; j0 < n_sub; j0 += 4) {
@@ -603,11 +636,13 @@ __global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p
                         }
                     }
                 }
+                QL_TR(3);
                 ql_tc_commit(empty0 + slot * 8u);
                 if (flags & kFlagLast) { ql_tc_commit(acc_bar); ++it; }
                 ql_mbar_arrive(ubempty0 + ub * 8u);
                 if (++slot == n_slots) { slot = 0; sph ^= 1u; }
             }
+            QL_TR_FLUSH(2, 8, true);
         }
         __syncwarp();
     } else if (warp == loader_warp) {
@@ -635,6 +670,7 @@ __global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p
         for (int i = 0; i < kMaskWords; ++i) pf_mask[i] = 0u;
         if (next_tile < n_tiles) load_tile_mask_raw(p, next_tile, pf_mask);
         uint32_t ur = 0;                                // units described so far
+        QL_TR_DECL(8);
         // returns true when it pushed the end-of-stream descriptor
         auto push_desc = [&]() -> bool {
             const uint32_t ub = ur & (uint32_t)(kUbufs - 1);
@@ -642,7 +678,9 @@ __global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p
             const uint32_t bar = ubfull0 + ub * 8u;
             if (s0 >= n_sub_tile) {
                 if (next_tile >= n_tiles) {
+                    QL_TR(2);
                     ql_mbar_wait(ubempty0 + ub * 8u, ((ur / kUbufs) & 1u) ^ 1u);
+                    QL_TR(0);
                     if (lane == 0) { sts_u32(ubuf, 0u); sts_u32(ubuf + 4u, 0u); ql_mbar_arrive(bar); }
                     __syncwarp();
                     ++ur;
@@ -675,7 +713,9 @@ __global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p
             const uint32_t ord_first = CH == 128 ? ((s0 * inv_nseg) >> 16) : s0;
             const uint32_t ord_last = CH == 128 ? (((s0 + n_sub - 1u) * inv_nseg) >> 16) : s0 + n_sub - 1u;
             const uint32_t slab_bytes = (ord_last - ord_first + 1u) * (QL_TILE_M * 4u);
+            QL_TR(2);
             ql_mbar_wait(ubempty0 + ub * 8u, ((ur / kUbufs) & 1u) ^ 1u);
+            QL_TR(0);
             if ((uint32_t)lane < n_sub) {
                 const uint32_t c = s0 + (uint32_t)lane;
                 uint32_t ord = c, seg = 0;
@@ -689,8 +729,16 @@ __global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p
                 sts_u32(ubuf + 4u, (s0 == 0u ? kFlagFirst : 0u) | (s0 + n_sub >= n_sub_tile ? kFlagLast : 0u));
                 sts_u32(ubuf + 8u, s0);
             }
+            // whole pieces for the producers: the sub-chunks that pad the unit's last piece get all -1 slabs (CH < 128 only: one
+            // segment per offset, slab == sub-chunk)
+            if constexpr (kGroup > 1) {
+                const uint32_t padded = (n_sub + (uint32_t)kGroup - 1u) & ~(uint32_t)(kGroup - 1);
+                for (uint32_t sl = n_sub; sl < padded; ++sl)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ubuf + (uint32_t)kUbHdr + sl * (QL_TILE_M * 4u) + 16u * (uint32_t)lane), "r"(-1) : "memory");
+            }
             if (synth || QL_ABL(16)) {
-                asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ubuf + (uint32_t)kUbHdr + 16u * (uint32_t)lane), "r"(-1) : "memory");
+                for (uint32_t sl = 0; sl < (QL_ABL(16) ? ord_last - ord_first + 1u : 1u); ++sl)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ubuf + (uint32_t)kUbHdr + sl * (QL_TILE_M * 4u) + 16u * (uint32_t)lane), "r"(-1) : "memory");
                 __syncwarp();
                 if (lane == 0) ql_mbar_arrive(bar);
             } else {
@@ -718,7 +766,9 @@ __global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p
                 const uint32_t n_sub = (uint32_t)ql_lds_s32(ubuf);
                 if (n_sub == 0u) break;
                 const uint32_t fbar = full0 + slot * 8u;
+                QL_TR(2);
                 ql_mbar_wait(empty0 + slot * 8u, sph ^ 1u);
+                QL_TR(1);
                 if (lane == 0) ql_mbar_arrive_expect_tx(fbar, n_sub * b_sub_bytes);
                 __syncwarp();
                 if ((uint32_t)lane < n_sub) {
@@ -730,6 +780,8 @@ __global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p
                 if (++slot == n_slots) { slot = 0; sph ^= 1u; }
             }
         }
+        QL_TR(2);
+        QL_TR_FLUSH(3, 8, lane == 0);
     }
 
     ql_tc_fence_before();
@@ -743,6 +795,10 @@ __global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p
     }
     if (warp == mma_warp) ql_tmem_dealloc(tmem_base, kTmemCols);
 }
+
+#ifdef QL_SPCONV_ABLATE
+int g_launch_id = 0;
+#endif
 
 inline int elem_size(int dtype) { return dtype == QL_S8 ? 1 : (dtype == QL_F16 ? 2 : 0); }
 
@@ -818,7 +874,7 @@ size_t plan_conv(ConvParams& p, const ChunkGeom& g, int c_out, int kvol) {
     if (U < group) return 0;
     p.w_bytes = kvol * g.nseg * b_sub;
     auto ub_stride_of = [&](int u) {
-        const int offs = g.nseg > 1 ? (u + g.nseg - 2) / g.nseg + 1 : u;       // kernel offsets a unit of u sub-chunks can span
+        const int offs = g.nseg > 1 ? (u + g.nseg - 2) / g.nseg + 1 : u;       // kernel offsets a unit of u sub-chunks can span (u is whole pieces)
         return (kUbHdr + offs * QL_TILE_M * 4 + 127) & ~127;
     };
     const int fixed = 1024 + 128 + ((misc_bytes + 127) & ~127);
@@ -925,6 +981,9 @@ extern "C" int ql_spconv_mma_rows(const void* feats, int32_t in_dtype, const int
 
     const size_t smem_bytes = plan_conv(p, g, c_out, kvol);
     if (smem_bytes == 0) return QL_ERR_UNSUPPORTED;
+#ifdef QL_SPCONV_ABLATE
+    p.trace_id = g_launch_id++;
+#endif
 
     int64_t tiles = (n_out_cap + QL_TILE_M - 1) / QL_TILE_M;
     int grid = (int)(tiles < ql_num_sms() ? tiles : ql_num_sms());
@@ -957,5 +1016,13 @@ extern "C" int32_t ql_spconv_weights_streamed(int32_t c_in, int32_t c_out, int32
 #ifdef QL_SPCONV_ABLATE
 extern "C" int ql_debug_set_ablate(int32_t mask) {
     return cudaMemcpyToSymbol(g_ablate, &mask, sizeof(int)) == cudaSuccess ? QL_OK : QL_ERR_CUDA;
+}
+// copies the role trace [64][32] to the host and clears it
+extern "C" int ql_debug_read_trace(unsigned long long* out_host) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return QL_ERR_CUDA;
+    if (cudaMemcpyFromSymbol(out_host, g_trace, sizeof(unsigned long long) * 64 * 32) != cudaSuccess) return QL_ERR_CUDA;
+    static unsigned long long zeros[64 * 32];
+    g_launch_id = 0;
+    return cudaMemcpyToSymbol(g_trace, zeros, sizeof(zeros)) == cudaSuccess ? QL_OK : QL_ERR_CUDA;
 }
 #endif

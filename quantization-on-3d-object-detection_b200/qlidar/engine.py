@@ -22,6 +22,7 @@ import torch.nn as nn
 from . import ops
 from ._lib import QlidarError
 from .quant import QConvNd
+from .tensor_quant import quant_scale
 from .sparse import SparseConvolution, SparseSequential, SparseConvTensor, _round_up
 from .backbones import SparseBasicBlock
 
@@ -69,8 +70,12 @@ class Stage:
 
 
 def _bn_fold(bn: nn.BatchNorm1d):
-    a = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)      # eps read from the module
-    return a, bn.bias.detach().float() - a * bn.running_mean.detach().float()
+    """Eval-mode BatchNorm1d as y = a*x + b, on the HOST in fp32 (the oracle's mirror reproduces these bits: every scale that feeds
+    an int8 quantiser is computed with correctly rounded host arithmetic, never with a device reciprocal-multiply)."""
+    g, be = bn.weight.detach().float().cpu(), bn.bias.detach().float().cpu()
+    mu, var = bn.running_mean.detach().float().cpu(), bn.running_var.detach().float().cpu()
+    a = g / torch.sqrt(var + bn.eps)                                                          # eps read from the module
+    return a, be - a * mu
 
 
 def _unwrap(m):
@@ -135,7 +140,7 @@ class BackboneEngine:
                   pad=tuple(conv.padding), subm=conv.subm, relu=relu, residual=residual, block_input=block_input)
         if qw is not None:
             codes, amax_w, bound = qw.weight_codes()
-            w_scale = (amax_w / bound).cpu()
+            w_scale = amax_w.float().cpu() / bound                     # host: a true division
             L.act_bits = qw.act_quant.num_bits
             L.act_amax = None if qw.act_quant.amax is None else qw.act_quant.amax.detach().float().reshape(-1).cpu()
         else:
@@ -277,16 +282,16 @@ class BackboneEngine:
                     nb = int(ops.lib().ql_rulebook_group_workspace_bytes(so.cap))
                     if self.group_ws is None or self.group_ws.numel() < nb:
                         self.group_ws = z(nb, dt=torch.uint8)
-            L.out = z(so.cap, L.cout)
+            L.out = ops.zero_led_rows(so.cap, L.cout, torch.float16, dev)          # gathered by the next conv: zero-row contract
             L.out_absmax = self.absmax_pool[off:off + L.cout]
             off += L.cout
             L.in_absmax = prev_absmax
             prev_absmax = L.out_absmax
             if L.kind == "i8":
-                L.q_buf = z(self.stages[L.stage_in].cap, L.cin, dt=torch.int8)
+                L.q_buf = ops.zero_led_rows(self.stages[L.stage_in].cap, L.cin, torch.int8, dev)
                 L.act_scale = z(1, dt=torch.float32)
             elif L.kind in ("cw", "row"):
-                L.q_buf = z(self.stages[L.stage_in].cap, L.cin)
+                L.q_buf = ops.zero_led_rows(self.stages[L.stage_in].cap, L.cin, torch.float16, dev)
             if L.act_amax is not None:
                 L.act_amax = (L.act_amax.expand(L.cin) if L.act_amax.numel() == 1 else L.act_amax).contiguous().to(dev)
         # static calibration (collect_stats / compute_amax, quant/quantize.py:175-207): a per-tensor-quantised layer whose input
@@ -296,12 +301,11 @@ class BackboneEngine:
             L.fused_q = False
             if L.kind == "i8" and L.act_amax is not None:
                 bound = float(2 ** (L.act_bits - 1) - 1)
-                amax = L.act_amax.float()
-                L.act_scale.copy_((amax.max() / bound).reshape(1))
+                amax = L.act_amax.float().cpu()
+                L.act_scale.copy_((amax.max() / bound).reshape(1))                 # host: a true division
                 prev = self.layers[i - 1] if i > 0 else None
                 if prev is not None and prev.kind in ("f16", "i8", "cw", "row") and L.act_bits == 8:
-                    tiny = amax <= (1.0 / (1 << 24))
-                    prev.out_qscale = torch.where(tiny, torch.zeros_like(amax), bound / torch.where(tiny, torch.ones_like(amax), amax)).contiguous()
+                    prev.out_qscale = quant_scale(amax, bound).contiguous().to(dev)
                     prev.out_q = L.q_buf
                     L.fused_q = True
         last = self.stages[-1]

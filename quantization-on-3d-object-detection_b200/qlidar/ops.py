@@ -321,6 +321,24 @@ def bev_merge2d(feats: torch.Tensor, coords: torch.Tensor, n_dev: Optional[torch
     return out_feats, out_coords, n_out
 
 
+def zero_led_rows(n: int, c: int, dtype=torch.float16, device="cuda") -> torch.Tensor:
+    """[n, c] zero-initialised rows with one extra all-zero row IN FRONT of row 0 (same allocation): the layout the conv kernel
+    gathers from -- rulebook index -1 reads that row (include/qlidar.h, zero-row contract).  The returned view is tagged;
+    spconv_mma takes tagged tensors as they are and copies anything else into such a buffer."""
+    buf = torch.zeros((int(n) + 1, int(c)), dtype=dtype, device=device)
+    v = buf[1:]
+    v._ql_zero_led = buf                      # keeps the allocation (and the zero row) alive with the view
+    return v
+
+
+def _zero_led(feats: torch.Tensor) -> torch.Tensor:
+    if getattr(feats, "_ql_zero_led", None) is not None and feats.is_contiguous():
+        return feats
+    v = zero_led_rows(feats.shape[0], feats.shape[1], feats.dtype, feats.device)
+    v.copy_(feats)
+    return v
+
+
 def pack_weights(w: torch.Tensor) -> torch.Tensor:
     """w: CPU tensor (c_out, K, c_in) int8 codes or float16 -> CPU uint8 tensor with the shared-memory image."""
     if w.is_cuda:
@@ -360,6 +378,7 @@ def spconv_mma(feats: torch.Tensor, nbr: torch.Tensor, n_out_cap: int, n_out_dev
         raise QlidarError("residual must be float16")
     c_in = feats.shape[1]
     K = nbr.shape[1]
+    feats = _zero_led(feats)                      # zero-row contract of ql_spconv_mma (a copy unless allocated by zero_led_rows)
     if out is None:
         out = torch.empty((n_out_cap, c_out), dtype=out_dtype, device=feats.device)
     raw = out.dtype == torch.int32

@@ -19,7 +19,7 @@ import torch.nn as nn
 from . import ops
 from .sparse import (SparseConvolution, SparseConvTensor, SparseModule, SubMConv3d, SparseConv3d, SubMConv2d, SparseConv2d,
                      _make_output, _round_up)
-from .tensor_quant import QuantDescriptor, TensorQuantizer, reduce_amax
+from .tensor_quant import QuantDescriptor, TensorQuantizer, quant_scale, reduce_amax
 
 
 class QConvNd(SparseModule):
@@ -50,9 +50,7 @@ class QConvNd(SparseModule):
         wm = wt.reshape(oc, -1, ic).float()
         amax = self.w_quant.amax.view(-1).to(wm.device) if self.w_quant.amax is not None else wm.abs().amax(dim=(1, 2))
         bound = float(2 ** (self.w_quant.num_bits - 1) - 1)
-        tiny = amax <= (1.0 / (1 << 24))
-        scale = torch.where(tiny, torch.zeros_like(amax), bound / torch.where(tiny, torch.ones_like(amax), amax))
-        codes = torch.round(wm * scale.view(-1, 1, 1)).clamp_(-bound, bound)
+        codes = torch.round(wm * quant_scale(amax, bound).view(-1, 1, 1)).clamp_(-bound, bound)
         return codes, amax, bound
 
     def _prepared(self, dev, kind: str):
@@ -69,7 +67,7 @@ class QConvNd(SparseModule):
         w[:oc, :, :ic] = codes.to(w.dtype).cpu()
         packed = ops.pack_weights(w).to(dev)
         w_scale = torch.zeros(oc_p, dtype=torch.float32, device=dev)
-        w_scale[:oc] = (amax / bound).to(dev)                           # de-quantisation scale amax_w[oc] / bound
+        w_scale[:oc] = (amax.float().cpu() / bound).to(dev)             # de-quantisation scale amax_w[oc] / bound (a true division: on the host)
         shift = torch.zeros(oc_p, dtype=torch.float32, device=dev)
         if self.module.bias is not None:
             shift[:oc] = self.module.bias.detach().float().to(dev)
@@ -214,9 +212,7 @@ class SQConv3d(SparseModule):
         wm = wt.reshape(oc, -1, ic)
         bound = float(2 ** (self.w_quant.num_bits - 1) - 1)
         amax = wm.abs().amax(dim=(1, 2))
-        tiny = amax <= (1.0 / (1 << 24))
-        scale = torch.where(tiny, torch.zeros_like(amax), bound / torch.where(tiny, torch.ones_like(amax), amax))
-        codes = torch.round(wm * scale.view(-1, 1, 1)).clamp_(-bound, bound)
+        codes = torch.round(wm * quant_scale(amax, bound).view(-1, 1, 1)).clamp_(-bound, bound)
         ic_p, oc_p = _round_up(ic, 16), _round_up(oc, 16)
         w8 = torch.zeros((oc_p, wm.shape[1], ic_p), dtype=torch.int8)
         w8[:oc, :, :ic] = codes.to(torch.int8)

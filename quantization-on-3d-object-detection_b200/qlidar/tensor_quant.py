@@ -56,11 +56,19 @@ def reduce_amax(x: torch.Tensor, axis) -> torch.Tensor:
     return a.amax(dim=red, keepdim=True) if red else a
 
 
-def fake_quant(x: torch.Tensor, amax: torch.Tensor, num_bits: int) -> torch.Tensor:
-    bound = float(2 ** (num_bits - 1) - 1)
+def quant_scale(amax: torch.Tensor, bound: float) -> torch.Tensor:
+    """scale = bound / amax (0 where amax <= 2^-24) as ONE correctly rounded fp32 division per element, like [EXT]
+    pytorch_quantization (`max_bound / amax`, both tensors) and like the device (__fdiv_rn).  Python's `bound / tensor` is
+    tensor.reciprocal() * bound -- two roundings, one ulp off in a quarter of the cases -- and CUDA's `tensor / scalar`
+    multiplies by the reciprocal; an ulp in a scale flips int8 codes that sit on a rounding boundary."""
     amax = amax.to(torch.float32)
     tiny = amax <= (1.0 / (1 << 24))
-    scale = torch.where(tiny, torch.zeros_like(amax), bound / torch.where(tiny, torch.ones_like(amax), amax))
+    return torch.where(tiny, torch.zeros_like(amax), torch.full_like(amax, float(bound)) / torch.where(tiny, torch.ones_like(amax), amax))
+
+
+def fake_quant(x: torch.Tensor, amax: torch.Tensor, num_bits: int) -> torch.Tensor:
+    bound = float(2 ** (num_bits - 1) - 1)
+    scale = quant_scale(amax, bound)
     xf = x.to(torch.float32)
     q = torch.round(xf * scale).clamp_(-bound, bound)
     out = torch.where(scale == 0, torch.zeros_like(q), q / torch.where(scale == 0, torch.ones_like(scale), scale))

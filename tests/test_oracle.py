@@ -170,3 +170,48 @@ def test_im2col_conv_equals_per_offset_conv():
     w = torch.randn(32, 3, 3, 3, 16, dtype=torch.float64)
     b = torch.randn(32, dtype=torch.float64)
     assert (O.sparse_conv(x, nbr, w, b) - O.sparse_conv_im2col(x, nbr, w, b, chunk=100)).abs().max().item() < 1e-10
+
+
+def test_mirror_layers_agree_with_reference_math_teacher_forced():
+    """The mirror is not a second opinion about the network: fed layer by layer with ITS OWN inputs, the reference's fake-quant
+    math (quant/quant.py:36-58 restated, qconv_reference_math) + BatchNorm (+residual) + ReLU reproduces each mirror layer to 1e-3
+    of the layer's max (fp16 storage of the output is 2^-11 relative; the rest is fp32 summation order)."""
+    c = O.CONFIGS["kitti"]
+    pts = O.synth_batch("kitti", 1, n_az=260)
+    f_np, coords, _ = O.voxelize_mean_batch(pts, c["pc_range"], c["voxel_size"], c["max_pts"], c["max_voxels"])
+    grid = O.grid_size_xyz(c["pc_range"], c["voxel_size"])
+    order = np.argsort(O._lin(coords, O.sparse_shape_zyx(grid)), kind="stable")
+    feats, coords = torch.from_numpy(f_np[order]).contiguous(), np.ascontiguousarray(coords[order])
+    prog = O.backbone_specs("VoxelResBackBone8x", 4)
+    P = O.init_params(prog)
+    rec, out, taps = O.mirror_backbone_w8a8_pt(prog, P, feats, coords, O.sparse_shape_zyx(grid), 1)
+    x = O.SpT(None, coords.astype(np.int32), O.sparse_shape_zyx(grid), 1)
+    prev_h = None
+    checked = 0
+    for op in prog:
+        if op["op"] == "tap":
+            continue
+        specs = [(op["conv"], op["bn"], None)] if op["op"] == "conv_bn_relu" else [(op["conv1"], op["bn1"], None), (op["conv2"], op["bn2"], "res")]
+        block_in = prev_h
+        for spec, bnname, res in specs:
+            r = rec[spec.name]
+            if spec.name != "conv_input.0":
+                xin = O.SpT(torch.from_numpy(prev_h.astype(np.float32)), x.coords, x.spatial_shape, 1, x.rulebooks)
+                # same amax as the mirror (the producing layer's fp32 maximum; the fp16-stored maximum differs by <= 2^-11 relative,
+                # enough to move codes that sit on a rounding boundary by one step = 0.8 % of amax)
+                y = O.run_conv(xin, spec, P, O.QuantCfg(mode="ref", w_bits=8, act_bits=8, cw=False,
+                                                         act_amax={spec.name: torch.tensor(float(r["amax_in"]))}))
+                y = O.bn_relu(y, bnname, P, 1e-3, True, None if res is None else torch.from_numpy(block_in.astype(np.float32)))
+                ref = y.features.numpy()
+                err = np.abs(r["out"].astype(np.float32) - ref).max() / max(np.abs(ref).max(), 1e-12)
+                assert err <= 1e-3, (spec.name, err)
+                checked += 1
+                x = O.SpT(None, y.coords, y.spatial_shape, 1, y.rulebooks)
+            else:
+                xin = O.SpT(feats, x.coords, x.spatial_shape, 1, x.rulebooks)
+                y = O.bn_relu(O.run_conv(xin, spec, P, O.QuantCfg()), bnname, P, 1e-3)
+                err = np.abs(r["out"].astype(np.float32) - y.features.numpy()).max() / np.abs(y.features.numpy()).max()
+                assert err <= 1e-3, err
+                x = O.SpT(None, y.coords, y.spatial_shape, 1, y.rulebooks)
+            prev_h = r["out"]
+    assert checked == 20

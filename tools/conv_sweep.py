@@ -12,6 +12,29 @@ import torch
 import bench
 
 KEYS = ("UNIT_SUBS", "SLOTS", "TEAMS", "STREAM", "MODE")
+ROLES = {0: ("epilogue", ["wait_acc", "work"]), 1: ("producer", ["wait_desc", "gather", "wait_slot", "st+arrive"]),
+         2: ("mma", ["wait_desc", "wait_acc", "wait_unit", "issue", "commit"]), 3: ("loader", ["wait_desc_free", "wait_slot", "work"])}
+
+
+def print_trace(eng):
+    """Role trace of the test-time build: share of each role's lifetime (lead thread, summed over the CTAs) per phase."""
+    import ctypes
+    from qlidar import _lib
+    lib = _lib.lib()
+    buf = (ctypes.c_ulonglong * (64 * 32))()
+    lib.ql_debug_read_trace(buf)                      # clear
+    eng._run_from_points()
+    torch.cuda.synchronize()
+    lib.ql_debug_read_trace(buf)
+    convs = [L for L in eng.layers if L.kind != "stem"]
+    for i, L in enumerate(convs):
+        row = [buf[i * 32 + j] for j in range(32)]
+        parts = []
+        for r, (name, phases) in ROLES.items():
+            tot = row[r * 8 + 7] or 1
+            parts.append(name + " " + "/".join(f"{ph}={100.0 * row[r * 8 + k] / tot:.0f}%" for k, ph in enumerate(phases)))
+        print(f"  {L.name:14s} " + " | ".join(parts), flush=True)
+
 
 
 def main():
@@ -26,11 +49,13 @@ def main():
     for cfg in (sys.argv[1:] or [""]):
         for k in KEYS:
             os.environ.pop("QL_SPCONV_" + k, None)
-        abl = 0
+        abl, trace = 0, False
         for kv in filter(None, cfg.split(",")):
             k, v = kv.split("=")
             if k == "ABLATE":                     # needs QLIDAR_LIB=.../libqlidar_b200_ablate.so (build.py --ablate)
                 abl = int(v)
+            elif k == "TRACE":
+                trace = bool(int(v))
             else:
                 os.environ["QL_SPCONV_" + k] = v
         from qlidar import _lib
@@ -42,6 +67,8 @@ def main():
         conv = {k.split(":", 1)[1]: v * 1e3 for k, v in t.items() if k.startswith("conv:")}
         tot = sum(conv.values())
         print(f"[{cfg or 'default'}] conv total {tot:.0f} us | " + " ".join(f"{k.replace('conv', 'c')}={v:.0f}" for k, v in conv.items()), flush=True)
+        if trace:
+            print_trace(eng)
 
 
 if __name__ == "__main__":
