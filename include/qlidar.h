@@ -238,6 +238,16 @@ int ql_quantize_rows(const void* x, int32_t in_dtype, int64_t n_cap, const int32
                      const float* absmax, const float* smooth, int32_t bits, int32_t mode,
                      void* out, float* act_scale_out, ql_stream_t stream);
 
+/* ---- SmoothQuant weight preparation on the device (quant/smoothquant.py:69-82 formula, per input channel, as intended for the
+ *      sparse convs by quant/quant_conv3d.py:141-236): smooth[ic] = act_absmax[ic]^alpha / w_ic_absmax[ic]^(1-alpha) (zeros -> 1),
+ *      w'[oc,k,ic] = w * smooth[ic], per-output-channel int8 codes of w' written into the packed image ql_spconv_mma reads
+ *      (same bytes as ql_pack_weights_host of those codes) and scale_out[oc] = amax(w'[oc]) / 127 * (bn_scale ? bn_scale[oc] : 1).
+ *      w: [c_out][kvol][c_in] fp32 (device); w_ic_absmax: [c_in] max over (oc, k) of |w|; act_absmax: [c_in] (dynamic: the
+ *      producing layer's epilogue; static: calibrated).  The activations are then quantised with ql_quantize_rows(smooth). */
+int ql_sq_prepare_weights(const float* w, const float* w_ic_absmax, const float* act_absmax, float alpha,
+                          int32_t c_in, int32_t c_out, int32_t kvol, const float* bn_scale,
+                          float* smooth_out, int8_t* packed_out, float* scale_out, ql_stream_t stream);
+
 /* ---- BEV hand-off (replaces HeightCompression.forward -> [EXT] SparseConvTensor.dense(),
  *      pcdet/models/backbones_2d/map_to_bev/height_compression.py:20-24): out[b, c*D+d, y, x], zero filled. */
 size_t ql_bev_densify_workspace_bytes(int32_t B, int32_t D, int32_t H, int32_t W);
@@ -259,6 +269,16 @@ size_t ql_bev_merge2d_workspace_bytes(int32_t B, int32_t H, int32_t W, int64_t n
 int ql_bev_merge2d(const void* feats, int32_t in_dtype, int32_t c, const int32_t* coords, int64_t n_cap, const int32_t* n_dev,
                    int32_t B, int32_t H, int32_t W, void* out_feats, int32_t out_dtype, int32_t* out_coords,
                    int64_t n_out_cap, int32_t* n_out_dev, void* workspace, size_t workspace_bytes, ql_stream_t stream);
+
+/* the same for SEVERAL site lists merged in one pass -- VoxelResBackBone8xVoxelNeXt.forward's concat of stages 4, 5, 6
+ * (spconv_backbone_voxelnext.py:194-199): segment i contributes rows feats[i] / coords[i] (counts n_dev[i], capacity n_cap[i]) with
+ * y and x multiplied by coord_scale[i] (1, 2, 4: `indices[:, 1:] *= 2` / `*= 4`; z is dropped, so its scaling does not matter).
+ * The pointer arrays are HOST arrays of device pointers.  out_coord_cols = 3: [b, y, x] (torch.unique order); 4: [b, 0, y, x],
+ * the form the rulebook entry points take for the 2-D tail. */
+int ql_bev_merge2d_multi(int32_t n_seg, const void* const* feats, int32_t in_dtype, int32_t c, const int32_t* const* coords,
+                         const int64_t* n_cap, const int32_t* const* n_dev, const int32_t* coord_scale,
+                         int32_t B, int32_t H, int32_t W, void* out_feats, int32_t out_dtype, int32_t* out_coords, int32_t out_coord_cols,
+                         int64_t n_out_cap, int32_t* n_out_dev, void* workspace, size_t workspace_bytes, ql_stream_t stream);
 
 #ifdef __cplusplus
 }

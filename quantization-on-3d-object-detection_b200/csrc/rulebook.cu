@@ -721,11 +721,12 @@ Merge2dWs merge2d_ws_layout(int B, int H, int W, int64_t n_out_cap, int c, bool 
 }
 
 __global__ void __launch_bounds__(256) k_m2d_mark(const int4* __restrict__ coords, int64_t n_cap, const int* __restrict__ n_dev, int B,
-                                                  int H, int W, uint32_t* __restrict__ bitmap) {
+                                                  int H, int W, int cscale, uint32_t* __restrict__ bitmap) {
     const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int4 c = coords[i];                                             // b, z, y, x
+    int4 c = coords[i];                                                   // b, z, y, x
+    c.z *= cscale; c.w *= cscale;                                         // a coarser stage's site on the target grid (voxelnext :194-195)
     if (c.x < 0 || c.x >= B || c.z < 0 || c.z >= H || c.w < 0 || c.w >= W) return;
     const uint32_t key = (uint32_t)((c.x * H + c.z) * W + c.w);
     const uint32_t bit = 1u << (key & 31u);
@@ -735,7 +736,7 @@ __global__ void __launch_bounds__(256) k_m2d_mark(const int4* __restrict__ coord
 __global__ void __launch_bounds__(QL_SCAN_THREADS) k_m2d_emit(const uint32_t* __restrict__ bitmap, int64_t n_words,
                                                              const int* __restrict__ block_offsets, int H, int W,
                                                              uint32_t* __restrict__ word_prefix, int* __restrict__ out_coords,
-                                                             int64_t n_out_cap) {
+                                                             int64_t n_out_cap, int out_cols) {
     const int64_t w = (int64_t)blockIdx.x * kWordsPerBlock + threadIdx.x;
     uint32_t bits = w < n_words ? bitmap[w] : 0u;
     int total;
@@ -748,9 +749,13 @@ __global__ void __launch_bounds__(QL_SCAN_THREADS) k_m2d_emit(const uint32_t* __
             uint32_t key = (uint32_t)w * 32u + pos;
             const int x = (int)(key % (uint32_t)W); key /= (uint32_t)W;
             const int y = (int)(key % (uint32_t)H); key /= (uint32_t)H;
-            out_coords[3 * (int64_t)rank] = (int)key;
-            out_coords[3 * (int64_t)rank + 1] = y;
-            out_coords[3 * (int64_t)rank + 2] = x;
+            if (out_cols == 4) {                                          // [b, 0, y, x]: the form the 2-D tail's rulebooks take
+                reinterpret_cast<int4*>(out_coords)[rank] = make_int4((int)key, 0, y, x);
+            } else {
+                out_coords[3 * (int64_t)rank] = (int)key;
+                out_coords[3 * (int64_t)rank + 1] = y;
+                out_coords[3 * (int64_t)rank + 2] = x;
+            }
         }
         ++rank;
     }
@@ -758,7 +763,7 @@ __global__ void __launch_bounds__(QL_SCAN_THREADS) k_m2d_emit(const uint32_t* __
 
 template <typename TIn>
 __global__ void __launch_bounds__(256) k_m2d_add(const TIn* __restrict__ feats, int c, const int4* __restrict__ coords, int64_t n_cap,
-                                                 const int* __restrict__ n_dev, int B, int H, int W,
+                                                 const int* __restrict__ n_dev, int B, int H, int W, int cscale,
                                                  const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_prefix,
                                                  int64_t n_out_cap, float* __restrict__ acc) {
     const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
@@ -767,7 +772,8 @@ __global__ void __launch_bounds__(256) k_m2d_add(const TIn* __restrict__ feats, 
     if (t >= n * groups) return;
     const int64_t row = t / groups;
     const int g4 = (int)(t - row * groups) * 4;
-    const int4 cc = coords[row];
+    int4 cc = coords[row];
+    cc.z *= cscale; cc.w *= cscale;
     if (cc.x < 0 || cc.x >= B || cc.z < 0 || cc.z >= H || cc.w < 0 || cc.w >= W) return;
     const uint32_t key = (uint32_t)((cc.x * H + cc.z) * W + cc.w);
     const uint32_t wd = key >> 5;
@@ -804,10 +810,23 @@ extern "C" size_t ql_bev_merge2d_workspace_bytes(int32_t B, int32_t H, int32_t W
 extern "C" int ql_bev_merge2d(const void* feats, int32_t in_dtype, int32_t c, const int32_t* coords, int64_t n_cap, const int32_t* n_dev,
                               int32_t B, int32_t H, int32_t W, void* out_feats, int32_t out_dtype, int32_t* out_coords,
                               int64_t n_out_cap, int32_t* n_out_dev, void* workspace, size_t workspace_bytes, ql_stream_t stream_) {
+    const int32_t one = 1;
+    return ql_bev_merge2d_multi(1, &feats, in_dtype, c, &coords, &n_cap, &n_dev, &one, B, H, W, out_feats, out_dtype, out_coords, 3, n_out_cap,
+                                n_out_dev, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int ql_bev_merge2d_multi(int32_t n_seg, const void* const* feats, int32_t in_dtype, int32_t c, const int32_t* const* coords,
+                                    const int64_t* n_cap, const int32_t* const* n_dev, const int32_t* coord_scale, int32_t B, int32_t H,
+                                    int32_t W, void* out_feats, int32_t out_dtype, int32_t* out_coords, int32_t out_coord_cols,
+                                    int64_t n_out_cap, int32_t* n_out_dev, void* workspace, size_t workspace_bytes, ql_stream_t stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
-    if (!feats || !coords || !out_feats || !out_coords || !n_out_dev || !workspace) return QL_ERR_INVALID;
+    if (n_seg <= 0 || n_seg > 8 || !feats || !coords || !n_cap || !n_dev || !coord_scale || !out_feats || !out_coords || !n_out_dev || !workspace)
+        return QL_ERR_INVALID;
     if ((in_dtype != QL_F16 && in_dtype != QL_F32) || (out_dtype != QL_F16 && out_dtype != QL_F32)) return QL_ERR_INVALID;
-    if (c <= 0 || c % 4 != 0 || B <= 0 || H <= 0 || W <= 0 || n_cap < 0 || n_out_cap <= 0 || n_cap >= 2147483647LL) return QL_ERR_INVALID;
+    if (out_coord_cols != 3 && out_coord_cols != 4) return QL_ERR_INVALID;
+    if (c <= 0 || c % 4 != 0 || B <= 0 || H <= 0 || W <= 0 || n_out_cap <= 0) return QL_ERR_INVALID;
+    for (int i = 0; i < n_seg; ++i)
+        if (!feats[i] || !coords[i] || n_cap[i] < 0 || n_cap[i] >= 2147483647LL || coord_scale[i] <= 0) return QL_ERR_INVALID;
     if ((double)B * H * W >= 4294967295.0) return QL_ERR_GRID_TOO_LARGE;
     const Merge2dWs w = merge2d_ws_layout(B, H, W, n_out_cap, c, out_dtype != QL_F32);
     if (workspace_bytes < w.total) return QL_ERR_WORKSPACE;
@@ -818,18 +837,21 @@ extern "C" int ql_bev_merge2d(const void* feats, int32_t in_dtype, int32_t c, co
     float* acc = out_dtype == QL_F32 ? (float*)out_feats : (float*)(ws + w.acc);
     if (cudaMemsetAsync(bitmap, 0, (size_t)w.n_words * 4, st) != cudaSuccess) return QL_ERR_CUDA;
     if (cudaMemsetAsync(acc, 0, (size_t)n_out_cap * c * 4, st) != cudaSuccess) return QL_ERR_CUDA;
-    if (n_cap > 0) k_m2d_mark<<<(unsigned)((n_cap + 255) / 256), 256, 0, st>>>((const int4*)coords, n_cap, n_dev, B, H, W, bitmap);
+    for (int i = 0; i < n_seg; ++i)
+        if (n_cap[i] > 0)
+            k_m2d_mark<<<(unsigned)((n_cap[i] + 255) / 256), 256, 0, st>>>((const int4*)coords[i], n_cap[i], n_dev[i], B, H, W, coord_scale[i], bitmap);
     k_rb_popc<<<(unsigned)w.n_blocks, QL_SCAN_THREADS, 0, st>>>(bitmap, w.n_words, blocks);
     k_scan_blocks<<<1, QL_SCAN_THREADS, 0, st>>>(blocks, (int)w.n_blocks, n_out_dev + 1, n_out_dev, n_out_cap);
-    k_m2d_emit<<<(unsigned)w.n_blocks, QL_SCAN_THREADS, 0, st>>>(bitmap, w.n_words, blocks, H, W, prefix, out_coords, n_out_cap);
-    if (n_cap > 0) {
-        const int64_t threads = n_cap * (c / 4);
+    k_m2d_emit<<<(unsigned)w.n_blocks, QL_SCAN_THREADS, 0, st>>>(bitmap, w.n_words, blocks, H, W, prefix, out_coords, n_out_cap, out_coord_cols);
+    for (int i = 0; i < n_seg; ++i) {
+        if (n_cap[i] <= 0) continue;
+        const int64_t threads = n_cap[i] * (c / 4);
         if (in_dtype == QL_F16)
-            k_m2d_add<__half><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const __half*)feats, c, (const int4*)coords, n_cap, n_dev, B, H,
-                                                                                 W, bitmap, prefix, n_out_cap, acc);
+            k_m2d_add<__half><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const __half*)feats[i], c, (const int4*)coords[i], n_cap[i], n_dev[i],
+                                                                                 B, H, W, coord_scale[i], bitmap, prefix, n_out_cap, acc);
         else
-            k_m2d_add<float><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const float*)feats, c, (const int4*)coords, n_cap, n_dev, B, H, W,
-                                                                                bitmap, prefix, n_out_cap, acc);
+            k_m2d_add<float><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const float*)feats[i], c, (const int4*)coords[i], n_cap[i], n_dev[i],
+                                                                                B, H, W, coord_scale[i], bitmap, prefix, n_out_cap, acc);
     }
     if (out_dtype == QL_F16)
         k_m2d_to_half<<<4 * ql_num_sms(), 256, 0, st>>>(acc, n_out_cap * (int64_t)c, c, n_out_dev, (__half*)out_feats);

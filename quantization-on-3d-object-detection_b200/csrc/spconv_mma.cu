@@ -56,7 +56,8 @@ constexpr uint32_t kFlagFirst = 1u, kFlagLast = 2u;
 // test-time build flag (never in the product library): bit 1 = no gather loads, 2 = no tcgen05.st, 4 = no tcgen05.mma,
 // 8 = no epilogue global traffic, 16 = no rulebook slab copies, 64 = no tcgen05.ld / epilogue arithmetic
 __device__ int g_ablate = 0;
-#define QL_ABL(bit) ((g_ablate & (bit)) != 0)
+#define QL_ABL(bit) ((abl_ & (bit)) != 0)
+#define QL_ABL_INIT const int abl_ = g_ablate
 // role trace of the same test-time build: clock64() around every wait / work phase of each role's lead thread, summed over
 // the CTAs of a launch into g_trace[launch % 64][role * 8 + counter] (tools/conv_sweep.py TRACE=1 prints the shares)
 __device__ unsigned long long g_trace[64][32];
@@ -66,6 +67,7 @@ __device__ unsigned long long g_trace[64][32];
         for (int i_ = 0; i_ < (n); ++i_) atomicAdd(&g_trace[p.trace_id & 63][(role) * 8 + i_], (unsigned long long)tr_[i_]); } } while (0)
 #else
 #define QL_ABL(bit) false
+#define QL_ABL_INIT
 #define QL_TR_DECL(n)
 #define QL_TR(i)
 #define QL_TR_FLUSH(role, n, lead)
@@ -262,6 +264,7 @@ __global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p
     const int warp = tid >> 5;
     const int lane = tid & 31;
     const int T = p.teams;
+    QL_ABL_INIT;
     const int mma_warp = kProducerWarp0 + 4 * T, loader_warp = mma_warp + 1;
     const uint32_t n_slots = (uint32_t)p.n_slots;
     const uint32_t S = (uint32_t)p.unit_cols;

@@ -51,10 +51,12 @@ SIGNATURES = {
     "ql_stem_conv": (C.c_int, [_p, _i32, _i32, _p, _p, _i64, _p, _i32, _i32, _p, _p, _p, _i32, _p, _i32, _p, _p]),
     "ql_absmax_cols": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p]),
     "ql_quantize_rows": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p, _i32, _i32, _p, _p, _p]),
+    "ql_sq_prepare_weights": (C.c_int, [_p, _p, _p, C.c_float, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
     "ql_bev_densify_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ql_bev_densify": (C.c_int, [_p, _i32, _i32, _p, _i64, _i32, _i32, _i32, _i32, _p, _i32, _p, _sz, _p]),
     "ql_bev_merge2d_workspace_bytes": (_sz, [_i32, _i32, _i32, _i64, _i32, _i32]),
     "ql_bev_merge2d": (C.c_int, [_p, _i32, _i32, _p, _i64, _p, _i32, _i32, _i32, _p, _i32, _p, _i64, _p, _p, _sz, _p]),
+    "ql_bev_merge2d_multi": (C.c_int, [_i32, _p, _i32, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _p, _i32, _p, _i32, _i64, _p, _p, _sz, _p]),
     "ql_bev_densify_ranked": (C.c_int, [_p, _i32, _i32, _p, _p, _i64, _p, _i32, _i32, _i32, _i32, _p, _i32, _p, _sz, _p]),
 }
 

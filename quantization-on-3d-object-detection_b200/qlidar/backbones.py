@@ -86,6 +86,18 @@ class SparseBasicBlock(spconv.SparseModule):
 
 
 class _BackboneBase(nn.Module):
+    """forward(batch_dict) -- the reference's plugin call (spconv_backbone.py:243-295) -- is the FAST path: the first call compiles
+    the module tree into a qlidar.engine.BackboneEngine (BN folded into the conv epilogues, weights packed, every buffer allocated
+    once, the whole forward captured in one CUDA graph) and later calls replay it; the engine is rebuilt when a parameter, a
+    buffer (calibrated amax, BN statistics) or a quantiser switch changes, or when the input outgrows its capacity.  The op-by-op
+    module tree below still runs -- every conv one fused kernel, BatchNorm / ReLU / residual as separate ATen kernels -- while
+    calibrating (collect_stats disables the quantisers), in training mode, for module trees the engine cannot schedule, and
+    when `use_engine` is False.  One host synchronisation per call remains: the reference API returns exactly-sized tensors.
+    Row order: the engine returns every stage in ascending-key order (x_conv1 included: the reference keeps the voxeliser's
+    order there); coordinates travel with the features, so consumers that index by `indices` are unaffected."""
+    use_engine = True
+    engine_bev_dtype = None                   # set by HeightCompression.attach(): the BEV map is then produced inside the graph
+
     def _input_tensor(self, batch_dict):
         voxel_features, voxel_coords = batch_dict['voxel_features'], batch_dict['voxel_coords']
         # load_data_to_gpu casts coords to float32 (pcdet/models/__init__.py:36); `.int()` undoes it (spconv_backbone.py:258)
@@ -99,6 +111,83 @@ class _BackboneBase(nn.Module):
         batch_dict.update({'multi_scale_3d_features': taps})
         batch_dict.update({'multi_scale_3d_strides': {'x_conv1': 1, 'x_conv2': 2, 'x_conv3': 4, 'x_conv4': 8}})
         return batch_dict
+
+    # ------------------------------------------------------------------ engine-backed plugin call
+    def _state_signature(self):
+        from .tensor_quant import TensorQuantizer
+        sig = [(p.data_ptr(), p._version) for p in self.parameters()]
+        sig += [(b.data_ptr(), b._version) for b in self.buffers()]
+        for m in self.modules():
+            sig.append(type(m).__name__)
+            if isinstance(m, TensorQuantizer):
+                sig.append((m._disabled, m._if_quant, m._if_calib, m.num_bits, None if m.amax is None else (m.amax.data_ptr(), m.amax._version)))
+        return hash(tuple(sig))
+
+    def _engine_eligible(self, batch_dict) -> bool:
+        from .tensor_quant import TensorQuantizer
+        if not self.use_engine or self.training or torch.is_grad_enabled() or getattr(self, "_engine_unsupported", False):
+            return False
+        if not batch_dict['voxel_features'].is_cuda:
+            return False
+        for m in self.modules():
+            if isinstance(m, TensorQuantizer) and (m._if_calib or m._disabled or not m._if_quant):
+                return False                                    # calibration / quantisers off: the eager tree collects the statistics
+        return True
+
+    def _engine_for(self, batch_dict):
+        from .engine import BackboneEngine
+        from ._lib import QlidarError
+        V, B = int(batch_dict['voxel_features'].shape[0]), int(batch_dict['batch_size'])
+        sig = self._state_signature()
+        st = getattr(self, "_engine_state", None)
+        if st is not None and st["sig"] == sig and st["B"] == B and V <= st["cap"] and st["bev"] == self.engine_bev_dtype:
+            return st["eng"]
+        cap = max(int(V * 1.25) + 1024, 0 if st is None else st["cap"])
+        ratio = 1.3 if st is None else st.get("ratio", 1.3)
+        try:
+            eng = BackboneEngine(self, B, cap, stage_cap_ratio=ratio, bev=self.engine_bev_dtype is not None,
+                                 bev_dtype=self.engine_bev_dtype or torch.float16, device=batch_dict['voxel_features'].device)
+        except QlidarError:
+            self._engine_unsupported = True                     # a module tree the engine cannot schedule: the eager tree serves it
+            return None
+        self._engine_state = dict(sig=sig, B=B, cap=cap, eng=eng, ratio=ratio, bev=self.engine_bev_dtype)
+        return eng
+
+    def _engine_forward(self, batch_dict):
+        eng = self._engine_for(batch_dict)
+        if eng is None:
+            return None
+        vf, vc = batch_dict['voxel_features'], batch_dict['voxel_coords']
+        for attempt in range(3):
+            out = eng.forward_voxels(vf, vc)
+            counts = torch.stack([st.n_dev for st in eng.stages]).cpu()         # the one synchronisation of the call
+            if not bool((counts[1:, 1] > counts[1:, 0]).any()):
+                break
+            # a stage outgrew its capacity (denser scene than any before): enlarge and run again
+            self._engine_state["ratio"] *= 1.5
+            self._engine_state["sig"] = None
+            eng = self._engine_for(batch_dict)
+        n = [int(v) for v in counts[:, 0].tolist()]
+        B = int(batch_dict['batch_size'])
+
+        def tensor(feats, stage_i):
+            stg = eng.stages[stage_i]
+            t = SparseConvTensor(features=feats[:n[stage_i]], indices=stg.coords[:n[stage_i]], spatial_shape=list(stg.grid[1:]), batch_size=B)
+            if vf.dtype != feats.dtype:
+                t._surface_dtype = vf.dtype                         # fp32 in -> fp32 out, converted when read
+            return t
+
+        last = eng.layers[-1]
+        enc = tensor(last.out, last.stage_out)
+        if getattr(eng, "merge_stage", None) is not None:                        # VoxelNeXt: the encoded tensor is 2-D, [b, y, x]
+            enc = SparseConvTensor(features=enc._features, indices=enc.indices[:, [0, 2, 3]].contiguous(),
+                                   spatial_shape=enc.spatial_shape[1:], batch_size=B)
+            if vf.dtype != enc._features.dtype:
+                enc._surface_dtype = vf.dtype
+        if eng.bev:
+            enc._ql_spatial_features = eng.spatial_features                     # HeightCompression takes the fused map
+        taps = {L.tap: tensor(L.out, L.stage_out) for L in eng.layers if L.tap}
+        return self._publish(batch_dict, enc, taps)
 
 
 class VoxelBackBone8x(_BackboneBase):
@@ -131,6 +220,10 @@ class VoxelBackBone8x(_BackboneBase):
         self.backbone_channels = {'x_conv1': 16, 'x_conv2': 32, 'x_conv3': 64, 'x_conv4': 64}
 
     def forward(self, batch_dict):
+        if self._engine_eligible(batch_dict):
+            done = self._engine_forward(batch_dict)
+            if done is not None:
+                return done
         x = self.conv_input(self._input_tensor(batch_dict))
         x_conv1 = self.conv1(x)
         x_conv2 = self.conv2(x_conv1)
@@ -173,6 +266,10 @@ class VoxelResBackBone8x(_BackboneBase):
         self.backbone_channels = {'x_conv1': 16, 'x_conv2': 32, 'x_conv3': 64, 'x_conv4': 128}
 
     def forward(self, batch_dict):
+        if self._engine_eligible(batch_dict):
+            done = self._engine_forward(batch_dict)
+            if done is not None:
+                return done
         x = self.conv_input(self._input_tensor(batch_dict))
         x_conv1 = self.conv1(x)
         x_conv2 = self.conv2(x_conv1)
@@ -228,6 +325,10 @@ class VoxelResBackBone8xVoxelNeXt(_BackboneBase):
         return SparseConvTensor(features=f[:n], indices=c3[:n], spatial_shape=spatial_shape, batch_size=x_conv.batch_size)
 
     def forward(self, batch_dict):
+        if self._engine_eligible(batch_dict):
+            done = self._engine_forward(batch_dict)
+            if done is not None:
+                return done
         x = self.conv_input(self._input_tensor(batch_dict))
         x_conv1 = self.conv1(x)
         x_conv2 = self.conv2(x_conv1)
@@ -315,8 +416,19 @@ class HeightCompression(nn.Module):
         self.model_cfg = _cfg(model_cfg)
         self.num_bev_features = self.model_cfg.NUM_BEV_FEATURES
 
+    def attach(self, backbone, dtype=torch.float32):
+        """Optional: let `backbone`'s engine produce the BEV map inside its CUDA graph (one kernel, no memset + scatter + permute);
+        forward() then returns that buffer.  dtype float32 = the reference's; float16 halves the largest write of the path."""
+        backbone.engine_bev_dtype = dtype
+        return self
+
     def forward(self, batch_dict):
         t = batch_dict['encoded_spconv_tensor']
+        fused = getattr(t, "_ql_spatial_features", None)
+        if fused is not None:
+            batch_dict['spatial_features'] = fused
+            batch_dict['spatial_features_stride'] = batch_dict['encoded_spconv_tensor_stride']
+            return batch_dict
         spatial_features = t.dense()
         N, C, D, H, W = spatial_features.shape
         batch_dict['spatial_features'] = spatial_features.view(N, C * D, H, W)

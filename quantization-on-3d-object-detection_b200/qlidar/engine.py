@@ -21,7 +21,7 @@ import torch.nn as nn
 
 from . import ops
 from ._lib import QlidarError
-from .quant import QConvNd
+from .quant import QConvNd, SQConv3d
 from .tensor_quant import quant_scale
 from .sparse import SparseConvolution, SparseSequential, SparseConvTensor, _round_up
 from .backbones import SparseBasicBlock
@@ -57,6 +57,15 @@ class Layer:
     out_q: Optional[torch.Tensor] = None         # static mode: this layer's epilogue also writes the NEXT layer's int8 codes here
     out_qscale: Optional[torch.Tensor] = None    # ... with these per-channel quantisation scales (bound / calibrated amax)
     fused_q: bool = False                        # this layer's codes come from the previous layer's epilogue
+    merge_srcs: Optional[list] = None            # 'merge' (VoxelNeXt bev_out): the layers whose outputs are merged, and their
+    merge_scales: Optional[list] = None          # coordinate scales onto the target grid
+    ws: Optional[torch.Tensor] = None
+    smooth: Optional[torch.Tensor] = None        # SmoothQuant: per-input-channel smoothing scale (device)
+    sq_dynamic: bool = False                     # ... re-derived (with the weight image and the scale) inside the graph per forward
+    sq_alpha: float = 0.5
+    w_f32: Optional[torch.Tensor] = None
+    w_ic: Optional[torch.Tensor] = None
+    bn_a: Optional[torch.Tensor] = None
 
 
 @dataclass
@@ -79,6 +88,8 @@ def _bn_fold(bn: nn.BatchNorm1d):
 
 
 def _unwrap(m):
+    if isinstance(m, SQConv3d):
+        return m.spconv3d, m
     if isinstance(m, QConvNd):
         return m.module, m
     if isinstance(m, SparseConvolution):
@@ -130,15 +141,23 @@ class BackboneEngine:
     # ------------------------------------------------------------------ compile the module tree into a layer list
     def _add_conv(self, name, convm, bn, relu, residual=False, block_input=False):
         conv, qw = _unwrap(convm)
-        if conv.ndim != 3:
-            raise QlidarError("the engine schedules the 3-D backbones; VoxelNeXt's 2-D tail runs through the module path")
         a, b = _bn_fold(bn)
         K = int(np.prod(conv.kernel_size))
         cin, cout = conv.in_channels, conv.out_channels
         bias = conv.bias.detach().float() if conv.bias is not None else torch.zeros(cout)
-        L = Layer(name=name, kind="f16", cin=cin, cout=cout, ksize=tuple(conv.kernel_size), stride=tuple(conv.stride),
-                  pad=tuple(conv.padding), subm=conv.subm, relu=relu, residual=residual, block_input=block_input)
-        if qw is not None:
+        # 2-D convs (VoxelNeXt's tail) run as D = 1 slabs: zyx triples with a unit z axis
+        L = Layer(name=name, kind="f16", cin=cin, cout=cout, ksize=tuple(conv._k3()), stride=tuple(conv._s3()),
+                  pad=tuple(conv._p3()) if not conv.subm else tuple(k // 2 for k in conv._k3()), subm=conv.subm, relu=relu,
+                  residual=residual, block_input=block_input)
+        sq = isinstance(qw, SQConv3d)
+        if sq:
+            # SmoothQuant W8A8 (SQConv3d): static (calibrated per-channel amax) -> smoothed codes prepared once on the host;
+            # dynamic -> re-prepared on the device inside the graph from the producing layer's abs-max (ql_sq_prepare_weights);
+            # the scalar variant (no scaling_factor) cancels in both quantisers and is plain W8A8 per-tensor
+            L.act_bits = qw.act_quant.num_bits
+            L.act_amax = None if qw.act_amax is None else qw.act_amax.detach().float().reshape(-1).cpu()
+            codes = None
+        elif qw is not None:
             codes, amax_w, bound = qw.weight_codes()
             w_scale = amax_w.float().cpu() / bound                     # host: a true division
             L.act_bits = qw.act_quant.num_bits
@@ -159,6 +178,31 @@ class BackboneEngine:
         else:
             if cin % 16 or cout % 16:
                 raise QlidarError("engine layers need channel counts that are multiples of 16")
+            if sq:
+                if cin % 16 or cout % 16:
+                    raise QlidarError("SQConv3d engine layers need channel counts that are multiples of 16")
+                L.kind = "sq"
+                L.shift = (bias.cpu() * a.cpu() + b.cpu()).to(self.dev)
+                if qw.scaling_factor is None or L.act_amax is not None:
+                    s_host = None if qw.scaling_factor is None else qw.smoothing_scale(L.act_amax.expand(cin) if L.act_amax.numel() == 1 else L.act_amax)
+                    packed, _, _, w_sc, _ = qw._prepare(torch.device("cpu"), s_host)
+                    L.w = packed.to(self.dev)
+                    L.scale = (w_sc.cpu() * a.cpu()).to(self.dev)
+                    L.smooth = None if s_host is None else s_host.float().contiguous().to(self.dev)
+                    L.sq_dynamic = False
+                else:
+                    L.sq_dynamic = True
+                    L.sq_alpha = float(qw.scaling_factor)
+                    wf = conv.weight.detach().float().reshape(cout, K, cin).contiguous().to(self.dev)
+                    L.w_f32, L.w_ic = wf, wf.abs().amax(dim=(0, 1)).contiguous()
+                    L.bn_a = a.cpu().contiguous().to(self.dev)
+                    L.w = torch.zeros(int(ops.lib().ql_packed_weight_bytes(cin, cout, K, ops.QL_S8)), dtype=torch.uint8, device=self.dev)
+                    L.scale = torch.zeros(cout, dtype=torch.float32, device=self.dev)
+                    L.smooth = torch.ones(cin, dtype=torch.float32, device=self.dev)
+                self.layers_sq = getattr(self, "layers_sq", 0) + 1
+                L.stage_in = len(self.stages) - 1
+                self._finish_layer(L, conv, K)
+                return L
             if qw is None or L.act_bits > 8:
                 L.kind = "f16"
                 wt = conv.weight.detach().float().reshape(cout, K, cin).cpu() if codes is None else codes.cpu()
@@ -174,15 +218,20 @@ class BackboneEngine:
                 L.w = ops.pack_weights(codes.cpu().to(torch.int8)).to(self.dev)
             L.scale = (w_scale * a.cpu()).to(self.dev)
             L.shift = (bias.cpu() * a.cpu() + b.cpu()).to(self.dev)
-        # stage bookkeeping
         L.stage_in = len(self.stages) - 1
+        self._finish_layer(L, conv, K)
+        return L
+
+    def _finish_layer(self, L, conv, K):
+        """Stage bookkeeping: which stage the layer reads / writes and which rulebook it uses."""
+        cin, cout = L.cin, L.cout
         if conv.subm:
             L.stage_out = L.stage_in
             # grouped (rows binned by line key) or plain rulebook; the SIMT stem always takes the plain one, so a grouped
             # stage 1 builds two rulebooks (the second on the side stream, under the stem)
             grp = self.group_rows
             if isinstance(grp, str):
-                streamed = L.kind != "stem" and ops.weights_streamed(cin, cout, K, torch.int8 if L.kind == "i8" else torch.float16)
+                streamed = L.kind != "stem" and ops.weights_streamed(cin, cout, K, torch.int8 if L.kind in ("i8", "sq") else torch.float16)
                 grp = streamed                                  # "auto": only where the weights are streamed (DESIGN.md 5c)
             ranked = L.stage_in > 0 or self.sort_stage1
             grp = bool(grp) and ranked and L.kind != "stem" and L.ksize[2] <= 31
@@ -191,13 +240,15 @@ class BackboneEngine:
             g = self.stages[-1].grid
             od, oh, ow = ops.conv_out_shape(g[1:], L.ksize, L.stride, L.pad)
             cap = max(128, int(self.stages[-1].cap * self._cap_ratio))
-            if self._stage_caps is not None:
+            if self._stage_caps is not None and len(self.stages) < len(self._stage_caps):
                 cap = int(self._stage_caps[len(self.stages)])
+            elif self.merge_stage is not None and L.stage_in >= self.merge_stage:
+                # a regular (dilating) 2-D conv on the merged sites: at most k*k outputs per input, never more than the grid
+                cap = int(min(g[0] * od * oh * ow, self.stages[-1].cap * max(2.0, self._cap_ratio)))
             self.stages.append(Stage((g[0], od, oh, ow), cap))
             L.stage_out = len(self.stages) - 1
             L.rb_key = ("strided", L.stage_in, L.ksize, L.stride, L.pad)
         self.layers.append(L)
-        return L
 
     def _compile(self, bb):
         def seq_conv_bn_relu(prefix, seq):
@@ -207,6 +258,8 @@ class BackboneEngine:
             return self._add_conv(prefix + ".0", mods[0], mods[1], True)
 
         seq_conv_bn_relu("conv_input", bb.conv_input)
+        stage_last = {}
+        self.merge_stage = None
         i = 1
         while hasattr(bb, f"conv{i}"):
             top = getattr(bb, f"conv{i}")
@@ -224,9 +277,37 @@ class BackboneEngine:
                     raise QlidarError(f"{p}: unsupported child {type(child).__name__}")
             if i <= 4:
                 last.tap = f"x_conv{i}"
+            stage_last[i] = last
             i += 1
-        seq_conv_bn_relu("conv_out", bb.conv_out)
+        if hasattr(bb, "shared_conv"):
+            # VoxelResBackBone8xVoxelNeXt.forward (spconv_backbone_voxelnext.py:194-225): stages 5 / 6 land on the stage-4 grid
+            # (indices * 2 / * 4), the three site lists are merged in 2-D (z dropped, duplicates summed), then the 2-D tail
+            if not all(k in stage_last for k in (4, 5, 6)):
+                raise QlidarError("VoxelNeXt backbone: conv4, conv5 and conv6 expected")
+            self._add_merge([stage_last[4], stage_last[5], stage_last[6]], [1, 2, 4])
+            seq_conv_bn_relu("conv_out", bb.conv_out)
+            mods = list(bb.shared_conv._modules.values())
+            if not (len(mods) == 3 and isinstance(mods[1], nn.BatchNorm1d) and isinstance(mods[2], nn.ReLU)):
+                raise QlidarError("shared_conv: expected conv, BatchNorm1d, ReLU")
+            self._add_conv("shared_conv.0", mods[0], mods[1], True)
+            self.bev = False                                            # fully sparse: there is no dense BEV hand-off
+        else:
+            seq_conv_bn_relu("conv_out", bb.conv_out)
         self.num_convs = len(self.layers)
+
+    def _add_merge(self, srcs, scales):
+        s4 = self.stages[srcs[0].stage_out]
+        B, _, H, W = s4.grid
+        cap = sum(self.stages[L.stage_out].cap for L in srcs)
+        L = Layer(name="bev_out", kind="merge", cin=srcs[0].cout, cout=srcs[0].cout, ksize=(1, 1, 1), stride=(1, 1, 1), pad=(0, 0, 0),
+                  subm=False, relu=False, residual=False, block_input=False)
+        L.merge_srcs, L.merge_scales = list(srcs), list(scales)
+        L.stage_in = srcs[0].stage_out
+        self.stages.append(Stage((B, 1, H, W), cap))
+        L.stage_out = len(self.stages) - 1
+        L.rb_key = None
+        self.merge_stage = L.stage_out
+        self.layers.append(L)
 
     # ------------------------------------------------------------------ static buffers
     def _allocate(self):
@@ -272,7 +353,9 @@ class BackboneEngine:
         prev_absmax = None
         for L in self.layers:
             so = self.stages[L.stage_out]
-            if L.rb_key not in self.rulebooks:
+            if L.kind == "merge":
+                L.ws = z(int(ops.lib().ql_bev_merge2d_workspace_bytes(so.grid[0], so.grid[2], so.grid[3], so.cap, L.cout, ops.QL_F16)), dt=torch.uint8)
+            elif L.rb_key not in self.rulebooks:
                 K = int(np.prod(L.ksize))
                 self.rulebooks[L.rb_key] = z(ops.num_tiles(so.cap), K, ops.TILE_M, dt=torch.int32)
                 self.kmasks[L.rb_key] = z(ops.num_tiles(so.cap), ops.mask_words(K), dt=torch.int32)
@@ -287,7 +370,7 @@ class BackboneEngine:
             off += L.cout
             L.in_absmax = prev_absmax
             prev_absmax = L.out_absmax
-            if L.kind == "i8":
+            if L.kind in ("i8", "sq"):
                 L.q_buf = ops.zero_led_rows(self.stages[L.stage_in].cap, L.cin, torch.int8, dev)
                 L.act_scale = z(1, dt=torch.float32)
             elif L.kind in ("cw", "row"):
@@ -314,7 +397,7 @@ class BackboneEngine:
             self.spatial_features = z(B, self.layers[-1].cout * D, H, W, dt=self.bev_dtype)
             self.bev_ws = z(int(ops.lib().ql_bev_densify_workspace_bytes(B, D, H, W)), dt=torch.uint8)
         self._need_absmax = [i for i, L in enumerate(self.layers[:-1])
-                             if self.layers[i + 1].kind in ("i8", "cw") and self.layers[i + 1].act_amax is None]
+                             if self.layers[i + 1].kind in ("i8", "cw", "sq") and self.layers[i + 1].act_amax is None]
 
     # ------------------------------------------------------------------ the schedule
     def _op(self, label, n_kernels, fn, *a, **kw):
@@ -366,8 +449,8 @@ class BackboneEngine:
                 ev.record(self._side)
                 ready["sorted"] = ev
             for L in self.layers:
-                if L.rb_key in seen:
-                    continue
+                if L.rb_key is None or L.rb_key in seen or (self.merge_stage is not None and L.stage_in >= self.merge_stage):
+                    continue                  # (the 2-D tail's rulebooks depend on the merge, which runs on the main stream)
                 seen.add(L.rb_key)
                 self._build_rulebook(L)
                 ev = torch.cuda.Event()
@@ -385,13 +468,23 @@ class BackboneEngine:
         block_in = None
         if self._need_absmax:
             self.absmax_pool.zero_()
-        overlap = self.overlap_rulebooks and self._timing is None and len({L.rb_key for L in self.layers}) > 1
+        overlap = self.overlap_rulebooks and self._timing is None and len({L.rb_key for L in self.layers if L.rb_key is not None}) > 1
         if ready is None:
             ready = self._fork_rulebooks() if overlap else {}
         else:
             overlap = True
         for i, L in enumerate(self.layers):
             si, so = self.stages[L.stage_in], self.stages[L.stage_out]
+            absmax = L.out_absmax if i in self._need_absmax else None
+            if L.kind == "merge":
+                # VoxelNeXt bev_out: stages 4 / 5 / 6 onto the stage-4 grid, z dropped, duplicates summed (kernels: 3 marks, popc, scan,
+                # emit, 3 adds, fp32 -> fp16)
+                segs = [(m.out, self.stages[m.stage_out].coords, self.stages[m.stage_out].n_dev, sc) for m, sc in zip(L.merge_srcs, L.merge_scales)]
+                self._op("bev_merge2d", 10, ops.bev_merge2d_multi, segs, (so.grid[0], so.grid[2], so.grid[3]), so.cap, L.out, so.coords, so.n_dev, L.ws)
+                if absmax is not None:
+                    self._op("absmax:" + L.name, 1, ops.absmax_cols, L.out, so.n_dev, absmax)
+                x = L.out
+                continue
             nbr, kmask, perm = self.rulebooks[L.rb_key], self.kmasks[L.rb_key], self.row_perms[L.rb_key]
             if L.rb_key not in built:
                 if L.rb_key in ready:
@@ -399,7 +492,6 @@ class BackboneEngine:
                 else:
                     self._build_rulebook(L)
                 built.add(L.rb_key)
-            absmax = L.out_absmax if i in self._need_absmax else None
             if L.block_input:
                 block_in = x
             res = block_in if L.residual else None
@@ -417,6 +509,15 @@ class BackboneEngine:
                              act_scale=L.act_scale)
                 self._op("conv:" + L.name, 1, ops.spconv_mma, L.q_buf, nbr, so.cap, so.n_dev, L.cout, L.w, L.scale, L.shift, act_scale=L.act_scale, residual=res,
                                relu=L.relu, out=L.out, absmax=absmax, kmask=kmask, out_q=L.out_q, out_qscale=L.out_qscale, row_perm=perm)
+            elif L.kind == "sq":
+                am = L.act_amax if L.act_amax is not None else L.in_absmax
+                if L.sq_dynamic:
+                    self._op("sq_prepare:" + L.name, 2, ops.sq_prepare_weights, L.w_f32, L.w_ic, am, L.sq_alpha, bn_scale=L.bn_a, smooth=L.smooth,
+                             packed=L.w, scale=L.scale)
+                self._op("quantize:" + L.name, 1, ops.quantize_rows, x, am, ops.QL_Q_CODES_PER_TENSOR, L.act_bits, si.n_dev, smooth=L.smooth, out=L.q_buf,
+                         act_scale=L.act_scale)
+                self._op("conv:" + L.name, 1, ops.spconv_mma, L.q_buf, nbr, so.cap, so.n_dev, L.cout, L.w, L.scale, L.shift, act_scale=L.act_scale, residual=res,
+                               relu=L.relu, out=L.out, absmax=absmax, kmask=kmask, row_perm=perm)
             elif L.kind in ("cw", "row"):
                 if L.kind == "row":
                     self._op("quantize:" + L.name, 1, ops.quantize_rows, x, None, ops.QL_Q_FAKE_PER_ROW, L.act_bits, si.n_dev, out=L.q_buf)
@@ -561,6 +662,8 @@ class BackboneEngine:
         acct = []
         pairs = {}
         for L in self.layers:
+            if L.kind == "merge":
+                continue
             n_in, n_out = counts[L.stage_in], counts[L.stage_out]
             K = int(np.prod(L.ksize))
             tiles = ops.num_tiles(n_out)

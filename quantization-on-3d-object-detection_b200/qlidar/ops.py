@@ -321,6 +321,26 @@ def bev_merge2d(feats: torch.Tensor, coords: torch.Tensor, n_dev: Optional[torch
     return out_feats, out_coords, n_out
 
 
+def bev_merge2d_multi(segments, grid_bhw, n_out_cap: int, out_feats: torch.Tensor, out_coords: torch.Tensor, n_out_dev: torch.Tensor,
+                      workspace: torch.Tensor):
+    """VoxelNeXt's stage-4/5/6 merge in one pass.  segments: list of (feats [cap, c], coords [cap, 4] int32, n_dev, coord_scale);
+    out_coords [n_out_cap, 3 or 4] int32 (4: [b, 0, y, x]); everything preallocated (graph-capturable)."""
+    n = len(segments)
+    feats = [s[0] for s in segments]
+    _need_cuda(*feats, *[s[1] for s in segments], *[s[2] for s in segments], out_feats, out_coords, n_out_dev, workspace)
+    c = feats[0].shape[1]
+    B, H, W = [int(v) for v in grid_bhw]
+    fp = (C.c_void_p * n)(*[f.data_ptr() for f in feats])
+    cp = (C.c_void_p * n)(*[s[1].data_ptr() for s in segments])
+    caps = (C.c_int64 * n)(*[int(s[0].shape[0]) for s in segments])
+    nd = (C.c_void_p * n)(*[None if s[2] is None else s[2].data_ptr() for s in segments])
+    sc = (C.c_int32 * n)(*[int(s[3]) for s in segments])
+    check(lib().ql_bev_merge2d_multi(n, fp, _DT[feats[0].dtype], c, cp, caps, nd, sc, B, H, W, _ptr(out_feats), _DT[out_feats.dtype],
+                                     _ptr(out_coords), int(out_coords.shape[1]), int(n_out_cap), _ptr(n_out_dev), _ptr(workspace),
+                                     workspace.numel(), _stream()), "ql_bev_merge2d_multi")
+    return out_feats, out_coords, n_out_dev
+
+
 def zero_led_rows(n: int, c: int, dtype=torch.float16, device="cuda") -> torch.Tensor:
     """[n, c] zero-initialised rows with one extra all-zero row IN FRONT of row 0 (same allocation): the layout the conv kernel
     gathers from -- rulebook index -1 reads that row (include/qlidar.h, zero-row contract).  The returned view is tagged;
@@ -354,6 +374,26 @@ def pack_weights(w: torch.Tensor) -> torch.Tensor:
     out = torch.empty(nbytes, dtype=torch.uint8)
     check(lib().ql_pack_weights_host(C.c_void_p(w.data_ptr()), dt, c_in, c_out, K, C.c_void_p(out.data_ptr())), "ql_pack_weights_host")
     return out
+
+
+def sq_prepare_weights(w_okc: torch.Tensor, w_ic_absmax: torch.Tensor, act_absmax: torch.Tensor, alpha: float,
+                       bn_scale: Optional[torch.Tensor] = None, smooth: Optional[torch.Tensor] = None,
+                       packed: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None):
+    """SmoothQuant on the device: w_okc (c_out, K, c_in) fp32 -> (smooth [c_in], packed int8 weight image, scale [c_out])."""
+    _need_cuda(w_okc, w_ic_absmax, act_absmax, bn_scale, smooth, packed, scale)
+    if w_okc.dtype != torch.float32 or w_okc.dim() != 3:
+        raise QlidarError("sq_prepare_weights expects (c_out, K, c_in) float32 weights")
+    c_out, K, c_in = w_okc.shape
+    dev = w_okc.device
+    if smooth is None:
+        smooth = torch.empty(c_in, dtype=torch.float32, device=dev)
+    if packed is None:
+        packed = torch.empty(int(lib().ql_packed_weight_bytes(c_in, c_out, K, QL_S8)), dtype=torch.uint8, device=dev)
+    if scale is None:
+        scale = torch.empty(c_out, dtype=torch.float32, device=dev)
+    check(lib().ql_sq_prepare_weights(_ptr(w_okc), _ptr(w_ic_absmax), _ptr(act_absmax), C.c_float(float(alpha)), c_in, c_out, K,
+                                      _ptr(bn_scale), _ptr(smooth), _ptr(packed), _ptr(scale), _stream()), "ql_sq_prepare_weights")
+    return smooth, packed, scale
 
 
 def weights_streamed(c_in: int, c_out: int, kvol: int, dtype: torch.dtype = torch.float16) -> bool:

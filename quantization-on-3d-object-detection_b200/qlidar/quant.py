@@ -174,9 +174,9 @@ class SQConv3d(SparseModule):
       * SQConv3d(spconv3d, scaling_factor=a)    quant/quant_conv3d.py:141-236 (non-functional as shipped: dense unfold on
         the CPU with prints): its intent with the quant/smoothquant.py:72-79 formula, per input channel,
         s[ic] = amax_x[ic]^a / (max_{oc,k} |w[oc,k,ic]|)^(1-a), zeros -> 1; x' = x / s, w' = w * s; W8A8-pt on (x', w').
-    act_amax: optional calibrated per-channel |x| maxima (static SmoothQuant; weights are then prepared once).  Without it
-    the maxima are taken from the incoming features on every call and the smoothed weights are re-quantised and
-    re-packed per call (a host round trip: the eager module path, not the engine)."""
+    act_amax: optional calibrated per-channel |x| maxima (static SmoothQuant; weights are then prepared once, on the host).
+    Without it the maxima are taken from the incoming features on every call and the smoothed weights are re-quantised into the
+    kernel's packed image ON THE DEVICE (ql_sq_prepare_weights) -- no host round trip, so the engine can capture the layer."""
 
     def __init__(self, spconv3d: SparseConvolution = None, scaling_factor: Optional[float] = None, module: SparseConvolution = None,
                  w_bits: int = 8, act_bits: int = 8, act_amax: Optional[torch.Tensor] = None):
@@ -192,6 +192,7 @@ class SQConv3d(SparseModule):
         self.original_weight = self.spconv3d.weight.data.clone()
         self.act_amax = None if act_amax is None else act_amax.detach().float().reshape(-1).clone()
         self._cache = None
+        self._dev = None
 
     def smoothing_scale(self, amax_ic: torch.Tensor) -> Optional[torch.Tensor]:
         """fp32 on the host, the oracle's arithmetic (oracle smoothquant_scale), so that codes are reproducible bit for bit."""
@@ -224,6 +225,27 @@ class SQConv3d(SparseModule):
             shift[:oc] = conv.bias.detach().float().to(dev)
         return packed, ic_p, oc_p, w_scale, shift
 
+    def _device_state(self, dev):
+        """fp32 weights (oc_p, K, ic_p), their per-input-channel |w| maxima, bias and the output buffers of the device-side
+        preparation (ql_sq_prepare_weights) -- the dynamic per-channel path never leaves the device."""
+        conv = self.spconv3d
+        key = (conv.weight._version, conv.weight.data_ptr(), str(dev))
+        if self._dev is not None and self._dev[0] == key:
+            return self._dev[1]
+        wt = conv.weight.detach().float()
+        oc, ic = wt.shape[0], wt.shape[-1]
+        ic_p, oc_p = _round_up(ic, 16), _round_up(oc, 16)
+        w = torch.zeros((oc_p, wt.numel() // (oc * ic), ic_p), dtype=torch.float32, device=dev)
+        w[:oc, :, :ic] = wt.reshape(oc, -1, ic).to(dev)
+        shift = torch.zeros(oc_p, dtype=torch.float32, device=dev)
+        if conv.bias is not None:
+            shift[:oc] = conv.bias.detach().float().to(dev)
+        st = dict(w=w, w_ic=w.abs().amax(dim=(0, 1)).contiguous(), shift=shift, ic_p=ic_p, oc_p=oc_p,
+                  smooth=torch.empty(ic_p, dtype=torch.float32, device=dev), scale=torch.empty(oc_p, dtype=torch.float32, device=dev),
+                  packed=torch.empty(int(ops.lib().ql_packed_weight_bytes(ic_p, oc_p, w.shape[1], ops.QL_S8)), dtype=torch.uint8, device=dev))
+        self._dev = (key, st)
+        return st
+
     def forward(self, x: SparseConvTensor) -> SparseConvTensor:
         conv = self.spconv3d
         rb = conv.get_rulebook(x)
@@ -232,20 +254,32 @@ class SQConv3d(SparseModule):
         f = (f if f.dtype in (torch.float16, torch.float32) else f.float()).contiguous()
         n_dev = x._n_dev
         static = self.act_amax is not None
+        out_dtype = torch.float32 if in_dtype == torch.float32 else torch.float16
+        if not static and self.scaling_factor is not None:
+            # dynamic per-channel SmoothQuant, all on the device: abs-max -> smoothing scale + smoothed int8 weight image -> codes -> conv
+            st = self._device_state(f.device)
+            if st["ic_p"] != conv.in_channels:
+                f = torch.nn.functional.pad(f, (0, st["ic_p"] - conv.in_channels)).contiguous()
+            amax_ic = ops.absmax_cols(f, n_dev)
+            ops.sq_prepare_weights(st["w"], st["w_ic"], amax_ic, float(self.scaling_factor), smooth=st["smooth"], packed=st["packed"], scale=st["scale"])
+            q, act_scale = ops.quantize_rows(f, amax_ic, ops.QL_Q_CODES_PER_TENSOR, self.act_quant.num_bits, n_dev, smooth=st["smooth"])
+            y = ops.spconv_mma(q, rb.nbr, rb.n_out, rb.n_out_dev, st["oc_p"], st["packed"], st["scale"], st["shift"], act_scale=act_scale,
+                               out_dtype=out_dtype, kmask=rb.kmask)
+            if st["oc_p"] != conv.out_channels:
+                y = y[:, :conv.out_channels].contiguous()
+            return _make_output(x, rb, y, conv.ndim)
         amax_ic = self.act_amax.to(f.device) if static else ops.absmax_cols(f, n_dev)
-        if static and self._cache is not None:
+        if self._cache is not None and (static or self.scaling_factor is None):
             s_dev, prep = self._cache
         else:
-            s = self.smoothing_scale(amax_ic)
+            s = self.smoothing_scale(amax_ic)                 # None for the scalar variant: the weights are prepared once
             s_dev = None if s is None else s.to(f.device).contiguous()
             prep = self._prepare(f.device, s)
-            if static:
-                self._cache = (s_dev, prep)
+            self._cache = (s_dev, prep)
         packed, ic_p, oc_p, w_scale, shift = prep
         q, act_scale = ops.quantize_rows(f, amax_ic.contiguous(), ops.QL_Q_CODES_PER_TENSOR, self.act_quant.num_bits, n_dev, smooth=s_dev)
         if ic_p != conv.in_channels:
             q = torch.nn.functional.pad(q, (0, ic_p - conv.in_channels)).contiguous()
-        out_dtype = torch.float32 if in_dtype == torch.float32 else torch.float16
         y = ops.spconv_mma(q, rb.nbr, rb.n_out, rb.n_out_dev, oc_p, packed, w_scale, shift, act_scale=act_scale, out_dtype=out_dtype, kmask=rb.kmask)
         if oc_p != conv.out_channels:
             y = y[:, :conv.out_channels].contiguous()

@@ -39,7 +39,9 @@ class SparseConvTensor:
             raise QlidarError("indices must be int32 (the reference passes voxel_coords.int(), spconv_backbone.py:258)")
         if _check and features.shape[0] != indices.shape[0]:
             raise QlidarError("features and indices disagree on the number of active sites")
-        self.features = features
+        self._features = features
+        self._features_as = None          # (dtype, cast copy): engine outputs are stored fp16 and surface in the caller's dtype on demand
+        self._surface_dtype = None
         self.indices = indices
         self.spatial_shape = [int(s) for s in spatial_shape]
         self.batch_size = int(batch_size)
@@ -52,6 +54,20 @@ class SparseConvTensor:
         self._n_dev: Optional[torch.Tensor] = None
 
     # ---- spconv API ----
+    @property
+    def features(self) -> torch.Tensor:
+        """The (N, C) feature rows.  A tensor published by the engine keeps its fp16 rows and converts to the caller's dtype
+        (the reference's fp32) the first time someone reads them -- CenterPoint never reads the multi-scale taps."""
+        if self._surface_dtype is None or self._features.dtype == self._surface_dtype:
+            return self._features
+        if self._features_as is None:
+            self._features_as = self._features.to(self._surface_dtype)
+        return self._features_as
+
+    @features.setter
+    def features(self, value: torch.Tensor):
+        self._features, self._features_as, self._surface_dtype = value, None, None
+
     @property
     def spatial_size(self):
         n = 1

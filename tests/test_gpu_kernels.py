@@ -650,3 +650,33 @@ def test_voxelize_phases_equal_the_single_call(ops):
     assert (out[0][:n] == -7.0).all()                                   # features untouched so far
     ops.voxelize_mean(p, c["pc_range"], c["voxel_size"], grid, 2, c["max_pts"], cap, out=out, workspace=ws, phase="features")
     assert torch.equal(out[0][:n], a[0][:n]) and torch.equal(out[2][:n], a[2][:n]) and torch.equal(out[1][:n], a[1][:n])
+
+
+# ------------------------------------------------------------------------------------------------ SmoothQuant weight preparation
+@pytest.mark.parametrize("cin,cout,K", [(16, 16, 27), (32, 64, 27), (64, 64, 27), (128, 128, 3), (256, 256, 9), (48, 32, 5)])
+def test_sq_prepare_weights_layout_and_codes(ops, cin, cout, K):
+    """ql_sq_prepare_weights writes the conv kernel's packed image: with act_absmax == the weights' own per-channel maxima and
+    alpha = 0.5 the smoothing scale is exactly 1 (a^0.5 / a^0.5), so the image must equal, byte for byte, ql_pack_weights_host of
+    the plain per-output-channel codes, and the scale amax_w / 127 * bn; with real activation maxima the codes equal the host
+    formula's up to the device's powf (<= 1 code step on a handful of weights)."""
+    rng = np.random.default_rng(cin + cout)
+    w = torch.from_numpy(rng.normal(size=(cout, K, cin)).astype(np.float32))
+    bn = torch.from_numpy(rng.uniform(0.5, 1.5, cout).astype(np.float32))
+    w_ic = w.abs().amax(dim=(0, 1))
+    smooth, packed, scale = ops.sq_prepare_weights(dev(w), dev(w_ic), dev(w_ic), 0.5, bn_scale=dev(bn))
+    assert torch.equal(smooth.cpu(), torch.ones(cin))
+    amax = w.abs().amax(dim=(1, 2))
+    codes = torch.round(w * (torch.full_like(amax, 127.0) / amax).view(-1, 1, 1)).clamp_(-127, 127).to(torch.int8)
+    assert torch.equal(packed.cpu(), ops.pack_weights(codes))
+    assert torch.equal(scale.cpu(), (amax / 127.0) * bn)
+    # real statistics: s = amax_x^a / amax_w^(1-a)
+    ax = torch.from_numpy(rng.uniform(0.1, 30.0, cin).astype(np.float32))
+    ax[3] = 0.0                                                               # a dead channel: s -> 1
+    smooth, packed, scale = ops.sq_prepare_weights(dev(w), dev(w_ic), dev(ax), 0.8)
+    s_ref = O.smoothquant_scale(ax, w.reshape(cout, K, 1, 1, cin), 0.8)
+    assert torch.allclose(smooth.cpu(), s_ref, rtol=2e-6) and smooth[3].item() == 1.0
+    ws = w * smooth.cpu().view(1, 1, -1)
+    amax2 = ws.abs().amax(dim=(1, 2))
+    codes2 = torch.round(ws * (torch.full_like(amax2, 127.0) / amax2).view(-1, 1, 1)).clamp_(-127, 127).to(torch.int8)
+    assert torch.equal(packed.cpu(), ops.pack_weights(codes2))                # same smoothing vector -> same image
+    assert torch.equal(scale.cpu(), amax2 / 127.0)

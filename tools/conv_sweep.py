@@ -11,7 +11,7 @@ import torch
 
 import bench
 
-KEYS = ("UNIT_SUBS", "SLOTS", "TEAMS", "STREAM", "MODE")
+KEYS = ("UNIT_SUBS", "SLOTS", "TEAMS", "STREAM", "MODE", "CTAS", "ACC")
 ROLES = {0: ("epilogue", ["wait_acc", "work"]), 1: ("producer", ["wait_desc", "gather", "wait_slot", "st+arrive"]),
          2: ("mma", ["wait_desc", "wait_acc", "wait_unit", "issue", "commit"]), 3: ("loader", ["wait_desc_free", "wait_slot", "work"])}
 
