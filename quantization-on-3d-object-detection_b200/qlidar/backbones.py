@@ -134,23 +134,30 @@ class _BackboneBase(nn.Module):
                 return False                                    # calibration / quantisers off: the eager tree collects the statistics
         return True
 
-    def _engine_for(self, batch_dict):
+    def _engine_for(self, batch_dict, stage_caps=None):
         from .engine import BackboneEngine
         from ._lib import QlidarError
         V, B = int(batch_dict['voxel_features'].shape[0]), int(batch_dict['batch_size'])
         sig = self._state_signature()
         st = getattr(self, "_engine_state", None)
-        if st is not None and st["sig"] == sig and st["B"] == B and V <= st["cap"] and st["bev"] == self.engine_bev_dtype:
+        if (stage_caps is None and st is not None and st["sig"] == sig and st["B"] == B and V <= st["cap"]
+                and st["bev"] == self.engine_bev_dtype):
             return st["eng"]
         cap = max(int(V * 1.25) + 1024, 0 if st is None else st["cap"])
-        ratio = 1.3 if st is None else st.get("ratio", 1.3)
+        if stage_caps is None and st is not None and st["sig"] == sig and st["B"] == B:
+            # the same model on a bigger input: scale the stage capacities learnt so far
+            stage_caps = [int(c * cap / st["cap"]) + 128 for c in st["eng_caps"]]
+        if stage_caps is not None:
+            stage_caps = [max(cap, stage_caps[0])] + list(stage_caps[1:])
+            cap = stage_caps[0]
+        self._engine_state = None                                   # release the old engine's buffers before allocating the new ones
         try:
-            eng = BackboneEngine(self, B, cap, stage_cap_ratio=ratio, bev=self.engine_bev_dtype is not None,
+            eng = BackboneEngine(self, B, cap, stage_cap_ratio=1.3, stage_caps=stage_caps, bev=self.engine_bev_dtype is not None,
                                  bev_dtype=self.engine_bev_dtype or torch.float16, device=batch_dict['voxel_features'].device)
         except QlidarError:
             self._engine_unsupported = True                     # a module tree the engine cannot schedule: the eager tree serves it
             return None
-        self._engine_state = dict(sig=sig, B=B, cap=cap, eng=eng, ratio=ratio, bev=self.engine_bev_dtype)
+        self._engine_state = dict(sig=sig, B=B, cap=cap, eng=eng, bev=self.engine_bev_dtype, eng_caps=[s.cap for s in eng.stages])
         return eng
 
     def _engine_forward(self, batch_dict):
@@ -158,15 +165,21 @@ class _BackboneBase(nn.Module):
         if eng is None:
             return None
         vf, vc = batch_dict['voxel_features'], batch_dict['voxel_coords']
-        for attempt in range(3):
+        for attempt in range(10):
             out = eng.forward_voxels(vf, vc)
             counts = torch.stack([st.n_dev for st in eng.stages]).cpu()         # the one synchronisation of the call
-            if not bool((counts[1:, 1] > counts[1:, 0]).any()):
+            over = (counts[:, 1] > counts[:, 0]).tolist()
+            if not any(over[1:]):
                 break
-            # a stage outgrew its capacity (denser scene than any before): enlarge and run again
-            self._engine_state["ratio"] *= 1.5
-            self._engine_state["sig"] = None
-            eng = self._engine_for(batch_dict)
+            # A stage outgrew its capacity (a denser scene than any before; 5^3 stride-2 convs multiply the site count by up to
+            # 5): size that stage from the number of sites FOUND, scale the later ones (they saw a truncated input) and run again.
+            first = over.index(True, 1)
+            caps = [s.cap for s in eng.stages]
+            grow = float(counts[first, 1]) / max(float(counts[first, 0]), 1.0) * 1.2
+            caps = caps[:first] + [int(c * grow) + 1024 for c in caps[first:]]
+            eng = self._engine_for(batch_dict, stage_caps=caps)
+        else:
+            raise RuntimeError("engine stage capacities did not converge")
         n = [int(v) for v in counts[:, 0].tolist()]
         B = int(batch_dict['batch_size'])
 

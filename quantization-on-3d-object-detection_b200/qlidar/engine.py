@@ -340,6 +340,8 @@ class BackboneEngine:
         # one strided-rulebook workspace per produced stage: its bitmap + prefix is that stage's rank index, used by the
         # submanifold rulebooks (and the BEV hand-off) that follow instead of a hash table
         for L in self.layers:
+            if L.kind == "merge":
+                continue                                          # its stage's rank index lives in the merge workspace (below)
             if not L.subm and self.stages[L.stage_out].rank is None:
                 gi = self.stages[L.stage_in].grid
                 w = z(ops.rulebook_strided_workspace_bytes(gi, L.ksize, L.stride, L.pad), dt=torch.uint8)
@@ -355,6 +357,10 @@ class BackboneEngine:
             so = self.stages[L.stage_out]
             if L.kind == "merge":
                 L.ws = z(int(ops.lib().ql_bev_merge2d_workspace_bytes(so.grid[0], so.grid[2], so.grid[3], so.cap, L.cout, ops.QL_F16)), dt=torch.uint8)
+                # the merge numbers its sites with the same bitmap + popcount prefix as a strided build (key (b*H + y)*W + x == the
+                # 3-D key with D = 1): that pair, at the head of its workspace, is the merged stage's rank index
+                n_words = (so.grid[0] * so.grid[2] * so.grid[3] + 31) // 32
+                so.rank = ops.RankIndex(L.ws, L.ws.data_ptr(), L.ws.data_ptr() + ((n_words * 4 + 255) & ~255), n_words)
             elif L.rb_key not in self.rulebooks:
                 K = int(np.prod(L.ksize))
                 self.rulebooks[L.rb_key] = z(ops.num_tiles(so.cap), K, ops.TILE_M, dt=torch.int32)

@@ -356,22 +356,21 @@ def test_second_backbone_w8a8_smoothquant_surgery():
 
 
 # ------------------------------------------------------------------------------------------------ VoxelNeXt (config 4)
-@pytest.mark.parametrize("quant", [None, (8, 8, False)])
-def test_voxelnext_backbone_module_path(quant):
-    """VoxelResBackBone8xVoxelNeXt (spconv_backbone_voxelnext.py:70-225) with the Waymo-large kernel sizes [5,5,3,3]: six 3-D
-    stages, stage-5/6 indices scaled onto the stage-4 grid, 2-D merge of duplicate (b,y,x) rows, SparseConv2d + SubMConv2d tail."""
+def _voxelnext_case(cfg, dataset, pc_range, batch, quant, **synth_kw):
     import qlidar
-    cfg = dict(SPCONV_KERNEL_SIZES=[5, 5, 3, 3], CHANNELS=[16, 32, 64, 128, 128], OUT_CHANNEL=128)
-    c = O.CONFIGS["kitti"]
-    pc_range = [0.0, -12.8, -3.0, 25.6, 12.8, 1.0]                     # 512 x 512 x 40 crop: keeps all six stage shapes non-trivial
-    pts = O.synth_batch("kitti", 2, n_az=500)
-    m = (pts[:, 1] >= 0) & (pts[:, 1] < 25.6) & (pts[:, 2] >= -12.8) & (pts[:, 2] < 12.8)
-    pts = pts[m]
+    c = O.CONFIGS[dataset]
+    pts = O.synth_batch(dataset, batch, **synth_kw)
+    if pc_range is None:
+        pc_range = c["pc_range"]
+    else:
+        m = (pts[:, 1] >= pc_range[0]) & (pts[:, 1] < pc_range[3]) & (pts[:, 2] >= pc_range[1]) & (pts[:, 2] < pc_range[4])
+        pts = pts[m]
     feats, coords, _ = O.voxelize_mean_batch(pts, pc_range, c["voxel_size"], c["max_pts"], c["max_voxels"])
     grid = O.grid_size_xyz(pc_range, c["voxel_size"])
-    prog = O.backbone_specs("VoxelResBackBone8xVoxelNeXt", 4, cfg["CHANNELS"], cfg["SPCONV_KERNEL_SIZES"], cfg["OUT_CHANNEL"])
+    nfeat = c["nfeat"]
+    prog = O.backbone_specs("VoxelResBackBone8xVoxelNeXt", nfeat, cfg["CHANNELS"], cfg["SPCONV_KERNEL_SIZES"], cfg["OUT_CHANNEL"])
     P = O.init_params(prog)
-    bb = qlidar.VoxelResBackBone8xVoxelNeXt(cfg, 4, np.asarray(grid))
+    bb = qlidar.VoxelResBackBone8xVoxelNeXt(cfg, nfeat, np.asarray(grid))
     sd = {k: (v.reshape(v.shape[0], *v.shape[2:]) if k in ("conv_out.0.weight", "shared_conv.0.weight") else v) for k, v in P.items()}
     missing, unexpected = bb.load_state_dict(sd, strict=False)
     assert not unexpected and all(k.endswith("num_batches_tracked") for k in missing), (missing, unexpected)
@@ -383,16 +382,51 @@ def test_voxelnext_backbone_module_path(quant):
         no_list = ("conv_input.0", "conv_out.0", "shared_conv.0")                      # the 2-D tail is not a 3-D conv: not swapped
         qc = O.QuantCfg(mode="ref", w_bits=w_bits, act_bits=act_bits, cw=cw, no_list=no_list)
         assert sum(isinstance(mm, qlidar.QConvNd) for mm in bb.modules()) == 5 * 5 + 4
-    ref, taps = O.backbone_forward(prog, P, torch.from_numpy(feats), coords, O.sparse_shape_zyx(grid), 2, qc)
+    ref, taps = O.backbone_forward(prog, P, torch.from_numpy(feats), coords, O.sparse_shape_zyx(grid), batch, qc)
+    return bb, feats, coords, ref, taps
+
+
+def _check_voxelnext(bb, feats, coords, batch, ref, taps, a8, use_engine):
+    bb.use_engine = use_engine
     with torch.no_grad():
-        out = bb(batch_dict(torch.from_numpy(feats), coords, 2))
+        for _ in range(2 if use_engine else 1):                                         # the second call replays the captured graph
+            out = bb(batch_dict(torch.from_numpy(feats), coords, batch))
+    assert (getattr(bb, "_engine_state", None) is not None) == use_engine
     enc = out["encoded_spconv_tensor"]
     got_idx = enc.indices.cpu().numpy()
     assert np.array_equal(got_idx, ref.coords[:, [0, 2, 3]])                            # 2-D indices [b, y, x], same (sorted) order
-    check_feats(enc.features, ref.features, quant is not None)
+    assert list(enc.spatial_shape) == list(ref.spatial_shape[1:])
+    check_feats(enc.features, ref.features, a8)
     assert out["encoded_spconv_tensor_stride"] == 8
     for k in ("x_conv1", "x_conv2", "x_conv3"):
-        assert np.array_equal(out["multi_scale_3d_features"][k].indices.cpu().numpy(), taps[k].coords)
+        t = taps[k]
+        o = np.argsort(O._lin(t.coords, t.spatial_shape), kind="stable") if use_engine else np.arange(t.coords.shape[0])
+        assert np.array_equal(out["multi_scale_3d_features"][k].indices.cpu().numpy(), t.coords[o])
+        check_feats(out["multi_scale_3d_features"][k].features, t.features[torch.from_numpy(o)], a8)
+
+
+@pytest.mark.parametrize("use_engine", [True, False])
+@pytest.mark.parametrize("quant", [None, (8, 8, False)])
+def test_voxelnext_backbone_module_path(quant, use_engine):
+    """VoxelResBackBone8xVoxelNeXt (spconv_backbone_voxelnext.py:70-225) with the Waymo-large kernel sizes [5,5,3,3]: six 3-D
+    stages, stage-5/6 indices scaled onto the stage-4 grid, 2-D merge of duplicate (b,y,x) rows, SparseConv2d + SubMConv2d tail --
+    through the plugin call, engine (graph replay) and eager tree."""
+    cfg = dict(SPCONV_KERNEL_SIZES=[5, 5, 3, 3], CHANNELS=[16, 32, 64, 128, 128], OUT_CHANNEL=128)
+    pc_range = [0.0, -12.8, -3.0, 25.6, 12.8, 1.0]                     # 512 x 512 x 40 crop: keeps all six stage shapes non-trivial
+    bb, feats, coords, ref, taps = _voxelnext_case(cfg, "kitti", pc_range, 2, quant, n_az=500)
+    _check_voxelnext(bb, feats, coords, 2, ref, taps, quant is not None, use_engine)
+
+
+@pytest.mark.parametrize("quant", [(8, 16, True), (8, 8, False)])
+def test_voxelnext_waymo_large_through_the_engine(quant):
+    """BASELINE config 4 at its real shape: waymo_models/voxelnext_ioubranch_large.yaml:13-16 -- CHANNELS [32, 64, 128, 256, 256],
+    SPCONV_KERNEL_SIZES [5, 5, 3, 3], OUT_CHANNEL 256 -- on the full Waymo grid [41, 1504, 1504] (a thinned frame so that the CPU
+    oracle finishes in seconds): 5^3 strided rulebooks (K = 125), 512-byte rows (C = 256), the three-stage 2-D merge and the 2-D
+    tail, all inside one graph replay behind the plugin call."""
+    cfg = dict(SPCONV_KERNEL_SIZES=[5, 5, 3, 3], CHANNELS=[32, 64, 128, 256, 256], OUT_CHANNEL=256)
+    bb, feats, coords, ref, taps = _voxelnext_case(cfg, "waymo", None, 1, quant, n_beams=20, n_az=500)
+    assert feats.shape[0] > 5000 and ref.coords.shape[0] > 500
+    _check_voxelnext(bb, feats, coords, 1, ref, taps, quant[1] <= 8, True)
 
 
 def test_engine_static_calibration_fuses_requantisation():

@@ -680,3 +680,40 @@ def test_sq_prepare_weights_layout_and_codes(ops, cin, cout, K):
     codes2 = torch.round(ws * (torch.full_like(amax2, 127.0) / amax2).view(-1, 1, 1)).clamp_(-127, 127).to(torch.int8)
     assert torch.equal(packed.cpu(), ops.pack_weights(codes2))                # same smoothing vector -> same image
     assert torch.equal(scale.cpu(), amax2 / 127.0)
+
+
+def test_bev_merge2d_multi_equals_concat_then_merge(ops):
+    """ql_bev_merge2d_multi (VoxelNeXt: stages 4 / 5 / 6 merged in one pass, coarser stages scaled onto the target grid) == the
+    oracle's concat -> drop z -> unique -> index_add_ (spconv_backbone_voxelnext.py:149-164,194-199); device-side counts, 4-column
+    output coordinates, and the bitmap + prefix it leaves serve as the merged stage's rank index."""
+    rng = np.random.default_rng(91)
+    B, H, W, C = 2, 48, 40, 32
+    segs_np, scales = [], [1, 2, 4]
+    for sc in scales:
+        cs = random_coords(rng, B, 3, H // sc, W // sc, 0.15)
+        f = rng.normal(size=(cs.shape[0] + 17, C)).astype(np.float32)
+        segs_np.append((f, cs))
+    cat_f = torch.cat([torch.from_numpy(f[:c.shape[0]]).half().float() for f, c in segs_np])
+    cat_c = np.concatenate([np.concatenate([c[:, :2], c[:, 2:] * sc], axis=1) for (f, c), sc in zip(segs_np, scales)])
+    ref_f, ref_c = O.bev_merge2d(cat_f, cat_c)
+    segs = []
+    for (f, c), sc in zip(segs_np, scales):
+        cc = torch.zeros((f.shape[0], 4), dtype=torch.int32, device="cuda")
+        cc[:c.shape[0]] = dev(c)
+        segs.append((dev(torch.from_numpy(f).half()), cc, torch.tensor([c.shape[0], c.shape[0]], dtype=torch.int32, device="cuda"), sc))
+    cap = ref_c.shape[0] + 9
+    out_f = ops.zero_led_rows(cap, C)
+    out_c = torch.zeros((cap, 4), dtype=torch.int32, device="cuda")
+    n_out = torch.zeros(2, dtype=torch.int32, device="cuda")
+    ws = torch.zeros(int(ops.lib().ql_bev_merge2d_workspace_bytes(B, H, W, cap, C, ops.QL_F16)), dtype=torch.uint8, device="cuda")
+    ops.bev_merge2d_multi(segs, (B, H, W), cap, out_f, out_c, n_out, ws)
+    n = ref_c.shape[0]
+    assert n_out.tolist() == [n, n]
+    got_c = out_c[:n].cpu().numpy()
+    assert np.array_equal(got_c[:, [0, 2, 3]], ref_c) and (got_c[:, 1] == 0).all()
+    assert (out_f[:n].float().cpu() - ref_f).abs().max().item() <= 2e-3 * ref_f.abs().max().item()
+    # rank index left in the workspace: a submanifold 2-D rulebook through it == the oracle's
+    n_words = (B * H * W + 31) // 32
+    index = ops.RankIndex(ws, ws.data_ptr(), ws.data_ptr() + ((n_words * 4 + 255) & ~255), n_words)
+    nbr, km = ops.rulebook_subm_ranked(out_c, n_out, (B, 1, H, W), (1, 3, 3), index)
+    assert np.array_equal(dense_nbr(ops, nbr, km, n), O.rulebook_subm(got_c, [1, H, W], (1, 3, 3)))
