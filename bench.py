@@ -1,14 +1,23 @@
 #!/usr/bin/env python
-"""bench.py -- CenterPoint 3-D-backbone frames/s on B200 (BASELINE.json metric), one JSON line on stdout.
+"""bench.py -- 3-D-backbone frames/s on B200 (BASELINE.json metric), one JSON line on stdout.
 
-Workload (BASELINE.json configs[1]): CenterPoint Waymo VoxelResBackBone8x, W8A16 "progressive" quantisation
-(QConvNd(w_bits=8, act_bits=16, cw=True) on every backbone conv except conv_input.0, as quant_centerpoint.quant with
-sq=True), batch 4 synthetic ~146k-voxel frames per GPU.  One step = voxelize+meanVFE -> 9 rulebooks -> 21 fused convs ->
-BEV densify for one batch.  N GPUs = N independent frame shards (rank r takes frames r::N, pcdet/datasets/__init__.py:45-49),
-no collective on the hot path; NCCL only gathers the per-rank stage counts ("detections" placeholder) after timing.
+Default workload (BASELINE.json configs[1], the one the metric is quoted on): CenterPoint Waymo VoxelResBackBone8x, W8A16
+"progressive" quantisation (QConvNd(w_bits=8, act_bits=16, cw=True) on every backbone conv except conv_input.0, as
+quant_centerpoint.quant with sq=True), batch 4 synthetic ~146k-voxel frames per GPU.  One step = voxelize+meanVFE -> 9 rulebooks
+-> 21 fused convs -> BEV densify for one batch.  --config N selects BASELINE.json's other configurations (1-based):
+  1  CenterPoint KITTI geometry, VoxelResBackBone8x, the repo's INT8 mode QConvNd(8, 8, cw=True), 1 frame (~21 k voxels)
+  2  (default) CenterPoint Waymo W8A16, batch 4
+  3  SECOND sparse middle extractor (VoxelBackBone8x) W8A8 with SmoothQuant (SQConv3d, alpha 0.5), KITTI-shaped frames, batch 4
+  4  VoxelNeXt Waymo-large backbone (CHANNELS [32,64,128,256,256], kernels [5,5,3,3]) INT8 QConvNd(8, 8, cw=False), batch 2
+N GPUs = N independent frame shards (rank r takes frames r::N, pcdet/datasets/__init__.py:45-49), no collective on the hot path;
+NCCL only gathers per-frame result blocks after timing.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]              our arm (CUDA, C ABI)
-  python bench.py --impl reference [--steps K] [--warmup W]         the reference's CPU path (oracle port) on the host cores
+`value` times the engine with the points resident in HBM; `e2e` goes through the reference-facing plugin calls --
+VoxelizeMeanVFE(batch_dict) -> backbone(batch_dict) -> HeightCompression(batch_dict) -- from pinned HOST points, H2D inside the
+timed region, and reads the encoded sparse tensor (features + indices) back to the host every step.
+
+  python bench.py [--config C] [--gpus N] [--steps K] [--warmup W]      our arm (CUDA, C ABI)
+  python bench.py --impl reference [--config C] [--steps K] [--warmup W] the reference's CPU path (oracle port) on the host cores
 """
 from __future__ import annotations
 
@@ -27,19 +36,45 @@ import numpy as np
 import torch
 
 METRIC = "centerpoint_3d_backbone_frames_per_sec"
-BATCH = 4
-W_BITS, ACT_BITS, CW = 8, 16, True
 NO_LIST = ["conv_input.0"]                     # quant/quant_centerpoint.py:24-26 (backbone_no_list, module-relative path)
-WORKLOAD = "centerpoint_waymo_voxelresbackbone8x_w8a16_batch4_synthetic_146k_voxel_frames"
+# BASELINE.json configs (1-based).  quant: ("q", w_bits, act_bits, cw) = q_conv3d / QConvNd;  ("sq", alpha) = sq_conv3d / SQConv3d
+WORKLOADS = {
+    1: dict(workload="centerpoint_kitti_voxelresbackbone8x_w8a8cw_1_synthetic_21k_voxel_frame", dataset="kitti", arch="VoxelResBackBone8x",
+            cfg={}, quant=("q", 8, 8, True), batch=1, synth=dict(n_az=2000), metric="centerpoint_3d_backbone_frames_per_sec",
+            dtype="int8-code activations (per input channel) x int8-code weights as exact fp16, fp32 accumulate (W8A8-cw)",
+            quant_txt="QConvNd(w_bits=8, act_bits=8, cw=True), conv_input.0 unquantised (quant_centerpoint.quant, sq=True)"),
+    2: dict(workload="centerpoint_waymo_voxelresbackbone8x_w8a16_batch4_synthetic_146k_voxel_frames", dataset="waymo", arch="VoxelResBackBone8x",
+            cfg={}, quant=("q", 8, 16, True), batch=4, synth={}, metric="centerpoint_3d_backbone_frames_per_sec",
+            dtype="f16 activations x int8-code weights, fp32 accumulate (W8A16)",
+            quant_txt="QConvNd(w_bits=8, act_bits=16, cw=True), conv_input.0 unquantised"),
+    3: dict(workload="second_kitti_voxelbackbone8x_w8a8_smoothquant_batch4_synthetic_21k_voxel_frames", dataset="kitti", arch="VoxelBackBone8x",
+            cfg={}, quant=("sq", 0.5), batch=4, synth=dict(n_az=2000), metric="second_3d_backbone_frames_per_sec",
+            dtype="int8 x int8 -> int32 (W8A8, SmoothQuant per input channel, dynamic)",
+            quant_txt="SQConv3d(scaling_factor=0.5) on every conv but conv_input.0 (quant_second.py no_list)"),
+    4: dict(workload="voxelnext_waymo_large_backbone_w8a8_batch2_synthetic_146k_voxel_frames", dataset="waymo", arch="VoxelResBackBone8xVoxelNeXt",
+            cfg=dict(SPCONV_KERNEL_SIZES=[5, 5, 3, 3], CHANNELS=[32, 64, 128, 256, 256], OUT_CHANNEL=256), quant=("q", 8, 8, False), batch=2,
+            synth={}, metric="voxelnext_3d_backbone_frames_per_sec", dtype="int8 x int8 -> int32 (W8A8 per tensor)",
+            quant_txt="QConvNd(w_bits=8, act_bits=8, cw=False) on the 3-D convs but conv_input.0; 2-D tail fp16 (waymo_models/voxelnext_ioubranch_large.yaml:13-16)"),
+}
+# module-level view of the selected workload (tools/ import these)
+W = WORKLOADS[2]
+BATCH = W["batch"]
+WORKLOAD = W["workload"]
+
+
+def select(config: int):
+    global W, BATCH, WORKLOAD, METRIC
+    W = WORKLOADS[config]
+    BATCH, WORKLOAD, METRIC = W["batch"], W["workload"], W["metric"]
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def make_batch(first_seed: int, batch: int = BATCH) -> np.ndarray:
+def make_batch(first_seed: int, batch: int = None) -> np.ndarray:
     from qlidar import synth
-    return synth.synth_batch("waymo", batch, first_seed=first_seed)
+    return synth.synth_batch(W["dataset"], BATCH if batch is None else batch, first_seed=first_seed, **W["synth"])
 
 
 def peaks():
@@ -141,31 +176,71 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------- our arm
-def build_engine(device, max_points, w_bits=None, act_bits=None, cw=None):
+def build_backbone(device, quant=None):
+    """The selected workload's backbone with random-init weights / BN statistics and its quantisation surgery."""
     import qlidar
-    w_bits = W_BITS if w_bits is None else w_bits
-    act_bits = ACT_BITS if act_bits is None else act_bits
-    cw = CW if cw is None else cw
     from qlidar import synth
-    c = synth.CONFIGS["waymo"]
+    c = synth.CONFIGS[W["dataset"]]
     r = np.asarray(c["pc_range"], dtype=np.float64)
     grid = np.round((r[3:6] - r[0:3]) / np.asarray(c["voxel_size"], dtype=np.float64)).astype(np.int64)
     torch.manual_seed(4)                                      # the reference's seed (quant_centerpoint.py:174)
-    bb = qlidar.VoxelResBackBone8x({}, c["nfeat"], grid)
+    bb = getattr(qlidar, W["arch"])(dict(W["cfg"]), c["nfeat"], grid)
     with torch.no_grad():                                     # random-init BN statistics per SURVEY.md 8d
         for m in bb.modules():
             if isinstance(m, torch.nn.BatchNorm1d):
                 m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.1); m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
     bb = bb.to(device).eval()
-    qlidar.q_conv3d(bb, {}, "", w_bits, act_bits, cw, (qlidar.SubMConv3d, qlidar.SparseConv3d), NO_LIST)
-    # every frame is capped at MAX_NUMBER_OF_VOXELS = 150 000 voxels in first-touch order like the reference's per-frame CPU
-    # voxeliser (waymo_dataset.yaml:79-84; the synthetic frames hold 98 k - 160 k voxels depending on the seed), so the batch
-    # capacity BATCH * 150 000 can never overflow
+    quant = W["quant"] if quant is None else quant
+    src = (qlidar.SubMConv3d, qlidar.SparseConv3d)
+    if quant[0] == "q":
+        qlidar.q_conv3d(bb, {}, "", quant[1], quant[2], quant[3], src, NO_LIST)
+    elif quant[0] == "sq":
+        qlidar.sq_conv3d(bb, {}, "", quant[1], 8, 8, src, NO_LIST)
+    return bb, c
+
+
+def stage_caps_for(cap):
+    # 5^3 stride-2 convs (VoxelNeXt-large) multiply the active sites ~4x at stage 2; the 8x backbones stay below 1.25x
+    if W["arch"] == "VoxelResBackBone8xVoxelNeXt":
+        return [cap, int(4.5 * cap), int(3.0 * cap), int(1.0 * cap), int(0.4 * cap), int(0.15 * cap)]
+    return [cap, int(1.25 * cap), int(0.75 * cap), int(0.5 * cap), int(0.5 * cap)]
+
+
+def build_engine(device, max_points, w_bits=None, act_bits=None, cw=None, bb=None):
+    import qlidar
+    quant = None if w_bits is None else ("q", w_bits, act_bits, cw)
+    c = None
+    if bb is None:
+        bb, c = build_backbone(device, quant)
+    else:
+        from qlidar import synth
+        c = synth.CONFIGS[W["dataset"]]
+    # every frame is capped at MAX_NUMBER_OF_VOXELS voxels in first-touch order like the reference's per-frame CPU voxeliser
+    # (waymo_dataset.yaml:79-84: 150 000; kitti_dataset.yaml:65-70: 40 000), so the batch capacity can never overflow
     cap = BATCH * c["max_voxels"]
     eng = qlidar.BackboneEngine(bb, BATCH, cap, max_points=max_points, pc_range=c["pc_range"], voxel_size=c["voxel_size"],
                                 max_pts_per_voxel=c["max_pts"], use_graph=True, device=device, max_voxels_per_frame=c["max_voxels"],
-                                stage_caps=[cap, int(1.25 * cap), int(0.75 * cap), int(0.5 * cap), int(0.5 * cap)], **ENGINE_KW)
+                                stage_caps=stage_caps_for(cap), **ENGINE_KW)
     return eng, bb
+
+
+def timed_steps(eng, steps, flush, world, dist, sampler=None):
+    """K graph replays, L2 flushed before each, CUDA events per step on the launching stream; returns the per-step milliseconds."""
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if sampler is not None:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        flush()
+        ev[i][0].record()
+        eng.forward_points()
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    return [a.elapsed_time(b) for a, b in ev]
 
 
 def run_ours(args):
@@ -177,18 +252,25 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    try:                                                      # one rank per GPU: keep each on the cores next to its GPU when the OS says which
+        n_cpu = os.cpu_count() or 1
+        if world > 1 and hasattr(os, "sched_setaffinity") and n_cpu >= 2 * world:
+            per = n_cpu // world
+            os.sched_setaffinity(0, set(range(local * per, (local + 1) * per)))
+    except OSError:
+        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from qlidar import ops
+    import qlidar
+    from qlidar import ops, shard
 
     # frames r::N of the job's N*BATCH frames (pcdet/datasets/__init__.py:40-50 via qlidar.shard): frame f has seed 1000 + f
-    from qlidar import shard
     my_frames = shard.frames_for_rank(world * BATCH, rank, world)
     pts_np = np.concatenate([np.concatenate([np.full((f.shape[0], 1), i, np.float32), f[:, 1:]], axis=1)
                              for i, f in enumerate(make_batch(1000 + fr, 1) for fr in my_frames)])
     P = pts_np.shape[0]
     host_pts = [torch.from_numpy(pts_np).pin_memory(), torch.from_numpy(pts_np.copy()).pin_memory()]
-    eng, _ = build_engine(dev, P)
+    eng, bb = build_engine(dev, P)
     eng.set_points(host_pts[0])
     flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
@@ -206,36 +288,59 @@ def run_ours(args):
 
     # ---- timed region A: device-resident inputs, K steps, L2 flushed between steps, CUDA events per step ----
     sampler = ClockSampler(local)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for i in range(args.steps):
-        flush()
-        ev[i][0].record()
-        eng.forward_points()
-        ev[i][1].record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    step_ms = timed_steps(eng, args.steps, flush, world, dist, sampler)
     clocks = sampler.stop()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
     t = torch.tensor([total_ms], device=dev)
+    all_ms = [total_ms]
     if world > 1:
+        gather = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gather, t)
+        all_ms = [float(g.item()) for g in gather]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     value = world * BATCH * args.steps / (total_ms_max / 1e3)
 
-    # ---- timed region B (e2e): pinned host points -> H2D -> step -> D2H of the stage counts, double buffered ----
+    # ---- timed region B (e2e): the reference-facing plugin calls on HOST points.  Per step: pinned host points -> H2D (copy stream,
+    #      double buffered) -> VoxelizeMeanVFE(batch_dict) -> backbone(batch_dict) [-> HeightCompression(batch_dict)] -> the encoded
+    #      sparse tensor (fp16 feature rows + int32 indices) D2H into pinned host buffers (copy stream).  The plugins are attached,
+    #      so the three calls replay ONE graph; the backbone call's read-back of the stage counts is the step's only host sync. ----
+    del eng
+    torch.cuda.empty_cache()
+    c = qlidar.synth.CONFIGS[W["dataset"]]
+    vfe = qlidar.VoxelizeMeanVFE({}, c["nfeat"], c["voxel_size"], c["pc_range"], c["max_pts"], c["max_voxels"]).attach(bb)
+    has_bev = W["arch"] != "VoxelResBackBone8xVoxelNeXt"
+    hc = qlidar.HeightCompression(qlidar.Cfg(NUM_BEV_FEATURES=256)).attach(bb, torch.float16) if has_bev else None
     copy_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream()
     stage_in = [torch.empty((P, pts_np.shape[1]), dtype=torch.float32, device=dev) for _ in range(2)]
-    counts_dev = torch.zeros((len(eng.stages), 2), dtype=torch.int32, device=dev)
-    counts_host = torch.zeros((len(eng.stages), 2), dtype=torch.int32).pin_memory()
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
+    produced = [torch.cuda.Event() for _ in range(2)]
+    drained = [torch.cuda.Event() for _ in range(2)]
+
+    def plugin_step(points_dev):
+        bd = {"points": points_dev, "batch_size": BATCH}
+        with torch.no_grad():
+            bd = bb(vfe(bd))
+            if hc is not None:
+                bd = hc(bd)
+        return bd
+
+    bd = plugin_step(stage_in[0].copy_(host_pts[0]))           # builds the engine behind the plugin call
+    for _ in range(2):
+        bd = plugin_step(stage_in[0])
+    torch.cuda.synchronize()
+    enc = bd["encoded_spconv_tensor"]
+    n_enc, c_enc, idx_cols = enc._features.shape[0], enc._features.shape[1], enc.indices.shape[1]
+    assert n_enc == counts[-1], (n_enc, counts)
+    cap_enc = bb._engine_state["eng"].stages[-1].cap
+    host_feats = [torch.empty((cap_enc, c_enc), dtype=torch.float16).pin_memory() for _ in range(2)]
+    host_idx = [torch.empty((cap_enc, idx_cols), dtype=torch.int32).pin_memory() for _ in range(2)]
+    # the engine owns ONE set of output buffers: a step's result is moved aside on the device (a ~10 us copy) so that its D2H can
+    # overlap the next step's compute
+    out_feats = [torch.empty((cap_enc, c_enc), dtype=torch.float16, device=dev) for _ in range(2)]
+    out_idx = [torch.empty((cap_enc, idx_cols), dtype=torch.int32, device=dev) for _ in range(2)]
     e2e_steps = args.steps
 
     def h2d(i):
@@ -244,24 +349,34 @@ def run_ours(args):
             stage_in[i & 1].copy_(host_pts[i & 1], non_blocking=True)
             copied[i & 1].record(copy_stream)
 
-    for e in consumed:
+    for e in consumed + drained:
         e.record(main)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record(main)
     h2d(0)
+    d2h_bytes = 0
     for i in range(e2e_steps):
         if i + 1 < e2e_steps:
-            h2d(i + 1)                                         # overlaps the previous step's compute
+            h2d(i + 1)                                         # overlaps this step's compute
         main.wait_event(copied[i & 1])
-        eng.points[:P].copy_(stage_in[i & 1], non_blocking=True)   # device-side hand-off into the graph's static input
+        bd = plugin_step(stage_in[i & 1])
         consumed[i & 1].record(main)
-        eng.forward_points()
-        torch.stack([st.n_dev for st in eng.stages], out=counts_dev)
-        counts_host.copy_(counts_dev, non_blocking=True)       # the step's host-visible result
+        enc = bd["encoded_spconv_tensor"]
+        n = enc._features.shape[0]
+        main.wait_event(drained[i & 1])                        # the side buffers of two steps ago have reached the host
+        out_feats[i & 1][:n].copy_(enc._features, non_blocking=True)
+        out_idx[i & 1][:n].copy_(enc.indices, non_blocking=True)
+        produced[i & 1].record(main)
+        with torch.cuda.stream(copy_stream):                   # the step's host-visible result
+            copy_stream.wait_event(produced[i & 1])
+            host_feats[i & 1][:n].copy_(out_feats[i & 1][:n], non_blocking=True)
+            host_idx[i & 1][:n].copy_(out_idx[i & 1][:n], non_blocking=True)
+            drained[i & 1].record(copy_stream)
+        d2h_bytes = n * c_enc * 2 + n * idx_cols * 4
+    copy_stream.synchronize()
     e_end.record(main)
     torch.cuda.synchronize()
     if world > 1:
@@ -270,15 +385,21 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * BATCH * e2e_steps / (float(e2e_ms.item()) / 1e3)
-    assert counts_host[:, 0].tolist() == counts, "e2e path disagrees with the device-resident path"
+    last = (e2e_steps - 1) & 1
+    assert torch.equal(host_idx[last][:n_enc], enc.indices.cpu()) and host_feats[last][:n_enc].abs().sum().item() > 0, "e2e read-back is empty / wrong"
+    eng = bb._engine_state["eng"]
+    assert eng.counts() == counts, "the plugin-call path disagrees with the device-resident path"
 
-    # ---- NCCL only gathers detections (here: per-rank stage counts) after the timed regions ----
+    # ---- NCCL only gathers per-frame results after the timed regions: one fixed-shape block per frame (its rows of the encoded
+    #      tensor's per-channel sums + site count stand in for padded detections), merged back into dataset order ----
     gathered = None
     if world > 1:
-        # one fixed-shape block per frame of this rank (here the batch's stage counts stand in for padded detections),
-        # merged back into dataset order: common_utils.py:229-250 without the pickle files
-        mine = counts_dev.flatten().to(torch.float32).unsqueeze(0).repeat(BATCH, 1).contiguous()
-        gathered = shard.gather_frame_results(mine, world * BATCH)[:world].to(torch.int64).cpu().tolist()   # frame r belongs to rank r
+        f32 = enc._features.float()
+        b_idx = enc.indices[:, 0].long()
+        mine = torch.zeros((BATCH, c_enc + 1), dtype=torch.float32, device=dev)
+        mine[:, :c_enc].index_add_(0, b_idx, f32)
+        mine[:, c_enc] = torch.bincount(b_idx, minlength=BATCH).float()
+        gathered = shard.gather_frame_results(mine.contiguous(), world * BATCH)[:, c_enc].to(torch.int64).cpu().tolist()   # sites per frame, dataset order
 
     if rank != 0:
         if world > 1:
@@ -287,8 +408,10 @@ def run_ours(args):
 
     # ---- per-kernel accounting (rank 0): eager pass, CUDA events around every op on the launching stream ----
     pk = peaks()
+    eng.set_points(host_pts[0])
     times = eng.profile_ops(from_points=True, iters=5, flush=flush)
-    acct = {a["name"]: a for a in eng.layer_accounting()}
+    acct_list = eng.layer_accounting()
+    acct = {a["name"]: a for a in acct_list}
     conv_ms = {k.split(":", 1)[1]: v for k, v in times.items() if k.startswith("conv:")}
     conv_bytes = sum(acct[n]["bytes_alg"] for n in conv_ms)
     conv_flops = sum(acct[n]["flops_alg"] for n in conv_ms)
@@ -298,118 +421,128 @@ def run_ours(args):
         g = k.split(":")[0]
         groups[g] = groups.get(g, 0.0) + v
     eager_total = sum(times.values())
-    n0, P_in = counts[0], P
-    F = eng.nfeat
-    vox_bytes = P_in * (F + 1) * 4 + n0 * F * 4 + n0 * 16
-    last = eng.stages[-1]
-    bev_bytes = counts[-1] * 128 * 2 + int(np.prod(eng.spatial_features.shape)) * 2
-    rb_bytes = 0
-    for L in eng.layers:
-        pass
-    stage_gbs = {
-        "voxelize_mean": vox_bytes / (times["voxelize_mean"] / 1e3) / 1e9,
-        "bev_densify": bev_bytes / (times["bev_densify"] / 1e3) / 1e9,
-        "spconv_mma_all_layers": conv_bytes / conv_t / 1e9,
-    }
+    n0, F = counts[0], eng.nfeat
+    vox_bytes = P * (F + 1) * 4 + n0 * F * 4 + n0 * 16
+    stage_bytes = {"voxelize_mean": vox_bytes}
+    if eng.bev:
+        stage_bytes["bev_densify"] = counts[-1] * eng.layers[-1].cout * 2 + int(np.prod(eng.spatial_features.shape)) * eng.spatial_features.element_size()
+    # hash / rulebook stages: subm N*16 + 4*P, strided N_in*16 + N_out*16 + 4*P; renumbering: coordinates + feature rows in
+    # and out + the stage's bitmap (read twice: popcount, prefix) and prefix array
+    rb_sub = rb_str = 0
+    seen = set()
+    by_name = {L.name: L for L in eng.layers}
+    for a in acct_list:
+        L = by_name[a["name"]]
+        if L.rb_key in seen:
+            continue
+        seen.add(L.rb_key)
+        if L.subm:
+            rb_sub += a["n_out"] * 16 + 4 * a["pairs"]
+        else:
+            rb_str += a["n_in"] * 16 + a["n_out"] * 16 + 4 * a["pairs"]
+    stage_bytes["rulebook_subm"], stage_bytes["rulebook_strided"] = rb_sub, rb_str
+    if eng.sort_stage1:
+        cells = int(np.prod(eng.stages[0].grid))
+        stage_bytes["sort_stage1"] = n0 * (16 + 32) * 2 + n0 * 4 + (cells // 8) * 3
+    stage_bytes["spconv_mma_all_layers"] = conv_bytes
+    stage_t = dict(groups)
+    stage_t["spconv_mma_all_layers"] = conv_t * 1e3
+    stage_gbs = {k: v / (stage_t[k] / 1e3) / 1e9 for k, v in stage_bytes.items() if k in stage_t and stage_t[k] > 0}
     per_layer = [dict(name=n, ms=round(conv_ms[n], 4), gbs=round(acct[n]["bytes_alg"] / (conv_ms[n] / 1e3) / 1e9, 1),
                       tflops=round(acct[n]["flops_alg"] / (conv_ms[n] / 1e3) / 1e12, 2), cin=acct[n]["cin"], cout=acct[n]["cout"],
-                      n_out=acct[n]["n_out"], pairs=acct[n]["pairs"]) for n in conv_ms]
-    # measured DRAM traffic of the same 20 launches from the committed ncu capture (profiles/, not measured in this run)
-    traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
-    if os.path.exists(tp):
+                      n_out=acct[n]["n_out"], pairs=acct[n]["pairs"], live_slabs_per_tile=round(acct[n]["live_slabs"] / max(acct[n]["tiles"], 1), 2))
+                 for n in conv_ms]
+    # measured DRAM traffic of the conv launches from the committed ncu capture of the SAME command (profiles/, not measured in this run)
+    traffic, traffic_src, traffic_rw = None, None, None
+    tp = os.path.join(ROOT, "profiles", "r02_conv_traffic.json")
+    if args.config == 2 and os.path.exists(tp):
         tj = json.load(open(tp))
-        traffic, traffic_src = int(tj["traffic_bytes_per_step"]), "profiles/r01_conv_traffic.json (ncu --set full, dram__bytes_read+write over the 20 launches)"
-    roofline = {"kernel": "k_spconv_ts<f16> (the 20 tcgen05 sparse-conv launches of one step, aggregated)", "bound": "hbm",
+        traffic = int(tj["traffic_bytes_per_step"])
+        traffic_rw = {"read": int(tj["dram_read_bytes_per_step"]), "write": int(tj["dram_write_bytes_per_step"])}
+        traffic_src = "profiles/r02_conv_traffic.json (ncu --set full, dram__bytes_read + dram__bytes_write over the conv launches of one step)"
+    roofline = {"kernel": "k_spconv_ts (the tcgen05 sparse-conv launches of one step, aggregated)", "bound": "hbm",
                 "achieved": round(conv_bytes / conv_t / 1e9, 1), "peak": pk["hbm"], "unit": "GB/s",
-                "frac": round(conv_bytes / conv_t / 1e9 / pk["hbm"], 4), "traffic": traffic, "traffic_source": traffic_src,
+                "frac": round(conv_bytes / conv_t / 1e9 / pk["hbm"], 4), "traffic": traffic, "traffic_read_write": traffic_rw, "traffic_source": traffic_src,
                 "peak_source": pk["src"],
                 "alg_bytes_per_step": conv_bytes, "kernel_ms_per_step": round(conv_t * 1e3, 3),
                 "share_of_step": round(conv_t * 1e3 / eager_total, 3),
+                "rulebook_bytes_read_per_step": int(sum(a["rulebook_bytes_read"] for a in acct_list)),
+                "rulebook_bytes_alg_per_step": int(sum(4 * a["pairs"] for a in acct_list)),
                 "tensor_tflops_alg": round(conv_flops / conv_t / 1e12, 2), "tensor_frac_of_bf16_peak": round(conv_flops / conv_t / 1e12 / pk["bf16"], 4)}
 
-    # ---- INT8 leg (BASELINE metric: "INT8 sparse-conv TOPS"): the same backbone as W8A8 per-tensor (QConvNd(8, 8, cw=False):
-    #      int8 codes x int8 codes -> INT32 on tcgen05 kind::i8, dynamic abs-max fused into the producing epilogue) ----
+    # ---- INT8 leg (BASELINE metric: "INT8 sparse-conv TOPS"; headline config only): the same backbone as W8A8 per-tensor
+    #      (QConvNd(8, 8, cw=False): int8 codes x int8 codes -> INT32 on tcgen05 kind::i8) ----
     int8_leg = None
-    try:
-        import qlidar
-        del eng
-        torch.cuda.empty_cache()
+    if args.config == 2:
+        try:
+            del eng, bb, vfe, hc
+            torch.cuda.empty_cache()
 
-        def time_engine(e8):
-            e8.set_points(host_pts[0])
-            for _ in range(3):
-                e8.forward_points()
-            torch.cuda.synchronize()
-            ev8 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-            for i in range(args.steps):
-                flush()
-                ev8[i][0].record()
-                e8.forward_points()
-                ev8[i][1].record()
-            torch.cuda.synchronize()
-            ms8 = float(np.median([a.elapsed_time(b) for a, b in ev8]))
-            t8 = e8.profile_ops(from_points=True, iters=3, flush=flush)
-            acct8 = {a["name"]: a for a in e8.layer_accounting()}
-            c8 = {k.split(":", 1)[1]: v for k, v in t8.items() if k.startswith("conv:")}
-            i8_names = [n for n in c8 if acct8[n]["kind"] == "i8"]
-            ops8 = sum(acct8[n]["flops_alg"] for n in i8_names)
-            tc8 = sum(c8[n] for n in i8_names) / 1e3
-            q8 = sum(v for k, v in t8.items() if k.startswith("quantize:")) / 1e3
-            return {"frames_per_sec": round(BATCH / (ms8 / 1e3), 2), "ms_per_step": round(ms8, 4), "conv_ms_per_step": round(tc8 * 1e3, 4),
-                    "quantize_ms_per_step": round(q8 * 1e3, 4), "tops_alg": round(ops8 / tc8 / 1e12, 2),
-                    "frac_of_2x_bf16_peak": round(ops8 / tc8 / 1e12 / (2 * pk["bf16"]), 4),
-                    "frac_of_i8_mma_peak": round(ops8 / tc8 / 1e12 / I8_MMA_PEAK_TOPS, 4)}
+            def time_engine(e8):
+                e8.set_points(host_pts[0])
+                for _ in range(3):
+                    e8.forward_points()
+                torch.cuda.synchronize()
+                ms8 = float(np.median(timed_steps(e8, args.steps, flush, 1, None)))
+                t8 = e8.profile_ops(from_points=True, iters=3, flush=flush)
+                acct8 = {a["name"]: a for a in e8.layer_accounting()}
+                c8 = {k.split(":", 1)[1]: v for k, v in t8.items() if k.startswith("conv:")}
+                i8_names = [n for n in c8 if acct8[n]["kind"] == "i8"]
+                ops8 = sum(acct8[n]["flops_alg"] for n in i8_names)
+                tc8 = sum(c8[n] for n in i8_names) / 1e3
+                q8 = sum(v for k, v in t8.items() if k.startswith("quantize:")) / 1e3
+                return {"frames_per_sec": round(BATCH / (ms8 / 1e3), 2), "ms_per_step": round(ms8, 4), "conv_ms_per_step": round(tc8 * 1e3, 4),
+                        "quantize_ms_per_step": round(q8 * 1e3, 4), "tops_alg": round(ops8 / tc8 / 1e12, 2),
+                        "frac_of_2x_bf16_peak": round(ops8 / tc8 / 1e12 / (2 * pk["bf16"]), 4),
+                        "frac_of_i8_mma_peak": round(ops8 / tc8 / 1e12 / I8_MMA_PEAK_TOPS, 4)}
 
-        eng8, bb8 = build_engine(dev, P, 8, 8, False)
-        dyn = time_engine(eng8)
-        # static calibration exactly as the reference drivers do it (collect_stats -> compute_amax, quant/quantize.py:175-207),
-        # one batch through the eager module path, then a second engine that consumes the frozen amax tables
-        n0 = eng8.counts()[0]
-        calib = {"voxel_features": eng8.vox_feats[:n0, :eng8.nfeat].clone(), "voxel_coords": eng8.stages[0].coords[:n0].float(), "batch_size": BATCH}
-        del eng8
-        torch.cuda.empty_cache()
+            eng8, bb8 = build_engine(dev, P, 8, 8, False)
+            dyn = time_engine(eng8)
+            # static calibration exactly as the reference drivers do it (collect_stats -> compute_amax, quant/quantize.py:175-207),
+            # one batch through the eager module tree, then a second engine that consumes the frozen amax tables
+            n0_ = eng8.counts()[0]
+            calib = {"voxel_features": eng8.vox_feats[:n0_, :eng8.nfeat].clone(), "voxel_coords": eng8.stages[0].coords[:n0_].float(), "batch_size": BATCH}
+            del eng8
+            torch.cuda.empty_cache()
 
-        class _Pipe(torch.nn.Module):
-            def __init__(self, m):
-                super().__init__()
-                self.backbone_3d = m
+            class _Pipe(torch.nn.Module):
+                def __init__(self, m):
+                    super().__init__()
+                    self.backbone_3d = m
 
-            def forward(self, bd):
-                return self.backbone_3d(bd)
+                def forward(self, bd):
+                    return self.backbone_3d(bd)
 
-        qlidar.collect_stats(_Pipe(bb8), [calib], n_batches=0)
-        qlidar.compute_amax(bb8, dev)
-        c = __import__("qlidar").synth.CONFIGS["waymo"]
-        cap = BATCH * c["max_voxels"]
-        eng8s = qlidar.BackboneEngine(bb8, BATCH, cap, max_points=P, pc_range=c["pc_range"], voxel_size=c["voxel_size"],
-                                      max_pts_per_voxel=c["max_pts"], use_graph=True, device=dev, max_voxels_per_frame=c["max_voxels"],
-                                      stage_caps=[cap, int(1.25 * cap), int(0.75 * cap), int(0.5 * cap), int(0.5 * cap)], **ENGINE_KW)
-        sta = time_engine(eng8s)
-        sta["fused_requantised_layers"] = int(sum(L.fused_q for L in eng8s.layers))
-        int8_leg = {"mode": "QConvNd(w_bits=8, act_bits=8, cw=False): W8A8 per-tensor, INT32 accumulate (tcgen05 kind::i8)",
-                    "dynamic_amax": dyn, "static_calibration": sta,
-                    "note": "INT8 peak is not in MEASURED_PEAKS.json; fractions against 2x the measured bf16 (cuBLAS) peak and against the "
-                            "measured tcgen05 kind::i8 issue ceiling (4596 TOPS, profiles/r01_mma_peak_microbench.txt). "
-                            "static = collect_stats/compute_amax on one batch, int8 codes written by the producing layer's epilogue"}
-    except Exception as e:                                     # the headline line must not depend on the extra leg
-        int8_leg = {"error": repr(e)[:200]}
+            qlidar.collect_stats(_Pipe(bb8), [calib], n_batches=0)
+            qlidar.compute_amax(bb8, dev)
+            eng8s, _ = build_engine(dev, P, bb=bb8)
+            sta = time_engine(eng8s)
+            sta["fused_requantised_layers"] = int(sum(L.fused_q for L in eng8s.layers))
+            int8_leg = {"mode": "QConvNd(w_bits=8, act_bits=8, cw=False): W8A8 per-tensor, INT32 accumulate (tcgen05 kind::i8)",
+                        "dynamic_amax": dyn, "static_calibration": sta,
+                        "note": "INT8 peak is not in MEASURED_PEAKS.json; fractions against 2x the measured bf16 (cuBLAS) peak and against the "
+                                "measured tcgen05 kind::i8 issue ceiling (4596 TOPS, profiles/r01_mma_peak_microbench.txt). "
+                                "static = collect_stats/compute_amax on one batch, int8 codes written by the producing layer's epilogue"}
+        except Exception as e:                                     # the headline line must not depend on the extra leg
+            int8_leg = {"error": repr(e)[:200]}
 
-    # ---- CPU baseline beside it: the oracle port on ONE frame of the same workload ----
-    cpu = cpu_baseline(pts_np, sample_frames=3, warm=0)        # ~10 s of host work: 3 of the batch's 4 frames
+    # ---- CPU baseline beside it: the oracle port on a bounded sample of the same workload ----
+    cpu = cpu_baseline(pts_np, budget_s=12.0)
 
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": round(total_ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16 activations x int8-code weights, fp32 accumulate (W8A16)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": BATCH, "points_per_step": int(P), "voxels_per_stage": counts,
-                   "l2": "512 MiB flush between timed steps", "quant": "QConvNd(w_bits=8, act_bits=16, cw=True), conv_input.0 unquantised",
+        "dtype": W["dtype"], "data": "synthetic",
+        "config": {"workload": WORKLOAD, "baseline_config": args.config, "frames_per_step_per_gpu": BATCH, "points_per_step": int(P), "voxels_per_stage": counts,
+                   "l2": "512 MiB flush between timed steps", "quant": W["quant_txt"],
                    "parallelism": f"frame-sharded x{world} (no data-path collective)"},
         "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": int(pts_np.nbytes),
-                "d2h_bytes_per_step": int(counts_host.numel() * 4), "ms_per_step": round(float(e2e_ms.item()) / e2e_steps, 4),
-                "note": "pinned host points -> H2D (copy stream, double buffered) -> graph replay -> D2H stage counts"},
+                "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": round(float(e2e_ms.item()) / e2e_steps, 4),
+                "note": "pinned host points -> H2D (copy stream, double buffered) -> VoxelizeMeanVFE(batch_dict) -> backbone(batch_dict)"
+                        + (" -> HeightCompression(batch_dict)" if has_bev else "") + " -> D2H of the encoded sparse tensor (fp16 rows + int32 indices)"},
         "gpu_launches": int(kernels_per_step * args.steps),
         "kernels_per_step": int(kernels_per_step),
+        "ms_per_step_per_rank": [round(m / args.steps, 4) for m in all_ms],
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
@@ -421,48 +554,66 @@ def run_ours(args):
         "step_ms_p10_p50_p90": [round(float(np.percentile(step_ms, q)), 4) for q in (10, 50, 90)],
     }
     if gathered is not None:
-        line["gathered_stage_counts"] = gathered
+        line["gathered_sites_per_frame"] = gathered
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------------------------------- CPU arms
-def cpu_baseline(pts_batch: np.ndarray, sample_frames: int = 1, warm: int = 0):
-    """The reference's CPU path restated (oracle/): per-frame hard voxelisation + MeanVFE + VoxelResBackBone8x with the
-    reference's fake-quant math (QConvNd, quant/quant.py:36-58) + HeightCompression, all host cores."""
+def oracle_runner():
+    """The reference's CPU path restated (oracle/) for the selected workload: per-frame hard voxelisation + MeanVFE + the backbone
+    with the reference's fake-quant math (QConvNd, quant/quant.py:36-58; SmoothQuant per SURVEY.md 8a-Q) [+ HeightCompression]."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import qlidar_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    c = O.CONFIGS["waymo"]
+    c = O.CONFIGS[W["dataset"]]
     grid = O.grid_size_xyz(c["pc_range"], c["voxel_size"])
-    prog = O.backbone_specs("VoxelResBackBone8x", c["nfeat"])
+    cfg = W["cfg"]
+    prog = O.backbone_specs(W["arch"], c["nfeat"], cfg.get("CHANNELS"), cfg.get("SPCONV_KERNEL_SIZES"), cfg.get("OUT_CHANNEL"))
     params = O.init_params(prog)
-    q = O.QuantCfg(mode="ref", w_bits=W_BITS, act_bits=ACT_BITS, cw=CW, no_list=tuple(NO_LIST), fast=True)
-    frames = [pts_batch[pts_batch[:, 0] == b] for b in range(int(pts_batch[:, 0].max()) + 1)]
+    qt = W["quant"]
+    no_list = tuple(NO_LIST) + (("conv_out.0", "shared_conv.0") if W["arch"] == "VoxelResBackBone8xVoxelNeXt" else ())
+    if qt[0] == "q":
+        q = O.QuantCfg(mode="ref", w_bits=qt[1], act_bits=qt[2], cw=qt[3], no_list=no_list, fast=True)
+    else:
+        q = O.QuantCfg(mode="w8a8_sq", alpha=qt[1], no_list=no_list, fast=True)
+    bev = W["arch"] != "VoxelResBackBone8xVoxelNeXt"
 
     def one(f):
         f = f.copy(); f[:, 0] = 0
         feats, coords, _ = O.voxelize_mean_batch(f, c["pc_range"], c["voxel_size"], c["max_pts"], c["max_voxels"])
         out, _ = O.backbone_forward(prog, params, torch.from_numpy(feats), coords, O.sparse_shape_zyx(grid), 1, q)
-        O.height_compression(out.features, out.coords, out.spatial_shape, 1)
+        if bev:
+            O.height_compression(out.features, out.coords, out.spatial_shape, 1)
         return coords.shape[0]
 
-    for i in range(warm):
-        one(frames[i % len(frames)])
-    t0 = time.perf_counter()
-    nv = [one(frames[i % len(frames)]) for i in range(sample_frames)]
-    dt = time.perf_counter() - t0
-    model = "unknown"
+    return one, cores
+
+
+def cpu_model():
     try:
         for l in open("/proc/cpuinfo"):
             if l.startswith("model name"):
-                model = l.split(":", 1)[1].strip(); break
+                return l.split(":", 1)[1].strip()
     except OSError:
         pass
-    return {"value": round(sample_frames / dt, 5), "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{sample_frames} frame(s) of the same batch ({nv[0]} voxels), torch CPU with {cores} threads, {model}",
+    return "unknown"
+
+
+def cpu_baseline(pts_batch: np.ndarray, budget_s: float = 12.0):
+    one, cores = oracle_runner()
+    frames = [pts_batch[pts_batch[:, 0] == b] for b in range(int(pts_batch[:, 0].max()) + 1)]
+    t0 = time.perf_counter()
+    nv, k = [], 0
+    while True:
+        nv.append(one(frames[k % len(frames)])); k += 1
+        if time.perf_counter() - t0 > budget_s or k >= 2 * len(frames):
+            break
+    dt = time.perf_counter() - t0
+    return {"value": round(k / dt, 5), "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{k} frame(s) of the same batch ({nv[0]} voxels in the first), torch CPU with {cores} threads, {cpu_model()}",
             "seconds": round(dt, 2)}
 
 
@@ -472,26 +623,11 @@ def run_reference(args):
         return                                                # other ranks exit 0 without work
     budget_s = 150.0
     pts = make_batch(1000, BATCH)
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import qlidar_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    c = O.CONFIGS["waymo"]
-    grid = O.grid_size_xyz(c["pc_range"], c["voxel_size"])
-    prog = O.backbone_specs("VoxelResBackBone8x", c["nfeat"])
-    params = O.init_params(prog)
-    q = O.QuantCfg(mode="ref", w_bits=W_BITS, act_bits=ACT_BITS, cw=CW, no_list=tuple(NO_LIST), fast=True)
+    one, cores = oracle_runner()
     frames = []
     for b in range(BATCH):
         f = pts[pts[:, 0] == b].copy(); f[:, 0] = 0
         frames.append(f)
-
-    def one(f):
-        feats, coords, _ = O.voxelize_mean_batch(f, c["pc_range"], c["voxel_size"], c["max_pts"], c["max_voxels"])
-        out, _ = O.backbone_forward(prog, params, torch.from_numpy(feats), coords, O.sparse_shape_zyx(grid), 1, q)
-        O.height_compression(out.features, out.coords, out.spatial_shape, 1)
-        return coords.shape[0]
-
     t_w = time.perf_counter()
     nv = one(frames[0])                                        # 1 warm-up frame (also sizes the budget)
     per = time.perf_counter() - t_w
@@ -505,11 +641,12 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     v = steps / dt
     base = {"value": round(v, 5), "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} step(s) of 1 frame ({nv} voxels) each; requested {args.steps} steps, bounded to ~{int(budget_s)} s"}
+            "sample": f"{steps} step(s) of 1 frame ({nv} voxels) each; requested {args.steps} steps, bounded to ~{int(budget_s)} s; {cpu_model()}"}
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 5), "unit": "frames/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
             "steps": steps, "warmup": warm_done, "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32 fake-quant (reference math)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "reference's CPU path = oracle port (spconv / pytorch_quantization are not installable here)"},
+            "config": {"workload": WORKLOAD, "baseline_config": args.config,
+                       "note": "reference's CPU path = oracle port (spconv / pytorch_quantization are not installable here)"},
             "cpu_baseline": base, "e2e": {"value": round(v, 5), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -521,7 +658,9 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(WORKLOADS), help="BASELINE.json configuration (1-based); 2 = the headline")
     args = ap.parse_args()
+    select(args.config)
     if args.impl == "reference":
         run_reference(args)
     else:

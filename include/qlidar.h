@@ -248,6 +248,21 @@ int ql_sq_prepare_weights(const float* w, const float* w_ic_absmax, const float*
                           int32_t c_in, int32_t c_out, int32_t kvol, const float* bn_scale,
                           float* smooth_out, int8_t* packed_out, float* scale_out, ql_stream_t stream);
 
+/* ---- dense SmoothQuant wrappers (quant/smoothquant.py:38-99 SQConv2d.forward and its 1-D / transposed / linear siblings;
+ *      quant/SQSubM2d.py:22-91): per-COLUMN statistics and int8 codes of F.unfold(x) without materialising it in floating point.
+ *      x: dense NCHW fp16/fp32; kernel / stride / pad / dilation are (h, w) pairs (host); columns in F.unfold order
+ *      c*kh*kw + ky*kw + kx.  ql_unfold_absmax: absmax_cols[col] = max(absmax_cols[col], max over windows |x|) (caller zeroes).
+ *      ql_unfold_quantize: out[m][col] int8 = clamp(rint(x / smooth_cols[col] * (bound / amax_t))), m = (b, oy, ox), rows
+ *      col_stride bytes apart (>= C*kh*kw, multiple of 16, pad columns 0), amax_t = max_col absmax_cols[col] / smooth_cols[col]
+ *      (the per-tensor input quantiser of quantize.py:59-76); scales_out = {bound / amax_t, amax_t / bound}. */
+int ql_unfold_absmax(const void* x, int32_t dtype, int32_t B, int32_t C, int32_t H, int32_t W,
+                     const int32_t* kernel_hw, const int32_t* stride_hw, const int32_t* pad_hw, const int32_t* dil_hw,
+                     float* absmax_cols, ql_stream_t stream);
+int ql_unfold_quantize(const void* x, int32_t dtype, int32_t B, int32_t C, int32_t H, int32_t W,
+                       const int32_t* kernel_hw, const int32_t* stride_hw, const int32_t* pad_hw, const int32_t* dil_hw,
+                       const float* absmax_cols, const float* smooth_cols, int32_t bits, int32_t col_stride,
+                       int8_t* out, float* scales_out, ql_stream_t stream);
+
 /* ---- BEV hand-off (replaces HeightCompression.forward -> [EXT] SparseConvTensor.dense(),
  *      pcdet/models/backbones_2d/map_to_bev/height_compression.py:20-24): out[b, c*D+d, y, x], zero filled. */
 size_t ql_bev_densify_workspace_bytes(int32_t B, int32_t D, int32_t H, int32_t W);

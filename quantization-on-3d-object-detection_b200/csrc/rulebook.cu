@@ -794,6 +794,13 @@ __global__ void __launch_bounds__(256) k_m2d_add(const TIn* __restrict__ feats, 
     for (int j = 0; j < 4; ++j) atomicAdd(dst + j, v[j]);
 }
 
+// acc[0 .. min(n_out, cap) * c) = 0: only the rows the merge produced (the capacity is a sum of stage capacities, hundreds of MB)
+__global__ void __launch_bounds__(256) k_m2d_zero(float4* __restrict__ acc4, int64_t n_out_cap, int c, const int* __restrict__ n_out_dev) {
+    const int64_t total4 = min((int64_t)n_out_dev[0], n_out_cap) * c / 4;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) acc4[i] = z;
+}
+
 __global__ void __launch_bounds__(256) k_m2d_to_half(const float* __restrict__ acc, int64_t n_elems_cap, int c, const int* __restrict__ n_out_dev,
                                                      __half* __restrict__ out) {
     const int64_t total = min((int64_t)n_out_dev[0] * c, n_elems_cap);
@@ -836,13 +843,13 @@ extern "C" int ql_bev_merge2d_multi(int32_t n_seg, const void* const* feats, int
     int* blocks = (int*)(ws + w.blocks);
     float* acc = out_dtype == QL_F32 ? (float*)out_feats : (float*)(ws + w.acc);
     if (cudaMemsetAsync(bitmap, 0, (size_t)w.n_words * 4, st) != cudaSuccess) return QL_ERR_CUDA;
-    if (cudaMemsetAsync(acc, 0, (size_t)n_out_cap * c * 4, st) != cudaSuccess) return QL_ERR_CUDA;
     for (int i = 0; i < n_seg; ++i)
         if (n_cap[i] > 0)
             k_m2d_mark<<<(unsigned)((n_cap[i] + 255) / 256), 256, 0, st>>>((const int4*)coords[i], n_cap[i], n_dev[i], B, H, W, coord_scale[i], bitmap);
     k_rb_popc<<<(unsigned)w.n_blocks, QL_SCAN_THREADS, 0, st>>>(bitmap, w.n_words, blocks);
     k_scan_blocks<<<1, QL_SCAN_THREADS, 0, st>>>(blocks, (int)w.n_blocks, n_out_dev + 1, n_out_dev, n_out_cap);
     k_m2d_emit<<<(unsigned)w.n_blocks, QL_SCAN_THREADS, 0, st>>>(bitmap, w.n_words, blocks, H, W, prefix, out_coords, n_out_cap, out_coord_cols);
+    k_m2d_zero<<<4 * ql_num_sms(), 256, 0, st>>>((float4*)acc, n_out_cap, c, n_out_dev);
     for (int i = 0; i < n_seg; ++i) {
         if (n_cap[i] <= 0) continue;
         const int64_t threads = n_cap[i] * (c / 4);

@@ -87,3 +87,133 @@ extern "C" int ql_sq_prepare_weights(const float* w, const float* w_ic_absmax, c
     QL_CUDA_CHECK_LAST();
     return QL_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Dense SmoothQuant wrappers (quant/smoothquant.py: SQConv2d / SQConv1d / SQConvT2d / SQLinear; quant/SQSubM2d.py): the reference
+// materialises F.unfold(x) in fp32 -- [B*L, ic*kh*kw] -- to take per-COLUMN activation maxima, divide by the smoothing scale and
+// fake-quantise.  Here the unfolded matrix only ever exists as int8 codes: ql_unfold_absmax takes the per-column maxima straight
+// from the NCHW map (no materialisation), ql_unfold_quantize writes the smoothed, quantised unfolded matrix once (1 byte per
+// element, columns in F.unfold order c*kh*kw + ky*kw + kx, zero padded to a multiple of 16), and the product with the smoothed
+// int8 weights is ONE ql_spconv_mma launch (kernel volume 1, identity rulebook, INT32 accumulate on tcgen05 kind::i8).
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct UnfoldGeom {
+    int B, C, H, W, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo;
+};
+
+__device__ __forceinline__ float ld_in(const void* x, int dtype, int64_t i) {
+    return dtype == QL_F16 ? __half2float(((const __half*)x)[i]) : ((const float*)x)[i];
+}
+
+// one CTA per (channel, batch) plane: every pixel updates the maxima of the kernel positions whose windows contain it
+__global__ void __launch_bounds__(256) k_unfold_absmax(const void* __restrict__ x, int dtype, UnfoldGeom g, float* __restrict__ absmax) {
+    extern __shared__ uint32_t s_m[];                    // [kh * kw]
+    const int K = g.kh * g.kw;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) s_m[i] = 0u;
+    __syncthreads();
+    const int c = blockIdx.x, b = blockIdx.y;
+    const int64_t plane = ((int64_t)b * g.C + c) * g.H * g.W;
+    for (int k = 0; k < K; ++k) {
+        const int ky = k / g.kw, kx = k - ky * g.kw;
+        float m = 0.f;
+        // the window of column (c, ky, kx): rows oy*sh - ph + ky*dh, oy in [0, Ho); same for x
+        for (int i = threadIdx.x; i < g.Ho * g.Wo; i += blockDim.x) {
+            const int oy = i / g.Wo, ox = i - oy * g.Wo;
+            const int y = oy * g.sh - g.ph + ky * g.dh, xx = ox * g.sw - g.pw + kx * g.dw;
+            if (y >= 0 && y < g.H && xx >= 0 && xx < g.W) m = fmaxf(m, fabsf(ld_in(x, dtype, plane + (int64_t)y * g.W + xx)));
+        }
+        m = ql_warp_max(m);
+        if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(&s_m[k], __float_as_uint(m));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += blockDim.x)
+        if (s_m[i]) atomicMax(reinterpret_cast<unsigned int*>(absmax) + c * K + i, s_m[i]);
+}
+
+// tensor amax of the smoothed columns and the (de-)quantisation scales: amax_t = max_col absmax[col] / smooth[col]
+__global__ void __launch_bounds__(256) k_unfold_scales(const float* __restrict__ absmax, const float* __restrict__ smooth, int n_cols,
+                                                       float bound, float* __restrict__ scales /* {quant scale, act_scale = amax/bound} */) {
+    __shared__ float s_red[8];
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n_cols; i += blockDim.x) m = fmaxf(m, __fdiv_rn(absmax[i], smooth[i]));
+    m = ql_warp_max(m);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t = fmaxf(t, s_red[i]);
+        scales[0] = t <= (1.0f / 16777216.0f) ? 0.f : __fdiv_rn(bound, t);
+        scales[1] = __fdiv_rn(t, bound);
+    }
+}
+
+// out[m][col] = clamp(rint((x / smooth[col]) * qscale)), m = (b, oy, ox), col = c*kh*kw + ky*kw + kx (F.unfold order); padding = 0
+__global__ void __launch_bounds__(256) k_unfold_quantize(const void* __restrict__ x, int dtype, UnfoldGeom g, const float* __restrict__ smooth,
+                                                         const float* __restrict__ scales, float bound, int n_cols, int col_stride,
+                                                         int8_t* __restrict__ out) {
+    const int64_t M = (int64_t)g.B * g.Ho * g.Wo;
+    const float qs = scales[0];
+    const int K = g.kh * g.kw;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M * col_stride; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = t / col_stride;
+        const int col = (int)(t - m * col_stride);
+        int8_t q = 0;
+        if (col < n_cols) {
+            const int c = col / K, k = col - c * K;
+            const int ky = k / g.kw, kx = k - ky * g.kw;
+            const int b = (int)(m / (g.Ho * g.Wo));
+            const int r = (int)(m - (int64_t)b * g.Ho * g.Wo);
+            const int oy = r / g.Wo, ox = r - oy * g.Wo;
+            const int y = oy * g.sh - g.ph + ky * g.dh, xx = ox * g.sw - g.pw + kx * g.dw;
+            if (y >= 0 && y < g.H && xx >= 0 && xx < g.W) {
+                const float v = __fdiv_rn(ld_in(x, dtype, (((int64_t)b * g.C + c) * g.H + y) * g.W + xx), smooth[col]);
+                q = (int8_t)(int)fminf(fmaxf(rintf(__fmul_rn(v, qs)), -bound), bound);
+            }
+        }
+        out[t] = q;
+    }
+}
+
+bool unfold_geom(int32_t B, int32_t C, int32_t H, int32_t W, const int32_t* k, const int32_t* s, const int32_t* p, const int32_t* d, UnfoldGeom& g) {
+    if (!k || !s || !p || !d || B <= 0 || C <= 0 || H <= 0 || W <= 0) return false;
+    g = UnfoldGeom{B, C, H, W, k[0], k[1], s[0], s[1], p[0], p[1], d[0], d[1], 0, 0};
+    if (g.kh <= 0 || g.kw <= 0 || g.sh <= 0 || g.sw <= 0 || g.ph < 0 || g.pw < 0 || g.dh <= 0 || g.dw <= 0) return false;
+    g.Ho = (H + 2 * g.ph - g.dh * (g.kh - 1) - 1) / g.sh + 1;
+    g.Wo = (W + 2 * g.pw - g.dw * (g.kw - 1) - 1) / g.sw + 1;
+    return g.Ho > 0 && g.Wo > 0;
+}
+
+}  // namespace
+
+extern "C" int ql_unfold_absmax(const void* x, int32_t dtype, int32_t B, int32_t C, int32_t H, int32_t W, const int32_t* kernel_hw,
+                                const int32_t* stride_hw, const int32_t* pad_hw, const int32_t* dil_hw, float* absmax_cols,
+                                ql_stream_t stream_) {
+    UnfoldGeom g;
+    if (!x || !absmax_cols || (dtype != QL_F16 && dtype != QL_F32) || !unfold_geom(B, C, H, W, kernel_hw, stride_hw, pad_hw, dil_hw, g))
+        return QL_ERR_INVALID;
+    k_unfold_absmax<<<dim3((unsigned)C, (unsigned)B), 256, (size_t)g.kh * g.kw * 4, (cudaStream_t)stream_>>>(x, dtype, g, absmax_cols);
+    QL_CUDA_CHECK_LAST();
+    return QL_OK;
+}
+
+extern "C" int ql_unfold_quantize(const void* x, int32_t dtype, int32_t B, int32_t C, int32_t H, int32_t W, const int32_t* kernel_hw,
+                                  const int32_t* stride_hw, const int32_t* pad_hw, const int32_t* dil_hw, const float* absmax_cols,
+                                  const float* smooth_cols, int32_t bits, int32_t col_stride, int8_t* out, float* scales_out,
+                                  ql_stream_t stream_) {
+    UnfoldGeom g;
+    if (!x || !absmax_cols || !smooth_cols || !out || !scales_out || (dtype != QL_F16 && dtype != QL_F32) || bits < 2 || bits > 8 ||
+        !unfold_geom(B, C, H, W, kernel_hw, stride_hw, pad_hw, dil_hw, g))
+        return QL_ERR_INVALID;
+    const int n_cols = C * g.kh * g.kw;
+    if (col_stride < n_cols || col_stride % 16 != 0) return QL_ERR_INVALID;
+    const float bound = (float)((1 << (bits - 1)) - 1);
+    cudaStream_t st = (cudaStream_t)stream_;
+    k_unfold_scales<<<1, 256, 0, st>>>(absmax_cols, smooth_cols, n_cols, bound, scales_out);
+    const int64_t total = (int64_t)g.B * g.Ho * g.Wo * col_stride;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 32 * ql_num_sms()) blocks = 32 * ql_num_sms();
+    k_unfold_quantize<<<(unsigned)blocks, 256, 0, st>>>(x, dtype, g, smooth_cols, scales_out, bound, n_cols, col_stride, out);
+    QL_CUDA_CHECK_LAST();
+    return QL_OK;
+}

@@ -9,7 +9,7 @@ from .sparse import (SparseConvTensor, SparseModule, SparseSequential, SparseCon
 from .tensor_quant import QuantDescriptor, TensorQuantizer, MaxCalibrator
 from .quant import QConvNd, QConv3d, QConv2d, GQConv3d, SQConv3d, q_conv3d, gq_conv3d, sq_conv3d, collect_stats, compute_amax
 from .backbones import (Cfg, post_act_block, SparseBasicBlock, VoxelBackBone8x, VoxelResBackBone8x,
-                        VoxelResBackBone8xVoxelNeXt, MeanVFE, DynamicMeanVFE, VoxelGeneratorWrapper, HeightCompression)
+                        VoxelResBackBone8xVoxelNeXt, MeanVFE, DynamicMeanVFE, VoxelizeMeanVFE, VoxelGeneratorWrapper, HeightCompression)
 from .engine import BackboneEngine
 from . import shard
 

@@ -52,6 +52,8 @@ SIGNATURES = {
     "ql_absmax_cols": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p]),
     "ql_quantize_rows": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p, _i32, _i32, _p, _p, _p]),
     "ql_sq_prepare_weights": (C.c_int, [_p, _p, _p, C.c_float, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
+    "ql_unfold_absmax": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p]),
+    "ql_unfold_quantize": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p]),
     "ql_bev_densify_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ql_bev_densify": (C.c_int, [_p, _i32, _i32, _p, _i64, _i32, _i32, _i32, _i32, _p, _i32, _p, _sz, _p]),
     "ql_bev_merge2d_workspace_bytes": (_sz, [_i32, _i32, _i32, _i64, _i32, _i32]),

@@ -113,61 +113,104 @@ class _BackboneBase(nn.Module):
         return batch_dict
 
     # ------------------------------------------------------------------ engine-backed plugin call
-    def _state_signature(self):
+    def _snapshot(self):
+        """What an engine was compiled from: every (container, key, object) of the module tree -- sub-modules, parameters, buffers,
+        quantiser amax -- and the tensors' version counters.  _unchanged() re-checks it in ~0.1 ms per call (identity + integer
+        compares, no hashing of data): surgery (q_conv3d swaps _modules entries), load_state_dict / optimiser steps (version bumps),
+        calibration (new _amax buffers, quantiser switches) all invalidate it."""
         from .tensor_quant import TensorQuantizer
-        sig = [(p.data_ptr(), p._version) for p in self.parameters()]
-        sig += [(b.data_ptr(), b._version) for b in self.buffers()]
+        entries, tensors, quants = [], [], []
         for m in self.modules():
-            sig.append(type(m).__name__)
+            for d in (m._modules, m._parameters, m._buffers):
+                for k, v in d.items():
+                    entries.append((d, k, v))
+                    if isinstance(v, torch.Tensor):
+                        tensors.append(v)
             if isinstance(m, TensorQuantizer):
-                sig.append((m._disabled, m._if_quant, m._if_calib, m.num_bits, None if m.amax is None else (m.amax.data_ptr(), m.amax._version)))
-        return hash(tuple(sig))
+                quants.append(m)
+        return dict(entries=entries, sizes=[(m, len(m._modules), len(m._parameters), len(m._buffers)) for m in self.modules()],
+                    tensors=tensors, versions=[t._version for t in tensors], quants=quants,
+                    qstate=[(q._disabled, q._if_quant, q._if_calib, q.num_bits) for q in quants])
+
+    @staticmethod
+    def _unchanged(snap) -> bool:
+        for d, k, v in snap["entries"]:
+            if d.get(k) is not v:
+                return False
+        for m, a, b, c in snap["sizes"]:
+            if len(m._modules) != a or len(m._parameters) != b or len(m._buffers) != c:
+                return False
+        for t, ver in zip(snap["tensors"], snap["versions"]):
+            if t._version != ver:
+                return False
+        for q, stt in zip(snap["quants"], snap["qstate"]):
+            if (q._disabled, q._if_quant, q._if_calib, q.num_bits) != stt:
+                return False
+        return True
 
     def _engine_eligible(self, batch_dict) -> bool:
-        from .tensor_quant import TensorQuantizer
         if not self.use_engine or self.training or torch.is_grad_enabled() or getattr(self, "_engine_unsupported", False):
             return False
-        if not batch_dict['voxel_features'].is_cuda:
+        src = batch_dict.get('_ql_points') if batch_dict.get('voxel_features') is None else batch_dict['voxel_features']
+        if src is None or not src.is_cuda:
             return False
-        for m in self.modules():
-            if isinstance(m, TensorQuantizer) and (m._if_calib or m._disabled or not m._if_quant):
+        st = getattr(self, "_engine_state", None)
+        quants = st["snap"]["quants"] if st is not None else None
+        if quants is None:
+            from .tensor_quant import TensorQuantizer
+            quants = [m for m in self.modules() if isinstance(m, TensorQuantizer)]
+        for m in quants:
+            if m._if_calib or m._disabled or not m._if_quant:
                 return False                                    # calibration / quantisers off: the eager tree collects the statistics
         return True
 
     def _engine_for(self, batch_dict, stage_caps=None):
         from .engine import BackboneEngine
         from ._lib import QlidarError
-        V, B = int(batch_dict['voxel_features'].shape[0]), int(batch_dict['batch_size'])
-        sig = self._state_signature()
+        B = int(batch_dict['batch_size'])
+        pts = batch_dict.get('_ql_points') if batch_dict.get('voxel_features') is None else None
+        vfe = getattr(self, "_ql_vfe", None) if pts is not None else None
+        if pts is not None:
+            V, P = B * vfe.max_voxels, int(pts.shape[0])            # per-frame MAX_NUMBER_OF_VOXELS: the batch capacity cannot overflow
+            dev = pts.device
+        else:
+            V, P = int(batch_dict['voxel_features'].shape[0]), None
+            dev = batch_dict['voxel_features'].device
         st = getattr(self, "_engine_state", None)
-        if (stage_caps is None and st is not None and st["sig"] == sig and st["B"] == B and V <= st["cap"]
-                and st["bev"] == self.engine_bev_dtype):
+        same = st is not None and self._unchanged(st["snap"]) and st["B"] == B and st["bev"] == self.engine_bev_dtype and (st["P"] is not None) == (P is not None)
+        if stage_caps is None and same and V <= st["cap"] and (P is None or P <= st["P"]):
             return st["eng"]
-        cap = max(int(V * 1.25) + 1024, 0 if st is None else st["cap"])
-        if stage_caps is None and st is not None and st["sig"] == sig and st["B"] == B:
+        cap = max(V if pts is not None else int(V * 1.25) + 1024, st["cap"] if same else 0)
+        if stage_caps is None and same:
             # the same model on a bigger input: scale the stage capacities learnt so far
             stage_caps = [int(c * cap / st["cap"]) + 128 for c in st["eng_caps"]]
         if stage_caps is not None:
             stage_caps = [max(cap, stage_caps[0])] + list(stage_caps[1:])
             cap = stage_caps[0]
+        max_points = None if P is None else max(int(P * 1.25) + 1024, st["P"] if same and st["P"] else 0)
         self._engine_state = None                                   # release the old engine's buffers before allocating the new ones
+        kw = {}
+        if pts is not None:
+            kw = dict(max_points=max_points, pc_range=vfe.point_cloud_range, voxel_size=vfe.voxel_size, max_pts_per_voxel=vfe.max_points_per_voxel,
+                      max_voxels_per_frame=vfe.max_voxels, n_point_features=vfe.num_point_features)
         try:
             eng = BackboneEngine(self, B, cap, stage_cap_ratio=1.3, stage_caps=stage_caps, bev=self.engine_bev_dtype is not None,
-                                 bev_dtype=self.engine_bev_dtype or torch.float16, device=batch_dict['voxel_features'].device)
+                                 bev_dtype=self.engine_bev_dtype or torch.float16, device=dev, **kw)
         except QlidarError:
             self._engine_unsupported = True                     # a module tree the engine cannot schedule: the eager tree serves it
             return None
-        self._engine_state = dict(sig=sig, B=B, cap=cap, eng=eng, bev=self.engine_bev_dtype, eng_caps=[s.cap for s in eng.stages])
+        self._engine_state = dict(snap=self._snapshot(), B=B, cap=cap, eng=eng, bev=self.engine_bev_dtype, eng_caps=[s.cap for s in eng.stages], P=max_points)
         return eng
 
     def _engine_forward(self, batch_dict):
         eng = self._engine_for(batch_dict)
         if eng is None:
             return None
-        vf, vc = batch_dict['voxel_features'], batch_dict['voxel_coords']
+        pts = batch_dict.get('_ql_points') if batch_dict.get('voxel_features') is None else None
+        vf, vc = (pts, None) if pts is not None else (batch_dict['voxel_features'], batch_dict['voxel_coords'])
         for attempt in range(10):
-            out = eng.forward_voxels(vf, vc)
-            counts = torch.stack([st.n_dev for st in eng.stages]).cpu()         # the one synchronisation of the call
+            out = eng.forward_points(pts) if pts is not None else eng.forward_voxels(vf, vc)
+            counts = eng.counts_dev.cpu()                                       # the one synchronisation of the call
             over = (counts[:, 1] > counts[:, 0]).tolist()
             if not any(over[1:]):
                 break
@@ -182,6 +225,10 @@ class _BackboneBase(nn.Module):
             raise RuntimeError("engine stage capacities did not converge")
         n = [int(v) for v in counts[:, 0].tolist()]
         B = int(batch_dict['batch_size'])
+        if pts is not None:
+            # the fused voxeliser's products, as the VFE plugin would have published them (rows in ascending-key order)
+            batch_dict['voxel_features'] = eng.vox_feats[:n[0], :eng.nfeat]
+            batch_dict['voxel_coords'] = eng.stages[0].coords[:n[0]]
 
         def tensor(feats, stage_i):
             stg = eng.stages[stage_i]
@@ -401,6 +448,52 @@ class DynamicMeanVFE(nn.Module):
         n = int(n_dev[0].item())
         batch_dict['voxel_features'] = feats[:n]
         batch_dict['voxel_coords'] = coords[:n]
+        return batch_dict
+
+
+class VoxelizeMeanVFE(nn.Module):
+    """Hard voxelisation + MeanVFE on the GPU behind the batch_dict contract: the work of DataProcessor.transform_points_to_voxels
+    (pcdet/datasets/processor/data_processor.py:133-180 -> [EXT] Point2VoxelCPU3d: MAX_POINTS_PER_VOXEL, per-frame MAX_NUMBER_OF_VOXELS,
+    first-touch order) + dataset.py:237-244 (batch column) + MeanVFE (mean_vfe.py:25-29), fused -- the (V, T, F) padded tensor is never
+    materialised.  Reads batch_dict['points'] (sum P, 1+F) with the batch index in column 0 (frames contiguous and ascending, as
+    collate_batch leaves them), writes voxel_features (V, F), voxel_coords (V, 4) int32 [b, z, y, x], voxel_num_points.
+    attach(backbone): the voxeliser then runs INSIDE the backbone's CUDA graph (points -> voxels -> rulebooks -> convs [-> BEV] in one
+    replay, no intermediate synchronisation); forward() only hands the points over and the backbone publishes voxel_features /
+    voxel_coords afterwards."""
+
+    def __init__(self, model_cfg=None, num_point_features=4, voxel_size=None, point_cloud_range=None, max_points_per_voxel=5,
+                 max_voxels=40000, **kwargs):
+        super().__init__()
+        self.model_cfg = _cfg(model_cfg)
+        self.num_point_features = int(num_point_features)
+        self.voxel_size = [float(v) for v in voxel_size]
+        self.point_cloud_range = [float(v) for v in point_cloud_range]
+        self.max_points_per_voxel, self.max_voxels = int(max_points_per_voxel), int(max_voxels)
+        r = np.asarray(self.point_cloud_range, dtype=np.float64)
+        self.grid_size = np.round((r[3:6] - r[0:3]) / np.asarray(self.voxel_size, dtype=np.float64)).astype(np.int64).tolist()
+        self._fused = False
+
+    def get_output_feature_dim(self):
+        return self.num_point_features
+
+    def attach(self, backbone):
+        backbone._ql_vfe = self
+        self._fused = True
+        return self
+
+    @torch.no_grad()
+    def forward(self, batch_dict, **kwargs):
+        points = batch_dict['points']
+        if self._fused:
+            batch_dict['_ql_points'] = points if points.is_contiguous() else points.contiguous()
+            batch_dict['voxel_features'] = None                    # published by the backbone call (one graph replay for both)
+            batch_dict['voxel_coords'] = None
+            return batch_dict
+        B = int(batch_dict['batch_size'])
+        feats, coords, npts, n_dev, _ = ops.voxelize_mean(points.contiguous(), self.point_cloud_range, self.voxel_size, self.grid_size, B,
+                                                          self.max_points_per_voxel, B * self.max_voxels, max_voxels_per_frame=self.max_voxels)
+        n = int(n_dev[0].item())
+        batch_dict['voxel_features'], batch_dict['voxel_coords'], batch_dict['voxel_num_points'] = feats[:n], coords[:n], npts[:n]
         return batch_dict
 
 

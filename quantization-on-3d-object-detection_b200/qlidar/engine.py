@@ -314,8 +314,10 @@ class BackboneEngine:
         dev = self.dev
         z = lambda *s, dt=torch.float16: torch.zeros(s, dtype=dt, device=dev)
         s0 = self.stages[0]
+        # every stage's (kept, found) row counts in ONE tensor: the host reads them with a single copy
+        self.counts_dev = z(len(self.stages), 2, dt=torch.int32)
         s0.coords = z(s0.cap, 4, dt=torch.int32)
-        s0.n_dev = z(2, dt=torch.int32)
+        s0.n_dev = self.counts_dev[0]
         # rows padded to 8 floats (32 bytes): the stem conv fetches a neighbour row with one 256-bit load
         self.vox_feats = z(s0.cap, 8 if self.nfeat <= 8 else self.nfeat, dt=torch.float32)
         self.vox_npts = z(s0.cap, dt=torch.int32)
@@ -333,9 +335,9 @@ class BackboneEngine:
             w0 = z(ops.rulebook_strided_workspace_bytes(s0.grid, 1, 1, 0), dt=torch.uint8)
             s0.rank = ops.rulebook_strided_index(s0.grid, 1, 1, 0, w0)
             self.sort_src = z(s0.cap, dt=torch.int32)                      # sorted row -> first-touch row
-        for st in self.stages[1:]:
+        for i, st in enumerate(self.stages[1:], start=1):
             st.coords = z(st.cap, 4, dt=torch.int32)
-            st.n_dev = z(2, dt=torch.int32)
+            st.n_dev = self.counts_dev[i]
             st.table = None                                   # key-sorted stages are indexed by rank (bitmap + prefix), not by hash
         # one strided-rulebook workspace per produced stage: its bitmap + prefix is that stage's rank index, used by the
         # submanifold rulebooks (and the BEV hand-off) that follow instead of a hash table
@@ -627,11 +629,11 @@ class BackboneEngine:
         return out
 
     def counts(self) -> List[int]:
-        return [int(v) for v in torch.stack([st.n_dev for st in self.stages])[:, 0].cpu().tolist()]
+        return [int(v) for v in self.counts_dev[:, 0].cpu().tolist()]
 
     def overflowed(self) -> bool:
         """True when a stage found more active sites than its capacity (rows were dropped): raise the capacities."""
-        c = torch.stack([st.n_dev for st in self.stages]).cpu()
+        c = self.counts_dev.cpu()
         if self.sort_stage1:
             c[0] = self.n_ft.cpu()                                   # (kept, found) of the voxeliser, not of the renumbering build
         over = c[:, 1] > c[:, 0]
