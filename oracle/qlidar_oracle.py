@@ -951,3 +951,83 @@ def mirror_backbone_w8a8_pt(prog, params, features, coords: np.ndarray, sparse_s
             raise ValueError(f"mirror: unsupported op {kind}")
     out = SpT(torch.from_numpy(x_h.astype(np.float32)), x.coords, x.spatial_shape, batch_size)
     return rec, out, taps
+
+
+# ----------------------------------------------------------------------------------------------
+# a15 / boundary: the dense SmoothQuant wrapper family (quant/smoothquant.py) and SQSubM2d (quant/SQSubM2d.py), restated.
+# Pinned by tests/golden/sq_dense.npz, which the reference's own smoothquant.py produced (tests/golden/make_golden_sq.py).
+# ----------------------------------------------------------------------------------------------
+def sq_dense_matmul(cols: torch.Tensor, w2d: torch.Tensor, alpha: float, w_bits: int = 8, act_bits: int = 8) -> torch.Tensor:
+    """The core every wrapper shares (quant/smoothquant.py:69-85): cols [M, K] unfolded activations, w2d [N, K];
+    scale = max|cols|^a / max|w|^(1-a) per column, zeros -> 1; w * scale, cols / scale; weight fake-quant per row (axis 0), input
+    per tensor; cols @ w.T."""
+    w_scale = w2d.abs().max(dim=0)[0]
+    act_scale = cols.abs().max(dim=0)[0]
+    scale = act_scale ** alpha / w_scale ** (1 - alpha)
+    scale[scale == 0] = 1
+    w = fake_quant(w2d * scale, w_bits, axis=0)
+    x = fake_quant(cols / scale, act_bits, axis=None)
+    return x @ w.t()
+
+
+def sq_conv2d(x, weight, bias, alpha, stride=1, padding=0, dilation=1):
+    """quant/smoothquant.py:38-99.  x (B, C, H, W), weight (oc, ic, k, k)."""
+    oc, ic, k, _ = weight.shape
+    B, _, H, W = x.shape
+    cols = F.unfold(x, kernel_size=k, dilation=dilation, padding=padding, stride=stride).permute(0, 2, 1).reshape(-1, ic * k * k)
+    y = sq_dense_matmul(cols, weight.reshape(oc, -1), alpha)
+    ho = (H + 2 * padding - dilation * (k - 1) - 1) // stride + 1
+    wo = (W + 2 * padding - dilation * (k - 1) - 1) // stride + 1
+    y = y.view(B, -1, oc).permute(0, 2, 1).reshape(B, oc, ho, wo)
+    return y if bias is None else y + bias.view(1, oc, 1, 1)
+
+
+def sq_conv1d(x, weight, bias, alpha, stride=1, padding=0, dilation=1):
+    """quant/smoothquant.py:133-176.  x (B, C, L), weight (oc, ic, k)."""
+    oc, ic, k = weight.shape
+    B, _, L = x.shape
+    cols = F.unfold(x.unsqueeze(2), kernel_size=(1, k), dilation=(1, dilation), padding=(0, padding), stride=(1, stride))
+    cols = cols.permute(0, 2, 1).reshape(-1, ic * k)
+    y = sq_dense_matmul(cols, weight.reshape(oc, -1), alpha)
+    lo = (L + 2 * padding - dilation * (k - 1) - 1) // stride + 1
+    y = y.view(B, lo, oc).permute(0, 2, 1)
+    return y if bias is None else y + bias.view(1, oc, 1)
+
+
+def sq_convT2d(x, weight, bias, alpha, stride=1, padding=0, output_padding=0, dilation=1):
+    """quant/smoothquant.py:214-270 (with `.reshape` where the file's `.view` raises on inputs of more than one pixel).
+    x (B, ic, H, W), weight (ic, oc, k, k)."""
+    ic, oc, k, _ = weight.shape
+    B, _, ih, iw = x.shape
+    w = weight.reshape(ic, -1).t()
+    rows = x.reshape(B, ic, ih * iw).permute(0, 2, 1).reshape(-1, ic)
+    y = sq_dense_matmul(rows, w, alpha).view(B, ih * iw, -1).permute(0, 2, 1)
+    ho = (ih - 1) * stride - 2 * padding + dilation * (k - 1) + output_padding + 1
+    wo = (iw - 1) * stride - 2 * padding + dilation * (k - 1) + output_padding + 1
+    y = F.fold(y, output_size=(ho, wo), kernel_size=k, dilation=dilation, padding=padding, stride=stride)
+    return y if bias is None else y + bias.view(1, oc, 1, 1)
+
+
+def sq_linear(x, weight, bias, alpha):
+    """quant/smoothquant.py:299-322.  x (S, B, in)."""
+    S, B, fin = x.shape
+    y = sq_dense_matmul(x.reshape(-1, fin), weight, alpha)
+    if bias is not None:
+        y = y + bias.view(1, -1)
+    return y.view(-1, B, weight.shape[0])
+
+
+def sq_subm2d(x, weight, alpha, kernel_size=3, stride=1, padding=1, dilation=1):
+    """quant/SQSubM2d.py:22-91 (the class itself cannot be constructed: NameError in __init__): unfold -> per-column scale ->
+    fake-quant -> fold (which SUMS overlapping patches) -> (weight (oc, k, k, ic), x (B, H, W, C))."""
+    oc, ic, k, _ = weight.shape
+    B, _, H, W = x.shape
+    ks = ic * k * k
+    cols = torch.transpose(F.unfold(x, kernel_size=k, padding=padding, stride=stride), 1, 2).reshape(-1, ks)
+    w_flat = weight.reshape(oc, ks).clone()
+    scale = cols.abs().max(dim=0)[0] ** alpha / w_flat.abs().max(dim=0)[0] ** (1 - alpha)
+    scale[scale == 0] = 1
+    cols = fake_quant(cols / scale, 8, axis=None)
+    w_flat = fake_quant(w_flat * scale, 8, axis=0)
+    xo = F.fold(cols.reshape(B, -1, ks).transpose(1, 2), (H, W), kernel_size=k, dilation=dilation, padding=padding, stride=stride)
+    return w_flat.view(oc, ic, k, k).permute(0, 2, 3, 1).contiguous(), xo.permute(0, 2, 3, 1)

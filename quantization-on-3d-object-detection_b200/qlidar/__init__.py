@@ -12,12 +12,17 @@ from .backbones import (Cfg, post_act_block, SparseBasicBlock, VoxelBackBone8x, 
                         VoxelResBackBone8xVoxelNeXt, MeanVFE, DynamicMeanVFE, VoxelizeMeanVFE, VoxelGeneratorWrapper, HeightCompression)
 from .engine import BackboneEngine
 from . import shard
+from . import smoothquant as _smoothquant_mod
+from .smoothquant import (SQConv2d, SQConv1d, SQConvT2d, SQLinear, SQSubM2d, SparseSQConv2d, smoothquant_layer, smoothquant)
 
 # `import qlidar as spconv` at pcdet/utils/spconv_utils.py:3-10 keeps the reference's attribute paths working:
 # spconv.__version__[2:] (:4), spconv.constants.SPCONV_USE_DIRECT_TABLE (:5), spconv.pytorch (:8), spconv.conv.SparseConvolution (:23),
 # spconv.pytorch.modules.SparseModule (quant/quant.py:3)
 import sys as _sys
 import types as _types
+
+# the reference's quant/quant_voxelnext.py names: QConv3d, QConv2d and the SPARSE SQConv2d(sqsubm2d, subm2d)
+quant_voxelnext = _types.SimpleNamespace(QConv3d=QConv3d, QConv2d=QConv2d, SQConv2d=SparseSQConv2d)
 
 __version__ = "2.3.6"
 constants = _types.SimpleNamespace(SPCONV_USE_DIRECT_TABLE=False)

@@ -1,0 +1,116 @@
+"""GPU parity of the SmoothQuant wrapper family (qlidar/smoothquant.py) -- real int8 kernels -- against (a) what the reference's own
+quant/smoothquant.py computed (tests/golden/sq_dense.npz) and (b) the oracle's restatement on shapes the shipped file cannot run.
+
+Tolerance: 1e-2 of max|y| (the north star's feature tolerance).  The int8 x int8 -> INT32 product equals the reference's
+fake-quant fp32 product exactly up to fp32 summation order; what remains is the device's powf in the smoothing scale, which can
+move a code that sits on a rounding boundary by one step."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import qlidar_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sq_dense.npz"))
+
+
+def _t(k):
+    return torch.from_numpy(G[k])
+
+
+def rel(got, ref):
+    return (got.double().cpu() - ref.double()).abs().max().item() / max(ref.abs().max().item(), 1e-12)
+
+
+CASES = {
+    "conv2d_3x3_s1": ("Conv2d", dict(in_channels=16, out_channels=32, kernel_size=3, stride=1, padding=1)),
+    "conv2d_3x3_s2": ("Conv2d", dict(in_channels=16, out_channels=16, kernel_size=3, stride=2, padding=1)),
+    "conv2d_1x1_head": ("Conv2d", dict(in_channels=32, out_channels=3, kernel_size=1)),
+    "conv1d_k3": ("Conv1d", dict(in_channels=16, out_channels=24, kernel_size=3, padding=1)),
+    "convT2d_k2_s2": ("ConvTranspose2d", dict(in_channels=16, out_channels=8, kernel_size=2, stride=2)),
+    "linear": ("Linear", dict(in_features=32, out_features=48)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_sq_wrapper_reproduces_the_references_output(name):
+    import qlidar
+    kind, kw = CASES[name]
+    tgt = {"Conv2d": qlidar.SQConv2d, "Conv1d": qlidar.SQConv1d, "ConvTranspose2d": qlidar.SQConvT2d, "Linear": qlidar.SQLinear}[kind]
+    layer = getattr(torch.nn, kind)(**kw)
+    with torch.no_grad():
+        layer.weight.copy_(_t(name + ":w"))
+        layer.bias.copy_(_t(name + ":b"))
+    layer = layer.cuda()
+    q = qlidar.smoothquant_layer(layer, tgt, 0.5, 8, 8)               # quant/quantize.py:48-76 construction
+    assert q.weight is layer.weight
+    with torch.no_grad():
+        y = q(_t(name + ":x").cuda())
+    ref = _t(name + ":y")
+    assert tuple(y.shape) == tuple(ref.shape) and y.dtype == torch.float32
+    assert rel(y, ref) <= TOL, (name, rel(y, ref))
+
+
+def test_sq_wrappers_on_shapes_the_shipped_file_cannot_run():
+    """SQConvT2d with real spatial extent (the reference's `.view` raises), the BEV backbone's shapes: 3x3 stride-2 conv with 128
+    channels, a k = s = 2 deconv whose N = oc*k*k exceeds one 256-column accumulator (cut into two launches), a 1x1 head."""
+    import qlidar
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((2, 128, 24, 20), generator=g)
+    x[:, 5] *= 15.0
+    conv = torch.nn.Conv2d(128, 128, 3, stride=2, padding=1)
+    deconv = torch.nn.ConvTranspose2d(128, 128, 2, stride=2)
+    head = torch.nn.Conv2d(128, 2, 1)
+    with torch.no_grad():
+        for m in (conv, deconv, head):
+            m.weight.copy_(torch.randn(m.weight.shape, generator=g) * 0.05)
+            m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+    refs = [O.sq_conv2d(x, conv.weight.detach(), conv.bias.detach(), 0.5, 2, 1),
+            O.sq_convT2d(x, deconv.weight.detach(), deconv.bias.detach(), 0.5, 2),
+            O.sq_conv2d(x, head.weight.detach(), head.bias.detach(), 0.5, 1, 0)]
+    mods = [qlidar.smoothquant_layer(conv.cuda(), qlidar.SQConv2d, 0.5, 8, 8),
+            qlidar.smoothquant_layer(deconv.cuda(), qlidar.SQConvT2d, 0.5, 8, 8),
+            qlidar.smoothquant_layer(head.cuda(), qlidar.SQConv2d, 0.5, 8, 8)]
+    for q, ref in zip(mods, refs):
+        with torch.no_grad():
+            y = q(x.cuda())
+        assert tuple(y.shape) == tuple(ref.shape)
+        assert rel(y, ref) <= TOL, (type(q).__name__, rel(y, ref))
+
+
+def test_sparse_sqconv2d_stays_sparse_and_matches_the_oracle():
+    """quant_voxelnext.SQConv2d(sqsubm2d, subm2d) -- the SparseModule over SQSubM2d + SubMConv2d -- on a sparse 2-D tensor of the
+    Waymo BEV grid size (188 x 188 would be the stride-8 map; here the full 1504 x 1504 stage-1 footprint to make the point): no
+    dense tensor is ever formed; result == W8A8 SmoothQuant per input channel (the unfold's per-column maxima on a sparse input)."""
+    import qlidar
+    rng = np.random.default_rng(5)
+    H = W = 1504
+    n = 6000
+    yx = np.unique(rng.integers(0, H, size=(n, 2)), axis=0)
+    # clustered sites so that the 3x3 neighbourhoods are not empty
+    yx = np.unique(np.concatenate([yx, yx + [0, 1], yx + [1, 0]]), axis=0)
+    yx = yx[(yx[:, 0] < H) & (yx[:, 1] < W)]
+    coords3 = np.concatenate([np.zeros((yx.shape[0], 1), np.int64), yx], axis=1).astype(np.int32)
+    C = 64
+    x = torch.from_numpy(rng.normal(size=(coords3.shape[0], C)).astype(np.float32))
+    x[::50, 7] *= 20
+    x = x.half().float()
+    subm = qlidar.SubMConv2d(C, C, 3, padding=1, bias=True, indice_key="s2d").cuda()
+    sq = qlidar.SQSubM2d(C, C, 3, 1, 1, input_quantizer=qlidar.TensorQuantizer(qlidar.QuantDescriptor(num_bits=8)),
+                         weight_quantizer=qlidar.TensorQuantizer(qlidar.QuantDescriptor(num_bits=8, axis=(0))), scaling_factor=0.5)
+    wrap = qlidar.quant_voxelnext.SQConv2d(sq, subm)
+    assert torch.equal(sq.weight.data, subm.weight.data.permute(0, 3, 1, 2))            # quant_voxelnext.py:123
+    st = qlidar.SparseConvTensor(x.cuda().half(), torch.from_numpy(coords3).cuda(), [H, W], 1)
+    before = torch.cuda.max_memory_allocated()
+    with torch.no_grad():
+        y = wrap(st)
+    assert torch.cuda.max_memory_allocated() - before < 200 << 20                      # a dense 1504^2 x 64 fp32 unfold would be > 5 GB
+    coords4 = np.stack([coords3[:, 0], np.zeros_like(coords3[:, 0]), coords3[:, 1], coords3[:, 2]], axis=1).astype(np.int32)
+    nbr = O.rulebook_subm(coords4, [1, H, W], (1, 3, 3))
+    w = subm.weight.detach().cpu().reshape(C, 1, 3, 3, C)
+    _, ref, _, _ = O.qconv_w8a8_sq(x, nbr, w, subm.bias.detach().cpu(), 0.5)
+    assert np.array_equal(y.indices.cpu().numpy(), coords3)
+    assert rel(y.features, ref) <= 3e-3, rel(y.features, ref)

@@ -215,3 +215,65 @@ def test_mirror_layers_agree_with_reference_math_teacher_forced():
                 x = O.SpT(None, y.coords, y.spatial_shape, 1, y.rulebooks)
             prev_h = r["out"]
     assert checked == 20
+
+
+def test_sq_dense_wrappers_match_the_references_own_file():
+    """oracle/sq_* restate quant/smoothquant.py; tests/golden/sq_dense.npz holds what that file itself computed (imported unmodified,
+    built the way quantize.py:48-76 builds it).  1e-5 of max|y|: same operations, same order."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sq_dense.npz"))
+    T = lambda k: torch.from_numpy(g[k])
+    cases = {
+        "conv2d_3x3_s1": lambda n: O.sq_conv2d(T(n + ":x"), T(n + ":w"), T(n + ":b"), 0.5, 1, 1),
+        "conv2d_3x3_s2": lambda n: O.sq_conv2d(T(n + ":x"), T(n + ":w"), T(n + ":b"), 0.5, 2, 1),
+        "conv2d_1x1_head": lambda n: O.sq_conv2d(T(n + ":x"), T(n + ":w"), T(n + ":b"), 0.5, 1, 0),
+        "conv1d_k3": lambda n: O.sq_conv1d(T(n + ":x"), T(n + ":w"), T(n + ":b"), 0.5, 1, 1),
+        "convT2d_k2_s2": lambda n: O.sq_convT2d(T(n + ":x"), T(n + ":w"), T(n + ":b"), 0.5, 2),
+        "linear": lambda n: O.sq_linear(T(n + ":x"), T(n + ":w"), T(n + ":b"), 0.5),
+    }
+    for name, fn in cases.items():
+        y, ref = fn(name), T(name + ":y")
+        assert y.shape == ref.shape, name
+        assert (y - ref).abs().max().item() <= 1e-5 * ref.abs().max().item(), name
+
+
+def test_sq_surgery_builds_wrappers_like_the_reference():
+    """smoothquant() / smoothquant_layer() (quant/quantize.py:48-115): `__new__` + attribute copy from the fp32 layer (tuples
+    collapse to their first element), quantisers attached, dotted-path no_list honoured; forward without a scaling_factor raises."""
+    import qlidar
+    net = torch.nn.Sequential()
+    net.add_module("blocks", torch.nn.Sequential(torch.nn.Conv2d(16, 32, 3, stride=2, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(32, 32, 3, padding=1)))
+    net.add_module("head", torch.nn.Conv2d(32, 3, 1))
+    w0 = net.blocks[0].weight
+    qlidar.smoothquant(net, {}, "", 0.5, 8, 8, torch.nn.Conv2d, qlidar.SQConv2d, ["head"])
+    assert isinstance(net.blocks[0], qlidar.SQConv2d) and isinstance(net.blocks[2], qlidar.SQConv2d) and isinstance(net.head, torch.nn.Conv2d)
+    q = net.blocks[0]
+    assert q.weight is w0 and q.kernel_size == 3 and q.stride == 2 and q.padding == 1 and q.scaling_factor == 0.5
+    assert q._weight_quantizer.num_bits == 8 and q._weight_quantizer.axis in ((0,), 0) and q._input_quantizer.axis is None
+    q.scaling_factor = None
+    with pytest.raises(ValueError):
+        q(torch.zeros(1, 16, 4, 4))
+    with pytest.raises(ValueError):
+        qlidar.smoothquant_layer(torch.nn.Conv2d(4, 4, 1), qlidar.SQConv2d, None, 8, 8)
+    # SQSubM2d: the constructor the reference intended (its own raises NameError), ValueError without a scaling factor
+    sq = qlidar.SQSubM2d(16, 16, 3, 1, 1, device="cpu", scaling_factor=None)
+    with pytest.raises(ValueError):
+        sq(torch.zeros(1, 16, 4, 4))
+
+
+def test_sqsubm2d_forward_matches_the_restated_file():
+    """qlidar.SQSubM2d.forward(dense) -> (weight, x): the literal unfold -> scale -> quantise -> fold sequence of quant/SQSubM2d.py:22-91
+    (whose class cannot be constructed as shipped) against the oracle's restatement; weight in the sparse conv's (oc, kh, kw, ic) layout."""
+    import qlidar
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn((2, 8, 9, 7), generator=g)
+    x[:, 3] *= 9
+    sq = qlidar.SQSubM2d(8, 12, 3, 1, 1, input_quantizer=qlidar.TensorQuantizer(qlidar.QuantDescriptor(num_bits=8)),
+                         weight_quantizer=qlidar.TensorQuantizer(qlidar.QuantDescriptor(num_bits=8, axis=(0))), device="cpu", scaling_factor=0.5)
+    with torch.no_grad():
+        sq.weight.copy_(torch.randn(sq.weight.shape, generator=g) * 0.3)
+        w, xo = sq(x)
+    w_ref, x_ref = O.sq_subm2d(x, sq.weight.detach(), 0.5)
+    assert tuple(w.shape) == (12, 3, 3, 8) and tuple(xo.shape) == (2, 9, 7, 8)
+    assert (w - w_ref).abs().max().item() <= 1e-6 * w_ref.abs().max().item()
+    assert (xo - x_ref).abs().max().item() <= 1e-5 * x_ref.abs().max().item()
