@@ -121,8 +121,17 @@ def voxelize_hard(points: np.ndarray, pc_range, voxel_size, max_pts: int, max_vo
     return voxels, coords, num
 
 
-def mean_vfe(voxels: np.ndarray, num_points: np.ndarray) -> np.ndarray:
-    """pcdet/models/backbones_3d/vfe/mean_vfe.py:25-29: sum over T / clamp_min(num_points, 1)."""
+def mean_vfe(voxels: np.ndarray, num_points: np.ndarray, sequential: bool = False) -> np.ndarray:
+    """pcdet/models/backbones_3d/vfe/mean_vfe.py:25-29: sum over T / clamp_min(num_points, 1).
+    The reference's summation order is whatever torch.sum(dim=1) does on its device (a cascade on the CPU: it differs from a
+    left-to-right sum in the last bit of ~5 % of the means).  sequential=True adds the T slots left to right in fp32 -- the order
+    of the CUDA voxeliser (csrc/voxelize.cu k_vox_finalize) -- for the kernel-numerics mirror, whose int8 codes must match bit for bit."""
+    if sequential:
+        s = np.zeros((voxels.shape[0], voxels.shape[2]), dtype=np.float32)
+        for t in range(voxels.shape[1]):
+            s = s + voxels[:, t]
+        n = np.maximum(num_points.astype(np.float32), np.float32(1.0)).reshape(-1, 1)
+        return (s / n).astype(np.float32)
     s = torch.from_numpy(voxels).sum(dim=1)
     n = torch.clamp_min(torch.from_numpy(num_points).view(-1, 1).float(), 1.0)
     return (s / n).numpy()
@@ -138,7 +147,7 @@ def collate_voxels(per_frame):
     return np.concatenate(feats), np.concatenate(coords), np.concatenate(nums)
 
 
-def voxelize_mean_batch(points_b: np.ndarray, pc_range, voxel_size, max_pts: int, max_voxels: int):
+def voxelize_mean_batch(points_b: np.ndarray, pc_range, voxel_size, max_pts: int, max_voxels: int, sequential: bool = False):
     """Fused a1+a2+a4 on a collated `points (sum P, 1+F)` array (batch index in column 0, frames
     contiguous): per-frame hard voxelization, mean VFE, `[b,z,y,x]` coords.  `max_voxels` is per frame.
     This is the semantics of the GPU op `ql_voxelize_mean` (first-touch order over the whole array)."""
@@ -148,7 +157,7 @@ def voxelize_mean_batch(points_b: np.ndarray, pc_range, voxel_size, max_pts: int
     for b in range(B):
         out.append(voxelize_hard(points_b[bidx == b, 1:], pc_range, voxel_size, max_pts, max_voxels))
     voxels, coords, nums = collate_voxels(out)
-    return mean_vfe(voxels, nums), coords, nums
+    return mean_vfe(voxels, nums, sequential), coords, nums
 
 
 def voxelize_dynamic_mean(points_b: np.ndarray, pc_range, voxel_size):
@@ -426,6 +435,25 @@ def sparse_conv_int(qx: torch.Tensor, nbr: np.ndarray, qw: torch.Tensor) -> torc
             continue
         g = x64.index_select(0, nbr_t[k][o])
         out.index_add_(0, o, g @ w[:, k, :].t())
+    assert out.abs().max() < 2 ** 31 if out.numel() else True
+    return out.to(torch.int32)
+
+
+def sparse_conv_int_f64(qx: torch.Tensor, nbr: np.ndarray, qw: torch.Tensor) -> torch.Tensor:
+    """sparse_conv_int through float64 BLAS: int8 x int8 products and their sums (|acc| < 2^31) are exact in float64, and dgemm is
+    ~100x faster than torch's int64 matmul on the CPU -- what makes a full-size (146 k voxels x 4 frames) mirror run affordable.
+    tests/test_oracle.py holds it to sparse_conv_int bit for bit."""
+    oc, ic = qw.shape[0], qw.shape[-1]
+    K, M = nbr.shape
+    w = qw.reshape(oc, K, ic).to(torch.float64)
+    out = torch.zeros((M, oc), dtype=torch.float64)
+    nbr_t = torch.from_numpy(nbr.astype(np.int64))
+    x64 = qx.to(torch.float64)
+    for k in range(K):
+        o = torch.nonzero(nbr_t[k] >= 0).squeeze(1)
+        if o.numel() == 0:
+            continue
+        out.index_add_(0, o, x64.index_select(0, nbr_t[k][o]) @ w[:, k, :].t())
     assert out.abs().max() < 2 ** 31 if out.numel() else True
     return out.to(torch.int32)
 
@@ -879,7 +907,8 @@ def mirror_epilogue(acc: np.ndarray, s, shift, residual_h: Optional[np.ndarray],
 
 
 def mirror_backbone_w8a8_pt(prog, params, features, coords: np.ndarray, sparse_shape, batch_size: int,
-                            no_list=("conv_input.0",), act_amax: Optional[Dict[str, float]] = None, bits: int = 8):
+                            no_list=("conv_input.0",), act_amax: Optional[Dict[str, float]] = None, bits: int = 8, fast: bool = False,
+                            keep: bool = True):
     """Returns (record, encoded SpT with fp16-valued features).  record[name] = dict(codes int8 (N_in, C_in) or None for the
     stem, acc int32 or None, y32 fp32 epilogue values, out fp16, out_coords, amax_in).  act_amax: calibrated per-layer scalar
     amax (static); None = dynamic."""
@@ -925,13 +954,17 @@ def mirror_backbone_w8a8_pt(prog, params, features, coords: np.ndarray, sparse_s
                 codes = mirror_codes(x_h.astype(np.float32), m, bits)
             act_scale = np.float32(m / bound)
             qw, amax_w = quantize_weight_per_oc(w, 8)
-            acc = sparse_conv_int(torch.from_numpy(codes), nbr, qw).numpy()
+            acc = (sparse_conv_int_f64 if fast else sparse_conv_int)(torch.from_numpy(codes), nbr, qw).numpy()
             s = _f32c((amax_w / quant_bound(8)) * a) * act_scale
             y32 = mirror_epilogue(acc, s, shift, residual_h)
             r = dict(codes=codes, acc=acc, amax_in=m)
             prev_conv_now = True
         out_h = y32.astype(np.float16)
         r.update(y32=y32, out=out_h, out_coords=out_coords)
+        if not keep:                              # full-size runs: keep checksums only
+            r = dict(amax_in=r["amax_in"], n_out=out_h.shape[0], codes_sum=None if r["codes"] is None else int(r["codes"].astype(np.int64).sum()),
+                     codes_abs_sum=None if r["codes"] is None else int(np.abs(r["codes"].astype(np.int64)).sum()),
+                     out_bits_sum=int(out_h.view(np.uint16).astype(np.uint64).sum()))
         rec[spec.name] = r
         x_h, y32_prev, prev_was_conv = out_h, y32, prev_conv_now
         return SpT(None, out_coords, list(out_shape), x.batch_size, x.rulebooks if spec.subm else {})

@@ -20,37 +20,6 @@ __global__ void __launch_bounds__(256) k_bev_index(const uint2* __restrict__ tab
     idxmap[cell] = ql_hash_lookup(table, cap_mask, (uint32_t)cell);       // the linear cell index IS the key
 }
 
-// the same cell -> row map from a rank index (key-sorted rows: row == rank), one thread per 32-cell bitmap word
-__global__ void __launch_bounds__(256) k_bev_index_ranked(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_prefix,
-                                                          int64_t n_cells, int64_t n_rows, const int* __restrict__ n_dev,
-                                                          int* __restrict__ idxmap) {
-    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t cell0 = w * 32;
-    if (cell0 >= n_cells) return;
-    const int64_t n = n_dev ? min((int64_t)*n_dev, n_rows) : n_rows;
-    const uint32_t bits = bitmap[w];
-    uint32_t rank = bits ? word_prefix[w] : 0u;
-    const int lim = (int)min((int64_t)32, n_cells - cell0);
-    if (lim == 32) {
-        int v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const bool on = (bits >> i) & 1u;
-            v[i] = (on && (int64_t)rank < n) ? (int)rank : -1;
-            rank += on ? 1u : 0u;
-        }
-        int4* o = reinterpret_cast<int4*>(idxmap + cell0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = make_int4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    } else {
-        for (int i = 0; i < lim; ++i) {
-            const bool on = (bits >> i) & 1u;
-            idxmap[cell0 + i] = (on && (int64_t)rank < n) ? (int)rank : -1;
-            rank += on ? 1u : 0u;
-        }
-    }
-}
-
 template <typename T>
 __device__ __forceinline__ float to_f(T v);
 template <>
@@ -64,9 +33,12 @@ __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
 
-template <typename TIn, typename TOut, int VEC, int CC>
+// kRanked: the cell -> row lookup is fused into the writer (no idxmap pass, no second launch): the VEC cells of a thread are VEC
+// consecutive keys, VEC-aligned (VEC divides 32 and W), so they are bits of ONE bitmap word: row = word_prefix + popc(bits below).
+template <typename TIn, typename TOut, int VEC, int CC, bool kRanked>
 __global__ void __launch_bounds__(256) k_bev_write(const TIn* __restrict__ feats, int C, const int* __restrict__ idxmap, QlGrid g,
-                                                   TOut* __restrict__ out) {
+                                                   TOut* __restrict__ out, const uint32_t* __restrict__ bitmap,
+                                                   const uint32_t* __restrict__ word_prefix, int64_t n_rows, const int* __restrict__ n_dev) {
     const int xgroups = g.W / VEC;
     const int cchunks = C / CC;
     const int64_t total = (int64_t)cchunks * g.B * g.D * g.H * xgroups;
@@ -79,8 +51,22 @@ __global__ void __launch_bounds__(256) k_bev_write(const TIn* __restrict__ feats
     const int c0 = (int)t * CC;
     const int64_t cell0 = (((int64_t)b * g.D + d) * g.H + y) * g.W + (int64_t)xg * VEC;
     int idx[VEC];
+    if constexpr (kRanked) {
+        const int64_t n = n_dev ? min((int64_t)*n_dev, n_rows) : n_rows;
+        const uint32_t w = (uint32_t)(cell0 >> 5), sh = (uint32_t)(cell0 & 31);
+        const uint32_t bits = __ldg(bitmap + w);
+        const uint32_t mine = (bits >> sh) & ((VEC == 32) ? 0xFFFFFFFFu : ((1u << VEC) - 1u));
+        uint32_t rank = mine ? __ldg(word_prefix + w) + (uint32_t)__popc(bits & ((1u << sh) - 1u)) : 0u;
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) idx[v] = idxmap[cell0 + v];
+        for (int v = 0; v < VEC; ++v) {
+            const bool on = (mine >> v) & 1u;
+            idx[v] = (on && (int64_t)rank < n) ? (int)rank : -1;
+            rank += on ? 1u : 0u;
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) idx[v] = idxmap[cell0 + v];
+    }
     TOut vals[CC][VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
@@ -121,25 +107,42 @@ __global__ void __launch_bounds__(256) k_bev_write(const TIn* __restrict__ feats
     }
 }
 
+struct RankArgs {
+    const uint32_t* bitmap;
+    const uint32_t* word_prefix;
+    int64_t n_rows;
+    const int* n_dev;
+};
+
 template <typename TIn, typename TOut, int VEC, int CC>
-int launch_write(const void* feats, int C, const int* idxmap, QlGrid g, void* out, cudaStream_t st) {
+int launch_write(const void* feats, int C, const int* idxmap, QlGrid g, void* out, cudaStream_t st, const RankArgs* ra) {
     const int64_t total = (int64_t)(C / CC) * g.B * g.D * g.H * (g.W / VEC);
-    k_bev_write<TIn, TOut, VEC, CC><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const TIn*)feats, C, idxmap, g, (TOut*)out);
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (ra)
+        k_bev_write<TIn, TOut, VEC, CC, true><<<blocks, 256, 0, st>>>((const TIn*)feats, C, nullptr, g, (TOut*)out, ra->bitmap, ra->word_prefix,
+                                                                       ra->n_rows, ra->n_dev);
+    else
+        k_bev_write<TIn, TOut, VEC, CC, false><<<blocks, 256, 0, st>>>((const TIn*)feats, C, idxmap, g, (TOut*)out, nullptr, nullptr, 0, nullptr);
     return 0;
 }
 
 template <typename TIn, typename TOut>
-int dispatch_write(const void* feats, int C, const int* idxmap, QlGrid g, void* out, cudaStream_t st) {
+int dispatch_write(const void* feats, int C, const int* idxmap, QlGrid g, void* out, cudaStream_t st, const RankArgs* ra = nullptr) {
     constexpr int kMaxVec = 16 / (int)sizeof(TOut);                    // 8 for fp16, 4 for fp32
     const bool feat_vec = (C % 8 == 0);
     if (feat_vec) {
-        if (g.W % kMaxVec == 0) return launch_write<TIn, TOut, kMaxVec, 8>(feats, C, idxmap, g, out, st);
-        if (g.W % 4 == 0) return launch_write<TIn, TOut, 4, 8>(feats, C, idxmap, g, out, st);
-        if (g.W % 2 == 0) return launch_write<TIn, TOut, 2, 8>(feats, C, idxmap, g, out, st);
-        return launch_write<TIn, TOut, 1, 8>(feats, C, idxmap, g, out, st);
+        // 16 channels (one 32-byte feature segment) per thread when they divide C: half the threads, twice the stores in flight each
+        if (C % 16 == 0 && sizeof(TIn) == 2) {
+            if (g.W % kMaxVec == 0) return launch_write<TIn, TOut, kMaxVec, 16>(feats, C, idxmap, g, out, st, ra);
+            if (g.W % 4 == 0) return launch_write<TIn, TOut, 4, 16>(feats, C, idxmap, g, out, st, ra);
+        }
+        if (g.W % kMaxVec == 0) return launch_write<TIn, TOut, kMaxVec, 8>(feats, C, idxmap, g, out, st, ra);
+        if (g.W % 4 == 0) return launch_write<TIn, TOut, 4, 8>(feats, C, idxmap, g, out, st, ra);
+        if (g.W % 2 == 0) return launch_write<TIn, TOut, 2, 8>(feats, C, idxmap, g, out, st, ra);
+        return launch_write<TIn, TOut, 1, 8>(feats, C, idxmap, g, out, st, ra);
     }
-    if (g.W % 4 == 0) return launch_write<TIn, TOut, 4, 1>(feats, C, idxmap, g, out, st);
-    return launch_write<TIn, TOut, 1, 1>(feats, C, idxmap, g, out, st);
+    if (g.W % 4 == 0) return launch_write<TIn, TOut, 4, 1>(feats, C, idxmap, g, out, st, ra);
+    return launch_write<TIn, TOut, 1, 1>(feats, C, idxmap, g, out, st, ra);
 }
 
 }  // namespace
@@ -179,14 +182,14 @@ extern "C" int ql_bev_densify_ranked(const void* feats, int32_t in_dtype, int32_
     if (workspace_bytes < ql_bev_densify_workspace_bytes(B, D, H, W)) return QL_ERR_WORKSPACE;
     QlGrid g{B, D, H, W};
     cudaStream_t st = (cudaStream_t)stream_;
-    int* idxmap = (int*)workspace;
-    const int64_t cells = (int64_t)B * D * H * W;
-    const int64_t words = (cells + 31) / 32;
-    k_bev_index_ranked<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(bitmap, word_prefix, cells, n_cap, n_dev, idxmap);
-    if (in_dtype == QL_F16 && out_dtype == QL_F16) dispatch_write<__half, __half>(feats, c, idxmap, g, out, st);
-    else if (in_dtype == QL_F16 && out_dtype == QL_F32) dispatch_write<__half, float>(feats, c, idxmap, g, out, st);
-    else if (in_dtype == QL_F32 && out_dtype == QL_F16) dispatch_write<float, __half>(feats, c, idxmap, g, out, st);
-    else dispatch_write<float, float>(feats, c, idxmap, g, out, st);
+    // one kernel: the rank lookup is fused into the writer (round 1 ran an index pass into `workspace` first: two launches for a
+    // 30 us stage); the workspace argument is kept for ABI stability and unused
+    (void)workspace;
+    const RankArgs ra{bitmap, word_prefix, n_cap, n_dev};
+    if (in_dtype == QL_F16 && out_dtype == QL_F16) dispatch_write<__half, __half>(feats, c, nullptr, g, out, st, &ra);
+    else if (in_dtype == QL_F16 && out_dtype == QL_F32) dispatch_write<__half, float>(feats, c, nullptr, g, out, st, &ra);
+    else if (in_dtype == QL_F32 && out_dtype == QL_F16) dispatch_write<float, __half>(feats, c, nullptr, g, out, st, &ra);
+    else dispatch_write<float, float>(feats, c, nullptr, g, out, st, &ra);
     QL_CUDA_CHECK_LAST();
     return QL_OK;
 }

@@ -173,3 +173,90 @@ def test_bev_channel_sums(frame):
     per_c = out.view(B, C, D, H, W).double().sum(dim=(0, 2, 3, 4))
     assert torch.equal(per_c, f[:m].double().sum(dim=0))
     assert int((out != 0).sum().item()) == int((f[:m] != 0).sum().item())
+
+
+# ------------------------------------------------------------------------------------------------ full-size oracle fixture
+# BASELINE configs[1] at its real size against the ORACLE'S OWN OUTPUTS (tests/golden/fullsize_waymo_b4.npz, produced once in the
+# build container by tests/golden/make_golden_fullsize.py: minutes of CPU, too long for the GPU box).
+@pytest.fixture(scope="module")
+def full():
+    import os
+    import qlidar_oracle as O
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize_waymo_b4.npz")
+    g = np.load(p)
+    pts = O.synth_batch("waymo", 4)                                       # seeds 1000-1003, the bench's frames
+    assert pts.shape[0] == int(g["n_points"])
+    return g, pts, O
+
+
+def _full_engine(O, pts, act_bits, cw, amax=None):
+    import qlidar
+    from test_gpu_backbone import build
+    c = O.CONFIGS["waymo"]
+    grid = O.grid_size_xyz(c["pc_range"], c["voxel_size"])
+    prog, P, bb = build("VoxelResBackBone8x", 5, grid)
+    qlidar.q_conv3d(bb, {}, "", 8, act_bits, cw, (qlidar.SubMConv3d, qlidar.SparseConv3d), ["conv_input.0"])
+    if amax is not None:
+        for n, m in bb.named_modules():
+            if n.endswith("act_quant"):
+                m.amax = torch.tensor(float(amax[n[:-len(".act_quant")]]), dtype=torch.float32, device="cuda")
+    cap = 4 * c["max_voxels"]
+    eng = qlidar.BackboneEngine(bb, 4, cap, max_points=pts.shape[0], pc_range=c["pc_range"], voxel_size=c["voxel_size"],
+                                max_pts_per_voxel=c["max_pts"], use_graph=True, max_voxels_per_frame=c["max_voxels"],
+                                stage_caps=[cap, int(1.25 * cap), int(0.75 * cap), int(0.5 * cap), int(0.5 * cap)])
+    for _ in range(2):
+        out = eng.forward_points(torch.from_numpy(pts))
+    torch.cuda.synchronize()
+    assert not eng.overflowed()
+    return eng, out
+
+
+def test_fullsize_w8a16_cw_matches_the_oracles_outputs(full):
+    """The headline configuration (W8A16, cw) on the bench's four frames: stage counts and encoded indices equal the oracle's, every
+    16th encoded row within 1e-2 of max|ref| (the north star's feature tolerance), per-channel sums of every stage within 1e-3."""
+    g, pts, O = full
+    eng, out = _full_engine(O, pts, 16, True)
+    counts = eng.counts()
+    assert counts == [int(v) for v in g["stage_counts"]]
+    n = counts[-1]
+    assert np.array_equal(out["encoded_coords"][:n].cpu().numpy(), g["encoded_indices"].astype(np.int32))
+    stride = int(g["row_stride"])
+    ref_rows = torch.from_numpy(g["w8a16_cw:encoded_rows"].astype(np.float32))
+    got_rows = out["encoded_features"][:n][::stride].float().cpu()
+    m = float(g["w8a16_cw:encoded_abs_max"])
+    assert (got_rows - ref_rows).abs().max().item() <= 1e-2 * m
+    sums = out["encoded_features"][:n].double().sum(dim=0).cpu().numpy()
+    ref_sums = g["w8a16_cw:encoded_channel_sums"]
+    assert np.abs(sums - ref_sums).max() <= 1e-3 * np.abs(ref_sums).max()
+    for name, (f, st) in out["taps"].items():
+        k = counts[eng.stages.index(st)]
+        s = f[:k].double().sum(dim=0).cpu().numpy()
+        r = g[f"w8a16_cw:{name}_channel_sums"]
+        assert np.abs(s - r).max() <= 1e-3 * np.abs(r).max(), name
+    # the BEV hand-off carries exactly those rows: channel c*D + d sums back to channel c
+    bev = out["spatial_features"].double().sum(dim=(0, 2, 3)).view(-1, 2).sum(dim=1).cpu().numpy()
+    assert np.abs(bev - ref_sums).max() <= 1e-3 * np.abs(ref_sums).max()
+
+
+def test_fullsize_w8a8_pt_static_is_bit_exact_against_the_mirror(full):
+    """W8A8 per-tensor with frozen amax on the same four frames, from raw points: the int8 codes of all 20 quantised layers and the fp16
+    rows of all 21 layers have the oracle mirror's checksums, and every 16th encoded row is identical -- tolerance zero at 582 k voxels."""
+    g, pts, O = full
+    names = [str(s) for s in g["w8a8_pt_static:layers"]]
+    amax = {n: a for n, a in zip(names, g["w8a8_pt_static:amax"])}
+    eng, out = _full_engine(O, pts, 8, False, amax)
+    counts = eng.counts()
+    assert counts == [int(v) for v in g["stage_counts"]]
+    assert [L.name for L in eng.layers] == names
+    for i, L in enumerate(eng.layers):
+        n_in, n_out = counts[L.stage_in], counts[L.stage_out]
+        assert n_out == int(g["w8a8_pt_static:n_out"][i])
+        if L.kind == "i8":
+            codes = L.q_buf[:n_in].to(torch.int64)
+            assert int(codes.sum().item()) == int(g["w8a8_pt_static:codes_sum"][i]), L.name
+            assert int(codes.abs().sum().item()) == int(g["w8a8_pt_static:codes_abs_sum"][i]), L.name
+        bits = int(L.out[:n_out].view(torch.int16).to(torch.int64).bitwise_and(0xFFFF).sum().item())
+        assert bits == int(g["w8a8_pt_static:out_bits_sum"][i]), L.name
+    n = counts[-1]
+    got = out["encoded_features"][:n][::int(g["row_stride"])].cpu().numpy()
+    assert np.array_equal(got.view(np.uint16), g["w8a8_pt_static:encoded_rows"].view(np.uint16))

@@ -277,3 +277,12 @@ def test_sqsubm2d_forward_matches_the_restated_file():
     assert tuple(w.shape) == (12, 3, 3, 8) and tuple(xo.shape) == (2, 9, 7, 8)
     assert (w - w_ref).abs().max().item() <= 1e-6 * w_ref.abs().max().item()
     assert (xo - x_ref).abs().max().item() <= 1e-5 * x_ref.abs().max().item()
+
+
+def test_sparse_conv_int_f64_is_exact():
+    rng = np.random.default_rng(12)
+    coords = O.synth_surface_sheet(40, seed=4, depth=10)
+    nbr = O.rulebook_subm(coords, [10, 40, 40], 3)
+    qx = torch.from_numpy(rng.integers(-127, 128, size=(coords.shape[0], 64)).astype(np.int8))
+    qw = torch.from_numpy(rng.integers(-127, 128, size=(32, 3, 3, 3, 64)).astype(np.int8))
+    assert torch.equal(O.sparse_conv_int_f64(qx, nbr, qw), O.sparse_conv_int(qx, nbr, qw))
