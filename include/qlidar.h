@@ -295,6 +295,40 @@ int ql_bev_merge2d_multi(int32_t n_seg, const void* const* feats, int32_t in_dty
                          int32_t B, int32_t H, int32_t W, void* out_feats, int32_t out_dtype, int32_t* out_coords, int32_t out_coord_cols,
                          int64_t n_out_cap, int32_t* n_out_dev, void* workspace, size_t workspace_bytes, ql_stream_t stream);
 
+/* ---- CenterHead post-processing, all on the device (replaces CenterHead.generate_predicted_boxes,
+ *      pcdet/models/dense_heads/center_head.py:297-365 -> centernet_utils._topk / decode_bbox_from_heatmap
+ *      (model_utils/centernet_utils.py:155-241) -> model_nms_utils.class_agnostic_nms (model_nms_utils.py:6-25) ->
+ *      iou3d_nms_utils.nms_gpu (ops/iou3d_nms/iou3d_nms_utils.py:120-135) -> nms_kernel + the HOST sweep of iou3d_nms.cpp
+ *      (ops/iou3d_nms/src/iou3d_nms_kernel.cu:295-339, iou3d_nms.cpp:137-183)).
+ *
+ *  ql_centerhead_decode: one head.  Maps are fp32 NCHW device arrays: hm [B,C,H,W] LOGITS (sigmoid is applied here), center
+ *      [B,2,H,W], center_z [B,1,H,W], dim [B,3,H,W] (log sizes; exp is applied here), rot [B,2,H,W] (cos, sin), vel [B,2,H,W] or
+ *      NULL, iou [B,1,H,W] or NULL.  K = MAX_OBJ_PER_SAMPLE (<= 1024).  voxel_size_xy / pc_min_xy / center_limit_range
+ *      (POST_CENTER_LIMIT_RANGE, 6 floats) are HOST arrays.  score_thresh < 0 = no threshold.  class_map: device int32 [C] or
+ *      NULL (class_id_mapping_each_head).  Outputs per frame, in descending score order, masked rows removed (the reference's
+ *      boolean-mask indexing): out_boxes [B,K,7 or 9] (x, y, z, dx, dy, dz, heading[, vx, vy]), out_scores [B,K], out_labels
+ *      [B,K] (mapped class, 0-based), out_iou [B,K] ((iou + 1) / 2) when iou is given, out_count [B]. */
+size_t ql_centerhead_decode_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W);
+int ql_centerhead_decode(const float* hm, const float* center, const float* center_z, const float* dim, const float* rot,
+                         const float* vel, const float* iou, int32_t B, int32_t C, int32_t H, int32_t W, int32_t K,
+                         float feature_map_stride, const float* voxel_size_xy, const float* pc_min_xy,
+                         const float* center_limit_range, float score_thresh, const int32_t* class_map, float* out_boxes,
+                         float* out_scores, int32_t* out_labels, float* out_iou, int32_t* out_count, void* workspace,
+                         size_t workspace_bytes, ql_stream_t stream);
+
+/*  ql_nms_rotated: greedy rotated-BEV-IoU NMS per frame.  boxes [B, n_cap, box_stride] fp32, each frame's first counts[b] rows
+ *      (device int32 [B]; NULL = n_cap) valid and ALREADY in descending score order (ql_centerhead_decode's order; nms_gpu sorts
+ *      first, iou3d_nms_utils.py:127-131).  The first min(count, pre_max) boxes take part (NMS_PRE_MAXSIZE); a box is suppressed
+ *      when its IoU with a kept earlier box is > thresh; at most post_max are kept (NMS_POST_MAXSIZE).  Outputs: keep
+ *      [B, post_max] indices into the frame's rows (-1 padded), keep_count [B]; optional gathers out_boxes [B, post_max, box_dim],
+ *      out_scores / out_labels [B, post_max] from scores / labels [B, n_cap] (labels get label_offset added: the reference's
+ *      final "+ 1").  iou_out (optional, tests): [B, n_cap, n_cap], upper-triangle pairwise IoU.  n_cap <= 2048. */
+size_t ql_nms_rotated_workspace_bytes(int32_t B, int32_t n_cap);
+int ql_nms_rotated(const float* boxes, int32_t box_stride, int32_t box_dim, const float* scores, const int32_t* labels,
+                   const int32_t* counts, int32_t B, int32_t n_cap, float thresh, int32_t pre_max, int32_t post_max,
+                   int32_t label_offset, int32_t* keep, int32_t* keep_count, float* out_boxes, float* out_scores,
+                   int32_t* out_labels, float* iou_out, void* workspace, size_t workspace_bytes, ql_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

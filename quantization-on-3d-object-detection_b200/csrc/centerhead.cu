@@ -1,0 +1,458 @@
+// CenterHead post-processing on the device: heat-map top-K, box decode, range / score mask, rotated BEV NMS with the
+// suppression sweep on the GPU -- no device->host copy anywhere on the path.
+//
+// Replaces:
+//   CenterHead.generate_predicted_boxes              pcdet/models/dense_heads/center_head.py:297-365
+//   centernet_utils._topk / decode_bbox_from_heatmap pcdet/models/model_utils/centernet_utils.py:155-241
+//   model_nms_utils.class_agnostic_nms               pcdet/models/model_utils/model_nms_utils.py:6-25
+//   iou3d_nms_utils.nms_gpu                          pcdet/ops/iou3d_nms/iou3d_nms_utils.py:120-135
+//   nms_kernel + the host sweep of iou3d_nms.cpp     pcdet/ops/iou3d_nms/src/iou3d_nms_kernel.cu:295-339, iou3d_nms.cpp:137-183
+//     (the reference cudaMallocs the mask, copies it to the host synchronously and sweeps it in a serial CPU loop per call)
+//
+// Kernels (4 launches per head, all stream ordered):
+//   k_ch_candidates     every heat-map cell: score = sigmoid(logit); cells above the score threshold are appended to the
+//                       frame's candidate list (the reference thresholds AFTER its top-K; a cell below the threshold can never
+//                       be output, so dropping it first changes nothing but the amount of sorting)
+//   k_ch_select_decode  one CTA per frame: exact top-K of the candidates (radix select on the score bits when the list is
+//                       longer than the sort width, then a bitonic sort by (score desc, cell index asc)), gather of the
+//                       regression maps, decode, range mask, order-preserving compaction
+//   k_nms_mask          64 x 64 blocks of the upper triangle of the pairwise rotated-IoU matrix -> suppression bit masks
+//   k_nms_sweep         one CTA per frame: mask rows staged in shared memory, one warp runs the greedy sweep, the CTA gathers
+//                       the kept boxes / scores / labels
+#include "ql_common.cuh"
+
+namespace {
+
+constexpr int kSelThreads = 1024;            // == the bitonic sort width; MAX_OBJ_PER_SAMPLE (K) must not exceed it
+constexpr int kNmsBlock = 64;                // boxes per mask word
+constexpr int kMaxBoxDim = 9;                // x y z dx dy dz heading (+ vx vy)
+
+struct HeadMaps {
+    const float* hm;        // [B, C, H, W] logits
+    const float* center;    // [B, 2, H, W]
+    const float* center_z;  // [B, 1, H, W]
+    const float* dim;       // [B, 3, H, W] log-sizes
+    const float* rot;       // [B, 2, H, W] (cos, sin)
+    const float* vel;       // [B, 2, H, W] or null
+    const float* iou;       // [B, 1, H, W] or null
+    int B, C, H, W, K;
+    float stride, vsx, vsy, pcx, pcy;
+    float lim[6];
+    float score_thresh;     // < 0: no score threshold
+    const int* class_map;   // [C] or null: label = class_map[class]
+};
+
+__device__ __forceinline__ float sigmoidf_ref(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }   // torch: 1 / (1 + exp(-x))
+
+__global__ void __launch_bounds__(256) k_ch_candidates(HeadMaps M, uint2* __restrict__ cand, int* __restrict__ cand_count) {
+    const int64_t n = (int64_t)M.C * M.H * M.W;
+    const int b = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool pass = false;
+    float s = 0.f;
+    if (i < n) {
+        s = sigmoidf_ref(M.hm[(int64_t)b * n + i]);
+        pass = M.score_thresh < 0.f || s > M.score_thresh;
+    }
+    const uint32_t vote = __ballot_sync(0xffffffffu, pass);
+    if (vote == 0u) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&cand_count[b], __popc(vote));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (pass) cand[(int64_t)b * n + base + __popc(vote & ((1u << lane) - 1u))] = make_uint2(__float_as_uint(s), (uint32_t)i);
+}
+
+// descending by score bits (scores are positive floats: their bit patterns order like the values), ties by ascending cell index
+__device__ __forceinline__ uint64_t sort_key(uint32_t score_bits, uint32_t idx) { return ((uint64_t)score_bits << 32) | (uint64_t)(~idx); }
+
+__global__ void __launch_bounds__(kSelThreads) k_ch_select_decode(HeadMaps M, const uint2* __restrict__ cand, const int* __restrict__ cand_count,
+                                                                   int box_dim, float* __restrict__ out_boxes, float* __restrict__ out_scores,
+                                                                   int* __restrict__ out_labels, float* __restrict__ out_iou, int* __restrict__ out_count) {
+    __shared__ uint64_t keys[kSelThreads];
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_mask, s_remaining, s_fill;
+    __shared__ int warp_sums[kSelThreads / 32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int64_t n_cells = (int64_t)M.C * M.H * M.W;
+    const uint2* list = cand + (int64_t)b * n_cells;
+    const int n = cand_count[b];
+    keys[tid] = 0ull;
+    if (tid == 0) { s_prefix = 0u; s_mask = 0u; s_remaining = (uint32_t)M.K; s_fill = 0u; }
+    __syncthreads();
+    if (n <= kSelThreads) {
+        if (tid < n) { const uint2 e = list[tid]; keys[tid] = sort_key(e.x, e.y); }
+    } else {
+        // radix select, 8 bits per pass from the top: after 4 passes s_prefix is the K-th largest score exactly and s_remaining the
+        // number of candidates EQUAL to it that belong to the top K
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (int j = tid; j < 256; j += kSelThreads) hist[j] = 0u;
+            __syncthreads();
+            const uint32_t prefix = s_prefix, mask = s_mask;
+            for (int j = tid; j < n; j += kSelThreads) {
+                const uint32_t k = list[j].x;
+                if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t rem = s_remaining, d = 255u;
+                for (;; --d) {
+                    const uint32_t h = hist[d];
+                    if (h >= rem || d == 0u) break;
+                    rem -= h;
+                }
+                s_remaining = rem;
+                s_prefix = prefix | (d << shift);
+                s_mask = mask | (255u << shift);
+            }
+            __syncthreads();
+        }
+        const uint32_t kth = s_prefix;
+        // everything above the K-th score, then the ties (as many as the sort width holds; the sort orders them by cell index)
+        for (int j = tid; j < n; j += kSelThreads) {
+            const uint2 e = list[j];
+            if (e.x > kth) keys[atomicAdd(&s_fill, 1u)] = sort_key(e.x, e.y);
+        }
+        __syncthreads();
+        for (int j = tid; j < n; j += kSelThreads) {
+            const uint2 e = list[j];
+            if (e.x == kth) {
+                const uint32_t pos = atomicAdd(&s_fill, 1u);
+                if (pos < (uint32_t)kSelThreads) keys[pos] = sort_key(e.x, e.y);
+            }
+        }
+    }
+    __syncthreads();
+    // bitonic sort, descending
+    for (int size = 2; size <= kSelThreads; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const int partner = tid ^ stride;
+            if (partner > tid) {
+                const uint64_t a = keys[tid], c = keys[partner];
+                const bool desc = (tid & size) == 0;
+                if (desc ? a < c : a > c) { keys[tid] = c; keys[partner] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    // decode candidate `tid` of the frame's top K
+    const int n_top = n < M.K ? n : M.K;
+    bool keep = false;
+    float box[kMaxBoxDim];
+    float score = 0.f, iou_v = 0.f;
+    int label = 0;
+    if (tid < n_top) {
+        const uint64_t k = keys[tid];
+        const uint32_t idx = ~(uint32_t)k;
+        score = __uint_as_float((uint32_t)(k >> 32));
+        const int hw = M.H * M.W;
+        const int cls = (int)(idx / (uint32_t)hw), cell = (int)(idx % (uint32_t)hw);
+        const int y = cell / M.W, x = cell % M.W;
+        const int64_t f = (int64_t)b * hw;                                  // frame offset in units of one H*W plane
+        const float cx = M.center[(f * 2 + 0 * hw) + cell], cy = M.center[(f * 2 + 1 * hw) + cell];
+        // xs = (x + center_x) * stride * voxel_x + pc_min_x, one fp32 rounding per torch op (centernet_utils.py:188-193)
+        box[0] = __fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn((float)x, cx), M.stride), M.vsx), M.pcx);
+        box[1] = __fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn((float)y, cy), M.stride), M.vsy), M.pcy);
+        box[2] = M.center_z[f + cell];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) box[3 + j] = expf(M.dim[(f * 3 + (int64_t)j * hw) + cell]);
+        const float rc = M.rot[(f * 2 + 0 * hw) + cell], rs = M.rot[(f * 2 + 1 * hw) + cell];
+        box[6] = atan2f(rs, rc);
+        box[7] = box[8] = 0.f;
+        if (M.vel) { box[7] = M.vel[(f * 2 + 0 * hw) + cell]; box[8] = M.vel[(f * 2 + 1 * hw) + cell]; }
+        if (M.iou) iou_v = __fmul_rn(__fadd_rn(M.iou[f + cell], 1.0f), 0.5f);
+        label = M.class_map ? M.class_map[cls] : cls;
+        keep = box[0] >= M.lim[0] && box[1] >= M.lim[1] && box[2] >= M.lim[2] && box[0] <= M.lim[3] && box[1] <= M.lim[4] && box[2] <= M.lim[5];
+        if (M.score_thresh >= 0.f) keep = keep && score > M.score_thresh;
+    }
+    // order-preserving compaction over the CTA
+    const uint32_t vote = __ballot_sync(0xffffffffu, keep);
+    const int lane = tid & 31, wid = tid >> 5;
+    if (lane == 0) warp_sums[wid] = __popc(vote);
+    __syncthreads();
+    if (wid == 0) {
+        int v = warp_sums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        warp_sums[lane] = v;                                                // inclusive
+    }
+    __syncthreads();
+    if (keep) {
+        const int pos = (wid ? warp_sums[wid - 1] : 0) + __popc(vote & ((1u << lane) - 1u));
+        float* o = out_boxes + ((int64_t)b * M.K + pos) * box_dim;
+        for (int j = 0; j < box_dim; ++j) o[j] = box[j];
+        out_scores[(int64_t)b * M.K + pos] = score;
+        out_labels[(int64_t)b * M.K + pos] = label;
+        if (out_iou) out_iou[(int64_t)b * M.K + pos] = iou_v;
+    }
+    if (tid == 0) out_count[b] = warp_sums[kSelThreads / 32 - 1];
+}
+
+// ---------------------------------------------------------------------------------------------- rotated BEV IoU
+// Two rectangles [x, y, z, dx, dy, dz, heading]: the intersection polygon's vertices are the edge-edge crossings plus the corners
+// of one rectangle inside the other; they are ordered by angle around their centroid and the area is a triangle fan.  The
+// arithmetic follows iou3d_nms_kernel.cu:35-235 operation for operation (same tolerances: EPS 1e-8, containment margin 1e-2)
+// so that a pair's "IoU > threshold" bit agrees with the reference's.
+struct P2 {
+    float x, y;
+};
+constexpr float kEps = 1e-8f;
+
+__device__ __forceinline__ float cross3(const P2& p1, const P2& p2, const P2& p0) {
+    return (p1.x - p0.x) * (p2.y - p0.y) - (p2.x - p0.x) * (p1.y - p0.y);
+}
+
+__device__ __forceinline__ bool seg_cross(const P2& p1, const P2& p0, const P2& q1, const P2& q0, P2& out) {
+    if (!(fminf(p0.x, p1.x) <= fmaxf(q0.x, q1.x) && fminf(q0.x, q1.x) <= fmaxf(p0.x, p1.x) && fminf(p0.y, p1.y) <= fmaxf(q0.y, q1.y) &&
+          fminf(q0.y, q1.y) <= fmaxf(p0.y, p1.y)))
+        return false;
+    const float s1 = cross3(q0, p1, p0), s2 = cross3(p1, q1, p0), s3 = cross3(p0, q1, q0), s4 = cross3(q1, p1, q0);
+    if (!(s1 * s2 > 0.f && s3 * s4 > 0.f)) return false;
+    const float s5 = cross3(q1, p1, p0);
+    if (fabsf(s5 - s1) > kEps) {
+        out.x = (s5 * q0.x - s1 * q1.x) / (s5 - s1);
+        out.y = (s5 * q0.y - s1 * q1.y) / (s5 - s1);
+    } else {
+        const float a0 = p0.y - p1.y, b0 = p1.x - p0.x, c0 = p0.x * p1.y - p1.x * p0.y;
+        const float a1 = q0.y - q1.y, b1 = q1.x - q0.x, c1 = q0.x * q1.y - q1.x * q0.y;
+        const float D = a0 * b1 - a1 * b0;
+        out.x = (b0 * c1 - b1 * c0) / D;
+        out.y = (a1 * c0 - a0 * c1) / D;
+    }
+    return true;
+}
+
+__device__ __forceinline__ bool inside_rect(const float* box, const P2& p) {
+    const float margin = 1e-2f;
+    const float c = cosf(-box[6]), s = sinf(-box[6]);
+    const float rx = (p.x - box[0]) * c + (p.y - box[1]) * (-s);
+    const float ry = (p.x - box[0]) * s + (p.y - box[1]) * c;
+    return fabsf(rx) < box[3] / 2 + margin && fabsf(ry) < box[4] / 2 + margin;
+}
+
+__device__ __forceinline__ void rect_corners(const float* box, P2 (&c)[5]) {
+    const float hx = box[3] / 2, hy = box[4] / 2;
+    const float x1 = box[0] - hx, y1 = box[1] - hy, x2 = box[0] + hx, y2 = box[1] + hy;
+    const float ca = cosf(box[6]), sa = sinf(box[6]);
+    const float px[4] = {x1, x2, x2, x1}, py[4] = {y1, y1, y2, y2};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        c[k].x = (px[k] - box[0]) * ca + (py[k] - box[1]) * (-sa) + box[0];
+        c[k].y = (px[k] - box[0]) * sa + (py[k] - box[1]) * ca + box[1];
+    }
+    c[4] = c[0];
+}
+
+__device__ float rect_overlap(const float* a, const float* b) {
+    P2 ca[5], cb[5];
+    rect_corners(a, ca);
+    rect_corners(b, cb);
+    P2 pts[16];
+    float ang[16];
+    P2 centre{0.f, 0.f};
+    int cnt = 0;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            if (seg_cross(ca[i + 1], ca[i], cb[j + 1], cb[j], pts[cnt])) {
+                centre.x = centre.x + pts[cnt].x;
+                centre.y = centre.y + pts[cnt].y;
+                ++cnt;
+            }
+    for (int k = 0; k < 4; ++k) {
+        if (inside_rect(a, cb[k])) {
+            centre.x = centre.x + cb[k].x;
+            centre.y = centre.y + cb[k].y;
+            pts[cnt++] = cb[k];
+        }
+        if (inside_rect(b, ca[k])) {
+            centre.x = centre.x + ca[k].x;
+            centre.y = centre.y + ca[k].y;
+            pts[cnt++] = ca[k];
+        }
+    }
+    if (cnt == 0) return 0.f;
+    centre.x /= cnt;
+    centre.y /= cnt;
+    // ascending angle around the centroid; a stable insertion sort gives the order of the reference's bubble sort
+    for (int k = 0; k < cnt; ++k) ang[k] = atan2f(pts[k].y - centre.y, pts[k].x - centre.x);
+    for (int k = 1; k < cnt; ++k) {
+        const P2 p = pts[k];
+        const float t = ang[k];
+        int j = k - 1;
+        while (j >= 0 && ang[j] > t) {
+            pts[j + 1] = pts[j];
+            ang[j + 1] = ang[j];
+            --j;
+        }
+        pts[j + 1] = p;
+        ang[j + 1] = t;
+    }
+    float area = 0.f;
+    for (int k = 0; k < cnt - 1; ++k) {
+        const float ux = pts[k].x - pts[0].x, uy = pts[k].y - pts[0].y;
+        const float vx = pts[k + 1].x - pts[0].x, vy = pts[k + 1].y - pts[0].y;
+        area += ux * vy - uy * vx;
+    }
+    return fabsf(area) / 2.0f;
+}
+
+__device__ __forceinline__ float rect_iou(const float* a, const float* b) {
+    const float sa = a[3] * a[4], sb = b[3] * b[4];
+    const float ov = rect_overlap(a, b);
+    return ov / fmaxf(sa + sb - ov, kEps);
+}
+
+// grid (col block, row block, frame); only the upper triangle computes
+__global__ void __launch_bounds__(kNmsBlock) k_nms_mask(const float* __restrict__ boxes, int box_stride, const int* __restrict__ counts, int n_cap,
+                                                        int pre_max, float thresh, unsigned long long* __restrict__ mask, int col_blocks,
+                                                        float* __restrict__ iou_out) {
+    const int b = blockIdx.z, rb = blockIdx.y, cbk = blockIdx.x;
+    int n = counts ? counts[b] : n_cap;
+    n = n < n_cap ? n : n_cap;
+    n = n < pre_max ? n : pre_max;
+    const int row = rb * kNmsBlock + threadIdx.x;
+    if (rb * kNmsBlock >= n || cbk * kNmsBlock >= n) return;
+    unsigned long long* mrow = mask + ((int64_t)b * n_cap + row) * col_blocks + cbk;
+    if (cbk < rb) {
+        if (row < n) *mrow = 0ull;
+        return;
+    }
+    __shared__ float sbox[kNmsBlock * 7];
+    const float* fb = boxes + (int64_t)b * n_cap * box_stride;
+    const int col_n = min(n - cbk * kNmsBlock, kNmsBlock);
+    if ((int)threadIdx.x < col_n) {
+        const float* src = fb + (int64_t)(cbk * kNmsBlock + threadIdx.x) * box_stride;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) sbox[threadIdx.x * 7 + j] = src[j];
+    }
+    __syncthreads();
+    if (row >= n) return;
+    float cur[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) cur[j] = fb[(int64_t)row * box_stride + j];
+    unsigned long long t = 0ull;
+    const int start = rb == cbk ? (int)threadIdx.x + 1 : 0;
+    for (int i = start; i < col_n; ++i) {
+        const float v = rect_iou(cur, sbox + i * 7);
+        if (iou_out) iou_out[((int64_t)b * n_cap + row) * n_cap + cbk * kNmsBlock + i] = v;
+        if (v > thresh) t |= 1ull << i;
+    }
+    *mrow = t;
+}
+
+// one CTA per frame; dynamic shared memory holds the frame's mask rows [n][col_blocks]
+__global__ void __launch_bounds__(256) k_nms_sweep(const float* __restrict__ boxes, int box_stride, int box_dim, const float* __restrict__ scores,
+                                                   const int* __restrict__ labels, const int* __restrict__ counts, int n_cap, int pre_max,
+                                                   int post_max, const unsigned long long* __restrict__ mask, int col_blocks, int label_offset,
+                                                   int* __restrict__ keep, int* __restrict__ keep_count, float* __restrict__ out_boxes,
+                                                   float* __restrict__ out_scores, int* __restrict__ out_labels) {
+    extern __shared__ unsigned long long smask[];
+    __shared__ int s_nk;
+    int* skeep = reinterpret_cast<int*>(smask + (size_t)n_cap * col_blocks);
+    const int b = blockIdx.x;
+    int n = counts ? counts[b] : n_cap;
+    n = n < n_cap ? n : n_cap;
+    n = n < pre_max ? n : pre_max;
+    const int cb_n = (n + kNmsBlock - 1) / kNmsBlock;
+    const unsigned long long* gm = mask + (int64_t)b * n_cap * col_blocks;
+    for (int i = threadIdx.x; i < n * cb_n; i += blockDim.x) {
+        const int r = i / cb_n, c = i % cb_n;
+        smask[r * col_blocks + c] = gm[(int64_t)r * col_blocks + c];
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;                                       // lane c owns removed-word c (col_blocks <= 32)
+        unsigned long long remv = 0ull;
+        int nk = 0;
+        for (int i = 0; i < n && nk < post_max; ++i) {
+            const unsigned long long w = __shfl_sync(0xffffffffu, remv, i >> 6);
+            if (!((w >> (i & 63)) & 1ull)) {
+                if (lane == 0) skeep[nk] = i;
+                ++nk;
+                if (lane < cb_n && lane >= (i >> 6)) remv |= smask[i * col_blocks + lane];
+            }
+        }
+        if (lane == 0) { s_nk = nk; keep_count[b] = nk; }
+    }
+    __syncthreads();
+    const int nk = s_nk;
+    for (int k = threadIdx.x; k < post_max; k += blockDim.x) keep[(int64_t)b * post_max + k] = k < nk ? skeep[k] : -1;
+    if (out_boxes) {
+        for (int e = threadIdx.x; e < nk * box_dim; e += blockDim.x) {
+            const int k = e / box_dim, j = e % box_dim;
+            out_boxes[((int64_t)b * post_max + k) * box_dim + j] = boxes[((int64_t)b * n_cap + skeep[k]) * box_stride + j];
+        }
+    }
+    for (int k = threadIdx.x; k < nk; k += blockDim.x) {
+        if (out_scores && scores) out_scores[(int64_t)b * post_max + k] = scores[(int64_t)b * n_cap + skeep[k]];
+        if (out_labels && labels) out_labels[(int64_t)b * post_max + k] = labels[(int64_t)b * n_cap + skeep[k]] + label_offset;
+    }
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" size_t ql_centerhead_decode_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W) {
+    return align256((size_t)B * C * H * W * sizeof(uint2)) + align256((size_t)B * sizeof(int));
+}
+
+extern "C" int ql_centerhead_decode(const float* hm, const float* center, const float* center_z, const float* dim, const float* rot, const float* vel,
+                                    const float* iou, int32_t B, int32_t C, int32_t H, int32_t W, int32_t K, float feature_map_stride,
+                                    const float* voxel_size_xy, const float* pc_min_xy, const float* center_limit_range, float score_thresh,
+                                    const int32_t* class_map, float* out_boxes, float* out_scores, int32_t* out_labels, float* out_iou,
+                                    int32_t* out_count, void* workspace, size_t workspace_bytes, ql_stream_t stream_) {
+    if (!hm || !center || !center_z || !dim || !rot || !voxel_size_xy || !pc_min_xy || !center_limit_range || !out_boxes || !out_scores ||
+        !out_labels || !out_count || !workspace)
+        return QL_ERR_INVALID;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0 || K > kSelThreads || (iou && !out_iou)) return QL_ERR_INVALID;
+    if ((double)C * H * W >= 2147483647.0) return QL_ERR_GRID_TOO_LARGE;
+    if (workspace_bytes < ql_centerhead_decode_workspace_bytes(B, C, H, W)) return QL_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream_;
+    HeadMaps M;
+    M.hm = hm; M.center = center; M.center_z = center_z; M.dim = dim; M.rot = rot; M.vel = vel; M.iou = iou;
+    M.B = B; M.C = C; M.H = H; M.W = W; M.K = K;
+    M.stride = feature_map_stride; M.vsx = voxel_size_xy[0]; M.vsy = voxel_size_xy[1]; M.pcx = pc_min_xy[0]; M.pcy = pc_min_xy[1];
+    for (int i = 0; i < 6; ++i) M.lim[i] = center_limit_range[i];
+    M.score_thresh = score_thresh;
+    M.class_map = class_map;
+    uint2* cand = (uint2*)workspace;
+    int* cand_count = (int*)((char*)workspace + align256((size_t)B * C * H * W * sizeof(uint2)));
+    if (cudaMemsetAsync(cand_count, 0, (size_t)B * sizeof(int), st) != cudaSuccess) return QL_ERR_CUDA;
+    const int64_t n = (int64_t)C * H * W;
+    k_ch_candidates<<<dim3((unsigned)((n + 255) / 256), (unsigned)B), 256, 0, st>>>(M, cand, cand_count);
+    k_ch_select_decode<<<(unsigned)B, kSelThreads, 0, st>>>(M, cand, cand_count, vel ? 9 : 7, out_boxes, out_scores, out_labels, out_iou, out_count);
+    QL_CUDA_CHECK_LAST();
+    return QL_OK;
+}
+
+extern "C" size_t ql_nms_rotated_workspace_bytes(int32_t B, int32_t n_cap) {
+    const size_t col_blocks = ((size_t)n_cap + kNmsBlock - 1) / kNmsBlock;
+    return align256((size_t)B * n_cap * col_blocks * sizeof(unsigned long long));
+}
+
+extern "C" int ql_nms_rotated(const float* boxes, int32_t box_stride, int32_t box_dim, const float* scores, const int32_t* labels,
+                              const int32_t* counts, int32_t B, int32_t n_cap, float thresh, int32_t pre_max, int32_t post_max,
+                              int32_t label_offset, int32_t* keep, int32_t* keep_count, float* out_boxes, float* out_scores,
+                              int32_t* out_labels, float* iou_out, void* workspace, size_t workspace_bytes, ql_stream_t stream_) {
+    if (!boxes || !keep || !keep_count || !workspace || B <= 0 || n_cap <= 0 || box_stride < 7 || box_dim < 7 || box_dim > box_stride ||
+        pre_max <= 0 || post_max <= 0)
+        return QL_ERR_INVALID;
+    const int col_blocks = (n_cap + kNmsBlock - 1) / kNmsBlock;
+    if (col_blocks > 32) return QL_ERR_UNSUPPORTED;                        // the sweep keeps one removed-word per lane: n_cap <= 2048
+    if (workspace_bytes < ql_nms_rotated_workspace_bytes(B, n_cap)) return QL_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream_;
+    unsigned long long* mask = (unsigned long long*)workspace;
+    k_nms_mask<<<dim3((unsigned)col_blocks, (unsigned)col_blocks, (unsigned)B), kNmsBlock, 0, st>>>(boxes, box_stride, counts, n_cap, pre_max, thresh,
+                                                                                                  mask, col_blocks, iou_out);
+    const size_t smem = (size_t)n_cap * col_blocks * sizeof(unsigned long long) + (size_t)post_max * sizeof(int);
+    if (smem > 200 * 1024) return QL_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(k_nms_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return QL_ERR_CUDA;
+    k_nms_sweep<<<(unsigned)B, 256, smem, st>>>(boxes, box_stride, box_dim, scores, labels, counts, n_cap, pre_max, post_max, mask, col_blocks,
+                                                label_offset, keep, keep_count, out_boxes, out_scores, out_labels);
+    QL_CUDA_CHECK_LAST();
+    return QL_OK;
+}

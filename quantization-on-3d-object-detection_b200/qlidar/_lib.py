@@ -60,6 +60,11 @@ SIGNATURES = {
     "ql_bev_merge2d": (C.c_int, [_p, _i32, _i32, _p, _i64, _p, _i32, _i32, _i32, _p, _i32, _p, _i64, _p, _p, _sz, _p]),
     "ql_bev_merge2d_multi": (C.c_int, [_i32, _p, _i32, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _p, _i32, _p, _i32, _i64, _p, _p, _sz, _p]),
     "ql_bev_densify_ranked": (C.c_int, [_p, _i32, _i32, _p, _p, _i64, _p, _i32, _i32, _i32, _i32, _p, _i32, _p, _sz, _p]),
+    "ql_centerhead_decode_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "ql_centerhead_decode": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, C.c_float, _p, _p, _p, C.c_float, _p,
+                                       _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "ql_nms_rotated_workspace_bytes": (_sz, [_i32, _i32]),
+    "ql_nms_rotated": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _i32, C.c_float, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }
 
 _lib = None
