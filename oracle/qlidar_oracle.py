@@ -865,6 +865,8 @@ def _qlo():
         lib.qlo_stem_conv.restype = None
         lib.qlo_epilogue.argtypes = [vp, i64, i32, vp, vp, vp, i32, vp]
         lib.qlo_epilogue.restype = None
+        lib.qlo_rect_iou_matrix.argtypes = [vp, i64, i64, vp]
+        lib.qlo_rect_iou_matrix.restype = None
         _QLO = lib
     return _QLO
 
@@ -1064,3 +1066,135 @@ def sq_subm2d(x, weight, alpha, kernel_size=3, stride=1, padding=1, dilation=1):
     w_flat = fake_quant(w_flat * scale, 8, axis=0)
     xo = F.fold(cols.reshape(B, -1, ks).transpose(1, 2), (H, W), kernel_size=k, dilation=dilation, padding=padding, stride=stride)
     return w_flat.view(oc, ic, k, k).permute(0, 2, 3, 1).contiguous(), xo.permute(0, 2, 3, 1)
+
+
+# ----------------------------------------------------------------------------------------------
+# CenterHead post-processing: heat-map top-K, decode, range/score mask, rotated NMS.
+# numpy fp32, one rounding per reference torch op; the rotated IoU is C (oracle/qloracle_c.c, qlo_rect_iou).
+# ----------------------------------------------------------------------------------------------
+def sigmoid32(x: np.ndarray) -> np.ndarray:
+    """torch.sigmoid, fp32: 1 / (1 + exp(-x)) (center_head.py:307)."""
+    x = np.asarray(x, dtype=np.float32)
+    return (np.float32(1.0) / (np.float32(1.0) + np.exp(-x, dtype=np.float32))).astype(np.float32)
+
+
+def centerhead_topk(scores: np.ndarray, K: int):
+    """centernet_utils._topk (centernet_utils.py:155-173): per-class top-K over the H*W cells, then top-K over the C*K survivors.
+    Ties (torch.topk leaves their order unspecified) go to the lower index at both levels.  Returns per frame
+    (score, cell index, class, y, x), each [B, K]."""
+    B, C, H, W = scores.shape
+    flat = scores.reshape(B, C, H * W)
+    K1 = min(K, H * W)
+    o1 = np.argsort(-flat, axis=2, kind="stable")[:, :, :K1]                                   # (B, C, K1) cell indices
+    s1 = np.take_along_axis(flat, o1, axis=2)
+    s1f, o1f = s1.reshape(B, C * K1), o1.reshape(B, C * K1)
+    o2 = np.argsort(-s1f, axis=1, kind="stable")[:, :min(K, C * K1)]
+    score = np.take_along_axis(s1f, o2, axis=1)
+    cls = (o2 // K1).astype(np.int32)
+    ind = np.take_along_axis(o1f, o2, axis=1)
+    ys = (ind // W).astype(np.float32)
+    xs = (ind % W).astype(np.int32).astype(np.float32)
+    return score, ind, cls, ys, xs
+
+
+def centerhead_decode(hm, center, center_z, dim, rot, vel, iou, K, feature_map_stride, voxel_size, point_cloud_range,
+                      post_center_limit_range, score_thresh, class_map=None):
+    """CenterHead.generate_predicted_boxes up to the NMS (center_head.py:297-327) -> decode_bbox_from_heatmap
+    (centernet_utils.py:176-241).  Inputs are the RAW head outputs (hm logits, dim log-sizes, rot = (cos, sin), iou raw), numpy
+    NCHW fp32.  Returns a list (one per frame) of dicts pred_boxes (n, 7|9), pred_scores, pred_labels (class_map applied, 0-based),
+    [pred_iou]."""
+    f32 = np.float32
+    hm = sigmoid32(hm)
+    dim = np.exp(np.asarray(dim, f32), dtype=f32)
+    B = hm.shape[0]
+    score, ind, cls, ys, xs = centerhead_topk(hm, K)
+    Kk = score.shape[1]
+
+    def gather(m):                                                       # _transpose_and_gather_feat (centernet_utils.py:148-152)
+        m = np.asarray(m, f32)
+        c = m.shape[1]
+        return np.take_along_axis(m.reshape(B, c, -1), np.broadcast_to(ind[:, None, :], (B, c, Kk)), axis=2).transpose(0, 2, 1)
+
+    ctr, cz, dm, rt = gather(center), gather(center_z), gather(dim), gather(rot)
+    angle = np.arctan2(rt[:, :, 1:2], rt[:, :, 0:1]).astype(f32)
+    xs = (xs[:, :, None] + ctr[:, :, 0:1]).astype(f32)
+    ys = (ys[:, :, None] + ctr[:, :, 1:2]).astype(f32)
+    xs = ((xs * f32(feature_map_stride)).astype(f32) * f32(voxel_size[0])).astype(f32) + f32(point_cloud_range[0])
+    ys = ((ys * f32(feature_map_stride)).astype(f32) * f32(voxel_size[1])).astype(f32) + f32(point_cloud_range[1])
+    parts = [xs.astype(f32), ys.astype(f32), cz, dm, angle]
+    if vel is not None:
+        parts.append(gather(vel))
+    boxes = np.concatenate(parts, axis=-1).astype(f32)
+    piou = None
+    if iou is not None:
+        piou = ((gather(iou)[:, :, 0] + f32(1.0)) * f32(0.5)).astype(f32)
+    lim = np.asarray(post_center_limit_range, f32)
+    mask = (boxes[..., :3] >= lim[:3]).all(2) & (boxes[..., :3] <= lim[3:]).all(2)
+    if score_thresh is not None:
+        mask &= score > f32(score_thresh)
+    out = []
+    for b in range(B):
+        m = mask[b]
+        lab = cls[b, m]
+        if class_map is not None:
+            lab = np.asarray(class_map)[lab]
+        d = {"pred_boxes": boxes[b, m], "pred_scores": score[b, m], "pred_labels": lab.astype(np.int32)}
+        if piou is not None:
+            d["pred_iou"] = piou[b, m]
+        out.append(d)
+    return out
+
+
+def rect_iou_matrix(boxes: np.ndarray) -> np.ndarray:
+    """pairwise rotated BEV IoU, upper triangle (iou_bev, iou3d_nms_kernel.cu:227-234)."""
+    b = np.ascontiguousarray(boxes, dtype=np.float32)
+    n = b.shape[0]
+    out = np.zeros((n, n), np.float32)
+    if n:
+        _qlo().qlo_rect_iou_matrix(b.ctypes.data, n, b.shape[1], out.ctypes.data)
+    return out
+
+
+def nms_rotated(boxes: np.ndarray, scores: np.ndarray, thresh: float, pre_max=None, post_max=None, iou=None) -> np.ndarray:
+    """iou3d_nms_utils.nms_gpu (iou3d_nms_utils.py:120-135) + the sweep of iou3d_nms.cpp:137-183 + class_agnostic_nms's
+    [:NMS_POST_MAXSIZE] (model_nms_utils.py:19): sort by score (descending, stable), keep the first pre_max, walk them in order, a
+    box is kept unless an earlier KEPT box overlaps it with IoU > thresh.  Returns indices into `boxes`.  `iou` (optional): a
+    precomputed pairwise matrix of the SORTED, truncated boxes (e.g. the reference kernel's, for bit-identical decisions)."""
+    order = np.argsort(-np.asarray(scores, np.float32), kind="stable")
+    if pre_max is not None:
+        order = order[:pre_max]
+    b = np.asarray(boxes, np.float32)[order][:, :7]
+    m = rect_iou_matrix(b) if iou is None else iou
+    n = b.shape[0]
+    removed = np.zeros(n, bool)
+    keep = []
+    for i in range(n):
+        if removed[i]:
+            continue
+        keep.append(i)
+        removed[i + 1:] |= m[i, i + 1:] > np.float32(thresh)
+    keep = np.asarray(keep, np.int64)
+    if post_max is not None:
+        keep = keep[:post_max]
+    return order[keep]
+
+
+def centerhead_generate_predicted_boxes(pred_dicts, class_id_mapping_each_head, K, feature_map_stride, voxel_size, point_cloud_range,
+                                        post_center_limit_range, score_thresh, nms_thresh, nms_pre, nms_post, use_vel=False):
+    """CenterHead.generate_predicted_boxes with NMS_TYPE nms_gpu (center_head.py:297-365).  pred_dicts: one dict of numpy NCHW maps per
+    head.  Returns a list per frame of pred_boxes / pred_scores / pred_labels (1-based)."""
+    B = pred_dicts[0]["hm"].shape[0]
+    ret = [{"pred_boxes": [], "pred_scores": [], "pred_labels": []} for _ in range(B)]
+    for h, pd in enumerate(pred_dicts):
+        dec = centerhead_decode(pd["hm"], pd["center"], pd["center_z"], pd["dim"], pd["rot"], pd.get("vel") if use_vel else None, None, K,
+                                feature_map_stride, voxel_size, point_cloud_range, post_center_limit_range, score_thresh,
+                                class_map=class_id_mapping_each_head[h])
+        for b, d in enumerate(dec):
+            sel = nms_rotated(d["pred_boxes"], d["pred_scores"], nms_thresh, nms_pre, nms_post) if len(d["pred_scores"]) else np.zeros(0, np.int64)
+            ret[b]["pred_boxes"].append(d["pred_boxes"][sel])
+            ret[b]["pred_scores"].append(d["pred_scores"][sel])
+            ret[b]["pred_labels"].append(d["pred_labels"][sel])
+    for b in range(B):
+        ret[b] = {"pred_boxes": np.concatenate(ret[b]["pred_boxes"], 0), "pred_scores": np.concatenate(ret[b]["pred_scores"], 0),
+                  "pred_labels": np.concatenate(ret[b]["pred_labels"], 0) + 1}
+    return ret

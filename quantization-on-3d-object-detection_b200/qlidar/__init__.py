@@ -12,6 +12,7 @@ from .backbones import (Cfg, post_act_block, SparseBasicBlock, VoxelBackBone8x, 
                         VoxelResBackBone8xVoxelNeXt, MeanVFE, DynamicMeanVFE, VoxelizeMeanVFE, VoxelGeneratorWrapper, HeightCompression)
 from .engine import BackboneEngine
 from . import shard
+from .center_head import CenterHeadPostProcessor
 from . import smoothquant as _smoothquant_mod
 from .smoothquant import (SQConv2d, SQConv1d, SQConvT2d, SQLinear, SQSubM2d, SparseSQConv2d, smoothquant_layer, smoothquant)
 

@@ -502,3 +502,69 @@ def bev_densify(feats: torch.Tensor, table: torch.Tensor, grid, out: Optional[to
     check(lib().ql_bev_densify(_ptr(feats), _DT[feats.dtype], c, _ptr(table), table.numel(), B, D, H, W, _ptr(out), _DT[out.dtype],
                                _ptr(workspace), workspace.numel(), _stream()), "ql_bev_densify")
     return out
+
+
+# ------------------------------------------------------------------ CenterHead post-processing (csrc/centerhead.cu)
+def _host_f32(vals, n):
+    a = (C.c_float * n)(*[float(v) for v in list(vals)[:n]])
+    return a
+
+
+def centerhead_decode(hm: torch.Tensor, center: torch.Tensor, center_z: torch.Tensor, dim: torch.Tensor, rot: torch.Tensor,
+                      vel: Optional[torch.Tensor], iou: Optional[torch.Tensor], K: int, feature_map_stride, voxel_size, point_cloud_range,
+                      post_center_limit_range, score_thresh: Optional[float], class_map: Optional[torch.Tensor] = None,
+                      workspace: Optional[torch.Tensor] = None):
+    """One head of CenterHead.generate_predicted_boxes up to (not including) NMS (center_head.py:297-327 ->
+    centernet_utils.decode_bbox_from_heatmap, centernet_utils.py:176-241).  `hm` are LOGITS, `dim` log-sizes, `rot` = (cos, sin), `iou`
+    the raw head output.  Returns (boxes [B,K,7|9], scores [B,K], labels [B,K] int32 (class_map applied, 0-based), iou [B,K] or None,
+    count [B] int32): per frame the first count[b] rows are the masked candidates in descending score order."""
+    maps = [hm, center, center_z, dim, rot, vel, iou]
+    _need_cuda(*maps, class_map)
+    for t in maps:
+        if t is not None and t.dtype != torch.float32:
+            raise QlidarError("centerhead_decode expects fp32 head maps")
+    B, Cn, H, W = [int(v) for v in hm.shape]
+    dev = hm.device
+    bd = 9 if vel is not None else 7
+    boxes = torch.zeros((B, K, bd), dtype=torch.float32, device=dev)
+    scores = torch.zeros((B, K), dtype=torch.float32, device=dev)
+    labels = torch.zeros((B, K), dtype=torch.int32, device=dev)
+    out_iou = torch.zeros((B, K), dtype=torch.float32, device=dev) if iou is not None else None
+    count = torch.zeros((B,), dtype=torch.int32, device=dev)
+    ws_bytes = int(lib().ql_centerhead_decode_workspace_bytes(B, Cn, H, W))
+    if workspace is None or workspace.numel() < ws_bytes:
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib().ql_centerhead_decode(_ptr(hm), _ptr(center), _ptr(center_z), _ptr(dim), _ptr(rot), _ptr(vel), _ptr(iou), B, Cn, H, W, int(K),
+                                     float(feature_map_stride), _host_f32(voxel_size, 2), _host_f32(point_cloud_range, 2),
+                                     _host_f32(post_center_limit_range, 6), -1.0 if score_thresh is None else float(score_thresh),
+                                     _ptr(class_map), _ptr(boxes), _ptr(scores), _ptr(labels), _ptr(out_iou), _ptr(count), _ptr(workspace),
+                                     workspace.numel(), _stream()), "ql_centerhead_decode")
+    return boxes, scores, labels, out_iou, count
+
+
+def nms_rotated(boxes: torch.Tensor, scores: Optional[torch.Tensor], labels: Optional[torch.Tensor], counts: Optional[torch.Tensor],
+                thresh: float, pre_max: int, post_max: int, label_offset: int = 0, box_dim: Optional[int] = None, return_iou: bool = False,
+                workspace: Optional[torch.Tensor] = None):
+    """Greedy rotated-BEV-IoU NMS per frame with the sweep on the device (iou3d_nms_utils.nms_gpu, iou3d_nms_utils.py:120-135; nms_kernel,
+    iou3d_nms_kernel.cu:295-339; the host sweep of iou3d_nms.cpp:137-183).  boxes [B, n_cap, >=7] fp32, each frame's first counts[b]
+    rows in DESCENDING score order.  Returns a dict: keep [B, post_max] int32 (-1 padded), keep_count [B], boxes [B, post_max, box_dim],
+    scores / labels [B, post_max] when given, iou [B, n_cap, n_cap] (upper triangle) when return_iou."""
+    _need_cuda(boxes, scores, labels, counts)
+    if boxes.dtype != torch.float32 or boxes.dim() != 3:
+        raise QlidarError("nms_rotated expects fp32 [B, n_cap, box_stride] boxes")
+    B, n_cap, stride = [int(v) for v in boxes.shape]
+    bd = int(box_dim) if box_dim is not None else stride
+    dev = boxes.device
+    keep = torch.empty((B, post_max), dtype=torch.int32, device=dev)
+    keep_count = torch.zeros((B,), dtype=torch.int32, device=dev)
+    out_boxes = torch.zeros((B, post_max, bd), dtype=torch.float32, device=dev)
+    out_scores = torch.zeros((B, post_max), dtype=torch.float32, device=dev) if scores is not None else None
+    out_labels = torch.zeros((B, post_max), dtype=torch.int32, device=dev) if labels is not None else None
+    iou = torch.zeros((B, n_cap, n_cap), dtype=torch.float32, device=dev) if return_iou else None
+    ws_bytes = int(lib().ql_nms_rotated_workspace_bytes(B, n_cap))
+    if workspace is None or workspace.numel() < ws_bytes:
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib().ql_nms_rotated(_ptr(boxes), stride, bd, _ptr(scores), _ptr(labels), _ptr(counts), B, n_cap, float(thresh), int(pre_max),
+                               int(post_max), int(label_offset), _ptr(keep), _ptr(keep_count), _ptr(out_boxes), _ptr(out_scores),
+                               _ptr(out_labels), _ptr(iou), _ptr(workspace), workspace.numel(), _stream()), "ql_nms_rotated")
+    return {"keep": keep, "keep_count": keep_count, "boxes": out_boxes, "scores": out_scores, "labels": out_labels, "iou": iou}
