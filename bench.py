@@ -526,6 +526,13 @@ def run_ours(args):
         except Exception as e:                                     # the headline line must not depend on the extra leg
             int8_leg = {"error": repr(e)[:200]}
 
+    head_post = None
+    if args.config in (1, 2):
+        try:
+            head_post = head_post_leg(dev)
+        except Exception as e:
+            head_post = {"error": repr(e)[:200]}
+
     # ---- CPU baseline beside it: the oracle port on a bounded sample of the same workload ----
     cpu = cpu_baseline(pts_np, budget_s=12.0)
 
@@ -551,6 +558,7 @@ def run_ours(args):
         "stage_frac_of_hbm_peak": {k: round(v / pk["hbm"], 4) for k, v in stage_gbs.items()},
         "conv_layers": per_layer,
         "int8": int8_leg,
+        "head_post": head_post,
         "step_ms_p10_p50_p90": [round(float(np.percentile(step_ms, q)), 4) for q in (10, 50, 90)],
     }
     if gathered is not None:
@@ -561,6 +569,40 @@ def run_ours(args):
 
 
 # ----------------------------------------------------------------------------------------------------- CPU arms
+def head_post_leg(dev, batch=4, hw=188, classes=3, iters=30):
+    """SURVEY 8(f) rank 1, timed beside the headline: CenterHead.generate_predicted_boxes at the Waymo head size (4 frames x 3 classes x
+    188 x 188 maps, K = 500, NMS 0.7 / 4096 / 500) through CenterHeadPostProcessor -- 4 kernel launches, no host sync (lazy=True)."""
+    import qlidar
+    g = np.random.default_rng(5)
+    hm = (g.standard_normal((batch, classes, hw, hw)) * 0.7 - 6.0).astype(np.float32)
+    for b in range(batch):
+        cy, cx = g.integers(2, hw - 2, 250), g.integers(2, hw - 2, 250)
+        for k in range(750):
+            hm[b, g.integers(0, classes), np.clip(cy[k % 250] + g.integers(-1, 2), 0, hw - 1), np.clip(cx[k % 250] + g.integers(-1, 2), 0, hw - 1)] = g.uniform(-1.5, 3.0)
+    maps = {"hm": hm, "center": g.random((batch, 2, hw, hw), dtype=np.float32), "center_z": (g.standard_normal((batch, 1, hw, hw)) * 0.5 + 1).astype(np.float32),
+            "dim": (g.standard_normal((batch, 3, hw, hw)) * 0.2 + np.log(np.array([4.5, 2.0, 1.6]))[None, :, None, None]).astype(np.float32),
+            "rot": g.standard_normal((batch, 2, hw, hw)).astype(np.float32)}
+    maps = {k: torch.from_numpy(v).to(dev) for k, v in maps.items()}
+    post = {"SCORE_THRESH": 0.1, "POST_CENTER_LIMIT_RANGE": [-75.2, -75.2, -2, 75.2, 75.2, 4], "MAX_OBJ_PER_SAMPLE": 500,
+            "NMS_CONFIG": {"NMS_TYPE": "nms_gpu", "NMS_THRESH": 0.7, "NMS_PRE_MAXSIZE": 4096, "NMS_POST_MAXSIZE": 500}}
+    pp = qlidar.CenterHeadPostProcessor(["Vehicle", "Pedestrian", "Cyclist"], [["Vehicle", "Pedestrian", "Cyclist"]], [-75.2, -75.2, -2.0, 75.2, 75.2, 4.0],
+                                        [0.1, 0.1, 0.15], 8, post, device=dev)
+    for _ in range(3):
+        out = pp.generate_predicted_boxes(batch, [maps], lazy=True)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in ev:
+        a.record()
+        out = pp.generate_predicted_boxes(batch, [maps], lazy=True)
+        b.record()
+    torch.cuda.synchronize()
+    us = sorted(a.elapsed_time(b) * 1e3 for a, b in ev)
+    return {"what": "CenterHead.generate_predicted_boxes on the device (top-K 500, decode, rotated NMS + sweep), 4 frames x 3 x 188 x 188, includes "
+                    "the host-side launch overhead of its 4 kernels + output allocations (eager, no graph)",
+            "us_per_call_median": round(us[len(us) // 2], 1), "us_per_call_min": round(us[0], 1),
+            "candidates_kept_per_frame": [int(v) for v in out[0]["keep_count"].cpu().tolist()], "kernel_launches": 4}
+
+
 def oracle_runner():
     """The reference's CPU path restated (oracle/) for the selected workload: per-frame hard voxelisation + MeanVFE + the backbone
     with the reference's fake-quant math (QConvNd, quant/quant.py:36-58; SmoothQuant per SURVEY.md 8a-Q) [+ HeightCompression]."""

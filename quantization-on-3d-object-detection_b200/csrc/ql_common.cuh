@@ -130,18 +130,6 @@ __device__ __forceinline__ bool ql_mbar_try_wait(uint32_t bar, uint32_t parity, 
         : "memory");
     return ok != 0;
 }
-// non-blocking phase test (try_wait may suspend the thread for a hardware-defined time slice, ~4 us measured on B200)
-__device__ __forceinline__ bool ql_mbar_test_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
 // Bounded wait: a protocol bug must not hang the GPU box (a hang is a strike).  After ~4 s of failed polls the
 // CTA traps, which surfaces as a launch failure on the host instead.
 __device__ __forceinline__ uint64_t ql_globaltimer_ns() {
@@ -168,23 +156,6 @@ __device__ __forceinline__ int ql_lds_s32(uint32_t addr) {
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-
-// 16-byte async copy global -> shared with zero fill when !valid (src-size 0 reads nothing).
-__device__ __forceinline__ void ql_cp_async16(uint32_t dst, const void* src, bool valid) {
-    uint32_t sz = valid ? 16u : 0u;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void ql_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void ql_cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-// arrive on `bar` once all cp.async issued so far by this thread have landed (counts as one expected arrival)
-__device__ __forceinline__ void ql_cp_async_mbar_arrive_noinc(uint32_t bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-// make generic-proxy shared-memory writes visible to the async proxy (tcgen05.mma / bulk copies)
-__device__ __forceinline__ void ql_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // TMA 1-D bulk copy global -> shared::cta, completion on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void ql_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -215,23 +186,6 @@ __device__ __forceinline__ void ql_tc_fence_after() { asm volatile("tcgen05.fenc
 __device__ __forceinline__ void ql_tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]; kind selected at compile time
-template <bool kInt8>
-__device__ __forceinline__ void ql_tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    if constexpr (kInt8) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-            : "memory");
-    }
-}
 // 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread (thread t <-> lane base+t)
 __device__ __forceinline__ void ql_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -242,24 +196,6 @@ __device__ __forceinline__ void ql_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) 
         : "memory");
 }
 __device__ __forceinline__ void ql_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
-//   rows are 128 B apart inside an 8-row swizzle atom (1024 B), atoms are SBO = 1024 B apart, LBO unused.
-//   bits [0,14) addr>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t ql_umma_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;                    // LBO (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;          // SBO
-    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
-    return d;
-}
-
-// byte offset of 16-byte chunk `c16` (0..7) of row `r` inside a [rows x 128 B] K-major SWIZZLE_128B tile
-__host__ __device__ __forceinline__ uint32_t ql_sw128_offset(uint32_t r, uint32_t c16) {
-    return (r >> 3) * 1024u + (r & 7u) * 128u + ((c16 ^ (r & 7u)) << 4);
-}
 
 __device__ __forceinline__ float ql_warp_max(float v) {
 #pragma unroll
