@@ -16,9 +16,10 @@
 //   k_ch_select_decode  one CTA per frame: exact top-K of the candidates (radix select on the score bits when the list is
 //                       longer than the sort width, then a bitonic sort by (score desc, cell index asc)), gather of the
 //                       regression maps, decode, range mask, order-preserving compaction
-//   k_nms_mask          64 x 64 blocks of the upper triangle of the pairwise rotated-IoU matrix -> suppression bit masks
-//   k_nms_sweep         one CTA per frame: mask rows staged in shared memory, one warp runs the greedy sweep, the CTA gathers
-//                       the kept boxes / scores / labels
+//   k_nms_mask          one thread per pair of the upper triangle of the pairwise rotated-IoU matrix (far-apart pairs rejected by a
+//                       circle test), a warp ballot = half a 64-bit suppression word
+//   k_nms_sweep         one CTA per frame: mask rows staged in shared memory, one warp runs the greedy sweep 64 boxes at a time
+//                       (fixed-point iteration over the block's diagonal bit matrix), the CTA gathers the kept boxes / scores / labels
 #include "ql_common.cuh"
 
 namespace {
@@ -305,45 +306,53 @@ __device__ __forceinline__ float rect_iou(const float* a, const float* b) {
     return ov / fmaxf(sa + sb - ov, kEps);
 }
 
-// grid (col block, row block, frame); only the upper triangle computes
-__global__ void __launch_bounds__(kNmsBlock) k_nms_mask(const float* __restrict__ boxes, int box_stride, const int* __restrict__ counts, int n_cap,
-                                                        int pre_max, float thresh, unsigned long long* __restrict__ mask, int col_blocks,
-                                                        float* __restrict__ iou_out) {
-    const int b = blockIdx.z, rb = blockIdx.y, cbk = blockIdx.x;
+// One thread per (row, column) pair of the upper triangle: grid (col block, row group, frame), block = 64 columns x kMaskRows rows.
+// A warp covers 32 consecutive columns of one row, so its ballot is one half of the row's 64-bit mask word.  Pairs whose
+// circumscribed circles (+ the containment margin) do not meet have no crossing and no contained corner: IoU = 0 without the
+// polygon code -- the common case by far, and what keeps the divergent slow path rare.
+constexpr int kMaskRows = 4;
+__global__ void __launch_bounds__(kNmsBlock * kMaskRows) k_nms_mask(const float* __restrict__ boxes, int box_stride, const int* __restrict__ counts,
+                                                                    int n_cap, int pre_max, float thresh, uint32_t* __restrict__ mask32, int col_blocks,
+                                                                    float* __restrict__ iou_out) {
+    const int b = blockIdx.z, cbk = blockIdx.x;
     int n = counts ? counts[b] : n_cap;
     n = n < n_cap ? n : n_cap;
     n = n < pre_max ? n : pre_max;
-    const int row = rb * kNmsBlock + threadIdx.x;
-    if (rb * kNmsBlock >= n || cbk * kNmsBlock >= n) return;
-    unsigned long long* mrow = mask + ((int64_t)b * n_cap + row) * col_blocks + cbk;
-    if (cbk < rb) {
-        if (row < n) *mrow = 0ull;
-        return;
-    }
-    __shared__ float sbox[kNmsBlock * 7];
+    const int c = threadIdx.x & (kNmsBlock - 1), r = threadIdx.x / kNmsBlock;
+    const int row = blockIdx.y * kMaskRows + r, col = cbk * kNmsBlock + c;
+    const int row0 = blockIdx.y * kMaskRows;
+    if (row0 >= n || cbk * kNmsBlock >= n || cbk < row0 / kNmsBlock) return;       // CTA-uniform: nothing of the upper triangle here
+    __shared__ float scol[kNmsBlock * 7];
+    __shared__ float srow[kMaskRows * 7];
     const float* fb = boxes + (int64_t)b * n_cap * box_stride;
-    const int col_n = min(n - cbk * kNmsBlock, kNmsBlock);
-    if ((int)threadIdx.x < col_n) {
-        const float* src = fb + (int64_t)(cbk * kNmsBlock + threadIdx.x) * box_stride;
+    if (r == 0 && col < n) {
 #pragma unroll
-        for (int j = 0; j < 7; ++j) sbox[threadIdx.x * 7 + j] = src[j];
+        for (int j = 0; j < 7; ++j) scol[c * 7 + j] = fb[(int64_t)col * box_stride + j];
+    }
+    if (threadIdx.x < kMaskRows * 7) {
+        const int rr = threadIdx.x / 7, j = threadIdx.x % 7;
+        if (row0 + rr < n) srow[threadIdx.x] = fb[(int64_t)(row0 + rr) * box_stride + j];
     }
     __syncthreads();
-    if (row >= n) return;
-    float cur[7];
-#pragma unroll
-    for (int j = 0; j < 7; ++j) cur[j] = fb[(int64_t)row * box_stride + j];
-    unsigned long long t = 0ull;
-    const int start = rb == cbk ? (int)threadIdx.x + 1 : 0;
-    for (int i = start; i < col_n; ++i) {
-        const float v = rect_iou(cur, sbox + i * 7);
-        if (iou_out) iou_out[((int64_t)b * n_cap + row) * n_cap + cbk * kNmsBlock + i] = v;
-        if (v > thresh) t |= 1ull << i;
+    bool hit = false;
+    if (row < n && col < n && col > row) {
+        const float* A = srow + r * 7;
+        const float* Bx = scol + c * 7;
+        const float dx = A[0] - Bx[0], dy = A[1] - Bx[1];
+        const float ra = 0.5f * sqrtf(A[3] * A[3] + A[4] * A[4]), rb = 0.5f * sqrtf(Bx[3] * Bx[3] + Bx[4] * Bx[4]);
+        const float reach = ra + rb + 0.1f;
+        float v = 0.f;
+        if (dx * dx + dy * dy <= reach * reach) v = rect_iou(A, Bx);
+        if (iou_out) iou_out[((int64_t)b * n_cap + row) * n_cap + col] = v;
+        hit = v > thresh;
     }
-    *mrow = t;
+    const uint32_t bits = __ballot_sync(0xffffffffu, hit);
+    if ((threadIdx.x & 31) == 0 && row < n) mask32[(((int64_t)b * n_cap + row) * col_blocks + cbk) * 2 + ((c >> 5) & 1)] = bits;
 }
 
-// one CTA per frame; dynamic shared memory holds the frame's mask rows [n][col_blocks]
+// one CTA per frame; dynamic shared memory holds the frame's mask rows [n][col_blocks].  The greedy sweep is sequential only inside a
+// 64-box block (through the block's diagonal mask words); one warp resolves a block by fixed-point iteration, then ORs the kept rows
+// into the removed-words of the later blocks, lane c owning word c.
 __global__ void __launch_bounds__(256) k_nms_sweep(const float* __restrict__ boxes, int box_stride, int box_dim, const float* __restrict__ scores,
                                                    const int* __restrict__ labels, const int* __restrict__ counts, int n_cap, int pre_max,
                                                    int post_max, const unsigned long long* __restrict__ mask, int col_blocks, int label_offset,
@@ -358,23 +367,57 @@ __global__ void __launch_bounds__(256) k_nms_sweep(const float* __restrict__ box
     n = n < pre_max ? n : pre_max;
     const int cb_n = (n + kNmsBlock - 1) / kNmsBlock;
     const unsigned long long* gm = mask + (int64_t)b * n_cap * col_blocks;
+    // only the upper triangle was written: word c of row r exists for c >= r / 64
     for (int i = threadIdx.x; i < n * cb_n; i += blockDim.x) {
         const int r = i / cb_n, c = i % cb_n;
-        smask[r * col_blocks + c] = gm[(int64_t)r * col_blocks + c];
+        smask[r * col_blocks + c] = c >= (r >> 6) ? gm[(int64_t)r * col_blocks + c] : 0ull;
     }
     __syncthreads();
     if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;                                       // lane c owns removed-word c (col_blocks <= 32)
-        unsigned long long remv = 0ull;
+        const int lane = threadIdx.x;
+        unsigned long long remv = 0ull;                                     // lane c: removed bits of block c
         int nk = 0;
-        for (int i = 0; i < n && nk < post_max; ++i) {
-            const unsigned long long w = __shfl_sync(0xffffffffu, remv, i >> 6);
-            if (!((w >> (i & 63)) & 1ull)) {
-                if (lane == 0) skeep[nk] = i;
-                ++nk;
-                if (lane < cb_n && lane >= (i >> 6)) remv |= smask[i * col_blocks + lane];
+        for (int w = 0; w < cb_n && nk < post_max; ++w) {
+            const int base = w * kNmsBlock;
+            const int in_block = min(n - base, kNmsBlock);
+            unsigned long long dead = __shfl_sync(0xffffffffu, remv, w);
+            if (in_block < 64) dead |= ~0ull << in_block;
+            // Inside the block box j survives iff it is alive and no SURVIVING earlier box of the block suppresses it.  Lane L owns
+            // boxes L and L + 32 and the columns of the diagonal 64 x 64 bit matrix that belong to them; the survivor set is the fixed
+            // point of kept[j] = alive[j] & !(col[j] & kept), reached level by level of the suppression chains (a handful of
+            // ballots instead of 64 dependent steps).
+            const int j0 = lane, j1 = lane + 32;
+            unsigned long long col0 = 0ull, col1 = 0ull;
+#pragma unroll 8
+            for (int i = 0; i < kNmsBlock; ++i) {
+                if (i < in_block) {
+                    const unsigned long long word = smask[(base + i) * col_blocks + w];
+                    col0 |= ((word >> j0) & 1ull) << i;
+                    col1 |= ((word >> j1) & 1ull) << i;
+                }
+            }
+            const bool alive0 = !((dead >> j0) & 1ull), alive1 = !((dead >> j1) & 1ull);
+            unsigned long long kept = (unsigned long long)__ballot_sync(0xffffffffu, alive0) | ((unsigned long long)__ballot_sync(0xffffffffu, alive1) << 32);
+            for (int it = 0; it < kNmsBlock; ++it) {
+                const bool k0 = alive0 && !(col0 & kept), k1 = alive1 && !(col1 & kept);
+                const unsigned long long nxt = (unsigned long long)__ballot_sync(0xffffffffu, k0) | ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32);
+                if (nxt == kept) break;
+                kept = nxt;
+            }
+            const int p0 = nk + __popcll(kept & ((1ull << j0) - 1ull)), p1 = nk + __popcll(kept & ((1ull << j1) - 1ull));
+            if (((kept >> j0) & 1ull) && p0 < post_max) skeep[p0] = base + j0;
+            if (((kept >> j1) & 1ull) && p1 < post_max) skeep[p1] = base + j1;
+            nk = min(nk + __popcll(kept), post_max);
+            // the kept rows of this block suppress boxes of the later blocks
+            if (lane > w && lane < cb_n) {
+                unsigned long long acc = 0ull;
+#pragma unroll 8
+                for (int j = 0; j < kNmsBlock; ++j)
+                    if ((kept >> j) & 1ull) acc |= smask[(base + j) * col_blocks + lane];
+                remv |= acc;
             }
         }
+        __syncwarp();
         if (lane == 0) { s_nk = nk; keep_count[b] = nk; }
     }
     __syncthreads();
@@ -446,8 +489,9 @@ extern "C" int ql_nms_rotated(const float* boxes, int32_t box_stride, int32_t bo
     if (workspace_bytes < ql_nms_rotated_workspace_bytes(B, n_cap)) return QL_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream_;
     unsigned long long* mask = (unsigned long long*)workspace;
-    k_nms_mask<<<dim3((unsigned)col_blocks, (unsigned)col_blocks, (unsigned)B), kNmsBlock, 0, st>>>(boxes, box_stride, counts, n_cap, pre_max, thresh,
-                                                                                                  mask, col_blocks, iou_out);
+    // rows past a frame's count are never written or read; words left of the diagonal are never read
+    k_nms_mask<<<dim3((unsigned)col_blocks, (unsigned)((n_cap + kMaskRows - 1) / kMaskRows), (unsigned)B), kNmsBlock * kMaskRows, 0, st>>>(
+        boxes, box_stride, counts, n_cap, pre_max, thresh, (uint32_t*)mask, col_blocks, iou_out);
     const size_t smem = (size_t)n_cap * col_blocks * sizeof(unsigned long long) + (size_t)post_max * sizeof(int);
     if (smem > 200 * 1024) return QL_ERR_UNSUPPORTED;
     if (cudaFuncSetAttribute(k_nms_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return QL_ERR_CUDA;
