@@ -295,6 +295,26 @@ int ql_bev_merge2d_multi(int32_t n_seg, const void* const* feats, int32_t in_dty
                          int32_t B, int32_t H, int32_t W, void* out_feats, int32_t out_dtype, int32_t* out_coords, int32_t out_coord_cols,
                          int64_t n_out_cap, int32_t* n_out_dev, void* workspace, size_t workspace_bytes, ql_stream_t stream);
 
+/* ---- key-sorted voxelisation straight from the points (engine front end; no reference counterpart: the reference's voxeliser is
+ *      first-touch ordered, spconv's order downstream is implementation-defined, and the engine works in ascending-key order).
+ *      Same point layout / range / voxel size / grid arguments as ql_voxelize_mean.  The voxel id of a point is the rank of its cell
+ *      in the stage-1 bitmap, so the call also leaves the stage's rank index in rank_workspace (layout of
+ *      ql_rulebook_strided_index(B, grid_z + 1, grid_y, grid_x, {1,1,1}, {1,1,1}, {0,0,0})).  No per-frame voxel cap in this order:
+ *      frame_counts [B] (optional) reports the voxels found per frame so that the caller can fall back to ql_voxelize_mean.
+ *      ql_voxelize_sorted_features (same arguments and workspace, stream-ordered after the coordinates half; max_pts >= 1) writes the
+ *      means of each voxel's first max_pts points (by index; bit-identical to ql_voxelize_mean's) and the point counts. */
+size_t ql_voxelize_sorted_workspace_bytes(int64_t max_points, int64_t max_voxels, int32_t max_pts);
+int ql_voxelize_sorted_coords(const float* points, int64_t n_points, int32_t point_stride, int32_t has_batch_col, int32_t n_feat,
+                              const float* range_min, const float* vsize, const int32_t* grid_xyz, int32_t batch_size,
+                              int64_t max_voxels, int32_t* out_coords, int32_t* n_voxels_dev, int32_t* frame_counts,
+                              void* rank_workspace, size_t rank_workspace_bytes, void* workspace, size_t workspace_bytes,
+                              ql_stream_t stream);
+int ql_voxelize_sorted_features(const float* points, int64_t n_points, int32_t point_stride, int32_t has_batch_col, int32_t n_feat,
+                                const float* range_min, const float* vsize, const int32_t* grid_xyz, int32_t batch_size,
+                                int32_t max_pts, int64_t max_voxels, const int32_t* n_voxels_dev, float* out_feats,
+                                int32_t out_feat_stride, int32_t* out_npts, void* workspace, size_t workspace_bytes,
+                                ql_stream_t stream);
+
 /* ---- CenterHead post-processing, all on the device (replaces CenterHead.generate_predicted_boxes,
  *      pcdet/models/dense_heads/center_head.py:297-365 -> centernet_utils._topk / decode_bbox_from_heatmap
  *      (model_utils/centernet_utils.py:155-241) -> model_nms_utils.class_agnostic_nms (model_nms_utils.py:6-25) ->

@@ -560,6 +560,198 @@ extern "C" int ql_renumber_by_key(const int32_t* in_coords, int64_t n_cap, const
     return QL_OK;
 }
 
+namespace {
+// ------------------------------------------------------------------------------------------------
+// KEY-SORTED voxelisation straight from the points (the engine's front end, round 2).
+// The hash voxeliser (voxelize.cu) numbers voxels in first-touch order like the reference's CPU voxeliser and the engine then
+// renumbered them by key: hash insert + first-touch numbering (two scans) + renumbering = 13 launches, 0.16 ms on the critical path
+// in front of the first rulebook.  When the order is going to be ascending-key anyway, the voxel id of a point IS the rank of its
+// cell in the stage-1 bitmap: mark -> popcount / scan / prefix (the rank index the rulebooks use) -> every point looks its rank up.
+// No hash table, no first-touch pass, no renumbering, no row move.  The per-frame voxel cap (MAX_NUMBER_OF_VOXELS, first-touch
+// order in the reference) cannot be reproduced in this order: frame_counts reports the voxels found per frame and the caller falls
+// back to the hash voxeliser when a frame exceeds its cap (qlidar/engine.py).  Features: the same deterministic first-T-points
+// selection and left-to-right sums as voxelize.cu, so the means are bit-identical to the hash path's.
+// ------------------------------------------------------------------------------------------------
+struct PtGeom {
+    const float* points;
+    int64_t n_points;
+    int stride, has_b, n_feat;
+    float mnx, mny, mnz, vsx, vsy, vsz;
+    int gx, gy, gz;
+    QlGrid grid;
+};
+
+__device__ __forceinline__ uint32_t point_key(const PtGeom& P, int64_t p) {
+    const float* row = P.points + p * P.stride;
+    const int o = P.has_b ? 1 : 0;
+    const int b = P.has_b ? (int)row[0] : 0;
+    // fp32 floor((p - min) / vs) with IEEE division: identical to numpy/torch fp32 (dynamic_mean_vfe.py:53) and to voxelize.cu
+    const float fx = floorf(__fdiv_rn(__fsub_rn(row[o + 0], P.mnx), P.vsx));
+    const float fy = floorf(__fdiv_rn(__fsub_rn(row[o + 1], P.mny), P.vsy));
+    const float fz = floorf(__fdiv_rn(__fsub_rn(row[o + 2], P.mnz), P.vsz));
+    const bool ok = fx >= 0.f && fx < (float)P.gx && fy >= 0.f && fy < (float)P.gy && fz >= 0.f && fz < (float)P.gz && b >= 0 && b < P.grid.B;
+    return ok ? ql_key(P.grid, b, (int)fz, (int)fy, (int)fx) : 0xFFFFFFFFu;
+}
+
+__global__ void __launch_bounds__(256) k_vs_mark(PtGeom P, uint32_t* __restrict__ bitmap, uint32_t* __restrict__ pt_key) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n_points) return;
+    const uint32_t key = point_key(P, p);
+    pt_key[p] = key;
+    if (key == 0xFFFFFFFFu) return;
+    const uint32_t bit = 1u << (key & 31u);
+    if (!(__ldcg(&bitmap[key >> 5]) & bit)) atomicOr(&bitmap[key >> 5], bit);      // ~3 points per voxel: test before the atomic
+}
+
+// point -> rank of its cell (= voxel id, ascending key); the voxel's coordinates are written by every one of its points (same value)
+__global__ void __launch_bounds__(256) k_vs_rank(int64_t n_points, QlGrid g, const uint32_t* __restrict__ bitmap,
+                                                 const uint32_t* __restrict__ word_prefix, int64_t max_voxels, uint32_t* __restrict__ pt_key_rank,
+                                                 int4* __restrict__ out_coords) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_points) return;
+    const uint32_t key = pt_key_rank[p];
+    if (key == 0xFFFFFFFFu) return;
+    const uint32_t w = key >> 5;
+    const uint32_t rank = __ldg(word_prefix + w) + (uint32_t)__popc(__ldg(bitmap + w) & ((1u << (key & 31u)) - 1u));
+    if ((int64_t)rank >= max_voxels) { pt_key_rank[p] = 0xFFFFFFFFu; return; }    // beyond the batch capacity: dropped (reported as found > kept)
+    pt_key_rank[p] = rank;
+    out_coords[rank] = ql_unkey(g, key);
+}
+
+// voxels found per frame = rank of the frame's first cell in the next frame minus its own
+__global__ void k_vs_frames(QlGrid g, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_prefix, const int* __restrict__ n_dev,
+                            int* __restrict__ frame_counts) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= g.B) return;
+    const int64_t per = (int64_t)g.D * g.H * g.W;
+    auto rank_of = [&](int64_t cell) -> int64_t {
+        if (cell >= per * g.B) return (int64_t)n_dev[1];                          // total found
+        const uint32_t w = (uint32_t)(cell >> 5), sh = (uint32_t)(cell & 31);
+        return (int64_t)word_prefix[w] + __popc(bitmap[w] & ((1u << sh) - 1u));
+    };
+    frame_counts[b] = (int)(rank_of(per * (b + 1)) - rank_of(per * b));
+}
+
+// the max_pts smallest point indices of every voxel: slot t ends up holding the (t+1)-th smallest regardless of arrival order
+__global__ void __launch_bounds__(256) k_vs_select(int64_t n_points, const uint32_t* __restrict__ pt_rank, int max_pts, uint32_t* __restrict__ tmin) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_points) return;
+    const uint32_t r = pt_rank[p];
+    if (r == 0xFFFFFFFFu) return;
+    uint32_t v = (uint32_t)p;
+    uint32_t* a = tmin + (int64_t)r * max_pts;
+    for (int t = 0; t < max_pts; ++t) {
+        const uint32_t old = atomicMin(&a[t], v);
+        if (old == 0xFFFFFFFFu) break;
+        v = old > v ? old : v;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_vs_mean(PtGeom P, const uint32_t* __restrict__ tmin, int max_pts, const int* __restrict__ n_dev,
+                                                 float* __restrict__ out_feats, int out_stride, int* __restrict__ out_npts) {
+    const int vid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vid >= n_dev[0]) return;
+    float acc[16];
+#pragma unroll
+    for (int f = 0; f < 16; ++f) acc[f] = 0.f;
+    const uint32_t* a = tmin + (int64_t)vid * max_pts;
+    int n = 0;
+    for (int t = 0; t < max_pts; ++t) {
+        const uint32_t p = a[t];
+        if (p == 0xFFFFFFFFu) break;
+        const float* row = P.points + (int64_t)p * P.stride + (P.has_b ? 1 : 0);
+#pragma unroll
+        for (int f = 0; f < 16; ++f)
+            if (f < P.n_feat) acc[f] = __fadd_rn(acc[f], row[f]);
+        ++n;
+    }
+    const float d = (float)(n > 0 ? n : 1);
+#pragma unroll
+    for (int f = 0; f < 16; ++f)
+        if (f < P.n_feat) out_feats[(int64_t)vid * out_stride + f] = __fdiv_rn(acc[f], d);
+    for (int f = P.n_feat; f < out_stride; ++f) out_feats[(int64_t)vid * out_stride + f] = 0.f;
+    out_npts[vid] = n;
+}
+
+inline size_t vs_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static bool pt_geom(PtGeom& P, const float* points, int64_t n_points, int32_t point_stride, int32_t has_batch_col, int32_t n_feat,
+                    const float* range_min, const float* vsize, const int32_t* grid_xyz, int32_t batch_size) {
+    if ((!points && n_points > 0) || !range_min || !vsize || !grid_xyz || n_feat < 3 || n_feat > 16 ||
+        point_stride < n_feat + (has_batch_col ? 1 : 0) || batch_size <= 0 || n_points < 0 || n_points >= 2147483647LL)
+        return false;
+    P.points = points; P.n_points = n_points; P.stride = point_stride; P.has_b = has_batch_col; P.n_feat = n_feat;
+    P.mnx = range_min[0]; P.mny = range_min[1]; P.mnz = range_min[2];
+    P.vsx = vsize[0]; P.vsy = vsize[1]; P.vsz = vsize[2];
+    P.gx = grid_xyz[0]; P.gy = grid_xyz[1]; P.gz = grid_xyz[2];
+    P.grid = QlGrid{batch_size, grid_xyz[2] + 1, grid_xyz[1], grid_xyz[0]};      // the backbone's sparse_shape depth (spconv_backbone.py:191)
+    return true;
+}
+
+}  // namespace
+
+extern "C" size_t ql_voxelize_sorted_workspace_bytes(int64_t max_points, int64_t max_voxels, int32_t max_pts) {
+    return vs_align((size_t)max_points * 4) + vs_align((size_t)max_voxels * (size_t)(max_pts > 0 ? max_pts : 1) * 4);
+}
+
+// coordinates half: out_coords [max_voxels, 4] (b, z, y, x) ascending by key, n_voxels_dev {kept, found}, frame_counts [B] (optional),
+// and in rank_workspace the stage's rank index (the layout of ql_rulebook_strided_index(B, D, H, W, 1, 1, 0))
+extern "C" int ql_voxelize_sorted_coords(const float* points, int64_t n_points, int32_t point_stride, int32_t has_batch_col, int32_t n_feat,
+                                         const float* range_min, const float* vsize, const int32_t* grid_xyz, int32_t batch_size,
+                                         int64_t max_voxels, int32_t* out_coords, int32_t* n_voxels_dev, int32_t* frame_counts,
+                                         void* rank_workspace, size_t rank_workspace_bytes, void* workspace, size_t workspace_bytes,
+                                         ql_stream_t stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    PtGeom P;
+    if (!pt_geom(P, points, n_points, point_stride, has_batch_col, n_feat, range_min, vsize, grid_xyz, batch_size) || !out_coords ||
+        !n_voxels_dev || !rank_workspace || !workspace || max_voxels <= 0)
+        return QL_ERR_INVALID;
+    const QlGrid g = P.grid;
+    if ((double)g.B * g.D * g.H * g.W >= 4294967295.0) return QL_ERR_GRID_TOO_LARGE;
+    const StridedWs w = strided_ws_layout(g);
+    if (rank_workspace_bytes < w.total || workspace_bytes < ql_voxelize_sorted_workspace_bytes(n_points, max_voxels, 1)) return QL_ERR_WORKSPACE;
+    char* ws = (char*)rank_workspace;
+    uint32_t* bitmap = (uint32_t*)(ws + w.bitmap);
+    uint32_t* prefix = (uint32_t*)(ws + w.prefix);
+    int* blocks = (int*)(ws + w.blocks);
+    uint32_t* pt_key = (uint32_t*)workspace;
+    const int64_t n4 = w.n_words / 4;
+    const unsigned nb4 = (unsigned)((n4 + QL_SCAN_THREADS - 1) / QL_SCAN_THREADS);
+    if (cudaMemsetAsync(bitmap, 0, (size_t)w.n_words * 4, st) != cudaSuccess) return QL_ERR_CUDA;
+    const unsigned gp = (unsigned)((n_points + 255) / 256);
+    if (n_points > 0) k_vs_mark<<<gp, 256, 0, st>>>(P, bitmap, pt_key);
+    k_rn_popc4<<<nb4, QL_SCAN_THREADS, 0, st>>>((const uint4*)bitmap, n4, blocks);
+    k_scan_blocks<<<1, QL_SCAN_THREADS, 0, st>>>(blocks, (int)nb4, n_voxels_dev + 1, n_voxels_dev, max_voxels);
+    k_rn_prefix4<<<nb4, QL_SCAN_THREADS, 0, st>>>((const uint4*)bitmap, n4, blocks, (uint4*)prefix);
+    if (n_points > 0) k_vs_rank<<<gp, 256, 0, st>>>(n_points, g, bitmap, prefix, max_voxels, pt_key, (int4*)out_coords);
+    if (frame_counts) k_vs_frames<<<(unsigned)((g.B + 63) / 64), 64, 0, st>>>(g, bitmap, prefix, n_voxels_dev, frame_counts);
+    QL_CUDA_CHECK_LAST();
+    return QL_OK;
+}
+
+// features half (same points, same workspace, stream-ordered after the coordinates half): out_feats [max_voxels, out_feat_stride]
+// = the mean of each voxel's first max_pts points (by point index), out_npts = how many that was
+extern "C" int ql_voxelize_sorted_features(const float* points, int64_t n_points, int32_t point_stride, int32_t has_batch_col, int32_t n_feat,
+                                           const float* range_min, const float* vsize, const int32_t* grid_xyz, int32_t batch_size,
+                                           int32_t max_pts, int64_t max_voxels, const int32_t* n_voxels_dev, float* out_feats,
+                                           int32_t out_feat_stride, int32_t* out_npts, void* workspace, size_t workspace_bytes,
+                                           ql_stream_t stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    PtGeom P;
+    if (!pt_geom(P, points, n_points, point_stride, has_batch_col, n_feat, range_min, vsize, grid_xyz, batch_size) || !n_voxels_dev ||
+        !out_feats || !out_npts || !workspace || max_voxels <= 0 || out_feat_stride < n_feat)
+        return QL_ERR_INVALID;
+    if (max_pts <= 0) return QL_ERR_UNSUPPORTED;                            // the cap-free (dynamic) mean stays on the hash voxeliser
+    if (workspace_bytes < ql_voxelize_sorted_workspace_bytes(n_points, max_voxels, max_pts)) return QL_ERR_WORKSPACE;
+    const uint32_t* pt_rank = (const uint32_t*)workspace;
+    uint32_t* tmin = (uint32_t*)((char*)workspace + vs_align((size_t)n_points * 4));
+    if (cudaMemsetAsync(tmin, 0xFF, (size_t)max_voxels * max_pts * 4, st) != cudaSuccess) return QL_ERR_CUDA;
+    if (n_points > 0) k_vs_select<<<(unsigned)((n_points + 255) / 256), 256, 0, st>>>(n_points, pt_rank, max_pts, tmin);
+    k_vs_mean<<<(unsigned)((max_voxels + 255) / 256), 256, 0, st>>>(P, tmin, max_pts, n_voxels_dev, out_feats, out_feat_stride, out_npts);
+    QL_CUDA_CHECK_LAST();
+    return QL_OK;
+}
+
 extern "C" int ql_rulebook_subm_ranked(const int32_t* coords, int64_t n_cap, const int32_t* n_dev, int32_t B, int32_t D, int32_t H,
                                        int32_t W, const int32_t* ksize, const uint32_t* bitmap, const uint32_t* word_prefix,
                                        int32_t* nbr_out, uint32_t* tile_kmask, ql_stream_t stream_) {

@@ -60,6 +60,9 @@ SIGNATURES = {
     "ql_bev_merge2d": (C.c_int, [_p, _i32, _i32, _p, _i64, _p, _i32, _i32, _i32, _p, _i32, _p, _i64, _p, _p, _sz, _p]),
     "ql_bev_merge2d_multi": (C.c_int, [_i32, _p, _i32, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _p, _i32, _p, _i32, _i64, _p, _p, _sz, _p]),
     "ql_bev_densify_ranked": (C.c_int, [_p, _i32, _i32, _p, _p, _i64, _p, _i32, _i32, _i32, _i32, _p, _i32, _p, _sz, _p]),
+    "ql_voxelize_sorted_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "ql_voxelize_sorted_coords": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p, _i32, _i64, _p, _p, _p, _p, _sz, _p, _sz, _p]),
+    "ql_voxelize_sorted_features": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _i64, _p, _p, _i32, _p, _p, _sz, _p]),
     "ql_centerhead_decode_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ql_centerhead_decode": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, C.c_float, _p, _p, _p, C.c_float, _p,
                                        _p, _p, _p, _p, _p, _p, _sz, _p]),

@@ -192,7 +192,8 @@ class _BackboneBase(nn.Module):
         kw = {}
         if pts is not None:
             kw = dict(max_points=max_points, pc_range=vfe.point_cloud_range, voxel_size=vfe.voxel_size, max_pts_per_voxel=vfe.max_points_per_voxel,
-                      max_voxels_per_frame=vfe.max_voxels, n_point_features=vfe.num_point_features)
+                      max_voxels_per_frame=vfe.max_voxels, n_point_features=vfe.num_point_features,
+                      sorted_voxelizer=not getattr(self, "_ql_frame_cap_hit", False))
         try:
             eng = BackboneEngine(self, B, cap, stage_cap_ratio=1.3, stage_caps=stage_caps, bev=self.engine_bev_dtype is not None,
                                  bev_dtype=self.engine_bev_dtype or torch.float16, device=dev, **kw)
@@ -210,7 +211,13 @@ class _BackboneBase(nn.Module):
         vf, vc = (pts, None) if pts is not None else (batch_dict['voxel_features'], batch_dict['voxel_coords'])
         for attempt in range(10):
             out = eng.forward_points(pts) if pts is not None else eng.forward_voxels(vf, vc)
-            counts = eng.counts_dev.cpu()                                       # the one synchronisation of the call
+            call = eng.counts_all.cpu()                                         # the one synchronisation of the call
+            counts = call[:2 * len(eng.stages)].view(len(eng.stages), 2)
+            if pts is not None and eng.frame_cap_exceeded(call):
+                # a frame has more voxels than MAX_NUMBER_OF_VOXELS: only the first-touch voxeliser drops the reference's choice of them
+                eng.use_hash_voxelizer()
+                self._ql_frame_cap_hit = True                                   # engines compiled later for this model start on the hash path
+                continue
             over = (counts[:, 1] > counts[:, 0]).tolist()
             if not any(over[1:]):
                 break

@@ -15,6 +15,8 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -101,11 +103,13 @@ class BackboneEngine:
     def __init__(self, backbone: nn.Module, batch_size: int, max_voxels: int, *, max_points: Optional[int] = None,
                  pc_range=None, voxel_size=None, max_pts_per_voxel: int = 5, n_point_features: Optional[int] = None,
                  bev: bool = True, bev_dtype=torch.float16, use_graph: bool = True, stage_cap_ratio: float = 1.0, stage_caps=None,
-                 device="cuda", max_voxels_per_frame: int = 0, group_rows="auto", overlap_rulebooks: bool = True, sort_stage1: bool = True):
+                 device="cuda", max_voxels_per_frame: int = 0, group_rows="auto", overlap_rulebooks: bool = True, sort_stage1: bool = True,
+                 sorted_voxelizer: Optional[bool] = None):
         self.dev = torch.device(device)
         self.B = int(batch_size)
         self.max_voxels = int(max_voxels)                 # capacity, total over the batch
         self.max_voxels_per_frame = int(max_voxels_per_frame)   # the reference's MAX_NUMBER_OF_VOXELS (0 = only the batch capacity)
+        self._sorted_voxelizer_arg = sorted_voxelizer
         self.max_points = max_points
         self.pc_range, self.voxel_size, self.max_pts = pc_range, voxel_size, int(max_pts_per_voxel)
         self.bev, self.bev_dtype, self.use_graph = bev, bev_dtype, use_graph
@@ -131,6 +135,7 @@ class BackboneEngine:
         self.rulebooks: Dict[tuple, torch.Tensor] = {}
         self._cap_ratio = stage_cap_ratio
         self._stage_caps = list(stage_caps) if stage_caps is not None else None
+        self._last_from_points = False
         self._graph = None
         self._timing = None
         self.kernels_per_forward = 0
@@ -315,7 +320,10 @@ class BackboneEngine:
         z = lambda *s, dt=torch.float16: torch.zeros(s, dtype=dt, device=dev)
         s0 = self.stages[0]
         # every stage's (kept, found) row counts in ONE tensor: the host reads them with a single copy
-        self.counts_dev = z(len(self.stages), 2, dt=torch.int32)
+        # (kept, found) per stage, then the voxels found per frame by the key-sorted voxeliser: ONE tensor, one D2H read per forward
+        self.counts_all = z(2 * len(self.stages) + self.B, dt=torch.int32)
+        self.counts_dev = self.counts_all[:2 * len(self.stages)].view(len(self.stages), 2)
+        self.frame_counts = self.counts_all[2 * len(self.stages):]
         s0.coords = z(s0.cap, 4, dt=torch.int32)
         s0.n_dev = self.counts_dev[0]
         # rows padded to 8 floats (32 bytes): the stem conv fetches a neighbour row with one 256-bit load
@@ -335,6 +343,16 @@ class BackboneEngine:
             w0 = z(ops.rulebook_strided_workspace_bytes(s0.grid, 1, 1, 0), dt=torch.uint8)
             s0.rank = ops.rulebook_strided_index(s0.grid, 1, 1, 0, w0)
             self.sort_src = z(s0.cap, dt=torch.int32)                      # sorted row -> first-touch row
+        # key-sorted voxelisation straight from the points (csrc/rulebook.cu, ql_voxelize_sorted_*): the default from-points front end.
+        # It cannot apply the per-frame voxel cap (a first-touch notion): frame_counts is checked after every forward and the engine
+        # falls back to the hash voxeliser + renumbering for good once a frame exceeds it (frame_cap_exceeded()).
+        # sorted_voxelizer=None: on when no per-frame cap was asked for (nothing to fall back from); True: on, and the CALLER checks
+        # frame_cap_exceeded() after a forward (the plugin path and bench.py do); False: always the hash voxeliser.
+        want = (not self.max_voxels_per_frame) if self._sorted_voxelizer_arg is None else bool(self._sorted_voxelizer_arg)
+        self.sorted_voxelizer = bool(want and self.sort_stage1 and self.max_points is not None and self.max_pts > 0 and
+                                     os.environ.get("QL_SORTED_VOXELIZER", "1") != "0")
+        if self.sorted_voxelizer:
+            self.vs_ws = z(int(ops.lib().ql_voxelize_sorted_workspace_bytes(self.max_points, s0.cap, self.max_pts)), dt=torch.uint8)
         for i, st in enumerate(self.stages[1:], start=1):
             st.coords = z(st.cap, 4, dt=torch.int32)
             st.n_dev = self.counts_dev[i]
@@ -449,7 +467,7 @@ class BackboneEngine:
         self._side.wait_event(fork)
         ready, seen = {}, (set() if with_first else {self.layers[0].rb_key})
         with torch.cuda.stream(self._side):
-            if with_first:
+            if with_first and not self.sorted_voxelizer:
                 s0 = self.stages[0]
                 self._op("sort_stage1", 5, ops.renumber_by_key, self.coords_ft, self.n_ft, s0.grid, s0.rank.workspace, out_coords=s0.coords,
                          n_out_dev=s0.n_dev, src_row=self.sort_src)
@@ -466,9 +484,9 @@ class BackboneEngine:
                 ready[L.rb_key] = ev
         return ready
 
-    def _run_backbone(self, ready=None):
+    def _run_backbone(self, ready=None, sorted_input=False):
         built = set()
-        if self.sort_stage1 and ready is None:
+        if self.sort_stage1 and ready is None and not sorted_input:
             s0 = self.stages[0]
             # kernels: mark, popc, scan, prefix, assign (coordinates + feature rows move to their rank)
             self._op("sort_stage1", 5, self._sort_stage1, s0)
@@ -540,7 +558,7 @@ class BackboneEngine:
         if self.bev:
             last = self.stages[-1]
             if last.rank is not None:
-                self._op("bev_densify", 2, ops.bev_densify_ranked, x, last.rank, last.n_dev, last.grid, out=self.spatial_features, workspace=self.bev_ws)
+                self._op("bev_densify", 1, ops.bev_densify_ranked, x, last.rank, last.n_dev, last.grid, out=self.spatial_features, workspace=self.bev_ws)
             else:
                 self._op("bev_densify", 2, ops.bev_densify, x, last.table, last.grid, out=self.spatial_features, workspace=self.bev_ws)
 
@@ -556,7 +574,20 @@ class BackboneEngine:
         vox = lambda label, nk, phase: self._op(label, nk, ops.voxelize_mean, self.points, self.pc_range, self.voxel_size, self.grid_xyz, self.B,
                                                  self.max_pts, s0.cap, out=out, workspace=self.vox_ws,
                                                  max_voxels_per_frame=self.max_voxels_per_frame, phase=phase)
-        if self.sort_stage1 and self.overlap_rulebooks and self._timing is None:
+        if self.sorted_voxelizer:
+            vs = lambda label, nk, phase: self._op(label, nk, ops.voxelize_sorted, self.points, self.pc_range, self.voxel_size, self.grid_xyz, self.B,
+                                                    self.max_pts, s0.cap, s0.rank.workspace, out=(self.vox_feats, s0.coords, self.vox_npts, s0.n_dev),
+                                                    workspace=self.vs_ws, frame_counts=self.frame_counts, phase=phase)
+            # kernels: mark, popc, scan, prefix, rank (+ frames) | select, mean
+            vs("voxelize_mean", 6, "coords")
+            if self.overlap_rulebooks and self._timing is None:
+                ready = self._fork_rulebooks(with_first=True)
+                vs("voxelize_mean", 2, "features")
+                self._run_backbone(ready=ready)
+            else:
+                vs("voxelize_mean", 2, "features")
+                self._run_backbone(sorted_input=True)
+        elif self.sort_stage1 and self.overlap_rulebooks and self._timing is None:
             # coordinates are final after the numbering passes: renumbering, the first rulebook and every later rulebook run on the
             # side stream under the voxeliser's feature passes (point selection + means), then the feature rows move to their rank
             vox("voxelize_mean", 5 if self.max_voxels_per_frame else 4, "coords")
@@ -598,8 +629,24 @@ class BackboneEngine:
     def forward_points(self, points: Optional[torch.Tensor] = None):
         if points is not None:
             self.set_points(points)
+        self._last_from_points = True
         self._replay(self._run_from_points)
         return self.outputs()
+
+    def frame_cap_exceeded(self, counts_all_host: Optional[torch.Tensor] = None) -> bool:
+        """True when the key-sorted voxeliser found more voxels in some frame than max_voxels_per_frame.  The reference drops such a
+        frame's surplus voxels in FIRST-TOUCH order (its CPU voxeliser, data_processor.py:45-61), which only the hash voxeliser
+        reproduces: call use_hash_voxelizer() and run the batch again.  counts_all_host: a host copy of self.counts_all the caller
+        already made (otherwise one D2H read here)."""
+        if not (self.sorted_voxelizer and self.max_voxels_per_frame and self._last_from_points):
+            return False
+        fc = (counts_all_host if counts_all_host is not None else self.counts_all.cpu())[2 * len(self.stages):]
+        return bool((fc > int(self.max_voxels_per_frame)).any())
+
+    def use_hash_voxelizer(self):
+        """Switch the from-points front end back to the first-touch hash voxeliser + renumbering (and re-capture the graph)."""
+        self.sorted_voxelizer = False
+        self._graph = None
 
     def forward_voxels(self, voxel_features: torch.Tensor, voxel_coords: torch.Tensor):
         """batch_dict-style entry: already voxelised input (voxel_features (V,F) fp32, voxel_coords (V,4) int32/float)."""
@@ -608,6 +655,7 @@ class BackboneEngine:
         if V > s0.cap:
             raise QlidarError("more voxels than the engine capacity")
         vc = voxel_coords.int() if voxel_coords.dtype != torch.int32 else voxel_coords
+        self._last_from_points = False
         if self.sort_stage1:
             self.vox_feats_ft[:V, :voxel_features.shape[1]].copy_(voxel_features)
             self.coords_ft[:V].copy_(vc)
@@ -634,7 +682,7 @@ class BackboneEngine:
     def overflowed(self) -> bool:
         """True when a stage found more active sites than its capacity (rows were dropped): raise the capacities."""
         c = self.counts_dev.cpu()
-        if self.sort_stage1:
+        if self.sort_stage1 and not (self.sorted_voxelizer and self._last_from_points):
             c[0] = self.n_ft.cpu()                                   # (kept, found) of the voxeliser, not of the renumbering build
         over = c[:, 1] > c[:, 0]
         if self.max_voxels_per_frame and self.stages[0].cap >= self.B * self.max_voxels_per_frame:

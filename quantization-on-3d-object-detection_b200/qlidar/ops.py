@@ -105,6 +105,44 @@ def voxelize_mean(points: torch.Tensor, pc_range, voxel_size, grid_xyz, batch_si
     return feats, coords, npts, n_dev, table
 
 
+def voxelize_sorted(points: torch.Tensor, pc_range, voxel_size, grid_xyz, batch_size: int, max_pts: int, max_voxels: int,
+                    rank_workspace: torch.Tensor, has_batch_col: bool = True, n_feat: Optional[int] = None, out=None, workspace=None,
+                    frame_counts: Optional[torch.Tensor] = None, phase: str = "both"):
+    """Key-sorted voxelisation straight from the points (include/qlidar.h: ql_voxelize_sorted_*): voxel ids are the ranks of the
+    occupied cells in ascending linear key; rank_workspace (rulebook_strided_workspace_bytes((B, gz + 1, gy, gx), 1, 1, 0)) receives the
+    stage's rank index.  phase "coords" / "features" (same buffers, in that order) or "both".
+    Returns (feats [max_voxels, F], coords [max_voxels, 4] i32, npts, n_dev [2] = (kept, found))."""
+    _need_cuda(points, rank_workspace, frame_counts)
+    if points.dtype != torch.float32 or points.dim() != 2:
+        raise QlidarError("points must be a float32 (P, stride) tensor")
+    P, stride = points.shape
+    F = int(n_feat) if n_feat is not None else stride - (1 if has_batch_col else 0)
+    dev = points.device
+    if out is None:
+        feats = torch.empty((max_voxels, F), dtype=torch.float32, device=dev)
+        coords = torch.empty((max_voxels, 4), dtype=torch.int32, device=dev)
+        npts = torch.empty((max_voxels,), dtype=torch.int32, device=dev)
+        n_dev = torch.zeros((2,), dtype=torch.int32, device=dev)
+    else:
+        feats, coords, npts, n_dev = out
+    ws_bytes = int(lib().ql_voxelize_sorted_workspace_bytes(P, max_voxels, max_pts))
+    if workspace is None or workspace.numel() < ws_bytes:
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    rmin = (C.c_float * 3)(*[float(v) for v in pc_range[:3]])
+    vs = (C.c_float * 3)(*[float(v) for v in voxel_size])
+    g = (C.c_int32 * 3)(*[int(v) for v in grid_xyz])
+    hb = 1 if has_batch_col else 0
+    if phase in ("both", "coords"):
+        check(lib().ql_voxelize_sorted_coords(_ptr(points), P, stride, hb, F, rmin, vs, g, int(batch_size), int(max_voxels), _ptr(coords), _ptr(n_dev),
+                                              _ptr(frame_counts), _ptr(rank_workspace), rank_workspace.numel(), _ptr(workspace), workspace.numel(),
+                                              _stream()), "ql_voxelize_sorted_coords")
+    if phase in ("both", "features"):
+        check(lib().ql_voxelize_sorted_features(_ptr(points), P, stride, hb, F, rmin, vs, g, int(batch_size), int(max_pts), int(max_voxels),
+                                                _ptr(n_dev), _ptr(feats), int(feats.shape[1]), _ptr(npts), _ptr(workspace), workspace.numel(),
+                                                _stream()), "ql_voxelize_sorted_features")
+    return feats, coords, npts, n_dev
+
+
 def mean_vfe(voxels: torch.Tensor, num_points: torch.Tensor) -> torch.Tensor:
     _need_cuda(voxels, num_points)
     V, T, F = voxels.shape

@@ -525,3 +525,40 @@ def test_engine_empty_ragged_and_single_voxel_inputs():
         ref_bev = O.height_compression(ref.features, ref.coords, ref.spatial_shape, 2)
         check_feats(out["spatial_features"], ref_bev, False)
         assert out["spatial_features"][1].abs().sum().item() == 0          # the empty frame's BEV map
+
+
+def test_engine_sorted_voxelizer_steps_aside_when_a_frame_exceeds_its_voxel_cap():
+    """The key-sorted front end cannot drop a frame's surplus voxels in the reference's first-touch order: it reports the frame counts,
+    frame_cap_exceeded() says so, and after use_hash_voxelizer() the engine gives exactly what an engine built on the hash voxeliser
+    gives (which test_voxelize_per_frame_voxel_cap holds to the oracle).  Under the cap both front ends agree row for row."""
+    import qlidar
+    pts, feats, coords, grid, c = make_frame("waymo", batch=2)
+    per_frame = np.bincount(coords[:, 0], minlength=2)
+    prog, P, bb = build("VoxelResBackBone8x", 5, grid)
+    mk = lambda cap_pf, sv: qlidar.BackboneEngine(bb, 2, 2 * max(cap_pf, 1), max_points=pts.shape[0] + 500, pc_range=c["pc_range"],
+                                                   voxel_size=c["voxel_size"], max_pts_per_voxel=c["max_pts"], stage_cap_ratio=4.0,
+                                                   max_voxels_per_frame=cap_pf, sorted_voxelizer=sv)
+
+    def run(eng):
+        for _ in range(2):
+            out = eng.forward_points(torch.from_numpy(pts))
+        torch.cuda.synchronize()
+        n = eng.counts()
+        return n, out["encoded_coords"][:n[-1]].cpu().numpy(), out["encoded_features"][:n[-1]].cpu().numpy()
+
+    roomy = int(per_frame.max()) + 10
+    es, eh = mk(roomy, True), mk(roomy, False)
+    assert es.sorted_voxelizer and not eh.sorted_voxelizer
+    ns, cs, fs = run(es)
+    nh, ch, fh = run(eh)
+    assert not es.frame_cap_exceeded() and ns == nh and np.array_equal(cs, ch) and np.array_equal(fs, fh)
+    assert es.frame_counts.cpu().tolist() == per_frame.tolist()
+    tight = int(per_frame.min()) - 100                                  # both frames over their cap
+    es, eh = mk(tight, True), mk(tight, False)
+    run(es)
+    assert es.frame_cap_exceeded()
+    es.use_hash_voxelizer()
+    ns, cs, fs = run(es)
+    nh, ch, fh = run(eh)
+    assert ns[0] == 2 * tight and ns == nh and np.array_equal(cs, ch) and np.array_equal(fs, fh)
+    assert mk(tight, None).sorted_voxelizer is False and mk(0, None).sorted_voxelizer is True

@@ -150,6 +150,44 @@ def test_rulebook_strided_overflow_is_safe(ops):
 
 # ------------------------------------------------------------------------------------------------ voxelization
 @pytest.mark.parametrize("cfg,batch", [("kitti", 1), ("waymo", 2)])
+def test_voxelize_sorted_is_the_hash_voxelizer_in_key_order(ops, cfg, batch):
+    """ql_voxelize_sorted_*: the same voxels, point counts and (bit for bit) the same means as the reference-ordered voxeliser, rows in
+    ascending linear key; the rank index it leaves serves the stage-1 rulebook; frame_counts = voxels per frame."""
+    c = O.CONFIGS[cfg]
+    kw = dict(n_az=500) if cfg == "kitti" else dict(n_beams=32, n_az=700)
+    pts = O.synth_batch(cfg, batch, **kw)
+    grid = O.grid_size_xyz(c["pc_range"], c["voxel_size"])
+    sshape = O.sparse_shape_zyx(grid)
+    f_ref, c_ref, n_ref = O.voxelize_mean_batch(pts, c["pc_range"], c["voxel_size"], c["max_pts"], 10 ** 7, sequential=True)
+    order = np.argsort(O._lin(c_ref, sshape), kind="stable")
+    cap = c_ref.shape[0] + 100
+    g4 = (batch, *sshape)
+    ws = torch.zeros(ops.rulebook_strided_workspace_bytes(g4, 1, 1, 0), dtype=torch.uint8, device="cuda")
+    fc = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    feats, coords, npts, n_dev = ops.voxelize_sorted(dev(pts), c["pc_range"], c["voxel_size"], grid, batch, c["max_pts"], cap, ws, frame_counts=fc)
+    n = int(n_dev[0].item())
+    assert n == c_ref.shape[0] and int(n_dev[1].item()) == n
+    assert np.array_equal(coords[:n].cpu().numpy(), c_ref[order])
+    assert np.array_equal(npts[:n].cpu().numpy(), n_ref[order])
+    assert np.array_equal(feats[:n].cpu().numpy().view(np.uint32), f_ref[order].view(np.uint32))      # left-to-right sums: bit-exact
+    assert np.array_equal(fc.cpu().numpy(), np.bincount(c_ref[:, 0], minlength=batch))
+    # the same features as the hash voxeliser, row for row after sorting
+    hf, hc, hn, hnd, _ = ops.voxelize_mean(dev(pts), c["pc_range"], c["voxel_size"], grid, batch, c["max_pts"], cap)
+    ho = np.argsort(O._lin(hc[:n].cpu().numpy(), sshape), kind="stable")
+    assert np.array_equal(hf[:n].cpu().numpy()[ho].view(np.uint32), feats[:n].cpu().numpy().view(np.uint32))
+    # rank index -> identity rulebook
+    rank = ops.rulebook_strided_index(g4, 1, 1, 0, ws)
+    nbr, km = ops.rulebook_subm_ranked(coords, n_dev, g4, (1, 1, 1), rank)
+    assert np.array_equal(dense_nbr(ops, nbr, km, n)[0], np.arange(n))
+    # batch capacity smaller than the voxel count: the first `cap` voxels in key order are kept, found is reported
+    small = n // 2
+    f2, c2, n2, nd2 = ops.voxelize_sorted(dev(pts), c["pc_range"], c["voxel_size"], grid, batch, c["max_pts"], small, ws)
+    assert nd2.cpu().tolist() == [small, n]
+    assert np.array_equal(c2[:small].cpu().numpy(), c_ref[order][:small])
+    assert np.array_equal(f2[:small].cpu().numpy().view(np.uint32), f_ref[order][:small].view(np.uint32))
+
+
+@pytest.mark.parametrize("cfg,batch", [("kitti", 1), ("waymo", 2)])
 def test_voxelize_hard_matches_cpu_voxelizer(ops, cfg, batch):
     c = O.CONFIGS[cfg]
     kw = dict(n_az=500) if cfg == "kitti" else dict(n_beams=32, n_az=700)
