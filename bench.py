@@ -363,6 +363,25 @@ def run_ours(args):
         dist.barrier()
     torch.cuda.synchronize()
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # From here on the plugin call does not read the row counts back (backbone.engine_lazy_counts: the three warm-up calls above sized the
+    # engine): it returns as soon as the graph replay is queued, so the host prepares step i+1 while the GPU runs step i.  Step i's
+    # encoded rows are moved aside on the device right after the call (an upper bound of rows: its count is not on the host yet) and
+    # read back to the host one iteration later, when its count has arrived.
+    bb.engine_lazy_counts = True
+    rows_ub = min(cap_enc, int(n_enc * 1.25) + 1024)
+    pending = [None, None]
+
+    def drain(j):
+        e_j = pending[j & 1]
+        n_j = e_j.num_rows()                                   # waits for step j's counts (long since on the host)
+        assert n_j <= rows_ub, (n_j, rows_ub)
+        with torch.cuda.stream(copy_stream):                   # the step's host-visible result
+            copy_stream.wait_event(produced[j & 1])
+            host_feats[j & 1][:n_j].copy_(out_feats[j & 1][:n_j], non_blocking=True)
+            host_idx[j & 1][:n_j].copy_(out_idx[j & 1][:n_j], non_blocking=True)
+            drained[j & 1].record(copy_stream)
+        return n_j * c_enc * 2 + n_j * idx_cols * 4
+
     e_start.record(main)
     h2d(0)
     d2h_bytes = 0
@@ -373,17 +392,15 @@ def run_ours(args):
         bd = plugin_step(stage_in[i & 1])
         consumed[i & 1].record(main)
         enc = bd["encoded_spconv_tensor"]
-        n = enc._features.shape[0]
         main.wait_event(drained[i & 1])                        # the side buffers of two steps ago have reached the host
-        out_feats[i & 1][:n].copy_(enc._features, non_blocking=True)
-        out_idx[i & 1][:n].copy_(enc.indices, non_blocking=True)
+        out_feats[i & 1][:rows_ub].copy_(enc.capacity_features[:rows_ub], non_blocking=True)
+        src_idx = enc.capacity_indices[:rows_ub]
+        out_idx[i & 1][:rows_ub].copy_(src_idx if enc._index_cols is None else src_idx[:, enc._index_cols], non_blocking=True)
         produced[i & 1].record(main)
-        with torch.cuda.stream(copy_stream):                   # the step's host-visible result
-            copy_stream.wait_event(produced[i & 1])
-            host_feats[i & 1][:n].copy_(out_feats[i & 1][:n], non_blocking=True)
-            host_idx[i & 1][:n].copy_(out_idx[i & 1][:n], non_blocking=True)
-            drained[i & 1].record(copy_stream)
-        d2h_bytes = n * c_enc * 2 + n * idx_cols * 4
+        pending[i & 1] = enc
+        if i > 0:
+            d2h_bytes = drain(i - 1)
+    d2h_bytes = drain(e2e_steps - 1)
     copy_stream.synchronize()
     e_end.record(main)
     torch.cuda.synchronize()
@@ -395,6 +412,7 @@ def run_ours(args):
     e2e_value = world * BATCH * e2e_steps / (float(e2e_ms.item()) / 1e3)
     last = (e2e_steps - 1) & 1
     assert torch.equal(host_idx[last][:n_enc], enc.indices.cpu()) and host_feats[last][:n_enc].abs().sum().item() > 0, "e2e read-back is empty / wrong"
+    bb.engine_lazy_counts = False
     eng = bb._engine_state["eng"]
     assert eng.counts() == counts, "the plugin-call path disagrees with the device-resident path"
 
@@ -558,7 +576,7 @@ def run_ours(args):
                    "parallelism": f"frame-sharded x{world} (no data-path collective)"},
         "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": int(pts_np.nbytes),
                 "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": round(float(e2e_ms.item()) / e2e_steps, 4),
-                "note": "pinned host points -> H2D (copy stream, double buffered) -> VoxelizeMeanVFE(batch_dict) -> backbone(batch_dict)"
+                "note": "pinned host points -> H2D (copy stream, double buffered) -> VoxelizeMeanVFE(batch_dict) -> backbone(batch_dict) [engine_lazy_counts: no count read-back inside the call]"
                         + (" -> HeightCompression(batch_dict)" if has_bev else "") + " -> D2H of the encoded sparse tensor (fp16 rows + int32 indices)"},
         "gpu_launches": int(kernels_per_step * args.steps),
         "kernels_per_step": int(kernels_per_step),

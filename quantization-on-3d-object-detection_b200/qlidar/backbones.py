@@ -96,6 +96,10 @@ class _BackboneBase(nn.Module):
     Row order: the engine returns every stage in ascending-key order (x_conv1 included: the reference keeps the voxeliser's
     order there); coordinates travel with the features, so consumers that index by `indices` are unaffected."""
     use_engine = True
+    # True: once a synchronous call has sized the engine for the kind of batch it sees, later calls return WITHOUT reading the row counts
+    # back (the call's only host synchronisation): the published sparse tensors are LazySparseConvTensor objects that resolve their shape
+    # on first access, their rows live in the engine's buffers until the next call.  See sparse.LazySparseConvTensor.
+    engine_lazy_counts = False
     engine_bev_dtype = None                   # set by HeightCompression.attach(): the BEV map is then produced inside the graph
 
     def _input_tensor(self, batch_dict):
@@ -209,6 +213,9 @@ class _BackboneBase(nn.Module):
             return None
         pts = batch_dict.get('_ql_points') if batch_dict.get('voxel_features') is None else None
         vf, vc = (pts, None) if pts is not None else (batch_dict['voxel_features'], batch_dict['voxel_coords'])
+        B = int(batch_dict['batch_size'])
+        if self.engine_lazy_counts and self._engine_state.get("settled"):
+            return self._engine_forward_lazy(batch_dict, eng, pts, vf, vc, B)
         for attempt in range(10):
             out = eng.forward_points(pts) if pts is not None else eng.forward_voxels(vf, vc)
             call = eng.counts_all.cpu()                                         # the one synchronisation of the call
@@ -230,8 +237,8 @@ class _BackboneBase(nn.Module):
             eng = self._engine_for(batch_dict, stage_caps=caps)
         else:
             raise RuntimeError("engine stage capacities did not converge")
+        self._engine_state["settled"] = True                                    # capacities and the voxeliser choice fit this kind of batch
         n = [int(v) for v in counts[:, 0].tolist()]
-        B = int(batch_dict['batch_size'])
         if pts is not None:
             # the fused voxeliser's products, as the VFE plugin would have published them (rows in ascending-key order)
             batch_dict['voxel_features'] = eng.vox_feats[:n[0], :eng.nfeat]
@@ -255,6 +262,57 @@ class _BackboneBase(nn.Module):
             enc._ql_spatial_features = eng.spatial_features                     # HeightCompression takes the fused map
         taps = {L.tap: tensor(L.out, L.stage_out) for L in eng.layers if L.tap}
         return self._publish(batch_dict, enc, taps)
+
+
+def _engine_forward_lazy(self, batch_dict, eng, pts, vf, vc, B):
+    """The plugin call without its host synchronisation (engine_lazy_counts): the graph is replayed, the counts start their way to
+    the host (pinned ring slot + event) and the published sparse tensors resolve their shapes on first access.  Only after one
+    synchronous call has sized the engine for this kind of batch ("settled"); overflows then surface as errors at resolve time."""
+    from .sparse import LazySparseConvTensor, PendingCounts
+    eng.forward_points(pts) if pts is not None else eng.forward_voxels(vf, vc)
+    ring = self.__dict__.setdefault("_ql_count_ring", [])
+    k = self.__dict__.get("_ql_count_k", 0)
+    self._ql_count_k = k + 1
+    if len(ring) < 16:
+        ring.append([torch.empty(eng.counts_all.numel(), dtype=torch.int32).pin_memory(), None])
+        slot = ring[-1]
+    else:
+        slot = ring[k % 16]
+        if slot[1] is not None and slot[1]._n is None and slot[0].numel() == eng.counts_all.numel():
+            try:
+                slot[1].counts()                                                # 16 calls old and never read: settle it before its slot is reused
+            except Exception:
+                pass
+        if slot[0].numel() != eng.counts_all.numel():
+            slot[0] = torch.empty(eng.counts_all.numel(), dtype=torch.int32).pin_memory()
+    slot[0].copy_(eng.counts_all, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    pend = PendingCounts(slot[0], ev, len(eng.stages), eng.max_voxels_per_frame if (pts is not None and eng.sorted_voxelizer) else 0)
+    slot[1] = pend
+    if pts is not None:
+        # capacity-sized: the first voxel_count rows are valid (this mode's one deviation from the plugin contract)
+        batch_dict['voxel_features'] = eng.vox_feats[:, :eng.nfeat]
+        batch_dict['voxel_coords'] = eng.stages[0].coords
+        batch_dict['voxel_count'] = eng.stages[0].n_dev
+
+    def tensor(feats, stage_i, cols=None, shape=None):
+        stg = eng.stages[stage_i]
+        return LazySparseConvTensor(pend, stage_i, feats, stg.coords, shape if shape is not None else list(stg.grid[1:]), B,
+                                    surface_dtype=vf.dtype, index_cols=cols)
+
+    last = eng.layers[-1]
+    if getattr(eng, "merge_stage", None) is not None:                            # VoxelNeXt: the encoded tensor is 2-D, [b, y, x]
+        enc = tensor(last.out, last.stage_out, cols=[0, 2, 3], shape=list(eng.stages[last.stage_out].grid[2:]))
+    else:
+        enc = tensor(last.out, last.stage_out)
+    if eng.bev:
+        enc._ql_spatial_features = eng.spatial_features
+    taps = {L.tap: tensor(L.out, L.stage_out) for L in eng.layers if L.tap}
+    return self._publish(batch_dict, enc, taps)
+
+
+_BackboneBase._engine_forward_lazy = _engine_forward_lazy
 
 
 class VoxelBackBone8x(_BackboneBase):

@@ -136,6 +136,76 @@ class SparseConvTensor:
         return self._table
 
 
+class PendingCounts:
+    """The (kept, found) row counts of one engine forward, on their way to the host: an asynchronous copy into pinned memory plus the
+    event that marks its arrival.  counts() waits for the event (usually long past) and returns the kept rows per stage; it raises
+    if the forward overflowed a stage capacity or a per-frame voxel cap -- the synchronous plugin call handles those by re-running,
+    a deferred one no longer can."""
+
+    def __init__(self, host: torch.Tensor, event: torch.cuda.Event, n_stages: int, frame_cap: int = 0):
+        self.host, self.event, self.n_stages, self.frame_cap = host, event, n_stages, int(frame_cap)
+        self._n: Optional[List[int]] = None
+
+    def counts(self) -> List[int]:
+        if self._n is None:
+            self.event.synchronize()
+            c = self.host[:2 * self.n_stages].view(self.n_stages, 2)
+            if bool((c[1:, 1] > c[1:, 0]).any()) or (self.frame_cap and bool((self.host[2 * self.n_stages:] > self.frame_cap).any())):
+                raise QlidarError("an engine capacity or per-frame voxel cap was exceeded in a deferred-count call: run this batch with "
+                                  "engine_lazy_counts = False once (the synchronous call re-sizes the engine) and switch it back on")
+            self._n = [int(v) for v in c[:, 0].tolist()]
+        return self._n
+
+
+class LazySparseConvTensor(SparseConvTensor):
+    """An engine result whose row count is still on the device (backbone.engine_lazy_counts = True): `features` / `indices` are cut out
+    of the engine's capacity-sized buffers the first time anyone reads them, which is when the host first needs the count.  A
+    CenterPoint forward never does (the dense BEV map has a fixed shape), so the whole plugin chain stays free of host synchronisation
+    and the host can queue the next batch while this one runs.  capacity_features / capacity_indices are the engine's own buffers:
+    they hold this call's rows until the next call of the same backbone overwrites them."""
+
+    def __init__(self, pending: PendingCounts, stage_i: int, feats_full: torch.Tensor, coords_full: torch.Tensor, spatial_shape, batch_size: int,
+                 surface_dtype=None, index_cols=None):
+        self._pending, self._stage_i = pending, stage_i
+        self.capacity_features, self.capacity_indices, self._index_cols = feats_full, coords_full, index_cols
+        self._lazy_f = self._lazy_i = None
+        self._features_as = None
+        self._surface_dtype = surface_dtype if (surface_dtype is not None and surface_dtype != feats_full.dtype) else None
+        self.spatial_shape = [int(v) for v in spatial_shape]
+        self.batch_size = int(batch_size)
+        self.indice_dict = {}
+        self.grid = None
+        self.voxel_num = None
+        self.benchmark = False
+        self._table = None
+        self._table_src = None
+        self._n_dev = None
+
+    def num_rows(self) -> int:
+        return self._pending.counts()[self._stage_i]
+
+    @property
+    def _features(self):
+        if self._lazy_f is None:
+            self._lazy_f = self.capacity_features[:self.num_rows()]
+        return self._lazy_f
+
+    @_features.setter
+    def _features(self, value):
+        self._lazy_f = value
+
+    @property
+    def indices(self):
+        if self._lazy_i is None:
+            idx = self.capacity_indices[:self.num_rows()]
+            self._lazy_i = idx if self._index_cols is None else idx[:, self._index_cols].contiguous()
+        return self._lazy_i
+
+    @indices.setter
+    def indices(self, value):
+        self._lazy_i = value
+
+
 class SparseModule(nn.Module):
     """Marker base ([EXT] spconv.pytorch.modules.SparseModule; quant/quant.py:3)."""
     pass

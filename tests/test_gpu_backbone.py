@@ -562,3 +562,55 @@ def test_engine_sorted_voxelizer_steps_aside_when_a_frame_exceeds_its_voxel_cap(
     nh, ch, fh = run(eh)
     assert ns[0] == 2 * tight and ns == nh and np.array_equal(cs, ch) and np.array_equal(fs, fh)
     assert mk(tight, None).sorted_voxelizer is False and mk(0, None).sorted_voxelizer is True
+
+
+@pytest.mark.parametrize("arch", ["VoxelResBackBone8x", "VoxelResBackBone8xVoxelNeXt"])
+def test_plugin_call_with_deferred_counts_gives_the_same_tensors(arch):
+    """backbone.engine_lazy_counts: after one synchronous call has sized the engine, the plugin call queues the graph replay and returns
+    without reading the row counts back; the published tensors resolve their shapes on first access and equal the synchronous call's.
+    From raw points (VoxelizeMeanVFE attached) and from a voxelised batch_dict; an overflowing batch raises when its shape is read."""
+    import qlidar
+    pts, feats, coords, grid, c = make_frame("waymo", batch=2)
+    nfeat = 5
+    if arch == "VoxelResBackBone8xVoxelNeXt":
+        bb = qlidar.VoxelResBackBone8xVoxelNeXt(qlidar.Cfg(SPCONV_KERNEL_SIZES=[3, 3, 3, 3], OUT_CHANNEL=128, CHANNELS=[16, 32, 64, 128, 128]),
+                                                nfeat, np.asarray(grid)).cuda().eval()
+    else:
+        _, _, bb = build(arch, nfeat, grid)
+    vfe = qlidar.VoxelizeMeanVFE({}, nfeat, c["voxel_size"], c["pc_range"], c["max_pts"], coords.shape[0] + 100).attach(bb)
+    tp = torch.from_numpy(pts).cuda()
+
+    def call():
+        with torch.no_grad():
+            return bb(vfe({"points": tp, "batch_size": 2}))
+
+    sync = call()
+    e0 = sync["encoded_spconv_tensor"]
+    ref_f, ref_i = e0.features.clone(), e0.indices.clone()
+    ref_taps = {k: (t.features.clone(), t.indices.clone()) for k, t in sync["multi_scale_3d_features"].items()}
+    bb.engine_lazy_counts = True
+    for _ in range(3):
+        lazy = call()
+    e1 = lazy["encoded_spconv_tensor"]
+    assert type(e1).__name__ == "LazySparseConvTensor" and e1._lazy_f is None          # nothing read back yet
+    assert e1.spatial_shape == e0.spatial_shape and e1.batch_size == 2
+    assert e1.num_rows() == ref_f.shape[0]
+    assert torch.equal(e1.indices, ref_i) and torch.equal(e1.features, ref_f) and e1.features.dtype == ref_f.dtype
+    for k, t in lazy["multi_scale_3d_features"].items():
+        assert torch.equal(t.features, ref_taps[k][0]) and torch.equal(t.indices, ref_taps[k][1]), k
+    n0 = int(lazy["voxel_count"][0].item())
+    assert n0 == coords.shape[0] and lazy["voxel_coords"].shape[0] >= n0
+    # a batch twice as dense as anything the engine was sized for: the deferred call cannot re-run itself, it says so
+    dense = torch.cat([tp, tp + torch.tensor([0, 0.05, 0.05, 0.07, 0, 0], device="cuda")[: tp.shape[1]]])[: int(tp.shape[0] * 1.2)].contiguous()
+    eng = bb._engine_state["eng"]
+    if dense.shape[0] <= eng.max_points:
+        with torch.no_grad():
+            over = bb(vfe({"points": dense, "batch_size": 2}))
+        try:
+            over["encoded_spconv_tensor"].num_rows()
+            overflowed = False
+        except qlidar.QlidarError:
+            overflowed = True
+        c_all = eng.counts_all.cpu()
+        assert overflowed == bool((c_all[2:2 * len(eng.stages)].view(-1, 2)[:, 1] > c_all[2:2 * len(eng.stages)].view(-1, 2)[:, 0]).any()
+                                  or eng.frame_cap_exceeded(c_all))
