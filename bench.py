@@ -594,7 +594,7 @@ def run_ours(args):
     }
     if gathered is not None:
         line["gathered_sites_per_frame"] = gathered
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -722,10 +722,29 @@ def run_reference(args):
                        "note": "reference's CPU path = oracle port (spconv / pytorch_quantization are not installable here)"},
             "cpu_baseline": base, "e2e": {"value": round(v, 5), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The run's ONE stdout line.  File descriptor 1 was pointed at stderr for the duration of the run (main()): libraries that write to
+    stdout from C (NCCL prints its version line there) cannot get in front of the JSON."""
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
