@@ -136,6 +136,28 @@ int main() {
         const double f = run<false>(n, iters, sms), i = run<true>(n, iters, sms);
         printf("%6d %14.1f %14.1f\n", n, f, i);
     }
+    // sustained: the same N = 256 loop for >= 3 s of back-to-back launches (power / clock settling), against the burst figure above
+    for (int kind = 0; kind < 2; ++kind) {
+        const size_t smem = 1024 + 256 * 128;
+        const int it2 = 1 << 20;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        float ms = 0.f;
+        int launches = 0;
+        do {
+            for (int r = 0; r < 8; ++r) {
+                if (kind) k_peak<true><<<sms, 128, smem>>>(256, it2); else k_peak<false><<<sms, 128, smem>>>(256, it2);
+                ++launches;
+            }
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            cudaEventElapsedTime(&ms, e0, e1);
+        } while (ms < 3000.f);
+        const double kelems = kind ? 32.0 : 16.0;
+        printf("sustained %s N=256: %.1f %s over %.2f s (%d launches)\n", kind ? "kind::i8 " : "kind::f16", 2.0 * 128.0 * 256 * kelems * (double)it2 * sms * launches / (ms * 1e-3) / 1e12,
+               kind ? "TOPS" : "TFLOP/s", ms * 1e-3, launches);
+    }
     long long* cyc;
     cudaMalloc(&cyc, 16);
     const size_t smem = 1024 + 256 * 128;
