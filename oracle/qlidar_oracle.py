@@ -1198,3 +1198,76 @@ def centerhead_generate_predicted_boxes(pred_dicts, class_id_mapping_each_head, 
         ret[b] = {"pred_boxes": np.concatenate(ret[b]["pred_boxes"], 0), "pred_scores": np.concatenate(ret[b]["pred_scores"], 0),
                   "pred_labels": np.concatenate(ret[b]["pred_labels"], 0) + 1}
     return ret
+
+
+# ----------------------------------------------------------------------------------------------
+# Histogram calibration ([EXT] pytorch_quantization calib.HistogramCalibrator, published algorithm; parity UNPINNED: the package is
+# neither in this image nor vendored by the reference -- call sites quant/quantize.py:138-145,198-207, count_time_n_memory.py:304-365).
+# numpy, float64, written independently of qlidar/tensor_quant.py.
+# ----------------------------------------------------------------------------------------------
+def hist_collect(batches, num_bins=2048):
+    """|x| histogram with equal bins over [0, max of the FIRST batch]; later batches extend the range with bins of the same width."""
+    hist = edges = None
+    for x in batches:
+        a = np.abs(np.asarray(x, dtype=np.float32)).reshape(-1)
+        if a.size == 0:
+            continue
+        if hist is None:
+            top = float(a.max()) if a.max() > 0 else 1.0
+            edges = np.linspace(0.0, top, num_bins + 1, dtype=np.float32)
+            hist, _ = np.histogram(a, bins=num_bins, range=(0.0, top))
+            hist = hist.astype(np.float64)
+        else:
+            width = edges[1] - edges[0]
+            if a.max() > edges[-1]:
+                n = int(np.ceil(np.float32(a.max()) / width))
+                edges = (np.arange(n + 1, dtype=np.float32) * width).astype(np.float32)
+            h, _ = np.histogram(a, bins=len(edges) - 1, range=(0.0, float(edges[-1])))
+            h = h.astype(np.float64)
+            h[:len(hist)] += hist
+            hist = h
+    return hist, edges
+
+
+def hist_amax_percentile(hist, edges, percentile=99.99):
+    cdf = np.cumsum(hist / hist.sum())
+    return np.float32(edges[min(int(np.searchsorted(cdf, percentile / 100.0)), len(edges) - 1)])
+
+
+def hist_amax_mse(hist, edges, num_bits=8, stride=1, start_bin=128):
+    centers = ((edges[1:].astype(np.float64) + edges[:-1]) / 2).astype(np.float32)
+    bound = np.float32(2 ** (num_bits - 1) - 1)
+    best = None
+    for i in range(start_bin, len(hist) + 1, stride):
+        amax = centers[i - 1]
+        scale = bound / amax
+        q = np.clip(np.rint(centers * scale), -bound, bound) / scale
+        err = float(np.mean(((q - centers).astype(np.float32) ** 2) * hist.astype(np.float32)))
+        if best is None or err < best[0]:
+            best = (err, amax)
+    return np.float32(best[1])
+
+
+def hist_amax_entropy(hist, edges, num_bits=8, stride=1, start_bin=128):
+    bins = hist.astype(np.float64).copy()
+    bins[0] = bins[1]
+    levels = 1 << (num_bits - 1)
+    best = None
+    for i in range(max(start_bin, levels), len(bins) + 1, stride):
+        ref = bins[:i].copy()
+        ref[i - 1] += bins[i:].sum()
+        cand = np.zeros(i)
+        lvl = (np.arange(i) * levels) // i
+        for L in range(levels):
+            sel = lvl == L
+            nz = sel & (bins[:i] != 0)
+            if nz.any():
+                cand[nz] = bins[:i][sel].sum() / nz.sum()
+        p, q = ref / ref.sum(), cand / cand.sum()
+        m = p > 0
+        if (q[m] == 0).any():
+            continue
+        kl = float(np.sum(p[m] * np.log(p[m] / q[m])))
+        if best is None or kl < best[0]:
+            best = (kl, i)
+    return np.float32(edges[best[1] if best else len(bins)])

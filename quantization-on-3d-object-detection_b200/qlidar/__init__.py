@@ -6,7 +6,7 @@ from . import ops
 from ._lib import QlidarError, lib
 from .sparse import (SparseConvTensor, SparseModule, SparseSequential, SparseConvolution, SubMConv3d, SparseConv3d,
                      SubMConv2d, SparseConv2d, SparseInverseConv3d, replace_feature)
-from .tensor_quant import QuantDescriptor, TensorQuantizer, MaxCalibrator
+from .tensor_quant import QuantDescriptor, TensorQuantizer, MaxCalibrator, HistogramCalibrator
 from .quant import QConvNd, QConv3d, QConv2d, GQConv3d, SQConv3d, q_conv3d, gq_conv3d, sq_conv3d, collect_stats, compute_amax
 from .backbones import (Cfg, post_act_block, SparseBasicBlock, VoxelBackBone8x, VoxelResBackBone8x,
                         VoxelResBackBone8xVoxelNeXt, MeanVFE, DynamicMeanVFE, VoxelizeMeanVFE, VoxelGeneratorWrapper, HeightCompression)

@@ -19,7 +19,7 @@ import torch.nn as nn
 from . import ops
 from .sparse import (SparseConvolution, SparseConvTensor, SparseModule, SubMConv3d, SparseConv3d, SubMConv2d, SparseConv2d,
                      _make_output, _round_up)
-from .tensor_quant import QuantDescriptor, TensorQuantizer, quant_scale, reduce_amax
+from .tensor_quant import QuantDescriptor, TensorQuantizer, MaxCalibrator, HistogramCalibrator, quant_scale, reduce_amax
 
 
 class QConvNd(SparseModule):
@@ -87,7 +87,9 @@ class QConvNd(SparseModule):
     def forward(self, x: SparseConvTensor) -> SparseConvTensor:
         conv = self.module
         aq = self.act_quant
-        if aq._if_calib:                                             # collect_stats: MaxCalibrator running max
+        if aq._if_calib and isinstance(aq._calibrator, HistogramCalibrator):
+            aq._calibrator.collect(x.features)                       # the histogram needs every value, not the reduced maxima
+        elif aq._if_calib:                                           # collect_stats: MaxCalibrator running max
             am = ops.absmax_cols(x.features.contiguous(), x._n_dev)
             aq._calibrator.collect(am.view(1, -1) if self.cw else am.max().view(()))  # noqa: the calibrator sees reduced maxima
         if aq._disabled or not aq._if_quant:
@@ -333,7 +335,10 @@ def compute_amax(model, device, **kwargs):
     for _, module in model.named_modules():
         if isinstance(module, TensorQuantizer):
             if module._calibrator is not None:
-                module.load_calib_amax(strict=False)
+                if isinstance(module._calibrator, MaxCalibrator):
+                    module.load_calib_amax(strict=False)
+                else:
+                    module.load_calib_amax(**kwargs)                # method='entropy' | 'mse' | 'percentile', percentile=...
                 if module.amax is not None:
                     module._amax = module._amax.to(device)
     return

@@ -320,3 +320,44 @@ def test_rotated_iou_and_nms_oracle_known_answers():
     assert list(O.nms_rotated(b, s, 0.3)) == [0, 3]
     assert list(O.nms_rotated(b, s[::-1].copy(), 0.5)) == [5, 4, 3, 2]      # score order decides who survives
     assert list(O.nms_rotated(b, s, 0.5, pre_max=2)) == [0] and list(O.nms_rotated(b, s, 0.5, post_max=2)) == [0, 2]
+
+
+# ---------------------------------------------------------------------------------------------- histogram calibration
+def test_histogram_calibrator_matches_the_numpy_restatement_and_closed_forms():
+    """qlidar.HistogramCalibrator (torch) against the oracle's independent numpy restatement on a multi-batch activation stream whose
+    range grows, for the three compute_amax methods; plus closed-form cases: a uniform distribution's 50th percentile, and an outlier
+    that max-calibration would follow while entropy / percentile clip it."""
+    import qlidar
+    g = torch.Generator().manual_seed(3)
+    batches = [torch.relu(torch.randn(20000, generator=g)) * s for s in (1.0, 1.5, 0.8)]
+    batches[1][7] = 40.0                                                        # one outlier, far above the bulk
+    cal = qlidar.HistogramCalibrator(8, None, False)
+    for b in batches:
+        cal.collect(b)
+    hist, edges = O.hist_collect([b.numpy() for b in batches])
+    assert cal._calib_hist.numel() == len(hist)
+    assert np.array_equal(cal._calib_hist.numpy().astype(np.int64), hist.astype(np.int64))
+    np.testing.assert_allclose(cal._calib_bin_edges.numpy(), edges, rtol=1e-6)
+    a_pct = float(cal.compute_amax("percentile", percentile=99.9))
+    a_mse = float(cal.compute_amax("mse", stride=16))
+    a_ent = float(cal.compute_amax("entropy", stride=8))
+    assert abs(a_pct - float(O.hist_amax_percentile(hist, edges, 99.9))) <= 1e-6 * a_pct
+    assert abs(a_mse - float(O.hist_amax_mse(hist, edges, 8, 16))) <= 1e-6 * a_mse
+    assert abs(a_ent - float(O.hist_amax_entropy(hist, edges, 8, 8))) <= 1e-6 * a_ent
+    for a in (a_pct, a_ent):
+        assert 2.0 < a < 10.0                                                   # the bulk (sigma <= 1.5), not the outlier at 40
+    assert 10.0 < a_mse < 40.0                   # squared error weighs the one clipped outlier (34^2) above the bulk's finer steps
+    # closed form: uniform on [0, 1): the median edge
+    u = qlidar.HistogramCalibrator(8, None, False, num_bins=1000)
+    u.collect(torch.arange(100000, dtype=torch.float32) / 100000)
+    assert abs(float(u.compute_amax("percentile", percentile=50.0)) - 0.5) <= 2e-3
+    # through the quantiser, the way quant/quantize.py:175-207 drives it
+    q = qlidar.TensorQuantizer(qlidar.QuantDescriptor(num_bits=8, calib_method="histogram"))
+    q.enable_calib(); q.disable_quant()
+    for b in batches:
+        q(b)
+    q.disable_calib(); q.enable_quant()
+    q.load_calib_amax("percentile", percentile=99.9)
+    assert abs(float(q.amax) - a_pct) <= 1e-6 * a_pct
+    y = q(batches[0])
+    assert float(y.abs().max()) <= a_pct * (1 + 1e-6) and torch.unique(y).numel() <= 255
