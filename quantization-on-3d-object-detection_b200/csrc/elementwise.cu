@@ -13,7 +13,7 @@ __device__ __forceinline__ float load_as_float(const void* x, int dtype, int64_t
 __global__ void __launch_bounds__(256) k_absmax_cols(const void* x, int dtype, int64_t n_cap, const int* n_dev, int c,
                                                      float* absmax) {
     extern __shared__ uint32_t s_max[];
-    const int64_t n = n_dev ? (int64_t)*n_dev : n_cap;
+    const int64_t n = n_dev ? min((int64_t)*n_dev, (int64_t)n_cap) : n_cap;
     for (int j = threadIdx.x; j < c; j += blockDim.x) s_max[j] = 0u;
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) k_absmax_cols(const void* x, int dtype, i
 __global__ void __launch_bounds__(256) k_absmax_cols_h8(const __half* __restrict__ x, int64_t n_cap, const int* __restrict__ n_dev, int c,
                                                         float* absmax) {
     extern __shared__ uint32_t s_max[];
-    const int64_t n = n_dev ? (int64_t)*n_dev : n_cap;
+    const int64_t n = n_dev ? min((int64_t)*n_dev, (int64_t)n_cap) : n_cap;
     for (int j = threadIdx.x; j < c; j += blockDim.x) s_max[j] = 0u;
     __syncthreads();
     const int groups = c >> 3;
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) k_quantize_rows(const void* x, int in_dty
     float* s_scale = s_par;
     float* s_inv = s_par + c;
     float* s_smooth = s_par + 2 * c;
-    const int64_t n = n_dev ? (int64_t)*n_dev : n_cap;
+    const int64_t n = n_dev ? min((int64_t)*n_dev, (int64_t)n_cap) : n_cap;
     __shared__ float s_tensor_amax;
     if (threadIdx.x == 0) {
         float m = 0.f;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) k_quantize_rows_h8(const __half* __restri
     extern __shared__ float s_par[];                   // [c] scale, [c] smooth
     float* s_scale = s_par;
     float* s_smooth = s_par + c;
-    const int64_t n = n_dev ? (int64_t)*n_dev : n_cap;
+    const int64_t n = n_dev ? min((int64_t)*n_dev, (int64_t)n_cap) : n_cap;
     __shared__ float s_tensor_amax;
     if (threadIdx.x == 0) {
         float m = 0.f;
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256) k_quantize_rows_h8(const __half* __restri
 // per-row amax (GQConv3d, quant/quant_conv3d.py:112-131): one warp per row
 __global__ void __launch_bounds__(256) k_fake_quant_per_row(const void* x, int in_dtype, int64_t n_cap, const int* n_dev, int c,
                                                             float bound, __half* out) {
-    const int64_t n = n_dev ? (int64_t)*n_dev : n_cap;
+    const int64_t n = n_dev ? min((int64_t)*n_dev, (int64_t)n_cap) : n_cap;
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(QL_TILE_M) k_stem_conv(const float* __restrict
     constexpr int CI = C_IN > 0 ? C_IN : 16;           // register rows sized for the widest generic input
     extern __shared__ float s_w[];                     // [kvol][c_in][C_OUT] then uint32 absmax[C_OUT]
     uint32_t* s_absmax = reinterpret_cast<uint32_t*>(s_w + kvol * c_in * C_OUT);
-    const int64_t n = n_dev ? (int64_t)*n_dev : n_cap;
+    const int64_t n = n_dev ? min((int64_t)*n_dev, (int64_t)n_cap) : n_cap;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t tile = (int64_t)blockIdx.x * 4 + warp;
     if ((int64_t)blockIdx.x * 4 * QL_TILE_M >= n) return;             // whole CTA past the device-side row count

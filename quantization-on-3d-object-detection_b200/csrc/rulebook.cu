@@ -210,7 +210,7 @@ __device__ __forceinline__ void for_each_candidate(const int4& c, const ConvGeom
 
 __global__ void __launch_bounds__(256) k_rb_mark(const int4* __restrict__ in_coords, int64_t n_cap, const int* __restrict__ n_dev,
                                                  ConvGeom cg, QlGrid gout, uint32_t* __restrict__ bitmap) {
-    const int64_t n = n_dev ? (int64_t)*n_dev : n_cap;
+    const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;        // clamped: a producer that found more rows than its capacity kept only n_cap
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int4 c = in_coords[i];
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(256) k_rb_scatter(const int4* __restrict__ in_
                                                     ConvGeom cg, QlGrid gout, const uint32_t* __restrict__ bitmap,
                                                     const uint32_t* __restrict__ word_prefix, int64_t n_out_cap,
                                                     int* __restrict__ nbr) {
-    const int64_t n = n_dev ? (int64_t)*n_dev : n_cap;
+    const int64_t n = n_dev ? min((int64_t)*n_dev, (int64_t)n_cap) : n_cap;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int4 c = in_coords[i];

@@ -245,7 +245,7 @@ __global__ void k_mean_vfe(const float* voxels, const void* num, int num_is_floa
 
 __global__ void k_hash_build(const int4* coords, int64_t n_cap, const int* n_dev, QlGrid g, uint2* table, uint32_t cap_mask) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t n = n_dev ? (int64_t)*n_dev : n_cap;
+    int64_t n = n_dev ? min((int64_t)*n_dev, (int64_t)n_cap) : n_cap;
     if (i >= n) return;
     int4 c = coords[i];
     uint32_t s = ql_hash_insert(table, cap_mask, ql_key(g, c.x, c.y, c.z, c.w));

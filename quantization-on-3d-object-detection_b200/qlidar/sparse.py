@@ -340,6 +340,23 @@ class SparseConvolution(SparseModule):
         rb = self.get_rulebook(x)
         f = x.features
         in_dtype = f.dtype
+        if in_dtype == torch.float32 and self.in_channels <= 8 and self.out_channels in (16, 32) and self.ndim == 3:
+            # the un-quantised stem on raw point features (conv_input.0: metre-scale coordinates, intensities up to 255): fp32 SIMT
+            # conv like the engine's, not the fp16 tensor-core path -- a half cast here would round the inputs (and overflow above
+            # 65504) before calibration ever sees them
+            key = ("stem", self.weight._version, self.weight.data_ptr(), str(f.device))
+            hit = self._pack_cache.get("stem")
+            if hit is None or hit[0] != key:
+                K = 1
+                for k in self.kernel_size:
+                    K *= k
+                w_kio = self.weight.detach().float().reshape(self.out_channels, K, self.in_channels).permute(1, 2, 0).contiguous().to(f.device)
+                hit = (key, w_kio)
+                self._pack_cache["stem"] = hit
+            scale = torch.ones(self.out_channels, dtype=torch.float32, device=f.device)
+            shift = self.bias.detach().float().to(f.device) if self.bias is not None else torch.zeros(self.out_channels, dtype=torch.float32, device=f.device)
+            y = ops.stem_conv(f.contiguous(), rb.nbr, rb.n_out, rb.n_out_dev, hit[1], scale, shift, relu=False, out_dtype=torch.float32, kmask=rb.kmask)
+            return _make_output(x, rb, y, self.ndim)
         packed, ic_p, oc_p = self._packed_weight(f.device)
         fh = f if f.dtype == torch.float16 else f.to(torch.float16)
         if ic_p != self.in_channels:
