@@ -54,7 +54,7 @@ constexpr uint32_t kFlagFirst = 1u, kFlagLast = 2u;
 
 #ifdef QL_SPCONV_ABLATE
 // test-time build flag (never in the product library): bit 1 = no gather loads, 2 = no tcgen05.st, 4 = no tcgen05.mma,
-// 8 = no epilogue global traffic, 16 = no rulebook slab copies, 64 = no tcgen05.ld / epilogue arithmetic
+// 8 = no epilogue global traffic, 16 = no rulebook slab copies, 32 = no streamed-weight copies, 64 = no tcgen05.ld / epilogue arithmetic
 __device__ int g_ablate = 0;
 #define QL_ABL(bit) ((abl_ & (bit)) != 0)
 #define QL_ABL_INIT const int abl_ = g_ablate
@@ -772,11 +772,15 @@ __global__ void __launch_bounds__(kThreadsMax, 1) k_spconv_ts(const ConvParams p
                 QL_TR(2);
                 ql_mbar_wait(empty0 + slot * 8u, sph ^ 1u);
                 QL_TR(1);
-                if (lane == 0) ql_mbar_arrive_expect_tx(fbar, n_sub * b_sub_bytes);
-                __syncwarp();
-                if ((uint32_t)lane < n_sub) {
-                    const uint32_t chunk = (uint32_t)ql_lds_s32(ubuf + 16u + 4u * (uint32_t)lane);
-                    ql_bulk_g2s(smem_base_u32 + (slot * U + (uint32_t)lane) * b_sub_bytes, p.w_packed + (size_t)chunk * b_sub_bytes, b_sub_bytes, fbar);
+                if (QL_ABL(32)) {                                   // (test-time build) no weight stream: the B slots keep whatever they hold
+                    if (lane == 0) ql_mbar_arrive(fbar);
+                } else {
+                    if (lane == 0) ql_mbar_arrive_expect_tx(fbar, n_sub * b_sub_bytes);
+                    __syncwarp();
+                    if ((uint32_t)lane < n_sub) {
+                        const uint32_t chunk = (uint32_t)ql_lds_s32(ubuf + 16u + 4u * (uint32_t)lane);
+                        ql_bulk_g2s(smem_base_u32 + (slot * U + (uint32_t)lane) * b_sub_bytes, p.w_packed + (size_t)chunk * b_sub_bytes, b_sub_bytes, fbar);
+                    }
                 }
                 __syncwarp();
                 ++uw;
