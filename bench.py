@@ -89,6 +89,15 @@ def peaks():
 # tcgen05.mma kind::i8 ceiling of this pool's B200s (M = 128, N >= 128, A in TMEM, all 148 SMs issuing back to back):
 # tools/microbench/mma_peak.cu, output committed as profiles/r01_mma_peak_microbench.txt (kind::f16: 2233 TFLOP/s)
 I8_MMA_PEAK_TOPS = 4596.0
+
+
+def i8_gemm_peak():
+    """Sustained dense 8192^3 INT8 GEMM throughput of a B200 of this pool (tools/int8_gemm_peak.py, committed measurement), or None."""
+    p = os.path.join(ROOT, "profiles", "r02_int8_gemm_peak.json")
+    try:
+        return float(json.load(open(p))["int8_sustained_tops"])
+    except Exception:
+        return None
 # experiment switch: extra BackboneEngine keyword arguments as JSON, e.g. QL_ENGINE_KW='{"group_rows": false}' (default: none)
 ENGINE_KW = json.loads(os.environ.get("QL_ENGINE_KW", "{}"))
 
@@ -525,7 +534,8 @@ def run_ours(args):
                 return {"frames_per_sec": round(BATCH / (ms8 / 1e3), 2), "ms_per_step": round(ms8, 4), "conv_ms_per_step": round(tc8 * 1e3, 4),
                         "quantize_ms_per_step": round(q8 * 1e3, 4), "tops_alg": round(ops8 / tc8 / 1e12, 2),
                         "frac_of_2x_bf16_peak": round(ops8 / tc8 / 1e12 / (2 * pk["bf16"]), 4),
-                        "frac_of_i8_mma_peak": round(ops8 / tc8 / 1e12 / I8_MMA_PEAK_TOPS, 4)}
+                        "frac_of_i8_mma_peak": round(ops8 / tc8 / 1e12 / I8_MMA_PEAK_TOPS, 4),
+                        "frac_of_i8_gemm_sustained_peak": (round(ops8 / tc8 / 1e12 / i8_gemm_peak(), 4) if i8_gemm_peak() else None)}
 
             eng8, bb8 = build_engine(dev, P, 8, 8, False)
             dyn = time_engine(eng8)
@@ -551,8 +561,9 @@ def run_ours(args):
             sta["fused_requantised_layers"] = int(sum(L.fused_q for L in eng8s.layers))
             int8_leg = {"mode": "QConvNd(w_bits=8, act_bits=8, cw=False): W8A8 per-tensor, INT32 accumulate (tcgen05 kind::i8)",
                         "dynamic_amax": dyn, "static_calibration": sta,
-                        "note": "INT8 peak is not in MEASURED_PEAKS.json; fractions against 2x the measured bf16 (cuBLAS) peak and against the "
-                                "measured tcgen05 kind::i8 issue ceiling (4596 TOPS, profiles/r01_mma_peak_microbench.txt). "
+                        "note": "INT8 peak is not in MEASURED_PEAKS.json; fractions against 2x the measured bf16 (cuBLAS) peak, against the "
+                                "measured tcgen05 kind::i8 issue ceiling (4596 TOPS, profiles/r02_mma_peak_microbench.txt) and against the SUSTAINED "
+                                "dense 8192^3 INT8 GEMM of this pool's B200 (2478 TOPS; burst 2968; profiles/r02_int8_gemm_peak.json). "
                                 "static = collect_stats/compute_amax on one batch, int8 codes written by the producing layer's epilogue"}
         except Exception as e:                                     # the headline line must not depend on the extra leg
             int8_leg = {"error": repr(e)[:200]}
