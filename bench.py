@@ -391,31 +391,48 @@ def run_ours(args):
             drained[j & 1].record(copy_stream)
         return n_j * c_enc * 2 + n_j * idx_cols * 4
 
-    e_start.record(main)
-    h2d(0)
     d2h_bytes = 0
-    for i in range(e2e_steps):
-        if i + 1 < e2e_steps:
-            h2d(i + 1)                                         # overlaps this step's compute
-        main.wait_event(copied[i & 1])
-        bd = plugin_step(stage_in[i & 1])
-        consumed[i & 1].record(main)
-        enc = bd["encoded_spconv_tensor"]
-        main.wait_event(drained[i & 1])                        # the side buffers of two steps ago have reached the host
-        out_feats[i & 1][:rows_ub].copy_(enc.capacity_features[:rows_ub], non_blocking=True)
-        src_idx = enc.capacity_indices[:rows_ub]
-        out_idx[i & 1][:rows_ub].copy_(src_idx if enc._index_cols is None else src_idx[:, enc._index_cols], non_blocking=True)
-        produced[i & 1].record(main)
-        pending[i & 1] = enc
-        if i > 0:
-            d2h_bytes = drain(i - 1)
-    d2h_bytes = drain(e2e_steps - 1)
-    copy_stream.synchronize()
-    e_end.record(main)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e2e_ms = torch.tensor([e_start.elapsed_time(e_end)], device=dev)
+    enc = None
+    def e2e_pass():
+        nonlocal d2h_bytes, enc
+        e_start.record(main)
+        h2d(0)
+        d2h_bytes = 0
+        for i in range(e2e_steps):
+            if i + 1 < e2e_steps:
+                h2d(i + 1)                                         # overlaps this step's compute
+            main.wait_event(copied[i & 1])
+            bd = plugin_step(stage_in[i & 1])
+            consumed[i & 1].record(main)
+            enc = bd["encoded_spconv_tensor"]
+            main.wait_event(drained[i & 1])                        # the side buffers of two steps ago have reached the host
+            out_feats[i & 1][:rows_ub].copy_(enc.capacity_features[:rows_ub], non_blocking=True)
+            src_idx = enc.capacity_indices[:rows_ub]
+            out_idx[i & 1][:rows_ub].copy_(src_idx if enc._index_cols is None else src_idx[:, enc._index_cols], non_blocking=True)
+            produced[i & 1].record(main)
+            pending[i & 1] = enc
+            if i > 0:
+                d2h_bytes = drain(i - 1)
+        d2h_bytes = drain(e2e_steps - 1)
+        copy_stream.synchronize()
+        e_end.record(main)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return e_start.elapsed_time(e_end)
+
+    # three passes of K steps each (every pass: barrier, K pipelined steps with their H2D and D2H, drain, sync); the MEDIAN pass is
+    # reported -- one 60 ms pass is at the mercy of a single host hiccup now that the host only has to stay ahead of the GPU
+    e2e_passes = []
+    for _ in range(3):
+        for e in consumed + drained:
+            e.record(main)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e2e_passes.append(e2e_pass())
+    e2e_passes.sort()
+    e2e_ms = torch.tensor([e2e_passes[1]], device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * BATCH * e2e_steps / (float(e2e_ms.item()) / 1e3)
@@ -587,6 +604,7 @@ def run_ours(args):
                    "parallelism": f"frame-sharded x{world} (no data-path collective)"},
         "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": int(pts_np.nbytes),
                 "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": round(float(e2e_ms.item()) / e2e_steps, 4),
+                "ms_per_step_of_the_three_passes": [round(v / e2e_steps, 4) for v in e2e_passes],
                 "note": "pinned host points -> H2D (copy stream, double buffered) -> VoxelizeMeanVFE(batch_dict) -> backbone(batch_dict) [engine_lazy_counts: no count read-back inside the call]"
                         + (" -> HeightCompression(batch_dict)" if has_bev else "") + " -> D2H of the encoded sparse tensor (fp16 rows + int32 indices)"},
         "gpu_launches": int(kernels_per_step * args.steps),
