@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "qlidar", "libqlidar_b200.so")
-SOURCES = ["voxelize.cu", "rulebook.cu", "spconv_mma.cu", "elementwise.cu", "bev.cu", "smoothquant.cu", "centerhead.cu"]
+SOURCES = ["voxelize.cu", "rulebook.cu", "spconv_mma.cu", "spconv_warp.cu", "elementwise.cu", "bev.cu", "smoothquant.cu", "centerhead.cu"]
 HEADERS = ["ql_common.cuh", "ql_scan.cuh", os.path.join("..", "..", "include", "qlidar.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -36,6 +36,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+int ql_spconv_warp_try(const void* feats, int32_t in_dtype, const int32_t* nbr, const uint32_t* tile_kmask, const int32_t* row_perm,
+                       int64_t n_out_cap, const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t kvol, const void* w_packed,
+                       const float* scale, const float* shift, const float* act_scale_dev, const void* residual_f16, int32_t relu,
+                       void* out, int32_t out_dtype, int8_t* out_q, const float* out_qscale, float* absmax, cudaStream_t st);   // spconv_warp.cu
+
 namespace {
 
 constexpr int kMaxTeams = 4;
@@ -974,6 +979,12 @@ extern "C" int ql_spconv_mma_rows(const void* feats, int32_t in_dtype, const int
     if (c_in <= 0 || (c_in * es) % 16 != 0 || c_out < 16 || c_out % 16 != 0 || c_out > 256 || kvol <= 0 || kvol > 32 * kMaskWords)
         return QL_ERR_UNSUPPORTED;
     if (n_out_cap <= 0) return QL_OK;
+    {
+        // narrow layers (rows <= 64 bytes): the register-gather kernel of spconv_warp.cu
+        const int r = ql_spconv_warp_try(feats, in_dtype, nbr, tile_kmask, row_perm, n_out_cap, n_out_dev, c_in, c_out, kvol, w_packed, scale, shift,
+                                         act_scale_dev, residual_f16, relu, out, out_dtype, out_q, out_qscale, absmax, st);
+        if (r != 1) return r;
+    }
 
     ConvParams p;
     memset(&p, 0, sizeof(p));

@@ -623,8 +623,10 @@ class BackboneEngine:
         if P > self.max_points:
             raise QlidarError("more points than max_points")
         self.points[:P].copy_(points, non_blocking=True)
-        if P < self.max_points:
-            self.points[P:, 1:4] = 1e30
+        prev = getattr(self, "_points_valid", self.max_points)      # rows >= prev are parked already (the buffer starts out parked)
+        if P < prev:
+            self.points[P:prev, 1:4] = 1e30
+        self._points_valid = P
 
     def forward_points(self, points: Optional[torch.Tensor] = None):
         if points is not None:
