@@ -130,19 +130,26 @@ __global__ void __launch_bounds__(256) k_quantize_rows_h8(const __half* __restri
     float* s_scale = s_par;
     float* s_smooth = s_par + c;
     const int64_t n = n_dev ? min((int64_t)*n_dev, (int64_t)n_cap) : n_cap;
-    __shared__ float s_tensor_amax;
-    if (threadIdx.x == 0) {
+    // per-tensor amax = max over the channels, taken by the whole block (one thread walking c dependent global loads cost every
+    // CTA of the C = 128 launches ~10 us before its first row)
+    __shared__ unsigned int s_tensor_amax_u;
+    if (threadIdx.x == 0) s_tensor_amax_u = 0u;
+    __syncthreads();
+    {
         float m = 0.f;
-        if (mode == QL_Q_CODES_PER_TENSOR || mode == QL_Q_FAKE_PER_TENSOR)
-            for (int j = 0; j < c; ++j) m = fmaxf(m, smooth ? __fdiv_rn(absmax[j], smooth[j]) : absmax[j]);
-        s_tensor_amax = m;
+        for (int j = threadIdx.x; j < c; j += blockDim.x) {
+            const float am = smooth ? __fdiv_rn(absmax[j], smooth[j]) : absmax[j];
+            s_scale[j] = am;                                   // parked: turned into the scale below
+            s_smooth[j] = smooth ? smooth[j] : 1.0f;
+            m = fmaxf(m, am);
+        }
+        const unsigned int mu = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(m, 0.f)));   // non-negative floats order like their bits
+        if ((threadIdx.x & 31) == 0 && mu) atomicMax(&s_tensor_amax_u, mu);
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < c; j += blockDim.x) {
-        float am = (mode == QL_Q_FAKE_PER_CHANNEL) ? (smooth ? __fdiv_rn(absmax[j], smooth[j]) : absmax[j]) : s_tensor_amax;
-        s_scale[j] = quant_scale_of(am, bound);
-        s_smooth[j] = smooth ? smooth[j] : 1.0f;
-    }
+    const float s_tensor_amax = (mode == QL_Q_CODES_PER_TENSOR || mode == QL_Q_FAKE_PER_TENSOR) ? __uint_as_float(s_tensor_amax_u) : 0.f;
+    for (int j = threadIdx.x; j < c; j += blockDim.x)
+        s_scale[j] = quant_scale_of(mode == QL_Q_FAKE_PER_CHANNEL ? s_scale[j] : s_tensor_amax, bound);
     if (blockIdx.x == 0 && threadIdx.x == 0 && act_scale_out) act_scale_out[0] = __fdiv_rn(s_tensor_amax, bound);
     __syncthreads();
     const int groups = c >> 3;

@@ -380,9 +380,10 @@ int ql_spconv_warp_try(const void* feats, int32_t in_dtype, const int32_t* nbr, 
                        int64_t n_out_cap, const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t kvol, const void* w_packed,
                        const float* scale, const float* shift, const float* act_scale_dev, const void* residual_f16, int32_t relu,
                        void* out, int32_t out_dtype, int8_t* out_q, const float* out_qscale, float* absmax, cudaStream_t st) {
-    // tuning override, read per call so that one process can A/B: 0 = never, 1 = default, 2 = also 64-byte rows x 64 outputs
+    // OPT-IN (read per call so that one process can A/B): 0 / unset = never -- on the B200 the tcgen05 kernel is 2x faster on every
+    // layer of the bench (profiles/r02_warp_kernel_ab.md) --, 1 = narrow layers, 2 = also 64-byte rows x 64 outputs
     const char* mode_s = getenv("QL_SPCONV_WARP");
-    const int mode = (mode_s && *mode_s) ? atoi(mode_s) : 1;
+    const int mode = (mode_s && *mode_s) ? atoi(mode_s) : 0;
     if (mode == 0) return 1;
     const bool i8 = in_dtype == QL_S8;
     const int rb = c_in * (i8 ? 1 : 2);

@@ -490,6 +490,64 @@ def test_spconv_epilogue_fusion(ops):
     assert dq.max().item() <= 1 and (dq > 0).double().mean().item() < 0.02   # only rounding-boundary flips
 
 
+@pytest.mark.parametrize("cin,cout,int8", [(16, 16, False), (32, 32, False), (16, 32, False), (32, 64, False), (16, 16, True),
+                                            (16, 32, True), (32, 32, True), (64, 32, True)])
+def test_spconv_register_gather_kernel_equals_the_tcgen05_kernel(ops, monkeypatch, cin, cout, int8):
+    """csrc/spconv_warp.cu (mma.sync, one warp per 16 rows; opt-in through QL_SPCONV_WARP, profiles/r02_warp_kernel_ab.md) against
+    k_spconv_ts on the same compact rulebook, full epilogue: INT32 accumulators / int8 paths bit-identical, fp16 within the fp32
+    summation-order bound."""
+    rng = np.random.default_rng(70 + cin + cout)
+    S = 60
+    coords_np = O.synth_surface_sheet(S, seed=71, depth=12)
+    N = coords_np.shape[0]
+    coords = torch.from_numpy(coords_np).cuda()
+    grid = (1, 12, S, S)
+    table = ops.hash_build(coords, None, grid)
+    nbr, kmask = ops.rulebook_subm(coords, None, grid, 3, table, with_mask=True)
+    n_live = N - 37
+    n_dev = torch.tensor([n_live], dtype=torch.int32, device="cuda")
+    if int8:
+        x = torch.from_numpy(rng.integers(-127, 128, size=(N, cin)).astype(np.int8)).cuda()
+        w = torch.from_numpy(rng.integers(-127, 128, size=(cout, 27, cin)).astype(np.int8))
+    else:
+        x = torch.from_numpy(rng.normal(size=(N, cin)).astype(np.float32)).half().cuda()
+        w = torch.from_numpy(rng.integers(-127, 128, size=(cout, 27, cin)).astype(np.float32)).half()
+    wp = ops.pack_weights(w).cuda()
+    scale = torch.from_numpy(rng.uniform(0.5, 1.5, cout).astype(np.float32)).cuda() * 1e-3
+    shift = torch.from_numpy(rng.normal(size=cout).astype(np.float32)).cuda()
+    res = torch.from_numpy(rng.normal(size=(N, cout)).astype(np.float32)).half().cuda()
+    qscale = torch.from_numpy(rng.uniform(20, 40, cout).astype(np.float32)).cuda()
+    act = torch.tensor([0.37], dtype=torch.float32, device="cuda")
+
+    def run(mode, raw):
+        monkeypatch.setenv("QL_SPCONV_WARP", mode)
+        if raw:
+            out = torch.full((N, cout), -777, dtype=torch.int32, device="cuda")
+            ops.spconv_mma(x, nbr, N, n_dev, cout, wp, torch.ones_like(scale), torch.zeros_like(shift), out=out, kmask=kmask)
+            return (out,)
+        out = torch.zeros((N, cout), dtype=torch.float16, device="cuda")
+        out_q = torch.zeros((N, cout), dtype=torch.int8, device="cuda")
+        absmax = torch.zeros(cout, dtype=torch.float32, device="cuda")
+        ops.spconv_mma(x, nbr, N, n_dev, cout, wp, scale, shift, act_scale=act, residual=res, relu=True, out=out, out_q=out_q,
+                       out_qscale=qscale, absmax=absmax, kmask=kmask)
+        return out, out_q, absmax
+
+    if int8:
+        a, = run("0", True)
+        b, = run("2", True)
+        assert torch.equal(a, b)
+        for ta, tb in zip(run("0", False), run("2", False)):
+            assert torch.equal(ta, tb)
+    else:
+        a, aq, am = run("0", False)
+        b, bq, bm = run("2", False)
+        tol = 1e-3 * a.float().abs().max().item()
+        assert (a.float() - b.float()).abs().max().item() <= tol
+        assert (a[n_live:] == 0).all() and (b[n_live:] == 0).all()
+        assert (aq.int() - bq.int()).abs().max().item() <= 1
+        np.testing.assert_allclose(am.cpu().numpy(), bm.cpu().numpy(), rtol=1e-3)
+
+
 def test_stem_conv(ops):
     rng = np.random.default_rng(40)
     coords, nbr = _conv_case(rng, 3000, 5, 16)
