@@ -592,6 +592,13 @@ def run_ours(args):
         except Exception as e:
             head_post = {"error": repr(e)[:200]}
 
+    bev2d = None
+    if args.config == 2:
+        try:
+            bev2d = bev_backbone_leg(dev)
+        except Exception as e:
+            bev2d = {"error": repr(e)[:200]}
+
     # ---- CPU baseline beside it: the oracle port on a bounded sample of the same workload ----
     cpu = cpu_baseline(pts_np, budget_s=12.0)
 
@@ -619,6 +626,7 @@ def run_ours(args):
         "conv_layers": per_layer,
         "int8": int8_leg,
         "head_post": head_post,
+        "bev_backbone_int8": bev2d,
         "step_ms_p10_p50_p90": [round(float(np.percentile(step_ms, q)), 4) for q in (10, 50, 90)],
     }
     if gathered is not None:
@@ -661,6 +669,49 @@ def head_post_leg(dev, batch=4, hw=188, classes=3, iters=30):
                     "the host-side launch overhead of its 4 kernels + output allocations (eager, no graph)",
             "us_per_call_median": round(us[len(us) // 2], 1), "us_per_call_min": round(us[0], 1),
             "candidates_kept_per_frame": [int(v) for v in out[0]["keep_count"].cpu().tolist()], "kernel_launches": 4}
+
+
+def bev_backbone_leg(dev, batch=4, hw=188, iters=5):
+    """SURVEY 8(f) rank 2, timed beside the headline: BaseBEVBackbone at the Waymo CenterPoint shape (cfgs/waymo_models/centerpoint.yaml
+    BACKBONE_2D: 256 -> [128 x 6 convs, 256 x 6 convs, stride 2], de-blocks to 2 x 256) on a 4 x 256 x 188 x 188 map, after the reference's
+    SmoothQuant surgery (quant_centerpoint.py:96-106: every nn.Conv2d -> SQConv2d W8A8, dynamic per-column smoothing): per conv one unfold +
+    abs-max pass, one smooth + quantise pass, the weight preparation and ONE tcgen05 kind::i8 launch with BN + ReLU in its epilogue."""
+    import qlidar
+    torch.manual_seed(6)
+    m = qlidar.BaseBEVBackbone(dict(LAYER_NUMS=[5, 5], LAYER_STRIDES=[1, 2], NUM_FILTERS=[128, 256], UPSAMPLE_STRIDES=[1, 2],
+                                    NUM_UPSAMPLE_FILTERS=[256, 256]), 256).to(dev).eval()
+    x = torch.relu(torch.randn((batch, 256, hw, hw), device=dev))
+    x[:, 7] *= 12.0
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for a, b in ev:
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        t = sorted(a.elapsed_time(b) for a, b in ev)
+        return t[len(t) // 2]
+
+    with torch.no_grad():
+        ms_fp32 = timed(lambda: m({"spatial_features": x}))
+        y32 = m({"spatial_features": x})["spatial_features_2d"]
+        qlidar.smoothquant(m, {}, "", 0.5, 8, 8, (torch.nn.Conv2d), qlidar.SQConv2d, [])
+        ms_i8 = timed(lambda: m({"spatial_features": x}))
+        y8 = m({"spatial_features": x})["spatial_features_2d"]
+    macs = 0
+    h = hw
+    for lvl, (n, s_, c_in, c_out) in enumerate([(5, 1, 256, 128), (5, 2, 128, 256)]):
+        h = h // s_
+        macs += batch * h * h * 9 * (c_in * c_out + n * c_out * c_out)
+    return {"what": "BaseBEVBackbone(256 -> 128 x 6, 256 x 6; de-blocks 2 x 256) on 4 x 256 x 188 x 188, nn.Conv2d -> SQConv2d (W8A8 SmoothQuant, "
+                    "dynamic), BN + ReLU in the int8 GEMM's epilogue; ConvTranspose2d de-blocks fp32 (cuDNN) as in the reference's surgery",
+            "ms_per_call_int8": round(ms_i8, 3), "ms_per_call_fp32_torch_cudnn": round(ms_fp32, 3),
+            "conv_tops_alg_int8": round(2 * macs / (ms_i8 * 1e-3) / 1e12, 1),
+            "rel_diff_int8_vs_fp32": round(float((y8 - y32).abs().max() / y32.abs().max()), 4), "sq_layers": 12}
 
 
 def oracle_runner():

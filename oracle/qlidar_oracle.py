@@ -1017,6 +1017,44 @@ def sq_conv2d(x, weight, bias, alpha, stride=1, padding=0, dilation=1):
     return y if bias is None else y + bias.view(1, oc, 1, 1)
 
 
+
+def base_bev_backbone(x, params, cfg, alpha=None, no_list=()):
+    """pcdet/models/backbones_2d/base_bev_backbone.py:26-113 (eval mode) with the surgery of quant/quant_centerpoint.py:96-106
+    applied when `alpha` is given: every nn.Conv2d whose dotted path is not in no_list runs as quant/smoothquant.py SQConv2d
+    (sq_conv2d above); ConvTranspose2d layers stay fp32.  params: the module's state dict (torch tensors), cfg: dict with
+    LAYER_NUMS / LAYER_STRIDES / NUM_FILTERS / UPSAMPLE_STRIDES / NUM_UPSAMPLE_FILTERS."""
+    def bn_relu(y, pre):
+        a = params[pre + ".weight"] / torch.sqrt(params[pre + ".running_var"] + 1e-3)
+        b = params[pre + ".bias"] - a * params[pre + ".running_mean"]
+        return torch.relu(y * a.view(1, -1, 1, 1) + b.view(1, -1, 1, 1))
+
+    def conv(y, path, stride, pad):
+        w = params[path + ".weight"]
+        if alpha is not None and path not in no_list:
+            return sq_conv2d(y, w, None, alpha, stride, pad)
+        return F.conv2d(y, w, None, stride, pad)
+
+    ups = []
+    n_up = len(cfg.get("UPSAMPLE_STRIDES") or [])
+    for lvl, (n_layers, stride) in enumerate(zip(cfg["LAYER_NUMS"], cfg["LAYER_STRIDES"])):
+        pre = "blocks.%d." % lvl
+        x = bn_relu(conv(F.pad(x, (1, 1, 1, 1)), pre + "1", stride, 0), pre + "2")         # ZeroPad2d(1) + conv(padding=0)
+        for k in range(n_layers):
+            x = bn_relu(conv(x, pre + str(4 + 3 * k), 1, 1), pre + str(5 + 3 * k))
+        if n_up:
+            us = cfg["UPSAMPLE_STRIDES"][lvl]
+            dpre = "deblocks.%d." % lvl
+            if us >= 1:
+                u = F.conv_transpose2d(x, params[dpre + "0.weight"], None, stride=us)
+            else:
+                ds = int(round(1 / us))
+                u = conv(x, dpre + "0", ds, 0)
+            ups.append(bn_relu(u, dpre + "1"))
+        else:
+            ups.append(x)
+    return torch.cat(ups, dim=1) if len(ups) > 1 else ups[0]
+
+
 def sq_conv1d(x, weight, bias, alpha, stride=1, padding=0, dilation=1):
     """quant/smoothquant.py:133-176.  x (B, C, L), weight (oc, ic, k)."""
     oc, ic, k = weight.shape

@@ -59,7 +59,8 @@ def _identity_rulebook(m: int, dev) -> torch.Tensor:
 
 
 def _int8_gemm(codes: torch.Tensor, act_scale: torch.Tensor, w_rows: torch.Tensor, act_absmax_cols: torch.Tensor, alpha: float,
-               bias: Optional[torch.Tensor], smooth: torch.Tensor, out_dtype) -> torch.Tensor:
+               bias: Optional[torch.Tensor], smooth: torch.Tensor, out_dtype, post_a: Optional[torch.Tensor] = None,
+               post_b: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
     """codes [M, Kp] int8 (already smoothed + quantised with `smooth`), w_rows [N, Kp] fp32 (columns padded like the codes):
     returns [M, N] = dequantised product with the smoothed, per-row (output channel) quantised weights.  N is cut into blocks of
     256 output channels (the kernel's widest accumulator)."""
@@ -80,7 +81,15 @@ def _int8_gemm(codes: torch.Tensor, act_scale: torch.Tensor, w_rows: torch.Tenso
         shift = torch.zeros(nb_p, dtype=torch.float32, device=dev)
         if bias is not None:
             shift[:nb] = bias[n0:n0 + nb].float()
-        y = ops.spconv_mma(codes, nbr, M, None, nb_p, packed, scale, shift, act_scale=act_scale, out_dtype=out_dtype)
+        if post_a is not None:
+            # an affine per-output-channel op that follows the layer (eval BatchNorm: a * y + b) rides in the kernel's one FMA:
+            # a * (acc * s + bias) + b = acc * (s * a) + (a * bias + b)
+            a = torch.ones(nb_p, dtype=torch.float32, device=dev)
+            a[:nb] = post_a[n0:n0 + nb].float()
+            scale = scale * a
+            shift = shift * a
+            shift[:nb] += post_b[n0:n0 + nb].float()
+        y = ops.spconv_mma(codes, nbr, M, None, nb_p, packed, scale, shift, act_scale=act_scale, out_dtype=out_dtype, relu=relu)
         outs.append(y[:, :nb])
     return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
 
@@ -101,7 +110,7 @@ class _SQDense(nn.Module):
         if self.scaling_factor is None:
             raise ValueError("Please specify the scaling_factor parameter!")
 
-    def _conv_rows(self, x: torch.Tensor, w2d: torch.Tensor, kernel, stride, pad, dil, bias) -> torch.Tensor:
+    def _conv_rows(self, x: torch.Tensor, w2d: torch.Tensor, kernel, stride, pad, dil, bias, post_a=None, post_b=None, relu=False) -> torch.Tensor:
         if not x.is_cuda:
             raise ops.QlidarError("qlidar SmoothQuant wrappers run on CUDA tensors (there is no CPU fallback)")
         x = x.contiguous()
@@ -128,7 +137,7 @@ class _SQDense(nn.Module):
         ops.check(lib().ql_unfold_quantize(ops._ptr(x), ops._DT[x.dtype], B, C, H, W, i32(kernel), i32(stride), i32(pad), i32(dil), ops._ptr(absmax),
                                            ops._ptr(smooth), _bits(self._input_quantizer), kp, ops._ptr(codes), ops._ptr(scales), ops._stream()),
                   "ql_unfold_quantize")
-        y = _int8_gemm(codes, scales[1:2], w_rows, absmax, float(self.scaling_factor), bias, smooth, torch.float32)
+        y = _int8_gemm(codes, scales[1:2], w_rows, absmax, float(self.scaling_factor), bias, smooth, torch.float32, post_a, post_b, relu)
         return y, (B, Ho, Wo)
 
 
@@ -147,10 +156,17 @@ class SQConv2d(_SQDense):
         self.bias = nn.Parameter(torch.empty(out_channels, device=device))
 
     def forward(self, x):
+        return self.forward_fused(x)
+
+    def forward_fused(self, x, extra_pad: int = 0, post_a=None, post_b=None, relu: bool = False):
+        """forward() with what surrounds the layer in BaseBEVBackbone's blocks folded in: a ZeroPad2d in front (`extra_pad`, added to
+        the unfold's padding: zero columns either way), an eval-mode BatchNorm2d behind it (y * post_a + post_b per output channel) and
+        a ReLU, both in the conv kernel's epilogue."""
         self._check()
-        k, s, p, d = _one(self.kernel_size), _one(self.stride), _one(self.padding), _one(self.dilation)
+        k, s, p, d = _one(self.kernel_size), _one(self.stride), _one(self.padding) + int(extra_pad), _one(self.dilation)
         w2d = self.weight.detach().reshape(self.out_channels, -1)
-        y, (B, Ho, Wo) = self._conv_rows(x, w2d, (k, k), (s, s), (p, p), (d, d), None if self.bias is None else self.bias.detach())
+        y, (B, Ho, Wo) = self._conv_rows(x, w2d, (k, k), (s, s), (p, p), (d, d), None if self.bias is None else self.bias.detach(),
+                                         post_a, post_b, relu)
         return y.view(B, Ho * Wo, self.out_channels).permute(0, 2, 1).reshape(B, self.out_channels, Ho, Wo).to(x.dtype)
 
 
