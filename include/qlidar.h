@@ -336,6 +336,29 @@ int ql_centerhead_decode(const float* hm, const float* center, const float* cent
                          float* out_scores, int32_t* out_labels, float* out_iou, int32_t* out_count, void* workspace,
                          size_t workspace_bytes, ql_stream_t stream);
 
+/* ---- VoxelNeXt sparse head post-processing (replaces VoxelNeXtHead.generate_predicted_boxes,
+ *      pcdet/models/dense_heads/voxelnext_head.py:418-488 -> centernet_utils._topk_1d / gather_feat_idx /
+ *      decode_bbox_from_voxels_nuscenes (model_utils/centernet_utils.py:243-354) and rotate_class_specific_nms_iou (:308-331)).
+ *
+ *  ql_voxelhead_decode: ql_centerhead_decode over a SPARSE head: per-voxel row-major fp32 arrays hm [N,C] logits, center [N,2],
+ *      center_z [N,1], dim [N,3] log sizes, rot [N,2] (cos, sin), vel [N,2] / NULL, iou [N,1] / NULL (raw head output: (iou+1)/2
+ *      clamped to [0,1] is applied here), indices_byx int32 [N,3] = the 2-D sparse tensor's (batch, y, x), n_dev = device row count
+ *      or NULL (= n_cap).  Per frame: top-K over its (voxel, class) scores, decode, range / score mask.  Outputs as
+ *      ql_centerhead_decode.
+ *  ql_voxelhead_class_split: the IoU-branch re-scoring: per (class, frame) the frame's decoded boxes of that class with score
+ *      score^(1-r[c]) * iou^(r[c]), sorted by it; out_* are [num_class, B, K(, box_dim)], out_counts [num_class, B] -- one
+ *      ql_nms_rotated call per class (its own threshold / pre / post sizes) finishes rotate_class_specific_nms_iou. */
+size_t ql_voxelhead_decode_workspace_bytes(int32_t B, int32_t C, int64_t n_cap);
+int ql_voxelhead_decode(const float* hm, const float* center, const float* center_z, const float* dim, const float* rot,
+                        const float* vel, const float* iou, const int32_t* indices_byx, int64_t n_cap, const int32_t* n_dev,
+                        int32_t B, int32_t C, int32_t K, float feature_map_stride, const float* voxel_size_xy,
+                        const float* pc_min_xy, const float* center_limit_range, float score_thresh, const int32_t* class_map,
+                        float* out_boxes, float* out_scores, int32_t* out_labels, float* out_iou, int32_t* out_count,
+                        void* workspace, size_t workspace_bytes, ql_stream_t stream);
+int ql_voxelhead_class_split(const float* boxes, int32_t box_dim, const float* scores, const int32_t* labels, const float* ious,
+                             const int32_t* counts, int32_t B, int32_t K, int32_t num_class, const float* rectifier_dev,
+                             float* out_boxes, float* out_scores, int32_t* out_labels, int32_t* out_counts, ql_stream_t stream);
+
 /*  ql_nms_rotated: greedy rotated-BEV-IoU NMS per frame.  boxes [B, n_cap, box_stride] fp32, each frame's first counts[b] rows
  *      (device int32 [B]; NULL = n_cap) valid and ALREADY in descending score order (ql_centerhead_decode's order; nms_gpu sorts
  *      first, iou3d_nms_utils.py:127-131).  The first min(count, pre_max) boxes take part (NMS_PRE_MAXSIZE); a box is suppressed

@@ -1239,6 +1239,96 @@ def centerhead_generate_predicted_boxes(pred_dicts, class_id_mapping_each_head, 
 
 
 # ----------------------------------------------------------------------------------------------
+# VoxelNeXt sparse head: per-voxel head outputs -> boxes.
+# ----------------------------------------------------------------------------------------------
+def voxelhead_decode(hm, center, center_z, dim, rot, vel, iou, indices, batch_size, K, feature_map_stride, voxel_size,
+                     point_cloud_range, post_center_limit_range, score_thresh, class_map=None):
+    """VoxelNeXtHead.generate_predicted_boxes up to the NMS (voxelnext_head.py:418-456) -> decode_bbox_from_voxels_nuscenes
+    (centernet_utils.py:289-354) with _topk_1d's `nuscenes=True` branch (:243-276: per class top-K over the frame's voxels, then top-K
+    of the C*K survivors; ties to the lower index) and gather_feat_idx (:278-287).  Inputs are the RAW per-voxel head outputs, numpy
+    fp32: hm [N, C] logits, center [N, 2], center_z [N, 1], dim [N, 3] log-sizes, rot [N, 2] = (cos, sin), vel [N, 2] / None, iou
+    [N, 1] / None (raw: (iou + 1) / 2 clamped to [0, 1] here), indices [N, 3] = (batch, y, x).  Frames with fewer than K voxels take
+    min(K, .) at both levels (the reference's torch.stack would raise on ragged frames; its `topk_ind // K` class rule is kept for full
+    frames and restated as `// K1` otherwise).  Returns a list per frame of dicts pred_boxes / pred_scores / pred_labels [/ pred_iou]."""
+    f32 = np.float32
+    hm = sigmoid32(hm)
+    dim = np.exp(np.asarray(dim, f32), dtype=f32)
+    indices = np.asarray(indices)
+    lim = np.asarray(post_center_limit_range, f32)
+    out = []
+    for b in range(batch_size):
+        rows = np.nonzero(indices[:, 0] == b)[0]
+        sc = hm[rows].T                                                                 # (C, Nb)
+        C, Nb = sc.shape
+        K1 = min(K, Nb)
+        o1 = np.argsort(-sc, axis=1, kind="stable")[:, :K1]
+        s1 = np.take_along_axis(sc, o1, axis=1).reshape(-1)
+        o2 = np.argsort(-s1, kind="stable")[:min(K, s1.shape[0])]
+        score = s1[o2]
+        cls = (o2 // max(K1, 1)).astype(np.int32)
+        r = rows[o1.reshape(-1)[o2]]
+        ctr, cz, dm, rt = np.asarray(center, f32)[r], np.asarray(center_z, f32)[r], dim[r], np.asarray(rot, f32)[r]
+        angle = np.arctan2(rt[:, 1:2], rt[:, 0:1]).astype(f32)
+        xs = (indices[r, 2:3].astype(f32) + ctr[:, 0:1]).astype(f32)
+        ys = (indices[r, 1:2].astype(f32) + ctr[:, 1:2]).astype(f32)
+        xs = ((xs * f32(feature_map_stride)).astype(f32) * f32(voxel_size[0])).astype(f32) + f32(point_cloud_range[0])
+        ys = ((ys * f32(feature_map_stride)).astype(f32) * f32(voxel_size[1])).astype(f32) + f32(point_cloud_range[1])
+        parts = [xs.astype(f32), ys.astype(f32), cz, dm, angle]
+        if vel is not None:
+            parts.append(np.asarray(vel, f32)[r])
+        boxes = np.concatenate(parts, axis=-1).astype(f32)
+        mask = (boxes[:, :3] >= lim[:3]).all(1) & (boxes[:, :3] <= lim[3:]).all(1)
+        if score_thresh is not None:
+            mask &= score > f32(score_thresh)
+        lab = cls[mask]
+        if class_map is not None:
+            lab = np.asarray(class_map)[lab]
+        d = {"pred_boxes": boxes[mask], "pred_scores": score[mask], "pred_labels": lab.astype(np.int32)}
+        if iou is not None:
+            pi = ((np.asarray(iou, f32)[r, 0] + f32(1.0)) * f32(0.5)).astype(f32)
+            d["pred_iou"] = np.clip(pi, f32(0.0), f32(1.0))[mask]
+        out.append(d)
+    return out
+
+
+def voxelhead_generate_predicted_boxes(pred_dicts, indices, batch_size, class_id_mapping_each_head, K, feature_map_stride, voxel_size,
+                                       point_cloud_range, post_center_limit_range, score_thresh, nms_thresh, nms_pre, nms_post,
+                                       iou_branch=False, rectifier=None, num_class=None, use_vel=False):
+    """VoxelNeXtHead.generate_predicted_boxes (voxelnext_head.py:418-488).  Without the IoU branch: class-agnostic NMS per head
+    (scalar nms_thresh / pre / post).  With it: the heads' boxes are concatenated per frame and rotate_class_specific_nms_iou (:308-331)
+    runs one NMS per class on the scores score^(1-r) * iou^r with that class's threshold / pre / post sizes (lists)."""
+    ret = [{"pred_boxes": [], "pred_scores": [], "pred_labels": [], "pred_iou": []} for _ in range(batch_size)]
+    for h, pd in enumerate(pred_dicts):
+        dec = voxelhead_decode(pd["hm"], pd["center"], pd["center_z"], pd["dim"], pd["rot"], pd.get("vel") if use_vel else None,
+                               pd.get("iou") if iou_branch else None, indices, batch_size, K, feature_map_stride, voxel_size,
+                               point_cloud_range, post_center_limit_range, score_thresh, class_map=class_id_mapping_each_head[h])
+        for b, d in enumerate(dec):
+            if not iou_branch:
+                sel = nms_rotated(d["pred_boxes"], d["pred_scores"], nms_thresh, nms_pre, nms_post) if len(d["pred_scores"]) else np.zeros(0, np.int64)
+            else:
+                sel = np.arange(len(d["pred_scores"]))
+                ret[b]["pred_iou"].append(d["pred_iou"])
+            ret[b]["pred_boxes"].append(d["pred_boxes"][sel])
+            ret[b]["pred_scores"].append(d["pred_scores"][sel])
+            ret[b]["pred_labels"].append(d["pred_labels"][sel])
+    out = []
+    for b in range(batch_size):
+        boxes, scores, labels = (np.concatenate(ret[b][k], 0) for k in ("pred_boxes", "pred_scores", "pred_labels"))
+        if iou_branch:
+            ious = np.concatenate(ret[b]["pred_iou"], 0)
+            bl, sl, ll = [], [], []
+            for c in range(num_class):
+                m = labels == c
+                r = np.float32(rectifier[c])
+                sc = (np.power(scores[m], np.float32(1.0) - r, dtype=np.float32) * np.power(ious[m], r, dtype=np.float32)).astype(np.float32)
+                sel = nms_rotated(boxes[m], sc, nms_thresh[c], nms_pre[c], nms_post[c]) if m.any() else np.zeros(0, np.int64)
+                bl.append(boxes[m][sel]); sl.append(sc[sel]); ll.append(labels[m][sel])
+            boxes, scores, labels = np.concatenate(bl, 0), np.concatenate(sl, 0), np.concatenate(ll, 0)
+        out.append({"pred_boxes": boxes, "pred_scores": scores, "pred_labels": labels + 1})
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # Histogram calibration ([EXT] pytorch_quantization calib.HistogramCalibrator, published algorithm; parity UNPINNED: the package is
 # neither in this image nor vendored by the reference -- call sites quant/quantize.py:138-145,198-207, count_time_n_memory.py:304-365).
 # numpy, float64, written independently of qlidar/tensor_quant.py.

@@ -41,6 +41,11 @@ struct HeadMaps {
     float lim[6];
     float score_thresh;     // < 0: no score threshold
     const int* class_map;   // [C] or null: label = class_map[class]
+    // SPARSE head (VoxelNeXtHead): the "maps" are row-major per-voxel arrays hm [N, C], center [N, 2], ... and a voxel's cell is
+    // sp_indices[row] = (b, y, x); a candidate's index is cls * sp_n + row.  Null = the dense NCHW head above.
+    const int* sp_indices;
+    int sp_n;
+    int64_t list_stride;    // candidate-list capacity per frame (C*H*W dense, C*N sparse)
 };
 
 __device__ __forceinline__ float sigmoidf_ref(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }   // torch: 1 / (1 + exp(-x))
@@ -64,6 +69,29 @@ __global__ void __launch_bounds__(256) k_ch_candidates(HeadMaps M, uint2* __rest
     if (pass) cand[(int64_t)b * n + base + __popc(vote & ((1u << lane) - 1u))] = make_uint2(__float_as_uint(s), (uint32_t)i);
 }
 
+// sparse head: one thread per (voxel row, class); the frame comes from the row's batch index
+__global__ void __launch_bounds__(256) k_vh_candidates(HeadMaps M, const int* __restrict__ n_dev, uint2* __restrict__ cand, int* __restrict__ cand_count) {
+    const int n_rows = n_dev ? min(*n_dev, M.sp_n) : M.sp_n;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool pass = false;
+    float s = 0.f;
+    int b = 0, row = 0, cls = 0;
+    if (i < (int64_t)n_rows * M.C) {
+        row = (int)(i / M.C); cls = (int)(i - (int64_t)row * M.C);
+        b = M.sp_indices[3 * row];
+        s = sigmoidf_ref(M.hm[i]);
+        pass = b >= 0 && b < M.B && (M.score_thresh < 0.f || s > M.score_thresh);
+    }
+    if (!pass) return;
+    // lanes of the same frame share one atomic (rows are ordered by frame almost everywhere)
+    const uint32_t peers = __match_any_sync(__activemask(), b);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&cand_count[b], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    cand[(int64_t)b * M.list_stride + base + __popc(peers & ((1u << lane) - 1u))] = make_uint2(__float_as_uint(s), (uint32_t)(cls * M.sp_n + row));
+}
+
 // descending by score bits (scores are positive floats: their bit patterns order like the values), ties by ascending cell index
 __device__ __forceinline__ uint64_t sort_key(uint32_t score_bits, uint32_t idx) { return ((uint64_t)score_bits << 32) | (uint64_t)(~idx); }
 
@@ -75,8 +103,7 @@ __global__ void __launch_bounds__(kSelThreads) k_ch_select_decode(HeadMaps M, co
     __shared__ uint32_t s_prefix, s_mask, s_remaining, s_fill;
     __shared__ int warp_sums[kSelThreads / 32];
     const int b = blockIdx.x, tid = threadIdx.x;
-    const int64_t n_cells = (int64_t)M.C * M.H * M.W;
-    const uint2* list = cand + (int64_t)b * n_cells;
+    const uint2* list = cand + (int64_t)b * M.list_stride;
     const int n = cand_count[b];
     keys[tid] = 0ull;
     if (tid == 0) { s_prefix = 0u; s_mask = 0u; s_remaining = (uint32_t)M.K; s_fill = 0u; }
@@ -146,22 +173,31 @@ __global__ void __launch_bounds__(kSelThreads) k_ch_select_decode(HeadMaps M, co
         const uint64_t k = keys[tid];
         const uint32_t idx = ~(uint32_t)k;
         score = __uint_as_float((uint32_t)(k >> 32));
-        const int hw = M.H * M.W;
-        const int cls = (int)(idx / (uint32_t)hw), cell = (int)(idx % (uint32_t)hw);
-        const int y = cell / M.W, x = cell % M.W;
-        const int64_t f = (int64_t)b * hw;                                  // frame offset in units of one H*W plane
-        const float cx = M.center[(f * 2 + 0 * hw) + cell], cy = M.center[(f * 2 + 1 * hw) + cell];
+        // dense: plane p of a [B, P, H, W] map at (f * P + p * hw) + cell; sparse: column p of a [N, P] array at cell * P + p
+        const bool sp = M.sp_indices != nullptr;
+        const int hw = sp ? 1 : M.H * M.W;
+        const uint32_t per_cls = sp ? (uint32_t)M.sp_n : (uint32_t)hw;
+        const int cls = (int)(idx / per_cls);
+        const int64_t cell = (int64_t)(idx % per_cls);
+        const int y = sp ? M.sp_indices[3 * cell + 1] : (int)(cell / M.W), x = sp ? M.sp_indices[3 * cell + 2] : (int)(cell % M.W);
+        const int64_t f = sp ? 0 : (int64_t)b * hw;                         // frame offset in units of one H*W plane
+        #define QL_HEAD_AT(ptr, P, p) (sp ? (ptr)[cell * (P) + (p)] : (ptr)[(f * (P) + (int64_t)(p) * hw) + cell])
+        const float cx = QL_HEAD_AT(M.center, 2, 0), cy = QL_HEAD_AT(M.center, 2, 1);
         // xs = (x + center_x) * stride * voxel_x + pc_min_x, one fp32 rounding per torch op (centernet_utils.py:188-193)
         box[0] = __fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn((float)x, cx), M.stride), M.vsx), M.pcx);
         box[1] = __fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn((float)y, cy), M.stride), M.vsy), M.pcy);
-        box[2] = M.center_z[f + cell];
+        box[2] = QL_HEAD_AT(M.center_z, 1, 0);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) box[3 + j] = expf(M.dim[(f * 3 + (int64_t)j * hw) + cell]);
-        const float rc = M.rot[(f * 2 + 0 * hw) + cell], rs = M.rot[(f * 2 + 1 * hw) + cell];
+        for (int j = 0; j < 3; ++j) box[3 + j] = expf(QL_HEAD_AT(M.dim, 3, j));
+        const float rc = QL_HEAD_AT(M.rot, 2, 0), rs = QL_HEAD_AT(M.rot, 2, 1);
         box[6] = atan2f(rs, rc);
         box[7] = box[8] = 0.f;
-        if (M.vel) { box[7] = M.vel[(f * 2 + 0 * hw) + cell]; box[8] = M.vel[(f * 2 + 1 * hw) + cell]; }
-        if (M.iou) iou_v = __fmul_rn(__fadd_rn(M.iou[f + cell], 1.0f), 0.5f);
+        if (M.vel) { box[7] = QL_HEAD_AT(M.vel, 2, 0); box[8] = QL_HEAD_AT(M.vel, 2, 1); }
+        if (M.iou) {
+            iou_v = __fmul_rn(__fadd_rn(QL_HEAD_AT(M.iou, 1, 0), 1.0f), 0.5f);
+            if (sp) iou_v = fminf(fmaxf(iou_v, 0.f), 1.f);                  // decode_bbox_from_voxels_nuscenes clamps (centernet_utils.py:324)
+        }
+        #undef QL_HEAD_AT
         label = M.class_map ? M.class_map[cls] : cls;
         keep = box[0] >= M.lim[0] && box[1] >= M.lim[1] && box[2] >= M.lim[2] && box[0] <= M.lim[3] && box[1] <= M.lim[4] && box[2] <= M.lim[5];
         if (M.score_thresh >= 0.f) keep = keep && score > M.score_thresh;
@@ -462,12 +498,110 @@ extern "C" int ql_centerhead_decode(const float* hm, const float* center, const 
     for (int i = 0; i < 6; ++i) M.lim[i] = center_limit_range[i];
     M.score_thresh = score_thresh;
     M.class_map = class_map;
+    M.sp_indices = nullptr; M.sp_n = 0; M.list_stride = (int64_t)C * H * W;
     uint2* cand = (uint2*)workspace;
     int* cand_count = (int*)((char*)workspace + align256((size_t)B * C * H * W * sizeof(uint2)));
     if (cudaMemsetAsync(cand_count, 0, (size_t)B * sizeof(int), st) != cudaSuccess) return QL_ERR_CUDA;
     const int64_t n = (int64_t)C * H * W;
     k_ch_candidates<<<dim3((unsigned)((n + 255) / 256), (unsigned)B), 256, 0, st>>>(M, cand, cand_count);
     k_ch_select_decode<<<(unsigned)B, kSelThreads, 0, st>>>(M, cand, cand_count, vel ? 9 : 7, out_boxes, out_scores, out_labels, out_iou, out_count);
+    QL_CUDA_CHECK_LAST();
+    return QL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- VoxelNeXt sparse head
+extern "C" size_t ql_voxelhead_decode_workspace_bytes(int32_t B, int32_t C, int64_t n_cap) {
+    return align256((size_t)B * C * (size_t)n_cap * sizeof(uint2)) + align256((size_t)B * sizeof(int));
+}
+
+extern "C" int ql_voxelhead_decode(const float* hm, const float* center, const float* center_z, const float* dim, const float* rot, const float* vel,
+                                   const float* iou, const int32_t* indices_byx, int64_t n_cap, const int32_t* n_dev, int32_t B, int32_t C,
+                                   int32_t K, float feature_map_stride, const float* voxel_size_xy, const float* pc_min_xy,
+                                   const float* center_limit_range, float score_thresh, const int32_t* class_map, float* out_boxes,
+                                   float* out_scores, int32_t* out_labels, float* out_iou, int32_t* out_count, void* workspace,
+                                   size_t workspace_bytes, ql_stream_t stream_) {
+    if (!hm || !center || !center_z || !dim || !rot || !indices_byx || !voxel_size_xy || !pc_min_xy || !center_limit_range || !out_boxes ||
+        !out_scores || !out_labels || !out_count || !workspace)
+        return QL_ERR_INVALID;
+    if (B <= 0 || C <= 0 || n_cap < 0 || K <= 0 || K > kSelThreads || (iou && !out_iou)) return QL_ERR_INVALID;
+    if ((double)C * (double)n_cap >= 2147483647.0) return QL_ERR_GRID_TOO_LARGE;
+    if (workspace_bytes < ql_voxelhead_decode_workspace_bytes(B, C, n_cap)) return QL_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream_;
+    HeadMaps M;
+    M.hm = hm; M.center = center; M.center_z = center_z; M.dim = dim; M.rot = rot; M.vel = vel; M.iou = iou;
+    M.B = B; M.C = C; M.H = 1; M.W = 1; M.K = K;
+    M.stride = feature_map_stride; M.vsx = voxel_size_xy[0]; M.vsy = voxel_size_xy[1]; M.pcx = pc_min_xy[0]; M.pcy = pc_min_xy[1];
+    for (int i = 0; i < 6; ++i) M.lim[i] = center_limit_range[i];
+    M.score_thresh = score_thresh;
+    M.class_map = class_map;
+    M.sp_indices = indices_byx; M.sp_n = (int)n_cap; M.list_stride = (int64_t)C * n_cap;
+    uint2* cand = (uint2*)workspace;
+    int* cand_count = (int*)((char*)workspace + align256((size_t)B * C * (size_t)n_cap * sizeof(uint2)));
+    if (cudaMemsetAsync(cand_count, 0, (size_t)B * sizeof(int), st) != cudaSuccess) return QL_ERR_CUDA;
+    const int64_t n = (int64_t)C * n_cap;
+    if (n > 0) k_vh_candidates<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(M, n_dev, cand, cand_count);
+    k_ch_select_decode<<<(unsigned)B, kSelThreads, 0, st>>>(M, cand, cand_count, vel ? 9 : 7, out_boxes, out_scores, out_labels, out_iou, out_count);
+    QL_CUDA_CHECK_LAST();
+    return QL_OK;
+}
+
+namespace {
+// One CTA per (class, frame): the frame's decoded boxes of that class, re-scored score^(1-r) * iou^r and sorted by the new score
+// (descending, ties by position) -- the per-class input of rotate_class_specific_nms_iou (voxelnext_head.py:308-331).
+__global__ void __launch_bounds__(kSelThreads) k_vh_class_split(const float* __restrict__ boxes, int box_dim, const float* __restrict__ scores,
+                                                                 const int* __restrict__ labels, const float* __restrict__ ious,
+                                                                 const int* __restrict__ counts, int K, int B, const float* __restrict__ rectifier,
+                                                                 float* __restrict__ out_boxes, float* __restrict__ out_scores,
+                                                                 int* __restrict__ out_labels, int* __restrict__ out_counts) {
+    __shared__ uint64_t keys[kSelThreads];
+    __shared__ int s_n;
+    const int b = blockIdx.x, cls = blockIdx.y, tid = threadIdx.x;
+    const int n = min(counts[b], K);
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    uint64_t key = 0ull;
+    if (tid < n && labels[(int64_t)b * K + tid] == cls) {
+        const float r = rectifier[cls];
+        const float sc = __fmul_rn(powf(scores[(int64_t)b * K + tid], __fsub_rn(1.0f, r)), powf(ious[(int64_t)b * K + tid], r));
+        key = ((uint64_t)__float_as_uint(fmaxf(sc, 0.f)) << 32) | (uint64_t)(~(uint32_t)tid) | (1ull << 63);   // bit 63: a real entry
+        atomicAdd(&s_n, 1);
+    }
+    keys[tid] = key;
+    __syncthreads();
+    for (int size = 2; size <= kSelThreads; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const int partner = tid ^ stride;
+            if (partner > tid) {
+                const uint64_t a = keys[tid], c = keys[partner];
+                const bool desc = (tid & size) == 0;
+                if (desc ? a < c : a > c) { keys[tid] = c; keys[partner] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    const int m = s_n;
+    const int64_t slot = ((int64_t)cls * B + b) * K;
+    if (tid < m) {
+        const uint64_t k = keys[tid];
+        const int src = (int)(~(uint32_t)k);
+        const float* in = boxes + ((int64_t)b * K + src) * box_dim;
+        float* o = out_boxes + (slot + tid) * box_dim;
+        for (int j = 0; j < box_dim; ++j) o[j] = in[j];
+        out_scores[slot + tid] = __uint_as_float((uint32_t)(k >> 32) & 0x7FFFFFFFu);
+        out_labels[slot + tid] = cls;
+    }
+    if (tid == 0) out_counts[cls * B + b] = m;
+}
+}  // namespace
+
+extern "C" int ql_voxelhead_class_split(const float* boxes, int32_t box_dim, const float* scores, const int32_t* labels, const float* ious,
+                                        const int32_t* counts, int32_t B, int32_t K, int32_t num_class, const float* rectifier_dev,
+                                        float* out_boxes, float* out_scores, int32_t* out_labels, int32_t* out_counts, ql_stream_t stream_) {
+    if (!boxes || !scores || !labels || !ious || !counts || !rectifier_dev || !out_boxes || !out_scores || !out_labels || !out_counts)
+        return QL_ERR_INVALID;
+    if (B <= 0 || K <= 0 || K > kSelThreads || num_class <= 0 || box_dim < 7 || box_dim > kMaxBoxDim) return QL_ERR_INVALID;
+    k_vh_class_split<<<dim3((unsigned)B, (unsigned)num_class), kSelThreads, 0, (cudaStream_t)stream_>>>(
+        boxes, box_dim, scores, labels, ious, counts, K, B, rectifier_dev, out_boxes, out_scores, out_labels, out_counts);
     QL_CUDA_CHECK_LAST();
     return QL_OK;
 }

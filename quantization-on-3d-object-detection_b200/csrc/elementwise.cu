@@ -156,9 +156,20 @@ __global__ void __launch_bounds__(256) k_quantize_rows_h8(const __half* __restri
     const int64_t total = n * groups;
     const bool has_smooth = smooth != nullptr;
     const bool pow2 = (groups & (groups - 1)) == 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // two 16-byte loads in flight per thread (one per half of the grid-stride step): with one, the resident threads of an SM hold
+    // ~32 KB in flight, short of what the HBM latency needs
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * step) {
+      const int64_t i1 = i0 + step;
+      uint4 raw2[2];
+      raw2[0] = *reinterpret_cast<const uint4*>(x + i0 * 8);
+      raw2[1] = i1 < total ? *reinterpret_cast<const uint4*>(x + i1 * 8) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t i = u == 0 ? i0 : i1;
+        if (i >= total) break;
         const int ch0 = (pow2 ? (int)(i & (int64_t)(groups - 1)) : (int)(i % groups)) * 8;
-        const uint4 raw = *reinterpret_cast<const uint4*>(x + i * 8);
+        const uint4 raw = raw2[u];
         const __half2* h = reinterpret_cast<const __half2*>(&raw);
         float v[8];
 #pragma unroll
@@ -192,6 +203,7 @@ __global__ void __launch_bounds__(256) k_quantize_rows_h8(const __half* __restri
             }
             *reinterpret_cast<uint4*>((__half*)out + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
         }
+      }
     }
 }
 

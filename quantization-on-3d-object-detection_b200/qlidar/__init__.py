@@ -14,6 +14,7 @@ from .engine import BackboneEngine
 from . import shard
 from .center_head import CenterHeadPostProcessor
 from .bev_backbone import BaseBEVBackbone
+from .voxelnext_head import VoxelNeXtHead, SeparateHead
 from . import smoothquant as _smoothquant_mod
 from .smoothquant import (SQConv2d, SQConv1d, SQConvT2d, SQLinear, SQSubM2d, SparseSQConv2d, smoothquant_layer, smoothquant)
 

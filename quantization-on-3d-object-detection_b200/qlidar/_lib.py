@@ -66,6 +66,10 @@ SIGNATURES = {
     "ql_centerhead_decode_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ql_centerhead_decode": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, C.c_float, _p, _p, _p, C.c_float, _p,
                                        _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "ql_voxelhead_decode_workspace_bytes": (_sz, [_i32, _i32, _i64]),
+    "ql_voxelhead_decode": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _i32, _i32, _i32, C.c_float, _p, _p, _p, C.c_float, _p,
+                                      _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "ql_voxelhead_class_split": (C.c_int, [_p, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "ql_nms_rotated_workspace_bytes": (_sz, [_i32, _i32]),
     "ql_nms_rotated": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _i32, C.c_float, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }

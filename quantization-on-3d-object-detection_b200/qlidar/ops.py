@@ -580,6 +580,61 @@ def centerhead_decode(hm: torch.Tensor, center: torch.Tensor, center_z: torch.Te
     return boxes, scores, labels, out_iou, count
 
 
+def voxelhead_decode(hm: torch.Tensor, center: torch.Tensor, center_z: torch.Tensor, dim: torch.Tensor, rot: torch.Tensor,
+                     vel: Optional[torch.Tensor], iou: Optional[torch.Tensor], indices_byx: torch.Tensor, n_dev: Optional[torch.Tensor],
+                     batch_size: int, K: int, feature_map_stride, voxel_size, point_cloud_range, post_center_limit_range,
+                     score_thresh: Optional[float], class_map: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
+    """One head of VoxelNeXtHead.generate_predicted_boxes up to (not including) NMS (voxelnext_head.py:418-456 ->
+    centernet_utils.decode_bbox_from_voxels_nuscenes, centernet_utils.py:289-354).  Per-voxel row-major fp32 arrays: `hm` [N, C] LOGITS,
+    `dim` [N, 3] log-sizes, `rot` [N, 2] = (cos, sin), `iou` [N, 1] the raw head output; indices_byx int32 [N, 3] = the sparse tensor's
+    (batch, y, x).  Returns (boxes [B,K,7|9], scores, labels int32 (class_map applied), iou [B,K] or None, count [B])."""
+    arrs = [hm, center, center_z, dim, rot, vel, iou]
+    _need_cuda(*arrs, indices_byx, n_dev, class_map)
+    for t in arrs:
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+            raise QlidarError("voxelhead_decode expects contiguous fp32 per-voxel arrays")
+    if indices_byx.dtype != torch.int32 or indices_byx.dim() != 2 or indices_byx.shape[1] != 3 or not indices_byx.is_contiguous():
+        raise QlidarError("indices must be int32 [N, 3] (batch, y, x)")
+    N, Cn = int(hm.shape[0]), int(hm.shape[1])
+    B = int(batch_size)
+    dev = hm.device
+    bd = 9 if vel is not None else 7
+    boxes = torch.zeros((B, K, bd), dtype=torch.float32, device=dev)
+    scores = torch.zeros((B, K), dtype=torch.float32, device=dev)
+    labels = torch.zeros((B, K), dtype=torch.int32, device=dev)
+    out_iou = torch.zeros((B, K), dtype=torch.float32, device=dev) if iou is not None else None
+    count = torch.zeros((B,), dtype=torch.int32, device=dev)
+    ws_bytes = int(lib().ql_voxelhead_decode_workspace_bytes(B, Cn, N))
+    if workspace is None or workspace.numel() < ws_bytes:
+        workspace = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+    check(lib().ql_voxelhead_decode(_ptr(hm), _ptr(center), _ptr(center_z), _ptr(dim), _ptr(rot), _ptr(vel), _ptr(iou), _ptr(indices_byx), N,
+                                    _ptr(n_dev), B, Cn, int(K), float(feature_map_stride), _host_f32(voxel_size, 2),
+                                    _host_f32(point_cloud_range, 2), _host_f32(post_center_limit_range, 6),
+                                    -1.0 if score_thresh is None else float(score_thresh), _ptr(class_map), _ptr(boxes), _ptr(scores),
+                                    _ptr(labels), _ptr(out_iou), _ptr(count), _ptr(workspace), workspace.numel(), _stream()),
+          "ql_voxelhead_decode")
+    return boxes, scores, labels, out_iou, count
+
+
+def voxelhead_class_split(boxes: torch.Tensor, scores: torch.Tensor, labels: torch.Tensor, ious: torch.Tensor, count: torch.Tensor,
+                          rectifier: torch.Tensor):
+    """The first half of rotate_class_specific_nms_iou (voxelnext_head.py:308-331): per class c the frame's boxes with label c,
+    re-scored score^(1-r[c]) * iou^r[c] and sorted by the new score.  Returns (boxes [C,B,K,bd], scores [C,B,K], labels [C,B,K],
+    counts [C,B])."""
+    _need_cuda(boxes, scores, labels, ious, count, rectifier)
+    B, K, bd = [int(v) for v in boxes.shape]
+    Cn = int(rectifier.numel())
+    dev = boxes.device
+    ob = torch.zeros((Cn, B, K, bd), dtype=torch.float32, device=dev)
+    os_ = torch.zeros((Cn, B, K), dtype=torch.float32, device=dev)
+    ol = torch.zeros((Cn, B, K), dtype=torch.int32, device=dev)
+    oc = torch.zeros((Cn, B), dtype=torch.int32, device=dev)
+    check(lib().ql_voxelhead_class_split(_ptr(boxes.contiguous()), bd, _ptr(scores.contiguous()), _ptr(labels.contiguous()), _ptr(ious.contiguous()),
+                                         _ptr(count), B, K, Cn, _ptr(rectifier.float().contiguous()), _ptr(ob), _ptr(os_), _ptr(ol), _ptr(oc),
+                                         _stream()), "ql_voxelhead_class_split")
+    return ob, os_, ol, oc
+
+
 def nms_rotated(boxes: torch.Tensor, scores: Optional[torch.Tensor], labels: Optional[torch.Tensor], counts: Optional[torch.Tensor],
                 thresh: float, pre_max: int, post_max: int, label_offset: int = 0, box_dim: Optional[int] = None, return_iou: bool = False,
                 workspace: Optional[torch.Tensor] = None):
