@@ -175,6 +175,98 @@ __global__ void __launch_bounds__(256) k_unfold_quantize(const void* __restrict_
     }
 }
 
+// k_unfold_absmax for 3 x 3 kernels in ONE pass over the plane: a pixel updates, in registers, the maxima of the (ky, kx) columns
+// whose windows contain it (the general kernel above re-reads the plane once per kernel position: 282 us per BEV-backbone layer)
+__global__ void __launch_bounds__(256) k_unfold_absmax_3x3(const void* __restrict__ x, int dtype, UnfoldGeom g, float* __restrict__ absmax) {
+    __shared__ uint32_t s_m[9];
+    if (threadIdx.x < 9) s_m[threadIdx.x] = 0u;
+    __syncthreads();
+    const int c = blockIdx.x, b = blockIdx.y;
+    const int64_t plane = ((int64_t)b * g.C + c) * g.H * g.W;
+    float m[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) m[k] = 0.f;
+    for (int i = threadIdx.x; i < g.H * g.W; i += blockDim.x) {
+        const int y = i / g.W, xx = i - y * g.W;
+        const float v = fabsf(ld_in(x, dtype, plane + i));
+        bool vy[3], vx[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int ty = y + g.ph - k * g.dh, tx = xx + g.pw - k * g.dw;       // oy * sh, ox * sw of the window that sees this pixel at k
+            vy[k] = ty >= 0 && ty % g.sh == 0 && ty / g.sh < g.Ho;
+            vx[k] = tx >= 0 && tx % g.sw == 0 && tx / g.sw < g.Wo;
+        }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+                if (vy[ky] && vx[kx]) m[ky * 3 + kx] = fmaxf(m[ky * 3 + kx], v);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float w = ql_warp_max(m[k]);
+        if ((threadIdx.x & 31) == 0 && w > 0.f) atomicMax(&s_m[k], __float_as_uint(w));
+    }
+    __syncthreads();
+    if (threadIdx.x < 9 && s_m[threadIdx.x]) atomicMax(reinterpret_cast<unsigned int*>(absmax) + c * 9 + threadIdx.x, s_m[threadIdx.x]);
+}
+
+// k_unfold_quantize, tiled (C % 16 == 0, no padding columns): one CTA = 32 consecutive output pixels of one output row, all columns in
+// groups of 16 channels.  The group's input patch is staged in shared memory with loads that are contiguous along x; every thread then
+// produces 16 consecutive codes of one pixel's row (one 16-byte store; a pixel's 16 * kh * kw bytes of the group are contiguous).  The
+// element-per-thread kernel above reads a different channel plane with every lane and stores single bytes: 1.02 ms per BEV-backbone layer.
+constexpr int kUqPix = 32, kUqCg = 16;
+__global__ void __launch_bounds__(256) k_unfold_quantize_tiled(const void* __restrict__ x, int dtype, UnfoldGeom g, const float* __restrict__ smooth,
+                                                               const float* __restrict__ scales, float bound, int col_stride,
+                                                               int8_t* __restrict__ out) {
+    extern __shared__ float s_uq[];
+    const int K = g.kh * g.kw, GK = kUqCg * K, SEG = GK / 16;
+    const int Wp = (kUqPix - 1) * g.sw + (g.kw - 1) * g.dw + 1;
+    float* s_patch = s_uq;                                   // [16][kh][Wp]
+    float* s_smooth = s_patch + kUqCg * g.kh * Wp;           // [GK]
+    int* s_off = reinterpret_cast<int*>(s_smooth + GK);      // [GK]: patch offset of column (c_local, ky, kx) for pixel 0
+    const int tiles_x = (g.Wo + kUqPix - 1) / kUqPix;
+    const int tx = blockIdx.x % tiles_x, oy = (blockIdx.x / tiles_x) % g.Ho, b = blockIdx.x / (tiles_x * g.Ho);
+    const int ox0 = tx * kUqPix;
+    const float qs = scales[0];
+    for (int i = threadIdx.x; i < GK; i += blockDim.x) {
+        const int cl = i / K, k = i - cl * K, ky = k / g.kw, kx = k - ky * g.kw;
+        s_off[i] = (cl * g.kh + ky) * Wp + kx * g.dw;
+    }
+    const int64_t m0 = ((int64_t)b * g.Ho + oy) * g.Wo + ox0;
+    const int x_start = ox0 * g.sw - g.pw;
+    for (int c0 = 0; c0 < g.C; c0 += kUqCg) {
+        __syncthreads();                                     // the previous group's readers are done (and s_off is visible)
+        for (int i = threadIdx.x; i < kUqCg * g.kh * Wp; i += blockDim.x) {
+            const int xi = i % Wp, r = i / Wp, ky = r % g.kh, cl = r / g.kh;
+            const int y = oy * g.sh - g.ph + ky * g.dh, xg = x_start + xi;
+            float v = 0.f;
+            if (y >= 0 && y < g.H && xg >= 0 && xg < g.W) v = ld_in(x, dtype, (((int64_t)b * g.C + c0 + cl) * g.H + y) * g.W + xg);
+            s_patch[i] = v;
+        }
+        for (int i = threadIdx.x; i < GK; i += blockDim.x) s_smooth[i] = smooth[c0 * K + i];
+        __syncthreads();
+        for (int item = threadIdx.x; item < kUqPix * SEG; item += blockDim.x) {
+            const int p = item / SEG, j = item - p * SEG;
+            if (ox0 + p >= g.Wo) continue;
+            uint32_t w4[4];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                uint32_t word = 0u;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int cl = 16 * j + 4 * q4 + e;
+                    const float v = __fdiv_rn(s_patch[s_off[cl] + p * g.sw], s_smooth[cl]);
+                    const float q = fminf(fmaxf(rintf(__fmul_rn(v, qs)), -bound), bound);
+                    word |= ((uint32_t)(uint8_t)(int8_t)(int)q) << (8 * e);
+                }
+                w4[q4] = word;
+            }
+            *reinterpret_cast<uint4*>(out + (m0 + p) * col_stride + (int64_t)c0 * K + 16 * j) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        }
+    }
+}
+
 bool unfold_geom(int32_t B, int32_t C, int32_t H, int32_t W, const int32_t* k, const int32_t* s, const int32_t* p, const int32_t* d, UnfoldGeom& g) {
     if (!k || !s || !p || !d || B <= 0 || C <= 0 || H <= 0 || W <= 0) return false;
     g = UnfoldGeom{B, C, H, W, k[0], k[1], s[0], s[1], p[0], p[1], d[0], d[1], 0, 0};
@@ -192,7 +284,10 @@ extern "C" int ql_unfold_absmax(const void* x, int32_t dtype, int32_t B, int32_t
     UnfoldGeom g;
     if (!x || !absmax_cols || (dtype != QL_F16 && dtype != QL_F32) || !unfold_geom(B, C, H, W, kernel_hw, stride_hw, pad_hw, dil_hw, g))
         return QL_ERR_INVALID;
-    k_unfold_absmax<<<dim3((unsigned)C, (unsigned)B), 256, (size_t)g.kh * g.kw * 4, (cudaStream_t)stream_>>>(x, dtype, g, absmax_cols);
+    if (g.kh == 3 && g.kw == 3)
+        k_unfold_absmax_3x3<<<dim3((unsigned)C, (unsigned)B), 256, 0, (cudaStream_t)stream_>>>(x, dtype, g, absmax_cols);
+    else
+        k_unfold_absmax<<<dim3((unsigned)C, (unsigned)B), 256, (size_t)g.kh * g.kw * 4, (cudaStream_t)stream_>>>(x, dtype, g, absmax_cols);
     QL_CUDA_CHECK_LAST();
     return QL_OK;
 }
@@ -210,6 +305,16 @@ extern "C" int ql_unfold_quantize(const void* x, int32_t dtype, int32_t B, int32
     const float bound = (float)((1 << (bits - 1)) - 1);
     cudaStream_t st = (cudaStream_t)stream_;
     k_unfold_scales<<<1, 256, 0, st>>>(absmax_cols, smooth_cols, n_cols, bound, scales_out);
+    {
+        const int K = g.kh * g.kw, Wp = (kUqPix - 1) * g.sw + (g.kw - 1) * g.dw + 1;
+        const size_t smem = ((size_t)kUqCg * g.kh * Wp + 2 * (size_t)kUqCg * K) * 4;
+        const int64_t ctas = (int64_t)g.B * g.Ho * ((g.Wo + kUqPix - 1) / kUqPix);
+        if (C % kUqCg == 0 && col_stride == n_cols && smem <= 48 * 1024 && ctas < 2147483647LL && ((uintptr_t)out & 15) == 0) {
+            k_unfold_quantize_tiled<<<(unsigned)ctas, 256, smem, st>>>(x, dtype, g, smooth_cols, scales_out, bound, col_stride, out);
+            QL_CUDA_CHECK_LAST();
+            return QL_OK;
+        }
+    }
     const int64_t total = (int64_t)g.B * g.Ho * g.Wo * col_stride;
     int64_t blocks = (total + 255) / 256;
     if (blocks > 32 * ql_num_sms()) blocks = 32 * ql_num_sms();

@@ -15,6 +15,7 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
+import gc
 import os
 
 import numpy as np
@@ -608,8 +609,18 @@ class BackboneEngine:
             fn()                                                  # warm-up (first-use attribute setup) outside capture
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                fn()
+            # no garbage collection while the stream is capturing: a collected engine of an earlier call frees pinned host buffers and
+            # CUDA graphs, and the allocator's event bookkeeping for them is not capturable (seen once as
+            # cudaErrorStreamCaptureInvalidated in the plugin tests, where engines of several backbones die in one process)
+            gc_was_on = gc.isenabled()
+            gc.collect()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g):
+                    fn()
+            finally:
+                if gc_was_on:
+                    gc.enable()
             self._graph = (fn.__func__, g)
         self._graph[1].replay()
 

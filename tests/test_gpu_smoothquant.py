@@ -81,6 +81,25 @@ def test_sq_wrappers_on_shapes_the_shipped_file_cannot_run():
         assert rel(y, ref) <= TOL, (type(q).__name__, rel(y, ref))
 
 
+def test_sq_conv2d_channel_counts_off_the_tiled_path():
+    """24 input channels (not a multiple of 16: padded columns, the element-per-thread unfold kernels) and a 5 x 5 kernel (the general
+    abs-max kernel) against the oracle"""
+    import qlidar
+    g = torch.Generator().manual_seed(9)
+    for cin, k, s_, p_ in ((24, 3, 1, 1), (32, 5, 2, 2)):
+        x = torch.randn((2, cin, 14, 11), generator=g)
+        x[:, 3] *= 9.0
+        conv = torch.nn.Conv2d(cin, 16, k, stride=s_, padding=p_)
+        with torch.no_grad():
+            conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * 0.1)
+            conv.bias.copy_(torch.randn(conv.bias.shape, generator=g) * 0.1)
+        ref = O.sq_conv2d(x, conv.weight.detach(), conv.bias.detach(), 0.5, s_, p_)
+        q = qlidar.smoothquant_layer(conv.cuda(), qlidar.SQConv2d, 0.5, 8, 8)
+        with torch.no_grad():
+            y = q(x.cuda())
+        assert rel(y, ref) <= TOL, (cin, k, rel(y, ref))
+
+
 def test_sparse_sqconv2d_stays_sparse_and_matches_the_oracle():
     """quant_voxelnext.SQConv2d(sqsubm2d, subm2d) -- the SparseModule over SQSubM2d + SubMConv2d -- on a sparse 2-D tensor of the
     Waymo BEV grid size (188 x 188 would be the stride-8 map; here the full 1504 x 1504 stage-1 footprint to make the point): no
