@@ -186,9 +186,18 @@ __global__ void __launch_bounds__(256) k_unfold_absmax_3x3(const void* __restric
     float m[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) m[k] = 0.f;
-    for (int i = threadIdx.x; i < g.H * g.W; i += blockDim.x) {
+    // gridDim.z CTAs share a plane (interleaved 1024-pixel blocks); four loads in flight per thread
+    const int hw = g.H * g.W;
+    for (int i0 = blockIdx.z * 1024 + threadIdx.x; i0 < hw; i0 += gridDim.z * 1024) {
+      float v4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v4[u] = i0 + u * 256 < hw ? ld_in(x, dtype, plane + i0 + u * 256) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 256;
+        if (i >= hw) break;
         const int y = i / g.W, xx = i - y * g.W;
-        const float v = fabsf(ld_in(x, dtype, plane + i));
+        const float v = fabsf(v4[u]);
         bool vy[3], vx[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -201,6 +210,7 @@ __global__ void __launch_bounds__(256) k_unfold_absmax_3x3(const void* __restric
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx)
                 if (vy[ky] && vx[kx]) m[ky * 3 + kx] = fmaxf(m[ky * 3 + kx], v);
+      }
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
@@ -285,7 +295,8 @@ extern "C" int ql_unfold_absmax(const void* x, int32_t dtype, int32_t B, int32_t
     if (!x || !absmax_cols || (dtype != QL_F16 && dtype != QL_F32) || !unfold_geom(B, C, H, W, kernel_hw, stride_hw, pad_hw, dil_hw, g))
         return QL_ERR_INVALID;
     if (g.kh == 3 && g.kw == 3)
-        k_unfold_absmax_3x3<<<dim3((unsigned)C, (unsigned)B), 256, 0, (cudaStream_t)stream_>>>(x, dtype, g, absmax_cols);
+        k_unfold_absmax_3x3<<<dim3((unsigned)C, (unsigned)B, (unsigned)((H * W + 4095) / 4096 < 8 ? (H * W + 4095) / 4096 : 8)), 256, 0,
+                              (cudaStream_t)stream_>>>(x, dtype, g, absmax_cols);
     else
         k_unfold_absmax<<<dim3((unsigned)C, (unsigned)B), 256, (size_t)g.kh * g.kw * 4, (cudaStream_t)stream_>>>(x, dtype, g, absmax_cols);
     QL_CUDA_CHECK_LAST();
