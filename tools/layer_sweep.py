@@ -118,7 +118,7 @@ def main():
                 rows.append(dict(N=n, C=C, mode=mode, conv_us=tc, sorted_us=alt[0], grouped_us=alt[1], quant_us=tq, gbs=gbs, tflops=tf))
                 lines.append(f"| {n} | {pairs / n:.1f} | {live_txt} | {C} | {mode} | {tc:.1f} | {alt[0]:.1f} | {alt[1]:.1f} | {tq:.1f} | {gbs:.0f} | {gbs / hbm:.3f} | {tf:.1f} | {tf / tpk:.3f} |")
                 print(lines[-1], flush=True)
-    head = (f"# r01 - SubMConv3d layer sweep (BASELINE config 5), B200\n\n`python tools/layer_sweep.py --iters {args.iters}`; peaks ({src}): HBM {hbm} GB/s, "
+    head = (f"# SubMConv3d layer sweep (BASELINE config 5), B200\n\n`python tools/layer_sweep.py --iters {args.iters}`; peaks ({src}): HBM {hbm} GB/s, "
             f"bf16 {bf16} TFLOP/s (INT8 fraction against 2x that); kernel = `k_spconv_ts`, L2 flushed between iterations, medians.\n"
             "Three tilings of the same sites (bit-identical results): the generator's raster order (hash rulebook), rows renumbered by key (`ql_renumber_by_key`, "
             "what the engine does for stage 1) and key-sorted + grouped by line key (`ql_rulebook_subm_ranked_grouped`); GB/s and TFLOP/s use the best of the three.\n"
