@@ -179,38 +179,44 @@ __global__ void __launch_bounds__(256) k_unfold_quantize(const void* __restrict_
 // whose windows contain it (the general kernel above re-reads the plane once per kernel position: 282 us per BEV-backbone layer)
 __global__ void __launch_bounds__(256) k_unfold_absmax_3x3(const void* __restrict__ x, int dtype, UnfoldGeom g, float* __restrict__ absmax) {
     __shared__ uint32_t s_m[9];
+    extern __shared__ uint8_t s_tab[];                   // [H] which ky see row y, [W] which kx see column x (bit masks)
+    uint8_t* s_vy = s_tab;
+    uint8_t* s_vx = s_tab + g.H;
     if (threadIdx.x < 9) s_m[threadIdx.x] = 0u;
+    for (int i = threadIdx.x; i < g.H + g.W; i += blockDim.x) {
+        const bool is_y = i < g.H;
+        const int pos = is_y ? i : i - g.H;
+        const int pad = is_y ? g.ph : g.pw, dil = is_y ? g.dh : g.dw, st = is_y ? g.sh : g.sw, n_out = is_y ? g.Ho : g.Wo;
+        uint32_t mask = 0u;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int t = pos + pad - k * dil;           // o * stride of the window that sees this row / column at kernel position k
+            if (t >= 0 && t % st == 0 && t / st < n_out) mask |= 1u << k;
+        }
+        s_tab[i] = (uint8_t)mask;
+    }
     __syncthreads();
     const int c = blockIdx.x, b = blockIdx.y;
     const int64_t plane = ((int64_t)b * g.C + c) * g.H * g.W;
     float m[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) m[k] = 0.f;
-    // gridDim.z CTAs share a plane (interleaved 1024-pixel blocks); four loads in flight per thread
-    const int hw = g.H * g.W;
-    for (int i0 = blockIdx.z * 1024 + threadIdx.x; i0 < hw; i0 += gridDim.z * 1024) {
-      float v4[4];
+    // a warp per image row (gridDim.z CTAs share the plane), lanes along x: no division in the loop
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int y = blockIdx.z * 8 + warp; y < g.H; y += gridDim.z * 8) {
+        const uint32_t my = s_vy[y];
+        if (my == 0u) continue;
+        const int64_t row = plane + (int64_t)y * g.W;
+#pragma unroll 2
+        for (int xx = lane; xx < g.W; xx += 32) {
+            const float v = fabsf(ld_in(x, dtype, row + xx));
+            const uint32_t mx = s_vx[xx];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v4[u] = i0 + u * 256 < hw ? ld_in(x, dtype, plane + i0 + u * 256) : 0.f;
+            for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * 256;
-        if (i >= hw) break;
-        const int y = i / g.W, xx = i - y * g.W;
-        const float v = fabsf(v4[u]);
-        bool vy[3], vx[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int ty = y + g.ph - k * g.dh, tx = xx + g.pw - k * g.dw;       // oy * sh, ox * sw of the window that sees this pixel at k
-            vy[k] = ty >= 0 && ty % g.sh == 0 && ty / g.sh < g.Ho;
-            vx[k] = tx >= 0 && tx % g.sw == 0 && tx / g.sw < g.Wo;
+                for (int kx = 0; kx < 3; ++kx)
+                    if (((my >> ky) & 1u) && ((mx >> kx) & 1u)) m[ky * 3 + kx] = fmaxf(m[ky * 3 + kx], v);
         }
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx)
-                if (vy[ky] && vx[kx]) m[ky * 3 + kx] = fmaxf(m[ky * 3 + kx], v);
-      }
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
@@ -294,8 +300,8 @@ extern "C" int ql_unfold_absmax(const void* x, int32_t dtype, int32_t B, int32_t
     UnfoldGeom g;
     if (!x || !absmax_cols || (dtype != QL_F16 && dtype != QL_F32) || !unfold_geom(B, C, H, W, kernel_hw, stride_hw, pad_hw, dil_hw, g))
         return QL_ERR_INVALID;
-    if (g.kh == 3 && g.kw == 3)
-        k_unfold_absmax_3x3<<<dim3((unsigned)C, (unsigned)B, (unsigned)((H * W + 4095) / 4096 < 8 ? (H * W + 4095) / 4096 : 8)), 256, 0,
+    if (g.kh == 3 && g.kw == 3 && H + W <= 40000)
+        k_unfold_absmax_3x3<<<dim3((unsigned)C, (unsigned)B, (unsigned)((H + 23) / 24 < 8 ? (H + 23) / 24 : 8)), 256, (size_t)(H + W),
                               (cudaStream_t)stream_>>>(x, dtype, g, absmax_cols);
     else
         k_unfold_absmax<<<dim3((unsigned)C, (unsigned)B), 256, (size_t)g.kh * g.kw * 4, (cudaStream_t)stream_>>>(x, dtype, g, absmax_cols);

@@ -379,11 +379,16 @@ def bev_merge2d_multi(segments, grid_bhw, n_out_cap: int, out_feats: torch.Tenso
     return out_feats, out_coords, n_out_dev
 
 
-def zero_led_rows(n: int, c: int, dtype=torch.float16, device="cuda") -> torch.Tensor:
+def zero_led_rows(n: int, c: int, dtype=torch.float16, device="cuda", fill: bool = True) -> torch.Tensor:
     """[n, c] zero-initialised rows with one extra all-zero row IN FRONT of row 0 (same allocation): the layout the conv kernel
     gathers from -- rulebook index -1 reads that row (include/qlidar.h, zero-row contract).  The returned view is tagged;
-    spconv_mma takes tagged tensors as they are and copies anything else into such a buffer."""
-    buf = torch.zeros((int(n) + 1, int(c)), dtype=dtype, device=device)
+    spconv_mma takes tagged tensors as they are and copies anything else into such a buffer.  fill=False zeroes only the leading
+    row (for a caller that writes every other row itself)."""
+    if fill:
+        buf = torch.zeros((int(n) + 1, int(c)), dtype=dtype, device=device)
+    else:
+        buf = torch.empty((int(n) + 1, int(c)), dtype=dtype, device=device)
+        buf[0].zero_()
     v = buf[1:]
     v._ql_zero_led = buf                      # keeps the allocation (and the zero row) alive with the view
     return v
@@ -392,7 +397,7 @@ def zero_led_rows(n: int, c: int, dtype=torch.float16, device="cuda") -> torch.T
 def _zero_led(feats: torch.Tensor) -> torch.Tensor:
     if getattr(feats, "_ql_zero_led", None) is not None and feats.is_contiguous():
         return feats
-    v = zero_led_rows(feats.shape[0], feats.shape[1], feats.dtype, feats.device)
+    v = zero_led_rows(feats.shape[0], feats.shape[1], feats.dtype, feats.device, fill=False)
     v.copy_(feats)
     return v
 
@@ -604,6 +609,8 @@ def voxelhead_decode(hm: torch.Tensor, center: torch.Tensor, center_z: torch.Ten
     labels = torch.zeros((B, K), dtype=torch.int32, device=dev)
     out_iou = torch.zeros((B, K), dtype=torch.float32, device=dev) if iou is not None else None
     count = torch.zeros((B,), dtype=torch.int32, device=dev)
+    if N == 0:                                    # an empty sparse tensor: no candidates in any frame
+        return boxes, scores, labels, out_iou, count
     ws_bytes = int(lib().ql_voxelhead_decode_workspace_bytes(B, Cn, N))
     if workspace is None or workspace.numel() < ws_bytes:
         workspace = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)

@@ -132,7 +132,7 @@ class _SQDense(nn.Module):
         Ho = (H + 2 * pad[0] - dil[0] * (kernel[0] - 1) - 1) // stride[0] + 1
         Wo = (W + 2 * pad[1] - dil[1] * (kernel[1] - 1) - 1) // stride[1] + 1
         M = B * Ho * Wo
-        codes = ops.zero_led_rows(M, kp, torch.int8, dev)
+        codes = ops.zero_led_rows(M, kp, torch.int8, dev, fill=False)         # ql_unfold_quantize writes every row (padding columns too)
         scales = torch.empty(2, dtype=torch.float32, device=dev)
         ops.check(lib().ql_unfold_quantize(ops._ptr(x), ops._DT[x.dtype], B, C, H, W, i32(kernel), i32(stride), i32(pad), i32(dil), ops._ptr(absmax),
                                            ops._ptr(smooth), _bits(self._input_quantizer), kp, ops._ptr(codes), ops._ptr(scales), ops._stream()),
