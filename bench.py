@@ -453,6 +453,32 @@ def run_ours(args):
         mine[:, c_enc] = torch.bincount(b_idx, minlength=BATCH).float()
         gathered = shard.gather_frame_results(mine.contiguous(), world * BATCH)[:, c_enc].to(torch.int64).cpu().tolist()   # sites per frame, dataset order
 
+    # ---- ... and REAL padded detections (SURVEY 8(f) rank 1 + 8(e)): every rank runs CenterHead.generate_predicted_boxes on the device
+    #      (top-K 500, decode, rotated NMS) for ITS frames -- head maps are synthetic per FRAME (seeded by the dataset index: there is no
+    #      trained head), so any rank produces the same maps for the same frame --, packs [frames, 500, 10] = boxes(7) | score | label |
+    #      kept count, and one NCCL all-gather merges them into dataset order (replaces common_utils.merge_results_dist's pickle + barriers,
+    #      pcdet/utils/common_utils.py:229-250).  Gate: rank 0 recomputes every frame of the job in one process and requires the gathered
+    #      block to be IDENTICAL (same boxes in the same order, i.e. IoU = 1 >= 0.99).  Every rank always calls the collective with a
+    #      fixed-shape block (zeros if its own post-processing failed), so a failure cannot desynchronise the ranks. ----
+    det_info = None
+    if args.config in (1, 2):
+        det_err = None
+        try:
+            mine_det = frame_detections(my_frames, dev)
+        except Exception as e:
+            det_err = repr(e)[:200]
+            mine_det = torch.zeros((len(my_frames), 500, 10), dtype=torch.float32, device=dev)
+        all_det = shard.gather_frame_results(mine_det.contiguous(), world * BATCH)
+        if rank == 0:
+            try:
+                every = list(range(world * BATCH))
+                ref_det = torch.cat([frame_detections(every[i:i + BATCH], dev) for i in range(0, len(every), BATCH)], 0)
+                det_info = {"shape": list(all_det.shape), "frames": len(every), "gathered_over": "nccl all_gather" if world > 1 else "single process",
+                            "identical_to_one_process_run": bool(torch.equal(all_det, ref_det)),
+                            "kept_per_frame": [int(v) for v in all_det[:, 0, 9].cpu().tolist()], "error": det_err}
+            except Exception as e:
+                det_info = {"error": (det_err or "") + " | " + repr(e)[:200]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -631,6 +657,8 @@ def run_ours(args):
     }
     if gathered is not None:
         line["gathered_sites_per_frame"] = gathered
+    if det_info is not None:
+        line["detections_gather"] = det_info
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -669,6 +697,43 @@ def head_post_leg(dev, batch=4, hw=188, classes=3, iters=30):
                     "the host-side launch overhead of its 4 kernels + output allocations (eager, no graph)",
             "us_per_call_median": round(us[len(us) // 2], 1), "us_per_call_min": round(us[0], 1),
             "candidates_kept_per_frame": [int(v) for v in out[0]["keep_count"].cpu().tolist()], "kernel_launches": 4}
+
+
+_HEAD_POST = {"SCORE_THRESH": 0.1, "POST_CENTER_LIMIT_RANGE": [-75.2, -75.2, -2, 75.2, 75.2, 4], "MAX_OBJ_PER_SAMPLE": 500,
+              "NMS_CONFIG": {"NMS_TYPE": "nms_gpu", "NMS_THRESH": 0.7, "NMS_PRE_MAXSIZE": 4096, "NMS_POST_MAXSIZE": 500}}
+
+
+def frame_head_maps(frame_id: int, hw=188, classes=3):
+    """Synthetic CenterHead outputs of ONE frame, a function of the frame's dataset index only (~250 object-like clusters of peaks)."""
+    g = np.random.default_rng(7000 + int(frame_id))
+    hm = (g.standard_normal((classes, hw, hw)) * 0.7 - 6.0).astype(np.float32)
+    cy, cx = g.integers(2, hw - 2, 250), g.integers(2, hw - 2, 250)
+    cls, dy, dx, val = g.integers(0, classes, 750), g.integers(-1, 2, 750), g.integers(-1, 2, 750), g.uniform(-1.5, 3.0, 750)
+    for k in range(750):
+        hm[cls[k], np.clip(cy[k % 250] + dy[k], 0, hw - 1), np.clip(cx[k % 250] + dx[k], 0, hw - 1)] = val[k]
+    return {"hm": hm, "center": g.random((2, hw, hw), dtype=np.float32), "center_z": (g.standard_normal((1, hw, hw)) * 0.5 + 1).astype(np.float32),
+            "dim": (g.standard_normal((3, hw, hw)) * 0.2 + np.log(np.array([4.5, 2.0, 1.6]))[:, None, None]).astype(np.float32),
+            "rot": g.standard_normal((2, hw, hw)).astype(np.float32)}
+
+
+def frame_detections(frame_ids, dev):
+    """[len(frame_ids), 500, 10] fp32 padded detections of the given dataset frames: boxes (7) | score | label (1-based) | kept count (row 0)."""
+    import qlidar
+    per = [frame_head_maps(f) for f in frame_ids]
+    maps = {k: torch.from_numpy(np.stack([m[k] for m in per])).to(dev) for k in per[0]}
+    pp = qlidar.CenterHeadPostProcessor(["Vehicle", "Pedestrian", "Cyclist"], [["Vehicle", "Pedestrian", "Cyclist"]], [-75.2, -75.2, -2.0, 75.2, 75.2, 4.0],
+                                        [0.1, 0.1, 0.15], 8, _HEAD_POST, device=dev)
+    o = pp.generate_predicted_boxes(len(frame_ids), [maps], lazy=True)[0]
+    n = len(frame_ids)
+    block = torch.zeros((n, 500, 10), dtype=torch.float32, device=dev)
+    block[:, :, :7] = o["boxes"][:, :, :7]
+    block[:, :, 7] = o["scores"]
+    block[:, :, 8] = o["labels"].float()
+    block[:, 0, 9] = o["keep_count"].float()
+    # rows past the kept count are whatever the NMS left there: zero them so that the block is a function of the frame alone
+    valid = torch.arange(500, device=dev)[None, :] < o["keep_count"][:, None]
+    block[:, :, :9] = torch.where(valid[:, :, None], block[:, :, :9], torch.zeros_like(block[:, :, :9]))
+    return block
 
 
 def bev_backbone_leg(dev, batch=4, hw=188, iters=5):
