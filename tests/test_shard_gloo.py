@@ -75,3 +75,18 @@ def test_single_process_passthrough():
     from qlidar import shard
     x = torch.arange(12.0).reshape(4, 3)
     assert torch.equal(shard.gather_frame_results(x, 3), x[:3])
+
+
+def test_bench_head_maps_are_a_function_of_the_dataset_frame_index():
+    """bench.py's detections gate compares what the ranks gathered with a one-process recomputation: the synthetic head maps of a
+    frame must depend on its dataset index alone (not on the rank, the batch it is stacked into or the call order)."""
+    import importlib.util
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_for_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    a, b, c = bench.frame_head_maps(5), bench.frame_head_maps(6), bench.frame_head_maps(5)
+    assert set(a) == {"hm", "center", "center_z", "dim", "rot"} and a["hm"].shape == (3, 188, 188)
+    assert all(np.array_equal(a[k], c[k]) for k in a) and not np.array_equal(a["hm"], b["hm"])
+    assert (1.0 / (1.0 + np.exp(-a["hm"])) > 0.1).sum() > 300                 # enough candidates above SCORE_THRESH for the NMS to work on
